@@ -1,0 +1,151 @@
+/* fse_b200.h — C ABI of the B200-native FluentSpeech spec_denoiser + HiFi-GAN hot path.
+ *
+ * The reference (Zain-Jiang/Speech-Editing-Toolkit) has no FFI: its seams for this path are Python
+ * registries.  This header is the boundary a binding would target; the ctypes binding
+ * that ships with this repo is speech_editing_toolkit_b200/_lib.py, and INTEGRATION.md shows the stub a
+ * reference maintainer adds.  Each entry point cites the reference interface it replaces
+ * (file:line relative to the reference tree).
+ *
+ * Conventions
+ *   - return 0 on success, a negative FSE_E* code on failure; fse_last_error() returns the message of the
+ *     last failure on the calling thread.
+ *   - no ownership transfer: every I/O and workspace buffer is allocated by the caller (PyTorch);
+ *     the handle owns only its repacked copy of the weights.
+ *   - all device work is enqueued on the passed cudaStream_t (as void*); no host synchronisation inside,
+ *     except in the fse_*_host convenience calls which take HOST buffers and synchronise before returning.
+ *   - one handle per device; not thread-safe per handle; re-entrant across handles.
+ *   - there is NO CPU fallback: every compute call fails with FSE_ECUDA when no sm_100 device is usable.
+ */
+#ifndef FSE_B200_H
+#define FSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSE_OK 0
+#define FSE_EINVAL (-1)   /* bad argument / shape / missing weight */
+#define FSE_ECUDA (-2)    /* CUDA runtime or driver error (message has the detail) */
+#define FSE_ESTATE (-3)   /* call order violated (e.g. weights not loaded) */
+
+/* arithmetic mode of the contractions */
+#define FSE_MODE_TC_BF16 0    /* tcgen05 tensor cores, bf16 operands, fp32 accumulate (default, the product) */
+#define FSE_MODE_SIMT_F32 1   /* CUDA cores, fp32 operands: the reference's exact fp32 arithmetic contract */
+#define FSE_MODE_SIMT_BF16 2  /* CUDA cores over the bf16 operands: on-device cross-check of the TC path */
+
+typedef struct fse_denoiser fse_denoiser;
+typedef struct fse_vocoder fse_vocoder;
+
+/* Hyper-parameters of DiffNet (diffnet.py:84-108) as read from egs/spec_denoiser.yaml:76-81,128. */
+typedef struct fse_denoiser_config {
+  int32_t n_mels;                 /* audio_num_mel_bins, 80 */
+  int32_t hidden;                 /* hidden_size (conditioner channels), 192 */
+  int32_t channels;               /* residual_channels, 256 */
+  int32_t layers;                 /* residual_layers, 20 */
+  int32_t dilation_cycle_length;  /* dilation = 2**(layer % cycle), shipped configs: 1 */
+  int32_t mode;                   /* FSE_MODE_* */
+} fse_denoiser_config;
+
+/* A named fp32 tensor in HOST memory (a reference state_dict entry). */
+typedef struct fse_tensor {
+  const char* name;    /* reference state_dict key, e.g. "residual_layers.3.dilated_conv.weight" */
+  const float* data;   /* host pointer, contiguous, fp32 */
+  int64_t numel;
+} fse_tensor;
+
+const char* fse_last_error(void);
+int fse_version(void);
+
+/* --- denoiser -------------------------------------------------------------------------------- */
+
+/* replaces DIFF_DECODERS[hparams['diff_decoder_type']](hparams) -> DiffNet.__init__
+ * (tasks/speech_editing/spec_denoiser.py:13-15, diffnet.py:84-108) */
+int fse_denoiser_create(const fse_denoiser_config* cfg, fse_denoiser** out);
+void fse_denoiser_destroy(fse_denoiser* h);
+
+/* replaces load_ckpt(model, ..., 'model') for the `denoise_fn.*` keys (utils/commons/ckpt_utils.py:26-66):
+ * takes the reference state_dict entries unchanged, repacks them on the device. */
+int fse_denoiser_load_weights(fse_denoiser* h, const fse_tensor* tensors, int32_t n);
+
+/* posterior buffers of GaussianDiffusion.__init__ (spec_denoiser.py:61-69), each of length timesteps+1:
+ * posterior_mean_coef1, posterior_mean_coef2, posterior_log_variance_clipped (host pointers). */
+int fse_denoiser_set_schedule(fse_denoiser* h, int32_t timesteps, const float* coef1, const float* coef2,
+                              const float* logvar_clipped);
+
+/* bytes of device workspace the calls below need for a [B, *, T] batch */
+int64_t fse_denoiser_workspace_bytes(const fse_denoiser* h, int32_t B, int32_t T);
+
+/* replaces DiffNet.forward(spec, diffusion_step, cond) (diffnet.py:110-132).
+ *   x_t   [B, n_mels, T] fp32 device (the reference's spec[:,0])
+ *   cond  [B, T, hidden] fp32 device — the PHYSICAL layout of the reference's `cond`
+ *         (decoder_inp.transpose(1,2) is a view of a [B,T,H] tensor, spec_denoiser.py:167)
+ *   t     [B] int64 device
+ *   x0    [B, n_mels, T] fp32 device (out) */
+int fse_denoise_step(fse_denoiser* h, const float* x_t, const float* cond, const int64_t* t, float* x0,
+                     int32_t B, int32_t T, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* replaces GaussianDiffusion.q_posterior_sample (spec_denoiser.py:95-101):
+ *   x_prev = coef1[t] x0 + coef2[t] x_t + [t != 0] exp(0.5 logvar[t]) noise.
+ * noise may be NULL: normals then come from the in-kernel Philox stream (seed, step). */
+int fse_posterior_step(fse_denoiser* h, const float* x0, const float* x_t, const int64_t* t, const float* noise,
+                       uint64_t seed, uint32_t step, float* x_prev, int32_t B, int32_t T, void* stream);
+
+/* replaces the infer branch of GaussianDiffusion.forward (spec_denoiser.py:177-185): x_S ~ N(0,I), then
+ * p_sample for t = S-1..0 (spec_denoiser.py:103-108), output x[:,0].transpose(1,2).
+ *   cond    [B, T, hidden] fp32 device
+ *   noise   NULL (Philox, keyed by seed) or [(S+1), B, n_mels, T] fp32 device: noise[0] = x_S,
+ *           noise[1+k] = the draw of iteration k (t = S-1-k), incl. the unused draw at t = 0
+ *   ref_mel [B, T, n_mels] and mask [B, T] (0/1) optional (both or neither): when given the output is
+ *           composited mel*mask + ref*(1-mask) (tasks/speech_editing/spec_denoiser.py:53,84)
+ *   mel_out [B, T, n_mels] fp32 device (out)
+ *   x_trace NULL or [S, B, n_mels, T] fp32 device: x after every iteration (tests) */
+int fse_sample(fse_denoiser* h, const float* cond, const float* noise, uint64_t seed, const float* ref_mel,
+               const float* mask, float* mel_out, float* x_trace, int32_t B, int32_t T, void* workspace,
+               int64_t workspace_bytes, void* stream);
+
+/* Host-buffer convenience of fse_sample (what a foreign-language binding calls): copies cond (and the
+ * optional ref/mask/noise) host->device, samples, copies mel_out device->host, synchronises.
+ * All pointers are HOST pointers; the library allocates and frees its own device scratch. */
+int fse_sample_host(fse_denoiser* h, const float* cond, const float* noise, uint64_t seed, const float* ref_mel,
+                    const float* mask, float* mel_out, int32_t B, int32_t T);
+
+/* number of kernels the last fse_denoise_step / fse_sample call on this handle enqueued */
+int64_t fse_denoiser_last_launches(const fse_denoiser* h);
+
+/* --- HiFi-GAN generator ---------------------------------------------------------------------- */
+
+/* The generator hyper-parameters of modules/vocoder/hifigan/hifigan.py:101-124 (config.yaml of the
+ * vocoder checkpoint; not shipped with the reference — HiFi-GAN V1 is assumed by the benchmarks). */
+typedef struct fse_vocoder_config {
+  int32_t n_mels;                    /* 80 */
+  int32_t upsample_initial_channel;  /* 512 */
+  int32_t num_upsamples;             /* <= 8 */
+  int32_t upsample_rates[8];
+  int32_t upsample_kernel_sizes[8];
+  int32_t num_kernels;               /* <= 4 */
+  int32_t resblock_kernel_sizes[4];
+  int32_t resblock_dilations[4][3];  /* ResBlock1: three dilations per block */
+  int32_t mode;                      /* FSE_MODE_* */
+} fse_vocoder_config;
+
+/* replaces HifiGanGenerator.__init__ (hifigan.py:101-124) */
+int fse_vocoder_create(const fse_vocoder_config* cfg, fse_vocoder** out);
+void fse_vocoder_destroy(fse_vocoder* h);
+/* replaces load_ckpt(model, base_dir, 'model_gen') (tasks/tts/vocoder_infer/hifigan.py:13-21): takes the
+ * reference state_dict (weight_g / weight_v pairs, or folded .weight) and folds weight-norm once. */
+int fse_vocoder_load_weights(fse_vocoder* h, const fse_tensor* tensors, int32_t n);
+int64_t fse_vocoder_workspace_bytes(const fse_vocoder* h, int32_t B, int32_t T);
+/* replaces HifiGanGenerator.forward (hifigan.py:126-142) behind BaseTTSInfer.run_vocoder
+ * (inference/tts/base_tts_infer.py:44-47): mel [B, T, n_mels] fp32 device -> wav [B, T*hop] fp32 device */
+int fse_vocoder_forward(fse_vocoder* h, const float* mel, float* wav, int32_t B, int32_t T, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+/* Host-buffer convenience (HifiGAN.spec2wav, tasks/tts/vocoder_infer/hifigan.py:23-31) */
+int fse_vocoder_forward_host(fse_vocoder* h, const float* mel, float* wav, int32_t B, int32_t T);
+int64_t fse_vocoder_last_launches(const fse_vocoder* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSE_B200_H */

@@ -1,0 +1,114 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (imported from /root/reference) on
+seeded synthetic weights / inputs.  Runs only in the build container (the reference cannot travel);
+the fixtures it writes are committed.  Usage:  python oracle/make_golden.py
+
+The reference has no tests or golden vectors of its own, so these fixtures — outputs of
+the reference's own code — are what pins both the numpy oracle and the CUDA path.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import refshim  # noqa: E402
+from speech_editing_toolkit_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+SEED = 1234
+
+
+def to_torch(sd):
+    return {k: torch.from_numpy(v.copy()) for k, v in sd.items()}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(SEED)
+    torch.set_num_threads(8)
+    hp = refshim.install("egs/spec_denoiser.yaml", overrides="timesteps=10")
+    from modules.speech_editing.spec_denoiser.diffnet import DiffNet
+    from modules.speech_editing.spec_denoiser import spec_denoiser as sdmod
+    from modules.vocoder.hifigan.hifigan import HifiGanGenerator
+
+    # ---- DiffNet.forward, one step, ragged T and two different t ------------------------------
+    sd = synth.denoiser_state_dict(SEED)
+    net = DiffNet(hp["audio_num_mel_bins"]).eval()
+    net.load_state_dict(to_torch(sd), strict=True)
+    B, T = 2, 80
+    rs = np.random.RandomState(SEED + 1)
+    x = rs.standard_normal((B, 80, T)).astype(np.float32)
+    cond = synth.synthetic_cond(SEED, B, T)
+    t = np.array([7, 0], dtype=np.int64)
+    with torch.no_grad():
+        # the reference passes cond as the transposed VIEW of a [B,T,H] tensor (spec_denoiser.py:167)
+        x0 = net(torch.from_numpy(x)[:, None], torch.from_numpy(t), torch.from_numpy(cond).transpose(1, 2))[:, 0].numpy()
+    np.savez_compressed(os.path.join(OUT, "diffnet_step.npz"), seed=SEED, B=B, T=T, x=x, t=t, x0=x0)
+    print("diffnet_step", x0.shape, float(np.abs(x0).mean()))
+
+    # ---- config C1: B=1, T=256, S=10 sampling through the reference's own p_sample -----------------
+    S, B, T = 10, 1, 256
+    model = sdmod.GaussianDiffusion(phone_encoder=list(range(80)), out_dims=80, denoise_fn=net, timesteps=S,
+                                    time_scale=hp["timescale"], loss_type=hp["diff_loss_type"],
+                                    spec_min=hp["spec_min"], spec_max=hp["spec_max"]).eval()
+    cond = synth.synthetic_cond(SEED + 1, B, T)
+    noise = synth.synthetic_noise(SEED + 1, S, B, T)
+    draws = iter(torch.from_numpy(noise[1:]))
+    orig = sdmod.noise_like
+    sdmod.noise_like = lambda shape, device, repeat=False: next(draws)[:, None]     # inject the pre-drawn normals
+    try:
+        xt = torch.from_numpy(noise[0])[:, None]
+        cond_t = torch.from_numpy(cond).transpose(1, 2)
+        trace = []
+        for i in reversed(range(S)):                                                # spec_denoiser.py:181-182
+            xt = model.p_sample(xt, torch.full((B,), i, dtype=torch.long), cond_t)
+            trace.append(xt[:, 0].numpy().copy())
+        mel = xt[:, 0].transpose(1, 2).numpy().copy()                               # :183
+    finally:
+        sdmod.noise_like = orig
+    np.savez_compressed(os.path.join(OUT, "sample_c1.npz"), seed=SEED + 1, B=B, T=T, S=S, mel_out=mel,
+                        x_after_first=trace[0], x_after_fifth=trace[4])
+    print("sample_c1", mel.shape, float(np.abs(mel).mean()))
+    sched = {k: getattr(model, k).numpy() for k in ("betas", "alphas_cumprod", "posterior_mean_coef1", "posterior_mean_coef2",
+                                                    "posterior_log_variance_clipped", "posterior_variance")}
+    kat = {f"sched10_{k}": v for k, v in sched.items()}
+    for S2 in (4, 8, 100):
+        m2 = sdmod.GaussianDiffusion(phone_encoder=list(range(80)), out_dims=80, denoise_fn=net, timesteps=S2, time_scale=1,
+                                     loss_type="l1", spec_min=[], spec_max=[])
+        for k in ("betas", "posterior_mean_coef1", "posterior_mean_coef2", "posterior_log_variance_clipped"):
+            kat[f"sched{S2}_{k}"] = getattr(m2, k).numpy()
+
+    # ---- integer / index known answers, from the reference functions ----------
+    from utils.audio.pitch.utils import f0_to_coarse
+    from utils.audio.align import mel2token_to_dur
+    from modules.tts.commons.align_ops import expand_states
+    f0 = np.array([0, 50, 80, 100, 220, 440, 600, 900, 1200], dtype=np.float32)
+    kat["f0_in"] = f0
+    kat["f0_coarse"] = f0_to_coarse(torch.from_numpy(f0)).numpy()
+    m2t = np.array([[1, 1, 2, 2, 2, 4, 0, 0]], dtype=np.int64)
+    kat["mel2token"] = m2t
+    kat["mel2token_dur"] = mel2token_to_dur(torch.from_numpy(m2t), 5).numpy()
+    hs = np.arange(6, dtype=np.float32).reshape(1, 3, 2)
+    m2p = np.array([[1, 1, 3, 0]], dtype=np.int64)
+    kat["expand_h"], kat["expand_idx"] = hs, m2p
+    kat["expand_out"] = expand_states(torch.from_numpy(hs), torch.from_numpy(m2p)).numpy()
+    np.savez_compressed(os.path.join(OUT, "kat.npz"), **kat)
+    print("kat", sorted(kat)[:4], "...")
+
+    # ---- HiFi-GAN V1 generator ------------------------------------------------------------------
+    from oracle.fluentspeech_oracle import HIFIGAN_V1
+    gen = HifiGanGenerator(dict(HIFIGAN_V1)).eval()
+    hsd = synth.hifigan_state_dict(SEED)
+    gen.load_state_dict(to_torch(hsd), strict=True)
+    B, T = 1, 24
+    mel_in = np.clip(np.random.RandomState(SEED + 2).standard_normal((B, T, 80)) * 1.5 - 3.0, -6, 1.5).astype(np.float32)
+    with torch.no_grad():
+        wav = gen(torch.from_numpy(mel_in).transpose(1, 2)).numpy()          # [B,1,T*256]
+    np.savez_compressed(os.path.join(OUT, "hifigan_v1.npz"), seed=SEED, B=B, T=T, mel=mel_in, wav=wav[:, 0])
+    print("hifigan", wav.shape, float(np.abs(wav).mean()), float(np.abs(wav).max()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,86 @@
+"""ctypes binding of the C ABI declared in include/fse_b200.h.
+
+There is deliberately NO fallback: if libfse_b200.so is missing or a call fails, an exception is
+raised.  (The oracle under oracle/ is test infrastructure and is never imported from here.)
+"""
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+FSE_MODE_TC_BF16 = 0
+FSE_MODE_SIMT_F32 = 1
+FSE_MODE_SIMT_BF16 = 2
+MODES = {"tc_bf16": FSE_MODE_TC_BF16, "simt_f32": FSE_MODE_SIMT_F32, "simt_bf16": FSE_MODE_SIMT_BF16}
+
+
+class FseError(RuntimeError):
+    pass
+
+
+class DenoiserConfig(C.Structure):
+    _fields_ = [("n_mels", C.c_int32), ("hidden", C.c_int32), ("channels", C.c_int32), ("layers", C.c_int32),
+                ("dilation_cycle_length", C.c_int32), ("mode", C.c_int32)]
+
+
+class VocoderConfig(C.Structure):
+    _fields_ = [("n_mels", C.c_int32), ("upsample_initial_channel", C.c_int32), ("num_upsamples", C.c_int32),
+                ("upsample_rates", C.c_int32 * 8), ("upsample_kernel_sizes", C.c_int32 * 8),
+                ("num_kernels", C.c_int32), ("resblock_kernel_sizes", C.c_int32 * 4),
+                ("resblock_dilations", (C.c_int32 * 3) * 4), ("mode", C.c_int32)]
+
+
+class Tensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.POINTER(C.c_float)), ("numel", C.c_int64)]
+
+
+_P = C.c_void_p
+_F = C.POINTER(C.c_float)
+
+# name -> (restype, argtypes); every symbol of include/fse_b200.h
+SIGNATURES = {
+    "fse_last_error": (C.c_char_p, []),
+    "fse_version": (C.c_int, []),
+    "fse_denoiser_create": (C.c_int, [C.POINTER(DenoiserConfig), C.POINTER(_P)]),
+    "fse_denoiser_destroy": (None, [_P]),
+    "fse_denoiser_load_weights": (C.c_int, [_P, C.POINTER(Tensor), C.c_int32]),
+    "fse_denoiser_set_schedule": (C.c_int, [_P, C.c_int32, _F, _F, _F]),
+    "fse_denoiser_workspace_bytes": (C.c_int64, [_P, C.c_int32, C.c_int32]),
+    "fse_denoise_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
+    "fse_posterior_step": (C.c_int, [_P, _P, _P, _P, _P, C.c_uint64, C.c_uint32, _P, C.c_int32, C.c_int32, _P]),
+    "fse_sample": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
+    "fse_sample_host": (C.c_int, [_P, _P, _P, C.c_uint64, _P, _P, _P, C.c_int32, C.c_int32]),
+    "fse_denoiser_last_launches": (C.c_int64, [_P]),
+    "fse_vocoder_create": (C.c_int, [C.POINTER(VocoderConfig), C.POINTER(_P)]),
+    "fse_vocoder_destroy": (None, [_P]),
+    "fse_vocoder_load_weights": (C.c_int, [_P, C.POINTER(Tensor), C.c_int32]),
+    "fse_vocoder_workspace_bytes": (C.c_int64, [_P, C.c_int32, C.c_int32]),
+    "fse_vocoder_forward": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
+    "fse_vocoder_forward_host": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32]),
+    "fse_vocoder_last_launches": (C.c_int64, [_P]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libfse_b200.so (once).  Raises ImportError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(needs nvcc).  There is no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = lib().fse_last_error()
+        raise FseError(f"fse error {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,282 @@
+// Channels-last 1-D convolution as a shifted GEMM, the one compute primitive of this library.
+//
+//   Out[(b,t), n] = sum_{tap, c} A0[b, t + off[tap], c] * W[n, (tap, c)]  +  sum_c A1[b, t, c] * W[n, (ntaps, c)]
+//
+// rows = frames (b,t) of a [B, T, C] channels-last activation, zero outside [0, T) (that IS the
+// conv zero padding), columns = output channels, fp32 accumulation, result handed to an epilogue
+// functor  epi.apply<NV>(b, t, n0, acc[NV])  (NV consecutive columns of one frame).
+//
+// Two back ends behind the same operand layout:
+//   * conv_gemm_tc_kernel  — sm_100a tensor cores: TMA (cp.async.bulk.tensor, 128B/64B swizzle,
+//     out-of-bounds zero fill = conv padding) -> shared memory ring -> tcgen05.mma (bf16 x bf16 -> fp32
+//     in TMEM, M=128 frames, N<=256 channels) -> tcgen05.ld -> epilogue.  Warp-specialised:
+//     warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator, warps 2..5 epilogue.
+//   * conv_gemm_simt_kernel — plain CUDA-core tiled GEMM over fp32 or bf16 operands; the exact-fp32
+//     mode of the library and the on-device cross-check of the tensor-core path.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "ptx_sm100.cuh"
+
+namespace fse {
+
+constexpr int kMaxTaps = 12;
+
+struct ConvGemmParams {
+  int B;       // items
+  int Trows;   // output rows (frames) per item; tiles never straddle items
+  int Tsrc;    // frames per item of the sources (SIMT bounds check; TC relies on TMA OOB fill)
+  int C0, C1;  // channels of source 0 (with taps) and source 1 (single tap, offset 0; 0 = unused)
+  int ntaps;
+  int tap_off[kMaxTaps];
+  int KB;      // k-block width in channels: 64 (128B swizzle) or 32 (64B swizzle)
+  int nkb0;    // k-blocks per tap for source 0 = ceil(C0/KB)
+  int nkb1;    // k-blocks for source 1
+  int N;       // output columns
+  int Kp;      // padded K of the packed weight = (ntaps*nkb0 + nkb1)*KB
+};
+
+// ------------------------------------------------------------------------------------------
+// small vector store helpers
+// ------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void st_vec(float* p, const float* v) {
+  static_assert(NV % 2 == 0, "NV");
+  if constexpr (NV % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i)
+      reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV / 2; ++i) reinterpret_cast<float2*>(p)[i] = make_float2(v[2 * i], v[2 * i + 1]);
+  }
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <int NV>
+__device__ __forceinline__ void st_vec(__nv_bfloat16* p, const float* v) {
+  static_assert(NV % 2 == 0, "NV");
+  if constexpr (NV % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < NV / 8; ++i)
+      reinterpret_cast<uint4*>(p)[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+  } else if constexpr (NV % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i)
+      reinterpret_cast<uint2*>(p)[i] = make_uint2(pack_bf16x2(v[4 * i], v[4 * i + 1]), pack_bf16x2(v[4 * i + 2], v[4 * i + 3]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV / 2; ++i) reinterpret_cast<uint32_t*>(p)[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+  }
+}
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// ------------------------------------------------------------------------------------------
+// CUDA-core back end
+// ------------------------------------------------------------------------------------------
+template <typename TOp, class Epi>
+__global__ void __launch_bounds__(256) conv_gemm_simt_kernel(ConvGemmParams p, const TOp* __restrict__ A0,
+                                                             const TOp* __restrict__ A1, const TOp* __restrict__ W,
+                                                             Epi epi) {
+  __shared__ float As[16][68];
+  __shared__ float Ws[16][68];
+  const int tiles_per_item = (p.Trows + 63) / 64;
+  const int b = blockIdx.x / tiles_per_item;
+  const int t0 = (blockIdx.x % tiles_per_item) * 64;
+  const int n0 = blockIdx.y * 64;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int sub = p.KB / 16;
+  const int nk16 = p.Kp / 16;
+  const int nkb_src0 = p.ntaps * p.nkb0;
+  for (int j = 0; j < nk16; ++j) {
+    const int kb = j / sub;
+    const TOp* src;
+    int C, cb, off;
+    if (kb < nkb_src0) {
+      const int tap = kb / p.nkb0;
+      src = A0; C = p.C0; off = p.tap_off[tap];
+      cb = (kb % p.nkb0) * p.KB + (j % sub) * 16;
+    } else {
+      src = A1; C = p.C1; off = 0;
+      cb = (kb - nkb_src0) * p.KB + (j % sub) * 16;
+    }
+    {
+      const int tt = t0 + lrow + off;
+      const bool ok = (tt >= 0) && (tt < p.Tsrc);
+      const TOp* rp = src + (static_cast<size_t>(b) * p.Tsrc + (ok ? tt : 0)) * C;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int ch = cb + lk + q;
+        As[lk + q][lrow] = (ok && ch < C) ? to_f32(rp[ch]) : 0.f;
+      }
+      const int n = n0 + lrow;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        Ws[lk + q][lrow] = (n < p.N) ? to_f32(W[static_cast<size_t>(n) * p.Kp + j * 16 + lk + q]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 w = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) acc[i][jj] = fmaf(av[i], wv[jj], acc[i][jj]);
+    }
+    __syncthreads();
+  }
+  const int n = n0 + tx * 4;
+  if (n < p.N) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int t = t0 + ty * 4 + i;
+      if (t < p.Trows) epi.template apply<4>(b, t, n, acc[i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// tcgen05 back end
+// ------------------------------------------------------------------------------------------
+constexpr int kTcThreads = 192;   // warp 0: TMA, warp 1: MMA/TMEM, warps 2-5: epilogue
+constexpr int kTileM = 128;       // frames per tile = TMEM lanes
+
+__host__ __device__ inline int tc_b_stage_bytes(int BN, int KB) { return ((BN * KB * 2 + 1023) / 1024) * 1024; }
+__host__ __device__ inline int tc_a_stage_bytes(int KB) { return kTileM * KB * 2; }
+__host__ inline int tc_tmem_cols(int BN) { int c = 32; while (c < BN) c <<= 1; return c; }
+__host__ inline size_t tc_smem_bytes(int BN, int KB, int stages) {
+  return 1024 + static_cast<size_t>(stages) * (tc_a_stage_bytes(KB) + tc_b_stage_bytes(BN, KB)) + 8 * (2 * stages + 1) + 16;
+}
+
+template <int KB, int CH, class Epi>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                    const __grid_constant__ CUtensorMap mapW, ConvGemmParams p, int BN, int stages, Epi epi) {
+  static_assert(KB == 64 || KB == 32, "k-block");
+  static_assert(CH == 32 || CH == 16, "epilogue chunk");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int A_BYTES = tc_a_stage_bytes(KB);
+  const int B_BYTES = tc_b_stage_bytes(BN, KB);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + stages * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * B_BYTES);
+  uint64_t* empty = full + stages;
+  uint64_t* tmem_full = empty + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int tiles_per_item = (p.Trows + kTileM - 1) / kTileM;
+  const int b = blockIdx.x / tiles_per_item;
+  const int t0 = (blockIdx.x % tiles_per_item) * kTileM;
+  const int n0 = blockIdx.y * BN;
+  const int nkb_src0 = p.ntaps * p.nkb0;
+  const int nkb = nkb_src0 + p.nkb1;
+  uint32_t ncols = 32;
+  while (static_cast<int>(ncols) < BN) ncols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&mapA0);
+    if (p.nkb1 > 0) ptx::prefetch_tensormap(&mapA1);
+    ptx::prefetch_tensormap(&mapW);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < stages; ++s) {
+        ptx::mbar_init(&full[s], 1);
+        ptx::mbar_init(&empty[s], 1);
+      }
+      ptx::mbar_init(tmem_full, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, ncols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx_bytes = static_cast<uint32_t>(A_BYTES + BN * KB * 2);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        ptx::mbar_wait(&empty[s], ph ^ 1u);
+        ptx::mbar_arrive_expect_tx(&full[s], tx_bytes);
+        if (kb < nkb_src0) {
+          const int tap = kb / p.nkb0;
+          ptx::tma_load_3d(sA + s * A_BYTES, &mapA0, &full[s], (kb % p.nkb0) * KB, t0 + p.tap_off[tap], b);
+        } else {
+          ptx::tma_load_3d(sA + s * A_BYTES, &mapA1, &full[s], (kb - nkb_src0) * KB, t0, b);
+        }
+        ptx::tma_load_2d(sB + s * B_BYTES, &mapW, &full[s], kb * KB, n0);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(kTileM, BN);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % stages;
+      const uint32_t ph = (kb / stages) & 1;
+      ptx::mbar_wait(&full[s], ph);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = ptx::smem_u32(sA + s * A_BYTES);
+        const uint32_t b_addr = ptx::smem_u32(sB + s * B_BYTES);
+        const uint64_t da = (KB == 64) ? ptx::make_desc_k_sw128(a_addr) : ptx::make_desc_k_sw64(a_addr);
+        const uint64_t db = (KB == 64) ? ptx::make_desc_k_sw128(b_addr) : ptx::make_desc_k_sw64(b_addr);
+#pragma unroll
+        for (int k = 0; k < KB / 16; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the addr>>4 field
+          ptx::mma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        ptx::mma_commit(&empty[s]);
+        if (kb == nkb - 1) ptx::mma_commit(tmem_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int t = t0 + q * 32 + lane;
+    ptx::mbar_wait(tmem_full, 0);
+    ptx::tc_fence_after();
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int nchunks = BN / CH;
+    for (int c = 0; c < nchunks; ++c) {
+      uint32_t r[CH];
+      if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(lane_base + c * CH, r);
+      else ptx::tmem_ld_32x32b_x16(lane_base + c * CH, r);
+      ptx::tmem_wait_ld();
+      if (t < p.Trows) {
+        float v[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
+        epi.template apply<CH>(b, t, n0 + c * CH, v);
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, ncols);
+  }
+}
+
+}  // namespace fse

@@ -1,0 +1,640 @@
+// FluentSpeech spec_denoiser hot path on sm_100a: DiffNet step, posterior sample, sampling loop.
+// Reference semantics: modules/speech_editing/spec_denoiser/{diffnet.py:34-132, spec_denoiser.py:86-185}.
+#include <cmath>
+#include <memory>
+
+#include "epilogues.cuh"
+#include "fse_common.cuh"
+
+namespace fse {
+
+// ------------------------------------------------------------------ small kernels
+// t -> sinusoidal embedding -> Linear -> Mish -> Linear   (diffnet.py:34-46, 97-101, 121-122)
+__global__ void __launch_bounds__(256) temb_kernel(const float* __restrict__ tvals, const float* __restrict__ W0,
+                                                   const float* __restrict__ b0, const float* __restrict__ W2,
+                                                   const float* __restrict__ b2, float* __restrict__ temb, int C) {
+  extern __shared__ float sh[];          // e[C] + hid[4C]
+  float* e = sh;
+  float* hid = sh + C;
+  const int ti = blockIdx.x;
+  const float t = tvals[ti];
+  const int half = C / 2;
+  const float coef = logf(10000.0f) / static_cast<float>(half - 1);
+  for (int j = threadIdx.x; j < half; j += blockDim.x) {
+    const float f = expf(static_cast<float>(j) * -coef);
+    const float a = t * f;
+    e[j] = sinf(a);
+    e[j + half] = cosf(a);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 4 * C; o += blockDim.x) {
+    const float* w = W0 + static_cast<size_t>(o) * C;
+    float acc = 0.f;
+    for (int k = 0; k < C; ++k) acc = fmaf(w[k], e[k], acc);
+    acc += b0[o];
+    const float sp = acc > 20.f ? acc : log1pf(expf(acc));   // F.softplus, threshold 20
+    hid[o] = acc * tanhf(sp);                                 // Mish (diffnet.py:14-16)
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < C; o += blockDim.x) {
+    const float* w = W2 + static_cast<size_t>(o) * 4 * C;
+    float acc = 0.f;
+    for (int k = 0; k < 4 * C; ++k) acc = fmaf(w[k], hid[k], acc);
+    temb[static_cast<size_t>(ti) * C + o] = acc + b2[o];
+  }
+}
+
+// d[ti][l][:] = W_dp[l] temb[ti] + b_dp[l]     (diffnet.py:69)
+__global__ void __launch_bounds__(256) dproj_kernel(const float* __restrict__ temb, const float* __restrict__ Wdp,
+                                                    const float* __restrict__ bdp, float* __restrict__ d, int C, int L) {
+  extern __shared__ float sh[];
+  const int l = blockIdx.x, ti = blockIdx.y;
+  for (int k = threadIdx.x; k < C; k += blockDim.x) sh[k] = temb[static_cast<size_t>(ti) * C + k];
+  __syncthreads();
+  for (int o = threadIdx.x; o < C; o += blockDim.x) {
+    const float* w = Wdp + (static_cast<size_t>(l) * C + o) * C;
+    float acc = 0.f;
+    for (int k = 0; k < C; ++k) acc = fmaf(w[k], sh[k], acc);
+    d[(static_cast<size_t>(ti) * L + l) * C + o] = acc + bdp[static_cast<size_t>(l) * C + o];
+  }
+}
+
+// dbias[ti][l][sec][n] = Wmac[l][sec][n][:] . d[ti][l][:] (+ bmac[l][n] for sec 0)
+__global__ void __launch_bounds__(256) dbias_kernel(const float* __restrict__ d, const float* __restrict__ Wmac,
+                                                    const float* __restrict__ bmac, float* __restrict__ dbias, int C,
+                                                    int L, int N2) {
+  extern __shared__ float sh[];
+  const int l = blockIdx.x, ti = blockIdx.y;
+  for (int k = threadIdx.x; k < C; k += blockDim.x) sh[k] = d[(static_cast<size_t>(ti) * L + l) * C + k];
+  __syncthreads();
+  const int rows = 3 * N2;
+  for (int r = blockIdx.z * blockDim.x + threadIdx.x; r < rows; r += gridDim.z * blockDim.x) {
+    const float* w = Wmac + (static_cast<size_t>(l) * rows + r) * C;
+    float acc = 0.f;
+    for (int k = 0; k < C; ++k) acc = fmaf(w[k], sh[k], acc);
+    if (r < N2) acc += bmac[static_cast<size_t>(l) * N2 + r];
+    dbias[(static_cast<size_t>(ti) * L + l) * rows + r] = acc;
+  }
+}
+
+__global__ void tvals_from_i64_kernel(const long long* __restrict__ t, float* __restrict__ tv, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tv[i] = static_cast<float>(t[i]);
+}
+__global__ void tvals_desc_kernel(float* __restrict__ tv, int S) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < S) tv[i] = static_cast<float>(S - 1 - i);
+}
+
+// x[B, M, T] fp32 -> operand copy xb[B*T, M] (channels-last)
+template <typename TOp>
+__global__ void __launch_bounds__(256) x_to_rows_kernel(const float* __restrict__ x, TOp* __restrict__ xb, int M, int T) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  TOp* dst = xb + (static_cast<size_t>(b) * T + t) * M;
+  for (int m = 0; m < M; m += 4) {
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = x[(static_cast<size_t>(b) * M + m + q) * T + t];
+    st_vec<4>(dst + m, v);
+  }
+}
+// x_S: copy of noise[0] or Philox normals (step id 0); writes x[B,M,T] and xb[B*T,M]
+template <typename TOp>
+__global__ void __launch_bounds__(256) init_x_kernel(const float* __restrict__ noise0, unsigned long long seed,
+                                                     float* __restrict__ x, TOp* __restrict__ xb, int M, int T) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const size_t row = static_cast<size_t>(b) * T + t;
+  for (int m = 0; m < M; m += 4) {
+    float v[4];
+    if (noise0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = noise0[(static_cast<size_t>(b) * M + m + q) * T + t];
+    } else {
+      philox_normal4(seed, 0u, static_cast<uint32_t>(row), static_cast<uint32_t>(m >> 2), v);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) x[(static_cast<size_t>(b) * M + m + q) * T + t] = v[q];
+    st_vec<4>(xb + row * M + m, v);
+  }
+}
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                          size_t n4) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    st_vec<4>(dst + 4 * i, f);
+  }
+}
+// q_posterior_sample as a stand-alone HBM-bound kernel (spec_denoiser.py:95-101); per-item t.
+__global__ void __launch_bounds__(256) posterior_kernel(const float* __restrict__ x0, const float* __restrict__ x_t,
+                                                        const long long* __restrict__ t, const float* __restrict__ noise,
+                                                        unsigned long long seed, unsigned step,
+                                                        const float* __restrict__ coef1, const float* __restrict__ coef2,
+                                                        const float* __restrict__ logvar, float* __restrict__ x_prev,
+                                                        int M, int T, int S) {
+  const int b = blockIdx.z;
+  const int m4 = blockIdx.y;     // group of 4 mel bins
+  const int tt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tt >= T) return;
+  long long tb = t[b];
+  tb = tb < 0 ? 0 : (tb > S ? S : tb);
+  const float c1 = coef1[tb], c2 = coef2[tb];
+  const float sigma = tb == 0 ? 0.f : expf(0.5f * logvar[tb]);
+  float z[4] = {0.f, 0.f, 0.f, 0.f};
+  if (!noise && sigma != 0.f)
+    philox_normal4(seed, step, static_cast<uint32_t>(static_cast<size_t>(b) * T + tt), static_cast<uint32_t>(m4), z);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int m = m4 * 4 + q;
+    if (m >= M) break;
+    const size_t idx = (static_cast<size_t>(b) * M + m) * T + tt;
+    const float zz = noise ? noise[idx] : z[q];
+    const float mean = __fadd_rn(__fmul_rn(c1, x0[idx]), __fmul_rn(c2, x_t[idx]));
+    x_prev[idx] = __fadd_rn(mean, __fmul_rn(sigma, zz));
+  }
+}
+
+}  // namespace fse
+
+using namespace fse;
+
+// ------------------------------------------------------------------ handle
+struct fse_denoiser {
+  fse_denoiser_config cfg{};
+  bool bf16 = true;
+  bool loaded = false;
+  int device = 0;
+  // packed weights
+  void* W_in = nullptr;  float* b_in = nullptr;  int Kp_in = 0;
+  void* W1 = nullptr;    int Kp1 = 0;             // [L][2C][Kp1]
+  void* W2 = nullptr;    float* b2 = nullptr;     // [L][2C][C], [L][2C]
+  void* W_skip = nullptr; float* b_skip = nullptr;
+  void* W_out = nullptr;  float* b_out = nullptr;
+  float* Wmac = nullptr;  float* bmac = nullptr;   // [L][3][2C][C], [L][2C]
+  float* Wdp = nullptr;   float* bdp = nullptr;    // [L][C][C], [L][C]
+  float* mlp0_w = nullptr; float* mlp0_b = nullptr; float* mlp2_w = nullptr; float* mlp2_b = nullptr;
+  // schedule
+  int S = 0;
+  std::vector<float> coef1, coef2, logvar;
+  float* d_coef1 = nullptr; float* d_coef2 = nullptr; float* d_logvar = nullptr;
+  // tensor maps (tensor-core mode)
+  CUtensorMap mW_in{}, mW_skip{}, mW_out{};
+  std::vector<CUtensorMap> mW1, mW2;
+  struct Plan {
+    const void* ws = nullptr; const void* cond = nullptr; int B = 0, T = 0;
+    CUtensorMap m_xb{}, m_hb{}, m_cond{}, m_u{}, m_sb{}, m_rb{};
+  } plan;
+  long long launches = 0;
+  // scratch owned for the *_host convenience call
+  void* host_ws = nullptr; size_t host_ws_bytes = 0;
+};
+
+namespace {
+
+struct Workspace {
+  float* h; void* hb; void* u; float* S; void* sb; void* rb; void* xb; void* condb;
+  float* xa; float* xbuf2; float* tvals; float* temb; float* d; float* dbias;
+  size_t bytes;
+};
+
+Workspace carve(const fse_denoiser* h, void* base, int B, int T) {
+  const size_t N = static_cast<size_t>(B) * T;
+  const int C = h->cfg.channels, H = h->cfg.hidden, M = h->cfg.n_mels, L = h->cfg.layers;
+  const size_t es = h->bf16 ? 2 : 4;
+  const size_t nT = static_cast<size_t>(std::max(std::max(B, h->S), 1));
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  Workspace w{};
+  uint8_t* p = static_cast<uint8_t*>(base);
+  size_t o;
+  o = take(N * C * 4);  w.h = reinterpret_cast<float*>(p + o);
+  o = take(N * C * es); w.hb = p + o;
+  o = take(N * C * es); w.u = p + o;
+  o = take(N * C * 4);  w.S = reinterpret_cast<float*>(p + o);
+  o = take(N * C * es); w.sb = p + o;
+  o = take(N * C * es); w.rb = p + o;
+  o = take(N * M * es); w.xb = p + o;
+  o = take(h->bf16 ? N * H * 2 : 0); w.condb = p + o;
+  o = take(N * M * 4);  w.xa = reinterpret_cast<float*>(p + o);
+  o = take(N * M * 4);  w.xbuf2 = reinterpret_cast<float*>(p + o);
+  o = take(nT * 4);     w.tvals = reinterpret_cast<float*>(p + o);
+  o = take(nT * C * 4); w.temb = reinterpret_cast<float*>(p + o);
+  o = take(nT * L * C * 4); w.d = reinterpret_cast<float*>(p + o);
+  o = take(nT * L * 3 * 2 * C * 4); w.dbias = reinterpret_cast<float*>(p + o);
+  w.bytes = off;
+  return w;
+}
+
+int check_device() {
+  int dev = 0;
+  FSE_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  FSE_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(FSE_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only (no fallback)", dev, prop.major, prop.minor);
+  return FSE_OK;
+}
+
+int build_plan(fse_denoiser* h, const Workspace& w, const void* ws, const void* cond, int B, int T) {
+  if (h->cfg.mode != FSE_MODE_TC_BF16) return FSE_OK;
+  auto& pl = h->plan;
+  if (pl.ws == ws && pl.B == B && pl.T == T && pl.cond == cond) return FSE_OK;
+  const int C = h->cfg.channels;
+  FSE_TRY(make_map_act(&pl.m_xb, w.xb, h->cfg.n_mels, T, B, 64));
+  FSE_TRY(make_map_act(&pl.m_hb, w.hb, C, T, B, 64));
+  FSE_TRY(make_map_act(&pl.m_cond, w.condb, h->cfg.hidden, T, B, 64));
+  FSE_TRY(make_map_act(&pl.m_u, w.u, C, T, B, 64));
+  FSE_TRY(make_map_act(&pl.m_sb, w.sb, C, T, B, 64));
+  FSE_TRY(make_map_act(&pl.m_rb, w.rb, C, T, B, 64));
+  pl.ws = ws; pl.B = B; pl.T = T; pl.cond = cond;
+  return FSE_OK;
+}
+
+// timestep tables for nT entries of w.tvals: temb -> d -> dbias
+int run_time_tables(fse_denoiser* h, const Workspace& w, int nT, cudaStream_t st) {
+  const int C = h->cfg.channels, L = h->cfg.layers;
+  temb_kernel<<<nT, 256, 5 * C * sizeof(float), st>>>(w.tvals, h->mlp0_w, h->mlp0_b, h->mlp2_w, h->mlp2_b, w.temb, C);
+  FSE_CUDA(cudaGetLastError());
+  dproj_kernel<<<dim3(L, nT), 256, C * sizeof(float), st>>>(w.temb, h->Wdp, h->bdp, w.d, C, L);
+  FSE_CUDA(cudaGetLastError());
+  dbias_kernel<<<dim3(L, nT, 3), 256, C * sizeof(float), st>>>(w.d, h->Wmac, h->bmac, w.dbias, C, L, 2 * C);
+  FSE_CUDA(cudaGetLastError());
+  h->launches += 3;
+  return FSE_OK;
+}
+
+struct OutSpec {
+  int mode; const float* x_t; float* x_out; const float* noise; unsigned long long seed; unsigned step;
+  float c1, c2, sigma; float* mel_out; const float* ref; const float* mask; bool write_xb;
+};
+
+// One DiffNet evaluation (+ fused posterior when out.mode == 1) over the operand copy xb already in the workspace.
+template <typename TOp>
+int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, int T, int tidx_base, int tidx_bstride,
+             const OutSpec& out, cudaStream_t st) {
+  const int C = h->cfg.channels, H = h->cfg.hidden, M = h->cfg.n_mels, L = h->cfg.layers, mode = h->cfg.mode;
+  const size_t es = sizeof(TOp);
+  const int zero = 0;
+  const bool tc = mode == FSE_MODE_TC_BF16;
+  // input projection
+  {
+    ConvGemmParams p = make_params(B, T, T, M, 1, &zero, 0, C, 64);
+    GemmOperands op; op.A0 = w.xb; op.W = h->W_in; op.mA0 = &h->plan.m_xb; op.mW = &h->mW_in; op.BN = 256;
+    if (C % 256 != 0) op.BN = C % 128 == 0 ? 128 : 64;
+    EpiIn<TOp> epi{h->b_in, w.h, static_cast<TOp*>(w.hb), C, T};
+    FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, &h->launches)));
+  }
+  const int bn2 = (2 * C) % 256 == 0 ? 256 : 128;
+  for (int l = 0; l < L; ++l) {
+    const int dil = 1 << (l % h->cfg.dilation_cycle_length);
+    const int offs[3] = {-dil, 0, dil};
+    {
+      ConvGemmParams p = make_params(B, T, T, C, 3, offs, H, 2 * C, 64);
+      GemmOperands op; op.A0 = w.hb; op.A1 = cond_op;
+      op.W = static_cast<const uint8_t*>(h->W1) + static_cast<size_t>(l) * 2 * C * h->Kp1 * es;
+      op.mA0 = &h->plan.m_hb; op.mA1 = &h->plan.m_cond; op.mW = tc ? &h->mW1[l] : nullptr; op.BN = bn2;
+      const float* db = w.dbias + (static_cast<size_t>(tidx_base) * L + l) * 3 * 2 * C;
+      const long long bstride = static_cast<long long>(tidx_bstride) * L * 3 * 2 * C;
+      if (tc) {
+        EpiGate<TOp, true> epi{db, bstride, static_cast<TOp*>(w.u), 2 * C, T, dil};
+        FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, &h->launches)));
+      } else {
+        EpiGate<TOp, false> epi{db, bstride, static_cast<TOp*>(w.u), 2 * C, T, dil};
+        FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, &h->launches)));
+      }
+    }
+    {
+      ConvGemmParams p = make_params(B, T, T, C, 1, &zero, 0, 2 * C, 64);
+      GemmOperands op; op.A0 = w.u;
+      op.W = static_cast<const uint8_t*>(h->W2) + static_cast<size_t>(l) * 2 * C * C * es;
+      op.mA0 = &h->plan.m_u; op.mW = tc ? &h->mW2[l] : nullptr; op.BN = bn2;
+      EpiRes<TOp> epi{h->b2 + static_cast<size_t>(l) * 2 * C, w.h, static_cast<TOp*>(w.hb), w.S, static_cast<TOp*>(w.sb),
+                      C, T, l == 0, l == L - 1, sqrtf(static_cast<float>(L))};
+      FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, &h->launches)));
+    }
+  }
+  {
+    ConvGemmParams p = make_params(B, T, T, C, 1, &zero, 0, C, 64);
+    GemmOperands op; op.A0 = w.sb; op.W = h->W_skip; op.mA0 = &h->plan.m_sb; op.mW = &h->mW_skip;
+    op.BN = C % 256 == 0 ? 256 : (C % 128 == 0 ? 128 : 64);
+    EpiSkip<TOp> epi{h->b_skip, static_cast<TOp*>(w.rb), C, T};
+    FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, &h->launches)));
+  }
+  {
+    ConvGemmParams p = make_params(B, T, T, C, 1, &zero, 0, M, 64);
+    GemmOperands op; op.A0 = w.rb; op.W = h->W_out; op.mA0 = &h->plan.m_rb; op.mW = &h->mW_out; op.BN = M;
+    EpiOut<TOp> epi{h->b_out, M, T, out.mode, out.x_t, out.x_out, out.write_xb ? static_cast<TOp*>(w.xb) : nullptr,
+                    out.noise, out.seed, out.step, out.c1, out.c2, out.sigma, out.mel_out, out.ref, out.mask};
+    FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, &h->launches)));
+  }
+  return FSE_OK;
+}
+
+template <typename TOp>
+int prepare_cond(fse_denoiser* h, const Workspace& w, const float* cond, int B, int T, cudaStream_t st, const void** cond_op) {
+  if constexpr (std::is_same<TOp, float>::value) {
+    *cond_op = cond;
+  } else {
+    const size_t n = static_cast<size_t>(B) * T * h->cfg.hidden;
+    if (n % 4 != 0) return fail(FSE_EINVAL, "B*T*hidden must be a multiple of 4");
+    f32_to_bf16_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, st>>>(cond, static_cast<__nv_bfloat16*>(w.condb), n / 4);
+    FSE_CUDA(cudaGetLastError());
+    ++h->launches;
+    *cond_op = w.condb;
+  }
+  return FSE_OK;
+}
+
+template <typename TOp>
+int denoise_step_impl(fse_denoiser* h, const float* x_t, const float* cond, const int64_t* t, float* x0, int B, int T,
+                      void* ws, cudaStream_t st) {
+  Workspace w = carve(h, ws, B, T);
+  FSE_TRY(build_plan(h, w, ws, cond, B, T));
+  const int M = h->cfg.n_mels;
+  tvals_from_i64_kernel<<<(B + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(t), w.tvals, B);
+  FSE_CUDA(cudaGetLastError());
+  ++h->launches;
+  FSE_TRY(run_time_tables(h, w, B, st));
+  const void* cond_op = nullptr;
+  FSE_TRY(prepare_cond<TOp>(h, w, cond, B, T, st, &cond_op));
+  x_to_rows_kernel<TOp><<<dim3((T + 255) / 256, B), 256, 0, st>>>(x_t, static_cast<TOp*>(w.xb), M, T);
+  FSE_CUDA(cudaGetLastError());
+  ++h->launches;
+  OutSpec out{0, nullptr, x0, nullptr, 0ull, 0u, 0.f, 0.f, 0.f, nullptr, nullptr, nullptr, false};
+  return run_step<TOp>(h, w, cond_op, B, T, 0, 1, out, st);
+}
+
+template <typename TOp>
+int sample_impl(fse_denoiser* h, const float* cond, const float* noise, uint64_t seed, const float* ref, const float* mask,
+                float* mel_out, float* x_trace, int B, int T, void* ws, cudaStream_t st) {
+  Workspace w = carve(h, ws, B, T);
+  FSE_TRY(build_plan(h, w, ws, cond, B, T));
+  const int M = h->cfg.n_mels, S = h->S;
+  const size_t xsz = static_cast<size_t>(B) * M * T;
+  tvals_desc_kernel<<<(S + 255) / 256, 256, 0, st>>>(w.tvals, S);
+  FSE_CUDA(cudaGetLastError());
+  ++h->launches;
+  FSE_TRY(run_time_tables(h, w, S, st));
+  const void* cond_op = nullptr;
+  FSE_TRY(prepare_cond<TOp>(h, w, cond, B, T, st, &cond_op));
+  init_x_kernel<TOp><<<dim3((T + 255) / 256, B), 256, 0, st>>>(noise, seed, w.xa, static_cast<TOp*>(w.xb), M, T);
+  FSE_CUDA(cudaGetLastError());
+  ++h->launches;
+  float* x_cur = w.xa;
+  for (int k = 0; k < S; ++k) {
+    const int t = S - 1 - k;                                   // spec_denoiser.py:181 reversed(range(0, S))
+    float* x_next = x_trace ? x_trace + static_cast<size_t>(k) * xsz : (x_cur == w.xa ? w.xbuf2 : w.xa);
+    OutSpec out{};
+    out.mode = 1; out.x_t = x_cur; out.x_out = x_next;
+    out.noise = noise ? noise + static_cast<size_t>(1 + k) * xsz : nullptr;
+    out.seed = seed; out.step = static_cast<unsigned>(k + 1);
+    out.c1 = h->coef1[t]; out.c2 = h->coef2[t];
+    out.sigma = t == 0 ? 0.f : expf(0.5f * h->logvar[t]);      // nonzero_mask * exp(0.5 logvar) (:100-101)
+    const bool last = k == S - 1;
+    out.mel_out = last ? mel_out : nullptr; out.ref = last ? ref : nullptr; out.mask = last ? mask : nullptr;
+    out.write_xb = !last;
+    FSE_TRY((run_step<TOp>(h, w, cond_op, B, T, k, 0, out, st)));
+    x_cur = x_next;
+  }
+  return FSE_OK;
+}
+
+int validate(const fse_denoiser* h, int B, int T, const void* ws, int64_t ws_bytes) {
+  if (!h) return fail(FSE_EINVAL, "null handle");
+  if (!h->loaded) return fail(FSE_ESTATE, "weights not loaded");
+  if (B <= 0 || T <= 0) return fail(FSE_EINVAL, "B and T must be positive (got %d, %d)", B, T);
+  if (!ws) return fail(FSE_EINVAL, "null workspace");
+  if ((reinterpret_cast<uintptr_t>(ws) & 1023) != 0) return fail(FSE_EINVAL, "workspace must be 1024-byte aligned");
+  const int64_t need = fse_denoiser_workspace_bytes(h, B, T);
+  if (ws_bytes < need) return fail(FSE_EINVAL, "workspace too small: %lld < %lld", (long long)ws_bytes, (long long)need);
+  return FSE_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* fse_last_error(void) { return last_error_ref().c_str(); }
+int fse_version(void) { return 100; }
+
+int fse_denoiser_create(const fse_denoiser_config* cfg, fse_denoiser** out) {
+  if (!cfg || !out) return fail(FSE_EINVAL, "null argument");
+  if (cfg->n_mels <= 0 || cfg->n_mels % 16 != 0) return fail(FSE_EINVAL, "n_mels must be a positive multiple of 16");
+  if (cfg->channels <= 0 || cfg->channels % 64 != 0) return fail(FSE_EINVAL, "channels must be a multiple of 64");
+  if (cfg->hidden <= 0 || cfg->hidden % 8 != 0) return fail(FSE_EINVAL, "hidden must be a multiple of 8");
+  if (cfg->layers <= 0 || cfg->dilation_cycle_length <= 0) return fail(FSE_EINVAL, "layers / dilation_cycle_length must be positive");
+  if (cfg->mode < 0 || cfg->mode > 2) return fail(FSE_EINVAL, "unknown mode %d", cfg->mode);
+  FSE_TRY(check_device());
+  auto* h = new fse_denoiser();
+  h->cfg = *cfg;
+  h->bf16 = cfg->mode != FSE_MODE_SIMT_F32;
+  cudaGetDevice(&h->device);
+  *out = h;
+  return FSE_OK;
+}
+
+void fse_denoiser_destroy(fse_denoiser* h) {
+  if (!h) return;
+  void* ptrs[] = {h->W_in, h->b_in, h->W1, h->W2, h->b2, h->W_skip, h->b_skip, h->W_out, h->b_out, h->Wmac, h->bmac,
+                  h->Wdp, h->bdp, h->mlp0_w, h->mlp0_b, h->mlp2_w, h->mlp2_b, h->d_coef1, h->d_coef2, h->d_logvar, h->host_ws};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete h;
+}
+
+int fse_denoiser_load_weights(fse_denoiser* h, const fse_tensor* tensors, int32_t n) {
+  if (!h || !tensors || n <= 0) return fail(FSE_EINVAL, "null argument");
+  if (h->loaded) return fail(FSE_ESTATE, "weights already loaded");
+  const int C = h->cfg.channels, H = h->cfg.hidden, M = h->cfg.n_mels, L = h->cfg.layers;
+  TensorTable tt(tensors, n);
+  int rc = FSE_OK;
+  auto G = [&](const std::string& name, int64_t numel) { return rc == FSE_OK ? tt.get(name, numel, &rc) : nullptr; };
+
+  // input projection [C, M, 1] -> [C, Kp_in]
+  h->Kp_in = (M + 63) / 64 * 64;
+  {
+    const float* w = G("input_projection.weight", (int64_t)C * M);
+    const float* b = G("input_projection.bias", C);
+    if (rc) return rc;
+    std::vector<float> p(static_cast<size_t>(C) * h->Kp_in, 0.f);
+    for (int o = 0; o < C; ++o) for (int c = 0; c < M; ++c) p[(size_t)o * h->Kp_in + c] = w[(size_t)o * M + c];
+    FSE_TRY(upload_operand(p, h->bf16, &h->W_in));
+    FSE_TRY(upload_f32(std::vector<float>(b, b + C), &h->b_in));
+  }
+  {
+    const float* w0 = G("mlp.0.weight", (int64_t)4 * C * C); const float* b0 = G("mlp.0.bias", 4 * C);
+    const float* w2 = G("mlp.2.weight", (int64_t)4 * C * C); const float* b2 = G("mlp.2.bias", C);
+    if (rc) return rc;
+    FSE_TRY(upload_f32(std::vector<float>(w0, w0 + (size_t)4 * C * C), &h->mlp0_w));
+    FSE_TRY(upload_f32(std::vector<float>(b0, b0 + 4 * C), &h->mlp0_b));
+    FSE_TRY(upload_f32(std::vector<float>(w2, w2 + (size_t)4 * C * C), &h->mlp2_w));
+    FSE_TRY(upload_f32(std::vector<float>(b2, b2 + C), &h->mlp2_b));
+  }
+  const int nkbC = C / 64, nkbH = (H + 63) / 64;
+  h->Kp1 = (3 * nkbC + nkbH) * 64;
+  const int N2 = 2 * C;
+  std::vector<float> W1((size_t)L * N2 * h->Kp1, 0.f), W2((size_t)L * N2 * C), b2v((size_t)L * N2);
+  std::vector<float> Wmac((size_t)L * 3 * N2 * C), bmac((size_t)L * N2), Wdp((size_t)L * C * C), bdp((size_t)L * C);
+  for (int l = 0; l < L; ++l) {
+    const std::string pre = "residual_layers." + std::to_string(l) + ".";
+    const float* wdc = G(pre + "dilated_conv.weight", (int64_t)N2 * C * 3);
+    const float* bdc = G(pre + "dilated_conv.bias", N2);
+    const float* wcp = G(pre + "conditioner_projection.weight", (int64_t)N2 * H);
+    const float* bcp = G(pre + "conditioner_projection.bias", N2);
+    const float* wop = G(pre + "output_projection.weight", (int64_t)N2 * C);
+    const float* bop = G(pre + "output_projection.bias", N2);
+    const float* wdp = G(pre + "diffusion_projection.weight", (int64_t)C * C);
+    const float* bd = G(pre + "diffusion_projection.bias", C);
+    if (rc) return rc;
+    for (int np = 0; np < N2; ++np) {
+      const int r = (np & 1) ? C + np / 2 : np / 2;      // interleave: even = gate j, odd = filter j (diffnet.py:76 chunk order)
+      float* row = &W1[((size_t)l * N2 + np) * h->Kp1];
+      float* rm = &Wmac[(((size_t)l * 3 + 0) * N2 + np) * C];
+      float* ra = &Wmac[(((size_t)l * 3 + 1) * N2 + np) * C];
+      float* rcc = &Wmac[(((size_t)l * 3 + 2) * N2 + np) * C];
+      for (int c = 0; c < C; ++c) {
+        const float* k3 = wdc + ((size_t)r * C + c) * 3;
+        for (int j = 0; j < 3; ++j) row[j * nkbC * 64 + c] = k3[j];
+        rm[c] = static_cast<float>(static_cast<double>(k3[0]) + k3[1] + k3[2]);
+        ra[c] = k3[0];
+        rcc[c] = k3[2];
+      }
+      for (int c = 0; c < H; ++c) row[3 * nkbC * 64 + c] = wcp[(size_t)r * H + c];
+      bmac[(size_t)l * N2 + np] = bdc[r] + bcp[r];
+    }
+    memcpy(&W2[(size_t)l * N2 * C], wop, sizeof(float) * N2 * C);
+    memcpy(&b2v[(size_t)l * N2], bop, sizeof(float) * N2);
+    memcpy(&Wdp[(size_t)l * C * C], wdp, sizeof(float) * C * C);
+    memcpy(&bdp[(size_t)l * C], bd, sizeof(float) * C);
+  }
+  FSE_TRY(upload_operand(W1, h->bf16, &h->W1));
+  FSE_TRY(upload_operand(W2, h->bf16, &h->W2));
+  FSE_TRY(upload_f32(b2v, &h->b2));
+  FSE_TRY(upload_f32(Wmac, &h->Wmac));
+  FSE_TRY(upload_f32(bmac, &h->bmac));
+  FSE_TRY(upload_f32(Wdp, &h->Wdp));
+  FSE_TRY(upload_f32(bdp, &h->bdp));
+  {
+    const float* ws = G("skip_projection.weight", (int64_t)C * C); const float* bs = G("skip_projection.bias", C);
+    const float* wo = G("output_projection.weight", (int64_t)M * C); const float* bo = G("output_projection.bias", M);
+    if (rc) return rc;
+    FSE_TRY(upload_operand(std::vector<float>(ws, ws + (size_t)C * C), h->bf16, &h->W_skip));
+    FSE_TRY(upload_f32(std::vector<float>(bs, bs + C), &h->b_skip));
+    FSE_TRY(upload_operand(std::vector<float>(wo, wo + (size_t)M * C), h->bf16, &h->W_out));
+    FSE_TRY(upload_f32(std::vector<float>(bo, bo + M), &h->b_out));
+  }
+  if (h->cfg.mode == FSE_MODE_TC_BF16) {
+    const int bnC = C % 256 == 0 ? 256 : (C % 128 == 0 ? 128 : 64);
+    const int bn2 = N2 % 256 == 0 ? 256 : 128;
+    FSE_TRY(make_map_w(&h->mW_in, h->W_in, h->Kp_in, C, 64, bnC));
+    FSE_TRY(make_map_w(&h->mW_skip, h->W_skip, C, C, 64, bnC));
+    FSE_TRY(make_map_w(&h->mW_out, h->W_out, C, M, 64, M));
+    h->mW1.resize(L); h->mW2.resize(L);
+    for (int l = 0; l < L; ++l) {
+      FSE_TRY(make_map_w(&h->mW1[l], static_cast<uint8_t*>(h->W1) + (size_t)l * N2 * h->Kp1 * 2, h->Kp1, N2, 64, bn2));
+      FSE_TRY(make_map_w(&h->mW2[l], static_cast<uint8_t*>(h->W2) + (size_t)l * N2 * C * 2, C, N2, 64, bn2));
+    }
+  }
+  h->loaded = true;
+  return FSE_OK;
+}
+
+int fse_denoiser_set_schedule(fse_denoiser* h, int32_t timesteps, const float* coef1, const float* coef2, const float* logvar) {
+  if (!h || !coef1 || !coef2 || !logvar || timesteps <= 0) return fail(FSE_EINVAL, "bad schedule argument");
+  h->S = timesteps;
+  h->coef1.assign(coef1, coef1 + timesteps + 1);
+  h->coef2.assign(coef2, coef2 + timesteps + 1);
+  h->logvar.assign(logvar, logvar + timesteps + 1);
+  for (float** p : {&h->d_coef1, &h->d_coef2, &h->d_logvar}) if (*p) { cudaFree(*p); *p = nullptr; }
+  FSE_TRY(upload_f32(h->coef1, &h->d_coef1));
+  FSE_TRY(upload_f32(h->coef2, &h->d_coef2));
+  FSE_TRY(upload_f32(h->logvar, &h->d_logvar));
+  h->plan.ws = nullptr;
+  return FSE_OK;
+}
+
+int64_t fse_denoiser_workspace_bytes(const fse_denoiser* h, int32_t B, int32_t T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  return static_cast<int64_t>(carve(h, nullptr, B, T).bytes);
+}
+
+int fse_denoise_step(fse_denoiser* h, const float* x_t, const float* cond, const int64_t* t, float* x0, int32_t B, int32_t T,
+                     void* workspace, int64_t workspace_bytes, void* stream) {
+  FSE_TRY(validate(h, B, T, workspace, workspace_bytes));
+  if (!x_t || !cond || !t || !x0) return fail(FSE_EINVAL, "null tensor argument");
+  h->launches = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return h->bf16 ? denoise_step_impl<__nv_bfloat16>(h, x_t, cond, t, x0, B, T, workspace, st)
+                 : denoise_step_impl<float>(h, x_t, cond, t, x0, B, T, workspace, st);
+}
+
+int fse_posterior_step(fse_denoiser* h, const float* x0, const float* x_t, const int64_t* t, const float* noise, uint64_t seed,
+                       uint32_t step, float* x_prev, int32_t B, int32_t T, void* stream) {
+  if (!h || !x0 || !x_t || !t || !x_prev) return fail(FSE_EINVAL, "null argument");
+  if (h->S <= 0) return fail(FSE_ESTATE, "schedule not set");
+  if (B <= 0 || T <= 0) return fail(FSE_EINVAL, "B and T must be positive");
+  const int M = h->cfg.n_mels;
+  posterior_kernel<<<dim3((T + 255) / 256, (M + 3) / 4, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x0, x_t, reinterpret_cast<const long long*>(t), noise, seed, step, h->d_coef1, h->d_coef2, h->d_logvar, x_prev, M, T, h->S);
+  FSE_CUDA(cudaGetLastError());
+  return FSE_OK;
+}
+
+int fse_sample(fse_denoiser* h, const float* cond, const float* noise, uint64_t seed, const float* ref_mel, const float* mask,
+               float* mel_out, float* x_trace, int32_t B, int32_t T, void* workspace, int64_t workspace_bytes, void* stream) {
+  FSE_TRY(validate(h, B, T, workspace, workspace_bytes));
+  if (h->S <= 0) return fail(FSE_ESTATE, "schedule not set");
+  if (!cond || !mel_out) return fail(FSE_EINVAL, "null tensor argument");
+  if ((ref_mel == nullptr) != (mask == nullptr)) return fail(FSE_EINVAL, "ref_mel and mask must be given together");
+  h->launches = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return h->bf16 ? sample_impl<__nv_bfloat16>(h, cond, noise, seed, ref_mel, mask, mel_out, x_trace, B, T, workspace, st)
+                 : sample_impl<float>(h, cond, noise, seed, ref_mel, mask, mel_out, x_trace, B, T, workspace, st);
+}
+
+int fse_sample_host(fse_denoiser* h, const float* cond, const float* noise, uint64_t seed, const float* ref_mel, const float* mask,
+                    float* mel_out, int32_t B, int32_t T) {
+  if (!h || !cond || !mel_out) return fail(FSE_EINVAL, "null argument");
+  if (!h->loaded) return fail(FSE_ESTATE, "weights not loaded");
+  if (h->S <= 0) return fail(FSE_ESTATE, "schedule not set");
+  if (B <= 0 || T <= 0) return fail(FSE_EINVAL, "B and T must be positive");
+  const int M = h->cfg.n_mels, H = h->cfg.hidden, S = h->S;
+  const size_t N = static_cast<size_t>(B) * T;
+  const size_t ws_bytes = static_cast<size_t>(fse_denoiser_workspace_bytes(h, B, T));
+  const size_t cond_b = align_up(N * H * 4, 1024), mel_b = align_up(N * M * 4, 1024), mask_b = align_up(N * 4, 1024);
+  const size_t noise_b = noise ? align_up(static_cast<size_t>(S + 1) * N * M * 4, 1024) : 0;
+  const size_t total = ws_bytes + cond_b + 2 * mel_b + mask_b + noise_b;
+  if (h->host_ws_bytes < total) {
+    if (h->host_ws) cudaFree(h->host_ws);
+    h->host_ws = nullptr; h->host_ws_bytes = 0;
+    FSE_CUDA(cudaMalloc(&h->host_ws, total));
+    h->host_ws_bytes = total;
+  }
+  uint8_t* p = static_cast<uint8_t*>(h->host_ws);
+  void* ws = p; p += ws_bytes;
+  float* d_cond = reinterpret_cast<float*>(p); p += cond_b;
+  float* d_mel = reinterpret_cast<float*>(p); p += mel_b;
+  float* d_ref = reinterpret_cast<float*>(p); p += mel_b;
+  float* d_mask = reinterpret_cast<float*>(p); p += mask_b;
+  float* d_noise = noise ? reinterpret_cast<float*>(p) : nullptr;
+  cudaStream_t st = nullptr;
+  FSE_CUDA(cudaMemcpyAsync(d_cond, cond, N * H * 4, cudaMemcpyHostToDevice, st));
+  if (ref_mel && mask) {
+    FSE_CUDA(cudaMemcpyAsync(d_ref, ref_mel, N * M * 4, cudaMemcpyHostToDevice, st));
+    FSE_CUDA(cudaMemcpyAsync(d_mask, mask, N * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (noise) FSE_CUDA(cudaMemcpyAsync(d_noise, noise, static_cast<size_t>(S + 1) * N * M * 4, cudaMemcpyHostToDevice, st));
+  FSE_TRY(fse_sample(h, d_cond, d_noise, seed, ref_mel ? d_ref : nullptr, mask ? d_mask : nullptr, d_mel, nullptr, B, T, ws,
+                     static_cast<int64_t>(ws_bytes), st));
+  FSE_CUDA(cudaMemcpyAsync(mel_out, d_mel, N * M * 4, cudaMemcpyDeviceToHost, st));
+  FSE_CUDA(cudaStreamSynchronize(st));
+  return FSE_OK;
+}
+
+int64_t fse_denoiser_last_launches(const fse_denoiser* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,250 @@
+// Epilogue functors of the FluentSpeech denoiser step (one per conv_gemm launch).
+// Each gets NV consecutive output columns [n0, n0+NV) of frame (b, t) as fp32 accumulators.
+// TOp is the operand type the NEXT GEMM reads (bf16 for tensor cores, float for the exact mode).
+// Reference semantics: modules/speech_editing/spec_denoiser/diffnet.py:68-81,110-132 and
+// spec_denoiser.py:86-108 (file:line relative to the reference tree).
+#pragma once
+#include "conv_gemm.cuh"
+
+namespace fse {
+
+// ------------------------------------------------------------------ scalar math
+template <bool Fast>
+__device__ __forceinline__ float tanh_f(float x) {
+  if constexpr (Fast) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+  } else {
+    return tanhf(x);
+  }
+}
+template <bool Fast>
+__device__ __forceinline__ float sigmoid_f(float x) {
+  if constexpr (Fast) return fmaf(0.5f, tanh_f<true>(0.5f * x), 0.5f);
+  else return 1.0f / (1.0f + expf(-x));
+}
+
+// Philox4x32-10 (counter-based RNG) + Box-Muller: 4 standard normals per call.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t step, uint32_t row, uint32_t grp, float (&z)[4]) {
+  uint32_t r[4];
+  philox4x32_10(row, grp, step, 0x46534542u, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+  const float u0 = (static_cast<float>(r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u1 = (static_cast<float>(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = (static_cast<float>(r[2] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u3 = (static_cast<float>(r[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+  float s, c;
+  sincosf(6.283185307179586f * u1, &s, &c);
+  z[0] = ra * c; z[1] = ra * s;
+  sincosf(6.283185307179586f * u3, &s, &c);
+  z[2] = rb * c; z[3] = rb * s;
+}
+
+// ------------------------------------------------------------------ input projection
+// h = relu(W_in x + b_in)  (diffnet.py:117-120); writes the fp32 residual stream and its operand copy.
+template <typename TOp>
+struct EpiIn {
+  const float* bias;   // [C]
+  float* h;            // [B*T, C] fp32 residual stream
+  TOp* hb;             // [B*T, C] operand copy
+  int C, T;
+  template <int NV>
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc) const {
+    const size_t o = (static_cast<size_t>(b) * T + t) * C + n0;
+    float v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = fmaxf(acc[i] + __ldg(bias + n0 + i), 0.f);
+    st_vec<NV>(h + o, v);
+    st_vec<NV>(hb + o, v);
+  }
+};
+
+// ------------------------------------------------------------------ gated activation
+// y = conv_k3(h + d) + conv_1x1(cond) (+ biases); u = sigmoid(gate) * tanh(filter)  (diffnet.py:69-77).
+// Columns are interleaved at weight-pack time: column 2j = gate channel j, 2j+1 = filter channel j.
+// The timestep shift d enters as an exact fp32 bias  m - [t<dil] a - [t>=T-dil] c  with
+// m = (W0+W1+W2) d + b_dc + b_cp,  a = W0 d,  c = W2 d  (zero padding is applied AFTER adding d in the
+// reference, so the taps that fall outside [0,T) must not see d).
+template <typename TOp, bool Fast>
+struct EpiGate {
+  const float* dbias;       // [.., 3, N] for this layer; row 0 = m, 1 = a, 2 = c
+  long long bstride;        // elements between consecutive batch items' tables (0: shared by the batch)
+  TOp* u;                   // [B*T, N/2]
+  int N, T, dil;
+  template <int NV>
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc) const {
+    const float* m = dbias + static_cast<size_t>(b) * bstride + n0;
+    const bool e0 = t < dil, e2 = t >= T - dil;
+    float v[NV / 2];
+#pragma unroll
+    for (int j = 0; j < NV / 2; ++j) {
+      float g = acc[2 * j] + __ldg(m + 2 * j);
+      float f = acc[2 * j + 1] + __ldg(m + 2 * j + 1);
+      if (e0) { g -= __ldg(m + N + 2 * j); f -= __ldg(m + N + 2 * j + 1); }
+      if (e2) { g -= __ldg(m + 2 * N + 2 * j); f -= __ldg(m + 2 * N + 2 * j + 1); }
+      v[j] = sigmoid_f<Fast>(g) * tanh_f<Fast>(f);
+    }
+    st_vec<NV / 2>(u + (static_cast<size_t>(b) * T + t) * (N / 2) + n0 / 2, v);
+  }
+};
+
+// ------------------------------------------------------------------ residual / skip
+// o = W_op u + b_op; h <- (h + o[:C]) / sqrt(2); S += o[C:]   (diffnet.py:79-81, :126-128).
+// Last layer writes the operand copy of S / sqrt(L) instead of S.
+template <typename TOp>
+struct EpiRes {
+  const float* bias;   // [2C]
+  float* h;            // [B*T, C]
+  TOp* hb;             // [B*T, C]
+  float* S;            // [B*T, C] running skip sum
+  TOp* sb;             // [B*T, C] operand copy of S/sqrt(L) (written by the last layer)
+  int C, T;
+  int first, last;
+  float sqrt_layers;
+  template <int NV>
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc) const {
+    const size_t row = static_cast<size_t>(b) * T + t;
+    float v[NV];
+    if (n0 < C) {
+      float* hp = h + row * C + n0;
+#pragma unroll
+      for (int i = 0; i < NV / 2; ++i) {
+        const float2 hv = reinterpret_cast<const float2*>(hp)[i];
+        v[2 * i] = __fdiv_rn(hv.x + (acc[2 * i] + __ldg(bias + n0 + 2 * i)), 1.41421356237309504880f);
+        v[2 * i + 1] = __fdiv_rn(hv.y + (acc[2 * i + 1] + __ldg(bias + n0 + 2 * i + 1)), 1.41421356237309504880f);
+      }
+      st_vec<NV>(hp, v);
+      st_vec<NV>(hb + row * C + n0, v);
+    } else {
+      const int c0 = n0 - C;
+      float* sp = S + row * C + c0;
+#pragma unroll
+      for (int i = 0; i < NV / 2; ++i) {
+        float2 sv = make_float2(0.f, 0.f);
+        if (!first) sv = reinterpret_cast<const float2*>(sp)[i];
+        v[2 * i] = sv.x + (acc[2 * i] + __ldg(bias + n0 + 2 * i));
+        v[2 * i + 1] = sv.y + (acc[2 * i + 1] + __ldg(bias + n0 + 2 * i + 1));
+      }
+      if (last) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = __fdiv_rn(v[i], sqrt_layers);
+        st_vec<NV>(sb + row * C + c0, v);
+      } else {
+        st_vec<NV>(sp, v);
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------ skip projection
+// r = relu(W_skip s + b_skip)  (diffnet.py:129-130)
+template <typename TOp>
+struct EpiSkip {
+  const float* bias;
+  TOp* rb;   // [B*T, C]
+  int C, T;
+  template <int NV>
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc) const {
+    float v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = fmaxf(acc[i] + __ldg(bias + n0 + i), 0.f);
+    st_vec<NV>(rb + (static_cast<size_t>(b) * T + t) * C + n0, v);
+  }
+};
+
+// ------------------------------------------------------------------ output projection + posterior sample
+// x0 = W_out r + b_out (diffnet.py:131); mode 0 stores x0 only (the DiffNet.forward contract);
+// mode 1 fuses q_posterior_sample (spec_denoiser.py:95-101):
+//   x_{t-1} = c1 x0 + c2 x_t + sigma z,  sigma = [t != 0] exp(0.5 logvar_clipped[t])
+// written as x_out[B,M,T] (reference layout) + operand copy xb[B*T, M] for the next step, and on the
+// final step mel_out[B,T,M] (= x[:,0].transpose(1,2), spec_denoiser.py:183) optionally composited with
+// the reference mel: mel*mask + ref*(1-mask) (tasks/speech_editing/spec_denoiser.py:53).
+template <typename TOp>
+struct EpiOut {
+  const float* bias;     // [M]
+  int M, T;
+  int mode;
+  const float* x_t;      // [B, M, T]
+  float* x_out;          // [B, M, T]  (mode 0: receives x0)
+  TOp* xb;               // [B*T, M] or null
+  const float* noise;    // [B, M, T] or null -> Philox
+  unsigned long long seed;
+  unsigned step;
+  float c1, c2, sigma;
+  float* mel_out;        // [B, T, M] or null
+  const float* ref;      // [B, T, M] or null
+  const float* mask;     // [B, T] or null
+  template <int NV>
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc) const {
+    if (n0 >= M) return;
+    const size_t row = static_cast<size_t>(b) * T + t;
+    float v[NV];
+#pragma unroll
+    for (int g = 0; g < NV / 4; ++g) {
+      float z[4] = {0.f, 0.f, 0.f, 0.f};
+      if (mode == 1 && noise == nullptr && sigma != 0.f)
+        philox_normal4(seed, step, static_cast<uint32_t>(row), static_cast<uint32_t>((n0 >> 2) + g), z);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = 4 * g + q;
+        const int m = n0 + i;
+        float val = 0.f;
+        if (m < M) {
+          const size_t idx = (static_cast<size_t>(b) * M + m) * T + t;
+          const float x0 = acc[i] + __ldg(bias + m);
+          if (mode == 0) {
+            val = x0;
+          } else {
+            const float zz = noise ? __ldg(noise + idx) : z[q];
+            const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, __ldg(x_t + idx)));
+            val = __fadd_rn(mean, __fmul_rn(sigma, zz));
+          }
+          x_out[idx] = val;
+        }
+        v[i] = val;
+      }
+    }
+    if (n0 + NV <= M) {
+      if (xb) st_vec<NV>(xb + row * M + n0, v);
+      if (mel_out) {
+        if (mask) {
+          const float mk = __ldg(mask + row);
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+            v[i] = __fadd_rn(__fmul_rn(v[i], mk), __fmul_rn(__ldg(ref + row * M + n0 + i), 1.0f - mk));
+        }
+        st_vec<NV>(mel_out + row * M + n0, v);
+      }
+    } else {
+      for (int i = 0; i < NV && n0 + i < M; ++i) {
+        if (xb) {
+          if constexpr (sizeof(TOp) == 2) xb[row * M + n0 + i] = __float2bfloat16_rn(v[i]);
+          else xb[row * M + n0 + i] = v[i];
+        }
+        if (mel_out) {
+          float o = v[i];
+          if (mask) {
+            const float mk = __ldg(mask + row);
+            o = __fadd_rn(__fmul_rn(o, mk), __fmul_rn(__ldg(ref + row * M + n0 + i), 1.0f - mk));
+          }
+          mel_out[row * M + n0 + i] = o;
+        }
+      }
+    }
+  }
+};
+
+}  // namespace fse

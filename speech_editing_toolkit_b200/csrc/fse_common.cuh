@@ -1,0 +1,212 @@
+// Host-side plumbing shared by denoiser.cu and hifigan.cu: error reporting, device buffers,
+// TMA tensor-map encoding and the conv_gemm launcher that picks the back end.
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/fse_b200.h"
+#include "conv_gemm.cuh"
+
+namespace fse {
+
+// ------------------------------------------------------------------ errors
+inline std::string& last_error_ref() {
+  static thread_local std::string msg;
+  return msg;
+}
+inline int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+#define FSE_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return ::fse::fail(FSE_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define FSE_TRY(expr)          \
+  do {                         \
+    int _rc = (expr);          \
+    if (_rc != FSE_OK) return _rc; \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ weights
+struct TensorTable {
+  std::unordered_map<std::string, const fse_tensor*> map;
+  TensorTable(const fse_tensor* t, int n) {
+    for (int i = 0; i < n; ++i) map[t[i].name] = &t[i];
+  }
+  const float* get(const std::string& name, int64_t numel, int* rc) const {
+    auto it = map.find(name);
+    if (it == map.end()) {
+      *rc = fail(FSE_EINVAL, "missing weight tensor '%s'", name.c_str());
+      return nullptr;
+    }
+    if (it->second->numel != numel) {
+      *rc = fail(FSE_EINVAL, "weight '%s' has %lld elements, expected %lld", name.c_str(),
+                 static_cast<long long>(it->second->numel), static_cast<long long>(numel));
+      return nullptr;
+    }
+    return it->second->data;
+  }
+  bool has(const std::string& name) const { return map.count(name) != 0; }
+};
+
+inline uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return static_cast<uint16_t>((u >> 16) | 0x40);
+  u += 0x7FFFu + ((u >> 16) & 1u);
+  return static_cast<uint16_t>(u >> 16);
+}
+
+// Upload a host fp32 matrix as the operand type of the mode (bf16 or fp32).
+inline int upload_operand(const std::vector<float>& host, bool bf16, void** dptr) {
+  if (bf16) {
+    std::vector<uint16_t> tmp(host.size());
+    for (size_t i = 0; i < host.size(); ++i) tmp[i] = f32_to_bf16_rne(host[i]);
+    FSE_CUDA(cudaMalloc(dptr, tmp.size() * 2));
+    FSE_CUDA(cudaMemcpy(*dptr, tmp.data(), tmp.size() * 2, cudaMemcpyHostToDevice));
+  } else {
+    FSE_CUDA(cudaMalloc(dptr, host.size() * 4));
+    FSE_CUDA(cudaMemcpy(*dptr, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return FSE_OK;
+}
+inline int upload_f32(const std::vector<float>& host, float** dptr) {
+  FSE_CUDA(cudaMalloc(reinterpret_cast<void**>(dptr), host.size() * 4));
+  FSE_CUDA(cudaMemcpy(*dptr, host.data(), host.size() * 4, cudaMemcpyHostToDevice));
+  return FSE_OK;
+}
+
+// ------------------------------------------------------------------ TMA tensor maps
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline int get_encode_fn(PFN_tmapEncodeTiled* out) {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    FSE_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) return fail(FSE_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+    fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  *out = fn;
+  return FSE_OK;
+}
+// bf16 activation [B, T, C] channels-last: dims (C, T, B), box (KB, 128, 1); out-of-range frames/channels read 0.
+inline int make_map_act(CUtensorMap* m, const void* ptr, int C, int T, int B, int KB) {
+  PFN_tmapEncodeTiled enc;
+  FSE_TRY(get_encode_fn(&enc));
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(T) * C * 2};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(KB), static_cast<cuuint32_t>(kTileM), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FSE_ECUDA, "cuTensorMapEncodeTiled(act C=%d T=%d B=%d) failed: %d", C, T, B, (int)r);
+  return FSE_OK;
+}
+// bf16 packed weight [N, Kp] row-major (K contiguous): dims (Kp, N), box (KB, BN).
+inline int make_map_w(CUtensorMap* m, const void* ptr, int Kp, int N, int KB, int BN) {
+  PFN_tmapEncodeTiled enc;
+  FSE_TRY(get_encode_fn(&enc));
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(Kp), static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(Kp) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(KB), static_cast<cuuint32_t>(BN)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FSE_ECUDA, "cuTensorMapEncodeTiled(w Kp=%d N=%d) failed: %d", Kp, N, (int)r);
+  return FSE_OK;
+}
+
+// ------------------------------------------------------------------ conv_gemm launcher
+struct GemmOperands {
+  const void* A0 = nullptr;   // [B, Tsrc, C0] operand type
+  const void* A1 = nullptr;   // [B, Tsrc, C1]
+  const void* W = nullptr;    // [N, Kp]
+  const CUtensorMap* mA0 = nullptr;
+  const CUtensorMap* mA1 = nullptr;
+  const CUtensorMap* mW = nullptr;
+  int BN = 256;               // tensor-core tile width (N % BN == 0)
+};
+
+inline ConvGemmParams make_params(int B, int Trows, int Tsrc, int C0, int ntaps, const int* offs, int C1, int N, int KB) {
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Trows = Trows; p.Tsrc = Tsrc; p.C0 = C0; p.C1 = C1; p.ntaps = ntaps;
+  for (int i = 0; i < ntaps; ++i) p.tap_off[i] = offs[i];
+  p.KB = KB;
+  p.nkb0 = (C0 + KB - 1) / KB;
+  p.nkb1 = (C1 + KB - 1) / KB;
+  p.N = N;
+  p.Kp = (ntaps * p.nkb0 + p.nkb1) * KB;
+  return p;
+}
+
+template <int KB, int CH, class Epi>
+inline int launch_tc(const ConvGemmParams& p, const GemmOperands& op, const Epi& epi, cudaStream_t st) {
+  static bool attr_set = false;
+  const int nkb = p.ntaps * p.nkb0 + p.nkb1;
+  const int stage_bytes = tc_a_stage_bytes(KB) + tc_b_stage_bytes(op.BN, KB);
+  int stages = (220 * 1024) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages > nkb) stages = nkb;
+  if (stages < 1) return fail(FSE_EINVAL, "conv_gemm: tile does not fit shared memory");
+  auto kern = conv_gemm_tc_kernel<KB, CH, Epi>;
+  if (!attr_set) {
+    FSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const size_t smem = tc_smem_bytes(op.BN, KB, stages);
+  const int tiles = (p.Trows + kTileM - 1) / kTileM;
+  dim3 grid(p.B * tiles, p.N / op.BN);
+  const CUtensorMap* mA1 = op.mA1 ? op.mA1 : op.mA0;
+  kern<<<grid, kTcThreads, smem, st>>>(*op.mA0, *mA1, *op.mW, p, op.BN, stages, epi);
+  FSE_CUDA(cudaGetLastError());
+  return FSE_OK;
+}
+
+// mode: FSE_MODE_*.  TOp = operand element type of this handle.
+template <typename TOp, class Epi>
+inline int run_conv_gemm(int mode, const ConvGemmParams& p, const GemmOperands& op, const Epi& epi, cudaStream_t st,
+                         long long* launches) {
+  if (launches) ++*launches;
+  if constexpr (std::is_same<TOp, __nv_bfloat16>::value) {
+    if (mode == FSE_MODE_TC_BF16) {
+      if (p.N % op.BN != 0 || op.BN % 16 != 0 || op.BN > 256) return fail(FSE_EINVAL, "conv_gemm: bad BN %d for N %d", op.BN, p.N);
+      if (!op.mA0 || !op.mW) return fail(FSE_ESTATE, "conv_gemm: tensor maps missing");
+      if (p.KB == 64) {
+        if (op.BN % 32 == 0) return launch_tc<64, 32, Epi>(p, op, epi, st);
+        return launch_tc<64, 16, Epi>(p, op, epi, st);
+      } else {
+        if (op.BN % 32 == 0) return launch_tc<32, 32, Epi>(p, op, epi, st);
+        return launch_tc<32, 16, Epi>(p, op, epi, st);
+      }
+    }
+  }
+  const int tiles = (p.Trows + 63) / 64;
+  dim3 grid(p.B * tiles, (p.N + 63) / 64);
+  conv_gemm_simt_kernel<TOp, Epi><<<grid, 256, 0, st>>>(p, static_cast<const TOp*>(op.A0), static_cast<const TOp*>(op.A1),
+                                                       static_cast<const TOp*>(op.W), epi);
+  FSE_CUDA(cudaGetLastError());
+  return FSE_OK;
+}
+
+}  // namespace fse

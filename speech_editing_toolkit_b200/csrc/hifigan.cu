@@ -1,0 +1,478 @@
+// HiFi-GAN generator forward on sm_100a (modules/vocoder/hifigan/hifigan.py:27-64, 101-142 of the reference).
+// Everything is channels-last [B, T_stage, C]; every conv / transposed conv is a conv_gemm launch:
+//   Conv1d(k, dilation d, "same" padding)   -> k taps at offsets (j - (k-1)/2) d
+//   ConvTranspose1d(k, stride u, pad p)      -> ceil(k/u)-tap GEMM with N' = u*C_out columns (one column block
+//                                               per output phase r), rows q in [0, T_in], element (q, r, co)
+//                                               lands at sample q*u + r - p
+// weight-norm (w = g v / ||v||) is folded once at load time.
+#include <cmath>
+
+#include "epilogues.cuh"
+#include "fse_common.cuh"
+
+namespace fse {
+
+__device__ __forceinline__ float lrelu(float x, float slope) { return x >= 0.f ? x : x * slope; }
+
+// out = lrelu(acc + bias)  — conv_pre (followed by the stage-0 leaky_relu, hifigan.py:127-129) and ResBlock1 convs1 (:53-55)
+template <typename TOp>
+struct EpiAct {
+  const float* bias;
+  TOp* out;   // [B*T, N]
+  int N, T;
+  float slope;
+  template <int NV>
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc) const {
+    float v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = lrelu(acc[i] + __ldg(bias + n0 + i), slope);
+    st_vec<NV>(out + (static_cast<size_t>(b) * T + t) * N + n0, v);
+  }
+};
+
+// transposed-conv phase scatter: x = acc + bias (fp32 stage input) and xa = lrelu(x, 0.1) (hifigan.py:130, :53)
+template <typename TOp>
+struct EpiUp {
+  const float* bias;   // [Cout]
+  float* x;            // [B, Tout, Cout]
+  TOp* xa;             // [B, Tout, Cout]
+  int Cout, Tout, u, pad;
+  template <int NV>
+  __device__ __forceinline__ void apply(int b, int q, int n0, const float* acc) const {
+    const int r = n0 / Cout, co = n0 % Cout;
+    const int tau = q * u + r - pad;
+    if (tau < 0 || tau >= Tout) return;
+    const size_t o = (static_cast<size_t>(b) * Tout + tau) * Cout + co;
+    float v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = acc[i] + __ldg(bias + co + i);
+    st_vec<NV>(x + o, v);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = lrelu(v[i], 0.1f);
+    st_vec<NV>(xa + o, v);
+  }
+};
+
+// ResBlock1 convs2 + residual (hifigan.py:56-57); the last pair of each block also folds the
+// mean over the parallel blocks (hifigan.py:131-137) and the activation feeding the next stage.
+template <typename TOp>
+struct EpiResAdd {
+  const float* bias;
+  const float* res;    // [B*T, N] fp32 residual input
+  float* y;            // [B*T, N] fp32 (kind 0)
+  TOp* ya;             // [B*T, N] lrelu(y, 0.1) (kind 0)
+  float* xs;           // [B*T, N] running sum over resblocks (kind 1..3)
+  TOp* next_a;         // [B*T, N] lrelu(mean, slope_next) operand for the next stage (kind 3)
+  float* final_f32;    // [B*T, N] lrelu(mean, slope_next) fp32 for conv_post (kind 3, last stage) or null
+  int N, T;
+  int kind;            // 0: inside a block; 1: first block end (xs = v); 2: middle (xs += v); 3: last (mean)
+  float num_kernels, slope_next;
+  template <int NV>
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc) const {
+    const size_t o = (static_cast<size_t>(b) * T + t) * N + n0;
+    float v[NV];
+#pragma unroll
+    for (int i = 0; i < NV / 2; ++i) {
+      const float2 rv = reinterpret_cast<const float2*>(res + o)[i];
+      v[2 * i] = (acc[2 * i] + __ldg(bias + n0 + 2 * i)) + rv.x;
+      v[2 * i + 1] = (acc[2 * i + 1] + __ldg(bias + n0 + 2 * i + 1)) + rv.y;
+    }
+    if (kind == 0) {
+      st_vec<NV>(y + o, v);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = lrelu(v[i], 0.1f);
+      st_vec<NV>(ya + o, v);
+    } else if (kind == 1) {
+      st_vec<NV>(xs + o, v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NV / 2; ++i) {
+        const float2 sv = reinterpret_cast<const float2*>(xs + o)[i];
+        v[2 * i] = sv.x + v[2 * i];
+        v[2 * i + 1] = sv.y + v[2 * i + 1];
+      }
+      if (kind == 2) {
+        st_vec<NV>(xs + o, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = lrelu(__fdiv_rn(v[i], num_kernels), slope_next);
+        if (final_f32) st_vec<NV>(final_f32 + o, v);
+        else st_vec<NV>(next_a + o, v);
+      }
+    }
+  }
+};
+
+// conv_post (C -> 1, k taps) + tanh on the already-activated fp32 stage output (hifigan.py:138-140)
+__global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict__ xin, const float* __restrict__ w,
+                                                        float bias, float* __restrict__ wav, int C, int T, int k) {
+  extern __shared__ float sw[];   // [k][C]
+  for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  float acc = 0.f;
+  const int half = (k - 1) / 2;
+  for (int j = 0; j < k; ++j) {
+    const int tt = t + j - half;
+    if (tt < 0 || tt >= T) continue;
+    const float4* row = reinterpret_cast<const float4*>(xin + (static_cast<size_t>(b) * T + tt) * C);
+    const float* wj = sw + j * C;
+    for (int c = 0; c < C / 4; ++c) {
+      const float4 v = __ldg(row + c);
+      acc = fmaf(v.x, wj[4 * c], acc); acc = fmaf(v.y, wj[4 * c + 1], acc);
+      acc = fmaf(v.z, wj[4 * c + 2], acc); acc = fmaf(v.w, wj[4 * c + 3], acc);
+    }
+  }
+  wav[static_cast<size_t>(b) * T + t] = tanhf(acc + bias);
+}
+
+__global__ void __launch_bounds__(256) voc_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n4) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n4) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    st_vec<4>(dst + 4 * i, f);
+  }
+}
+
+struct ConvW {
+  void* W = nullptr; float* bias = nullptr;
+  int Cin = 0, N = 0, ntaps = 0, KB = 64, Kp = 0, BN = 0;
+  int offs[kMaxTaps] = {0};
+  CUtensorMap map{};
+};
+
+}  // namespace fse
+
+using namespace fse;
+
+struct fse_vocoder {
+  fse_vocoder_config cfg{};
+  bool bf16 = true, loaded = false;
+  int hop = 1;
+  ConvW pre;
+  std::vector<ConvW> ups;
+  std::vector<ConvW> c1, c2;      // [stage][block][m]
+  float* post_w = nullptr; float post_b = 0.f; int post_k = 7;
+  struct Plan { const void* ws = nullptr; int B = 0, T = 0; std::vector<CUtensorMap> maps; } plan;
+  long long launches = 0;
+  void* host_ws = nullptr; size_t host_ws_bytes = 0;
+};
+
+namespace {
+
+int stage_channels(const fse_vocoder* h, int i) { return h->cfg.upsample_initial_channel >> (i + 1); }
+
+struct VWs {
+  void* melb; void* ua; float* x; void* xa; float* y; void* ya; void* tmp; float* xs;
+  size_t bytes;
+};
+VWs vcarve(const fse_vocoder* h, void* base, int B, int T) {
+  const size_t es = h->bf16 ? 2 : 4;
+  size_t maxel = static_cast<size_t>(T) * h->cfg.upsample_initial_channel;   // conv_pre output
+  size_t Ti = T;
+  for (int i = 0; i < h->cfg.num_upsamples; ++i) {
+    Ti *= h->cfg.upsample_rates[i];
+    maxel = std::max(maxel, Ti * stage_channels(h, i));
+  }
+  maxel *= B;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
+  uint8_t* p = static_cast<uint8_t*>(base);
+  VWs w{};
+  size_t o;
+  o = take(static_cast<size_t>(B) * T * h->cfg.n_mels * es); w.melb = p + o;
+  o = take(maxel * es); w.ua = p + o;
+  o = take(maxel * 4);  w.x = reinterpret_cast<float*>(p + o);
+  o = take(maxel * es); w.xa = p + o;
+  o = take(maxel * 4);  w.y = reinterpret_cast<float*>(p + o);
+  o = take(maxel * es); w.ya = p + o;
+  o = take(maxel * es); w.tmp = p + o;
+  o = take(maxel * 4);  w.xs = reinterpret_cast<float*>(p + o);
+  w.bytes = off;
+  return w;
+}
+
+// fold weight norm: w = g * v / ||v|| with the norm over all dims but 0 (torch weight_norm dim=0)
+std::vector<float> fold_wn(const TensorTable& tt, const std::string& name, int64_t d0, int64_t rest, int* rc) {
+  std::vector<float> w(static_cast<size_t>(d0 * rest));
+  if (tt.has(name + ".weight")) {
+    const float* p = tt.get(name + ".weight", d0 * rest, rc);
+    if (*rc == FSE_OK) w.assign(p, p + d0 * rest);
+    return w;
+  }
+  const float* v = tt.get(name + ".weight_v", d0 * rest, rc);
+  if (*rc != FSE_OK) return w;
+  const float* g = tt.get(name + ".weight_g", d0, rc);
+  if (*rc != FSE_OK) return w;
+  for (int64_t i = 0; i < d0; ++i) {
+    double ss = 0.0;
+    for (int64_t j = 0; j < rest; ++j) ss += static_cast<double>(v[i * rest + j]) * v[i * rest + j];
+    const float scale = static_cast<float>(g[i] / std::sqrt(ss));
+    for (int64_t j = 0; j < rest; ++j) w[i * rest + j] = v[i * rest + j] * scale;
+  }
+  return w;
+}
+
+int finish_convw(fse_vocoder* h, ConvW& cw, const std::vector<float>& packed, const float* bias, int nbias) {
+  FSE_TRY(upload_operand(packed, h->bf16, &cw.W));
+  FSE_TRY(upload_f32(std::vector<float>(bias, bias + nbias), &cw.bias));
+  if (h->cfg.mode == FSE_MODE_TC_BF16) FSE_TRY(make_map_w(&cw.map, cw.W, cw.Kp, cw.N, cw.KB, cw.BN));
+  return FSE_OK;
+}
+
+// Conv1d weight [Cout, Cin, k] -> packed [Cout, ntaps * nkb * KB]
+int pack_conv(fse_vocoder* h, const TensorTable& tt, const std::string& name, int Cout, int Cin, int k, int dil, ConvW& cw) {
+  int rc = FSE_OK;
+  std::vector<float> w = fold_wn(tt, name, Cout, static_cast<int64_t>(Cin) * k, &rc);
+  if (rc) return rc;
+  const float* bias = tt.get(name + ".bias", Cout, &rc);
+  if (rc) return rc;
+  if (k > kMaxTaps || k % 2 == 0) return fail(FSE_EINVAL, "%s: kernel size %d unsupported", name.c_str(), k);
+  cw.Cin = Cin; cw.N = Cout; cw.ntaps = k; cw.KB = Cin % 64 == 0 || Cin > 64 ? 64 : 32;
+  const int nkb = (Cin + cw.KB - 1) / cw.KB;
+  cw.Kp = k * nkb * cw.KB;
+  cw.BN = Cout <= 256 ? Cout : 256;
+  for (int j = 0; j < k; ++j) cw.offs[j] = (j - (k - 1) / 2) * dil;
+  std::vector<float> p(static_cast<size_t>(Cout) * cw.Kp, 0.f);
+  for (int o = 0; o < Cout; ++o)
+    for (int c = 0; c < Cin; ++c)
+      for (int j = 0; j < k; ++j) p[static_cast<size_t>(o) * cw.Kp + j * nkb * cw.KB + c] = w[(static_cast<size_t>(o) * Cin + c) * k + j];
+  return finish_convw(h, cw, p, bias, Cout);
+}
+
+// ConvTranspose1d weight [Cin, Cout, k], stride u -> packed [u*Cout, ntaps*nkb*KB], tap m <-> kernel index r + m*u, offset -m
+int pack_up(fse_vocoder* h, const TensorTable& tt, const std::string& name, int Cin, int Cout, int k, int u, ConvW& cw) {
+  int rc = FSE_OK;
+  std::vector<float> w = fold_wn(tt, name, Cin, static_cast<int64_t>(Cout) * k, &rc);   // dim 0 = Cin for ConvTranspose1d
+  if (rc) return rc;
+  const float* bias = tt.get(name + ".bias", Cout, &rc);
+  if (rc) return rc;
+  const int ntaps = (k + u - 1) / u;
+  if (ntaps > kMaxTaps) return fail(FSE_EINVAL, "%s: too many taps", name.c_str());
+  cw.Cin = Cin; cw.N = u * Cout; cw.ntaps = ntaps; cw.KB = 64;
+  const int nkb = (Cin + 63) / 64;
+  cw.Kp = ntaps * nkb * 64;
+  cw.BN = cw.N % 256 == 0 ? 256 : (cw.N % 128 == 0 ? 128 : (cw.N % 64 == 0 ? 64 : 32));
+  for (int m = 0; m < ntaps; ++m) cw.offs[m] = -m;
+  std::vector<float> p(static_cast<size_t>(cw.N) * cw.Kp, 0.f);
+  for (int r = 0; r < u; ++r)
+    for (int co = 0; co < Cout; ++co)
+      for (int m = 0; m < ntaps; ++m) {
+        const int j = r + m * u;
+        if (j >= k) continue;
+        for (int ci = 0; ci < Cin; ++ci)
+          p[(static_cast<size_t>(r) * Cout + co) * cw.Kp + m * nkb * 64 + ci] = w[(static_cast<size_t>(ci) * Cout + co) * k + j];
+      }
+  return finish_convw(h, cw, p, bias, Cout);
+}
+
+template <typename TOp, class Epi>
+int run_conv(fse_vocoder* h, const ConvW& cw, const void* A, const CUtensorMap* mA, int B, int Trows, int Tsrc, const Epi& epi, cudaStream_t st) {
+  ConvGemmParams p = make_params(B, Trows, Tsrc, cw.Cin, cw.ntaps, cw.offs, 0, cw.N, cw.KB);
+  GemmOperands op; op.A0 = A; op.W = cw.W; op.mA0 = mA; op.mW = &cw.map; op.BN = cw.BN;
+  return run_conv_gemm<TOp>(h->cfg.mode, p, op, epi, st, &h->launches);
+}
+
+template <typename TOp>
+int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, void* ws, cudaStream_t st) {
+  VWs w = vcarve(h, ws, B, T);
+  const auto& cfg = h->cfg;
+  const bool tc = cfg.mode == FSE_MODE_TC_BF16;
+  const int nu = cfg.num_upsamples, nk = cfg.num_kernels;
+  // tensor maps: [0] mel, [1] ua@pre, then per stage: ua(as ups input), xa, ya, tmp
+  if (tc && !(h->plan.ws == ws && h->plan.B == B && h->plan.T == T)) {
+    h->plan.maps.assign(2 + 4 * nu, CUtensorMap{});
+    FSE_TRY(make_map_act(&h->plan.maps[0], w.melb, cfg.n_mels, T, B, h->pre.KB));
+    int Tin = T, Cin = cfg.upsample_initial_channel;
+    for (int i = 0; i < nu; ++i) {
+      const int Cout = stage_channels(h, i), Tout = Tin * cfg.upsample_rates[i];
+      const int kb = h->c1[i * nk * 3].KB;
+      FSE_TRY(make_map_act(&h->plan.maps[2 + 4 * i + 0], w.ua, Cin, Tin, B, h->ups[i].KB));
+      FSE_TRY(make_map_act(&h->plan.maps[2 + 4 * i + 1], w.xa, Cout, Tout, B, kb));
+      FSE_TRY(make_map_act(&h->plan.maps[2 + 4 * i + 2], w.ya, Cout, Tout, B, kb));
+      FSE_TRY(make_map_act(&h->plan.maps[2 + 4 * i + 3], w.tmp, Cout, Tout, B, kb));
+      Tin = Tout; Cin = Cout;
+    }
+    h->plan.ws = ws; h->plan.B = B; h->plan.T = T;
+  }
+  auto M = [&](int idx) -> const CUtensorMap* { return tc ? &h->plan.maps[idx] : nullptr; };
+
+  const void* mel_op = mel;
+  if constexpr (std::is_same<TOp, __nv_bfloat16>::value) {
+    const size_t n = static_cast<size_t>(B) * T * cfg.n_mels;
+    voc_f32_to_bf16_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, st>>>(mel, static_cast<__nv_bfloat16*>(w.melb), n / 4);
+    FSE_CUDA(cudaGetLastError());
+    ++h->launches;
+    mel_op = w.melb;
+  }
+  {  // conv_pre + leaky_relu(0.1) of stage 0 (hifigan.py:127-129)
+    EpiAct<TOp> epi{h->pre.bias, static_cast<TOp*>(w.ua), h->pre.N, T, 0.1f};
+    FSE_TRY((run_conv<TOp>(h, h->pre, mel_op, M(0), B, T, T, epi, st)));
+  }
+  int Tin = T;
+  for (int i = 0; i < nu; ++i) {
+    const int u = cfg.upsample_rates[i], k = cfg.upsample_kernel_sizes[i], pad = (k - u) / 2;
+    const int Cout = stage_channels(h, i), Tout = Tin * u;
+    {
+      EpiUp<TOp> epi{h->ups[i].bias, w.x, static_cast<TOp*>(w.xa), Cout, Tout, u, pad};
+      FSE_TRY((run_conv<TOp>(h, h->ups[i], w.ua, M(2 + 4 * i), B, Tin + 1, Tin, epi, st)));
+    }
+    const bool last_stage = i == nu - 1;
+    for (int j = 0; j < nk; ++j) {
+      for (int m = 0; m < 3; ++m) {
+        const ConvW& a = h->c1[(i * nk + j) * 3 + m];
+        const ConvW& c = h->c2[(i * nk + j) * 3 + m];
+        {
+          EpiAct<TOp> epi{a.bias, static_cast<TOp*>(w.tmp), Cout, Tout, 0.1f};
+          FSE_TRY((run_conv<TOp>(h, a, m == 0 ? w.xa : w.ya, M(2 + 4 * i + (m == 0 ? 1 : 2)), B, Tout, Tout, epi, st)));
+        }
+        {
+          EpiResAdd<TOp> epi{};
+          epi.bias = c.bias; epi.res = m == 0 ? w.x : w.y; epi.y = w.y; epi.ya = static_cast<TOp*>(w.ya);
+          epi.xs = w.xs; epi.next_a = static_cast<TOp*>(w.ua); epi.final_f32 = last_stage ? w.xs : nullptr;
+          epi.N = Cout; epi.T = Tout;
+          epi.kind = m < 2 ? 0 : (nk == 1 ? 3 : (j == 0 ? 1 : (j == nk - 1 ? 3 : 2)));
+          epi.num_kernels = static_cast<float>(nk);
+          epi.slope_next = last_stage ? 0.01f : 0.1f;   // F.leaky_relu default slope before conv_post (hifigan.py:138)
+          FSE_TRY((run_conv<TOp>(h, c, w.tmp, M(2 + 4 * i + 3), B, Tout, Tout, epi, st)));
+        }
+      }
+    }
+    Tin = Tout;
+  }
+  const int Cl = stage_channels(h, nu - 1);
+  conv_post_kernel<<<dim3((Tin + 255) / 256, B), 256, h->post_k * Cl * sizeof(float), st>>>(w.xs, h->post_w, h->post_b, wav, Cl, Tin, h->post_k);
+  FSE_CUDA(cudaGetLastError());
+  ++h->launches;
+  return FSE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fse_vocoder_create(const fse_vocoder_config* cfg, fse_vocoder** out) {
+  if (!cfg || !out) return fail(FSE_EINVAL, "null argument");
+  if (cfg->num_upsamples <= 0 || cfg->num_upsamples > 8 || cfg->num_kernels <= 0 || cfg->num_kernels > 4)
+    return fail(FSE_EINVAL, "num_upsamples / num_kernels out of range");
+  if (cfg->n_mels % 8 != 0) return fail(FSE_EINVAL, "n_mels must be a multiple of 8");
+  if (cfg->mode < 0 || cfg->mode > 2) return fail(FSE_EINVAL, "unknown mode %d", cfg->mode);
+  int hop = 1;
+  for (int i = 0; i < cfg->num_upsamples; ++i) {
+    const int u = cfg->upsample_rates[i], k = cfg->upsample_kernel_sizes[i];
+    if (u <= 0 || k < u || (k - u) % 2 != 0) return fail(FSE_EINVAL, "upsample stage %d: need k >= u and (k-u) even", i);
+    const int c = cfg->upsample_initial_channel >> (i + 1);
+    if (c < 32 || c % 32 != 0) return fail(FSE_EINVAL, "stage %d has %d channels; need a multiple of 32", i, c);
+    hop *= u;
+  }
+  int dev = 0;
+  FSE_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  FSE_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(FSE_ECUDA, "device is sm_%d%d; this library is built for sm_100a only (no fallback)", prop.major, prop.minor);
+  auto* h = new fse_vocoder();
+  h->cfg = *cfg;
+  h->bf16 = cfg->mode != FSE_MODE_SIMT_F32;
+  h->hop = hop;
+  *out = h;
+  return FSE_OK;
+}
+
+void fse_vocoder_destroy(fse_vocoder* h) {
+  if (!h) return;
+  auto freew = [](ConvW& c) { if (c.W) cudaFree(c.W); if (c.bias) cudaFree(c.bias); };
+  freew(h->pre);
+  for (auto& c : h->ups) freew(c);
+  for (auto& c : h->c1) freew(c);
+  for (auto& c : h->c2) freew(c);
+  if (h->post_w) cudaFree(h->post_w);
+  if (h->host_ws) cudaFree(h->host_ws);
+  delete h;
+}
+
+int fse_vocoder_load_weights(fse_vocoder* h, const fse_tensor* tensors, int32_t n) {
+  if (!h || !tensors || n <= 0) return fail(FSE_EINVAL, "null argument");
+  if (h->loaded) return fail(FSE_ESTATE, "weights already loaded");
+  const auto& cfg = h->cfg;
+  TensorTable tt(tensors, n);
+  const int C0 = cfg.upsample_initial_channel, nu = cfg.num_upsamples, nk = cfg.num_kernels;
+  FSE_TRY(pack_conv(h, tt, "conv_pre", C0, cfg.n_mels, 7, 1, h->pre));
+  h->ups.resize(nu); h->c1.resize(nu * nk * 3); h->c2.resize(nu * nk * 3);
+  int Cin = C0;
+  for (int i = 0; i < nu; ++i) {
+    const int Cout = stage_channels(h, i);
+    FSE_TRY(pack_up(h, tt, "ups." + std::to_string(i), Cin, Cout, cfg.upsample_kernel_sizes[i], cfg.upsample_rates[i], h->ups[i]));
+    for (int j = 0; j < nk; ++j)
+      for (int m = 0; m < 3; ++m) {
+        const std::string pre = "resblocks." + std::to_string(i * nk + j) + ".";
+        FSE_TRY(pack_conv(h, tt, pre + "convs1." + std::to_string(m), Cout, Cout, cfg.resblock_kernel_sizes[j],
+                          cfg.resblock_dilations[j][m], h->c1[(i * nk + j) * 3 + m]));
+        FSE_TRY(pack_conv(h, tt, pre + "convs2." + std::to_string(m), Cout, Cout, cfg.resblock_kernel_sizes[j], 1,
+                          h->c2[(i * nk + j) * 3 + m]));
+      }
+    Cin = Cout;
+  }
+  {  // conv_post [1, Cl, 7] -> [7][Cl] fp32
+    int rc = FSE_OK;
+    std::vector<float> w = fold_wn(tt, "conv_post", 1, static_cast<int64_t>(Cin) * 7, &rc);
+    if (rc) return rc;
+    const float* b = tt.get("conv_post.bias", 1, &rc);
+    if (rc) return rc;
+    std::vector<float> p(static_cast<size_t>(7) * Cin);
+    for (int c = 0; c < Cin; ++c) for (int j = 0; j < 7; ++j) p[static_cast<size_t>(j) * Cin + c] = w[static_cast<size_t>(c) * 7 + j];
+    FSE_TRY(upload_f32(p, &h->post_w));
+    h->post_b = b[0];
+    h->post_k = 7;
+  }
+  h->loaded = true;
+  return FSE_OK;
+}
+
+int64_t fse_vocoder_workspace_bytes(const fse_vocoder* h, int32_t B, int32_t T) {
+  if (!h || B <= 0 || T <= 0) return 0;
+  return static_cast<int64_t>(vcarve(h, nullptr, B, T).bytes);
+}
+
+int fse_vocoder_forward(fse_vocoder* h, const float* mel, float* wav, int32_t B, int32_t T, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!h || !mel || !wav) return fail(FSE_EINVAL, "null argument");
+  if (!h->loaded) return fail(FSE_ESTATE, "weights not loaded");
+  if (B <= 0 || T <= 0) return fail(FSE_EINVAL, "B and T must be positive");
+  if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 1023)) return fail(FSE_EINVAL, "workspace must be non-null and 1024-byte aligned");
+  if (workspace_bytes < fse_vocoder_workspace_bytes(h, B, T)) return fail(FSE_EINVAL, "workspace too small");
+  if ((static_cast<size_t>(B) * T * h->cfg.n_mels) % 4 != 0) return fail(FSE_EINVAL, "B*T*n_mels must be a multiple of 4");
+  h->launches = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return h->bf16 ? forward_impl<__nv_bfloat16>(h, mel, wav, B, T, workspace, st) : forward_impl<float>(h, mel, wav, B, T, workspace, st);
+}
+
+int fse_vocoder_forward_host(fse_vocoder* h, const float* mel, float* wav, int32_t B, int32_t T) {
+  if (!h || !mel || !wav) return fail(FSE_EINVAL, "null argument");
+  if (!h->loaded) return fail(FSE_ESTATE, "weights not loaded");
+  if (B <= 0 || T <= 0) return fail(FSE_EINVAL, "B and T must be positive");
+  const size_t ws_bytes = static_cast<size_t>(fse_vocoder_workspace_bytes(h, B, T));
+  const size_t mel_b = align_up(static_cast<size_t>(B) * T * h->cfg.n_mels * 4, 1024);
+  const size_t wav_b = align_up(static_cast<size_t>(B) * T * h->hop * 4, 1024);
+  const size_t total = ws_bytes + mel_b + wav_b;
+  if (h->host_ws_bytes < total) {
+    if (h->host_ws) cudaFree(h->host_ws);
+    h->host_ws = nullptr; h->host_ws_bytes = 0;
+    FSE_CUDA(cudaMalloc(&h->host_ws, total));
+    h->host_ws_bytes = total;
+  }
+  uint8_t* p = static_cast<uint8_t*>(h->host_ws);
+  float* d_mel = reinterpret_cast<float*>(p + ws_bytes);
+  float* d_wav = reinterpret_cast<float*>(p + ws_bytes + mel_b);
+  cudaStream_t st = nullptr;
+  FSE_CUDA(cudaMemcpyAsync(d_mel, mel, static_cast<size_t>(B) * T * h->cfg.n_mels * 4, cudaMemcpyHostToDevice, st));
+  FSE_TRY(fse_vocoder_forward(h, d_mel, d_wav, B, T, p, static_cast<int64_t>(ws_bytes), st));
+  FSE_CUDA(cudaMemcpyAsync(wav, d_wav, static_cast<size_t>(B) * T * h->hop * 4, cudaMemcpyDeviceToHost, st));
+  FSE_CUDA(cudaStreamSynchronize(st));
+  return FSE_OK;
+}
+
+int64_t fse_vocoder_last_launches(const fse_vocoder* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

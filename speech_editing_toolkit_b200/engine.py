@@ -1,0 +1,222 @@
+"""Thin Python owners of the C-ABI handles.  PyTorch is plumbing here: it allocates device memory and
+provides the CUDA stream; all arithmetic of the hot path happens inside libfse_b200.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FseError, MODES, check
+
+
+def _as_f32_numpy(v) -> np.ndarray:
+    if isinstance(v, torch.Tensor):
+        v = v.detach().to("cpu", torch.float32).numpy()
+    return np.ascontiguousarray(v, dtype=np.float32)
+
+
+def _tensor_table(sd: Dict[str, object], skip_suffixes=()):
+    keep = []     # keep numpy arrays alive while the C call runs
+    names = [k for k in sd if not any(k.endswith(s) for s in skip_suffixes)]
+    arr = (_lib.Tensor * len(names))()
+    for i, k in enumerate(names):
+        a = _as_f32_numpy(sd[k])
+        keep.append(a)
+        arr[i].name = k.encode()
+        arr[i].data = a.ctypes.data_as(C.POINTER(C.c_float))
+        arr[i].numel = a.size
+    return arr, len(names), keep
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise FseError("tensor must live on a CUDA device; this path has no CPU implementation")
+
+
+class _Workspace:
+    """Caller-owned (torch-allocated) device workspace, grown on demand, 1024-byte aligned."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes: int, device):
+        if self.buf is None or self.buf.numel() < nbytes + 1024 or self.buf.device != device:
+            self.buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        base = self.buf.data_ptr()
+        aligned = (base + 1023) // 1024 * 1024
+        return C.c_void_p(aligned), nbytes
+
+
+class Denoiser:
+    """Handle of the DiffNet denoiser + sampling loop (fse_denoiser_* / fse_denoise_step / fse_sample)."""
+
+    def __init__(self, n_mels=80, hidden=192, channels=256, layers=20, dilation_cycle_length=1, mode="tc_bf16"):
+        self.cfg = _lib.DenoiserConfig(n_mels, hidden, channels, layers, dilation_cycle_length, MODES[mode])
+        self.mode = mode
+        self._h = C.c_void_p()
+        check(_lib.lib().fse_denoiser_create(C.byref(self.cfg), C.byref(self._h)))
+        self._ws = _Workspace()
+        self.timesteps = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _lib.lib().fse_denoiser_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd: Dict[str, object]):
+        arr, n, keep = _tensor_table(sd)
+        check(_lib.lib().fse_denoiser_load_weights(self._h, arr, n))
+        del keep
+
+    def set_schedule(self, coef1, coef2, logvar_clipped):
+        c1, c2, lv = (_as_f32_numpy(a) for a in (coef1, coef2, logvar_clipped))
+        assert c1.shape == c2.shape == lv.shape and c1.ndim == 1
+        self.timesteps = c1.shape[0] - 1
+        f = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        check(_lib.lib().fse_denoiser_set_schedule(self._h, self.timesteps, f(c1), f(c2), f(lv)))
+
+    def _workspace(self, B, T, device):
+        nbytes = _lib.lib().fse_denoiser_workspace_bytes(self._h, B, T)
+        return self._ws.get(nbytes, device)
+
+    @property
+    def last_launches(self) -> int:
+        return int(_lib.lib().fse_denoiser_last_launches(self._h))
+
+    def denoise_step(self, x_t: torch.Tensor, cond: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """x_t[B,M,T] fp32, cond[B,T,H] fp32 (physical layout), t[B] int64 -> x0[B,M,T]."""
+        _need_cuda(x_t, cond, t)
+        B, M, T = x_t.shape
+        x_t = x_t.contiguous().float(); cond = cond.contiguous().float(); t = t.contiguous().long()
+        assert cond.shape == (B, T, self.cfg.hidden), f"cond must be [B,T,H], got {tuple(cond.shape)}"
+        x0 = torch.empty_like(x_t)
+        ws, nbytes = self._workspace(B, T, x_t.device)
+        check(_lib.lib().fse_denoise_step(self._h, _ptr(x_t), _ptr(cond), _ptr(t), _ptr(x0), B, T, ws, nbytes, _stream()))
+        return x0
+
+    def posterior_step(self, x0, x_t, t, noise=None, seed=0, step=0) -> torch.Tensor:
+        _need_cuda(x0, x_t, t, noise)
+        B, M, T = x_t.shape
+        x0 = x0.contiguous().float(); x_t = x_t.contiguous().float(); t = t.contiguous().long()
+        if noise is not None:
+            noise = noise.contiguous().float()
+        out = torch.empty_like(x_t)
+        check(_lib.lib().fse_posterior_step(self._h, _ptr(x0), _ptr(x_t), _ptr(t), _ptr(noise), seed, step, _ptr(out), B, T, _stream()))
+        return out
+
+    def sample(self, cond: torch.Tensor, noise: Optional[torch.Tensor] = None, seed: int = 0,
+               ref_mel: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None, trace: bool = False):
+        """cond[B,T,H] -> mel_out[B,T,M].  noise: None (Philox) or [(S+1),B,M,T]."""
+        _need_cuda(cond, noise, ref_mel, mask)
+        B, T, H = cond.shape
+        M, S = self.cfg.n_mels, self.timesteps
+        cond = cond.contiguous().float()
+        if noise is not None:
+            noise = noise.contiguous().float()
+            assert noise.shape == (S + 1, B, M, T), f"noise must be [S+1,B,M,T], got {tuple(noise.shape)}"
+        if ref_mel is not None:
+            ref_mel = ref_mel.contiguous().float(); mask = mask.reshape(B, T).contiguous().float()
+        mel = torch.empty(B, T, M, dtype=torch.float32, device=cond.device)
+        xs = torch.empty(S, B, M, T, dtype=torch.float32, device=cond.device) if trace else None
+        ws, nbytes = self._workspace(B, T, cond.device)
+        check(_lib.lib().fse_sample(self._h, _ptr(cond), _ptr(noise), seed, _ptr(ref_mel), _ptr(mask), _ptr(mel), _ptr(xs),
+                                    B, T, ws, nbytes, _stream()))
+        return (mel, xs) if trace else mel
+
+    def sample_host(self, cond: np.ndarray, noise=None, seed: int = 0, ref_mel=None, mask=None) -> np.ndarray:
+        """HOST numpy in / out through fse_sample_host (H2D + D2H inside the call)."""
+        cond = np.ascontiguousarray(cond, dtype=np.float32)
+        B, T, H = cond.shape
+        out = np.empty((B, T, self.cfg.n_mels), dtype=np.float32)
+        p = lambda a: None if a is None else C.c_void_p(np.ascontiguousarray(a, dtype=np.float32).ctypes.data)
+        keep = [np.ascontiguousarray(a, dtype=np.float32) if a is not None else None for a in (noise, ref_mel, mask)]
+        q = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+        check(_lib.lib().fse_sample_host(self._h, C.c_void_p(cond.ctypes.data), q(keep[0]), seed, q(keep[1]), q(keep[2]),
+                                         C.c_void_p(out.ctypes.data), B, T))
+        return out
+
+
+HIFIGAN_V1 = dict(
+    upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4], upsample_initial_channel=512,
+    resblock="1", resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+)
+
+
+class Vocoder:
+    """Handle of the HiFi-GAN generator (fse_vocoder_*)."""
+
+    def __init__(self, config: dict = None, n_mels: int = 80, mode="tc_bf16"):
+        config = dict(HIFIGAN_V1 if config is None else config)
+        if str(config.get("resblock", "1")) != "1":
+            raise FseError("only ResBlock1 generators (HiFi-GAN V1/V2 family) are implemented")
+        cfg = _lib.VocoderConfig()
+        cfg.n_mels = n_mels
+        cfg.upsample_initial_channel = config["upsample_initial_channel"]
+        rates, ks = config["upsample_rates"], config["upsample_kernel_sizes"]
+        cfg.num_upsamples = len(rates)
+        for i, (u, k) in enumerate(zip(rates, ks)):
+            cfg.upsample_rates[i] = u
+            cfg.upsample_kernel_sizes[i] = k
+        rks, rds = config["resblock_kernel_sizes"], config["resblock_dilation_sizes"]
+        cfg.num_kernels = len(rks)
+        for j, (k, ds) in enumerate(zip(rks, rds)):
+            cfg.resblock_kernel_sizes[j] = k
+            assert len(ds) == 3, "ResBlock1 has three dilations"
+            for m, d in enumerate(ds):
+                cfg.resblock_dilations[j][m] = d
+        cfg.mode = MODES[mode]
+        self.cfg, self.config, self.mode = cfg, config, mode
+        self.hop = int(np.prod(rates))
+        self._h = C.c_void_p()
+        check(_lib.lib().fse_vocoder_create(C.byref(cfg), C.byref(self._h)))
+        self._ws = _Workspace()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _lib.lib().fse_vocoder_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd: Dict[str, object]):
+        arr, n, keep = _tensor_table(sd)
+        check(_lib.lib().fse_vocoder_load_weights(self._h, arr, n))
+        del keep
+
+    @property
+    def last_launches(self) -> int:
+        return int(_lib.lib().fse_vocoder_last_launches(self._h))
+
+    def forward(self, mel: torch.Tensor) -> torch.Tensor:
+        """mel[B,T,M] fp32 cuda -> wav[B,T*hop]."""
+        _need_cuda(mel)
+        B, T, M = mel.shape
+        mel = mel.contiguous().float()
+        wav = torch.empty(B, T * self.hop, dtype=torch.float32, device=mel.device)
+        nbytes = _lib.lib().fse_vocoder_workspace_bytes(self._h, B, T)
+        ws, nbytes = self._ws.get(nbytes, mel.device)
+        check(_lib.lib().fse_vocoder_forward(self._h, _ptr(mel), _ptr(wav), B, T, ws, nbytes, _stream()))
+        return wav
+
+    def forward_host(self, mel: np.ndarray) -> np.ndarray:
+        mel = np.ascontiguousarray(mel, dtype=np.float32)
+        B, T, M = mel.shape
+        wav = np.empty((B, T * self.hop), dtype=np.float32)
+        check(_lib.lib().fse_vocoder_forward_host(self._h, C.c_void_p(mel.ctypes.data), C.c_void_p(wav.ctypes.data), B, T))
+        return wav

@@ -1,0 +1,116 @@
+"""Seeded synthetic weights and inputs of the benchmark / parity workloads.
+
+Pretrained FluentSpeech / HiFi-GAN checkpoints are Google-Drive artefacts that are not available
+offline, so parity and throughput are measured on seeded random weights with the reference's
+state_dict layout.  numpy.random.RandomState is used because its stream is frozen across numpy
+versions (fixtures under tests/golden/ depend on it).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import numpy as np
+
+F32 = np.float32
+
+
+def denoiser_state_dict(seed: int = 1234, n_mels: int = 80, hidden: int = 192, channels: int = 256,
+                        layers: int = 20) -> Dict[str, np.ndarray]:
+    """Random `denoise_fn.*` state_dict with the reference's keys/shapes (diffnet.py:84-108).
+
+    Conv weights are kaiming-normal like the reference's Conv1d helper (diffnet.py:49-52); every bias is
+    randomised and the zero-initialised output_projection (diffnet.py:108) gets N(0, 0.05) so that parity
+    tests are not vacuous (SURVEY.md §8a zero-init trap)."""
+    rs = np.random.RandomState(seed)
+    C, H, M = channels, hidden, n_mels
+    sd: Dict[str, np.ndarray] = {}
+
+    def conv(name, co, ci, k, std=None):
+        std = math.sqrt(2.0 / (ci * k)) if std is None else std
+        sd[name + ".weight"] = (rs.standard_normal((co, ci, k)) * std).astype(F32)
+        sd[name + ".bias"] = (rs.standard_normal((co,)) * 0.05).astype(F32)
+
+    def lin(name, co, ci):
+        b = 1.0 / math.sqrt(ci)
+        sd[name + ".weight"] = rs.uniform(-b, b, (co, ci)).astype(F32)
+        sd[name + ".bias"] = rs.uniform(-b, b, (co,)).astype(F32)
+
+    conv("input_projection", C, M, 1)
+    lin("mlp.0", 4 * C, C)
+    lin("mlp.2", C, 4 * C)
+    for n in range(layers):
+        p = f"residual_layers.{n}."
+        conv(p + "dilated_conv", 2 * C, C, 3)
+        lin(p + "diffusion_projection", C, C)
+        conv(p + "conditioner_projection", 2 * C, H, 1)
+        conv(p + "output_projection", 2 * C, C, 1)
+    conv("skip_projection", C, C, 1)
+    conv("output_projection", M, C, 1, std=0.05)
+    return sd
+
+
+def hifigan_state_dict(seed: int = 1234, config: dict = None, n_mels: int = 80) -> Dict[str, np.ndarray]:
+    """Random HifiGanGenerator state_dict (weight_g / weight_v / bias per conv; hifigan.py:101-124).
+    weight_g is drawn independently of ||weight_v|| so that the weight-norm fold is exercised."""
+    from .engine import HIFIGAN_V1
+    cfg = dict(HIFIGAN_V1 if config is None else config)
+    rs = np.random.RandomState(seed)
+    sd: Dict[str, np.ndarray] = {}
+
+    def wn(name, shape, fan_in, gain=1.0):
+        v = (rs.standard_normal(shape) * gain / math.sqrt(fan_in)).astype(F32)
+        norm = np.sqrt((v.astype(np.float64) ** 2).sum(axis=tuple(range(1, v.ndim)), keepdims=True))
+        sd[name + ".weight_v"] = v
+        sd[name + ".weight_g"] = (norm * rs.uniform(0.8, 1.2, norm.shape)).astype(F32)
+
+    c0 = cfg["upsample_initial_channel"]
+    wn("conv_pre", (c0, n_mels, 7), n_mels * 7)
+    sd["conv_pre.bias"] = (rs.standard_normal((c0,)) * 0.02).astype(F32)
+    nk = len(cfg["resblock_kernel_sizes"])
+    ch = c0
+    for i, (u, k) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
+        cin, ch = ch, c0 // (2 ** (i + 1))
+        wn(f"ups.{i}", (cin, ch, k), cin * k / u, gain=1.4)           # ConvTranspose1d weight is [C_in, C_out, k]
+        sd[f"ups.{i}.bias"] = (rs.standard_normal((ch,)) * 0.02).astype(F32)
+        for j, rk in enumerate(cfg["resblock_kernel_sizes"]):
+            for m in range(3):
+                for part in ("convs1", "convs2"):
+                    name = f"resblocks.{i * nk + j}.{part}.{m}"
+                    wn(name, (ch, ch, rk), ch * rk, gain=0.7)
+                    sd[name + ".bias"] = (rs.standard_normal((ch,)) * 0.02).astype(F32)
+    wn("conv_post", (1, ch, 7), ch * 7, gain=0.12)
+    sd["conv_post.bias"] = (rs.standard_normal((1,)) * 0.02).astype(F32)
+    return sd
+
+
+def synthetic_cond(seed: int, B: int, T: int, hidden: int = 192) -> np.ndarray:
+    """Stand-in for the condition-encoder output decoder_inp[B,T,H] (spec_denoiser.py:159-167)."""
+    rs = np.random.RandomState(seed + 17)
+    return rs.standard_normal((B, T, hidden)).astype(F32)
+
+
+def synthetic_noise(seed: int, S: int, B: int, T: int, n_mels: int = 80) -> np.ndarray:
+    """Injected N(0,1) draws [(S+1),B,M,T]: x_S then one per iteration (spec_denoiser.py:98,180)."""
+    rs = np.random.RandomState(seed + 29)
+    return rs.standard_normal((S + 1, B, n_mels, T)).astype(F32)
+
+
+def synthetic_edit_batch(seed: int, B: int, T: int, n_mels: int = 80, vocab: int = 80, frames_per_phone: int = 8):
+    """Synthetic (text-token, mel-frame) editing batch of SURVEY.md §8d: uniform 8 frames/phone alignment,
+    log-mel reference in [-6, 1.5], a contiguous 30 % phone span masked for re-synthesis."""
+    rs = np.random.RandomState(seed + 41)
+    Tt = max(T // frames_per_phone, 1)
+    txt = rs.randint(3, vocab, size=(B, Tt)).astype(np.int64)
+    mel2ph = (np.arange(T)[None, :] // frames_per_phone + 1).clip(max=Tt).repeat(B, 0).astype(np.int64)
+    ref = np.clip(rs.standard_normal((B, T, n_mels)) * 1.5 - 3.0, -6.0, 1.5).astype(F32)
+    mask = np.zeros((B, T), dtype=F32)
+    span = max(int(round(0.3 * Tt)), 1)
+    for b in range(B):
+        s = rs.randint(0, Tt - span + 1)
+        ph = mel2ph[b]
+        mask[b] = ((ph > s) & (ph <= s + span)).astype(F32)
+    f0 = rs.uniform(6.5, 8.5, (B, T)).astype(F32)
+    uv = (rs.uniform(size=(B, T)) < 0.3).astype(F32)
+    spk = (rs.standard_normal((B, 256)) / 16).astype(F32)
+    return dict(txt_tokens=txt, mel2ph=mel2ph, ref_mels=ref, time_mel_masks=mask, f0=f0, uv=uv, spk_embed=spk)
