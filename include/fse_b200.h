@@ -145,6 +145,14 @@ int fse_vocoder_forward(fse_vocoder* h, const float* mel, float* wav, int32_t B,
 int fse_vocoder_forward_host(fse_vocoder* h, const float* mel, float* wav, int32_t B, int32_t T);
 int64_t fse_vocoder_last_launches(const fse_vocoder* h);
 
+/* --- test hook --------------------------------------------------------------------------------
+ * The bare conv-as-shifted-GEMM primitive with a store-only epilogue (tests/test_gpu_conv_gemm.py):
+ *   out[(b,t), n] = sum_{tap,c} A0[b, t+offs[tap], c] * W[n, tap*ceil(C0/KB)*KB + c]
+ * A0 [B,T,C0] bf16 device, W [N, ntaps*ceil(C0/KB)*KB] bf16 device (zero padded), out [B*T, N] fp32.
+ * mode is FSE_MODE_TC_BF16 or FSE_MODE_SIMT_BF16. */
+int fse_debug_conv_gemm(int32_t mode, const void* A0, const void* W, float* out, int32_t B, int32_t T, int32_t C0,
+                        int32_t ntaps, const int32_t* offs, int32_t N, int32_t BN, int32_t KB, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
