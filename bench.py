@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: FluentSpeech 100-step spec_denoiser sampling
++ HiFi-GAN V1 forward on synthetic (cond, mel) batches of 32 utterances x 1024 frames per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     (CPU arm: the path's torch CPU port on host cores)
+
+One "step" = one pass of the hot path over one batch: S=100 reverse-diffusion iterations of the DiffNet
+denoiser (43 kernels each) followed by the vocoder forward (79 kernels).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR, HOP = 22050, 256
+WORKLOAD = "FluentSpeech 100-step sampling + HiFi-GAN V1, B=32 x T=1024 per GPU (BASELINE configs[1]+vocoder; configs[2] at 8 GPUs)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
+    ap.add_argument("--frames", type=int, default=1024)
+    ap.add_argument("--timesteps", type=int, default=100)
+    ap.add_argument("--mode", default="tc_bf16", choices=["tc_bf16", "simt_f32", "simt_bf16"])
+    ap.add_argument("--no-vocoder", action="store_true")
+    ap.add_argument("--no-kernel-timing", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_sustained": d.get("bf16_tflops_sustained", 1400.0), "bf16_burst": d.get("bf16_tflops", 1590.0),
+                "hbm": d.get("hbm_gbs", 6650.0), "src": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------ CPU arm (torch port of the reference path)
+def cpu_sample(timesteps, full_frames, threads=None):
+    """Bounded CPU sample of the same workload: B=2 x T=1024 for 2 diffusion iterations + vocoder on
+    B=1 x T=128, extrapolated to frames/s of the full (S-step + vocoder) pipeline."""
+    import torch
+    from oracle import fluentspeech_oracle as O
+    from oracle import torch_port as P
+    from speech_editing_toolkit_b200 import schedule, synth
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p = P.to_torch(synth.denoiser_state_dict(1234))
+    hp = P.to_torch(synth.hifigan_state_dict(1234))
+    sched = {k: torch.from_numpy(v) for k, v in schedule.diffusion_buffers(timesteps).items()}
+    B, T, it = 2, 1024, 2
+    cond = torch.from_numpy(synth.synthetic_cond(1, B, T)).transpose(1, 2).contiguous()
+    P.sample_loop(p, sched, cond, timesteps, steps=1)                  # warm-up
+    t0 = time.perf_counter()
+    P.sample_loop(p, sched, cond, timesteps, steps=it)
+    t_fs = (time.perf_counter() - t0) / (B * T * it)                   # seconds per frame-iteration
+    Bv, Tv = 1, 128
+    mel = torch.randn(Bv, 80, Tv) - 3
+    P.hifigan_forward(hp, O.HIFIGAN_V1, mel[:, :, :32])
+    t0 = time.perf_counter()
+    P.hifigan_forward(hp, O.HIFIGAN_V1, mel)
+    t_voc = (time.perf_counter() - t0) / (Bv * Tv)
+    sec_per_frame = t_fs * timesteps + t_voc
+    return {"value": 1.0 / sec_per_frame, "unit": "mel-frames/s", "cores": cores, "kind": "port",
+            "sample": f"torch CPU port (oracle/torch_port.py): denoiser B=2xT=1024 for 2 of {timesteps} iterations "
+                      f"({t_fs * 1e6:.2f} us/frame-iteration) + HiFi-GAN B=1xT=128 ({t_voc * 1e6:.1f} us/frame), extrapolated",
+            "sec_per_frame_denoiser_iter": t_fs, "sec_per_frame_vocoder": t_voc}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(args.warmup and 1):
+        cpu_sample(args.timesteps, args.batch * args.frames)
+    t0 = time.perf_counter()
+    for _ in range(max(args.steps, 1)):
+        vals.append(cpu_sample(args.timesteps, args.batch * args.frames))
+    wall = time.perf_counter() - t0
+    best = max(vals, key=lambda v: v["value"])
+    v = float(np.mean([x["value"] for x in vals]))
+    frames = args.batch * args.frames
+    line = {"impl": "reference", "metric": "mel-frames/sec (100-step sampling + HiFi-GAN)", "value": v, "unit": "mel-frames/s",
+            "rtf": (1.0 / v) / (HOP / SR), "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": frames / v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "timesteps": args.timesteps,
+                                                             "note": "CPU arm: each step is a bounded sample, extrapolated; ms_per_step is the extrapolated full-batch time"},
+            "cpu_baseline": {k: best[k] for k in ("cores", "kind", "sample")} | {"value": v, "unit": "mel-frames/s"},
+            "e2e": {"value": v, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": wall}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from speech_editing_toolkit_b200 import schedule, synth
+    from speech_editing_toolkit_b200.engine import Denoiser, Vocoder
+
+    B, T, S = args.batch, args.frames, args.timesteps
+    den = Denoiser(mode=args.mode)
+    den.load_state_dict(synth.denoiser_state_dict(1234))
+    buf = schedule.diffusion_buffers(S)
+    den.set_schedule(buf["posterior_mean_coef1"], buf["posterior_mean_coef2"], buf["posterior_log_variance_clipped"])
+    voc = None
+    if not args.no_vocoder:
+        voc = Vocoder(mode=args.mode)
+        voc.load_state_dict(synth.hifigan_state_dict(1234))
+
+    # synthetic batch of this rank's shard (utterances rank*B .. rank*B+B-1)
+    batch = synth.synthetic_edit_batch(1000 + rank, B, T)
+    cond_h = torch.from_numpy(synth.synthetic_cond(1000 + rank, B, T)).pin_memory()
+    ref_h = torch.from_numpy(batch["ref_mels"]).pin_memory()
+    mask_h = torch.from_numpy(batch["time_mel_masks"]).pin_memory()
+    cond_d, ref_d, mask_d = cond_h.to(dev), ref_h.to(dev), mask_h.to(dev)
+    gathered = torch.empty(world * B, T, 80, device=dev) if world > 1 else None
+    mel_h = torch.empty(B, T, 80).pin_memory()
+    wav_h = torch.empty(B, T * HOP).pin_memory()
+
+    def step_resident(i):
+        mel = den.sample(cond_d, None, seed=i, ref_mel=ref_d, mask=mask_d)
+        wav = voc.forward(mel) if voc else None
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, mel)       # the one collective of the path
+        return mel, wav
+
+    def step_e2e(i):
+        c = cond_h.to(dev, non_blocking=True); r = ref_h.to(dev, non_blocking=True); m = mask_h.to(dev, non_blocking=True)
+        mel = den.sample(c, None, seed=i, ref_mel=r, mask=m)
+        mel_h.copy_(mel, non_blocking=True)
+        if voc:
+            wav_h.copy_(voc.forward(mel), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, K, profile=False):
+        barrier()
+        if profile:
+            den.profile(True)
+            if voc:
+                voc.profile(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    clk = ClockSampler(local)
+    clk.start()
+    use_prof = not args.no_kernel_timing
+    ms_total = timed(step_resident, args.steps, profile=use_prof)
+    clocks = clk.stop()
+    prof_d = den.profile_read() if use_prof else None
+    prof_v = voc.profile_read() if (use_prof and voc) else None
+    if use_prof:
+        den.profile(False)
+        if voc:
+            voc.profile(False)
+    launches = den.last_launches + (voc.last_launches if voc else 0)
+    ms_step = ms_total / args.steps
+    frames_total = world * B * T
+    value = frames_total / (ms_step / 1e3)
+
+    # a second timed pass without per-kernel events, to show what the events cost
+    ms_noprof = timed(step_resident, args.steps, profile=False) / args.steps if use_prof else ms_step
+
+    e2e = None
+    if not args.no_e2e:
+        step_e2e(0)
+        ms_e2e = timed(step_e2e, args.steps) / args.steps
+        h2d = cond_h.numel() * 4 + ref_h.numel() * 4 + mask_h.numel() * 4
+        d2h = mel_h.numel() * 4 + (wav_h.numel() * 4 if voc else 0)
+        e2e = {"value": frames_total / (ms_e2e / 1e3), "unit": "mel-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ms_e2e, "api": "Denoiser.sample + Vocoder.forward (ctypes -> fse_sample / fse_vocoder_forward), pinned host in/out"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    roofline = None
+    if prof_d:
+        g_ms, g_n = prof_d["gate_gemm"]
+        flops = 2.0 * B * T * 512 * 960                      # algorithmic: 0.983 MFLOP/frame (k=3 conv 512x768 + cond 512x192)
+        ach = flops / (g_ms / g_n * 1e-3) / 1e12 if g_n else 0.0
+        roofline = {"kernel": "conv_gemm_tc_kernel<EpiGate> (dilated k=3 conv + conditioner 1x1 + gate)", "bound": "tensor",
+                    "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
+                    "peak_source": pk["src"] + ", sustained bf16", "traffic": None,
+                    "avg_launch_us": g_ms / g_n * 1e3 if g_n else None, "launches_timed": g_n,
+                    "flops_per_launch": flops}
+    breakdown = {}
+    if prof_d:
+        breakdown["denoiser_ms_per_step"] = {k: v[0] / args.steps for k, v in prof_d.items()}
+    if prof_v:
+        breakdown["vocoder_ms_per_step"] = {k: v[0] / args.steps for k, v in prof_v.items()}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu = cpu_sample(S, B * T)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    audio_s = frames_total * HOP / SR
+    line = {
+        "metric": "mel-frames/sec (100-step sampling + HiFi-GAN)", "value": value, "unit": "mel-frames/s",
+        "rtf": (ms_step / 1e3) / audio_s, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "ms_per_step_without_kernel_events": ms_noprof, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if args.mode != "simt_f32" else "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD if (B, T, S) == (32, 1024, 100) and voc else f"custom B={B} T={T} S={S} vocoder={bool(voc)}",
+                   "batch_per_gpu": B, "frames": T, "timesteps": S, "vocoder": "HiFi-GAN V1 (assumed config, SURVEY fact 4)" if voc else None,
+                   "mode": args.mode, "noise": "in-kernel Philox4x32-10", "weights": "seeded random (synth.py), reference state_dict layout",
+                   "l2": "per-step working set (activations + vocoder workspace, >5 GB) exceeds the 126 MB L2; no explicit flush",
+                   "parallelism": f"batch-sharded x{world}, one all_gather of mels per step" if world > 1 else "single GPU"},
+        "gpu_launches": int(launches * args.steps), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
+        "breakdown": breakdown,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -145,6 +145,17 @@ int fse_vocoder_forward(fse_vocoder* h, const float* mel, float* wav, int32_t B,
 int fse_vocoder_forward_host(fse_vocoder* h, const float* mel, float* wav, int32_t B, int32_t T);
 int64_t fse_vocoder_last_launches(const fse_vocoder* h);
 
+/* --- kernel timing (opt-in) -------------------------------------------------------------------
+ * When enabled, every kernel the handle launches is bracketed by CUDA events on the launch stream;
+ * *_profile_read waits for them and returns the summed device time (ms) and launch count per kind
+ * since enabling (arrays of 8).  Denoiser kinds: 0 input projection, 1 gated dilated-conv GEMM,
+ * 2 residual/skip GEMM, 3 skip projection, 4 output projection + posterior.  Vocoder kinds: 0 conv_pre,
+ * 1 transposed conv, 2 ResBlock convs1, 3 ResBlock convs2 (+residual), 4 conv_post + tanh. */
+int fse_denoiser_profile(fse_denoiser* h, int32_t enable);
+int fse_denoiser_profile_read(fse_denoiser* h, double* ms_by_kind, int64_t* launches_by_kind);
+int fse_vocoder_profile(fse_vocoder* h, int32_t enable);
+int fse_vocoder_profile_read(fse_vocoder* h, double* ms_by_kind, int64_t* launches_by_kind);
+
 /* --- test hook --------------------------------------------------------------------------------
  * The bare conv-as-shifted-GEMM primitive with a store-only epilogue (tests/test_gpu_conv_gemm.py):
  *   out[(b,t), n] = sum_{tap,c} A0[b, t+offs[tap], c] * W[n, tap*ceil(C0/KB)*KB + c]

@@ -58,6 +58,10 @@ SIGNATURES = {
     "fse_vocoder_forward": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "fse_vocoder_forward_host": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32]),
     "fse_vocoder_last_launches": (C.c_int64, [_P]),
+    "fse_denoiser_profile": (C.c_int, [_P, C.c_int32]),
+    "fse_denoiser_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "fse_vocoder_profile": (C.c_int, [_P, C.c_int32]),
+    "fse_vocoder_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "fse_debug_conv_gemm": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, _P]),
 }

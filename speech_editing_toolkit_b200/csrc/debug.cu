@@ -32,5 +32,5 @@ extern "C" int fse_debug_conv_gemm(int32_t mode, const void* A0, const void* W, 
     op.mA0 = &mA; op.mW = &mW;
   }
   EpiStore epi{out, N, T};
-  return run_conv_gemm<__nv_bfloat16>(mode, p, op, epi, static_cast<cudaStream_t>(stream), nullptr);
+  return run_conv_gemm<__nv_bfloat16>(mode, p, op, epi, static_cast<cudaStream_t>(stream), LaunchCtx{});
 }

@@ -190,6 +190,7 @@ struct fse_denoiser {
     CUtensorMap m_xb{}, m_hb{}, m_cond{}, m_u{}, m_sb{}, m_rb{};
   } plan;
   long long launches = 0;
+  Profiler prof;
   // scratch owned for the *_host convenience call
   void* host_ws = nullptr; size_t host_ws_bytes = 0;
 };
@@ -286,7 +287,7 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
     GemmOperands op; op.A0 = w.xb; op.W = h->W_in; op.mA0 = &h->plan.m_xb; op.mW = &h->mW_in; op.BN = 256;
     if (C % 256 != 0) op.BN = C % 128 == 0 ? 128 : 64;
     EpiIn<TOp> epi{h->b_in, w.h, static_cast<TOp*>(w.hb), C, T};
-    FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, &h->launches)));
+    FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 0})));
   }
   const int bn2 = (2 * C) % 256 == 0 ? 256 : 128;
   for (int l = 0; l < L; ++l) {
@@ -301,10 +302,10 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
       const long long bstride = static_cast<long long>(tidx_bstride) * L * 3 * 2 * C;
       if (tc) {
         EpiGate<TOp, true> epi{db, bstride, static_cast<TOp*>(w.u), 2 * C, T, dil};
-        FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, &h->launches)));
+        FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 1})));
       } else {
         EpiGate<TOp, false> epi{db, bstride, static_cast<TOp*>(w.u), 2 * C, T, dil};
-        FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, &h->launches)));
+        FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 1})));
       }
     }
     {
@@ -314,7 +315,7 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
       op.mA0 = &h->plan.m_u; op.mW = tc ? &h->mW2[l] : nullptr; op.BN = bn2;
       EpiRes<TOp> epi{h->b2 + static_cast<size_t>(l) * 2 * C, w.h, static_cast<TOp*>(w.hb), w.S, static_cast<TOp*>(w.sb),
                       C, T, l == 0, l == L - 1, sqrtf(static_cast<float>(L))};
-      FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, &h->launches)));
+      FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 2})));
     }
   }
   {
@@ -322,14 +323,14 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
     GemmOperands op; op.A0 = w.sb; op.W = h->W_skip; op.mA0 = &h->plan.m_sb; op.mW = &h->mW_skip;
     op.BN = C % 256 == 0 ? 256 : (C % 128 == 0 ? 128 : 64);
     EpiSkip<TOp> epi{h->b_skip, static_cast<TOp*>(w.rb), C, T};
-    FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, &h->launches)));
+    FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 3})));
   }
   {
     ConvGemmParams p = make_params(B, T, T, C, 1, &zero, 0, M, 64);
     GemmOperands op; op.A0 = w.rb; op.W = h->W_out; op.mA0 = &h->plan.m_rb; op.mW = &h->mW_out; op.BN = M;
     EpiOut<TOp> epi{h->b_out, M, T, out.mode, out.x_t, out.x_out, out.write_xb ? static_cast<TOp*>(w.xb) : nullptr,
                     out.noise, out.seed, out.step, out.c1, out.c2, out.sigma, out.mel_out, out.ref, out.mask};
-    FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, &h->launches)));
+    FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 4})));
   }
   return FSE_OK;
 }
@@ -636,5 +637,15 @@ int fse_sample_host(fse_denoiser* h, const float* cond, const float* noise, uint
 }
 
 int64_t fse_denoiser_last_launches(const fse_denoiser* h) { return h ? h->launches : 0; }
+
+int fse_denoiser_profile(fse_denoiser* h, int32_t enable) {
+  if (!h) return fail(FSE_EINVAL, "null handle");
+  h->prof.enable(enable != 0);
+  return FSE_OK;
+}
+int fse_denoiser_profile_read(fse_denoiser* h, double* ms_by_kind, int64_t* launches_by_kind) {
+  if (!h || !ms_by_kind || !launches_by_kind) return fail(FSE_EINVAL, "null argument");
+  return h->prof.read(ms_by_kind, launches_by_kind);
+}
 
 }  // extern "C"

@@ -136,6 +136,54 @@ inline int make_map_w(CUtensorMap* m, const void* ptr, int Kp, int N, int KB, in
   return FSE_OK;
 }
 
+// ------------------------------------------------------------------ per-kind kernel timing (opt-in)
+// CUDA events recorded on the launch stream around each kernel, summed per kernel kind; used by
+// bench.py for the roofline object (B200_PROFILING.md: time on the launching stream).
+constexpr int kProfKinds = 8;
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> kind;
+  size_t used = 0;
+  void enable(bool e) {
+    on = e;
+    used = 0;
+    kind.clear();
+  }
+  void begin(int k, cudaStream_t st) {
+    if (!on) return;
+    if (ev.size() < 2 * (used + 1)) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { on = false; return; }
+      ev.push_back(a); ev.push_back(b);
+    }
+    kind.push_back(k);
+    cudaEventRecord(ev[2 * used], st);
+  }
+  void end(cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(ev[2 * used + 1], st);
+    ++used;
+  }
+  int read(double* ms, int64_t* counts) {
+    for (int i = 0; i < kProfKinds; ++i) { ms[i] = 0.0; counts[i] = 0; }
+    for (size_t i = 0; i < used; ++i) {
+      FSE_CUDA(cudaEventSynchronize(ev[2 * i + 1]));
+      float t = 0.f;
+      FSE_CUDA(cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]));
+      const int k = kind[i] < kProfKinds ? kind[i] : kProfKinds - 1;
+      ms[k] += t; counts[k] += 1;
+    }
+    return FSE_OK;
+  }
+  ~Profiler() { for (auto e : ev) cudaEventDestroy(e); }
+};
+struct LaunchCtx {
+  long long* launches = nullptr;
+  Profiler* prof = nullptr;
+  int kind = 0;
+};
+
 // ------------------------------------------------------------------ conv_gemm launcher
 struct GemmOperands {
   const void* A0 = nullptr;   // [B, Tsrc, C0] operand type
@@ -185,9 +233,7 @@ inline int launch_tc(const ConvGemmParams& p, const GemmOperands& op, const Epi&
 
 // mode: FSE_MODE_*.  TOp = operand element type of this handle.
 template <typename TOp, class Epi>
-inline int run_conv_gemm(int mode, const ConvGemmParams& p, const GemmOperands& op, const Epi& epi, cudaStream_t st,
-                         long long* launches) {
-  if (launches) ++*launches;
+inline int run_conv_gemm_impl(int mode, const ConvGemmParams& p, const GemmOperands& op, const Epi& epi, cudaStream_t st) {
   if constexpr (std::is_same<TOp, __nv_bfloat16>::value) {
     if (mode == FSE_MODE_TC_BF16) {
       if (p.N % op.BN != 0 || op.BN % 16 != 0 || op.BN > 256) return fail(FSE_EINVAL, "conv_gemm: bad BN %d for N %d", op.BN, p.N);
@@ -207,6 +253,16 @@ inline int run_conv_gemm(int mode, const ConvGemmParams& p, const GemmOperands& 
                                                        static_cast<const TOp*>(op.W), epi);
   FSE_CUDA(cudaGetLastError());
   return FSE_OK;
+}
+
+template <typename TOp, class Epi>
+inline int run_conv_gemm(int mode, const ConvGemmParams& p, const GemmOperands& op, const Epi& epi, cudaStream_t st,
+                         const LaunchCtx& ctx) {
+  if (ctx.launches) ++*ctx.launches;
+  if (ctx.prof) ctx.prof->begin(ctx.kind, st);
+  const int rc = run_conv_gemm_impl<TOp>(mode, p, op, epi, st);
+  if (ctx.prof) ctx.prof->end(st);
+  return rc;
 }
 
 }  // namespace fse

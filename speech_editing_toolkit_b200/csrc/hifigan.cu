@@ -158,6 +158,7 @@ struct fse_vocoder {
   float* post_w = nullptr; float post_b = 0.f; int post_k = 7;
   struct Plan { const void* ws = nullptr; int B = 0, T = 0; std::vector<CUtensorMap> maps; } plan;
   long long launches = 0;
+  Profiler prof;
   void* host_ws = nullptr; size_t host_ws_bytes = 0;
 };
 
@@ -270,10 +271,10 @@ int pack_up(fse_vocoder* h, const TensorTable& tt, const std::string& name, int 
 }
 
 template <typename TOp, class Epi>
-int run_conv(fse_vocoder* h, const ConvW& cw, const void* A, const CUtensorMap* mA, int B, int Trows, int Tsrc, const Epi& epi, cudaStream_t st) {
+int run_conv(fse_vocoder* h, const ConvW& cw, const void* A, const CUtensorMap* mA, int B, int Trows, int Tsrc, const Epi& epi, cudaStream_t st, int kind) {
   ConvGemmParams p = make_params(B, Trows, Tsrc, cw.Cin, cw.ntaps, cw.offs, 0, cw.N, cw.KB);
   GemmOperands op; op.A0 = A; op.W = cw.W; op.mA0 = mA; op.mW = &cw.map; op.BN = cw.BN;
-  return run_conv_gemm<TOp>(h->cfg.mode, p, op, epi, st, &h->launches);
+  return run_conv_gemm<TOp>(h->cfg.mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, kind});
 }
 
 template <typename TOp>
@@ -310,7 +311,7 @@ int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, voi
   }
   {  // conv_pre + leaky_relu(0.1) of stage 0 (hifigan.py:127-129)
     EpiAct<TOp> epi{h->pre.bias, static_cast<TOp*>(w.ua), h->pre.N, T, 0.1f};
-    FSE_TRY((run_conv<TOp>(h, h->pre, mel_op, M(0), B, T, T, epi, st)));
+    FSE_TRY((run_conv<TOp>(h, h->pre, mel_op, M(0), B, T, T, epi, st, 0)));
   }
   int Tin = T;
   for (int i = 0; i < nu; ++i) {
@@ -318,7 +319,7 @@ int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, voi
     const int Cout = stage_channels(h, i), Tout = Tin * u;
     {
       EpiUp<TOp> epi{h->ups[i].bias, w.x, static_cast<TOp*>(w.xa), Cout, Tout, u, pad};
-      FSE_TRY((run_conv<TOp>(h, h->ups[i], w.ua, M(2 + 4 * i), B, Tin + 1, Tin, epi, st)));
+      FSE_TRY((run_conv<TOp>(h, h->ups[i], w.ua, M(2 + 4 * i), B, Tin + 1, Tin, epi, st, 1)));
     }
     const bool last_stage = i == nu - 1;
     for (int j = 0; j < nk; ++j) {
@@ -327,7 +328,7 @@ int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, voi
         const ConvW& c = h->c2[(i * nk + j) * 3 + m];
         {
           EpiAct<TOp> epi{a.bias, static_cast<TOp*>(w.tmp), Cout, Tout, 0.1f};
-          FSE_TRY((run_conv<TOp>(h, a, m == 0 ? w.xa : w.ya, M(2 + 4 * i + (m == 0 ? 1 : 2)), B, Tout, Tout, epi, st)));
+          FSE_TRY((run_conv<TOp>(h, a, m == 0 ? w.xa : w.ya, M(2 + 4 * i + (m == 0 ? 1 : 2)), B, Tout, Tout, epi, st, 2)));
         }
         {
           EpiResAdd<TOp> epi{};
@@ -337,14 +338,16 @@ int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, voi
           epi.kind = m < 2 ? 0 : (nk == 1 ? 3 : (j == 0 ? 1 : (j == nk - 1 ? 3 : 2)));
           epi.num_kernels = static_cast<float>(nk);
           epi.slope_next = last_stage ? 0.01f : 0.1f;   // F.leaky_relu default slope before conv_post (hifigan.py:138)
-          FSE_TRY((run_conv<TOp>(h, c, w.tmp, M(2 + 4 * i + 3), B, Tout, Tout, epi, st)));
+          FSE_TRY((run_conv<TOp>(h, c, w.tmp, M(2 + 4 * i + 3), B, Tout, Tout, epi, st, 3)));
         }
       }
     }
     Tin = Tout;
   }
   const int Cl = stage_channels(h, nu - 1);
+  h->prof.begin(4, st);
   conv_post_kernel<<<dim3((Tin + 255) / 256, B), 256, h->post_k * Cl * sizeof(float), st>>>(w.xs, h->post_w, h->post_b, wav, Cl, Tin, h->post_k);
+  h->prof.end(st);
   FSE_CUDA(cudaGetLastError());
   ++h->launches;
   return FSE_OK;
@@ -474,5 +477,15 @@ int fse_vocoder_forward_host(fse_vocoder* h, const float* mel, float* wav, int32
 }
 
 int64_t fse_vocoder_last_launches(const fse_vocoder* h) { return h ? h->launches : 0; }
+
+int fse_vocoder_profile(fse_vocoder* h, int32_t enable) {
+  if (!h) return fail(FSE_EINVAL, "null handle");
+  h->prof.enable(enable != 0);
+  return FSE_OK;
+}
+int fse_vocoder_profile_read(fse_vocoder* h, double* ms_by_kind, int64_t* launches_by_kind) {
+  if (!h || !ms_by_kind || !launches_by_kind) return fail(FSE_EINVAL, "null argument");
+  return h->prof.read(ms_by_kind, launches_by_kind);
+}
 
 }  // extern "C"

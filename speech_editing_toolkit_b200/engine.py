@@ -98,6 +98,16 @@ class Denoiser:
     def last_launches(self) -> int:
         return int(_lib.lib().fse_denoiser_last_launches(self._h))
 
+    KINDS = ["input_proj", "gate_gemm", "res_gemm", "skip_proj", "out_proj_posterior"]
+
+    def profile(self, enable: bool):
+        check(_lib.lib().fse_denoiser_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        ms = (C.c_double * 8)(); cnt = (C.c_int64 * 8)()
+        check(_lib.lib().fse_denoiser_profile_read(self._h, ms, cnt))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(self.KINDS)}
+
     def denoise_step(self, x_t: torch.Tensor, cond: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
         """x_t[B,M,T] fp32, cond[B,T,H] fp32 (physical layout), t[B] int64 -> x0[B,M,T]."""
         _need_cuda(x_t, cond, t)
@@ -202,6 +212,16 @@ class Vocoder:
     @property
     def last_launches(self) -> int:
         return int(_lib.lib().fse_vocoder_last_launches(self._h))
+
+    KINDS = ["conv_pre", "upsample", "res_conv1", "res_conv2", "conv_post"]
+
+    def profile(self, enable: bool):
+        check(_lib.lib().fse_vocoder_profile(self._h, int(enable)))
+
+    def profile_read(self):
+        ms = (C.c_double * 8)(); cnt = (C.c_int64 * 8)()
+        check(_lib.lib().fse_vocoder_profile_read(self._h, ms, cnt))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(self.KINDS)}
 
     def forward(self, mel: torch.Tensor) -> torch.Tensor:
         """mel[B,T,M] fp32 cuda -> wav[B,T*hop]."""
