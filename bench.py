@@ -104,13 +104,29 @@ def cpu_sample(timesteps, full_frames, threads=None):
     from oracle import fluentspeech_oracle as O
     from oracle import torch_port as P
     from speech_editing_toolkit_b200 import schedule, synth
-    cores = threads or os.cpu_count() or 1
-    torch.set_num_threads(cores)
     p = P.to_torch(synth.denoiser_state_dict(1234))
     hp = P.to_torch(synth.hifigan_state_dict(1234))
     sched = {k: torch.from_numpy(v) for k, v in schedule.diffusion_buffers(timesteps).items()}
     B, T, it = 2, 1024, 2
     cond = torch.from_numpy(synth.synthetic_cond(1, B, T)).transpose(1, 2).contiguous()
+    if threads is None:
+        # "all the host threads it can use": the box may expose more logical CPUs than the container's quota, and
+        # oversubscribed OpenMP teams collapse, so probe a few team sizes on one iteration and keep the fastest.
+        avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        best = None
+        for n in sorted({avail, max(avail // 2, 1), 32, 16, 8}):
+            if n > avail:
+                continue
+            torch.set_num_threads(n)
+            P.sample_loop(p, sched, cond, timesteps, steps=1)
+            t0 = time.perf_counter()
+            P.sample_loop(p, sched, cond, timesteps, steps=1)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, n)
+        threads = best[1]
+    cores = threads
+    torch.set_num_threads(cores)
     P.sample_loop(p, sched, cond, timesteps, steps=1)                  # warm-up
     t0 = time.perf_counter()
     P.sample_loop(p, sched, cond, timesteps, steps=it)

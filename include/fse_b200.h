@@ -162,7 +162,8 @@ int fse_vocoder_profile_read(fse_vocoder* h, double* ms_by_kind, int64_t* launch
  * A0 [B,T,C0] bf16 device, W [N, ntaps*ceil(C0/KB)*KB] bf16 device (zero padded), out [B*T, N] fp32.
  * mode is FSE_MODE_TC_BF16 or FSE_MODE_SIMT_BF16. */
 int fse_debug_conv_gemm(int32_t mode, const void* A0, const void* W, float* out, int32_t B, int32_t T, int32_t C0,
-                        int32_t ntaps, const int32_t* offs, int32_t N, int32_t BN, int32_t KB, void* stream);
+                        int32_t ntaps, const int32_t* offs, int32_t N, int32_t BN, int32_t KB, void* stream,
+                        int64_t* dbg_stamps /* device [16] or NULL: clock64 phase stamps of CTA 0 */);
 
 #ifdef __cplusplus
 }

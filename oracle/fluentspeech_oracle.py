@@ -161,7 +161,7 @@ def diffnet_forward(p: Dict[str, np.ndarray], x: np.ndarray, t: np.ndarray, cond
     temb = linear(mish(linear(e, p["mlp.0.weight"], p["mlp.0.bias"])), p["mlp.2.weight"], p["mlp.2.bias"])  # :122
     skip_sum = np.zeros_like(h)
     layers = []
-    inv_sqrt2 = F32(1.0 / math.sqrt(2.0))
+    us = []
     for n in range(n_layers):
         pre = f"residual_layers.{n}."
         dil = 2 ** (n % dilation_cycle_length)                                   # :103
@@ -183,12 +183,28 @@ def diffnet_forward(p: Dict[str, np.ndarray], x: np.ndarray, t: np.ndarray, cond
         u = (sigmoid(gate) * np.tanh(filt)).astype(F32)                          # :77
         o = conv1d(u, p[pre + "output_projection.weight"], p[pre + "output_projection.bias"], gemm_dtype=gemm_dtype)
         res, skip = o[:, :C], o[:, C:]                                           # :80
-        h = ((h + res) * inv_sqrt2).astype(F32)                                  # :81
+        h = ((h + res) / F32(math.sqrt(2.0))).astype(F32)                        # :81
         skip_sum = (skip_sum + skip).astype(F32)
+        us.append(u)
         if return_layers:
             layers.append((h.copy(), skip.copy()))
-    s = (skip_sum / F32(math.sqrt(n_layers))).astype(F32)                        # :128
-    r = np.maximum(conv1d(s, p["skip_projection.weight"], p["skip_projection.bias"], gemm_dtype=gemm_dtype), 0)
+    if gemm_dtype == "bf16":
+        # device contract: skip_projection(sum_l skip_l / sqrt(L)) is ONE contraction over the concatenated
+        # gate outputs with the folded weight W_skip W_op,l[C:] / sqrt(L), rounded to bf16 after folding
+        inv = 1.0 / math.sqrt(n_layers)
+        Ws = p["skip_projection.weight"][:, :, 0].astype(np.float64)
+        acc = np.zeros_like(h)
+        bsum = np.zeros((C,), dtype=np.float64)
+        for n in range(n_layers):
+            Wo = p[f"residual_layers.{n}.output_projection.weight"][C:, :, 0].astype(np.float64)
+            Wc = (Ws @ Wo * inv).astype(F32)
+            acc += conv1d(us[n], Wc[:, :, None], None, gemm_dtype="bf16")
+            bsum += p[f"residual_layers.{n}.output_projection.bias"][C:]
+        bc = (p["skip_projection.bias"] + (Ws @ bsum) * inv).astype(F32)
+        r = np.maximum(acc + bc[None, :, None], 0)
+    else:
+        s = (skip_sum / F32(math.sqrt(n_layers))).astype(F32)                    # :128
+        r = np.maximum(conv1d(s, p["skip_projection.weight"], p["skip_projection.bias"]), 0)
     x0 = conv1d(r.astype(F32), p["output_projection.weight"], p["output_projection.bias"], gemm_dtype=gemm_dtype)
     if return_layers:
         return x0, layers

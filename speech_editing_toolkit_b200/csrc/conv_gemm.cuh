@@ -23,10 +23,13 @@ namespace fse {
 constexpr int kMaxTaps = 12;
 
 struct ConvGemmParams {
-  int B;       // items
+  int B;       // items processed by this launch
+  int b_off;   // index of the first item (rows / TMA batch coordinate are b_off + local index)
   int Trows;   // output rows (frames) per item; tiles never straddle items
   int Tsrc;    // frames per item of the sources (SIMT bounds check; TC relies on TMA OOB fill)
   int C0, C1;  // channels of source 0 (with taps) and source 1 (single tap, offset 0; 0 = unused)
+  int c_off0;  // first channel of source 0 inside its rows (a [.., ld0]-wide buffer holding several tensors)
+  int ld0;     // row stride of source 0 in elements (>= c_off0 + C0)
   int ntaps;
   int tap_off[kMaxTaps];
   int KB;      // k-block width in channels: 64 (128B swizzle) or 32 (64B swizzle)
@@ -34,6 +37,7 @@ struct ConvGemmParams {
   int nkb1;    // k-blocks for source 1
   int N;       // output columns
   int Kp;      // padded K of the packed weight = (ntaps*nkb0 + nkb1)*KB
+  long long* dbg;  // optional [32] clock64 phase stamps of CTA 0 (test hook), else null
 };
 
 // ------------------------------------------------------------------------------------------
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(ConvGemmParams p, c
   __shared__ float As[16][68];
   __shared__ float Ws[16][68];
   const int tiles_per_item = (p.Trows + 63) / 64;
-  const int b = blockIdx.x / tiles_per_item;
+  const int b = p.b_off + blockIdx.x / tiles_per_item;
   const int t0 = (blockIdx.x % tiles_per_item) * 64;
   const int n0 = blockIdx.y * 64;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -103,19 +107,19 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(ConvGemmParams p, c
   for (int j = 0; j < nk16; ++j) {
     const int kb = j / sub;
     const TOp* src;
-    int C, cb, off;
+    int C, cb, off, ld;
     if (kb < nkb_src0) {
       const int tap = kb / p.nkb0;
-      src = A0; C = p.C0; off = p.tap_off[tap];
+      src = A0 + p.c_off0; C = p.C0; off = p.tap_off[tap]; ld = p.ld0;
       cb = (kb % p.nkb0) * p.KB + (j % sub) * 16;
     } else {
-      src = A1; C = p.C1; off = 0;
+      src = A1; C = p.C1; off = 0; ld = p.C1;
       cb = (kb - nkb_src0) * p.KB + (j % sub) * 16;
     }
     {
       const int tt = t0 + lrow + off;
       const bool ok = (tt >= 0) && (tt < p.Tsrc);
-      const TOp* rp = src + (static_cast<size_t>(b) * p.Tsrc + (ok ? tt : 0)) * C;
+      const TOp* rp = src + (static_cast<size_t>(b) * p.Tsrc + (ok ? tt : 0)) * ld;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int ch = cb + lk + q;
@@ -145,22 +149,33 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(ConvGemmParams p, c
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int t = t0 + ty * 4 + i;
-      if (t < p.Trows) epi.template apply<4>(b, t, n, acc[i]);
+      if (t < p.Trows) {
+        float aux[4 * (Epi::kAux > 0 ? Epi::kAux : 1)];
+        if constexpr (Epi::kAux > 0) epi.template load_aux<4>(b, t, n, aux);
+        epi.template apply<4>(b, t, n, acc[i], aux);
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// tcgen05 back end
+// tcgen05 back end: persistent, warp-specialised, double-buffered accumulators
 // ------------------------------------------------------------------------------------------
-constexpr int kTcThreads = 192;   // warp 0: TMA, warp 1: MMA/TMEM, warps 2-5: epilogue
+//   warp 0      TMA producer: streams (A tile, W tile) k-blocks of successive output tiles through an
+//               smem ring (full/empty mbarriers)
+//   warp 1      MMA issuer + TMEM owner: tcgen05.mma into accumulator buffer (tile & 1); tcgen05.commit
+//               releases smem slots and signals acc_full
+//   warps 2..9  epilogue: tcgen05.ld the finished buffer (lane = frame, CH channels at a time), run the
+//               functor with prefetched residual operands, release the buffer (acc_empty)
+// so the epilogue of tile i overlaps the loads and MMAs of tile i+1.  One CTA per SM, grid = min(tiles, SMs).
+constexpr int kEpiWarps = 8;
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr int kTileM = 128;       // frames per tile = TMEM lanes
 
 __host__ __device__ inline int tc_b_stage_bytes(int BN, int KB) { return ((BN * KB * 2 + 1023) / 1024) * 1024; }
 __host__ __device__ inline int tc_a_stage_bytes(int KB) { return kTileM * KB * 2; }
-__host__ inline int tc_tmem_cols(int BN) { int c = 32; while (c < BN) c <<= 1; return c; }
 __host__ inline size_t tc_smem_bytes(int BN, int KB, int stages) {
-  return 1024 + static_cast<size_t>(stages) * (tc_a_stage_bytes(KB) + tc_b_stage_bytes(BN, KB)) + 8 * (2 * stages + 1) + 16;
+  return 1024 + static_cast<size_t>(stages) * (tc_a_stage_bytes(KB) + tc_b_stage_bytes(BN, KB)) + 8 * (2 * stages + 4) + 16;
 }
 
 template <int KB, int CH, class Epi>
@@ -177,19 +192,21 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   uint8_t* sB = smem + stages * A_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * B_BYTES);
   uint64_t* empty = full + stages;
-  uint64_t* tmem_full = empty + stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* acc_full = empty + stages;     // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+  long long* dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   const int tiles_per_item = (p.Trows + kTileM - 1) / kTileM;
-  const int b = blockIdx.x / tiles_per_item;
-  const int t0 = (blockIdx.x % tiles_per_item) * kTileM;
-  const int n0 = blockIdx.y * BN;
+  const int n_tiles = p.N / BN;
+  const int total_tiles = p.B * tiles_per_item * n_tiles;
   const int nkb_src0 = p.ntaps * p.nkb0;
   const int nkb = nkb_src0 + p.nkb1;
   uint32_t ncols = 32;
-  while (static_cast<int>(ncols) < BN) ncols <<= 1;
+  while (static_cast<int>(ncols) < 2 * BN) ncols <<= 1;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&mapA0);
@@ -202,7 +219,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         ptx::mbar_init(&full[s], 1);
         ptx::mbar_init(&empty[s], 1);
       }
-      ptx::mbar_init(tmem_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&acc_full[i], 1);
+        ptx::mbar_init(&acc_empty[i], kEpiWarps);
+      }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -213,66 +233,126 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const uint32_t tx_bytes = static_cast<uint32_t>(A_BYTES + BN * KB * 2);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (kb / stages) & 1;
-        ptx::mbar_wait(&empty[s], ph ^ 1u);
-        ptx::mbar_arrive_expect_tx(&full[s], tx_bytes);
-        if (kb < nkb_src0) {
-          const int tap = kb / p.nkb0;
-          ptx::tma_load_3d(sA + s * A_BYTES, &mapA0, &full[s], (kb % p.nkb0) * KB, t0 + p.tap_off[tap], b);
-        } else {
-          ptx::tma_load_3d(sA + s * A_BYTES, &mapA1, &full[s], (kb - nkb_src0) * KB, t0, b);
+      int kbg = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m = tile / n_tiles, n0 = (tile % n_tiles) * BN;
+        const int b = p.b_off + m / tiles_per_item, t0 = (m % tiles_per_item) * kTileM;
+        for (int kb = 0; kb < nkb; ++kb, ++kbg) {
+          const int s = kbg % stages;
+          const uint32_t ph = (kbg / stages) & 1;
+          ptx::mbar_wait(&empty[s], ph ^ 1u);
+          ptx::mbar_arrive_expect_tx(&full[s], tx_bytes);
+          if (kb < nkb_src0) {
+            const int tap = kb / p.nkb0;
+            ptx::tma_load_3d(sA + s * A_BYTES, &mapA0, &full[s], p.c_off0 + (kb % p.nkb0) * KB, t0 + p.tap_off[tap], b);
+          } else {
+            ptx::tma_load_3d(sA + s * A_BYTES, &mapA1, &full[s], (kb - nkb_src0) * KB, t0, b);
+          }
+          ptx::tma_load_2d(sB + s * B_BYTES, &mapW, &full[s], kb * KB, n0);
         }
-        ptx::tma_load_2d(sB + s * B_BYTES, &mapW, &full[s], kb * KB, n0);
+        if (dbg && tile == blockIdx.x) dbg[2] = clock64();      // all loads of the first tile issued
       }
     }
+    __syncwarp();   // reconverge: bar.sync below must be reached by whole warps
   } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
     const uint32_t idesc = ptx::make_idesc_bf16_f32(kTileM, BN);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int s = kb % stages;
-      const uint32_t ph = (kb / stages) & 1;
-      ptx::mbar_wait(&full[s], ph);
+    int kbg = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u);
       ptx::tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = ptx::smem_u32(sA + s * A_BYTES);
-        const uint32_t b_addr = ptx::smem_u32(sB + s * B_BYTES);
-        const uint64_t da = (KB == 64) ? ptx::make_desc_k_sw128(a_addr) : ptx::make_desc_k_sw64(a_addr);
-        const uint64_t db = (KB == 64) ? ptx::make_desc_k_sw128(b_addr) : ptx::make_desc_k_sw64(b_addr);
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
+      for (int kb = 0; kb < nkb; ++kb, ++kbg) {
+        const int s = kbg % stages;
+        const uint32_t ph = (kbg / stages) & 1;
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after();
+        if (dbg && lane == 0 && kbg == 0) dbg[3] = clock64();   // first k-block landed
+        if (lane == 0) {
+          const uint32_t a_addr = ptx::smem_u32(sA + s * A_BYTES);
+          const uint32_t b_addr = ptx::smem_u32(sB + s * B_BYTES);
+          const uint64_t da = (KB == 64) ? ptx::make_desc_k_sw128(a_addr) : ptx::make_desc_k_sw64(a_addr);
+          const uint64_t db = (KB == 64) ? ptx::make_desc_k_sw128(b_addr) : ptx::make_desc_k_sw64(b_addr);
 #pragma unroll
-        for (int k = 0; k < KB / 16; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the addr>>4 field
-          ptx::mma_f16_ss(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-        ptx::mma_commit(&empty[s]);
-        if (kb == nkb - 1) ptx::mma_commit(tmem_full);
+          for (int k = 0; k < KB / 16; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the addr>>4 field
+            ptx::mma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::mma_commit(&empty[s]);
+          if (kb == nkb - 1) ptx::mma_commit(&acc_full[buf]);
+          if (dbg && kb == nkb - 1 && it == 0) dbg[4] = clock64();   // all MMAs of the first tile issued
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
+    // ------------------------------------------------------------ epilogue
+    // Lane = frame (TMEM lane), CH consecutive channels per tcgen05.ld: every lane touches CH*4 (or CH*2)
+    // contiguous bytes of its own row, i.e. whole 32-byte sectors.  Residual operands (Epi::kAux floats per
+    // column) of the NEXT chunk are requested before the current chunk is processed, and the first chunk's
+    // before the accumulator is even complete, so their latency hides behind the MMAs / the previous chunk.
+    const int ew = warp - 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int t = t0 + q * 32 + lane;
-    ptx::mbar_wait(tmem_full, 0);
-    ptx::tc_fence_after();
-    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int half = ew >> 2;               // two warps share a quarter and split the column chunks
     const int nchunks = BN / CH;
-    for (int c = 0; c < nchunks; ++c) {
-      uint32_t r[CH];
-      if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(lane_base + c * CH, r);
-      else ptx::tmem_ld_32x32b_x16(lane_base + c * CH, r);
-      ptx::tmem_wait_ld();
-      if (t < p.Trows) {
-        float v[CH];
-#pragma unroll
-        for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
-        epi.template apply<CH>(b, t, n0 + c * CH, v);
+    constexpr int AUXN = CH * (Epi::kAux > 0 ? Epi::kAux : 1);
+    constexpr bool kPrefetch = Epi::kAux > 0 && AUXN <= 32;   // double-buffer only when it fits the register file
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int m = tile / n_tiles, n0 = (tile % n_tiles) * BN;
+      const int b = p.b_off + m / tiles_per_item, t0 = (m % tiles_per_item) * kTileM;
+      const int t = t0 + q * 32 + lane;
+      const bool row_ok = t < p.Trows;
+      const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+      float aux[AUXN];
+      if constexpr (kPrefetch) {
+        if (half < nchunks && row_ok) epi.template load_aux<CH>(b, t, n0 + half * CH, aux);
       }
+      ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      if (dbg && ew == 0 && lane == 0 && it == 0) dbg[5] = clock64();   // first accumulator complete
+      for (int c = half; c < nchunks; c += 2) {
+        uint32_t r[CH];
+        const bool stamp = dbg && ew == 0 && lane == 0 && it == 0 && c < 8;
+        if (stamp) dbg[16 + 4 * (c >> 1)] = clock64();
+        if constexpr (Epi::kAux > 0 && !kPrefetch) {
+          if (row_ok) epi.template load_aux<CH>(b, t, n0 + c * CH, aux);
+        }
+        if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(lane_base + c * CH, r);
+        else ptx::tmem_ld_32x32b_x16(lane_base + c * CH, r);
+        ptx::tmem_wait_ld();
+        if (stamp) dbg[17 + 4 * (c >> 1)] = clock64();
+        float aux_next[kPrefetch ? AUXN : 1];
+        if constexpr (kPrefetch) {
+          if (c + 2 < nchunks && row_ok) epi.template load_aux<CH>(b, t, n0 + (c + 2) * CH, aux_next);
+        }
+        if (stamp) dbg[18 + 4 * (c >> 1)] = clock64();
+        if (row_ok) {
+          float v[CH];
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
+          epi.template apply<CH>(b, t, n0 + c * CH, v, aux);
+        }
+        if constexpr (kPrefetch) {
+#pragma unroll
+          for (int j = 0; j < AUXN; ++j) aux[j] = aux_next[j];
+        }
+        if (stamp) dbg[19 + 4 * (c >> 1)] = clock64();
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+      if (dbg && lane == 0 && it == 0) dbg[6 + ew] = clock64();           // epilogue warp ew done with the first tile
     }
-    ptx::tc_fence_before();
   }
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[14] = clock64();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, ncols);

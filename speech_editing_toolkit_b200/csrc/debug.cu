@@ -4,10 +4,11 @@
 
 namespace fse {
 struct EpiStore {
+  static constexpr int kAux = 0;
   float* out;
   int N, T;
   template <int NV>
-  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc) const {
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float*) const {
     st_vec<NV>(out + (static_cast<size_t>(b) * T + t) * N + n0, acc);
   }
 };
@@ -16,7 +17,7 @@ struct EpiStore {
 using namespace fse;
 
 extern "C" int fse_debug_conv_gemm(int32_t mode, const void* A0, const void* W, float* out, int32_t B, int32_t T, int32_t C0,
-                                   int32_t ntaps, const int32_t* offs, int32_t N, int32_t BN, int32_t KB, void* stream) {
+                                   int32_t ntaps, const int32_t* offs, int32_t N, int32_t BN, int32_t KB, void* stream, int64_t* dbg_stamps) {
   if (!A0 || !W || !out || !offs) return fail(FSE_EINVAL, "null argument");
   if (ntaps <= 0 || ntaps > kMaxTaps) return fail(FSE_EINVAL, "ntaps out of range");
   if (KB != 64 && KB != 32) return fail(FSE_EINVAL, "KB must be 32 or 64");
@@ -24,6 +25,7 @@ extern "C" int fse_debug_conv_gemm(int32_t mode, const void* A0, const void* W, 
   int o[kMaxTaps];
   for (int i = 0; i < ntaps; ++i) o[i] = offs[i];
   ConvGemmParams p = make_params(B, T, T, C0, ntaps, o, 0, N, KB);
+  p.dbg = reinterpret_cast<long long*>(dbg_stamps);
   GemmOperands op; op.A0 = A0; op.W = W; op.BN = BN;
   CUtensorMap mA{}, mW{};
   if (mode == FSE_MODE_TC_BF16) {

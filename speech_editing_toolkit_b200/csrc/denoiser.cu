@@ -1,6 +1,8 @@
 // FluentSpeech spec_denoiser hot path on sm_100a: DiffNet step, posterior sample, sampling loop.
 // Reference semantics: modules/speech_editing/spec_denoiser/{diffnet.py:34-132, spec_denoiser.py:86-185}.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <memory>
 
 #include "epilogues.cuh"
@@ -172,8 +174,8 @@ struct fse_denoiser {
   // packed weights
   void* W_in = nullptr;  float* b_in = nullptr;  int Kp_in = 0;
   void* W1 = nullptr;    int Kp1 = 0;             // [L][2C][Kp1]
-  void* W2 = nullptr;    float* b2 = nullptr;     // [L][2C][C], [L][2C]
-  void* W_skip = nullptr; float* b_skip = nullptr;
+  void* W2 = nullptr;    float* b2 = nullptr;     // residual half of output_projection: [L][C][C], [L][C]
+  void* W_skip = nullptr; float* b_skip = nullptr; // folded skip path: [C][L*C], [C]
   void* W_out = nullptr;  float* b_out = nullptr;
   float* Wmac = nullptr;  float* bmac = nullptr;   // [L][3][2C][C], [L][2C]
   float* Wdp = nullptr;   float* bdp = nullptr;    // [L][C][C], [L][C]
@@ -187,9 +189,11 @@ struct fse_denoiser {
   std::vector<CUtensorMap> mW1, mW2;
   struct Plan {
     const void* ws = nullptr; const void* cond = nullptr; int B = 0, T = 0;
-    CUtensorMap m_xb{}, m_hb{}, m_cond{}, m_u{}, m_sb{}, m_rb{};
+    CUtensorMap m_xb{}, m_hb{}, m_cond{}, m_u{}, m_rb{};
   } plan;
   long long launches = 0;
+  int batch_chunk = 0;     // utterances per L2-resident chunk (0 = whole batch); FSE_BATCH_CHUNK overrides
+  long long* dbg_buf = nullptr;   // FSE_DBG_STAMPS=1: clock64 phase stamps of layer-3 kernels (developer aid)
   Profiler prof;
   // scratch owned for the *_host convenience call
   void* host_ws = nullptr; size_t host_ws_bytes = 0;
@@ -198,7 +202,7 @@ struct fse_denoiser {
 namespace {
 
 struct Workspace {
-  float* h; void* hb; void* u; float* S; void* sb; void* rb; void* xb; void* condb;
+  float* h; void* hb; void* u; void* rb; void* xb; void* condb;
   float* xa; float* xbuf2; float* tvals; float* temb; float* d; float* dbias;
   size_t bytes;
 };
@@ -215,9 +219,7 @@ Workspace carve(const fse_denoiser* h, void* base, int B, int T) {
   size_t o;
   o = take(N * C * 4);  w.h = reinterpret_cast<float*>(p + o);
   o = take(N * C * es); w.hb = p + o;
-  o = take(N * C * es); w.u = p + o;
-  o = take(N * C * 4);  w.S = reinterpret_cast<float*>(p + o);
-  o = take(N * C * es); w.sb = p + o;
+  o = take(N * L * C * es); w.u = p + o;      // gate outputs of ALL layers, [B*T, L*C]
   o = take(N * C * es); w.rb = p + o;
   o = take(N * M * es); w.xb = p + o;
   o = take(h->bf16 ? N * H * 2 : 0); w.condb = p + o;
@@ -248,8 +250,7 @@ int build_plan(fse_denoiser* h, const Workspace& w, const void* ws, const void* 
   FSE_TRY(make_map_act(&pl.m_xb, w.xb, h->cfg.n_mels, T, B, 64));
   FSE_TRY(make_map_act(&pl.m_hb, w.hb, C, T, B, 64));
   FSE_TRY(make_map_act(&pl.m_cond, w.condb, h->cfg.hidden, T, B, 64));
-  FSE_TRY(make_map_act(&pl.m_u, w.u, C, T, B, 64));
-  FSE_TRY(make_map_act(&pl.m_sb, w.sb, C, T, B, 64));
+  FSE_TRY(make_map_act(&pl.m_u, w.u, h->cfg.layers * C, T, B, 64));
   FSE_TRY(make_map_act(&pl.m_rb, w.rb, C, T, B, 64));
   pl.ws = ws; pl.B = B; pl.T = T; pl.cond = cond;
   return FSE_OK;
@@ -281,57 +282,72 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
   const size_t es = sizeof(TOp);
   const int zero = 0;
   const bool tc = mode == FSE_MODE_TC_BF16;
+  // The batch is walked in chunks of `chunk` utterances through ALL layers, so that the per-chunk working
+  // set (h, S fp32 + hb, u, cond operand copies, ~3.5 KB/frame) stays resident in the 126 MB L2 instead of
+  // streaming from HBM once per layer.
+  const int chunk = h->batch_chunk > 0 ? std::min(h->batch_chunk, B) : B;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+  const int Bc = std::min(chunk, B - b0);
   // input projection
   {
-    ConvGemmParams p = make_params(B, T, T, M, 1, &zero, 0, C, 64);
+    ConvGemmParams p = make_params(Bc, T, T, M, 1, &zero, 0, C, 64); p.b_off = b0;
     GemmOperands op; op.A0 = w.xb; op.W = h->W_in; op.mA0 = &h->plan.m_xb; op.mW = &h->mW_in; op.BN = 256;
     if (C % 256 != 0) op.BN = C % 128 == 0 ? 128 : 64;
     EpiIn<TOp> epi{h->b_in, w.h, static_cast<TOp*>(w.hb), C, T};
     FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 0})));
   }
   const int bn2 = (2 * C) % 256 == 0 ? 256 : 128;
+  const int bnr = C % 128 == 0 ? 128 : 64;      // residual GEMM: finer tiles balance better over the SMs
   for (int l = 0; l < L; ++l) {
     const int dil = 1 << (l % h->cfg.dilation_cycle_length);
     const int offs[3] = {-dil, 0, dil};
     {
-      ConvGemmParams p = make_params(B, T, T, C, 3, offs, H, 2 * C, 64);
+      ConvGemmParams p = make_params(Bc, T, T, C, 3, offs, H, 2 * C, 64); p.b_off = b0;
+      if (h->dbg_buf && l == 3) p.dbg = h->dbg_buf;
       GemmOperands op; op.A0 = w.hb; op.A1 = cond_op;
       op.W = static_cast<const uint8_t*>(h->W1) + static_cast<size_t>(l) * 2 * C * h->Kp1 * es;
       op.mA0 = &h->plan.m_hb; op.mA1 = &h->plan.m_cond; op.mW = tc ? &h->mW1[l] : nullptr; op.BN = bn2;
       const float* db = w.dbias + (static_cast<size_t>(tidx_base) * L + l) * 3 * 2 * C;
       const long long bstride = static_cast<long long>(tidx_bstride) * L * 3 * 2 * C;
       if (tc) {
-        EpiGate<TOp, true> epi{db, bstride, static_cast<TOp*>(w.u), 2 * C, T, dil};
+        EpiGate<TOp, true> epi{db, bstride, static_cast<TOp*>(w.u), 2 * C, T, dil, L * C, l * C};
         FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 1})));
       } else {
-        EpiGate<TOp, false> epi{db, bstride, static_cast<TOp*>(w.u), 2 * C, T, dil};
+        EpiGate<TOp, false> epi{db, bstride, static_cast<TOp*>(w.u), 2 * C, T, dil, L * C, l * C};
         FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 1})));
       }
     }
     {
-      ConvGemmParams p = make_params(B, T, T, C, 1, &zero, 0, 2 * C, 64);
+      ConvGemmParams p = make_params(Bc, T, T, C, 1, &zero, 0, C, 64); p.b_off = b0;
+      p.c_off0 = l * C; p.ld0 = L * C;
+      if (h->dbg_buf && l == 3) p.dbg = h->dbg_buf + 32;
       GemmOperands op; op.A0 = w.u;
-      op.W = static_cast<const uint8_t*>(h->W2) + static_cast<size_t>(l) * 2 * C * C * es;
-      op.mA0 = &h->plan.m_u; op.mW = tc ? &h->mW2[l] : nullptr; op.BN = bn2;
-      EpiRes<TOp> epi{h->b2 + static_cast<size_t>(l) * 2 * C, w.h, static_cast<TOp*>(w.hb), w.S, static_cast<TOp*>(w.sb),
-                      C, T, l == 0, l == L - 1, sqrtf(static_cast<float>(L))};
-      FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 2})));
+      op.W = static_cast<const uint8_t*>(h->W2) + static_cast<size_t>(l) * C * C * es;
+      op.mA0 = &h->plan.m_u; op.mW = tc ? &h->mW2[l] : nullptr; op.BN = bnr;
+      if (tc) {
+        EpiRes<TOp, true> epi{h->b2 + static_cast<size_t>(l) * C, w.h, static_cast<TOp*>(w.hb), C, T};
+        FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 2})));
+      } else {
+        EpiRes<TOp, false> epi{h->b2 + static_cast<size_t>(l) * C, w.h, static_cast<TOp*>(w.hb), C, T};
+        FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 2})));
+      }
     }
   }
   {
-    ConvGemmParams p = make_params(B, T, T, C, 1, &zero, 0, C, 64);
-    GemmOperands op; op.A0 = w.sb; op.W = h->W_skip; op.mA0 = &h->plan.m_sb; op.mW = &h->mW_skip;
+    ConvGemmParams p = make_params(Bc, T, T, L * C, 1, &zero, 0, C, 64); p.b_off = b0;
+    GemmOperands op; op.A0 = w.u; op.W = h->W_skip; op.mA0 = &h->plan.m_u; op.mW = &h->mW_skip;
     op.BN = C % 256 == 0 ? 256 : (C % 128 == 0 ? 128 : 64);
     EpiSkip<TOp> epi{h->b_skip, static_cast<TOp*>(w.rb), C, T};
     FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 3})));
   }
   {
-    ConvGemmParams p = make_params(B, T, T, C, 1, &zero, 0, M, 64);
+    ConvGemmParams p = make_params(Bc, T, T, C, 1, &zero, 0, M, 64); p.b_off = b0;
     GemmOperands op; op.A0 = w.rb; op.W = h->W_out; op.mA0 = &h->plan.m_rb; op.mW = &h->mW_out; op.BN = M;
     EpiOut<TOp> epi{h->b_out, M, T, out.mode, out.x_t, out.x_out, out.write_xb ? static_cast<TOp*>(w.xb) : nullptr,
                     out.noise, out.seed, out.step, out.c1, out.c2, out.sigma, out.mel_out, out.ref, out.mask};
     FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 4})));
   }
+  }  // batch chunk
   return FSE_OK;
 }
 
@@ -401,6 +417,18 @@ int sample_impl(fse_denoiser* h, const float* cond, const float* noise, uint64_t
     FSE_TRY((run_step<TOp>(h, w, cond_op, B, T, k, 0, out, st)));
     x_cur = x_next;
   }
+  if (h->dbg_buf) {
+    long long d[64];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(d, h->dbg_buf, sizeof(d), cudaMemcpyDeviceToHost);
+    for (int k = 0; k < 2; ++k) {
+      const long long* q = d + 32 * k; const long long t0 = q[0];
+      fprintf(stderr, "[fse stamps %s] setup=%lld loads_issued=%lld first_kb=%lld mma_issued=%lld acc_ready=%lld epi_done=%lld..%lld end=%lld chunks:",
+              k == 0 ? "gate" : "res", q[1] - t0, q[2] - t0, q[3] - t0, q[4] - t0, q[5] - t0, q[6] - t0, q[13] - t0, q[14] - t0);
+      for (int c = 0; c < 4; ++c) fprintf(stderr, " [%lld %lld %lld %lld]", q[16 + 4 * c] - t0, q[17 + 4 * c] - t0, q[18 + 4 * c] - t0, q[19 + 4 * c] - t0);
+      fprintf(stderr, "\n");
+    }
+  }
   return FSE_OK;
 }
 
@@ -434,6 +462,8 @@ int fse_denoiser_create(const fse_denoiser_config* cfg, fse_denoiser** out) {
   auto* h = new fse_denoiser();
   h->cfg = *cfg;
   h->bf16 = cfg->mode != FSE_MODE_SIMT_F32;
+  if (const char* e = getenv("FSE_BATCH_CHUNK")) h->batch_chunk = atoi(e);
+  if (getenv("FSE_DBG_STAMPS")) { cudaMalloc(reinterpret_cast<void**>(&h->dbg_buf), 64 * 8); cudaMemset(h->dbg_buf, 0, 64 * 8); }
   cudaGetDevice(&h->device);
   *out = h;
   return FSE_OK;
@@ -478,7 +508,8 @@ int fse_denoiser_load_weights(fse_denoiser* h, const fse_tensor* tensors, int32_
   const int nkbC = C / 64, nkbH = (H + 63) / 64;
   h->Kp1 = (3 * nkbC + nkbH) * 64;
   const int N2 = 2 * C;
-  std::vector<float> W1((size_t)L * N2 * h->Kp1, 0.f), W2((size_t)L * N2 * C), b2v((size_t)L * N2);
+  std::vector<float> W1((size_t)L * N2 * h->Kp1, 0.f), W2((size_t)L * C * C), b2v((size_t)L * C);
+  std::vector<const float*> wop_all(L), bop_all(L);
   std::vector<float> Wmac((size_t)L * 3 * N2 * C), bmac((size_t)L * N2), Wdp((size_t)L * C * C), bdp((size_t)L * C);
   for (int l = 0; l < L; ++l) {
     const std::string pre = "residual_layers." + std::to_string(l) + ".";
@@ -507,8 +538,9 @@ int fse_denoiser_load_weights(fse_denoiser* h, const fse_tensor* tensors, int32_
       for (int c = 0; c < H; ++c) row[3 * nkbC * 64 + c] = wcp[(size_t)r * H + c];
       bmac[(size_t)l * N2 + np] = bdc[r] + bcp[r];
     }
-    memcpy(&W2[(size_t)l * N2 * C], wop, sizeof(float) * N2 * C);
-    memcpy(&b2v[(size_t)l * N2], bop, sizeof(float) * N2);
+    memcpy(&W2[(size_t)l * C * C], wop, sizeof(float) * C * C);      // residual half = first C rows (diffnet.py:80 chunk order)
+    memcpy(&b2v[(size_t)l * C], bop, sizeof(float) * C);
+    wop_all[l] = wop; bop_all[l] = bop;
     memcpy(&Wdp[(size_t)l * C * C], wdp, sizeof(float) * C * C);
     memcpy(&bdp[(size_t)l * C], bd, sizeof(float) * C);
   }
@@ -523,21 +555,44 @@ int fse_denoiser_load_weights(fse_denoiser* h, const fse_tensor* tensors, int32_
     const float* ws = G("skip_projection.weight", (int64_t)C * C); const float* bs = G("skip_projection.bias", C);
     const float* wo = G("output_projection.weight", (int64_t)M * C); const float* bo = G("output_projection.bias", M);
     if (rc) return rc;
-    FSE_TRY(upload_operand(std::vector<float>(ws, ws + (size_t)C * C), h->bf16, &h->W_skip));
-    FSE_TRY(upload_f32(std::vector<float>(bs, bs + C), &h->b_skip));
+    // Fold  skip_projection( sum_l skip_l / sqrt(L) )  with skip_l = W_op,l[C:] u_l + b_op,l[C:]  into
+    //   W_comb[:, l*C:(l+1)*C] = W_skip W_op,l[C:] / sqrt(L),   b_comb = b_skip + W_skip (sum_l b_op,l[C:]) / sqrt(L)
+    const double inv = 1.0 / std::sqrt(static_cast<double>(L));
+    std::vector<float> Wc((size_t)C * L * C), bc(C);
+    std::vector<double> row(C), bsum(C, 0.0);
+    for (int l = 0; l < L; ++l)
+      for (int k = 0; k < C; ++k) bsum[k] += bop_all[l][C + k];
+    for (int o = 0; o < C; ++o) {
+      double acc = 0.0;
+      for (int k = 0; k < C; ++k) acc += static_cast<double>(ws[(size_t)o * C + k]) * bsum[k];
+      bc[o] = static_cast<float>(bs[o] + acc * inv);
+      for (int l = 0; l < L; ++l) {
+        std::fill(row.begin(), row.end(), 0.0);
+        for (int k = 0; k < C; ++k) {
+          const double wv = ws[(size_t)o * C + k];
+          const float* src = wop_all[l] + (size_t)(C + k) * C;
+          for (int c = 0; c < C; ++c) row[c] += wv * src[c];
+        }
+        float* dst = &Wc[(size_t)o * L * C + (size_t)l * C];
+        for (int c = 0; c < C; ++c) dst[c] = static_cast<float>(row[c] * inv);
+      }
+    }
+    FSE_TRY(upload_operand(Wc, h->bf16, &h->W_skip));
+    FSE_TRY(upload_f32(bc, &h->b_skip));
     FSE_TRY(upload_operand(std::vector<float>(wo, wo + (size_t)M * C), h->bf16, &h->W_out));
     FSE_TRY(upload_f32(std::vector<float>(bo, bo + M), &h->b_out));
   }
   if (h->cfg.mode == FSE_MODE_TC_BF16) {
     const int bnC = C % 256 == 0 ? 256 : (C % 128 == 0 ? 128 : 64);
     const int bn2 = N2 % 256 == 0 ? 256 : 128;
+    const int bnr = C % 128 == 0 ? 128 : 64;
     FSE_TRY(make_map_w(&h->mW_in, h->W_in, h->Kp_in, C, 64, bnC));
-    FSE_TRY(make_map_w(&h->mW_skip, h->W_skip, C, C, 64, bnC));
+    FSE_TRY(make_map_w(&h->mW_skip, h->W_skip, L * C, C, 64, bnC));
     FSE_TRY(make_map_w(&h->mW_out, h->W_out, C, M, 64, M));
     h->mW1.resize(L); h->mW2.resize(L);
     for (int l = 0; l < L; ++l) {
       FSE_TRY(make_map_w(&h->mW1[l], static_cast<uint8_t*>(h->W1) + (size_t)l * N2 * h->Kp1 * 2, h->Kp1, N2, 64, bn2));
-      FSE_TRY(make_map_w(&h->mW2[l], static_cast<uint8_t*>(h->W2) + (size_t)l * N2 * C * 2, C, N2, 64, bn2));
+      FSE_TRY(make_map_w(&h->mW2[l], static_cast<uint8_t*>(h->W2) + (size_t)l * C * C * 2, C, C, 64, bnr));
     }
   }
   h->loaded = true;

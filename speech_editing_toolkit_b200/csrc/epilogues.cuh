@@ -57,12 +57,13 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t step, uin
 // h = relu(W_in x + b_in)  (diffnet.py:117-120); writes the fp32 residual stream and its operand copy.
 template <typename TOp>
 struct EpiIn {
+  static constexpr int kAux = 0;
   const float* bias;   // [C]
   float* h;            // [B*T, C] fp32 residual stream
   TOp* hb;             // [B*T, C] operand copy
   int C, T;
   template <int NV>
-  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc) const {
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float*) const {
     const size_t o = (static_cast<size_t>(b) * T + t) * C + n0;
     float v[NV];
 #pragma unroll
@@ -80,84 +81,90 @@ struct EpiIn {
 // reference, so the taps that fall outside [0,T) must not see d).
 template <typename TOp, bool Fast>
 struct EpiGate {
+  static constexpr int kAux = 0;
   const float* dbias;       // [.., 3, N] for this layer; row 0 = m, 1 = a, 2 = c
   long long bstride;        // elements between consecutive batch items' tables (0: shared by the batch)
-  TOp* u;                   // [B*T, N/2]
+  TOp* u;                   // [B*T, ldu] rows; this layer's N/2 channels start at column u_off
   int N, T, dil;
+  int ldu, u_off;
   template <int NV>
-  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc) const {
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float*) const {
     const float* m = dbias + static_cast<size_t>(b) * bstride + n0;
     const bool e0 = t < dil, e2 = t >= T - dil;
+    float y[NV];
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+      const float4 mv = __ldg(reinterpret_cast<const float4*>(m) + i);
+      y[4 * i] = acc[4 * i] + mv.x; y[4 * i + 1] = acc[4 * i + 1] + mv.y;
+      y[4 * i + 2] = acc[4 * i + 2] + mv.z; y[4 * i + 3] = acc[4 * i + 3] + mv.w;
+    }
+    if (e0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) y[i] -= __ldg(m + N + i);
+    }
+    if (e2) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) y[i] -= __ldg(m + 2 * N + i);
+    }
     float v[NV / 2];
 #pragma unroll
-    for (int j = 0; j < NV / 2; ++j) {
-      float g = acc[2 * j] + __ldg(m + 2 * j);
-      float f = acc[2 * j + 1] + __ldg(m + 2 * j + 1);
-      if (e0) { g -= __ldg(m + N + 2 * j); f -= __ldg(m + N + 2 * j + 1); }
-      if (e2) { g -= __ldg(m + 2 * N + 2 * j); f -= __ldg(m + 2 * N + 2 * j + 1); }
-      v[j] = sigmoid_f<Fast>(g) * tanh_f<Fast>(f);
-    }
-    st_vec<NV / 2>(u + (static_cast<size_t>(b) * T + t) * (N / 2) + n0 / 2, v);
+    for (int j = 0; j < NV / 2; ++j) v[j] = sigmoid_f<Fast>(y[2 * j]) * tanh_f<Fast>(y[2 * j + 1]);
+    st_vec<NV / 2>(u + (static_cast<size_t>(b) * T + t) * ldu + u_off + n0 / 2, v);
   }
 };
 
-// ------------------------------------------------------------------ residual / skip
-// o = W_op u + b_op; h <- (h + o[:C]) / sqrt(2); S += o[C:]   (diffnet.py:79-81, :126-128).
-// Last layer writes the operand copy of S / sqrt(L) instead of S.
-template <typename TOp>
+// ------------------------------------------------------------------ residual
+// o_res = W_op[:C] u + b_op[:C];  h <- (h + o_res) / sqrt(2)   (diffnet.py:79-81).
+// The skip half of output_projection never materialises: sum_l skip_l / sqrt(L) followed by skip_projection
+// (diffnet.py:126-129) is linear in the per-layer gate outputs u_l, so it is evaluated at the end of the step
+// as ONE GEMM over the concatenated u_l with the folded weight W_skip W_op,l[C:] / sqrt(L) (EpiSkip below).
+template <typename TOp, bool Fast>
 struct EpiRes {
-  const float* bias;   // [2C]
+  static constexpr int kAux = 1;          // the fp32 residual stream h
+  const float* bias;   // [C]
   float* h;            // [B*T, C]
-  TOp* hb;             // [B*T, C]
-  float* S;            // [B*T, C] running skip sum
-  TOp* sb;             // [B*T, C] operand copy of S/sqrt(L) (written by the last layer)
+  TOp* hb;             // [B*T, C] operand copy
   int C, T;
-  int first, last;
-  float sqrt_layers;
   template <int NV>
-  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc) const {
-    const size_t row = static_cast<size_t>(b) * T + t;
+  __device__ __forceinline__ void load_aux(int b, int t, int n0, float* aux) const {
+    const float4* hp = reinterpret_cast<const float4*>(h + (static_cast<size_t>(b) * T + t) * C + n0);
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+      const float4 v = hp[i];
+      aux[4 * i] = v.x; aux[4 * i + 1] = v.y; aux[4 * i + 2] = v.z; aux[4 * i + 3] = v.w;
+    }
+  }
+  template <int NV>
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float* aux) const {
+    const size_t o = (static_cast<size_t>(b) * T + t) * C + n0;
     float v[NV];
-    if (n0 < C) {
-      float* hp = h + row * C + n0;
 #pragma unroll
-      for (int i = 0; i < NV / 2; ++i) {
-        const float2 hv = reinterpret_cast<const float2*>(hp)[i];
-        v[2 * i] = __fdiv_rn(hv.x + (acc[2 * i] + __ldg(bias + n0 + 2 * i)), 1.41421356237309504880f);
-        v[2 * i + 1] = __fdiv_rn(hv.y + (acc[2 * i + 1] + __ldg(bias + n0 + 2 * i + 1)), 1.41421356237309504880f);
-      }
-      st_vec<NV>(hp, v);
-      st_vec<NV>(hb + row * C + n0, v);
-    } else {
-      const int c0 = n0 - C;
-      float* sp = S + row * C + c0;
+    for (int i = 0; i < NV / 4; ++i) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n0) + i);
+      const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-      for (int i = 0; i < NV / 2; ++i) {
-        float2 sv = make_float2(0.f, 0.f);
-        if (!first) sv = reinterpret_cast<const float2*>(sp)[i];
-        v[2 * i] = sv.x + (acc[2 * i] + __ldg(bias + n0 + 2 * i));
-        v[2 * i + 1] = sv.y + (acc[2 * i + 1] + __ldg(bias + n0 + 2 * i + 1));
-      }
-      if (last) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) v[i] = __fdiv_rn(v[i], sqrt_layers);
-        st_vec<NV>(sb + row * C + c0, v);
-      } else {
-        st_vec<NV>(sp, v);
+      for (int q = 0; q < 4; ++q) {
+        const float sum = aux[4 * i + q] + (acc[4 * i + q] + bb[q]);
+        if constexpr (Fast) v[4 * i + q] = sum * 0.70710678118654752440f;
+        else v[4 * i + q] = __fdiv_rn(sum, 1.41421356237309504880f);   // torch: (x + residual) / sqrt(2.0)
       }
     }
+    st_vec<NV>(h + o, v);
+    st_vec<NV>(hb + o, v);
   }
 };
 
 // ------------------------------------------------------------------ skip projection
-// r = relu(W_skip s + b_skip)  (diffnet.py:129-130)
+// r = relu(W_skip s + b_skip), s = sum_l skip_l / sqrt(L)  (diffnet.py:126-130), with the sum folded into the
+// K axis of this GEMM (A = [u_0 | u_1 | ... | u_{L-1}], W = folded weight, bias = folded bias).
 template <typename TOp>
 struct EpiSkip {
+  static constexpr int kAux = 0;
   const float* bias;
   TOp* rb;   // [B*T, C]
   int C, T;
   template <int NV>
-  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc) const {
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float*) const {
     float v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = fmaxf(acc[i] + __ldg(bias + n0 + i), 0.f);
@@ -174,6 +181,7 @@ struct EpiSkip {
 // the reference mel: mel*mask + ref*(1-mask) (tasks/speech_editing/spec_denoiser.py:53).
 template <typename TOp>
 struct EpiOut {
+  static constexpr int kAux = 0;
   const float* bias;     // [M]
   int M, T;
   int mode;
@@ -188,7 +196,7 @@ struct EpiOut {
   const float* ref;      // [B, T, M] or null
   const float* mask;     // [B, T] or null
   template <int NV>
-  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc) const {
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float*) const {
     if (n0 >= M) return;
     const size_t row = static_cast<size_t>(b) * T + t;
     float v[NV];

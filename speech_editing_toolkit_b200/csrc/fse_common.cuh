@@ -198,7 +198,7 @@ struct GemmOperands {
 inline ConvGemmParams make_params(int B, int Trows, int Tsrc, int C0, int ntaps, const int* offs, int C1, int N, int KB) {
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
-  p.B = B; p.Trows = Trows; p.Tsrc = Tsrc; p.C0 = C0; p.C1 = C1; p.ntaps = ntaps;
+  p.B = B; p.Trows = Trows; p.Tsrc = Tsrc; p.C0 = C0; p.C1 = C1; p.ntaps = ntaps; p.ld0 = C0;
   for (int i = 0; i < ntaps; ++i) p.tap_off[i] = offs[i];
   p.KB = KB;
   p.nkb0 = (C0 + KB - 1) / KB;
@@ -213,7 +213,7 @@ inline int launch_tc(const ConvGemmParams& p, const GemmOperands& op, const Epi&
   static bool attr_set = false;
   const int nkb = p.ntaps * p.nkb0 + p.nkb1;
   const int stage_bytes = tc_a_stage_bytes(KB) + tc_b_stage_bytes(op.BN, KB);
-  int stages = (220 * 1024) / stage_bytes;
+  int stages = (225 * 1024) / stage_bytes;
   if (stages > 6) stages = 6;
   if (stages > nkb) stages = nkb;
   if (stages < 1) return fail(FSE_EINVAL, "conv_gemm: tile does not fit shared memory");
@@ -223,8 +223,14 @@ inline int launch_tc(const ConvGemmParams& p, const GemmOperands& op, const Epi&
     attr_set = true;
   }
   const size_t smem = tc_smem_bytes(op.BN, KB, stages);
-  const int tiles = (p.Trows + kTileM - 1) / kTileM;
-  dim3 grid(p.B * tiles, p.N / op.BN);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    FSE_CUDA(cudaGetDevice(&dev));
+    FSE_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int total_tiles = p.B * ((p.Trows + kTileM - 1) / kTileM) * (p.N / op.BN);
+  dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);   // persistent: one CTA per SM
   const CUtensorMap* mA1 = op.mA1 ? op.mA1 : op.mA0;
   kern<<<grid, kTcThreads, smem, st>>>(*op.mA0, *mA1, *op.mW, p, op.BN, stages, epi);
   FSE_CUDA(cudaGetLastError());

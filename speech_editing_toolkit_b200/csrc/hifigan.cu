@@ -17,12 +17,13 @@ __device__ __forceinline__ float lrelu(float x, float slope) { return x >= 0.f ?
 // out = lrelu(acc + bias)  — conv_pre (followed by the stage-0 leaky_relu, hifigan.py:127-129) and ResBlock1 convs1 (:53-55)
 template <typename TOp>
 struct EpiAct {
+  static constexpr int kAux = 0;
   const float* bias;
   TOp* out;   // [B*T, N]
   int N, T;
   float slope;
   template <int NV>
-  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc) const {
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float*) const {
     float v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = lrelu(acc[i] + __ldg(bias + n0 + i), slope);
@@ -33,12 +34,13 @@ struct EpiAct {
 // transposed-conv phase scatter: x = acc + bias (fp32 stage input) and xa = lrelu(x, 0.1) (hifigan.py:130, :53)
 template <typename TOp>
 struct EpiUp {
+  static constexpr int kAux = 0;
   const float* bias;   // [Cout]
   float* x;            // [B, Tout, Cout]
   TOp* xa;             // [B, Tout, Cout]
   int Cout, Tout, u, pad;
   template <int NV>
-  __device__ __forceinline__ void apply(int b, int q, int n0, const float* acc) const {
+  __device__ __forceinline__ void apply(int b, int q, int n0, const float* acc, const float*) const {
     const int r = n0 / Cout, co = n0 % Cout;
     const int tau = q * u + r - pad;
     if (tau < 0 || tau >= Tout) return;
@@ -57,6 +59,7 @@ struct EpiUp {
 // mean over the parallel blocks (hifigan.py:131-137) and the activation feeding the next stage.
 template <typename TOp>
 struct EpiResAdd {
+  static constexpr int kAux = 2;       // per column: residual input, running sum over resblocks
   const float* bias;
   const float* res;    // [B*T, N] fp32 residual input
   float* y;            // [B*T, N] fp32 (kind 0)
@@ -68,15 +71,27 @@ struct EpiResAdd {
   int kind;            // 0: inside a block; 1: first block end (xs = v); 2: middle (xs += v); 3: last (mean)
   float num_kernels, slope_next;
   template <int NV>
-  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc) const {
+  __device__ __forceinline__ void load_aux(int b, int t, int n0, float* aux) const {
+    const size_t o = (static_cast<size_t>(b) * T + t) * N + n0;
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+      const float4 v = reinterpret_cast<const float4*>(res + o)[i];
+      aux[4 * i] = v.x; aux[4 * i + 1] = v.y; aux[4 * i + 2] = v.z; aux[4 * i + 3] = v.w;
+    }
+    if (kind >= 2) {
+#pragma unroll
+      for (int i = 0; i < NV / 4; ++i) {
+        const float4 v = reinterpret_cast<const float4*>(xs + o)[i];
+        aux[NV + 4 * i] = v.x; aux[NV + 4 * i + 1] = v.y; aux[NV + 4 * i + 2] = v.z; aux[NV + 4 * i + 3] = v.w;
+      }
+    }
+  }
+  template <int NV>
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float* aux) const {
     const size_t o = (static_cast<size_t>(b) * T + t) * N + n0;
     float v[NV];
 #pragma unroll
-    for (int i = 0; i < NV / 2; ++i) {
-      const float2 rv = reinterpret_cast<const float2*>(res + o)[i];
-      v[2 * i] = (acc[2 * i] + __ldg(bias + n0 + 2 * i)) + rv.x;
-      v[2 * i + 1] = (acc[2 * i + 1] + __ldg(bias + n0 + 2 * i + 1)) + rv.y;
-    }
+    for (int i = 0; i < NV; ++i) v[i] = (acc[i] + __ldg(bias + n0 + i)) + aux[i];
     if (kind == 0) {
       st_vec<NV>(y + o, v);
 #pragma unroll
@@ -86,11 +101,7 @@ struct EpiResAdd {
       st_vec<NV>(xs + o, v);
     } else {
 #pragma unroll
-      for (int i = 0; i < NV / 2; ++i) {
-        const float2 sv = reinterpret_cast<const float2*>(xs + o)[i];
-        v[2 * i] = sv.x + v[2 * i];
-        v[2 * i + 1] = sv.y + v[2 * i + 1];
-      }
+      for (int i = 0; i < NV; ++i) v[i] = aux[NV + i] + v[i];
       if (kind == 2) {
         st_vec<NV>(xs + o, v);
       } else {

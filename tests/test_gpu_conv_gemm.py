@@ -15,7 +15,7 @@ def run(mode, A, W, B, T, C0, offs, N, BN, KB):
     arr = (C.c_int32 * len(offs))(*offs)
     _lib.check(_lib.lib().fse_debug_conv_gemm(_lib.MODES[mode], C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()),
                                               C.c_void_p(out.data_ptr()), B, T, C0, len(offs), arr, N, BN, KB,
-                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream), None))
     torch.cuda.synchronize()
     return out.cpu().numpy()
 
