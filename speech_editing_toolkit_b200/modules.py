@@ -1,0 +1,209 @@
+"""Host-side mirror of the reference's model seams for the hot path:
+
+  DiffNetB200            <-> modules/speech_editing/spec_denoiser/diffnet.py::DiffNet          (:84-132)
+  GaussianDiffusionB200  <-> modules/speech_editing/spec_denoiser/spec_denoiser.py::GaussianDiffusion (:16-185)
+  MelEncoder             <-> modules/speech_editing/commons/mel_encoder.py::MelEncoder        (:3-19)
+
+Same constructor arguments, same state_dict keys/shapes (reference checkpoints load unchanged), same
+forward() signatures and return values.  The nn.Modules only OWN the parameters; every forward goes
+through the C ABI (engine.Denoiser) — no torch arithmetic on the hot path and no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import schedule as _schedule
+from .engine import Denoiser
+from .hparams import hparams as _global_hparams
+
+
+class _ResidualBlockParams(nn.Module):
+    """Parameter container with the reference ResidualBlock's names/shapes (diffnet.py:60-66)."""
+
+    def __init__(self, encoder_hidden, residual_channels, dilation):
+        super().__init__()
+        C = residual_channels
+        self.dilation = dilation
+        self.dilated_conv = nn.Conv1d(C, 2 * C, 3, padding=dilation, dilation=dilation)
+        self.diffusion_projection = nn.Linear(C, C)
+        self.conditioner_projection = nn.Conv1d(encoder_hidden, 2 * C, 1)
+        self.output_projection = nn.Conv1d(C, 2 * C, 1)
+        for conv in (self.dilated_conv, self.conditioner_projection, self.output_projection):
+            nn.init.kaiming_normal_(conv.weight)
+
+
+class DiffNetB200(nn.Module):
+    """Drop-in for DiffNet: `DIFF_DECODERS['wavenet'](hparams)` (tasks/speech_editing/spec_denoiser.py:13-15)."""
+
+    def __init__(self, in_dims: int = 80, hparams: Optional[dict] = None):
+        super().__init__()
+        hp = _global_hparams if hparams is None else hparams
+        self.in_dims = in_dims
+        self.encoder_hidden = hp["hidden_size"]
+        self.n_layers = hp["residual_layers"]
+        self.channels = C = hp["residual_channels"]
+        self.dilation_cycle_length = hp["dilation_cycle_length"]
+        self.mode = hp.get("b200_mode", "tc_bf16")
+        self.input_projection = nn.Conv1d(in_dims, C, 1)
+        nn.init.kaiming_normal_(self.input_projection.weight)
+        self.mlp = nn.Sequential(nn.Linear(C, C * 4), nn.Identity(), nn.Linear(C * 4, C))   # index 1 is Mish (no params)
+        self.residual_layers = nn.ModuleList([
+            _ResidualBlockParams(self.encoder_hidden, C, 2 ** (i % self.dilation_cycle_length)) for i in range(self.n_layers)])
+        self.skip_projection = nn.Conv1d(C, C, 1)
+        nn.init.kaiming_normal_(self.skip_projection.weight)
+        self.output_projection = nn.Conv1d(C, in_dims, 1)
+        nn.init.zeros_(self.output_projection.weight)             # as the reference (diffnet.py:108)
+        self._engine: Optional[Denoiser] = None
+        self._engine_key = None
+
+    # -- engine management -----------------------------------------------------------------------
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def engine(self) -> Denoiser:
+        """The C-ABI handle holding the repacked weights; rebuilt when any parameter changed."""
+        key = self._weights_key()
+        if self._engine is None or key != self._engine_key:
+            eng = Denoiser(n_mels=self.in_dims, hidden=self.encoder_hidden, channels=self.channels, layers=self.n_layers,
+                           dilation_cycle_length=self.dilation_cycle_length, mode=self.mode)
+            eng.load_state_dict(self.state_dict())
+            self._engine, self._engine_key = eng, key
+        return self._engine
+
+    def forward(self, spec: torch.Tensor, diffusion_step: torch.Tensor, cond: torch.Tensor) -> torch.Tensor:
+        """spec[B,1,M,T], diffusion_step[B], cond[B,H,T] -> [B,1,M,T]   (diffnet.py:110-132)"""
+        x = spec[:, 0]
+        # the reference hands over cond as decoder_inp.transpose(1,2): its physical layout is already [B,T,H]
+        cond_bth = cond.transpose(1, 2).contiguous()
+        x0 = self.engine().denoise_step(x, cond_bth, diffusion_step.reshape(-1).long())
+        return x0[:, None, :, :]
+
+
+class MelEncoder(nn.Module):
+    """mel_encoder.py:3-19 — kept in torch (runs once per utterance; 'next' row f.1 of SURVEY §8)."""
+
+    def __init__(self, mel_bins=80, hidden_size=192):
+        super().__init__()
+        self.encoder = nn.Sequential(nn.Linear(mel_bins, hidden_size), nn.ReLU(), nn.Linear(hidden_size, hidden_size), nn.ReLU())
+        self.fc_out = nn.Linear(hidden_size, hidden_size)
+
+    def forward(self, x):
+        return self.fc_out(self.encoder(x))
+
+
+class GaussianDiffusionB200(nn.Module):
+    """Drop-in for GaussianDiffusion on the inference path.
+
+    `fs` (the FastSpeech condition encoder, fs.py:49-112) and `mel_encoder` are injected: inside the reference
+    tree they are the reference's own modules (see `from_reference` / INTEGRATION.md); they run once per
+    batch and stay PyTorch.  Everything from `cond` on — x_S draw, the S p_sample iterations
+    and the mask compositing — is one C-ABI call (fse_sample)."""
+
+    def __init__(self, phone_encoder, out_dims, denoise_fn, timesteps=1000, time_scale=1, loss_type="l1", betas=None,
+                 spec_min=None, spec_max=None, fs: Optional[nn.Module] = None, mel_encoder: Optional[nn.Module] = None,
+                 hparams: Optional[dict] = None):
+        super().__init__()
+        hp = _global_hparams if hparams is None else hparams
+        self.denoise_fn = denoise_fn
+        self.fs = fs
+        self.mel_encoder = mel_encoder if mel_encoder is not None else MelEncoder(out_dims, hp.get("hidden_size", 192))
+        self.mel_bins = out_dims
+        self.time_scale = time_scale
+        self.num_timesteps = int(timesteps)
+        self.loss_type = loss_type
+        if betas is not None and isinstance(betas, torch.Tensor):
+            betas = betas.detach().cpu().numpy()
+        bufs = _schedule.diffusion_buffers(self.num_timesteps, hp.get("schedule_type", "vpsde"), betas)
+        self.register_buffer("timesteps", torch.tensor(float(self.num_timesteps)))
+        self.register_buffer("timescale", torch.tensor(float(self.time_scale)))
+        for name in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+                     "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+                     "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2"):
+            self.register_buffer(name, torch.from_numpy(bufs[name]))
+        keep = hp.get("keep_bins", out_dims)
+        self.register_buffer("spec_min", torch.FloatTensor(spec_min or [])[None, None, :keep])
+        self.register_buffer("spec_max", torch.FloatTensor(spec_max or [])[None, None, :keep])
+        self._sched_key = None
+
+    @classmethod
+    def from_reference(cls, ref_model, mode: str = "tc_bf16"):
+        """Wrap an instantiated reference GaussianDiffusion: shares its fs / mel_encoder, copies denoise_fn weights."""
+        rd = ref_model.denoise_fn
+        hp = dict(hidden_size=rd.params.encoder_hidden, residual_layers=rd.params.residual_layers,
+                  residual_channels=rd.params.residual_channels, dilation_cycle_length=rd.params.dilation_cycle_length,
+                  b200_mode=mode, keep_bins=ref_model.mel_bins)
+        den = DiffNetB200(ref_model.mel_bins, hp)
+        den.load_state_dict(rd.state_dict())
+        new = cls(None, ref_model.mel_bins, den, timesteps=ref_model.num_timesteps, time_scale=ref_model.time_scale,
+                  loss_type=ref_model.loss_type, fs=ref_model.fs, mel_encoder=ref_model.mel_encoder, hparams=hp)
+        for name, buf in ref_model.named_buffers(recurse=False):     # the reference's own float64-derived schedule, bit for bit
+            if name in new._buffers:
+                new._buffers[name] = buf.detach().clone()
+        return new.to(next(ref_model.parameters()).device)
+
+    # -- engine plumbing -------------------------------------------------------------------------
+    def _engine(self) -> Denoiser:
+        eng = self.denoise_fn.engine()
+        key = (id(eng), self.posterior_mean_coef1.data_ptr(), self.posterior_mean_coef1._version)
+        if key != self._sched_key:
+            eng.set_schedule(self.posterior_mean_coef1, self.posterior_mean_coef2, self.posterior_log_variance_clipped)
+            self._sched_key = key
+        return eng
+
+    # -- reference API ---------------------------------------------------------------------------
+    def q_posterior(self, x_start, x_t, t):
+        """spec_denoiser.py:86-93 (tiny gathers; plain torch)."""
+        shape = (t.shape[0],) + (1,) * (x_t.dim() - 1)
+        mean = self.posterior_mean_coef1[t].reshape(shape) * x_start + self.posterior_mean_coef2[t].reshape(shape) * x_t
+        return mean, self.posterior_variance[t].reshape(shape), self.posterior_log_variance_clipped[t].reshape(shape)
+
+    @torch.no_grad()
+    def q_posterior_sample(self, x_start, x_t, t, noise=None, seed=0, step=0):
+        """spec_denoiser.py:95-101; x_*[B,1,M,T]."""
+        out = self._engine().posterior_step(x_start[:, 0], x_t[:, 0], t, None if noise is None else noise[:, 0], seed, step)
+        return out[:, None]
+
+    @torch.no_grad()
+    def p_sample(self, x_t, t, cond, spk_emb=None, clip_denoised=True, repeat_noise=False, noise=None, seed=0):
+        """spec_denoiser.py:103-108."""
+        x0 = self.denoise_fn(x_t, t, cond)
+        return self.q_posterior_sample(x0, x_t, t, noise=noise, seed=seed, step=int(t[0]) + 1)
+
+    @torch.no_grad()
+    def sample(self, cond_bth: torch.Tensor, noise=None, seed: int = 0, ref_mels=None, time_mel_masks=None):
+        """cond[B,T,H] -> mel_out[B,T,M] (optionally composited with ref_mels by the 0/1 mask)."""
+        mask = None if time_mel_masks is None else time_mel_masks.reshape(cond_bth.shape[0], cond_bth.shape[1])
+        return self._engine().sample(cond_bth, noise, seed, ref_mels if mask is not None else None, mask)
+
+    def forward(self, txt_tokens, time_mel_masks, mel2ph, spk_embed, ref_mels, f0, uv, energy=None, infer=False,
+                use_pred_mel2ph=False, use_pred_pitch=False, noise=None, seed=None):
+        """spec_denoiser.py:154-185, infer=True branch.  Returns the reference's dict (mel_out[B,T,M], ...)."""
+        if not infer:
+            raise NotImplementedError("GaussianDiffusionB200 implements the sampling path (infer=True); training stays on the "
+                                      "reference's GaussianDiffusion (SURVEY.md §8f row 3)")
+        if self.fs is None:
+            raise RuntimeError("no condition encoder: pass fs=<reference FastSpeech> or use GaussianDiffusionB200.from_reference()")
+        ret = self.fs(txt_tokens, time_mel_masks, mel2ph, spk_embed, f0, uv, energy, skip_decoder=True, infer=infer,
+                      use_pred_mel2ph=use_pred_mel2ph, use_pred_pitch=use_pred_pitch)
+        decoder_inp = ret["decoder_inp"]
+        tgt_nonpadding = (mel2ph > 0).float()[:, :, None]
+        decoder_inp = decoder_inp + self.mel_encoder(ref_mels * (1 - time_mel_masks)) * tgt_nonpadding
+        ret["decoder_inp"] = decoder_inp
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())      # follows torch.manual_seed like the reference's randn
+        x = self._engine().sample(decoder_inp.contiguous(), noise, seed)  # = x[:, 0].transpose(1, 2) of the reference loop
+        ret["mel_out"] = x
+        return ret
+
+    def norm_spec(self, x):
+        return x
+
+    def denorm_spec(self, x):
+        return x
+
+    def out2mel(self, x):
+        return x

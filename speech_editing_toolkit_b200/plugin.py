@@ -1,0 +1,183 @@
+"""The reference's task / inference seams for the spec_denoiser path, backed by the C ABI:
+
+  DIFF_DECODERS                       tasks/speech_editing/spec_denoiser.py:13-15 (+ inference/tts/spec_denoiser.py:26-28)
+  SpeechDenoiserTaskB200.start()      task_cls contract of tasks/run.py:9-14 (inference / test side of
+                                      tasks/speech_editing/spec_denoiser.py::SpeechDenoiserTask)
+  SpecDenoiserInferB200               class + method surface of inference/tts/spec_denoiser.py::SpecDenoiserInfer
+                                      (build_model / build_vocoder / run_vocoder / forward_model / infer_once)
+  install_into_reference()            registers the B200 denoiser / vocoder in the reference's own registries
+
+Text / MFA / pitch front-ends (g2p_en, MFA binary, parselmouth, resemblyzer) are outside the hot path; these
+classes take tensors at the `GaussianDiffusion.forward` boundary, like the benchmark does.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import synth
+from .ckpt import load_ckpt
+from .hparams import hparams, set_hparams
+from .modules import DiffNetB200, GaussianDiffusionB200
+from .vocoder import HifiGANB200, get_vocoder_cls, register_vocoder  # noqa: F401
+
+DIFF_DECODERS = {
+    "wavenet": lambda hp: DiffNetB200(hp["audio_num_mel_bins"], hp),
+    "wavenet_b200": lambda hp: DiffNetB200(hp["audio_num_mel_bins"], hp),
+}
+
+
+def install_into_reference() -> dict:
+    """Inside the reference tree: add 'wavenet_b200' to both DIFF_DECODERS dicts and 'HifiGAN_B200' to the
+    vocoder registry, so that `-hp diff_decoder_type=wavenet_b200,vocoder=HifiGAN_B200` selects this path."""
+    done = {}
+    for mod_name in ("tasks.speech_editing.spec_denoiser", "inference.tts.spec_denoiser"):
+        try:
+            mod = importlib.import_module(mod_name)
+            mod.DIFF_DECODERS["wavenet_b200"] = DIFF_DECODERS["wavenet_b200"]
+            done[mod_name] = True
+        except Exception as e:                       # reference (or one of its heavy deps) not importable here
+            done[mod_name] = repr(e)
+    try:
+        bv = importlib.import_module("tasks.tts.vocoder_infer.base_vocoder")
+        bv.REGISTERED_VOCODERS["HifiGAN_B200"] = HifiGANB200
+        done["vocoder"] = True
+    except Exception as e:
+        done["vocoder"] = repr(e)
+    return done
+
+
+def build_diffusion(hp: dict, phone_encoder=None, fs=None, mel_encoder=None) -> GaussianDiffusionB200:
+    """build_tts_model of the task (tasks/speech_editing/spec_denoiser.py:29-36) with the same hparams keys."""
+    return GaussianDiffusionB200(
+        phone_encoder=phone_encoder, out_dims=hp["audio_num_mel_bins"],
+        denoise_fn=DIFF_DECODERS[hp.get("diff_decoder_type", "wavenet")](hp),
+        timesteps=hp["timesteps"], time_scale=hp["timescale"], loss_type=hp["diff_loss_type"],
+        spec_min=hp["spec_min"], spec_max=hp["spec_max"], fs=fs, mel_encoder=mel_encoder, hparams=hp)
+
+
+class SpecDenoiserInferB200:
+    """inference/tts/spec_denoiser.py::SpecDenoiserInfer from the tensor boundary on."""
+
+    def __init__(self, hparams_: dict, device=None, fs=None, vocoder: Optional[HifiGANB200] = None):
+        self.hparams = hparams_
+        self.device = torch.device(device or "cuda")
+        self._fs = fs
+        self.model = self.build_model()
+        self.vocoder = vocoder if vocoder is not None else self.build_vocoder()
+
+    def build_model(self):
+        model = build_diffusion(self.hparams, fs=self._fs)
+        work_dir = self.hparams.get("work_dir", "")
+        if work_dir and os.path.isdir(work_dir):
+            load_ckpt(model, work_dir, "model", force=False, strict=False)     # schedule buffers depend on `timesteps`
+        return model.to(self.device).eval()
+
+    def build_vocoder(self):
+        ckpt = self.hparams.get("vocoder_ckpt", "")
+        if ckpt and os.path.exists(f"{ckpt}/config.yaml"):
+            return HifiGANB200(ckpt)
+        raise FileNotFoundError(f"vocoder checkpoint dir '{ckpt}' not found (config.yaml + model_ckpt_steps_*.ckpt)")
+
+    def run_vocoder(self, c: torch.Tensor) -> torch.Tensor:
+        """c[B,T,80] -> [B, T*hop]   (inference/tts/base_tts_infer.py:44-47)"""
+        return self.vocoder(c.to(self.device))
+
+    @torch.no_grad()
+    def forward_model(self, inp: dict):
+        """`inp` holds the tensors the reference builds just before calling the model
+        (inference/tts/spec_denoiser.py:133-138): either the full condition-encoder inputs (needs `fs`) or a
+        ready `cond[B,T,H]`.  Returns (wav_out, mel_out) like the reference's first two outputs per item."""
+        dev = self.device
+        ref = inp["ref_mels"].to(dev)
+        mask = inp["time_mel_masks"].to(dev).reshape(ref.shape[0], ref.shape[1], 1)
+        if "cond" in inp:
+            mel = self.model.sample(inp["cond"].to(dev), inp.get("noise"), int(inp.get("seed", 0)), ref, mask)
+        else:
+            out = self.model(inp["txt_tokens"].to(dev), time_mel_masks=mask, mel2ph=inp["mel2ph"].to(dev),
+                             spk_embed=inp["spk_embed"].to(dev), ref_mels=ref, f0=inp.get("f0"), uv=inp.get("uv"), energy=None,
+                             infer=True, use_pred_pitch=inp.get("use_pred_pitch", True), seed=inp.get("seed"))
+            mel = out["mel_out"] * mask + ref * (1 - mask)                       # :136
+        wav = self.run_vocoder(mel)
+        return wav, mel
+
+    def infer_once(self, inp: dict):
+        wav, mel = self.forward_model(inp)
+        return wav.cpu().numpy(), mel.cpu().numpy()
+
+
+class SpeechDenoiserTaskB200:
+    """task_cls for `--config egs/spec_denoiser.yaml -hp task_cls=speech_editing_toolkit_b200.plugin.SpeechDenoiserTaskB200`.
+
+    Only the inference / test leg of the reference task is provided (sampling + vocoder); `start()` runs it over
+    synthetic editing batches of the configured shape and reports throughput (no dataset, no trainer)."""
+
+    def __init__(self):
+        self.hparams = hparams
+        self.model = None
+        self.vocoder = None
+
+    def build_model(self):
+        self.model = build_diffusion(self.hparams).cuda().eval()
+        return self.model
+
+    def build_vocoder(self):
+        ckpt = self.hparams.get("vocoder_ckpt", "")
+        if ckpt and os.path.exists(f"{ckpt}/config.yaml"):
+            self.vocoder = HifiGANB200(ckpt)
+        else:                                                      # no shipped checkpoint: seeded HiFi-GAN V1 weights
+            self.vocoder = HifiGANB200(state_dict=synth.hifigan_state_dict(self.hparams.get("seed", 1234)))
+        return self.vocoder
+
+    @torch.no_grad()
+    def test_step(self, sample: dict, batch_idx: int = 0):
+        """speech_editing_base.py:151-192 minus file output: sample -> composite -> vocoder."""
+        dev = torch.device("cuda")
+        ref = sample["mels"].to(dev)
+        mask = sample["time_mel_masks"].to(dev)
+        mel = self.model.sample(sample["cond"].to(dev), None, int(sample.get("seed", batch_idx)), ref, mask)
+        wav = self.vocoder(mel)
+        return {"mel_out": mel, "wav_out": wav}
+
+    @classmethod
+    def start(cls):
+        import time
+        task = cls()
+        hp = task.hparams
+        task.build_model()
+        if hp.get("work_dir") and os.path.isdir(hp["work_dir"]):
+            load_ckpt(task.model, hp["work_dir"], "model", force=False, strict=False)
+        else:
+            task.model.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in synth.denoiser_state_dict(
+                hp.get("seed", 1234), hp["audio_num_mel_bins"], hp["hidden_size"], hp["residual_channels"], hp["residual_layers"]).items()})
+        task.build_vocoder()
+        B, T = int(hp.get("max_sentences", 16)), int(hp.get("b200_frames", 1024))
+        batch = synth.synthetic_edit_batch(hp.get("seed", 1234), B, T, hp["audio_num_mel_bins"])
+        sample = {"cond": torch.from_numpy(synth.synthetic_cond(hp.get("seed", 1234), B, T, hp["hidden_size"])),
+                  "mels": torch.from_numpy(batch["ref_mels"]), "time_mel_masks": torch.from_numpy(batch["time_mel_masks"])}
+        task.test_step(sample)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = task.test_step(sample, 1)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        audio = B * T * hp.get("hop_size", 256) / hp.get("audio_sample_rate", 22050)
+        print(f"| B200 spec_denoiser: {B}x{T} frames, {hp['timesteps']} steps + vocoder in {dt * 1e3:.1f} ms "
+              f"({B * T / dt:.0f} mel-frames/s, RTF {dt / audio:.5f}); mel {tuple(out['mel_out'].shape)} wav {tuple(out['wav_out'].shape)}")
+        return out
+
+
+def run_task():
+    """tasks/run.py:9-14 — import hparams['task_cls'] by dotted path and call .start()."""
+    assert hparams["task_cls"] != ""
+    pkg, cls_name = hparams["task_cls"].rsplit(".", 1)
+    getattr(importlib.import_module(pkg), cls_name).start()
+
+
+if __name__ == "__main__":
+    set_hparams()
+    run_task()

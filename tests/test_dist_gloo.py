@@ -1,0 +1,51 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the batch sharding + terminal all_gather."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from speech_editing_toolkit_b200 import dist as fdist
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (1, 5, 32, 33, 256):
+        for w in (1, 2, 3, 4, 8):
+            spans = [fdist.shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cond = torch.arange(n * 3 * 2, dtype=torch.float32).reshape(n, 3, 2)
+        mask = torch.arange(n, dtype=torch.float32).reshape(n, 1)
+        fn = lambda c, m: c * 2 + m[:, :, None]           # stand-in for "sample my shard"
+        out = fdist.run_sharded(fn, [cond, mask])
+        ok = torch.equal(out, fn(cond, mask))
+        q.put((rank, bool(ok), tuple(out.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [8, 5])
+def test_run_sharded_world2_gloo(n):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] for r in res) and all(r[2] == (n, 3, 2) for r in res)

@@ -1,0 +1,113 @@
+"""Host-side mirror of the reference seams (no GPU): config surface, state_dict layout, registries,
+checkpoint layout."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from oracle import refshim
+from speech_editing_toolkit_b200 import ckpt, hparams as hp_mod, synth
+
+needs_ref = pytest.mark.skipif(not refshim.available(), reason="reference tree not present (GPU box)")
+
+HP = dict(audio_num_mel_bins=80, hidden_size=192, residual_layers=20, residual_channels=256, dilation_cycle_length=1,
+          timesteps=8, timescale=1, diff_loss_type="l1", spec_min=[], spec_max=[], keep_bins=80, schedule_type="vpsde",
+          diff_decoder_type="wavenet")
+
+
+def test_set_hparams_base_chain_overrides_and_types(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "egs").mkdir()
+    (tmp_path / "egs" / "base.yaml").write_text("a: 1\nlr: 0.1\nlst: [1, 2]\nflag: false\nsub: {x: 1, y: 2}\nname: base\n")
+    (tmp_path / "egs" / "mid.yaml").write_text("base_config: ./base.yaml\na: 2\nsub: {y: 3}\n")
+    (tmp_path / "egs" / "top.yaml").write_text("base_config:\n  - egs/mid.yaml\nname: top\n")
+    cfg = hp_mod.set_hparams("egs/top.yaml", hparams_str="lr=0.5,lst=[3 4 5],flag=True,sub.x=7,name=z", print_hparams=False)
+    assert cfg["a"] == 2 and cfg["name"] == "z" and cfg["lr"] == 0.5 and cfg["lst"] == [3, 4, 5] and cfg["flag"] is True
+    assert cfg["sub"] == {"x": 7, "y": 3}
+    assert hp_mod.hparams["a"] == 2 and hp_mod.hparams["work_dir"] == "" and hp_mod.hparams["infer"] is False
+    # exp_name: config is saved once and wins over the yaml afterwards unless reset (reference: hparams.py:93-107,130-133)
+    hp_mod.set_hparams("egs/top.yaml", exp_name="e1", hparams_str="a=5", print_hparams=False)
+    assert yaml.safe_load(open("checkpoints/e1/config.yaml"))["a"] == 5
+    again = hp_mod.set_hparams("egs/top.yaml", exp_name="e1", print_hparams=False, global_hparams=False)
+    assert again["a"] == 5 and again["work_dir"] == "checkpoints/e1"
+
+
+@needs_ref
+@pytest.mark.parametrize("cfg,ov", [("egs/spec_denoiser.yaml", "timesteps=100"), ("egs/spec_denoiser_libritts.yaml", "timesteps=100,lr=0.001"),
+                                    ("egs/campnet.yaml", "max_sentences=64")])
+def test_reference_yaml_loads_unchanged_and_matches_reference_loader(cfg, ov, monkeypatch):
+    monkeypatch.chdir(refshim.REF_ROOT)
+    ours = hp_mod.set_hparams(cfg, hparams_str=ov, print_hparams=False, global_hparams=False)
+    ref_hp = refshim.install(cfg, overrides=ov)
+    assert ours == dict(ref_hp)
+    if "timesteps" in ov:
+        assert ours["timesteps"] == 100 and ours["residual_layers"] == 20
+
+
+def test_diffnet_state_dict_layout_and_checkpoint_roundtrip(tmp_path):
+    from speech_editing_toolkit_b200.modules import DiffNetB200, GaussianDiffusionB200
+    net = DiffNetB200(80, HP)
+    sd = synth.denoiser_state_dict(3)
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: v.shape for k, v in sd.items()}
+    assert float(net.output_projection.weight.abs().sum()) == 0.0            # zero init like the reference
+    model = GaussianDiffusionB200(None, 80, net, timesteps=8, hparams=HP)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    # trainer.py:457-470 layout, load_ckpt(model, dir, 'model')
+    torch.save({"state_dict": {"model": model.state_dict()}, "global_step": 7}, tmp_path / "model_ckpt_steps_7.ckpt")
+    torch.save({"state_dict": {"model": {}}, "global_step": 3}, tmp_path / "model_ckpt_steps_3.ckpt")
+    fresh = GaussianDiffusionB200(None, 80, DiffNetB200(80, HP), timesteps=8, hparams=HP)
+    path = ckpt.load_ckpt(fresh, str(tmp_path), "model")
+    assert path.endswith("model_ckpt_steps_7.ckpt")
+    for k, v in sd.items():
+        assert np.array_equal(fresh.denoise_fn.state_dict()[k].numpy(), v)
+    assert np.array_equal(fresh.posterior_mean_coef1.numpy(), model.posterior_mean_coef1.numpy())
+    with pytest.raises(NotImplementedError):
+        fresh(None, None, None, None, None, None, None, infer=False)
+
+
+@needs_ref
+def test_state_dict_keys_match_live_reference_modules():
+    refshim.install("egs/spec_denoiser.yaml")
+    from modules.speech_editing.spec_denoiser.diffnet import DiffNet
+    from modules.speech_editing.spec_denoiser.spec_denoiser import GaussianDiffusion
+    from speech_editing_toolkit_b200.modules import DiffNetB200, GaussianDiffusionB200
+    ref_net = DiffNet(80)
+    ours = DiffNetB200(80, HP)
+    assert {k: tuple(v.shape) for k, v in ours.state_dict().items()} == {k: tuple(v.shape) for k, v in ref_net.state_dict().items()}
+    ref = GaussianDiffusion(list(range(80)), 80, ref_net, timesteps=8, time_scale=1, loss_type="l1", spec_min=[], spec_max=[])
+    wrapped = GaussianDiffusionB200.from_reference(ref)
+    rsd, osd = ref.state_dict(), wrapped.state_dict()
+    assert set(rsd) == set(osd)
+    for k in rsd:
+        if not k.startswith(("fs.", "mel_encoder.", "denoise_fn.")):
+            assert torch.equal(rsd[k], osd[k]), k
+    assert wrapped.fs is ref.fs and wrapped.mel_encoder is ref.mel_encoder
+
+
+def test_registries_and_plugin_surface():
+    from speech_editing_toolkit_b200 import plugin, vocoder
+    assert vocoder.get_vocoder_cls("HifiGAN") is vocoder.HifiGANB200 and vocoder.get_vocoder_cls("HifiGAN_B200") is vocoder.HifiGANB200
+    assert vocoder.get_vocoder_cls("nope") is None
+    assert set(plugin.DIFF_DECODERS) == {"wavenet", "wavenet_b200"}
+    m = plugin.build_diffusion(HP)
+    assert type(m.denoise_fn).__name__ == "DiffNetB200" and m.num_timesteps == 8
+    for meth in ("build_model", "build_vocoder", "run_vocoder", "forward_model", "infer_once"):
+        assert hasattr(plugin.SpecDenoiserInferB200, meth)
+    assert hasattr(plugin.SpeechDenoiserTaskB200, "start") and callable(plugin.run_task)
+
+
+def test_vocoder_checkpoint_layout(tmp_path):
+    """<vocoder_ckpt>/config.yaml + model_ckpt_steps_N.ckpt with state_dict['model_gen']."""
+    from speech_editing_toolkit_b200.engine import HIFIGAN_V1
+    from speech_editing_toolkit_b200 import FseError
+    from speech_editing_toolkit_b200.vocoder import HifiGANB200
+    sd = synth.hifigan_state_dict(1)
+    assert sd["ups.0.weight_v"].shape == (512, 256, 16) and sd["ups.0.weight_g"].shape == (512, 1, 1)     # ConvTranspose1d: dim 0 = C_in
+    assert sd["conv_post.weight_v"].shape == (1, 32, 7) and len(sd) == 234
+    yaml.safe_dump(dict(HIFIGAN_V1, audio_num_mel_bins=80), open(tmp_path / "config.yaml", "w"))
+    torch.save({"state_dict": {"model_gen": {k: torch.from_numpy(v) for k, v in sd.items()}}}, tmp_path / "model_ckpt_steps_100.ckpt")
+    if not torch.cuda.is_available():
+        with pytest.raises(FseError):                 # files are found and parsed; only the CUDA handle cannot be made here
+            HifiGANB200(str(tmp_path))
