@@ -163,7 +163,10 @@ int fse_vocoder_profile_read(fse_vocoder* h, double* ms_by_kind, int64_t* launch
  * mode is FSE_MODE_TC_BF16 or FSE_MODE_SIMT_BF16. */
 int fse_debug_conv_gemm(int32_t mode, const void* A0, const void* W, float* out, int32_t B, int32_t T, int32_t C0,
                         int32_t ntaps, const int32_t* offs, int32_t N, int32_t BN, int32_t KB, void* stream,
-                        int64_t* dbg_stamps /* device [16] or NULL: clock64 phase stamps of CTA 0 */);
+                        int64_t* dbg_stamps /* device [32] or NULL: clock64 phase stamps of CTA 0 */,
+                        int32_t shared_a /* 0: one activation load per tap; 1: one load per channel block, taps read
+                                            row-shifted descriptors (2: probe variant that also sets the descriptor
+                                            base-offset field; measured wrong on B200) */);
 
 #ifdef __cplusplus
 }

@@ -63,7 +63,7 @@ SIGNATURES = {
     "fse_vocoder_profile": (C.c_int, [_P, C.c_int32]),
     "fse_vocoder_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "fse_debug_conv_gemm": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                      C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+                                      C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32]),
 }
 
 _lib = None

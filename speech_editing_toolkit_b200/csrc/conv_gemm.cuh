@@ -37,6 +37,11 @@ struct ConvGemmParams {
   int nkb1;    // k-blocks for source 1
   int N;       // output columns
   int Kp;      // padded K of the packed weight = (ntaps*nkb0 + nkb1)*KB
+  int shared_a;  // 1: load each channel block of source 0 ONCE per tile (Rrows = 128 + tap span rows) and feed every tap
+                 //    from row-shifted UMMA descriptors of that one smem copy (cuts activation ingest by ntaps)
+  int off_min;   // smallest tap offset; Rrows = 128 + max(off) - min(off)
+  int Rrows;
+  int bo_mode;   // descriptor base-offset convention for row-shifted starts (test hook; 1 = (addr>>7)&7)
   long long* dbg;  // optional [32] clock64 phase stamps of CTA 0 (test hook), else null
 };
 
@@ -174,27 +179,31 @@ constexpr int kTileM = 128;       // frames per tile = TMEM lanes
 
 __host__ __device__ inline int tc_b_stage_bytes(int BN, int KB) { return ((BN * KB * 2 + 1023) / 1024) * 1024; }
 __host__ __device__ inline int tc_a_stage_bytes(int KB) { return kTileM * KB * 2; }
-__host__ inline size_t tc_smem_bytes(int BN, int KB, int stages) {
-  return 1024 + static_cast<size_t>(stages) * (tc_a_stage_bytes(KB) + tc_b_stage_bytes(BN, KB)) + 8 * (2 * stages + 4) + 16;
+__host__ inline size_t tc_smem_bytes(int BN, int KB, int stages, int a_slots, int a_slot_bytes) {
+  return 1024 + static_cast<size_t>(a_slots) * a_slot_bytes + static_cast<size_t>(stages) * tc_b_stage_bytes(BN, KB) +
+         8 * (2 * stages + 4 + 2 * a_slots) + 16;
 }
 
 template <int KB, int CH, class Epi>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                    const __grid_constant__ CUtensorMap mapW, ConvGemmParams p, int BN, int stages, Epi epi) {
+                    const __grid_constant__ CUtensorMap mapW, ConvGemmParams p, int BN, int stages, int a_slots,
+                    int a_slot_bytes, Epi epi) {
   static_assert(KB == 64 || KB == 32, "k-block");
   static_assert(CH == 32 || CH == 16, "epilogue chunk");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int A_BYTES = tc_a_stage_bytes(KB);
+  const int A_BYTES = a_slot_bytes;        // non-shared mode: a_slots == stages, one A tile per W stage
   const int B_BYTES = tc_b_stage_bytes(BN, KB);
   uint8_t* sA = smem;
-  uint8_t* sB = smem + stages * A_BYTES;
+  uint8_t* sB = smem + a_slots * A_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * B_BYTES);
   uint64_t* empty = full + stages;
   uint64_t* acc_full = empty + stages;     // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* a_full = acc_empty + 2;        // [a_slots] (shared-A mode)
+  uint64_t* a_empty = a_full + a_slots;    // [a_slots]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + a_slots);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -223,6 +232,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         ptx::mbar_init(&acc_full[i], 1);
         ptx::mbar_init(&acc_empty[i], kEpiWarps);
       }
+      for (int i = 0; i < a_slots; ++i) {
+        ptx::mbar_init(&a_full[i], 1);
+        ptx::mbar_init(&a_empty[i], 1);
+      }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -233,12 +246,40 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may
+  // overlap the tail of the previous kernel in the stream; no global memory is touched before this point.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      const uint32_t tx_bytes = static_cast<uint32_t>(A_BYTES + BN * KB * 2);
+    if (lane == 0 && p.shared_a) {
+      int kbg = 0, ga = 0;
+      const int ngroups = p.nkb0 + p.nkb1;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m = tile / n_tiles, n0 = (tile % n_tiles) * BN;
+        const int b = p.b_off + m / tiles_per_item, t0 = (m % tiles_per_item) * kTileM;
+        for (int g = 0; g < ngroups; ++g, ++ga) {
+          const int slot = ga % a_slots;
+          ptx::mbar_wait(&a_empty[slot], ((ga / a_slots) & 1) ^ 1u);
+          const bool src0 = g < p.nkb0;
+          ptx::mbar_arrive_expect_tx(&a_full[slot], static_cast<uint32_t>((src0 ? p.Rrows : kTileM) * KB * 2));
+          if (src0) ptx::tma_load_3d(sA + slot * A_BYTES, &mapA0, &a_full[slot], p.c_off0 + g * KB, t0 + p.off_min, b);
+          else ptx::tma_load_3d(sA + slot * A_BYTES, &mapA1, &a_full[slot], (g - p.nkb0) * KB, t0, b);
+          const int ntap = src0 ? p.ntaps : 1;
+          for (int j = 0; j < ntap; ++j, ++kbg) {
+            const int s = kbg % stages;
+            ptx::mbar_wait(&empty[s], ((kbg / stages) & 1) ^ 1u);
+            ptx::mbar_arrive_expect_tx(&full[s], static_cast<uint32_t>(BN * KB * 2));
+            const int kb = src0 ? j * p.nkb0 + g : nkb_src0 + (g - p.nkb0);
+            ptx::tma_load_2d(sB + s * B_BYTES, &mapW, &full[s], kb * KB, n0);
+          }
+        }
+        if (dbg && tile == blockIdx.x) dbg[2] = clock64();
+      }
+    } else if (lane == 0) {
+      const uint32_t tx_bytes = static_cast<uint32_t>(kTileM * KB * 2 + BN * KB * 2);
       int kbg = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m = tile / n_tiles, n0 = (tile % n_tiles) * BN;
@@ -263,7 +304,52 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     const uint32_t idesc = ptx::make_idesc_bf16_f32(kTileM, BN);
-    int kbg = 0, it = 0;
+    int kbg = 0, it = 0, ga = 0;
+    if (p.shared_a) {
+      const int ngroups = p.nkb0 + p.nkb1;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
+        uint32_t accum = 0;
+        for (int g = 0; g < ngroups; ++g, ++ga) {
+          const int slot = ga % a_slots;
+          ptx::mbar_wait(&a_full[slot], (ga / a_slots) & 1);
+          const bool src0 = g < p.nkb0;
+          const int ntap = src0 ? p.ntaps : 1;
+          for (int j = 0; j < ntap; ++j, ++kbg) {
+            const int s = kbg % stages;
+            ptx::mbar_wait(&full[s], (kbg / stages) & 1);
+            ptx::tc_fence_after();
+            if (dbg && lane == 0 && kbg == 0) dbg[3] = clock64();
+            if (lane == 0) {
+              // row-shifted view of the one smem copy: tap j reads rows [shift, shift+128) of the Rrows-row tile
+              const int shift = src0 ? p.tap_off[j] - p.off_min : 0;
+              const uint32_t a_addr = ptx::smem_u32(sA + slot * A_BYTES) + static_cast<uint32_t>(shift * KB * 2);
+              const uint32_t b_addr = ptx::smem_u32(sB + s * B_BYTES);
+              const uint32_t bo = p.bo_mode ? ((a_addr >> 7) & (KB == 64 ? 7u : 3u)) : 0u;
+              const uint64_t da = ((KB == 64) ? ptx::make_desc_k_sw128(a_addr) : ptx::make_desc_k_sw64(a_addr)) |
+                                  (static_cast<uint64_t>(bo) << 49);
+              const uint64_t db = (KB == 64) ? ptx::make_desc_k_sw128(b_addr) : ptx::make_desc_k_sw64(b_addr);
+#pragma unroll
+              for (int k = 0; k < KB / 16; ++k) ptx::mma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, accum | (k != 0 ? 1u : 0u));
+              ptx::mma_commit(&empty[s]);
+            }
+            accum = 1;
+            __syncwarp();
+          }
+          if (lane == 0) {
+            ptx::mma_commit(&a_empty[slot]);
+            if (g == ngroups - 1) {
+              ptx::mma_commit(&acc_full[buf]);
+              if (dbg && it == 0) dbg[4] = clock64();
+            }
+          }
+          __syncwarp();
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u);
@@ -301,7 +387,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     const int half = ew >> 2;               // two warps share a quarter and split the column chunks
     const int nchunks = BN / CH;
     constexpr int AUXN = CH * (Epi::kAux > 0 ? Epi::kAux : 1);
-    constexpr bool kPrefetch = Epi::kAux > 0 && AUXN <= 32;   // double-buffer only when it fits the register file
+    // Residual operands: when a warp owns at most kMaxPre chunks of a tile and they fit in 64 registers, ALL of
+    // them are requested before the accumulator is awaited (one exposed memory latency per tile); otherwise the
+    // next chunk's operands are requested while the current chunk is processed (when they fit in 32 registers).
+    constexpr int kMaxPre = (Epi::kAux > 0 && AUXN <= 32) ? 64 / AUXN : 0;
+    constexpr bool kChunkAhead = Epi::kAux > 0 && AUXN <= 32;
+    const int my_chunks = (nchunks - half + 1) / 2;
+    const bool pre_all = kMaxPre > 0 && my_chunks <= kMaxPre;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -310,38 +402,61 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       const int t = t0 + q * 32 + lane;
       const bool row_ok = t < p.Trows;
       const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
-      float aux[AUXN];
-      if constexpr (kPrefetch) {
-        if (half < nchunks && row_ok) epi.template load_aux<CH>(b, t, n0 + half * CH, aux);
+      float aux[kMaxPre > 0 ? kMaxPre : 1][AUXN];
+      if constexpr (kChunkAhead) {
+        if (row_ok) {
+          if (pre_all) {
+#pragma unroll
+            for (int i = 0; i < kMaxPre; ++i)
+              if (i < my_chunks) epi.template load_aux<CH>(b, t, n0 + (half + 2 * i) * CH, aux[i]);
+          } else if (half < nchunks) {
+            epi.template load_aux<CH>(b, t, n0 + half * CH, aux[0]);
+          }
+        }
       }
       ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
       ptx::tc_fence_after();
       if (dbg && ew == 0 && lane == 0 && it == 0) dbg[5] = clock64();   // first accumulator complete
-      for (int c = half; c < nchunks; c += 2) {
+      int ci = 0;
+      for (int c = half; c < nchunks; c += 2, ++ci) {
         uint32_t r[CH];
         const bool stamp = dbg && ew == 0 && lane == 0 && it == 0 && c < 8;
         if (stamp) dbg[16 + 4 * (c >> 1)] = clock64();
-        if constexpr (Epi::kAux > 0 && !kPrefetch) {
-          if (row_ok) epi.template load_aux<CH>(b, t, n0 + c * CH, aux);
+        float aux_here[(Epi::kAux > 0 && !kChunkAhead) ? AUXN : 1];
+        if constexpr (Epi::kAux > 0 && !kChunkAhead) {
+          if (row_ok) epi.template load_aux<CH>(b, t, n0 + c * CH, aux_here);
         }
         if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(lane_base + c * CH, r);
         else ptx::tmem_ld_32x32b_x16(lane_base + c * CH, r);
         ptx::tmem_wait_ld();
         if (stamp) dbg[17 + 4 * (c >> 1)] = clock64();
-        float aux_next[kPrefetch ? AUXN : 1];
-        if constexpr (kPrefetch) {
-          if (c + 2 < nchunks && row_ok) epi.template load_aux<CH>(b, t, n0 + (c + 2) * CH, aux_next);
+        float aux_next[kChunkAhead ? AUXN : 1];
+        if constexpr (kChunkAhead) {
+          if (!pre_all && c + 2 < nchunks && row_ok) epi.template load_aux<CH>(b, t, n0 + (c + 2) * CH, aux_next);
         }
         if (stamp) dbg[18 + 4 * (c >> 1)] = clock64();
         if (row_ok) {
           float v[CH];
 #pragma unroll
           for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
-          epi.template apply<CH>(b, t, n0 + c * CH, v, aux);
-        }
-        if constexpr (kPrefetch) {
+          if constexpr (kChunkAhead) {
+            if (pre_all) {
+              // static register indexing: pick the pre-loaded set of this chunk
 #pragma unroll
-          for (int j = 0; j < AUXN; ++j) aux[j] = aux_next[j];
+              for (int i = 0; i < kMaxPre; ++i)
+                if (i == ci) epi.template apply<CH>(b, t, n0 + c * CH, v, aux[i]);
+            } else {
+              epi.template apply<CH>(b, t, n0 + c * CH, v, aux[0]);
+            }
+          } else {
+            epi.template apply<CH>(b, t, n0 + c * CH, v, aux_here);
+          }
+        }
+        if constexpr (kChunkAhead) {
+          if (!pre_all) {
+#pragma unroll
+            for (int j = 0; j < AUXN; ++j) aux[0][j] = aux_next[j];
+          }
         }
         if (stamp) dbg[19 + 4 * (c >> 1)] = clock64();
       }

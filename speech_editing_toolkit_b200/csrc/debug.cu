@@ -17,7 +17,8 @@ struct EpiStore {
 using namespace fse;
 
 extern "C" int fse_debug_conv_gemm(int32_t mode, const void* A0, const void* W, float* out, int32_t B, int32_t T, int32_t C0,
-                                   int32_t ntaps, const int32_t* offs, int32_t N, int32_t BN, int32_t KB, void* stream, int64_t* dbg_stamps) {
+                                   int32_t ntaps, const int32_t* offs, int32_t N, int32_t BN, int32_t KB, void* stream, int64_t* dbg_stamps,
+                                   int32_t shared_a /* 0 = one A load per tap, 1 = shared-A schedule (2 = same with descriptor base-offset set: known wrong, kept as a probe) */) {
   if (!A0 || !W || !out || !offs) return fail(FSE_EINVAL, "null argument");
   if (ntaps <= 0 || ntaps > kMaxTaps) return fail(FSE_EINVAL, "ntaps out of range");
   if (KB != 64 && KB != 32) return fail(FSE_EINVAL, "KB must be 32 or 64");
@@ -29,7 +30,13 @@ extern "C" int fse_debug_conv_gemm(int32_t mode, const void* A0, const void* W, 
   GemmOperands op; op.A0 = A0; op.W = W; op.BN = BN;
   CUtensorMap mA{}, mW{};
   if (mode == FSE_MODE_TC_BF16) {
-    FSE_TRY(make_map_act(&mA, A0, C0, T, B, KB));
+    int rows = kTileM;
+    if (shared_a) {
+      if (!enable_shared_a(p)) return fail(FSE_EINVAL, "shared-A schedule needs >= 2 taps and a span <= 128 rows");
+      p.bo_mode = shared_a == 2 ? 1 : 0;
+      rows = p.Rrows;
+    }
+    FSE_TRY(make_map_act(&mA, A0, C0, T, B, KB, rows));
     FSE_TRY(make_map_w(&mW, W, p.Kp, N, KB, BN));
     op.mA0 = &mA; op.mW = &mW;
   }

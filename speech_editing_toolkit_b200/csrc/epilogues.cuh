@@ -53,6 +53,24 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t step, uin
   z[2] = rb * c; z[3] = rb * s;
 }
 
+// Streaming (evict-first) stores for write-once data that is not re-read soon (the per-layer gate outputs),
+// so they do not push the fp32 residual stream out of L2.
+template <int NV>
+__device__ __forceinline__ void st_vec_stream(float* p, const float* v) { st_vec<NV>(p, v); }
+template <int NV>
+__device__ __forceinline__ void st_vec_stream(__nv_bfloat16* p, const float* v) {
+  if constexpr (NV % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < NV / 8; ++i)
+      asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p + 8 * i), "r"(pack_bf16x2(v[8 * i], v[8 * i + 1])),
+                   "r"(pack_bf16x2(v[8 * i + 2], v[8 * i + 3])), "r"(pack_bf16x2(v[8 * i + 4], v[8 * i + 5])),
+                   "r"(pack_bf16x2(v[8 * i + 6], v[8 * i + 7]))
+                   : "memory");
+  } else {
+    st_vec<NV>(p, v);
+  }
+}
+
 // ------------------------------------------------------------------ input projection
 // h = relu(W_in x + b_in)  (diffnet.py:117-120); writes the fp32 residual stream and its operand copy.
 template <typename TOp>
@@ -109,7 +127,7 @@ struct EpiGate {
     float v[NV / 2];
 #pragma unroll
     for (int j = 0; j < NV / 2; ++j) v[j] = sigmoid_f<Fast>(y[2 * j]) * tanh_f<Fast>(y[2 * j + 1]);
-    st_vec<NV / 2>(u + (static_cast<size_t>(b) * T + t) * ldu + u_off + n0 / 2, v);
+    st_vec_stream<NV / 2>(u + (static_cast<size_t>(b) * T + t) * ldu + u_off + n0 / 2, v);
   }
 };
 

@@ -108,12 +108,12 @@ inline int get_encode_fn(PFN_tmapEncodeTiled* out) {
   return FSE_OK;
 }
 // bf16 activation [B, T, C] channels-last: dims (C, T, B), box (KB, 128, 1); out-of-range frames/channels read 0.
-inline int make_map_act(CUtensorMap* m, const void* ptr, int C, int T, int B, int KB) {
+inline int make_map_act(CUtensorMap* m, const void* ptr, int C, int T, int B, int KB, int rows = kTileM) {
   PFN_tmapEncodeTiled enc;
   FSE_TRY(get_encode_fn(&enc));
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
   cuuint64_t strides[2] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(T) * C * 2};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(KB), static_cast<cuuint32_t>(kTileM), 1};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(KB), static_cast<cuuint32_t>(rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -208,21 +208,48 @@ inline ConvGemmParams make_params(int B, int Trows, int Tsrc, int C0, int ntaps,
   return p;
 }
 
+// Switch a parameter block to the shared-A schedule (source-0 tile loaded once per channel block with the
+// tap halo; taps read row-shifted descriptors).  The A0 tensor map must have been made with rows = Rrows.
+inline bool enable_shared_a(ConvGemmParams& p) {
+  int lo = p.tap_off[0], hi = p.tap_off[0];
+  for (int i = 1; i < p.ntaps; ++i) { lo = p.tap_off[i] < lo ? p.tap_off[i] : lo; hi = p.tap_off[i] > hi ? p.tap_off[i] : hi; }
+  const int R = kTileM + hi - lo;
+  if (p.ntaps < 2 || R > 256) return false;
+  p.shared_a = 1; p.off_min = lo; p.Rrows = R; p.bo_mode = 0;   // measured on B200: the swizzle is a function of the
+  // absolute smem address, so a row-shifted start needs NO descriptor base-offset (tools/shared_a_check.py)
+  return true;
+}
+inline int shared_a_rows(int ntaps, const int* offs) {
+  int lo = offs[0], hi = offs[0];
+  for (int i = 1; i < ntaps; ++i) { lo = offs[i] < lo ? offs[i] : lo; hi = offs[i] > hi ? offs[i] : hi; }
+  return kTileM + hi - lo;
+}
+
 template <int KB, int CH, class Epi>
 inline int launch_tc(const ConvGemmParams& p, const GemmOperands& op, const Epi& epi, cudaStream_t st) {
   static bool attr_set = false;
   const int nkb = p.ntaps * p.nkb0 + p.nkb1;
-  const int stage_bytes = tc_a_stage_bytes(KB) + tc_b_stage_bytes(op.BN, KB);
-  int stages = (225 * 1024) / stage_bytes;
-  if (stages > 6) stages = 6;
+  int stages, a_slots, a_slot_bytes;
+  if (p.shared_a) {
+    a_slot_bytes = static_cast<int>(align_up(static_cast<size_t>(p.Rrows > kTileM ? p.Rrows : kTileM) * KB * 2, 1024));
+    a_slots = p.nkb0 + p.nkb1 < 3 ? p.nkb0 + p.nkb1 : 3;
+    stages = (225 * 1024 - a_slots * a_slot_bytes) / tc_b_stage_bytes(op.BN, KB);
+    if (stages > 8) stages = 8;
+  } else {
+    a_slot_bytes = tc_a_stage_bytes(KB);
+    stages = (225 * 1024) / (a_slot_bytes + tc_b_stage_bytes(op.BN, KB));
+    if (stages > 6) stages = 6;
+    a_slots = 0;   // = stages, set below
+  }
   if (stages > nkb) stages = nkb;
   if (stages < 1) return fail(FSE_EINVAL, "conv_gemm: tile does not fit shared memory");
+  if (!p.shared_a) a_slots = stages;
   auto kern = conv_gemm_tc_kernel<KB, CH, Epi>;
   if (!attr_set) {
     FSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem = tc_smem_bytes(op.BN, KB, stages);
+  const size_t smem = tc_smem_bytes(op.BN, KB, stages, a_slots, a_slot_bytes);
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
@@ -232,7 +259,17 @@ inline int launch_tc(const ConvGemmParams& p, const GemmOperands& op, const Epi&
   const int total_tiles = p.B * ((p.Trows + kTileM - 1) / kTileM) * (p.N / op.BN);
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);   // persistent: one CTA per SM
   const CUtensorMap* mA1 = op.mA1 ? op.mA1 : op.mA0;
-  kern<<<grid, kTcThreads, smem, st>>>(*op.mA0, *mA1, *op.mW, p, op.BN, stages, epi);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous kernel's tail
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FSE_CUDA(cudaLaunchKernelEx(&cfg, kern, *op.mA0, *mA1, *op.mW, p, op.BN, stages, a_slots, a_slot_bytes, epi));
   FSE_CUDA(cudaGetLastError());
   return FSE_OK;
 }

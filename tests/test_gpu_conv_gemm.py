@@ -9,13 +9,13 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 
-def run(mode, A, W, B, T, C0, offs, N, BN, KB):
+def run(mode, A, W, B, T, C0, offs, N, BN, KB, shared_a=0):
     from speech_editing_toolkit_b200 import _lib
     out = torch.full((B * T, N), float("nan"), dtype=torch.float32, device="cuda")
     arr = (C.c_int32 * len(offs))(*offs)
     _lib.check(_lib.lib().fse_debug_conv_gemm(_lib.MODES[mode], C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()),
                                               C.c_void_p(out.data_ptr()), B, T, C0, len(offs), arr, N, BN, KB,
-                                              C.c_void_p(torch.cuda.current_stream().cuda_stream), None))
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream), None, shared_a))
     torch.cuda.synchronize()
     return out.cpu().numpy()
 
@@ -34,10 +34,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("B,T,C0,offs,N,BN,KB", CASES)
-def test_conv_gemm_tc_vs_simt_vs_host(lib_built, B, T, C0, offs, N, BN, KB):
-    if not torch.cuda.is_available():
-        pytest.skip("no CUDA device")
+def _operands(B, T, C0, offs, N, KB):
     rs = np.random.RandomState(B * 7 + T + C0 + N)
     nkb = (C0 + KB - 1) // KB
     Kp = len(offs) * nkb * KB
@@ -56,10 +53,33 @@ def test_conv_gemm_tc_vs_simt_vs_host(lib_built, B, T, C0, offs, N, BN, KB):
         if hi > lo:
             sh[:, lo:hi] = Af[:, lo + off:hi + off]
         ref += sh @ Wf[:, j * nkb * KB:j * nkb * KB + C0].T
-    ref = ref.reshape(B * T, N)
+    return A, W, ref.reshape(B * T, N)
+
+
+@pytest.mark.parametrize("B,T,C0,offs,N,BN,KB", CASES)
+def test_conv_gemm_tc_vs_simt_vs_host(lib_built, B, T, C0, offs, N, BN, KB):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    A, W, ref = _operands(B, T, C0, offs, N, KB)
     simt = run("simt_bf16", A, W, B, T, C0, offs, N, BN, KB)
     assert np.abs(simt - ref).max() < 1e-3, "CUDA-core path disagrees with the host reference"
     tc = run("tc_bf16", A, W, B, T, C0, offs, N, BN, KB)
     assert np.isfinite(tc).all(), f"tensor-core path left {np.isnan(tc).sum()} outputs unwritten"
+    err = np.abs(tc - ref)
+    assert err.max() < 1e-3, f"max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+SHARED_CASES = [c for c in CASES if len(c[3]) >= 2 and max(c[3]) - min(c[3]) <= 128]
+
+
+@pytest.mark.parametrize("B,T,C0,offs,N,BN,KB", SHARED_CASES)
+def test_conv_gemm_shared_a_schedule(lib_built, B, T, C0, offs, N, BN, KB):
+    """One activation load per channel block; every tap is a row-shifted UMMA descriptor of that smem copy
+    (start address + rows*row_bytes, base-offset field 0: the swizzle is keyed on absolute smem address bits)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    A, W, ref = _operands(B, T, C0, offs, N, KB)
+    tc = run("tc_bf16", A, W, B, T, C0, offs, N, BN, KB, shared_a=1)
+    assert np.isfinite(tc).all()
     err = np.abs(tc - ref)
     assert err.max() < 1e-3, f"max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 from speech_editing_toolkit_b200 import _lib
 
-def run(name, B, T, C0, offs, N, BN, KB=64, reps=3):
+def run(name, B, T, C0, offs, N, BN, KB=64, reps=3, shared_a=0):
     nkb = (C0 + KB - 1) // KB
     Kp = len(offs) * nkb * KB
     A = torch.randn(B, T, C0, device="cuda").to(torch.bfloat16)
@@ -19,7 +19,7 @@ def run(name, B, T, C0, offs, N, BN, KB=64, reps=3):
         e0.record()
         _lib.check(_lib.lib().fse_debug_conv_gemm(0, C.c_void_p(A.data_ptr()), C.c_void_p(W.data_ptr()), C.c_void_p(out.data_ptr()),
                                                   B, T, C0, len(offs), arr, N, BN, KB, C.c_void_p(torch.cuda.current_stream().cuda_stream),
-                                                  C.c_void_p(dbg.data_ptr())))
+                                                  C.c_void_p(dbg.data_ptr()), shared_a))
         e1.record()
         torch.cuda.synchronize()
         d = dbg.cpu().numpy()
@@ -34,4 +34,5 @@ if __name__ == "__main__":
     run("gate full (512 tiles)", 32, 1024, 256, [-1, 0, 1, 0], 512, 256)
     run("res 1 tile/CTA", 4, 1024, 256, [0], 512, 256)
     run("res full", 32, 1024, 256, [0], 512, 256)
-    run("gate BN=128 full", 32, 1024, 256, [-1, 0, 1, 0], 512, 128)
+    run("gate shared-A full", 32, 1024, 256, [-1, 0, 1], 512, 256, shared_a=1)
+    run("gate separate-A full (3 taps)", 32, 1024, 256, [-1, 0, 1], 512, 256, shared_a=0)
