@@ -284,9 +284,15 @@ def run_b200(args):
     roofline = None
     if prof_d:
         g_ms, g_n = prof_d["gate_gemm"]
-        flops = 2.0 * B * T * 512 * 960                      # algorithmic: 0.983 MFLOP/frame (k=3 conv 512x768 + cond 512x192)
+        fused = prof_d["res_gemm"][1] == 0
+        if fused:   # one launch = all 20 residual layers: per layer gate GEMM 0.983 MFLOP/frame + residual GEMM 0.131 MFLOP/frame
+            flops = 20 * 2.0 * B * T * (512 * 960 + 256 * 256)
+            kname = "denoiser_layers_kernel (20 x [k=3 conv + cond 1x1 + gate -> residual 1x1], fused, persistent)"
+        else:
+            flops = 2.0 * B * T * 512 * 960                  # algorithmic: 0.983 MFLOP/frame (k=3 conv 512x768 + cond 512x192)
+            kname = "conv_gemm_tc_kernel<EpiGate> (dilated k=3 conv + conditioner 1x1 + gate)"
         ach = flops / (g_ms / g_n * 1e-3) / 1e12 if g_n else 0.0
-        roofline = {"kernel": "conv_gemm_tc_kernel<EpiGate> (dilated k=3 conv + conditioner 1x1 + gate)", "bound": "tensor",
+        roofline = {"kernel": kname, "bound": "tensor",
                     "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                     "peak_source": pk["src"] + ", sustained bf16", "traffic": None,
                     "avg_launch_us": g_ms / g_n * 1e3 if g_n else None, "launches_timed": g_n,

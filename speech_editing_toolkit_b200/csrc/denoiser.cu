@@ -7,6 +7,7 @@
 
 #include "epilogues.cuh"
 #include "fse_common.cuh"
+#include "denoiser_fused.cuh"
 
 namespace fse {
 
@@ -187,9 +188,14 @@ struct fse_denoiser {
   // tensor maps (tensor-core mode)
   CUtensorMap mW_in{}, mW_skip{}, mW_out{};
   std::vector<CUtensorMap> mW1, mW2;
+  // fused multi-layer kernel (denoiser_fused.cuh): per-layer weight maps in device memory, grid barrier word
+  bool fused = false;
+  CUtensorMap* d_mW1 = nullptr; CUtensorMap* d_mW2f = nullptr; unsigned int* d_grid_bar = nullptr;
+  int num_sms = 0;
   struct Plan {
     const void* ws = nullptr; const void* cond = nullptr; int B = 0, T = 0;
     CUtensorMap m_xb{}, m_hb{}, m_cond{}, m_u{}, m_rb{};
+    CUtensorMap m_hb0_halo{}, m_hb1_halo{};     // 130-row boxes of the two hb buffers (fused kernel)
   } plan;
   long long launches = 0;
   int batch_chunk = 0;     // utterances per L2-resident chunk (0 = whole batch); FSE_BATCH_CHUNK overrides
@@ -202,7 +208,7 @@ struct fse_denoiser {
 namespace {
 
 struct Workspace {
-  float* h; void* hb; void* u; void* rb; void* xb; void* condb;
+  float* h; void* hb; void* hb1; void* u; void* rb; void* xb; void* condb;
   float* xa; float* xbuf2; float* tvals; float* temb; float* d; float* dbias;
   size_t bytes;
 };
@@ -219,6 +225,7 @@ Workspace carve(const fse_denoiser* h, void* base, int B, int T) {
   size_t o;
   o = take(N * C * 4);  w.h = reinterpret_cast<float*>(p + o);
   o = take(N * C * es); w.hb = p + o;
+  o = take(h->fused ? N * C * es : 0); w.hb1 = p + o;
   o = take(N * L * C * es); w.u = p + o;      // gate outputs of ALL layers, [B*T, L*C]
   o = take(N * C * es); w.rb = p + o;
   o = take(N * M * es); w.xb = p + o;
@@ -252,6 +259,10 @@ int build_plan(fse_denoiser* h, const Workspace& w, const void* ws, const void* 
   FSE_TRY(make_map_act(&pl.m_cond, w.condb, h->cfg.hidden, T, B, 64));
   FSE_TRY(make_map_act(&pl.m_u, w.u, h->cfg.layers * C, T, B, 64));
   FSE_TRY(make_map_act(&pl.m_rb, w.rb, C, T, B, 64));
+  if (h->fused) {
+    FSE_TRY(make_map_act(&pl.m_hb0_halo, w.hb, C, T, B, 64, 130));
+    FSE_TRY(make_map_act(&pl.m_hb1_halo, w.hb1, C, T, B, 64, 130));
+  }
   pl.ws = ws; pl.B = B; pl.T = T; pl.cond = cond;
   return FSE_OK;
 }
@@ -298,6 +309,32 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
   }
   const int bn2 = (2 * C) % 256 == 0 ? 256 : 128;
   const int bnr = C % 128 == 0 ? 128 : 64;      // residual GEMM: finer tiles balance better over the SMs
+  if constexpr (std::is_same<TOp, __nv_bfloat16>::value) {
+    if (h->fused) {
+      // all L residual layers in one persistent launch (denoiser_fused.cuh)
+      FusedParams fp{};
+      fp.B = Bc; fp.b_off = b0; fp.T = T; fp.L = L; fp.H = H;
+      fp.h = w.h; fp.hb0 = static_cast<__nv_bfloat16*>(w.hb); fp.hb1 = static_cast<__nv_bfloat16*>(w.hb1);
+      fp.u_all = static_cast<__nv_bfloat16*>(w.u);
+      fp.dbias = w.dbias + static_cast<size_t>(tidx_base) * L * 3 * 2 * C;
+      fp.dbias_bstride = static_cast<long long>(tidx_bstride) * L * 3 * 2 * C;
+      fp.b2 = h->b2; fp.grid_bar = h->d_grid_bar; fp.mW1 = h->d_mW1; fp.mW2 = h->d_mW2f;
+      static bool attr_set = false;
+      if (!attr_set) {
+        FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
+        attr_set = true;
+      }
+      const int tiles = Bc * ((T + kTileM - 1) / kTileM);
+      FSE_CUDA(cudaMemsetAsync(h->d_grid_bar, 0, sizeof(unsigned int), st));
+      ++h->launches;
+      h->prof.begin(1, st);
+      denoiser_layers_kernel<<<tiles < h->num_sms ? tiles : h->num_sms, kTcThreads, kFusedSmemBytes, st>>>(
+          h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp);
+      h->prof.end(st);
+      FSE_CUDA(cudaGetLastError());
+    }
+  }
+  if (!h->fused)
   for (int l = 0; l < L; ++l) {
     const int dil = 1 << (l % h->cfg.dilation_cycle_length);
     const int offs[3] = {-dil, 0, dil};
@@ -463,8 +500,13 @@ int fse_denoiser_create(const fse_denoiser_config* cfg, fse_denoiser** out) {
   h->cfg = *cfg;
   h->bf16 = cfg->mode != FSE_MODE_SIMT_F32;
   if (const char* e = getenv("FSE_BATCH_CHUNK")) h->batch_chunk = atoi(e);
+  // The fused multi-layer kernel covers the shipped configurations (256 residual channels, dilation 1, <= 256
+  // condition channels); anything else runs the per-layer kernels.  FSE_FUSED=0 forces the per-layer path.
+  h->fused = cfg->mode == FSE_MODE_TC_BF16 && cfg->channels == kFC && cfg->dilation_cycle_length == 1 && cfg->hidden <= 256 &&
+             cfg->hidden % 64 == 0 && !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 0);
   if (getenv("FSE_DBG_STAMPS")) { cudaMalloc(reinterpret_cast<void**>(&h->dbg_buf), 64 * 8); cudaMemset(h->dbg_buf, 0, 64 * 8); }
   cudaGetDevice(&h->device);
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
   *out = h;
   return FSE_OK;
 }
@@ -472,7 +514,8 @@ int fse_denoiser_create(const fse_denoiser_config* cfg, fse_denoiser** out) {
 void fse_denoiser_destroy(fse_denoiser* h) {
   if (!h) return;
   void* ptrs[] = {h->W_in, h->b_in, h->W1, h->W2, h->b2, h->W_skip, h->b_skip, h->W_out, h->b_out, h->Wmac, h->bmac,
-                  h->Wdp, h->bdp, h->mlp0_w, h->mlp0_b, h->mlp2_w, h->mlp2_b, h->d_coef1, h->d_coef2, h->d_logvar, h->host_ws};
+                  h->Wdp, h->bdp, h->mlp0_w, h->mlp0_b, h->mlp2_w, h->mlp2_b, h->d_coef1, h->d_coef2, h->d_logvar, h->host_ws,
+                  h->d_mW1, h->d_mW2f, h->d_grid_bar};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
 }
@@ -593,6 +636,15 @@ int fse_denoiser_load_weights(fse_denoiser* h, const fse_tensor* tensors, int32_
     for (int l = 0; l < L; ++l) {
       FSE_TRY(make_map_w(&h->mW1[l], static_cast<uint8_t*>(h->W1) + (size_t)l * N2 * h->Kp1 * 2, h->Kp1, N2, 64, bn2));
       FSE_TRY(make_map_w(&h->mW2[l], static_cast<uint8_t*>(h->W2) + (size_t)l * C * C * 2, C, C, 64, bnr));
+    }
+    if (h->fused) {
+      std::vector<CUtensorMap> w2f(L);
+      for (int l = 0; l < L; ++l) FSE_TRY(make_map_w(&w2f[l], static_cast<uint8_t*>(h->W2) + (size_t)l * C * C * 2, C, C, 64, 256));
+      FSE_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_mW1), sizeof(CUtensorMap) * L));
+      FSE_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_mW2f), sizeof(CUtensorMap) * L));
+      FSE_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_grid_bar), 256));
+      FSE_CUDA(cudaMemcpy(h->d_mW1, h->mW1.data(), sizeof(CUtensorMap) * L, cudaMemcpyHostToDevice));
+      FSE_CUDA(cudaMemcpy(h->d_mW2f, w2f.data(), sizeof(CUtensorMap) * L, cudaMemcpyHostToDevice));
     }
   }
   h->loaded = true;

@@ -1,0 +1,344 @@
+// All residual layers of one DiffNet evaluation in ONE persistent launch (diffnet.py:68-81 x L).
+//
+// Per layer l and 128-frame tile, one CTA runs three tensor-core jobs back to back, alternating between two
+// 256-column TMEM accumulators (job j uses buffer j & 1, epilogue j must have drained it before job j+2):
+//   G1a, G1b : y[:, half] = conv_k3(hb_l) W_dc^T + cond W_cp^T        K = 3*256 + H, N = 2 x 256 (gate/filter interleaved)
+//              epilogue: u = sigmoid(gate) * tanh(filter) (+ fp32 timestep bias) -> u_all[:, l*C ...] in HBM (for the
+//              folded skip GEMM) AND into shared memory in the UMMA K-major 128B-swizzled layout
+//   G2       : o = u W_op[:C]^T                                          K = 256 (A operand = the smem copy of u), N = 256
+//              epilogue: h <- (h + o + b) / sqrt(2)  (fp32, in place)  and hb_{l+1} (bf16, ping-pong buffer)
+// so u never round-trips through HBM between the two GEMMs, the residual epilogue hides behind the next tile's
+// MMAs, and the 40 launches per step (with their drain / fill / TMEM alloc) collapse into one.  The activation tile of
+// each 64-channel block is loaded once (130 rows) and the three conv taps are row-shifted UMMA descriptors of it.
+// Layers are separated by a grid-wide barrier (the conv halo of layer l+1 reads hb rows written by neighbour CTAs);
+// the launch is cooperative so that all CTAs are co-resident.
+#pragma once
+#include "epilogues.cuh"
+
+namespace fse {
+
+constexpr int kFC = 256;                       // residual channels handled by the fused kernel
+constexpr int kFusedASlots = 3, kFusedWStages = 3;
+constexpr int kFusedASlotBytes = 17408;        // 130 rows x 128 B rounded up to 1024
+constexpr int kFusedWStageBytes = 256 * 128;   // 256 weight rows x 64 bf16
+constexpr int kFusedUBytes = 4 * 128 * 128;    // u tile: 4 k-blocks of [128 rows x 64 bf16]
+constexpr size_t kFusedSmemBytes = 1024 + kFusedASlots * kFusedASlotBytes + kFusedWStages * kFusedWStageBytes + kFusedUBytes + 256;
+
+struct FusedParams {
+  int B, b_off, T, L, H;          // items of this launch, first item, frames per item, layers, cond channels
+  float* h;                       // [*, 256] fp32 residual stream, updated in place
+  __nv_bfloat16* hb0;             // operand copy read by even layers / written by odd layers
+  __nv_bfloat16* hb1;             // ... and vice versa
+  __nv_bfloat16* u_all;           // [*, L*256]
+  const float* dbias;             // timestep tables of this call: [.., L, 3, 512]
+  long long dbias_bstride;        // elements between consecutive items' tables (0: shared)
+  const float* b2;                // [L, 256] residual half of output_projection.bias
+  unsigned int* grid_bar;         // zeroed before the launch
+  const CUtensorMap* mW1;         // [L] in global memory: [512, 960] gate weights, box 64 x 256
+  const CUtensorMap* mW2;         // [L]: [256, 256] residual weights, box 64 x 256
+};
+
+__device__ __forceinline__ void fused_grid_barrier(unsigned int* bar, unsigned int target) {
+  __threadfence();
+  atomicAdd(bar, 1u);
+  const long long t0 = clock64();
+  unsigned int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    if (clock64() - t0 > 4000000000LL) {
+      printf("fse: grid barrier timed out (block %d, target %u, seen %u)\n", blockIdx.x, target, v);
+      __trap();
+    }
+  } while (v < target);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_constant__ CUtensorMap mapHb1,
+                       const __grid_constant__ CUtensorMap mapCond, FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + kFusedASlots * kFusedASlotBytes;
+  uint8_t* sU = sW + kFusedWStages * kFusedWStageBytes;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sU + kFusedUBytes);
+  uint64_t* a_empty = a_full + kFusedASlots;
+  uint64_t* w_full = a_empty + kFusedASlots;
+  uint64_t* w_empty = w_full + kFusedWStages;
+  uint64_t* acc_full = w_empty + kFusedWStages;   // [2]
+  uint64_t* acc_empty = acc_full + 2;             // [2]
+  uint64_t* u_full = acc_empty + 2;
+  uint64_t* u_empty = u_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_empty + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int tiles_per_item = (p.T + kTileM - 1) / kTileM;
+  const int total_tiles = p.B * tiles_per_item;
+  const int nkbH = (p.H + 63) / 64;
+  const int ngroups = 4 + nkbH;                    // 4 hb channel blocks (3 taps each) + cond blocks (1 tap)
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&mapHb0);
+    ptx::prefetch_tensormap(&mapHb1);
+    ptx::prefetch_tensormap(&mapCond);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < kFusedASlots; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+      for (int i = 0; i < kFusedWStages; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kEpiWarps); }
+      ptx::mbar_init(u_full, 2 * kEpiWarps);
+      ptx::mbar_init(u_empty, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // monotonic pipeline counters (continue across tiles and layers)
+  int ga = 0, kw = 0, it = 0;
+
+  for (int l = 0; l < p.L; ++l) {
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      if (lane == 0) {
+        const CUtensorMap* mHb = (l & 1) ? &mapHb1 : &mapHb0;
+        const CUtensorMap* mW1 = p.mW1 + l;
+        const CUtensorMap* mW2 = p.mW2 + l;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const int b = p.b_off + tile / tiles_per_item, t0 = (tile % tiles_per_item) * kTileM;
+          for (int half = 0; half < 2; ++half) {
+            for (int g = 0; g < ngroups; ++g, ++ga) {
+              const int slot = ga % kFusedASlots;
+              ptx::mbar_wait(&a_empty[slot], ((ga / kFusedASlots) & 1) ^ 1u);
+              if (g < 4) {
+                ptx::mbar_arrive_expect_tx(&a_full[slot], 130u * 128u);
+                ptx::tma_load_3d(sA + slot * kFusedASlotBytes, mHb, &a_full[slot], g * 64, t0 - 1, b);
+              } else {
+                ptx::mbar_arrive_expect_tx(&a_full[slot], 128u * 128u);
+                ptx::tma_load_3d(sA + slot * kFusedASlotBytes, &mapCond, &a_full[slot], (g - 4) * 64, t0, b);
+              }
+              const int ntap = g < 4 ? 3 : 1;
+              for (int j = 0; j < ntap; ++j, ++kw) {
+                const int s = kw % kFusedWStages;
+                ptx::mbar_wait(&w_empty[s], ((kw / kFusedWStages) & 1) ^ 1u);
+                ptx::mbar_arrive_expect_tx(&w_full[s], static_cast<uint32_t>(kFusedWStageBytes));
+                const int kb = g < 4 ? j * 4 + g : 12 + (g - 4);
+                ptx::tma_load_2d(sW + s * kFusedWStageBytes, mW1, &w_full[s], kb * 64, half * 256);
+              }
+            }
+          }
+          for (int kb = 0; kb < 4; ++kb, ++kw) {          // residual GEMM weights (its A operand is the smem copy of u)
+            const int s = kw % kFusedWStages;
+            ptx::mbar_wait(&w_empty[s], ((kw / kFusedWStages) & 1) ^ 1u);
+            ptx::mbar_arrive_expect_tx(&w_full[s], static_cast<uint32_t>(kFusedWStageBytes));
+            ptx::tma_load_2d(sW + s * kFusedWStageBytes, mW2, &w_full[s], kb * 64, 0);
+          }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer
+      const uint32_t idesc = ptx::make_idesc_bf16_f32(kTileM, 256);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int half = 0; half < 2; ++half) {
+          const int job = 3 * it + half, buf = job & 1;
+          ptx::mbar_wait(&acc_empty[buf], ((job >> 1) & 1) ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * 256);
+          uint32_t accum = 0;
+          for (int g = 0; g < ngroups; ++g, ++ga) {
+            const int slot = ga % kFusedASlots;
+            ptx::mbar_wait(&a_full[slot], (ga / kFusedASlots) & 1);
+            const int ntap = g < 4 ? 3 : 1;
+            for (int j = 0; j < ntap; ++j, ++kw) {
+              const int s = kw % kFusedWStages;
+              ptx::mbar_wait(&w_full[s], (kw / kFusedWStages) & 1);
+              ptx::tc_fence_after();
+              if (lane == 0) {
+                // hb tile holds frames t0-1 .. t0+128; tap j (offset j-1) starts at row j
+                const uint32_t a_addr = ptx::smem_u32(sA + slot * kFusedASlotBytes) + (g < 4 ? static_cast<uint32_t>(j * 128) : 0u);
+                const uint64_t da = ptx::make_desc_k_sw128(a_addr);
+                const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sW + s * kFusedWStageBytes));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, accum | (k != 0 ? 1u : 0u));
+                ptx::mma_commit(&w_empty[s]);
+              }
+              accum = 1;
+              __syncwarp();
+            }
+            if (lane == 0) ptx::mma_commit(&a_empty[slot]);
+            __syncwarp();
+          }
+          if (lane == 0) ptx::mma_commit(&acc_full[buf]);
+          __syncwarp();
+        }
+        {
+          const int job = 3 * it + 2, buf = job & 1;
+          ptx::mbar_wait(&acc_empty[buf], ((job >> 1) & 1) ^ 1u);
+          ptx::mbar_wait(u_full, it & 1);                 // both halves of u are in shared memory
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * 256);
+          for (int kb = 0; kb < 4; ++kb, ++kw) {
+            const int s = kw % kFusedWStages;
+            ptx::mbar_wait(&w_full[s], (kw / kFusedWStages) & 1);
+            ptx::tc_fence_after();
+            if (lane == 0) {
+              const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(sU + kb * 16384));
+              const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sW + s * kFusedWStageBytes));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              ptx::mma_commit(&w_empty[s]);
+            }
+            __syncwarp();
+          }
+          if (lane == 0) {
+            ptx::mma_commit(u_empty);
+            ptx::mma_commit(&acc_full[buf]);
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+      // ---------------------------------------------------------------- epilogue warps
+      const int ew = warp - 2;
+      const int q = warp & 3;
+      const int half2 = ew >> 2;
+      const float* b2 = p.b2 + static_cast<size_t>(l) * kFC;
+      __nv_bfloat16* hb_out = (l & 1) ? p.hb0 : p.hb1;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int b = p.b_off + tile / tiles_per_item, t0 = (tile % tiles_per_item) * kTileM;
+        const int r = q * 32 + lane;                    // row inside the tile = TMEM lane
+        const int t = t0 + r;
+        const bool row_ok = t < p.T;
+        const size_t row = static_cast<size_t>(b) * p.T + t;
+        const float* db = p.dbias + static_cast<size_t>(b) * p.dbias_bstride + static_cast<size_t>(l) * 3 * 512;
+        const bool e0 = t < 1, e2 = t >= p.T - 1;       // dilation 1: the taps that fell on the zero padding
+        if (it > 0) ptx::mbar_wait(u_empty, (it - 1) & 1);   // the previous tile's residual GEMM has finished reading u
+        for (int half = 0; half < 2; ++half) {
+          const int job = 3 * it + half, buf = job & 1;
+          ptx::mbar_wait(&acc_full[buf], (job >> 1) & 1);
+          ptx::tc_fence_after();
+          const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * 256);
+          for (int c = half2; c < 8; c += 2) {
+            uint32_t rr[32];
+            ptx::tmem_ld_32x32b_x32(lane_base + c * 32, rr);
+            ptx::tmem_wait_ld();
+            const int n0 = half * 256 + c * 32;           // first of 32 interleaved (gate, filter) columns
+            const float* m = db + n0;
+            float y[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 mv = __ldg(reinterpret_cast<const float4*>(m) + i);
+              y[4 * i] = __uint_as_float(rr[4 * i]) + mv.x; y[4 * i + 1] = __uint_as_float(rr[4 * i + 1]) + mv.y;
+              y[4 * i + 2] = __uint_as_float(rr[4 * i + 2]) + mv.z; y[4 * i + 3] = __uint_as_float(rr[4 * i + 3]) + mv.w;
+            }
+            if (e0) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) y[i] -= __ldg(m + 512 + i);
+            }
+            if (e2) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) y[i] -= __ldg(m + 1024 + i);
+            }
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              pk[j] = pack_bf16x2(sigmoid_f<true>(y[4 * j]) * tanh_f<true>(y[4 * j + 1]),
+                                  sigmoid_f<true>(y[4 * j + 2]) * tanh_f<true>(y[4 * j + 3]));
+            // u columns [ucol, ucol+16): HBM copy for the folded skip GEMM ...
+            const int ucol = half * 128 + c * 16;
+            if (row_ok) {
+              __nv_bfloat16* up = p.u_all + row * static_cast<size_t>(p.L * kFC) + l * kFC + ucol;
+              asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(up), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+              asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(up + 8), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+            }
+            // ... and the A operand of the residual GEMM: K-major, 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
+            uint8_t* ub = sU + (ucol >> 6) * 16384 + r * 128;
+            const int ch = (ucol & 63) >> 3;               // first of the two 16-byte chunks
+            *reinterpret_cast<uint4*>(ub + (((ch) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(ub + (((ch + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+          ptx::tc_fence_before();
+          ptx::fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            ptx::mbar_arrive(&acc_empty[buf]);
+            ptx::mbar_arrive(u_full);
+          }
+        }
+        {
+          // residual epilogue: h <- (h + o + b) / sqrt(2); chunk-ahead prefetch of h
+          const int job = 3 * it + 2, buf = job & 1;
+          float* hp = p.h + row * kFC;
+          __nv_bfloat16* hbp = hb_out + row * kFC;
+          float hv[32];
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 v = reinterpret_cast<const float4*>(hp + half2 * 32)[i];
+              hv[4 * i] = v.x; hv[4 * i + 1] = v.y; hv[4 * i + 2] = v.z; hv[4 * i + 3] = v.w;
+            }
+          }
+          ptx::mbar_wait(&acc_full[buf], (job >> 1) & 1);
+          ptx::tc_fence_after();
+          const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * 256);
+          for (int c = half2; c < 8; c += 2) {
+            uint32_t rr[32];
+            ptx::tmem_ld_32x32b_x32(lane_base + c * 32, rr);
+            ptx::tmem_wait_ld();
+            float hn[32];
+            if (c + 2 < 8 && row_ok) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 v = reinterpret_cast<const float4*>(hp + (c + 2) * 32)[i];
+                hn[4 * i] = v.x; hn[4 * i + 1] = v.y; hn[4 * i + 2] = v.z; hn[4 * i + 3] = v.w;
+              }
+            }
+            if (row_ok) {
+              float v[32];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(b2 + c * 32) + i);
+                v[4 * i] = (hv[4 * i] + (__uint_as_float(rr[4 * i]) + bv.x)) * 0.70710678118654752440f;
+                v[4 * i + 1] = (hv[4 * i + 1] + (__uint_as_float(rr[4 * i + 1]) + bv.y)) * 0.70710678118654752440f;
+                v[4 * i + 2] = (hv[4 * i + 2] + (__uint_as_float(rr[4 * i + 2]) + bv.z)) * 0.70710678118654752440f;
+                v[4 * i + 3] = (hv[4 * i + 3] + (__uint_as_float(rr[4 * i + 3]) + bv.w)) * 0.70710678118654752440f;
+              }
+              st_vec<32>(hp + c * 32, v);
+              st_vec<32>(hbp + c * 32, v);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) hv[i] = hn[i];
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+        }
+      }
+    }
+    // ------------------------------------------------------------------ layer boundary
+    // hb_{l+1} rows written by neighbour CTAs are read by the next layer's TMA loads (conv halo): grid-wide barrier.
+    if (l + 1 < p.L) {
+      __syncthreads();
+      if (threadIdx.x == 0) fused_grid_barrier(p.grid_bar, static_cast<unsigned int>(l + 1) * gridDim.x);
+      __syncwarp();
+      __syncthreads();
+      asm volatile("fence.proxy.async;" ::: "memory");      // other CTAs' generic-proxy stores -> our TMA (async proxy) loads
+    }
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace fse
