@@ -174,6 +174,12 @@ def run_b200(args):
     import torch
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    if rank == 0:                                   # make sure the in-tree library matches the sources (no-op when current)
+        from speech_editing_toolkit_b200 import build as _b
+        try:
+            _b.build()
+        except Exception as e:                      # no nvcc on this box: use the shipped .so
+            print(f"bench: build skipped ({e})", file=sys.stderr)
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")

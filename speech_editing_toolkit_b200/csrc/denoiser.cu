@@ -319,6 +319,7 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
       fp.dbias = w.dbias + static_cast<size_t>(tidx_base) * L * 3 * 2 * C;
       fp.dbias_bstride = static_cast<long long>(tidx_bstride) * L * 3 * 2 * C;
       fp.b2 = h->b2; fp.grid_bar = h->d_grid_bar; fp.mW1 = h->d_mW1; fp.mW2 = h->d_mW2f;
+      fp.dbg = h->dbg_buf;
       static bool attr_set = false;
       if (!attr_set) {
         FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
@@ -454,7 +455,19 @@ int sample_impl(fse_denoiser* h, const float* cond, const float* noise, uint64_t
     FSE_TRY((run_step<TOp>(h, w, cond_op, B, T, k, 0, out, st)));
     x_cur = x_next;
   }
-  if (h->dbg_buf) {
+  if (h->dbg_buf && h->fused) {
+    long long d[64];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(d, h->dbg_buf, sizeof(d), cudaMemcpyDeviceToHost);
+    const long long t0 = d[42];   // CTA 0 left the barrier before layer 3
+    fprintf(stderr, "[fse fused stamps, CTA0 layer3, cycles since barrier exit] barrier_enter(l2)=%lld\n", d[0] - t0);
+    for (int tl = 0; tl < 2; ++tl) {
+      const long long* m = d + 1 + tl * 8; const long long* e = d + 20 + tl * 8;
+      fprintf(stderr, "  tile%d MMA: G1a %lld..%lld G1b %lld..%lld G2 buf_free=%lld u_ready=%lld issued=%lld | EPI(w2): e1a %lld..%lld e1b %lld..%lld e2 %lld..%lld\n",
+              tl, m[0] - t0, m[1] - t0, m[2] - t0, m[3] - t0, m[4] - t0, m[5] - t0, m[6] - t0, e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0, e[5] - t0);
+    }
+    fprintf(stderr, "  layer3 end: syncthreads passed=%lld grid barrier passed=%lld\n", d[40] - t0, d[41] - t0);
+  } else if (h->dbg_buf) {
     long long d[64];
     cudaStreamSynchronize(st);
     cudaMemcpy(d, h->dbg_buf, sizeof(d), cudaMemcpyDeviceToHost);

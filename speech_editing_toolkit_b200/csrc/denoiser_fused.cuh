@@ -22,7 +22,8 @@ constexpr int kFusedASlots = 3, kFusedWStages = 3;
 constexpr int kFusedASlotBytes = 17408;        // 130 rows x 128 B rounded up to 1024
 constexpr int kFusedWStageBytes = 256 * 128;   // 256 weight rows x 64 bf16
 constexpr int kFusedUBytes = 4 * 128 * 128;    // u tile: 4 k-blocks of [128 rows x 64 bf16]
-constexpr size_t kFusedSmemBytes = 1024 + kFusedASlots * kFusedASlotBytes + kFusedWStages * kFusedWStageBytes + kFusedUBytes + 256;
+constexpr int kFusedBiasBytes = 3 * 512 * 4 + 256 * 4;   // per-layer timestep tables (m, a, c) + residual bias
+constexpr size_t kFusedSmemBytes = 1024 + kFusedASlots * kFusedASlotBytes + kFusedWStages * kFusedWStageBytes + kFusedUBytes + kFusedBiasBytes + 256;
 
 struct FusedParams {
   int B, b_off, T, L, H;          // items of this launch, first item, frames per item, layers, cond channels
@@ -36,7 +37,15 @@ struct FusedParams {
   unsigned int* grid_bar;         // zeroed before the launch
   const CUtensorMap* mW1;         // [L] in global memory: [512, 960] gate weights, box 64 x 256
   const CUtensorMap* mW2;         // [L]: [256, 256] residual weights, box 64 x 256
+  long long* dbg;                 // optional [64] clock64 stamps of CTA 0 in layer 3 (developer aid)
 };
+
+// fp32 residual stream: read once per layer, never reused from L1
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ void fused_grid_barrier(unsigned int* bar, unsigned int target) {
   __threadfence();
@@ -60,7 +69,8 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
   uint8_t* sA = smem;
   uint8_t* sW = sA + kFusedASlots * kFusedASlotBytes;
   uint8_t* sU = sW + kFusedWStages * kFusedWStageBytes;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sU + kFusedUBytes);
+  float* sBias = reinterpret_cast<float*>(sU + kFusedUBytes);          // [3][512] timestep tables + [256] residual bias of the layer
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sU + kFusedUBytes + kFusedBiasBytes);
   uint64_t* a_empty = a_full + kFusedASlots;
   uint64_t* w_full = a_empty + kFusedASlots;
   uint64_t* w_empty = w_full + kFusedWStages;
@@ -105,6 +115,15 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
   int ga = 0, kw = 0, it = 0;
 
   for (int l = 0; l < p.L; ++l) {
+    // Per-layer bias tables -> shared memory (L1 is streamed through by the fp32 residual traffic, so per-chunk __ldg of
+    // the tables kept missing).  With per-item tables (dbias_bstride != 0) only the residual bias is staged.
+    if (warp >= 2) {
+      const int e = threadIdx.x - 64;
+      if (p.dbias_bstride == 0)
+        for (int i = e; i < 3 * 512; i += kEpiWarps * 32) sBias[i] = __ldg(p.dbias + static_cast<size_t>(l) * 3 * 512 + i);
+      for (int i = e; i < 256; i += kEpiWarps * 32) sBias[3 * 512 + i] = __ldg(p.b2 + static_cast<size_t>(l) * kFC + i);
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");      // epilogue warps only
+    }
     if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer
       if (lane == 0) {
@@ -147,10 +166,13 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
       // ---------------------------------------------------------------- MMA issuer
       const uint32_t idesc = ptx::make_idesc_bf16_f32(kTileM, 256);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int tl = (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);   // local tile index in this layer
+        long long* dm = (p.dbg && blockIdx.x == 0 && l == 3 && lane == 0 && tl < 2) ? p.dbg + 1 + tl * 8 : nullptr;
         for (int half = 0; half < 2; ++half) {
           const int job = 3 * it + half, buf = job & 1;
           ptx::mbar_wait(&acc_empty[buf], ((job >> 1) & 1) ^ 1u);
           ptx::tc_fence_after();
+          if (dm) dm[half * 2] = clock64();                 // job may start (buffer free)
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * 256);
           uint32_t accum = 0;
           for (int g = 0; g < ngroups; ++g, ++ga) {
@@ -177,13 +199,16 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
             __syncwarp();
           }
           if (lane == 0) ptx::mma_commit(&acc_full[buf]);
+          if (dm) dm[half * 2 + 1] = clock64();             // all MMAs of the job issued
           __syncwarp();
         }
         {
           const int job = 3 * it + 2, buf = job & 1;
           ptx::mbar_wait(&acc_empty[buf], ((job >> 1) & 1) ^ 1u);
+          if (dm) dm[4] = clock64();
           ptx::mbar_wait(u_full, it & 1);                 // both halves of u are in shared memory
           ptx::tc_fence_after();
+          if (dm) dm[5] = clock64();
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * 256);
           for (int kb = 0; kb < 4; ++kb, ++kw) {
             const int s = kw % kFusedWStages;
@@ -202,6 +227,7 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
             ptx::mma_commit(u_empty);
             ptx::mma_commit(&acc_full[buf]);
           }
+          if (dm) dm[6] = clock64();
           __syncwarp();
         }
       }
@@ -220,32 +246,37 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
         const size_t row = static_cast<size_t>(b) * p.T + t;
         const float* db = p.dbias + static_cast<size_t>(b) * p.dbias_bstride + static_cast<size_t>(l) * 3 * 512;
         const bool e0 = t < 1, e2 = t >= p.T - 1;       // dilation 1: the taps that fell on the zero padding
+        const int tl = (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);
+        long long* de = (p.dbg && blockIdx.x == 0 && l == 3 && ew == 0 && lane == 0 && tl < 2) ? p.dbg + 20 + tl * 8 : nullptr;
         if (it > 0) ptx::mbar_wait(u_empty, (it - 1) & 1);   // the previous tile's residual GEMM has finished reading u
         for (int half = 0; half < 2; ++half) {
           const int job = 3 * it + half, buf = job & 1;
           ptx::mbar_wait(&acc_full[buf], (job >> 1) & 1);
           ptx::tc_fence_after();
+          if (de) de[half * 2] = clock64();                 // accumulator ready
           const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * 256);
-          for (int c = half2; c < 8; c += 2) {
+          for (int ci = 0; ci < 4; ++ci) {
+            const int c = half2 * 4 + ci;                 // contiguous ownership: this warp writes u k-block (2*half + half2) only
             uint32_t rr[32];
             ptx::tmem_ld_32x32b_x32(lane_base + c * 32, rr);
             ptx::tmem_wait_ld();
             const int n0 = half * 256 + c * 32;           // first of 32 interleaved (gate, filter) columns
-            const float* m = db + n0;
+            const bool shared_tab = p.dbias_bstride == 0;
+            const float* m = shared_tab ? sBias + n0 : db + n0;
             float y[32];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 mv = __ldg(reinterpret_cast<const float4*>(m) + i);
+              const float4 mv = shared_tab ? *(reinterpret_cast<const float4*>(m) + i) : __ldg(reinterpret_cast<const float4*>(m) + i);
               y[4 * i] = __uint_as_float(rr[4 * i]) + mv.x; y[4 * i + 1] = __uint_as_float(rr[4 * i + 1]) + mv.y;
               y[4 * i + 2] = __uint_as_float(rr[4 * i + 2]) + mv.z; y[4 * i + 3] = __uint_as_float(rr[4 * i + 3]) + mv.w;
             }
             if (e0) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) y[i] -= __ldg(m + 512 + i);
+              for (int i = 0; i < 32; ++i) y[i] -= m[512 + i];
             }
             if (e2) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) y[i] -= __ldg(m + 1024 + i);
+              for (int i = 0; i < 32; ++i) y[i] -= m[1024 + i];
             }
             uint32_t pk[8];
 #pragma unroll
@@ -272,62 +303,77 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
             ptx::mbar_arrive(&acc_empty[buf]);
             ptx::mbar_arrive(u_full);
           }
+          if (de) de[half * 2 + 1] = clock64();             // gate epilogue of this half done
         }
         {
-          // residual epilogue: h <- (h + o + b) / sqrt(2); chunk-ahead prefetch of h
+          // residual epilogue: h <- (h + o + b) / sqrt(2).
+          // The fp32 residual stream is accessed TRANSPOSED: the 32x32 accumulator chunk goes through a 4 KB
+          // XOR-swizzled scratch (the rows of the u tile that only this warp writes; u is dead between the residual
+          // GEMM and the next tile's gate epilogue), so that 8 lanes cover one 128-byte row segment: every global
+          // load/store instruction touches 4 cache lines instead of 32 (the lane-per-row form was LSU-bound).
           const int job = 3 * it + 2, buf = job & 1;
-          float* hp = p.h + row * kFC;
-          __nv_bfloat16* hbp = hb_out + row * kFC;
-          float hv[32];
-          if (row_ok) {
+          float* stg = reinterpret_cast<float*>(sU + half2 * 16384 + q * 4096);
+          const int cq = lane & 7, r0 = lane >> 3;
+          const int tq = t0 + q * 32 + r0;                      // frame of iteration 0; iteration i adds 4*i
+          const size_t rowq = static_cast<size_t>(b) * p.T + tq;
+          float* hq = p.h + rowq * kFC + cq * 4;
+          __nv_bfloat16* hbq = hb_out + rowq * kFC + cq * 4;
+          float4 hv[8], hn[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 v = reinterpret_cast<const float4*>(hp + half2 * 32)[i];
-              hv[4 * i] = v.x; hv[4 * i + 1] = v.y; hv[4 * i + 2] = v.z; hv[4 * i + 3] = v.w;
-            }
-          }
+          for (int i = 0; i < 8; ++i)
+            hv[i] = (tq + 4 * i < p.T) ? ld_stream_f4(hq + static_cast<size_t>(4 * i) * kFC + half2 * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
           ptx::mbar_wait(&acc_full[buf], (job >> 1) & 1);
           ptx::tc_fence_after();
+          if (de) de[4] = clock64();
           const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * 256);
-          for (int c = half2; c < 8; c += 2) {
+          for (int ci = 0; ci < 4; ++ci) {
+            const int c = half2 * 4 + ci;                       // this warp owns columns [half2*128, half2*128+128)
             uint32_t rr[32];
             ptx::tmem_ld_32x32b_x32(lane_base + c * 32, rr);
             ptx::tmem_wait_ld();
-            float hn[32];
-            if (c + 2 < 8 && row_ok) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 v = reinterpret_cast<const float4*>(hp + (c + 2) * 32)[i];
-                hn[4 * i] = v.x; hn[4 * i + 1] = v.y; hn[4 * i + 2] = v.z; hn[4 * i + 3] = v.w;
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(rr[4 * j], rr[4 * j + 1], rr[4 * j + 2], rr[4 * j + 3]);
+            __syncwarp();
+            if (ci + 1 < 4) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                hn[i] = (tq + 4 * i < p.T) ? ld_stream_f4(hq + static_cast<size_t>(4 * i) * kFC + (c + 1) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const float4 bv = *reinterpret_cast<const float4*>(sBias + 3 * 512 + c * 32 + cq * 4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rloc = 4 * i + r0;
+              const float4 a = *reinterpret_cast<const float4*>(stg + rloc * 32 + ((cq ^ (rloc & 7)) << 2));
+              if (tq + 4 * i < p.T) {
+                float v[4];
+                v[0] = (hv[i].x + (a.x + bv.x)) * 0.70710678118654752440f;
+                v[1] = (hv[i].y + (a.y + bv.y)) * 0.70710678118654752440f;
+                v[2] = (hv[i].z + (a.z + bv.z)) * 0.70710678118654752440f;
+                v[3] = (hv[i].w + (a.w + bv.w)) * 0.70710678118654752440f;
+                st_vec<4>(hq + static_cast<size_t>(4 * i) * kFC + c * 32, v);
+                st_vec<4>(hbq + static_cast<size_t>(4 * i) * kFC + c * 32, v);
               }
             }
-            if (row_ok) {
-              float v[32];
+            __syncwarp();
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(b2 + c * 32) + i);
-                v[4 * i] = (hv[4 * i] + (__uint_as_float(rr[4 * i]) + bv.x)) * 0.70710678118654752440f;
-                v[4 * i + 1] = (hv[4 * i + 1] + (__uint_as_float(rr[4 * i + 1]) + bv.y)) * 0.70710678118654752440f;
-                v[4 * i + 2] = (hv[4 * i + 2] + (__uint_as_float(rr[4 * i + 2]) + bv.z)) * 0.70710678118654752440f;
-                v[4 * i + 3] = (hv[4 * i + 3] + (__uint_as_float(rr[4 * i + 3]) + bv.w)) * 0.70710678118654752440f;
-              }
-              st_vec<32>(hp + c * 32, v);
-              st_vec<32>(hbp + c * 32, v);
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) hv[i] = hn[i];
+            for (int i = 0; i < 8; ++i) hv[i] = hn[i];
           }
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+          if (de) de[5] = clock64();
         }
       }
     }
     // ------------------------------------------------------------------ layer boundary
     // hb_{l+1} rows written by neighbour CTAs are read by the next layer's TMA loads (conv halo): grid-wide barrier.
     if (l + 1 < p.L) {
+      if (p.dbg && blockIdx.x == 0 && l == 2 && threadIdx.x == 64) p.dbg[0] = clock64();    // layer 3 starts after this barrier
       __syncthreads();
+      if (p.dbg && blockIdx.x == 0 && l == 3 && threadIdx.x == 0) p.dbg[40] = clock64();
       if (threadIdx.x == 0) fused_grid_barrier(p.grid_bar, static_cast<unsigned int>(l + 1) * gridDim.x);
+      if (p.dbg && blockIdx.x == 0 && (l == 3 || l == 2) && threadIdx.x == 0) p.dbg[41 + (l == 2)] = clock64();
       __syncwarp();
       __syncthreads();
       asm volatile("fence.proxy.async;" ::: "memory");      // other CTAs' generic-proxy stores -> our TMA (async proxy) loads
