@@ -190,7 +190,9 @@ struct fse_denoiser {
   std::vector<CUtensorMap> mW1, mW2;
   // fused multi-layer kernel (denoiser_fused.cuh): per-layer weight maps in device memory, grid barrier word
   bool fused = false;
-  CUtensorMap* d_mW1 = nullptr; CUtensorMap* d_mW2f = nullptr; unsigned int* d_grid_bar = nullptr;
+  bool fused_pair = false;   // FSE_FUSED=2: CTA pairs (tcgen05 cta_group::2), each CTA loads half of every weight tile
+  CUtensorMap* d_mW1 = nullptr; CUtensorMap* d_mW2f = nullptr; CUtensorMap* d_mW1p = nullptr; CUtensorMap* d_mW2p = nullptr;
+  unsigned int* d_grid_bar = nullptr;
   int num_sms = 0;
   struct Plan {
     const void* ws = nullptr; const void* cond = nullptr; int B = 0, T = 0;
@@ -319,18 +321,33 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
       fp.dbias = w.dbias + static_cast<size_t>(tidx_base) * L * 3 * 2 * C;
       fp.dbias_bstride = static_cast<long long>(tidx_bstride) * L * 3 * 2 * C;
       fp.b2 = h->b2; fp.grid_bar = h->d_grid_bar; fp.mW1 = h->d_mW1; fp.mW2 = h->d_mW2f;
+      fp.mW1p = h->d_mW1p; fp.mW2p = h->d_mW2p;
       fp.dbg = h->dbg_buf;
       static bool attr_set = false;
       if (!attr_set) {
-        FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
+        FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
+        FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
         attr_set = true;
       }
       const int tiles = Bc * ((T + kTileM - 1) / kTileM);
       FSE_CUDA(cudaMemsetAsync(h->d_grid_bar, 0, sizeof(unsigned int), st));
       ++h->launches;
       h->prof.begin(1, st);
-      denoiser_layers_kernel<<<tiles < h->num_sms ? tiles : h->num_sms, kTcThreads, kFusedSmemBytes, st>>>(
-          h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp);
+      if (h->fused_pair) {
+        int grid = (tiles + 1) / 2 * 2;                      // whole clusters of 2
+        const int max_grid = h->num_sms / 2 * 2;
+        if (grid > max_grid) grid = max_grid;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kFusedSmemBytes; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_layers_kernel<true>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp));
+      } else {
+        denoiser_layers_kernel<false><<<tiles < h->num_sms ? tiles : h->num_sms, kTcThreads, kFusedSmemBytes, st>>>(
+            h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp);
+      }
       h->prof.end(st);
       FSE_CUDA(cudaGetLastError());
     }
@@ -517,6 +534,7 @@ int fse_denoiser_create(const fse_denoiser_config* cfg, fse_denoiser** out) {
   // condition channels); anything else runs the per-layer kernels.  FSE_FUSED=0 forces the per-layer path.
   h->fused = cfg->mode == FSE_MODE_TC_BF16 && cfg->channels == kFC && cfg->dilation_cycle_length == 1 && cfg->hidden <= 256 &&
              cfg->hidden % 64 == 0 && !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 0);
+  h->fused_pair = h->fused && getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 2;
   if (getenv("FSE_DBG_STAMPS")) { cudaMalloc(reinterpret_cast<void**>(&h->dbg_buf), 64 * 8); cudaMemset(h->dbg_buf, 0, 64 * 8); }
   cudaGetDevice(&h->device);
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
@@ -528,7 +546,7 @@ void fse_denoiser_destroy(fse_denoiser* h) {
   if (!h) return;
   void* ptrs[] = {h->W_in, h->b_in, h->W1, h->W2, h->b2, h->W_skip, h->b_skip, h->W_out, h->b_out, h->Wmac, h->bmac,
                   h->Wdp, h->bdp, h->mlp0_w, h->mlp0_b, h->mlp2_w, h->mlp2_b, h->d_coef1, h->d_coef2, h->d_logvar, h->host_ws,
-                  h->d_mW1, h->d_mW2f, h->d_grid_bar};
+                  h->d_mW1, h->d_mW2f, h->d_mW1p, h->d_mW2p, h->d_grid_bar};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
 }
@@ -658,6 +676,15 @@ int fse_denoiser_load_weights(fse_denoiser* h, const fse_tensor* tensors, int32_
       FSE_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_grid_bar), 256));
       FSE_CUDA(cudaMemcpy(h->d_mW1, h->mW1.data(), sizeof(CUtensorMap) * L, cudaMemcpyHostToDevice));
       FSE_CUDA(cudaMemcpy(h->d_mW2f, w2f.data(), sizeof(CUtensorMap) * L, cudaMemcpyHostToDevice));
+      std::vector<CUtensorMap> w1p(L), w2p(L);
+      for (int l = 0; l < L; ++l) {
+        FSE_TRY(make_map_w(&w1p[l], static_cast<uint8_t*>(h->W1) + (size_t)l * N2 * h->Kp1 * 2, h->Kp1, N2, 64, 128));
+        FSE_TRY(make_map_w(&w2p[l], static_cast<uint8_t*>(h->W2) + (size_t)l * C * C * 2, C, C, 64, 128));
+      }
+      FSE_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_mW1p), sizeof(CUtensorMap) * L));
+      FSE_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_mW2p), sizeof(CUtensorMap) * L));
+      FSE_CUDA(cudaMemcpy(h->d_mW1p, w1p.data(), sizeof(CUtensorMap) * L, cudaMemcpyHostToDevice));
+      FSE_CUDA(cudaMemcpy(h->d_mW2p, w2p.data(), sizeof(CUtensorMap) * L, cudaMemcpyHostToDevice));
     }
   }
   h->loaded = true;

@@ -37,6 +37,8 @@ struct FusedParams {
   unsigned int* grid_bar;         // zeroed before the launch
   const CUtensorMap* mW1;         // [L] in global memory: [512, 960] gate weights, box 64 x 256
   const CUtensorMap* mW2;         // [L]: [256, 256] residual weights, box 64 x 256
+  const CUtensorMap* mW1p;        // [L] same tensors with box 64 x 128 (CTA-pair mode: each CTA loads half of every tile)
+  const CUtensorMap* mW2p;        // [L]
   long long* dbg;                 // optional [64] clock64 stamps of CTA 0 in layer 3 (developer aid)
 };
 
@@ -61,20 +63,26 @@ __device__ __forceinline__ void fused_grid_barrier(unsigned int* bar, unsigned i
   } while (v < target);
 }
 
+// kPair: the two CTAs of a cluster process two adjacent tiles with M = 256 tcgen05.mma.cta_group::2 instructions
+// issued by the leader; each CTA loads only HALF of every weight tile (the per-SM L2->SM ingest is the limiter).
+template <bool kPair>
 __global__ void __launch_bounds__(kTcThreads, 1)
 denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_constant__ CUtensorMap mapHb1,
                        const __grid_constant__ CUtensorMap mapCond, FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int WB = kPair ? 128 * 128 : 256 * 128;     // bytes of one weight stage (128 or 256 rows x 64 bf16)
+  constexpr int WS = kPair ? 2 * kFusedWStages : kFusedWStages;
+  constexpr uint32_t kMul = kPair ? 2u : 1u;
   uint8_t* sA = smem;
   uint8_t* sW = sA + kFusedASlots * kFusedASlotBytes;
-  uint8_t* sU = sW + kFusedWStages * kFusedWStageBytes;
+  uint8_t* sU = sW + WS * WB;
   float* sBias = reinterpret_cast<float*>(sU + kFusedUBytes);          // [3][512] timestep tables + [256] residual bias of the layer
   uint64_t* a_full = reinterpret_cast<uint64_t*>(sU + kFusedUBytes + kFusedBiasBytes);
   uint64_t* a_empty = a_full + kFusedASlots;
   uint64_t* w_full = a_empty + kFusedASlots;
-  uint64_t* w_empty = w_full + kFusedWStages;
-  uint64_t* acc_full = w_empty + kFusedWStages;   // [2]
+  uint64_t* w_empty = w_full + WS;
+  uint64_t* acc_full = w_empty + WS;              // [2]
   uint64_t* acc_empty = acc_full + 2;             // [2]
   uint64_t* u_full = acc_empty + 2;
   uint64_t* u_empty = u_full + 1;
@@ -84,6 +92,12 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
   const int lane = threadIdx.x & 31;
   const int tiles_per_item = (p.T + kTileM - 1) / kTileM;
   const int total_tiles = p.B * tiles_per_item;
+  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  // work units: a tile (or, in pair mode, two adjacent tiles 2u, 2u+1 handled by the CTAs of a cluster)
+  const int unit0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int unit_stride = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int total_units = kPair ? (total_tiles + 1) / 2 : total_tiles;
   const int nkbH = (p.H + 63) / 64;
   const int ngroups = 4 + nkbH;                    // 4 hb channel blocks (3 taps each) + cond blocks (1 tap)
 
@@ -95,18 +109,19 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < kFusedASlots; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
-      for (int i = 0; i < kFusedWStages; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
-      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kEpiWarps); }
-      ptx::mbar_init(u_full, 2 * kEpiWarps);
+      for (int i = 0; i < WS; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kEpiWarps * kMul); }
+      ptx::mbar_init(u_full, 2 * kEpiWarps * kMul);
       ptx::mbar_init(u_empty, 1);
       ptx::fence_barrier_init();
     }
     __syncwarp();
-    ptx::tmem_alloc(tmem_slot, 512);
-    ptx::tmem_relinquish();
+    if constexpr (kPair) { ptx::tmem_alloc_pair(tmem_slot, 512); ptx::tmem_relinquish_pair(); }
+    else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (kPair) ptx::cluster_sync_all();     // the peer's barriers are initialised before any remote arrive / TMA signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -128,45 +143,59 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
       // ---------------------------------------------------------------- TMA producer
       if (lane == 0) {
         const CUtensorMap* mHb = (l & 1) ? &mapHb1 : &mapHb0;
-        const CUtensorMap* mW1 = p.mW1 + l;
-        const CUtensorMap* mW2 = p.mW2 + l;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const CUtensorMap* mW1 = (kPair ? p.mW1p : p.mW1) + l;
+        const CUtensorMap* mW2 = (kPair ? p.mW2p : p.mW2) + l;
+        const int nrow = kPair ? static_cast<int>(rank) * 128 : 0;       // this CTA's half of every weight tile
+        for (int unit = unit0; unit < total_units; unit += unit_stride) {
+          const int tile = kPair ? 2 * unit + static_cast<int>(rank) : unit;
           const int b = p.b_off + tile / tiles_per_item, t0 = (tile % tiles_per_item) * kTileM;
           for (int half = 0; half < 2; ++half) {
             for (int g = 0; g < ngroups; ++g, ++ga) {
               const int slot = ga % kFusedASlots;
               ptx::mbar_wait(&a_empty[slot], ((ga / kFusedASlots) & 1) ^ 1u);
-              if (g < 4) {
-                ptx::mbar_arrive_expect_tx(&a_full[slot], 130u * 128u);
-                ptx::tma_load_3d(sA + slot * kFusedASlotBytes, mHb, &a_full[slot], g * 64, t0 - 1, b);
+              // pair mode: both CTAs' loads signal the LEADER's barrier, which expects the bytes of both
+              if (leader) ptx::mbar_arrive_expect_tx(&a_full[slot], (g < 4 ? 130u * 128u : 128u * 128u) * kMul);
+              if constexpr (kPair) {
+                const uint32_t bar = ptx::mapa_u32(ptx::smem_u32(&a_full[slot]), 0);
+                if (g < 4) ptx::tma_load_3d_pair(sA + slot * kFusedASlotBytes, mHb, bar, g * 64, t0 - 1, b);
+                else ptx::tma_load_3d_pair(sA + slot * kFusedASlotBytes, &mapCond, bar, (g - 4) * 64, t0, b);
               } else {
-                ptx::mbar_arrive_expect_tx(&a_full[slot], 128u * 128u);
-                ptx::tma_load_3d(sA + slot * kFusedASlotBytes, &mapCond, &a_full[slot], (g - 4) * 64, t0, b);
+                if (g < 4) ptx::tma_load_3d(sA + slot * kFusedASlotBytes, mHb, &a_full[slot], g * 64, t0 - 1, b);
+                else ptx::tma_load_3d(sA + slot * kFusedASlotBytes, &mapCond, &a_full[slot], (g - 4) * 64, t0, b);
               }
               const int ntap = g < 4 ? 3 : 1;
               for (int j = 0; j < ntap; ++j, ++kw) {
-                const int s = kw % kFusedWStages;
-                ptx::mbar_wait(&w_empty[s], ((kw / kFusedWStages) & 1) ^ 1u);
-                ptx::mbar_arrive_expect_tx(&w_full[s], static_cast<uint32_t>(kFusedWStageBytes));
+                const int s = kw % WS;
+                ptx::mbar_wait(&w_empty[s], ((kw / WS) & 1) ^ 1u);
+                if (leader) ptx::mbar_arrive_expect_tx(&w_full[s], static_cast<uint32_t>(WB) * kMul);
                 const int kb = g < 4 ? j * 4 + g : 12 + (g - 4);
-                ptx::tma_load_2d(sW + s * kFusedWStageBytes, mW1, &w_full[s], kb * 64, half * 256);
+                if constexpr (kPair) ptx::tma_load_2d_pair(sW + s * WB, mW1, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * 64, half * 256 + nrow);
+                else ptx::tma_load_2d(sW + s * WB, mW1, &w_full[s], kb * 64, half * 256);
               }
             }
           }
           for (int kb = 0; kb < 4; ++kb, ++kw) {          // residual GEMM weights (its A operand is the smem copy of u)
-            const int s = kw % kFusedWStages;
-            ptx::mbar_wait(&w_empty[s], ((kw / kFusedWStages) & 1) ^ 1u);
-            ptx::mbar_arrive_expect_tx(&w_full[s], static_cast<uint32_t>(kFusedWStageBytes));
-            ptx::tma_load_2d(sW + s * kFusedWStageBytes, mW2, &w_full[s], kb * 64, 0);
+            const int s = kw % WS;
+            ptx::mbar_wait(&w_empty[s], ((kw / WS) & 1) ^ 1u);
+            if (leader) ptx::mbar_arrive_expect_tx(&w_full[s], static_cast<uint32_t>(WB) * kMul);
+            if constexpr (kPair) ptx::tma_load_2d_pair(sW + s * WB, mW2, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * 64, nrow);
+            else ptx::tma_load_2d(sW + s * WB, mW2, &w_full[s], kb * 64, 0);
           }
         }
       }
       __syncwarp();
     } else if (warp == 1) {
       // ---------------------------------------------------------------- MMA issuer
-      const uint32_t idesc = ptx::make_idesc_bf16_f32(kTileM, 256);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int tl = (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);   // local tile index in this layer
+      const uint32_t idesc = ptx::make_idesc_bf16_f32(kPair ? 2 * kTileM : kTileM, 256);
+      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+        if constexpr (kPair) ptx::mma_f16_ss_pair(d, da, db, idesc, acc); else ptx::mma_f16_ss(d, da, db, idesc, acc);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (kPair) ptx::mma_commit_pair(bar); else ptx::mma_commit(bar);
+      };
+      if (leader)
+      for (int unit = unit0; unit < total_units; unit += unit_stride, ++it) {
+        const int tl = (unit - unit0) / unit_stride;   // local unit index in this layer
         long long* dm = (p.dbg && blockIdx.x == 0 && l == 3 && lane == 0 && tl < 2) ? p.dbg + 1 + tl * 8 : nullptr;
         for (int half = 0; half < 2; ++half) {
           const int job = 3 * it + half, buf = job & 1;
@@ -180,25 +209,25 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
             ptx::mbar_wait(&a_full[slot], (ga / kFusedASlots) & 1);
             const int ntap = g < 4 ? 3 : 1;
             for (int j = 0; j < ntap; ++j, ++kw) {
-              const int s = kw % kFusedWStages;
-              ptx::mbar_wait(&w_full[s], (kw / kFusedWStages) & 1);
+              const int s = kw % WS;
+              ptx::mbar_wait(&w_full[s], (kw / WS) & 1);
               ptx::tc_fence_after();
               if (lane == 0) {
                 // hb tile holds frames t0-1 .. t0+128; tap j (offset j-1) starts at row j
                 const uint32_t a_addr = ptx::smem_u32(sA + slot * kFusedASlotBytes) + (g < 4 ? static_cast<uint32_t>(j * 128) : 0u);
                 const uint64_t da = ptx::make_desc_k_sw128(a_addr);
-                const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sW + s * kFusedWStageBytes));
+                const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sW + s * WB));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, accum | (k != 0 ? 1u : 0u));
-                ptx::mma_commit(&w_empty[s]);
+                for (int k = 0; k < 4; ++k) mma(tmem_d, da + 2 * k, db + 2 * k, accum | (k != 0 ? 1u : 0u));
+                commit(&w_empty[s]);
               }
               accum = 1;
               __syncwarp();
             }
-            if (lane == 0) ptx::mma_commit(&a_empty[slot]);
+            if (lane == 0) commit(&a_empty[slot]);
             __syncwarp();
           }
-          if (lane == 0) ptx::mma_commit(&acc_full[buf]);
+          if (lane == 0) commit(&acc_full[buf]);
           if (dm) dm[half * 2 + 1] = clock64();             // all MMAs of the job issued
           __syncwarp();
         }
@@ -211,21 +240,21 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           if (dm) dm[5] = clock64();
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * 256);
           for (int kb = 0; kb < 4; ++kb, ++kw) {
-            const int s = kw % kFusedWStages;
-            ptx::mbar_wait(&w_full[s], (kw / kFusedWStages) & 1);
+            const int s = kw % WS;
+            ptx::mbar_wait(&w_full[s], (kw / WS) & 1);
             ptx::tc_fence_after();
             if (lane == 0) {
               const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(sU + kb * 16384));
-              const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sW + s * kFusedWStageBytes));
+              const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sW + s * WB));
 #pragma unroll
-              for (int k = 0; k < 4; ++k) ptx::mma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-              ptx::mma_commit(&w_empty[s]);
+              for (int k = 0; k < 4; ++k) mma(tmem_d, da + 2 * k, db + 2 * k, (kb | k) != 0 ? 1u : 0u);
+              commit(&w_empty[s]);
             }
             __syncwarp();
           }
           if (lane == 0) {
-            ptx::mma_commit(u_empty);
-            ptx::mma_commit(&acc_full[buf]);
+            commit(u_empty);
+            commit(&acc_full[buf]);
           }
           if (dm) dm[6] = clock64();
           __syncwarp();
@@ -238,15 +267,20 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
       const int half2 = ew >> 2;
       const float* b2 = p.b2 + static_cast<size_t>(l) * kFC;
       __nv_bfloat16* hb_out = (l & 1) ? p.hb0 : p.hb1;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      // arrivals that the leader's MMA warp waits for: local barrier, or (pair mode) the leader's barrier through the cluster window
+      auto arrive_leader = [&](uint64_t* bar) {
+        if constexpr (kPair) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(bar), 0)); else ptx::mbar_arrive(bar);
+      };
+      for (int unit = unit0; unit < total_units; unit += unit_stride, ++it) {
+        const int tile = kPair ? 2 * unit + static_cast<int>(rank) : unit;
         const int b = p.b_off + tile / tiles_per_item, t0 = (tile % tiles_per_item) * kTileM;
         const int r = q * 32 + lane;                    // row inside the tile = TMEM lane
-        const int t = t0 + r;
+        const int t = tile < total_tiles ? t0 + r : p.T;   // a dummy tile (odd tile count in pair mode) has no valid row
         const bool row_ok = t < p.T;
         const size_t row = static_cast<size_t>(b) * p.T + t;
         const float* db = p.dbias + static_cast<size_t>(b) * p.dbias_bstride + static_cast<size_t>(l) * 3 * 512;
         const bool e0 = t < 1, e2 = t >= p.T - 1;       // dilation 1: the taps that fell on the zero padding
-        const int tl = (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);
+        const int tl = (unit - unit0) / unit_stride;
         long long* de = (p.dbg && blockIdx.x == 0 && l == 3 && ew == 0 && lane == 0 && tl < 2) ? p.dbg + 20 + tl * 8 : nullptr;
         if (it > 0) ptx::mbar_wait(u_empty, (it - 1) & 1);   // the previous tile's residual GEMM has finished reading u
         for (int half = 0; half < 2; ++half) {
@@ -300,8 +334,8 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           ptx::fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to the tensor core (async proxy)
           __syncwarp();
           if (lane == 0) {
-            ptx::mbar_arrive(&acc_empty[buf]);
-            ptx::mbar_arrive(u_full);
+            arrive_leader(&acc_empty[buf]);
+            arrive_leader(u_full);
           }
           if (de) de[half * 2 + 1] = clock64();             // gate epilogue of this half done
         }
@@ -314,7 +348,7 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           const int job = 3 * it + 2, buf = job & 1;
           float* stg = reinterpret_cast<float*>(sU + half2 * 16384 + q * 4096);
           const int cq = lane & 7, r0 = lane >> 3;
-          const int tq = t0 + q * 32 + r0;                      // frame of iteration 0; iteration i adds 4*i
+          const int tq = tile < total_tiles ? t0 + q * 32 + r0 : p.T;   // frame of iteration 0; iteration i adds 4*i
           const size_t rowq = static_cast<size_t>(b) * p.T + tq;
           float* hq = p.h + rowq * kFC + cq * 4;
           __nv_bfloat16* hbq = hb_out + rowq * kFC + cq * 4;
@@ -361,7 +395,7 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           }
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+          if (lane == 0) arrive_leader(&acc_empty[buf]);
           if (de) de[5] = clock64();
         }
       }
@@ -381,9 +415,10 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   __syncthreads();
+  if constexpr (kPair) ptx::cluster_sync_all();     // the peer may still be reading our smem / signalling our barriers
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if constexpr (kPair) ptx::tmem_dealloc_pair(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 

@@ -6,6 +6,8 @@
 //                                               lands at sample q*u + r - p
 // weight-norm (w = g v / ||v||) is folded once at load time.
 #include <cmath>
+#include <cstdlib>
+#include <deque>
 
 #include "epilogues.cuh"
 #include "fse_common.cuh"
@@ -167,7 +169,10 @@ struct fse_vocoder {
   std::vector<ConvW> ups;
   std::vector<ConvW> c1, c2;      // [stage][block][m]
   float* post_w = nullptr; float post_b = 0.f; int post_k = 7;
-  struct Plan { const void* ws = nullptr; int B = 0, T = 0; std::vector<CUtensorMap> maps; } plan;
+  struct MapEntry { const void* buf; int C, T, KB, rows; CUtensorMap map; };
+  struct Plan { const void* ws = nullptr; int B = 0, T = 0; std::deque<MapEntry> cache; } plan;
+  bool shared_a = false;  // FSE_VOC_SHARED_A=1 enables the shared-activation schedule (measured slower on B200: row-shifted
+                          // descriptors slow the MMA operand fetch more than the saved activation ingest gains)
   long long launches = 0;
   Profiler prof;
   void* host_ws = nullptr; size_t host_ws_bytes = 0;
@@ -281,10 +286,29 @@ int pack_up(fse_vocoder* h, const TensorTable& tt, const std::string& name, int 
   return finish_convw(h, cw, p, bias, Cout);
 }
 
+// Tensor map of an activation buffer with a given box height, cached in the plan (cleared when the workspace changes).
+int get_act_map(fse_vocoder* h, const void* buf, int C, int T, int B, int KB, int rows, const CUtensorMap** out) {
+  for (auto& e : h->plan.cache)
+    if (e.buf == buf && e.C == C && e.T == T && e.KB == KB && e.rows == rows) { *out = &e.map; return FSE_OK; }
+  h->plan.cache.emplace_back();
+  auto& e = h->plan.cache.back();
+  e.buf = buf; e.C = C; e.T = T; e.KB = KB; e.rows = rows;
+  FSE_TRY(make_map_act(&e.map, buf, C, T, B, KB, rows));
+  *out = &e.map;
+  return FSE_OK;
+}
+
 template <typename TOp, class Epi>
-int run_conv(fse_vocoder* h, const ConvW& cw, const void* A, const CUtensorMap* mA, int B, int Trows, int Tsrc, const Epi& epi, cudaStream_t st, int kind) {
+int run_conv(fse_vocoder* h, const ConvW& cw, const void* A, int B, int Trows, int Tsrc, const Epi& epi, cudaStream_t st, int kind) {
   ConvGemmParams p = make_params(B, Trows, Tsrc, cw.Cin, cw.ntaps, cw.offs, 0, cw.N, cw.KB);
-  GemmOperands op; op.A0 = A; op.W = cw.W; op.mA0 = mA; op.mW = &cw.map; op.BN = cw.BN;
+  GemmOperands op; op.A0 = A; op.W = cw.W; op.mW = &cw.map; op.BN = cw.BN;
+  if (h->cfg.mode == FSE_MODE_TC_BF16) {
+    // every tap of a conv reads the same activation tile shifted by whole frames: load it once per channel block
+    // (with the tap halo) and feed the taps from row-shifted descriptors -> activation ingest / ntaps
+    int rows = kTileM;
+    if (h->shared_a && enable_shared_a(p)) rows = p.Rrows;
+    FSE_TRY(get_act_map(h, A, cw.Cin, Tsrc, B, cw.KB, rows, &op.mA0));
+  }
   return run_conv_gemm<TOp>(h->cfg.mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, kind});
 }
 
@@ -294,23 +318,10 @@ int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, voi
   const auto& cfg = h->cfg;
   const bool tc = cfg.mode == FSE_MODE_TC_BF16;
   const int nu = cfg.num_upsamples, nk = cfg.num_kernels;
-  // tensor maps: [0] mel, [1] ua@pre, then per stage: ua(as ups input), xa, ya, tmp
   if (tc && !(h->plan.ws == ws && h->plan.B == B && h->plan.T == T)) {
-    h->plan.maps.assign(2 + 4 * nu, CUtensorMap{});
-    FSE_TRY(make_map_act(&h->plan.maps[0], w.melb, cfg.n_mels, T, B, h->pre.KB));
-    int Tin = T, Cin = cfg.upsample_initial_channel;
-    for (int i = 0; i < nu; ++i) {
-      const int Cout = stage_channels(h, i), Tout = Tin * cfg.upsample_rates[i];
-      const int kb = h->c1[i * nk * 3].KB;
-      FSE_TRY(make_map_act(&h->plan.maps[2 + 4 * i + 0], w.ua, Cin, Tin, B, h->ups[i].KB));
-      FSE_TRY(make_map_act(&h->plan.maps[2 + 4 * i + 1], w.xa, Cout, Tout, B, kb));
-      FSE_TRY(make_map_act(&h->plan.maps[2 + 4 * i + 2], w.ya, Cout, Tout, B, kb));
-      FSE_TRY(make_map_act(&h->plan.maps[2 + 4 * i + 3], w.tmp, Cout, Tout, B, kb));
-      Tin = Tout; Cin = Cout;
-    }
+    h->plan.cache.clear();
     h->plan.ws = ws; h->plan.B = B; h->plan.T = T;
   }
-  auto M = [&](int idx) -> const CUtensorMap* { return tc ? &h->plan.maps[idx] : nullptr; };
 
   const void* mel_op = mel;
   if constexpr (std::is_same<TOp, __nv_bfloat16>::value) {
@@ -322,7 +333,7 @@ int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, voi
   }
   {  // conv_pre + leaky_relu(0.1) of stage 0 (hifigan.py:127-129)
     EpiAct<TOp> epi{h->pre.bias, static_cast<TOp*>(w.ua), h->pre.N, T, 0.1f};
-    FSE_TRY((run_conv<TOp>(h, h->pre, mel_op, M(0), B, T, T, epi, st, 0)));
+    FSE_TRY((run_conv<TOp>(h, h->pre, mel_op, B, T, T, epi, st, 0)));
   }
   int Tin = T;
   for (int i = 0; i < nu; ++i) {
@@ -330,7 +341,7 @@ int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, voi
     const int Cout = stage_channels(h, i), Tout = Tin * u;
     {
       EpiUp<TOp> epi{h->ups[i].bias, w.x, static_cast<TOp*>(w.xa), Cout, Tout, u, pad};
-      FSE_TRY((run_conv<TOp>(h, h->ups[i], w.ua, M(2 + 4 * i), B, Tin + 1, Tin, epi, st, 1)));
+      FSE_TRY((run_conv<TOp>(h, h->ups[i], w.ua, B, Tin + 1, Tin, epi, st, 1)));
     }
     const bool last_stage = i == nu - 1;
     for (int j = 0; j < nk; ++j) {
@@ -339,7 +350,7 @@ int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, voi
         const ConvW& c = h->c2[(i * nk + j) * 3 + m];
         {
           EpiAct<TOp> epi{a.bias, static_cast<TOp*>(w.tmp), Cout, Tout, 0.1f};
-          FSE_TRY((run_conv<TOp>(h, a, m == 0 ? w.xa : w.ya, M(2 + 4 * i + (m == 0 ? 1 : 2)), B, Tout, Tout, epi, st, 2)));
+          FSE_TRY((run_conv<TOp>(h, a, m == 0 ? w.xa : w.ya, B, Tout, Tout, epi, st, 2)));
         }
         {
           EpiResAdd<TOp> epi{};
@@ -349,7 +360,7 @@ int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, voi
           epi.kind = m < 2 ? 0 : (nk == 1 ? 3 : (j == 0 ? 1 : (j == nk - 1 ? 3 : 2)));
           epi.num_kernels = static_cast<float>(nk);
           epi.slope_next = last_stage ? 0.01f : 0.1f;   // F.leaky_relu default slope before conv_post (hifigan.py:138)
-          FSE_TRY((run_conv<TOp>(h, c, w.tmp, M(2 + 4 * i + 3), B, Tout, Tout, epi, st, 3)));
+          FSE_TRY((run_conv<TOp>(h, c, w.tmp, B, Tout, Tout, epi, st, 3)));
         }
       }
     }
@@ -391,6 +402,7 @@ int fse_vocoder_create(const fse_vocoder_config* cfg, fse_vocoder** out) {
   h->cfg = *cfg;
   h->bf16 = cfg->mode != FSE_MODE_SIMT_F32;
   h->hop = hop;
+  if (const char* e = getenv("FSE_VOC_SHARED_A")) h->shared_a = atoi(e) != 0;
   *out = h;
   return FSE_OK;
 }
