@@ -293,7 +293,7 @@ def run_b200(args):
         fused = prof_d["res_gemm"][1] == 0
         if fused:   # one launch = all 20 residual layers: per layer gate GEMM 0.983 MFLOP/frame + residual GEMM 0.131 MFLOP/frame
             flops = 20 * 2.0 * B * T * (512 * 960 + 256 * 256)
-            kname = "denoiser_layers_kernel (20 x [k=3 conv + cond 1x1 + gate -> residual 1x1], fused, persistent)"
+            kname = "denoiser_layers_kernel<pair> (20 x [k=3 conv + cond 1x1 + gate -> residual 1x1]; persistent, cta_group::2)"
         else:
             flops = 2.0 * B * T * 512 * 960                  # algorithmic: 0.983 MFLOP/frame (k=3 conv 512x768 + cond 512x192)
             kname = "conv_gemm_tc_kernel<EpiGate> (dilated k=3 conv + conditioner 1x1 + gate)"

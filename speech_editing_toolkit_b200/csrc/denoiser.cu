@@ -190,7 +190,7 @@ struct fse_denoiser {
   std::vector<CUtensorMap> mW1, mW2;
   // fused multi-layer kernel (denoiser_fused.cuh): per-layer weight maps in device memory, grid barrier word
   bool fused = false;
-  bool fused_pair = false;   // FSE_FUSED=2: CTA pairs (tcgen05 cta_group::2), each CTA loads half of every weight tile
+  bool fused_pair = false;   // default when fused: CTA pairs (tcgen05 cta_group::2), each CTA loads half of every weight tile
   CUtensorMap* d_mW1 = nullptr; CUtensorMap* d_mW2f = nullptr; CUtensorMap* d_mW1p = nullptr; CUtensorMap* d_mW2p = nullptr;
   unsigned int* d_grid_bar = nullptr;
   int num_sms = 0;
@@ -534,7 +534,7 @@ int fse_denoiser_create(const fse_denoiser_config* cfg, fse_denoiser** out) {
   // condition channels); anything else runs the per-layer kernels.  FSE_FUSED=0 forces the per-layer path.
   h->fused = cfg->mode == FSE_MODE_TC_BF16 && cfg->channels == kFC && cfg->dilation_cycle_length == 1 && cfg->hidden <= 256 &&
              cfg->hidden % 64 == 0 && !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 0);
-  h->fused_pair = h->fused && getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 2;
+  h->fused_pair = h->fused && !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 1);   // FSE_FUSED=1: single-CTA variant
   if (getenv("FSE_DBG_STAMPS")) { cudaMalloc(reinterpret_cast<void**>(&h->dbg_buf), 64 * 8); cudaMemset(h->dbg_buf, 0, 64 * 8); }
   cudaGetDevice(&h->device);
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
