@@ -37,6 +37,8 @@ struct ConvGemmParams {
   int nkb1;    // k-blocks for source 1
   int N;       // output columns
   int Kp;      // padded K of the packed weight = (ntaps*nkb0 + nkb1)*KB
+  int MT;        // 128-frame sub-tiles per job (non-shared schedule): one weight tile feeds MT activation tiles and the
+                 //    accumulator buffer holds MT x BN columns - amortises the per-job handshakes when BN is small
   int shared_a;  // 1: load each channel block of source 0 ONCE per tile (Rrows = 128 + tap span rows) and feed every tap
                  //    from row-shifted UMMA descriptors of that one smem copy (cuts activation ingest by ntaps)
   int off_min;   // smallest tap offset; Rrows = 128 + max(off) - min(off)
@@ -209,13 +211,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   const int lane = threadIdx.x & 31;
   long long* dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
-  const int tiles_per_item = (p.Trows + kTileM - 1) / kTileM;
+  const int MT = p.shared_a ? 1 : (p.MT > 0 ? p.MT : 1);
+  const int tile_rows = kTileM * MT;
+  const int tiles_per_item = (p.Trows + tile_rows - 1) / tile_rows;
   const int n_tiles = p.N / BN;
   const int total_tiles = p.B * tiles_per_item * n_tiles;
   const int nkb_src0 = p.ntaps * p.nkb0;
   const int nkb = nkb_src0 + p.nkb1;
   uint32_t ncols = 32;
-  while (static_cast<int>(ncols) < 2 * BN) ncols <<= 1;
+  while (static_cast<int>(ncols) < 2 * MT * BN) ncols <<= 1;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&mapA0);
@@ -259,7 +263,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       const int ngroups = p.nkb0 + p.nkb1;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m = tile / n_tiles, n0 = (tile % n_tiles) * BN;
-        const int b = p.b_off + m / tiles_per_item, t0 = (m % tiles_per_item) * kTileM;
+        const int b = p.b_off + m / tiles_per_item, t0 = (m % tiles_per_item) * tile_rows;
         for (int g = 0; g < ngroups; ++g, ++ga) {
           const int slot = ga % a_slots;
           ptx::mbar_wait(&a_empty[slot], ((ga / a_slots) & 1) ^ 1u);
@@ -279,21 +283,25 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         if (dbg && tile == blockIdx.x) dbg[2] = clock64();
       }
     } else if (lane == 0) {
-      const uint32_t tx_bytes = static_cast<uint32_t>(kTileM * KB * 2 + BN * KB * 2);
+      constexpr int A1 = kTileM * KB * 2;            // one 128-frame activation tile
+      const uint32_t tx_bytes = static_cast<uint32_t>(MT * A1 + BN * KB * 2);
       int kbg = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m = tile / n_tiles, n0 = (tile % n_tiles) * BN;
-        const int b = p.b_off + m / tiles_per_item, t0 = (m % tiles_per_item) * kTileM;
+        const int b = p.b_off + m / tiles_per_item, t0 = (m % tiles_per_item) * tile_rows;
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
           const int s = kbg % stages;
           const uint32_t ph = (kbg / stages) & 1;
           ptx::mbar_wait(&empty[s], ph ^ 1u);
           ptx::mbar_arrive_expect_tx(&full[s], tx_bytes);
-          if (kb < nkb_src0) {
-            const int tap = kb / p.nkb0;
-            ptx::tma_load_3d(sA + s * A_BYTES, &mapA0, &full[s], p.c_off0 + (kb % p.nkb0) * KB, t0 + p.tap_off[tap], b);
-          } else {
-            ptx::tma_load_3d(sA + s * A_BYTES, &mapA1, &full[s], (kb - nkb_src0) * KB, t0, b);
+          for (int mt = 0; mt < MT; ++mt) {
+            if (kb < nkb_src0) {
+              const int tap = kb / p.nkb0;
+              ptx::tma_load_3d(sA + s * A_BYTES + mt * A1, &mapA0, &full[s], p.c_off0 + (kb % p.nkb0) * KB,
+                               t0 + mt * kTileM + p.tap_off[tap], b);
+            } else {
+              ptx::tma_load_3d(sA + s * A_BYTES + mt * A1, &mapA1, &full[s], (kb - nkb_src0) * KB, t0 + mt * kTileM, b);
+            }
           }
           ptx::tma_load_2d(sB + s * B_BYTES, &mapW, &full[s], kb * KB, n0);
         }
@@ -354,7 +362,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       const int buf = it & 1;
       ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u);
       ptx::tc_fence_after();
-      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * MT * BN);
       for (int kb = 0; kb < nkb; ++kb, ++kbg) {
         const int s = kbg % stages;
         const uint32_t ph = (kbg / stages) & 1;
@@ -362,13 +370,15 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         ptx::tc_fence_after();
         if (dbg && lane == 0 && kbg == 0) dbg[3] = clock64();   // first k-block landed
         if (lane == 0) {
-          const uint32_t a_addr = ptx::smem_u32(sA + s * A_BYTES);
           const uint32_t b_addr = ptx::smem_u32(sB + s * B_BYTES);
-          const uint64_t da = (KB == 64) ? ptx::make_desc_k_sw128(a_addr) : ptx::make_desc_k_sw64(a_addr);
           const uint64_t db = (KB == 64) ? ptx::make_desc_k_sw128(b_addr) : ptx::make_desc_k_sw64(b_addr);
+          for (int mt = 0; mt < MT; ++mt) {          // the same weight tile against MT activation sub-tiles
+            const uint32_t a_addr = ptx::smem_u32(sA + s * A_BYTES + mt * (kTileM * KB * 2));
+            const uint64_t da = (KB == 64) ? ptx::make_desc_k_sw128(a_addr) : ptx::make_desc_k_sw64(a_addr);
 #pragma unroll
-          for (int k = 0; k < KB / 16; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the addr>>4 field
-            ptx::mma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < KB / 16; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the addr>>4 field
+              ptx::mma_f16_ss(tmem_d + static_cast<uint32_t>(mt * BN), da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           ptx::mma_commit(&empty[s]);
           if (kb == nkb - 1) ptx::mma_commit(&acc_full[buf]);
           if (dbg && kb == nkb - 1 && it == 0) dbg[4] = clock64();   // all MMAs of the first tile issued
@@ -385,7 +395,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     const int ew = warp - 2;
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int half = ew >> 2;               // two warps share a quarter and split the column chunks
-    const int nchunks = BN / CH;
+    const int cpb = BN / CH;                 // chunks per 128-frame sub-tile
+    const int nchunks = MT * cpb;
     constexpr int AUXN = CH * (Epi::kAux > 0 ? Epi::kAux : 1);
     // Residual operands: when a warp owns at most kMaxPre chunks of a tile and they fit in 64 registers, ALL of
     // them are requested before the accumulator is awaited (one exposed memory latency per tile); otherwise the
@@ -398,20 +409,19 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const int m = tile / n_tiles, n0 = (tile % n_tiles) * BN;
-      const int b = p.b_off + m / tiles_per_item, t0 = (m % tiles_per_item) * kTileM;
-      const int t = t0 + q * 32 + lane;
-      const bool row_ok = t < p.Trows;
-      const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * BN);
+      const int b = p.b_off + m / tiles_per_item, t0 = (m % tiles_per_item) * tile_rows;
+      const int tl0 = t0 + q * 32 + lane;      // frame of this lane in sub-tile 0; chunk c lives in sub-tile c / cpb
+      auto T_OF = [&](int c) { return tl0 + (c / cpb) * kTileM; };
+      auto N_OF = [&](int c) { return n0 + (c % cpb) * CH; };
+      const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * MT * BN);
       float aux[kMaxPre > 0 ? kMaxPre : 1][AUXN];
       if constexpr (kChunkAhead) {
-        if (row_ok) {
-          if (pre_all) {
+        if (pre_all) {
 #pragma unroll
-            for (int i = 0; i < kMaxPre; ++i)
-              if (i < my_chunks) epi.template load_aux<CH>(b, t, n0 + (half + 2 * i) * CH, aux[i]);
-          } else if (half < nchunks) {
-            epi.template load_aux<CH>(b, t, n0 + half * CH, aux[0]);
-          }
+          for (int i = 0; i < kMaxPre; ++i)
+            if (i < my_chunks && T_OF(half + 2 * i) < p.Trows) epi.template load_aux<CH>(b, T_OF(half + 2 * i), N_OF(half + 2 * i), aux[i]);
+        } else if (half < nchunks && T_OF(half) < p.Trows) {
+          epi.template load_aux<CH>(b, T_OF(half), N_OF(half), aux[0]);
         }
       }
       ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
@@ -420,11 +430,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       int ci = 0;
       for (int c = half; c < nchunks; c += 2, ++ci) {
         uint32_t r[CH];
+        const int t = T_OF(c);
+        const bool row_ok = t < p.Trows;
         const bool stamp = dbg && ew == 0 && lane == 0 && it == 0 && c < 8;
         if (stamp) dbg[16 + 4 * (c >> 1)] = clock64();
         float aux_here[(Epi::kAux > 0 && !kChunkAhead) ? AUXN : 1];
         if constexpr (Epi::kAux > 0 && !kChunkAhead) {
-          if (row_ok) epi.template load_aux<CH>(b, t, n0 + c * CH, aux_here);
+          if (row_ok) epi.template load_aux<CH>(b, t, N_OF(c), aux_here);
         }
         if constexpr (CH == 32) ptx::tmem_ld_32x32b_x32(lane_base + c * CH, r);
         else ptx::tmem_ld_32x32b_x16(lane_base + c * CH, r);
@@ -432,7 +444,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         if (stamp) dbg[17 + 4 * (c >> 1)] = clock64();
         float aux_next[kChunkAhead ? AUXN : 1];
         if constexpr (kChunkAhead) {
-          if (!pre_all && c + 2 < nchunks && row_ok) epi.template load_aux<CH>(b, t, n0 + (c + 2) * CH, aux_next);
+          if (!pre_all && c + 2 < nchunks && T_OF(c + 2) < p.Trows) epi.template load_aux<CH>(b, T_OF(c + 2), N_OF(c + 2), aux_next);
         }
         if (stamp) dbg[18 + 4 * (c >> 1)] = clock64();
         if (row_ok) {
@@ -444,12 +456,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
               // static register indexing: pick the pre-loaded set of this chunk
 #pragma unroll
               for (int i = 0; i < kMaxPre; ++i)
-                if (i == ci) epi.template apply<CH>(b, t, n0 + c * CH, v, aux[i]);
+                if (i == ci) epi.template apply<CH>(b, t, N_OF(c), v, aux[i]);
             } else {
-              epi.template apply<CH>(b, t, n0 + c * CH, v, aux[0]);
+              epi.template apply<CH>(b, t, N_OF(c), v, aux[0]);
             }
           } else {
-            epi.template apply<CH>(b, t, n0 + c * CH, v, aux_here);
+            epi.template apply<CH>(b, t, N_OF(c), v, aux_here);
           }
         }
         if constexpr (kChunkAhead) {

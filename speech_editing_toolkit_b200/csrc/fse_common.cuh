@@ -198,7 +198,7 @@ struct GemmOperands {
 inline ConvGemmParams make_params(int B, int Trows, int Tsrc, int C0, int ntaps, const int* offs, int C1, int N, int KB) {
   ConvGemmParams p;
   memset(&p, 0, sizeof(p));
-  p.B = B; p.Trows = Trows; p.Tsrc = Tsrc; p.C0 = C0; p.C1 = C1; p.ntaps = ntaps; p.ld0 = C0;
+  p.B = B; p.Trows = Trows; p.Tsrc = Tsrc; p.C0 = C0; p.C1 = C1; p.ntaps = ntaps; p.ld0 = C0; p.MT = 1;
   for (int i = 0; i < ntaps; ++i) p.tap_off[i] = offs[i];
   p.KB = KB;
   p.nkb0 = (C0 + KB - 1) / KB;
@@ -236,7 +236,7 @@ inline int launch_tc(const ConvGemmParams& p, const GemmOperands& op, const Epi&
     stages = (225 * 1024 - a_slots * a_slot_bytes) / tc_b_stage_bytes(op.BN, KB);
     if (stages > 8) stages = 8;
   } else {
-    a_slot_bytes = tc_a_stage_bytes(KB);
+    a_slot_bytes = tc_a_stage_bytes(KB) * (p.MT > 0 ? p.MT : 1);
     stages = (225 * 1024) / (a_slot_bytes + tc_b_stage_bytes(op.BN, KB));
     if (stages > 6) stages = 6;
     a_slots = 0;   // = stages, set below
@@ -256,7 +256,8 @@ inline int launch_tc(const ConvGemmParams& p, const GemmOperands& op, const Epi&
     FSE_CUDA(cudaGetDevice(&dev));
     FSE_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int total_tiles = p.B * ((p.Trows + kTileM - 1) / kTileM) * (p.N / op.BN);
+  const int tile_rows = kTileM * (p.shared_a ? 1 : (p.MT > 0 ? p.MT : 1));
+  const int total_tiles = p.B * ((p.Trows + tile_rows - 1) / tile_rows) * (p.N / op.BN);
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);   // persistent: one CTA per SM
   const CUtensorMap* mA1 = op.mA1 ? op.mA1 : op.mA0;
   cudaLaunchConfig_t cfg{};
