@@ -133,10 +133,19 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
     // Per-layer bias tables -> shared memory (L1 is streamed through by the fp32 residual traffic, so per-chunk __ldg of
     // the tables kept missing).  With per-item tables (dbias_bstride != 0) only the residual bias is staged.
     if (warp >= 2) {
-      const int e = threadIdx.x - 64;
-      if (p.dbias_bstride == 0)
-        for (int i = e; i < 3 * 512; i += kEpiWarps * 32) sBias[i] = __ldg(p.dbias + static_cast<size_t>(l) * 3 * 512 + i);
-      for (int i = e; i < 256; i += kEpiWarps * 32) sBias[3 * 512 + i] = __ldg(p.b2 + static_cast<size_t>(l) * kFC + i);
+      const int e = threadIdx.x - 64;                      // 0..255
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
+      const float4* tab = reinterpret_cast<const float4*>(p.dbias + static_cast<size_t>(l) * 3 * 512);
+      if (p.dbias_bstride == 0) {                          // 384 float4: all loads in flight before the first store
+        v0 = __ldg(tab + e);
+        if (e < 128) v1 = __ldg(tab + 256 + e);
+      }
+      if (e < 64) v2 = __ldg(reinterpret_cast<const float4*>(p.b2 + static_cast<size_t>(l) * kFC) + e);
+      if (p.dbias_bstride == 0) {
+        reinterpret_cast<float4*>(sBias)[e] = v0;
+        if (e < 128) reinterpret_cast<float4*>(sBias)[256 + e] = v1;
+      }
+      if (e < 64) reinterpret_cast<float4*>(sBias + 3 * 512)[e] = v2;
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");      // epilogue warps only
     }
     if (warp == 0) {

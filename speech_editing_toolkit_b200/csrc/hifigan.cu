@@ -171,7 +171,8 @@ struct fse_vocoder {
   float* post_w = nullptr; float post_b = 0.f; int post_k = 7;
   struct MapEntry { const void* buf; int C, T, KB, rows; CUtensorMap map; };
   struct Plan { const void* ws = nullptr; int B = 0, T = 0; std::deque<MapEntry> cache; } plan;
-  bool multi_tile = true; // FSE_VOC_MT=0 disables multi-sub-tile jobs for narrow layers
+  bool multi_tile = true; // FSE_VOC_MT=0 disables multi-sub-tile jobs for narrow layers; FSE_VOC_MT=2: larger jobs
+  int multi_tile_level = 2;
   bool shared_a = false;  // FSE_VOC_SHARED_A=1 enables the shared-activation schedule (measured slower on B200: row-shifted
                           // descriptors slow the MMA operand fetch more than the saved activation ingest gains)
   long long launches = 0;
@@ -309,7 +310,10 @@ int run_conv(fse_vocoder* h, const ConvW& cw, const void* A, int B, int Trows, i
     int rows = kTileM;
     if (h->shared_a && enable_shared_a(p)) rows = p.Rrows;
     // narrow layers (C_out <= 128): one job = several 128-frame sub-tiles against the same weight tiles
-    else if (h->multi_tile && cw.BN == cw.N) p.MT = cw.BN <= 32 ? 4 : (cw.BN <= 128 ? 2 : 1);
+    else if (h->multi_tile && cw.BN == cw.N) {
+      if (h->multi_tile_level >= 2) p.MT = cw.BN <= 32 ? 8 : (cw.BN <= 64 ? 4 : (cw.BN <= 128 ? 2 : 1));
+      else p.MT = cw.BN <= 32 ? 4 : (cw.BN <= 128 ? 2 : 1);
+    }
     FSE_TRY(get_act_map(h, A, cw.Cin, Tsrc, B, cw.KB, rows, &op.mA0));
   }
   return run_conv_gemm<TOp>(h->cfg.mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, kind});
@@ -406,7 +410,7 @@ int fse_vocoder_create(const fse_vocoder_config* cfg, fse_vocoder** out) {
   h->bf16 = cfg->mode != FSE_MODE_SIMT_F32;
   h->hop = hop;
   if (const char* e = getenv("FSE_VOC_SHARED_A")) h->shared_a = atoi(e) != 0;
-  if (const char* e = getenv("FSE_VOC_MT")) h->multi_tile = atoi(e) != 0;
+  if (const char* e = getenv("FSE_VOC_MT")) { h->multi_tile = atoi(e) != 0; h->multi_tile_level = atoi(e); }
   *out = h;
   return FSE_OK;
 }

@@ -164,7 +164,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (.release.cta) as in CUTLASS' ClusterBarrier::arrive(cta_id): a cluster-scope release would drain the
+  // thread's outstanding GLOBAL stores too (seen as ERRBAR stalls); the smem data was already published with fence.proxy.async
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: data lands in the executing CTA's smem, completion bytes are signalled on an mbarrier
 // given by its shared::cluster address (the leader CTA's barrier).
