@@ -6,7 +6,8 @@
   python bench.py --impl reference ...                     (CPU arm: the path's torch CPU port on host cores)
 
 One "step" = one pass of the hot path over one batch: S=100 reverse-diffusion iterations of the DiffNet
-denoiser (43 kernels each) followed by the vocoder forward (79 kernels).  Prints ONE JSON line (rank 0).
+denoiser (4 kernels each: input projection, the fused 20-layer kernel, folded skip GEMM, output projection + posterior)
+followed by the vocoder forward (79 kernels).  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -300,7 +301,10 @@ def run_b200(args):
         ach = flops / (g_ms / g_n * 1e-3) / 1e12 if g_n else 0.0
         roofline = {"kernel": kname, "bound": "tensor",
                     "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
-                    "peak_source": pk["src"] + ", sustained bf16", "traffic": None,
+                    "peak_source": pk["src"] + ", sustained bf16",
+                    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this shape, from the committed
+                    # `ncu --set full` capture (profiles/r01_ncu_fused_pair_kernel.md); null for the per-layer fallback kernels
+                    "traffic": 969868288 if (fused and (B, T) == (32, 1024)) else None, "traffic_unit": "bytes/launch (ncu)",
                     "avg_launch_us": g_ms / g_n * 1e3 if g_n else None, "launches_timed": g_n,
                     "flops_per_launch": flops}
     breakdown = {}

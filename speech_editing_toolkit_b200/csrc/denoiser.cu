@@ -190,6 +190,7 @@ struct fse_denoiser {
   std::vector<CUtensorMap> mW1, mW2;
   // fused multi-layer kernel (denoiser_fused.cuh): per-layer weight maps in device memory, grid barrier word
   bool fused = false;
+  bool fused_shared_a = true;    // one activation load per channel block + row-shifted tap descriptors (FSE_FUSED_SHARED_A=0: per-tap loads)
   bool fused_pair = false;   // default when fused: CTA pairs (tcgen05 cta_group::2), each CTA loads half of every weight tile
   CUtensorMap* d_mW1 = nullptr; CUtensorMap* d_mW2f = nullptr; CUtensorMap* d_mW1p = nullptr; CUtensorMap* d_mW2p = nullptr;
   unsigned int* d_grid_bar = nullptr;
@@ -197,7 +198,8 @@ struct fse_denoiser {
   struct Plan {
     const void* ws = nullptr; const void* cond = nullptr; int B = 0, T = 0;
     CUtensorMap m_xb{}, m_hb{}, m_cond{}, m_u{}, m_rb{};
-    CUtensorMap m_hb0_halo{}, m_hb1_halo{};     // 130-row boxes of the two hb buffers (fused kernel)
+    CUtensorMap m_hb0_halo{}, m_hb1_halo{};     // 130-row boxes of the two hb buffers (fused kernel, shared-A schedule)
+    CUtensorMap m_hb1{};                        // 128-row box of the second hb buffer
   } plan;
   long long launches = 0;
   int batch_chunk = 0;     // utterances per L2-resident chunk (0 = whole batch); FSE_BATCH_CHUNK overrides
@@ -264,6 +266,7 @@ int build_plan(fse_denoiser* h, const Workspace& w, const void* ws, const void* 
   if (h->fused) {
     FSE_TRY(make_map_act(&pl.m_hb0_halo, w.hb, C, T, B, 64, 130));
     FSE_TRY(make_map_act(&pl.m_hb1_halo, w.hb1, C, T, B, 64, 130));
+    FSE_TRY(make_map_act(&pl.m_hb1, w.hb1, C, T, B, 64));
   }
   pl.ws = ws; pl.B = B; pl.T = T; pl.cond = cond;
   return FSE_OK;
@@ -325,8 +328,9 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
       fp.dbg = h->dbg_buf;
       static bool attr_set = false;
       if (!attr_set) {
-        FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
-        FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
+        FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
+        FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
+        FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
         attr_set = true;
       }
       const int tiles = Bc * ((T + kTileM - 1) / kTileM);
@@ -343,9 +347,12 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_layers_kernel<true>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp));
+        if (h->fused_shared_a)
+          FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_layers_kernel<true, true>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp));
+        else
+          FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_layers_kernel<true, false>, h->plan.m_hb, h->plan.m_hb1, h->plan.m_cond, fp));
       } else {
-        denoiser_layers_kernel<false><<<tiles < h->num_sms ? tiles : h->num_sms, kTcThreads, kFusedSmemBytes, st>>>(
+        denoiser_layers_kernel<false, true><<<tiles < h->num_sms ? tiles : h->num_sms, kTcThreads, kFusedSmemBytes, st>>>(
             h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp);
       }
       h->prof.end(st);
@@ -535,6 +542,7 @@ int fse_denoiser_create(const fse_denoiser_config* cfg, fse_denoiser** out) {
   h->fused = cfg->mode == FSE_MODE_TC_BF16 && cfg->channels == kFC && cfg->dilation_cycle_length == 1 && cfg->hidden <= 256 &&
              cfg->hidden % 64 == 0 && !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 0);
   h->fused_pair = h->fused && !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 1);   // FSE_FUSED=1: single-CTA variant
+  h->fused_shared_a = !(getenv("FSE_FUSED_SHARED_A") && atoi(getenv("FSE_FUSED_SHARED_A")) == 0);   // measured: 92.3 vs 95.3 ms/step
   if (getenv("FSE_DBG_STAMPS")) { cudaMalloc(reinterpret_cast<void**>(&h->dbg_buf), 64 * 8); cudaMemset(h->dbg_buf, 0, 64 * 8); }
   cudaGetDevice(&h->device);
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);

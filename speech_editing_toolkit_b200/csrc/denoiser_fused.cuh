@@ -65,22 +65,27 @@ __device__ __forceinline__ void fused_grid_barrier(unsigned int* bar, unsigned i
 
 // kPair: the two CTAs of a cluster process two adjacent tiles with M = 256 tcgen05.mma.cta_group::2 instructions
 // issued by the leader; each CTA loads only HALF of every weight tile (the per-SM L2->SM ingest is the limiter).
-template <bool kPair>
+template <bool kPair, bool kSharedA>
 __global__ void __launch_bounds__(kTcThreads, 1)
 denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_constant__ CUtensorMap mapHb1,
                        const __grid_constant__ CUtensorMap mapCond, FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int WB = kPair ? 128 * 128 : 256 * 128;     // bytes of one weight stage (128 or 256 rows x 64 bf16)
-  constexpr int WS = kPair ? 2 * kFusedWStages : kFusedWStages;
+  // kSharedA: one 130-row activation load per channel block, taps = row-shifted descriptors (less ingest, but the
+  // misaligned operand fetch slows the MMA); otherwise one 128-row load per (tap, channel block).
+  constexpr int AS = kSharedA ? kFusedASlots : 4;
+  constexpr int AB = kSharedA ? kFusedASlotBytes : 128 * 128;
+  constexpr int WS = kPair ? (kSharedA ? 6 : 5) : kFusedWStages;
+  static_assert(AS * AB + WS * WB <= kFusedASlots * kFusedASlotBytes + kFusedWStages * kFusedWStageBytes, "smem budget");
   constexpr uint32_t kMul = kPair ? 2u : 1u;
   uint8_t* sA = smem;
-  uint8_t* sW = sA + kFusedASlots * kFusedASlotBytes;
+  uint8_t* sW = sA + AS * AB;
   uint8_t* sU = sW + WS * WB;
   float* sBias = reinterpret_cast<float*>(sU + kFusedUBytes);          // [3][512] timestep tables + [256] residual bias of the layer
   uint64_t* a_full = reinterpret_cast<uint64_t*>(sU + kFusedUBytes + kFusedBiasBytes);
-  uint64_t* a_empty = a_full + kFusedASlots;
-  uint64_t* w_full = a_empty + kFusedASlots;
+  uint64_t* a_empty = a_full + AS;
+  uint64_t* w_full = a_empty + AS;
   uint64_t* w_empty = w_full + WS;
   uint64_t* acc_full = w_empty + WS;              // [2]
   uint64_t* acc_empty = acc_full + 2;             // [2]
@@ -99,7 +104,8 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
   const int unit_stride = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int total_units = kPair ? (total_tiles + 1) / 2 : total_tiles;
   const int nkbH = (p.H + 63) / 64;
-  const int ngroups = 4 + nkbH;                    // 4 hb channel blocks (3 taps each) + cond blocks (1 tap)
+  const int nhb = kSharedA ? 4 : 12;               // hb groups: 4 channel blocks (3 taps each) or 12 (tap, block) pairs
+  const int ngroups = nhb + nkbH;                  // + cond blocks (1 tap)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&mapHb0);
@@ -108,7 +114,7 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < kFusedASlots; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+      for (int i = 0; i < AS; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
       for (int i = 0; i < WS; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
       for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kEpiWarps * kMul); }
       ptx::mbar_init(u_full, 2 * kEpiWarps * kMul);
@@ -160,24 +166,25 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           const int b = p.b_off + tile / tiles_per_item, t0 = (tile % tiles_per_item) * kTileM;
           for (int half = 0; half < 2; ++half) {
             for (int g = 0; g < ngroups; ++g, ++ga) {
-              const int slot = ga % kFusedASlots;
-              ptx::mbar_wait(&a_empty[slot], ((ga / kFusedASlots) & 1) ^ 1u);
+              const int slot = ga % AS;
+              ptx::mbar_wait(&a_empty[slot], ((ga / AS) & 1) ^ 1u);
               // pair mode: both CTAs' loads signal the LEADER's barrier, which expects the bytes of both
-              if (leader) ptx::mbar_arrive_expect_tx(&a_full[slot], (g < 4 ? 130u * 128u : 128u * 128u) * kMul);
+              const bool is_hb = g < nhb;
+              const uint32_t rows = (kSharedA && is_hb) ? 130u : 128u;
+              const int c0 = is_hb ? (kSharedA ? g : (g & 3)) * 64 : (g - nhb) * 64;
+              const int tt = is_hb ? (kSharedA ? t0 - 1 : t0 + (g >> 2) - 1) : t0;      // non-shared: tap g/4 has offset g/4 - 1
+              if (leader) ptx::mbar_arrive_expect_tx(&a_full[slot], rows * 128u * kMul);
               if constexpr (kPair) {
-                const uint32_t bar = ptx::mapa_u32(ptx::smem_u32(&a_full[slot]), 0);
-                if (g < 4) ptx::tma_load_3d_pair(sA + slot * kFusedASlotBytes, mHb, bar, g * 64, t0 - 1, b);
-                else ptx::tma_load_3d_pair(sA + slot * kFusedASlotBytes, &mapCond, bar, (g - 4) * 64, t0, b);
+                ptx::tma_load_3d_pair(sA + slot * AB, is_hb ? mHb : &mapCond, ptx::mapa_u32(ptx::smem_u32(&a_full[slot]), 0), c0, tt, b);
               } else {
-                if (g < 4) ptx::tma_load_3d(sA + slot * kFusedASlotBytes, mHb, &a_full[slot], g * 64, t0 - 1, b);
-                else ptx::tma_load_3d(sA + slot * kFusedASlotBytes, &mapCond, &a_full[slot], (g - 4) * 64, t0, b);
+                ptx::tma_load_3d(sA + slot * AB, is_hb ? mHb : &mapCond, &a_full[slot], c0, tt, b);
               }
-              const int ntap = g < 4 ? 3 : 1;
+              const int ntap = (kSharedA && is_hb) ? 3 : 1;
               for (int j = 0; j < ntap; ++j, ++kw) {
                 const int s = kw % WS;
                 ptx::mbar_wait(&w_empty[s], ((kw / WS) & 1) ^ 1u);
                 if (leader) ptx::mbar_arrive_expect_tx(&w_full[s], static_cast<uint32_t>(WB) * kMul);
-                const int kb = g < 4 ? j * 4 + g : 12 + (g - 4);
+                const int kb = kSharedA ? (g < 4 ? j * 4 + g : 12 + (g - 4)) : g;     // weight k-blocks are packed tap-major
                 if constexpr (kPair) ptx::tma_load_2d_pair(sW + s * WB, mW1, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * 64, half * 256 + nrow);
                 else ptx::tma_load_2d(sW + s * WB, mW1, &w_full[s], kb * 64, half * 256);
               }
@@ -214,16 +221,16 @@ denoiser_layers_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * 256);
           uint32_t accum = 0;
           for (int g = 0; g < ngroups; ++g, ++ga) {
-            const int slot = ga % kFusedASlots;
-            ptx::mbar_wait(&a_full[slot], (ga / kFusedASlots) & 1);
-            const int ntap = g < 4 ? 3 : 1;
+            const int slot = ga % AS;
+            ptx::mbar_wait(&a_full[slot], (ga / AS) & 1);
+            const int ntap = (kSharedA && g < nhb) ? 3 : 1;
             for (int j = 0; j < ntap; ++j, ++kw) {
               const int s = kw % WS;
               ptx::mbar_wait(&w_full[s], (kw / WS) & 1);
               ptx::tc_fence_after();
               if (lane == 0) {
                 // hb tile holds frames t0-1 .. t0+128; tap j (offset j-1) starts at row j
-                const uint32_t a_addr = ptx::smem_u32(sA + slot * kFusedASlotBytes) + (g < 4 ? static_cast<uint32_t>(j * 128) : 0u);
+                const uint32_t a_addr = ptx::smem_u32(sA + slot * AB) + ((kSharedA && g < nhb) ? static_cast<uint32_t>(j * 128) : 0u);
                 const uint64_t da = ptx::make_desc_k_sw128(a_addr);
                 const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sW + s * WB));
 #pragma unroll
