@@ -7,7 +7,7 @@
 
 #include "epilogues.cuh"
 #include "fse_common.cuh"
-#include "denoiser_fused.cuh"
+#include "denoiser_stream.cuh"
 
 namespace fse {
 
@@ -191,6 +191,7 @@ struct fse_denoiser {
   // fused multi-layer kernel (denoiser_fused.cuh): per-layer weight maps in device memory, grid barrier word
   bool fused = false;
   bool fused_shared_a = true;    // one activation load per channel block + row-shifted tap descriptors (FSE_FUSED_SHARED_A=0: per-tap loads)
+  bool fused_stream = true;  // (layer, unit) items dealt round-robin, neighbour flags instead of the grid barrier (FSE_FUSED_STREAM=0: lock step)
   bool fused_pair = false;   // default when fused: CTA pairs (tcgen05 cta_group::2), each CTA loads half of every weight tile
   CUtensorMap* d_mW1 = nullptr; CUtensorMap* d_mW2f = nullptr; CUtensorMap* d_mW1p = nullptr; CUtensorMap* d_mW2p = nullptr;
   unsigned int* d_grid_bar = nullptr;
@@ -214,6 +215,7 @@ namespace {
 struct Workspace {
   float* h; void* hb; void* hb1; void* u; void* rb; void* xb; void* condb;
   float* xa; float* xbuf2; float* tvals; float* temb; float* d; float* dbias;
+  unsigned int* done;             // [L, tiles] layer-publication counters of the streamed residual-layer kernel
   size_t bytes;
 };
 
@@ -240,6 +242,7 @@ Workspace carve(const fse_denoiser* h, void* base, int B, int T) {
   o = take(nT * C * 4); w.temb = reinterpret_cast<float*>(p + o);
   o = take(nT * L * C * 4); w.d = reinterpret_cast<float*>(p + o);
   o = take(nT * L * 3 * 2 * C * 4); w.dbias = reinterpret_cast<float*>(p + o);
+  o = take(h->fused ? static_cast<size_t>(L) * B * ((T + kTileM - 1) / kTileM) * 4 : 0); w.done = reinterpret_cast<unsigned int*>(p + o);
   w.bytes = off;
   return w;
 }
@@ -323,7 +326,7 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
       fp.u_all = static_cast<__nv_bfloat16*>(w.u);
       fp.dbias = w.dbias + static_cast<size_t>(tidx_base) * L * 3 * 2 * C;
       fp.dbias_bstride = static_cast<long long>(tidx_bstride) * L * 3 * 2 * C;
-      fp.b2 = h->b2; fp.grid_bar = h->d_grid_bar; fp.mW1 = h->d_mW1; fp.mW2 = h->d_mW2f;
+      fp.b2 = h->b2; fp.grid_bar = h->d_grid_bar; fp.done = w.done; fp.mW1 = h->d_mW1; fp.mW2 = h->d_mW2f;
       fp.mW1p = h->d_mW1p; fp.mW2p = h->d_mW2p;
       fp.dbg = h->dbg_buf;
       static bool attr_set = false;
@@ -331,10 +334,14 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
         FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
         FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
         FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
+        FSE_CUDA(cudaFuncSetAttribute(denoiser_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
+        FSE_CUDA(cudaFuncSetAttribute(denoiser_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
         attr_set = true;
       }
       const int tiles = Bc * ((T + kTileM - 1) / kTileM);
-      FSE_CUDA(cudaMemsetAsync(h->d_grid_bar, 0, sizeof(unsigned int), st));
+      const bool stream = h->fused_stream && h->fused_shared_a;
+      if (stream) FSE_CUDA(cudaMemsetAsync(w.done, 0, static_cast<size_t>(L) * tiles * sizeof(unsigned int), st));
+      else FSE_CUDA(cudaMemsetAsync(h->d_grid_bar, 0, sizeof(unsigned int), st));
       ++h->launches;
       h->prof.begin(1, st);
       if (h->fused_pair) {
@@ -347,10 +354,15 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        if (h->fused_shared_a)
+        if (stream)
+          FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_stream_kernel<true>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp));
+        else if (h->fused_shared_a)
           FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_layers_kernel<true, true>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp));
         else
           FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_layers_kernel<true, false>, h->plan.m_hb, h->plan.m_hb1, h->plan.m_cond, fp));
+      } else if (stream) {
+        denoiser_stream_kernel<false><<<tiles < h->num_sms ? tiles : h->num_sms, kTcThreads, kFusedSmemBytes, st>>>(
+            h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp);
       } else {
         denoiser_layers_kernel<false, true><<<tiles < h->num_sms ? tiles : h->num_sms, kTcThreads, kFusedSmemBytes, st>>>(
             h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp);
@@ -483,14 +495,19 @@ int sample_impl(fse_denoiser* h, const float* cond, const float* noise, uint64_t
     long long d[64];
     cudaStreamSynchronize(st);
     cudaMemcpy(d, h->dbg_buf, sizeof(d), cudaMemcpyDeviceToHost);
-    const long long t0 = d[42];   // CTA 0 left the barrier before layer 3
-    fprintf(stderr, "[fse fused stamps, CTA0 layer3, cycles since barrier exit] barrier_enter(l2)=%lld\n", d[0] - t0);
+    const bool stream = h->fused_stream && h->fused_shared_a;
+    // lock step: CTA 0's two tiles of layer 3, cycles since it left the barrier before layer 3; streamed: items 6, 7 of CTA 0
+    // (last DiffNet evaluation), cycles since kernel start
+    const long long t0 = stream ? d[0] : d[42];
+    if (!stream) fprintf(stderr, "[fse fused stamps, CTA0 layer3, cycles since barrier exit] barrier_enter(l2)=%lld\n", d[0] - t0);
+    else fprintf(stderr, "[fse streamed stamps, CTA0 items 6,7, cycles since kernel start]\n");
     for (int tl = 0; tl < 2; ++tl) {
       const long long* m = d + 1 + tl * 8; const long long* e = d + 20 + tl * 8;
       fprintf(stderr, "  tile%d MMA: G1a %lld..%lld G1b %lld..%lld G2 buf_free=%lld u_ready=%lld issued=%lld | EPI(w2): e1a %lld..%lld e1b %lld..%lld e2 %lld..%lld\n",
               tl, m[0] - t0, m[1] - t0, m[2] - t0, m[3] - t0, m[4] - t0, m[5] - t0, m[6] - t0, e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0, e[5] - t0);
+      if (stream) fprintf(stderr, "        producer: dependency wait %lld..%lld\n", d[40 + 2 * tl] - t0, d[41 + 2 * tl] - t0);
     }
-    fprintf(stderr, "  layer3 end: syncthreads passed=%lld grid barrier passed=%lld\n", d[40] - t0, d[41] - t0);
+    if (!stream) fprintf(stderr, "  layer3 end: syncthreads passed=%lld grid barrier passed=%lld\n", d[40] - t0, d[41] - t0);
   } else if (h->dbg_buf) {
     long long d[64];
     cudaStreamSynchronize(st);
@@ -542,6 +559,7 @@ int fse_denoiser_create(const fse_denoiser_config* cfg, fse_denoiser** out) {
   h->fused = cfg->mode == FSE_MODE_TC_BF16 && cfg->channels == kFC && cfg->dilation_cycle_length == 1 && cfg->hidden <= 256 &&
              cfg->hidden % 64 == 0 && !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 0);
   h->fused_pair = h->fused && !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 1);   // FSE_FUSED=1: single-CTA variant
+  h->fused_stream = !(getenv("FSE_FUSED_STREAM") && atoi(getenv("FSE_FUSED_STREAM")) == 0);
   h->fused_shared_a = !(getenv("FSE_FUSED_SHARED_A") && atoi(getenv("FSE_FUSED_SHARED_A")) == 0);   // measured: 92.3 vs 95.3 ms/step
   if (getenv("FSE_DBG_STAMPS")) { cudaMalloc(reinterpret_cast<void**>(&h->dbg_buf), 64 * 8); cudaMemset(h->dbg_buf, 0, 64 * 8); }
   cudaGetDevice(&h->device);

@@ -34,7 +34,8 @@ struct FusedParams {
   const float* dbias;             // timestep tables of this call: [.., L, 3, 512]
   long long dbias_bstride;        // elements between consecutive items' tables (0: shared)
   const float* b2;                // [L, 256] residual half of output_projection.bias
-  unsigned int* grid_bar;         // zeroed before the launch
+  unsigned int* grid_bar;         // zeroed before the launch (lock-step kernel)
+  unsigned int* done;             // [L, units] publication counters, zeroed before the launch (denoiser_stream.cuh)
   const CUtensorMap* mW1;         // [L] in global memory: [512, 960] gate weights, box 64 x 256
   const CUtensorMap* mW2;         // [L]: [256, 256] residual weights, box 64 x 256
   const CUtensorMap* mW1p;        // [L] same tensors with box 64 x 128 (CTA-pair mode: each CTA loads half of every tile)

@@ -1,0 +1,423 @@
+// All residual layers of one DiffNet evaluation as ONE stream of (layer, unit) work items (diffnet.py:68-81 x L).
+//
+// denoiser_fused.cuh runs the layers in lock step: every CTA (pair) owns the same tiles in every layer and a grid-wide
+// barrier separates the layers.  That leaves three holes per layer: the drain (the last tile's residual epilogue with an
+// idle tensor pipe), the barrier itself, and the refill of the TMA/MMA pipeline; and with 128 units on 74 CTA pairs, 20
+// pairs idle through every second half-layer.  Here the L x units items are numbered g = l * units + unit and dealt
+// round-robin (item g belongs to pair g mod npairs), so
+//   * every pair gets ceil/floor(L * units / npairs) items instead of L * ceil(units / npairs)  (35 instead of 40 at C2),
+//   * the TMA producer, the MMA issuer and the epilogue warps each walk their item list without ever meeting at a
+//     block- or grid-wide barrier: the tensor pipe starts item k+1 (usually of the next layer) while the epilogue warps
+//     are still in the residual epilogue of item k.
+// The only cross-CTA dependency is the k=3 conv halo plus the in-place residual stream: item (l, u) reads hb_l rows of
+// units u-1, u, u+1 and h rows of unit u, all written by the residual epilogues of layer l-1.  Each epilogue warp
+// publishes its rows with  stores -> __syncwarp -> __threadfence -> atomicAdd(done[l][u])  and the producer thread of
+// a CTA acquires done[l-1][u-1 .. u+1] (== epilogue warps of the unit) followed by fence.proxy.async before it issues
+// the item's TMA loads.  Dependencies point to strictly lower g, every pair works in increasing g and all CTAs are
+// co-resident (grid <= SM count, 1 CTA/SM), so the item with the smallest unfinished g can always run: no deadlock.
+// WAR on the hb ping-pong buffers: hb_{l+2} (same buffer as hb_l) is written by item (l+1, u), which waited for
+// done[l][u-1 .. u+1], i.e. for every reader of hb_l rows of unit u.
+//
+// Per item the three tensor-core jobs, the shared-memory u tile and the two epilogues are those of denoiser_fused.cuh.
+#pragma once
+#include "denoiser_fused.cuh"
+
+namespace fse {
+
+// h rows may have been written by another SM in the previous layer: read them from L2
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ void stream_wait_done(const unsigned int* flag, unsigned int target) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+  if (v >= target) return;
+  const long long t0 = clock64();
+  do {
+    __nanosleep(40);
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (clock64() - t0 > 4000000000LL) {
+      printf("fse: layer dependency wait timed out (block %d, flag %p, target %u, seen %u)\n", blockIdx.x, flag, target, v);
+      __trap();
+    }
+  } while (v < target);
+}
+
+template <bool kPair>
+__global__ void __launch_bounds__(kTcThreads, 1)
+denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_constant__ CUtensorMap mapHb1,
+                       const __grid_constant__ CUtensorMap mapCond, FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int WB = kPair ? 128 * 128 : 256 * 128;     // bytes of one weight stage (128 or 256 rows x 64 bf16)
+  constexpr int AS = kFusedASlots;                      // 130-row activation tiles; taps = row-shifted descriptors
+  constexpr int AB = kFusedASlotBytes;
+  constexpr int WS = kPair ? 6 : kFusedWStages;
+  static_assert(AS * AB + WS * WB <= kFusedASlots * kFusedASlotBytes + kFusedWStages * kFusedWStageBytes, "smem budget");
+  constexpr uint32_t kMul = kPair ? 2u : 1u;
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + AS * AB;
+  uint8_t* sU = sW + WS * WB;
+  float* sBias = reinterpret_cast<float*>(sU + kFusedUBytes);          // [3][512] timestep tables + [256] residual bias of the layer
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sU + kFusedUBytes + kFusedBiasBytes);
+  uint64_t* a_empty = a_full + AS;
+  uint64_t* w_full = a_empty + AS;
+  uint64_t* w_empty = w_full + WS;
+  uint64_t* acc_full = w_empty + WS;              // [2]
+  uint64_t* acc_empty = acc_full + 2;             // [2]
+  uint64_t* u_full = acc_empty + 2;
+  uint64_t* u_empty = u_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_empty + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int tiles_per_item = (p.T + kTileM - 1) / kTileM;
+  const int total_tiles = p.B * tiles_per_item;
+  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  // work units: a tile (or, in pair mode, two adjacent tiles 2u, 2u+1 handled by the CTAs of a cluster)
+  const int pair0 = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int npairs = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int total_units = kPair ? (total_tiles + 1) / 2 : total_tiles;
+  const int total_items = p.L * total_units;
+  const unsigned int done_target = kEpiWarps * kMul;     // epilogue warps that publish one unit
+  const int nkbH = (p.H + 63) / 64;
+  const int ngroups = 4 + nkbH;                    // 4 hb channel blocks (3 taps each) + cond blocks (1 tap)
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&mapHb0);
+    ptx::prefetch_tensormap(&mapHb1);
+    ptx::prefetch_tensormap(&mapCond);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < AS; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+      for (int i = 0; i < WS; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kEpiWarps * kMul); }
+      ptx::mbar_init(u_full, 2 * kEpiWarps * kMul);
+      ptx::mbar_init(u_empty, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    if constexpr (kPair) { ptx::tmem_alloc_pair(tmem_slot, 512); ptx::tmem_relinquish_pair(); }
+    else { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if constexpr (kPair) ptx::cluster_sync_all();     // the peer's barriers are initialised before any remote arrive / TMA signal
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[0] = clock64();
+  constexpr int kDbgItem = 6;                       // items 6 and 7 of CTA 0 are stamped (developer aid)
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int ga = 0, kw = 0, it = 0;
+      const int nrow = kPair ? static_cast<int>(rank) * 128 : 0;       // this CTA's half of every weight tile
+      for (int g = pair0; g < total_items; g += npairs, ++it) {
+        const int l = g / total_units, unit = g - l * total_units;
+        const CUtensorMap* mHb = (l & 1) ? &mapHb1 : &mapHb0;
+        const CUtensorMap* mW1 = (kPair ? p.mW1p : p.mW1) + l;
+        const CUtensorMap* mW2 = (kPair ? p.mW2p : p.mW2) + l;
+        const int tile = kPair ? 2 * unit + static_cast<int>(rank) : unit;
+        const int b = p.b_off + tile / tiles_per_item, t0 = (tile % tiles_per_item) * kTileM;
+        if (l > 0) {
+          // layer l-1 of this unit and of its two neighbours (conv halo) has been published
+          long long* dp = (p.dbg && blockIdx.x == 0 && it >= kDbgItem && it < kDbgItem + 2) ? p.dbg + 40 + (it - kDbgItem) * 2 : nullptr;
+          if (dp) dp[0] = clock64();
+          const unsigned int* f = p.done + static_cast<size_t>(l - 1) * total_units;
+          const int u_lo = unit > 0 ? unit - 1 : 0, u_hi = unit + 1 < total_units ? unit + 1 : total_units - 1;
+          for (int u = u_lo; u <= u_hi; ++u) stream_wait_done(f + u, done_target);
+          asm volatile("fence.proxy.async;" ::: "memory");      // other CTAs' generic-proxy stores -> our TMA (async proxy) loads
+          if (dp) dp[1] = clock64();
+        }
+        for (int half = 0; half < 2; ++half) {
+          for (int grp = 0; grp < ngroups; ++grp, ++ga) {
+            const int slot = ga % AS;
+            ptx::mbar_wait(&a_empty[slot], ((ga / AS) & 1) ^ 1u);
+            // pair mode: both CTAs' loads signal the LEADER's barrier, which expects the bytes of both
+            const bool is_hb = grp < 4;
+            const uint32_t rows = is_hb ? 130u : 128u;
+            const int c0 = is_hb ? grp * 64 : (grp - 4) * 64;
+            const int tt = is_hb ? t0 - 1 : t0;
+            if (leader) ptx::mbar_arrive_expect_tx(&a_full[slot], rows * 128u * kMul);
+            if constexpr (kPair) {
+              ptx::tma_load_3d_pair(sA + slot * AB, is_hb ? mHb : &mapCond, ptx::mapa_u32(ptx::smem_u32(&a_full[slot]), 0), c0, tt, b);
+            } else {
+              ptx::tma_load_3d(sA + slot * AB, is_hb ? mHb : &mapCond, &a_full[slot], c0, tt, b);
+            }
+            const int ntap = is_hb ? 3 : 1;
+            for (int j = 0; j < ntap; ++j, ++kw) {
+              const int s = kw % WS;
+              ptx::mbar_wait(&w_empty[s], ((kw / WS) & 1) ^ 1u);
+              if (leader) ptx::mbar_arrive_expect_tx(&w_full[s], static_cast<uint32_t>(WB) * kMul);
+              const int kb = is_hb ? j * 4 + grp : 12 + (grp - 4);      // weight k-blocks are packed tap-major
+              if constexpr (kPair) ptx::tma_load_2d_pair(sW + s * WB, mW1, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * 64, half * 256 + nrow);
+              else ptx::tma_load_2d(sW + s * WB, mW1, &w_full[s], kb * 64, half * 256);
+            }
+          }
+        }
+        for (int kb = 0; kb < 4; ++kb, ++kw) {          // residual GEMM weights (its A operand is the smem copy of u)
+          const int s = kw % WS;
+          ptx::mbar_wait(&w_empty[s], ((kw / WS) & 1) ^ 1u);
+          if (leader) ptx::mbar_arrive_expect_tx(&w_full[s], static_cast<uint32_t>(WB) * kMul);
+          if constexpr (kPair) ptx::tma_load_2d_pair(sW + s * WB, mW2, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * 64, nrow);
+          else ptx::tma_load_2d(sW + s * WB, mW2, &w_full[s], kb * 64, 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(kPair ? 2 * kTileM : kTileM, 256);
+    auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+      if constexpr (kPair) ptx::mma_f16_ss_pair(d, da, db, idesc, acc); else ptx::mma_f16_ss(d, da, db, idesc, acc);
+    };
+    auto commit = [&](uint64_t* bar) {
+      if constexpr (kPair) ptx::mma_commit_pair(bar); else ptx::mma_commit(bar);
+    };
+    if (leader) {
+      int ga = 0, kw = 0, it = 0;
+      for (int g = pair0; g < total_items; g += npairs, ++it) {
+        long long* dm = (p.dbg && blockIdx.x == 0 && lane == 0 && it >= kDbgItem && it < kDbgItem + 2) ? p.dbg + 1 + (it - kDbgItem) * 8 : nullptr;
+        for (int half = 0; half < 2; ++half) {
+          const int job = 3 * it + half, buf = job & 1;
+          ptx::mbar_wait(&acc_empty[buf], ((job >> 1) & 1) ^ 1u);
+          ptx::tc_fence_after();
+          if (dm) dm[half * 2] = clock64();                 // job may start (buffer free)
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * 256);
+          uint32_t accum = 0;
+          for (int grp = 0; grp < ngroups; ++grp, ++ga) {
+            const int slot = ga % AS;
+            ptx::mbar_wait(&a_full[slot], (ga / AS) & 1);
+            const int ntap = grp < 4 ? 3 : 1;
+            for (int j = 0; j < ntap; ++j, ++kw) {
+              const int s = kw % WS;
+              ptx::mbar_wait(&w_full[s], (kw / WS) & 1);
+              ptx::tc_fence_after();
+              if (lane == 0) {
+                // hb tile holds frames t0-1 .. t0+128; tap j (offset j-1) starts at row j
+                const uint32_t a_addr = ptx::smem_u32(sA + slot * AB) + (grp < 4 ? static_cast<uint32_t>(j * 128) : 0u);
+                const uint64_t da = ptx::make_desc_k_sw128(a_addr);
+                const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sW + s * WB));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma(tmem_d, da + 2 * k, db + 2 * k, accum | (k != 0 ? 1u : 0u));
+                commit(&w_empty[s]);
+              }
+              accum = 1;
+              __syncwarp();
+            }
+            if (lane == 0) commit(&a_empty[slot]);
+            __syncwarp();
+          }
+          if (lane == 0) commit(&acc_full[buf]);
+          if (dm) dm[half * 2 + 1] = clock64();             // all MMAs of the job issued
+          __syncwarp();
+        }
+        {
+          const int job = 3 * it + 2, buf = job & 1;
+          ptx::mbar_wait(&acc_empty[buf], ((job >> 1) & 1) ^ 1u);
+          if (dm) dm[4] = clock64();
+          ptx::mbar_wait(u_full, it & 1);                 // both halves of u are in shared memory
+          ptx::tc_fence_after();
+          if (dm) dm[5] = clock64();
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * 256);
+          for (int kb = 0; kb < 4; ++kb, ++kw) {
+            const int s = kw % WS;
+            ptx::mbar_wait(&w_full[s], (kw / WS) & 1);
+            ptx::tc_fence_after();
+            if (lane == 0) {
+              const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(sU + kb * 16384));
+              const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sW + s * WB));
+#pragma unroll
+              for (int k = 0; k < 4; ++k) mma(tmem_d, da + 2 * k, db + 2 * k, (kb | k) != 0 ? 1u : 0u);
+              commit(&w_empty[s]);
+            }
+            __syncwarp();
+          }
+          if (lane == 0) {
+            commit(u_empty);
+            commit(&acc_full[buf]);
+          }
+          if (dm) dm[6] = clock64();
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half2 = ew >> 2;
+    // arrivals that the leader's MMA warp waits for: local barrier, or (pair mode) the leader's barrier through the cluster window
+    auto arrive_leader = [&](uint64_t* bar) {
+      if constexpr (kPair) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(bar), 0)); else ptx::mbar_arrive(bar);
+    };
+    int it = 0, cur_l = -1;
+    for (int g = pair0; g < total_items; g += npairs, ++it) {
+      const int l = g / total_units, unit = g - l * total_units;
+      if (l != cur_l) {
+        // Per-layer bias tables -> shared memory (with per-item tables, dbias_bstride != 0, only the residual bias is staged).
+        if (cur_l >= 0) asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // everyone is done with the old tables
+        const int e = threadIdx.x - 64;                      // 0..255
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
+        const float4* tab = reinterpret_cast<const float4*>(p.dbias + static_cast<size_t>(l) * 3 * 512);
+        if (p.dbias_bstride == 0) {                          // 384 float4: all loads in flight before the first store
+          v0 = __ldg(tab + e);
+          if (e < 128) v1 = __ldg(tab + 256 + e);
+        }
+        if (e < 64) v2 = __ldg(reinterpret_cast<const float4*>(p.b2 + static_cast<size_t>(l) * kFC) + e);
+        if (p.dbias_bstride == 0) {
+          reinterpret_cast<float4*>(sBias)[e] = v0;
+          if (e < 128) reinterpret_cast<float4*>(sBias)[256 + e] = v1;
+        }
+        if (e < 64) reinterpret_cast<float4*>(sBias + 3 * 512)[e] = v2;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        cur_l = l;
+      }
+      __nv_bfloat16* hb_out = (l & 1) ? p.hb0 : p.hb1;
+      const int tile = kPair ? 2 * unit + static_cast<int>(rank) : unit;
+      const int b = p.b_off + tile / tiles_per_item, t0 = (tile % tiles_per_item) * kTileM;
+      const int r = q * 32 + lane;                    // row inside the tile = TMEM lane
+      const int t = tile < total_tiles ? t0 + r : p.T;   // a dummy tile (odd tile count in pair mode) has no valid row
+      const bool row_ok = t < p.T;
+      const size_t row = static_cast<size_t>(b) * p.T + t;
+      const float* db = p.dbias + static_cast<size_t>(b) * p.dbias_bstride + static_cast<size_t>(l) * 3 * 512;
+      const bool e0 = t < 1, e2 = t >= p.T - 1;       // dilation 1: the taps that fell on the zero padding
+      long long* de = (p.dbg && blockIdx.x == 0 && ew == 0 && lane == 0 && it >= kDbgItem && it < kDbgItem + 2) ? p.dbg + 20 + (it - kDbgItem) * 8 : nullptr;
+      if (it > 0) ptx::mbar_wait(u_empty, (it - 1) & 1);   // the previous item's residual GEMM has finished reading u
+      for (int half = 0; half < 2; ++half) {
+        const int job = 3 * it + half, buf = job & 1;
+        ptx::mbar_wait(&acc_full[buf], (job >> 1) & 1);
+        ptx::tc_fence_after();
+        if (de) de[half * 2] = clock64();                 // accumulator ready
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * 256);
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = half2 * 4 + ci;                 // contiguous ownership: this warp writes u k-block (2*half + half2) only
+          uint32_t rr[32];
+          ptx::tmem_ld_32x32b_x32(lane_base + c * 32, rr);
+          ptx::tmem_wait_ld();
+          const int n0 = half * 256 + c * 32;           // first of 32 interleaved (gate, filter) columns
+          const bool shared_tab = p.dbias_bstride == 0;
+          const float* m = shared_tab ? sBias + n0 : db + n0;
+          float y[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 mv = shared_tab ? *(reinterpret_cast<const float4*>(m) + i) : __ldg(reinterpret_cast<const float4*>(m) + i);
+            y[4 * i] = __uint_as_float(rr[4 * i]) + mv.x; y[4 * i + 1] = __uint_as_float(rr[4 * i + 1]) + mv.y;
+            y[4 * i + 2] = __uint_as_float(rr[4 * i + 2]) + mv.z; y[4 * i + 3] = __uint_as_float(rr[4 * i + 3]) + mv.w;
+          }
+          if (e0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] -= m[512 + i];
+          }
+          if (e2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] -= m[1024 + i];
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            pk[j] = pack_bf16x2(sigmoid_f<true>(y[4 * j]) * tanh_f<true>(y[4 * j + 1]),
+                                sigmoid_f<true>(y[4 * j + 2]) * tanh_f<true>(y[4 * j + 3]));
+          // u columns [ucol, ucol+16): HBM copy for the folded skip GEMM ...
+          const int ucol = half * 128 + c * 16;
+          if (row_ok) {
+            __nv_bfloat16* up = p.u_all + row * static_cast<size_t>(p.L * kFC) + l * kFC + ucol;
+            asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(up), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+            asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(up + 8), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+          }
+          // ... and the A operand of the residual GEMM: K-major, 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
+          uint8_t* ub = sU + (ucol >> 6) * 16384 + r * 128;
+          const int ch = (ucol & 63) >> 3;               // first of the two 16-byte chunks
+          *reinterpret_cast<uint4*>(ub + (((ch) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(ub + (((ch + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          arrive_leader(&acc_empty[buf]);
+          arrive_leader(u_full);
+        }
+        if (de) de[half * 2 + 1] = clock64();             // gate epilogue of this half done
+      }
+      {
+        // residual epilogue: h <- (h + o + b) / sqrt(2), accessed TRANSPOSED through a 4 KB XOR-swizzled scratch (the rows
+        // of the u tile that only this warp writes; u is dead between the residual GEMM and the next item's gate epilogue):
+        // 8 lanes cover one 128-byte row segment, so a global load/store instruction touches 4 cache lines instead of 32.
+        const int job = 3 * it + 2, buf = job & 1;
+        float* stg = reinterpret_cast<float*>(sU + half2 * 16384 + q * 4096);
+        const int cq = lane & 7, r0 = lane >> 3;
+        const int tq = tile < total_tiles ? t0 + q * 32 + r0 : p.T;   // frame of iteration 0; iteration i adds 4*i
+        const size_t rowq = static_cast<size_t>(b) * p.T + tq;
+        float* hq = p.h + rowq * kFC + cq * 4;
+        __nv_bfloat16* hbq = hb_out + rowq * kFC + cq * 4;
+        float4 hv[8], hn[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          hv[i] = (tq + 4 * i < p.T) ? ld_cg_f4(hq + static_cast<size_t>(4 * i) * kFC + half2 * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ptx::mbar_wait(&acc_full[buf], (job >> 1) & 1);
+        ptx::tc_fence_after();
+        if (de) de[4] = clock64();
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * 256);
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = half2 * 4 + ci;                       // this warp owns columns [half2*128, half2*128+128)
+          uint32_t rr[32];
+          ptx::tmem_ld_32x32b_x32(lane_base + c * 32, rr);
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(rr[4 * j], rr[4 * j + 1], rr[4 * j + 2], rr[4 * j + 3]);
+          __syncwarp();
+          if (ci + 1 < 4) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              hn[i] = (tq + 4 * i < p.T) ? ld_cg_f4(hq + static_cast<size_t>(4 * i) * kFC + (c + 1) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          const float4 bv = *reinterpret_cast<const float4*>(sBias + 3 * 512 + c * 32 + cq * 4);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rloc = 4 * i + r0;
+            const float4 a = *reinterpret_cast<const float4*>(stg + rloc * 32 + ((cq ^ (rloc & 7)) << 2));
+            if (tq + 4 * i < p.T) {
+              float v[4];
+              v[0] = (hv[i].x + (a.x + bv.x)) * 0.70710678118654752440f;
+              v[1] = (hv[i].y + (a.y + bv.y)) * 0.70710678118654752440f;
+              v[2] = (hv[i].z + (a.z + bv.z)) * 0.70710678118654752440f;
+              v[3] = (hv[i].w + (a.w + bv.w)) * 0.70710678118654752440f;
+              st_vec<4>(hq + static_cast<size_t>(4 * i) * kFC + c * 32, v);
+              st_vec<4>(hbq + static_cast<size_t>(4 * i) * kFC + c * 32, v);
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) hv[i] = hn[i];
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          arrive_leader(&acc_empty[buf]);
+          // publish this warp's h / hb rows of (l, unit) to the consumers of layer l+1 (see the header)
+          __threadfence();
+          atomicAdd(p.done + static_cast<size_t>(l) * total_units + unit, 1u);
+        }
+        if (de) de[5] = clock64();
+      }
+    }
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  __syncthreads();
+  if constexpr (kPair) ptx::cluster_sync_all();     // the peer may still be reading our smem / signalling our barriers
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    if constexpr (kPair) ptx::tmem_dealloc_pair(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace fse

@@ -45,11 +45,12 @@ __device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t step, uin
   const float u1 = (static_cast<float>(r[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
   const float u2 = (static_cast<float>(r[2] >> 8) + 0.5f) * (1.0f / 16777216.0f);
   const float u3 = (static_cast<float>(r[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-  const float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+  // fast intrinsics: the uniforms are 24-bit, so |log| and the phase are well inside the accurate range of the SFU paths
+  const float ra = sqrtf(-2.0f * __logf(u0)), rb = sqrtf(-2.0f * __logf(u2));
   float s, c;
-  sincosf(6.283185307179586f * u1, &s, &c);
+  __sincosf(6.283185307179586f * u1, &s, &c);
   z[0] = ra * c; z[1] = ra * s;
-  sincosf(6.283185307179586f * u3, &s, &c);
+  __sincosf(6.283185307179586f * u3, &s, &c);
   z[2] = rb * c; z[3] = rb * s;
 }
 
