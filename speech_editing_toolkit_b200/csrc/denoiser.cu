@@ -505,7 +505,7 @@ int sample_impl(fse_denoiser* h, const float* cond, const float* noise, uint64_t
       const long long* m = d + 1 + tl * 8; const long long* e = d + 20 + tl * 8;
       fprintf(stderr, "  tile%d MMA: G1a %lld..%lld G1b %lld..%lld G2 buf_free=%lld u_ready=%lld issued=%lld | EPI(w2): e1a %lld..%lld e1b %lld..%lld e2 %lld..%lld\n",
               tl, m[0] - t0, m[1] - t0, m[2] - t0, m[3] - t0, m[4] - t0, m[5] - t0, m[6] - t0, e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0, e[5] - t0);
-      if (stream) fprintf(stderr, "        producer: dependency wait %lld..%lld\n", d[40 + 2 * tl] - t0, d[41 + 2 * tl] - t0);
+      if (stream) fprintf(stderr, "        producer: dependency wait %lld..%lld | e2 released its TMEM buffer at %lld\n", d[40 + 2 * tl] - t0, d[41 + 2 * tl] - t0, e[6] - t0);
     }
     if (!stream) fprintf(stderr, "  layer3 end: syncthreads passed=%lld grid barrier passed=%lld\n", d[40] - t0, d[41] - t0);
   } else if (h->dbg_buf) {

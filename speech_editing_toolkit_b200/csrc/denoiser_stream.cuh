@@ -348,26 +348,27 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
         if (de) de[half * 2 + 1] = clock64();             // gate epilogue of this half done
       }
       {
-        // residual epilogue: h <- (h + o + b) / sqrt(2), accessed TRANSPOSED through a 4 KB XOR-swizzled scratch (the rows
-        // of the u tile that only this warp writes; u is dead between the residual GEMM and the next item's gate epilogue):
+        // residual epilogue: h <- (h + o + b) / sqrt(2), accessed TRANSPOSED through 4 KB XOR-swizzled scratches (rows of
+        // the u tile that only this warp writes; u is dead between the residual GEMM and the next item's gate epilogue):
         // 8 lanes cover one 128-byte row segment, so a global load/store instruction touches 4 cache lines instead of 32.
+        // Two scratches (this warp's rows of u k-blocks half2 and 2 + half2) let the accumulator leave TMEM two chunks
+        // ahead of the global traffic: the buffer goes back to the MMA warp after ~40 % of this epilogue (the next item's
+        // second gate job was waiting for exactly that).
         const int job = 3 * it + 2, buf = job & 1;
-        float* stg = reinterpret_cast<float*>(sU + half2 * 16384 + q * 4096);
+        float* stgA = reinterpret_cast<float*>(sU + half2 * 16384 + q * 4096);
+        float* stgB = reinterpret_cast<float*>(sU + (2 + half2) * 16384 + q * 4096);
         const int cq = lane & 7, r0 = lane >> 3;
         const int tq = tile < total_tiles ? t0 + q * 32 + r0 : p.T;   // frame of iteration 0; iteration i adds 4*i
         const size_t rowq = static_cast<size_t>(b) * p.T + tq;
         float* hq = p.h + rowq * kFC + cq * 4;
         __nv_bfloat16* hbq = hb_out + rowq * kFC + cq * 4;
-        float4 hv[8], hn[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          hv[i] = (tq + 4 * i < p.T) ? ld_cg_f4(hq + static_cast<size_t>(4 * i) * kFC + half2 * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
-        ptx::mbar_wait(&acc_full[buf], (job >> 1) & 1);
-        ptx::tc_fence_after();
-        if (de) de[4] = clock64();
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * 256);
-        for (int ci = 0; ci < 4; ++ci) {
-          const int c = half2 * 4 + ci;                       // this warp owns columns [half2*128, half2*128+128)
+        auto load_h = [&](int c, float4 (&hx)[8]) {                 // this lane's part of residual-stream chunk c
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            hx[i] = (tq + 4 * i < p.T) ? ld_cg_f4(hq + static_cast<size_t>(4 * i) * kFC + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        auto stage = [&](int c, float* stg) {                       // accumulator chunk c: TMEM -> registers -> scratch
           uint32_t rr[32];
           ptx::tmem_ld_32x32b_x32(lane_base + c * 32, rr);
           ptx::tmem_wait_ld();
@@ -375,11 +376,8 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(rr[4 * j], rr[4 * j + 1], rr[4 * j + 2], rr[4 * j + 3]);
           __syncwarp();
-          if (ci + 1 < 4) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              hn[i] = (tq + 4 * i < p.T) ? ld_cg_f4(hq + static_cast<size_t>(4 * i) * kFC + (c + 1) * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+        };
+        auto finish = [&](int c, const float* stg, const float4 (&hx)[8]) {
           const float4 bv = *reinterpret_cast<const float4*>(sBias + 3 * 512 + c * 32 + cq * 4);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -387,22 +385,38 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
             const float4 a = *reinterpret_cast<const float4*>(stg + rloc * 32 + ((cq ^ (rloc & 7)) << 2));
             if (tq + 4 * i < p.T) {
               float v[4];
-              v[0] = (hv[i].x + (a.x + bv.x)) * 0.70710678118654752440f;
-              v[1] = (hv[i].y + (a.y + bv.y)) * 0.70710678118654752440f;
-              v[2] = (hv[i].z + (a.z + bv.z)) * 0.70710678118654752440f;
-              v[3] = (hv[i].w + (a.w + bv.w)) * 0.70710678118654752440f;
+              v[0] = (hx[i].x + (a.x + bv.x)) * 0.70710678118654752440f;
+              v[1] = (hx[i].y + (a.y + bv.y)) * 0.70710678118654752440f;
+              v[2] = (hx[i].z + (a.z + bv.z)) * 0.70710678118654752440f;
+              v[3] = (hx[i].w + (a.w + bv.w)) * 0.70710678118654752440f;
               st_vec<4>(hq + static_cast<size_t>(4 * i) * kFC + c * 32, v);
               st_vec<4>(hbq + static_cast<size_t>(4 * i) * kFC + c * 32, v);
             }
           }
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) hv[i] = hn[i];
-        }
+          __syncwarp();                                             // all lanes have read the scratch
+        };
+        const int cb = half2 * 4;                                   // this warp owns columns [half2*128, half2*128+128)
+        float4 hv[8], hn[8];
+        load_h(cb, hv);
+        ptx::mbar_wait(&acc_full[buf], (job >> 1) & 1);
+        ptx::tc_fence_after();
+        if (de) de[4] = clock64();
+        stage(cb, stgA);
+        stage(cb + 1, stgB);
+        load_h(cb + 1, hn);
+        finish(cb, stgA, hv);
+        stage(cb + 2, stgA);
+        load_h(cb + 2, hv);
+        finish(cb + 1, stgB, hn);
+        stage(cb + 3, stgB);
         ptx::tc_fence_before();
         __syncwarp();
+        if (lane == 0) arrive_leader(&acc_empty[buf]);              // accumulator drained: early release
+        if (de) de[6] = clock64();
+        load_h(cb + 3, hn);
+        finish(cb + 2, stgA, hv);
+        finish(cb + 3, stgB, hn);
         if (lane == 0) {
-          arrive_leader(&acc_empty[buf]);
           // publish this warp's h / hb rows of (l, unit) to the consumers of layer l+1 (see the header)
           __threadfence();
           atomicAdd(p.done + static_cast<size_t>(l) * total_units + unit, 1u);
