@@ -349,7 +349,7 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
         const int max_grid = h->num_sms / 2 * 2;
         if (grid > max_grid) grid = max_grid;
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kFusedSmemBytes; cfg.stream = st;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(stream ? kStreamThreads : kTcThreads); cfg.dynamicSmemBytes = kFusedSmemBytes; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -361,7 +361,7 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
         else
           FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_layers_kernel<true, false>, h->plan.m_hb, h->plan.m_hb1, h->plan.m_cond, fp));
       } else if (stream) {
-        denoiser_stream_kernel<false><<<tiles < h->num_sms ? tiles : h->num_sms, kTcThreads, kFusedSmemBytes, st>>>(
+        denoiser_stream_kernel<false><<<tiles < h->num_sms ? tiles : h->num_sms, kStreamThreads, kFusedSmemBytes, st>>>(
             h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp);
       } else {
         denoiser_layers_kernel<false, true><<<tiles < h->num_sms ? tiles : h->num_sms, kTcThreads, kFusedSmemBytes, st>>>(

@@ -10,10 +10,10 @@
 //     block- or grid-wide barrier: the tensor pipe starts item k+1 (usually of the next layer) while the epilogue warps
 //     are still in the residual epilogue of item k.
 // The only cross-CTA dependency is the k=3 conv halo plus the in-place residual stream: item (l, u) reads hb_l rows of
-// units u-1, u, u+1 and h rows of unit u, all written by the residual epilogues of layer l-1.  Each epilogue warp
-// publishes its rows with  stores -> __syncwarp -> __threadfence -> atomicAdd(done[l][u])  and the producer thread of
-// a CTA acquires done[l-1][u-1 .. u+1] (== epilogue warps of the unit) followed by fence.proxy.async before it issues
-// the item's TMA loads.  Dependencies point to strictly lower g, every pair works in increasing g and all CTAs are
+// units u-1, u, u+1 and h rows of unit u, all written by the residual epilogues of layer l-1.  A CTA publishes its rows
+// with  stores -> mbarrier (all epilogue warps) -> publisher thread: __threadfence -> atomicAdd(done[l][u])  and the
+// producer thread of a CTA acquires done[l-1][u-1 .. u+1] (== epilogue warps of the unit) followed by
+// fence.proxy.async before it issues the item's TMA loads.  Dependencies point to strictly lower g, every pair works in increasing g and all CTAs are
 // co-resident (grid <= SM count, 1 CTA/SM), so the item with the smallest unfinished g can always run: no deadlock.
 // WAR on the hb ping-pong buffers: hb_{l+2} (same buffer as hb_l) is written by item (l+1, u), which waited for
 // done[l][u-1 .. u+1], i.e. for every reader of hb_l rows of unit u.
@@ -46,8 +46,10 @@ __device__ __forceinline__ void stream_wait_done(const unsigned int* flag, unsig
   } while (v < target);
 }
 
+constexpr int kStreamThreads = kTcThreads + 32;     // + the publisher warp
+
 template <bool kPair>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kStreamThreads, 1)
 denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_constant__ CUtensorMap mapHb1,
                        const __grid_constant__ CUtensorMap mapCond, FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -70,7 +72,8 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
   uint64_t* acc_empty = acc_full + 2;             // [2]
   uint64_t* u_full = acc_empty + 2;
   uint64_t* u_empty = u_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(u_empty + 1);
+  uint64_t* pub_bar = u_empty + 1;                // this CTA's epilogue warps have stored their h / hb rows of the item
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pub_bar + 1);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -83,7 +86,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
   const int npairs = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int total_units = kPair ? (total_tiles + 1) / 2 : total_tiles;
   const int total_items = p.L * total_units;
-  const unsigned int done_target = kEpiWarps * kMul;     // epilogue warps that publish one unit
+  const unsigned int done_target = kEpiWarps * kMul;     // epilogue warps that store one unit
   const int nkbH = (p.H + 63) / 64;
   const int ngroups = 4 + nkbH;                    // 4 hb channel blocks (3 taps each) + cond blocks (1 tap)
 
@@ -99,6 +102,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
       for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kEpiWarps * kMul); }
       ptx::mbar_init(u_full, 2 * kEpiWarps * kMul);
       ptx::mbar_init(u_empty, 1);
+      ptx::mbar_init(pub_bar, kEpiWarps);
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -249,6 +253,22 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
         }
       }
     }
+  } else if (warp == 2 + kEpiWarps) {
+    // ---------------------------------------------------------------- publisher
+    // The gpu-scope fence that publishes an item's h / hb rows waits until the stores have reached L2 (~2 k cycles under
+    // load).  The epilogue warps only arrive on a CTA-scope mbarrier; this otherwise idle thread takes the wait:
+    //   epilogue stores -> mbarrier.arrive (release.cta)  =>  try_wait (acquire.cta) -> fence.acq_rel.gpu -> atomicAdd
+    // (the cumulativity pattern of a grid sync: bar.sync, then ONE thread fences and signals for the whole CTA).
+    // The consumers need the flag ~1.7 item periods later, and an item lasts >10x the fence, so the parity wait cannot lap.
+    if (lane == 0) {
+      int it = 0;
+      for (int g = pair0; g < total_items; g += npairs, ++it) {
+        ptx::mbar_wait(pub_bar, it & 1);
+        __threadfence();
+        atomicAdd(p.done + g, static_cast<unsigned int>(kEpiWarps));     // g == l * total_units + unit
+      }
+    }
+    __syncwarp();
   } else {
     // ---------------------------------------------------------------- epilogue warps
     const int ew = warp - 2;
@@ -297,11 +317,12 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
         ptx::tc_fence_after();
         if (de) de[half * 2] = clock64();                 // accumulator ready
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * 256);
-        for (int ci = 0; ci < 4; ++ci) {
+        // accumulator chunks are fetched one ahead: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+        uint32_t ra[32], rb[32];
+        ptx::tmem_ld_32x32b_x32(lane_base + half2 * 128, ra);
+        ptx::tmem_wait_ld();
+        auto gate_chunk = [&](int ci, const uint32_t (&rr)[32]) {
           const int c = half2 * 4 + ci;                 // contiguous ownership: this warp writes u k-block (2*half + half2) only
-          uint32_t rr[32];
-          ptx::tmem_ld_32x32b_x32(lane_base + c * 32, rr);
-          ptx::tmem_wait_ld();
           const int n0 = half * 256 + c * 32;           // first of 32 interleaved (gate, filter) columns
           const bool shared_tab = p.dbias_bstride == 0;
           const float* m = shared_tab ? sBias + n0 : db + n0;
@@ -337,7 +358,17 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           const int ch = (ucol & 63) >> 3;               // first of the two 16-byte chunks
           *reinterpret_cast<uint4*>(ub + (((ch) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           *reinterpret_cast<uint4*>(ub + (((ch + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
+        };
+        ptx::tmem_ld_32x32b_x32(lane_base + half2 * 128 + 32, rb);
+        gate_chunk(0, ra);
+        ptx::tmem_wait_ld();
+        ptx::tmem_ld_32x32b_x32(lane_base + half2 * 128 + 64, ra);
+        gate_chunk(1, rb);
+        ptx::tmem_wait_ld();
+        ptx::tmem_ld_32x32b_x32(lane_base + half2 * 128 + 96, rb);
+        gate_chunk(2, ra);
+        ptx::tmem_wait_ld();
+        gate_chunk(3, rb);
         ptx::tc_fence_before();
         ptx::fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
@@ -396,31 +427,29 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           __syncwarp();                                             // all lanes have read the scratch
         };
         const int cb = half2 * 4;                                   // this warp owns columns [half2*128, half2*128+128)
-        float4 hv[8], hn[8];
-        load_h(cb, hv);
+        // The residual-stream loads are what this epilogue waits for (L2 latency under the weight traffic): three register
+        // sets keep two chunks in flight, and the first two are issued before the wait for the residual GEMM.
+        float4 h0[8], h1[8], h2[8];
+        load_h(cb, h0);
+        load_h(cb + 1, h1);
         ptx::mbar_wait(&acc_full[buf], (job >> 1) & 1);
         ptx::tc_fence_after();
         if (de) de[4] = clock64();
         stage(cb, stgA);
         stage(cb + 1, stgB);
-        load_h(cb + 1, hn);
-        finish(cb, stgA, hv);
+        load_h(cb + 2, h2);
+        finish(cb, stgA, h0);
         stage(cb + 2, stgA);
-        load_h(cb + 2, hv);
-        finish(cb + 1, stgB, hn);
+        load_h(cb + 3, h0);
+        finish(cb + 1, stgB, h1);
         stage(cb + 3, stgB);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_leader(&acc_empty[buf]);              // accumulator drained: early release
         if (de) de[6] = clock64();
-        load_h(cb + 3, hn);
-        finish(cb + 2, stgA, hv);
-        finish(cb + 3, stgB, hn);
-        if (lane == 0) {
-          // publish this warp's h / hb rows of (l, unit) to the consumers of layer l+1 (see the header)
-          __threadfence();
-          atomicAdd(p.done + static_cast<size_t>(l) * total_units + unit, 1u);
-        }
+        finish(cb + 2, stgA, h2);
+        finish(cb + 3, stgB, h0);
+        if (lane == 0) ptx::mbar_arrive(pub_bar);                   // (finish ends with __syncwarp) -> publisher warp
         if (de) de[5] = clock64();
       }
     }
