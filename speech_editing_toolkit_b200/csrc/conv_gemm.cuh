@@ -14,6 +14,7 @@
 //   * conv_gemm_simt_kernel — plain CUDA-core tiled GEMM over fp32 or bf16 operands; the exact-fp32
 //     mode of the library and the on-device cross-check of the tensor-core path.
 #pragma once
+#include <type_traits>
 #include <cuda_bf16.h>
 
 #include "ptx_sm100.cuh"
@@ -37,12 +38,14 @@ struct ConvGemmParams {
   int nkb1;    // k-blocks for source 1
   int N;       // output columns
   int Kp;      // padded K of the packed weight = (ntaps*nkb0 + nkb1)*KB
-  int MT;        // 128-frame sub-tiles per job (non-shared schedule): one weight tile feeds MT activation tiles and the
-                 //    accumulator buffer holds MT x BN columns - amortises the per-job handshakes when BN is small
-  int shared_a;  // 1: load each channel block of source 0 ONCE per tile (Rrows = 128 + tap span rows) and feed every tap
-                 //    from row-shifted UMMA descriptors of that one smem copy (cuts activation ingest by ntaps)
-  int off_min;   // smallest tap offset; Rrows = 128 + max(off) - min(off)
+  int MT;        // 128-frame sub-tiles per job: one weight tile feeds MT activation tiles and the accumulator buffer
+                 //    holds MT x BN columns - amortises the per-job handshakes and the weight reloads when BN is small
+  int shared_a;  // 1: load each channel block of source 0 ONCE per job (Rrows = 128*MT + tap span rows) and feed every
+                 //    (tap, sub-tile) from row-shifted UMMA descriptors of that one smem copy (activation ingest / ntaps)
+  int off_min;   // smallest tap offset; Rrows = 128*MT + max(off) - min(off)
   int Rrows;
+  int Rbox;      // shared-A: the job's rows arrive as nload TMA boxes of Rbox rows (<= 256, multiple of 8) laid end to end
+  int nload;
   int bo_mode;   // descriptor base-offset convention for row-shifted starts (test hook; 1 = (addr>>7)&7)
   long long* dbg;  // optional [32] clock64 phase stamps of CTA 0 (test hook), else null
 };
@@ -179,10 +182,19 @@ constexpr int kEpiWarps = 8;
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr int kTileM = 128;       // frames per tile = TMEM lanes
 
+// Epilogue functors that set `static constexpr bool kTransposed = true` are run through a per-warp shared-memory
+// transposition (conv_gemm_tc_kernel, CH == 32): 8 lanes cover 32 consecutive channels of one frame, so every global
+// load / store instruction touches 4 row segments of 64-128 contiguous bytes instead of 32 rows x 16 bytes.
+template <class E, class = void>
+struct epi_transposed : std::false_type {};
+template <class E>
+struct epi_transposed<E, std::void_t<decltype(E::kTransposed)>> : std::bool_constant<E::kTransposed> {};
+constexpr int kEpiScratchBytes = 8 * 32 * 32 * 4;     // kEpiWarps x [32 frames][32 fp32]
+
 __host__ __device__ inline int tc_b_stage_bytes(int BN, int KB) { return ((BN * KB * 2 + 1023) / 1024) * 1024; }
 __host__ __device__ inline int tc_a_stage_bytes(int KB) { return kTileM * KB * 2; }
-__host__ inline size_t tc_smem_bytes(int BN, int KB, int stages, int a_slots, int a_slot_bytes) {
-  return 1024 + static_cast<size_t>(a_slots) * a_slot_bytes + static_cast<size_t>(stages) * tc_b_stage_bytes(BN, KB) +
+__host__ inline size_t tc_smem_bytes(int BN, int KB, int stages, int a_slots, int a_slot_bytes, int scratch_bytes = 0) {
+  return 1024 + static_cast<size_t>(a_slots) * a_slot_bytes + static_cast<size_t>(stages) * tc_b_stage_bytes(BN, KB) + scratch_bytes +
          8 * (2 * stages + 4 + 2 * a_slots) + 16;
 }
 
@@ -190,7 +202,7 @@ template <int KB, int CH, class Epi>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapW, ConvGemmParams p, int BN, int stages, int a_slots,
-                    int a_slot_bytes, Epi epi) {
+                    int a_slot_bytes, int scratch_bytes, Epi epi) {
   static_assert(KB == 64 || KB == 32, "k-block");
   static_assert(CH == 32 || CH == 16, "epilogue chunk");
   extern __shared__ uint8_t smem_raw[];
@@ -199,7 +211,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   const int B_BYTES = tc_b_stage_bytes(BN, KB);
   uint8_t* sA = smem;
   uint8_t* sB = smem + a_slots * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + stages * B_BYTES);
+  uint8_t* sScratch = sB + stages * B_BYTES;       // transposed epilogue: [kEpiWarps][32][32] fp32
+  uint64_t* full = reinterpret_cast<uint64_t*>(sScratch + scratch_bytes);
   uint64_t* empty = full + stages;
   uint64_t* acc_full = empty + stages;     // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2]
@@ -211,7 +224,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   const int lane = threadIdx.x & 31;
   long long* dbg = (p.dbg && blockIdx.x == 0) ? p.dbg : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
-  const int MT = p.shared_a ? 1 : (p.MT > 0 ? p.MT : 1);
+  const int MT = p.MT > 0 ? p.MT : 1;
   const int tile_rows = kTileM * MT;
   const int tiles_per_item = (p.Trows + tile_rows - 1) / tile_rows;
   const int n_tiles = p.N / BN;
@@ -268,9 +281,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           const int slot = ga % a_slots;
           ptx::mbar_wait(&a_empty[slot], ((ga / a_slots) & 1) ^ 1u);
           const bool src0 = g < p.nkb0;
-          ptx::mbar_arrive_expect_tx(&a_full[slot], static_cast<uint32_t>((src0 ? p.Rrows : kTileM) * KB * 2));
-          if (src0) ptx::tma_load_3d(sA + slot * A_BYTES, &mapA0, &a_full[slot], p.c_off0 + g * KB, t0 + p.off_min, b);
-          else ptx::tma_load_3d(sA + slot * A_BYTES, &mapA1, &a_full[slot], (g - p.nkb0) * KB, t0, b);
+          const int box_bytes = p.Rbox * KB * 2;
+          ptx::mbar_arrive_expect_tx(&a_full[slot], static_cast<uint32_t>(src0 ? p.nload * box_bytes : kTileM * KB * 2));
+          if (src0) {
+            for (int i = 0; i < p.nload; ++i)
+              ptx::tma_load_3d(sA + slot * A_BYTES + i * box_bytes, &mapA0, &a_full[slot], p.c_off0 + g * KB, t0 + p.off_min + i * p.Rbox, b);
+          } else {
+            ptx::tma_load_3d(sA + slot * A_BYTES, &mapA1, &a_full[slot], (g - p.nkb0) * KB, t0, b);   // source 1: MT == 1 only
+          }
           const int ntap = src0 ? p.ntaps : 1;
           for (int j = 0; j < ntap; ++j, ++kbg) {
             const int s = kbg % stages;
@@ -312,6 +330,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     const uint32_t idesc = ptx::make_idesc_bf16_f32(kTileM, BN);
+    const bool el = ptx::elect_one();      // the one lane that issues every tcgen05.mma / commit of this CTA
     int kbg = 0, it = 0, ga = 0;
     if (p.shared_a) {
       const int ngroups = p.nkb0 + p.nkb1;
@@ -319,7 +338,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         const int buf = it & 1;
         ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * BN);
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * MT * BN);
         uint32_t accum = 0;
         for (int g = 0; g < ngroups; ++g, ++ga) {
           const int slot = ga % a_slots;
@@ -331,23 +350,30 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             ptx::mbar_wait(&full[s], (kbg / stages) & 1);
             ptx::tc_fence_after();
             if (dbg && lane == 0 && kbg == 0) dbg[3] = clock64();
-            if (lane == 0) {
-              // row-shifted view of the one smem copy: tap j reads rows [shift, shift+128) of the Rrows-row tile
+            {
+              // row-shifted views of the one smem copy: (tap j, sub-tile mt) reads rows [mt*128 + shift, +128) of the job's rows.
+              // Descriptors are computed by the whole warp (convergent code -> uniform registers); only the tcgen05
+              // instructions sit under the one-lane predicate (a divergent region would cost ~7 R2UR + a waterfall per MMA).
               const int shift = src0 ? p.tap_off[j] - p.off_min : 0;
-              const uint32_t a_addr = ptx::smem_u32(sA + slot * A_BYTES) + static_cast<uint32_t>(shift * KB * 2);
               const uint32_t b_addr = ptx::smem_u32(sB + s * B_BYTES);
-              const uint32_t bo = p.bo_mode ? ((a_addr >> 7) & (KB == 64 ? 7u : 3u)) : 0u;
-              const uint64_t da = ((KB == 64) ? ptx::make_desc_k_sw128(a_addr) : ptx::make_desc_k_sw64(a_addr)) |
-                                  (static_cast<uint64_t>(bo) << 49);
               const uint64_t db = (KB == 64) ? ptx::make_desc_k_sw128(b_addr) : ptx::make_desc_k_sw64(b_addr);
+              const uint32_t a_base = ptx::smem_u32(sA + slot * A_BYTES) + static_cast<uint32_t>(shift * KB * 2);
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t a_addr = a_base + static_cast<uint32_t>(mt * kTileM * KB * 2);
+                const uint32_t bo = p.bo_mode ? ((a_addr >> 7) & (KB == 64 ? 7u : 3u)) : 0u;
+                const uint64_t da = ((KB == 64) ? ptx::make_desc_k_sw128(a_addr) : ptx::make_desc_k_sw64(a_addr)) |
+                                    (static_cast<uint64_t>(bo) << 49);
+                const uint32_t td = tmem_d + static_cast<uint32_t>(mt * BN);
 #pragma unroll
-              for (int k = 0; k < KB / 16; ++k) ptx::mma_f16_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, accum | (k != 0 ? 1u : 0u));
-              ptx::mma_commit(&empty[s]);
+                for (int k = 0; k < KB / 16; ++k)
+                  if (el) ptx::mma_f16_ss(td, da + 2 * k, db + 2 * k, idesc, accum | (k != 0 ? 1u : 0u));
+              }
+              if (el) ptx::mma_commit(&empty[s]);
             }
             accum = 1;
             __syncwarp();
           }
-          if (lane == 0) {
+          if (el) {
             ptx::mma_commit(&a_empty[slot]);
             if (g == ngroups - 1) {
               ptx::mma_commit(&acc_full[buf]);
@@ -369,19 +395,24 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         ptx::mbar_wait(&full[s], ph);
         ptx::tc_fence_after();
         if (dbg && lane == 0 && kbg == 0) dbg[3] = clock64();   // first k-block landed
-        if (lane == 0) {
+        {
           const uint32_t b_addr = ptx::smem_u32(sB + s * B_BYTES);
           const uint64_t db = (KB == 64) ? ptx::make_desc_k_sw128(b_addr) : ptx::make_desc_k_sw64(b_addr);
+          const uint32_t a_base = ptx::smem_u32(sA + s * A_BYTES);
+          const uint32_t acc = kb != 0 ? 1u : 0u;
           for (int mt = 0; mt < MT; ++mt) {          // the same weight tile against MT activation sub-tiles
-            const uint32_t a_addr = ptx::smem_u32(sA + s * A_BYTES + mt * (kTileM * KB * 2));
+            const uint32_t a_addr = a_base + static_cast<uint32_t>(mt * (kTileM * KB * 2));
             const uint64_t da = (KB == 64) ? ptx::make_desc_k_sw128(a_addr) : ptx::make_desc_k_sw64(a_addr);
+            const uint32_t td = tmem_d + static_cast<uint32_t>(mt * BN);
 #pragma unroll
             for (int k = 0; k < KB / 16; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the addr>>4 field
-              ptx::mma_f16_ss(tmem_d + static_cast<uint32_t>(mt * BN), da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (el) ptx::mma_f16_ss(td, da + 2 * k, db + 2 * k, idesc, k != 0 ? 1u : acc);
           }
-          ptx::mma_commit(&empty[s]);
-          if (kb == nkb - 1) ptx::mma_commit(&acc_full[buf]);
-          if (dbg && kb == nkb - 1 && it == 0) dbg[4] = clock64();   // all MMAs of the first tile issued
+          if (el) {
+            ptx::mma_commit(&empty[s]);
+            if (kb == nkb - 1) ptx::mma_commit(&acc_full[buf]);
+            if (dbg && kb == nkb - 1 && it == 0) dbg[4] = clock64();   // all MMAs of the first tile issued
+          }
         }
         __syncwarp();
       }
@@ -397,6 +428,73 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     const int half = ew >> 2;               // two warps share a quarter and split the column chunks
     const int cpb = BN / CH;                 // chunks per 128-frame sub-tile
     const int nchunks = MT * cpb;
+    if constexpr (CH == 32 && epi_transposed<Epi>::value) {
+      // ---- transposed epilogue: accumulator chunk -> registers -> XOR-swizzled scratch -> lanes re-assigned so that 8 lanes
+      // cover the 32 channels of one frame (4 channels each) and a warp instruction covers 4 frames.  Residual operands of
+      // the NEXT chunk are requested while the current one is processed (first chunk: before the accumulator is awaited).
+      float* stg = reinterpret_cast<float*>(sScratch) + ew * 1024;
+      const int cq = lane & 7, r0 = lane >> 3;
+      constexpr int AX = Epi::kAux > 0 ? 4 * Epi::kAux : 1;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int m = tile / n_tiles, n0 = (tile % n_tiles) * BN;
+        const int b = p.b_off + m / tiles_per_item, t0 = (m % tiles_per_item) * tile_rows;
+        const int tq = t0 + q * 32 + r0;          // frame of iteration 0 in sub-tile 0; iteration i adds 4*i, sub-tile st adds 128*st
+        auto T_OF = [&](int c, int i) { return tq + (c / cpb) * kTileM + 4 * i; };
+        auto N_OF = [&](int c) { return n0 + (c % cpb) * CH + cq * 4; };
+        const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * MT * BN);
+        float aux[8][AX], aux_next[8][AX];
+        if constexpr (Epi::kAux > 0) {
+          if (half < nchunks) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (T_OF(half, i) < p.Trows) epi.template load_aux<4>(b, T_OF(half, i), N_OF(half), aux[i]);
+          }
+        }
+        ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+        ptx::tc_fence_after();
+        if (dbg && ew == 0 && lane == 0 && it == 0) dbg[5] = clock64();   // first accumulator complete
+        for (int c = half; c < nchunks; c += 2) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(lane_base + c * CH, r);
+          ptx::tmem_wait_ld();
+          if constexpr (Epi::kAux > 0) {
+            if (c + 2 < nchunks) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (T_OF(c + 2, i) < p.Trows) epi.template load_aux<4>(b, T_OF(c + 2, i), N_OF(c + 2), aux_next[i]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          __syncwarp();
+          const int nn = N_OF(c);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rloc = 4 * i + r0;
+            const float4 a = *reinterpret_cast<const float4*>(stg + rloc * 32 + ((cq ^ (rloc & 7)) << 2));
+            const int t = T_OF(c, i);
+            if (t < p.Trows) {
+              const float v[4] = {a.x, a.y, a.z, a.w};
+              epi.template apply<4>(b, t, nn, v, aux[i]);
+            }
+          }
+          __syncwarp();                                 // all lanes have read the scratch before the next chunk overwrites it
+          if constexpr (Epi::kAux > 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+              for (int j = 0; j < AX; ++j) aux[i][j] = aux_next[i][j];
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+        if (dbg && lane == 0 && it == 0) dbg[6 + ew] = clock64();           // epilogue warp ew done with the first tile
+      }
+    } else {
     constexpr int AUXN = CH * (Epi::kAux > 0 ? Epi::kAux : 1);
     // Residual operands: when a warp owns at most kMaxPre chunks of a tile and they fit in 64 registers, ALL of
     // them are requested before the accumulator is awaited (one exposed memory latency per tile); otherwise the
@@ -476,6 +574,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
       if (dbg && lane == 0 && it == 0) dbg[6 + ew] = clock64();           // epilogue warp ew done with the first tile
+    }
     }
   }
   __syncthreads();

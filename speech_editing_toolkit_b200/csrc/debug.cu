@@ -5,6 +5,7 @@
 namespace fse {
 struct EpiStore {
   static constexpr int kAux = 0;
+  static constexpr bool kTransposed = true;
   float* out;
   int N, T;
   template <int NV>
@@ -31,10 +32,15 @@ extern "C" int fse_debug_conv_gemm(int32_t mode, const void* A0, const void* W, 
   CUtensorMap mA{}, mW{};
   if (mode == FSE_MODE_TC_BF16) {
     int rows = kTileM;
-    if (shared_a) {
-      if (!enable_shared_a(p)) return fail(FSE_EINVAL, "shared-A schedule needs >= 2 taps and a span <= 128 rows");
-      p.bo_mode = shared_a == 2 ? 1 : 0;
-      rows = p.Rrows;
+    // shared_a = schedule + 16 * (MT - 1): MT 128-frame sub-tiles per job; schedule 0 = one A load per tap, 1 = shared-A,
+    // 2 = shared-A with the descriptor base-offset set (known wrong, kept as a probe)
+    const int mt = 1 + (shared_a >> 4), sched = shared_a & 15;
+    if (sched) {
+      if (!enable_shared_a(p, mt)) return fail(FSE_EINVAL, "shared-A schedule needs >= 2 taps and a job that fits shared memory");
+      p.bo_mode = sched == 2 ? 1 : 0;
+      rows = p.Rbox;
+    } else {
+      p.MT = mt;
     }
     FSE_TRY(make_map_act(&mA, A0, C0, T, B, KB, rows));
     FSE_TRY(make_map_w(&mW, W, p.Kp, N, KB, BN));

@@ -186,6 +186,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
       if constexpr (kPair) ptx::mma_commit_pair(bar); else ptx::mma_commit(bar);
     };
     if (leader) {
+      const bool el = ptx::elect_one();      // the one lane that issues every tcgen05.mma / commit of the pair
       int ga = 0, kw = 0, it = 0;
       for (int g = pair0; g < total_items; g += npairs, ++it) {
         long long* dm = (p.dbg && blockIdx.x == 0 && lane == 0 && it >= kDbgItem && it < kDbgItem + 2) ? p.dbg + 1 + (it - kDbgItem) * 8 : nullptr;
@@ -204,22 +205,25 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
               const int s = kw % WS;
               ptx::mbar_wait(&w_full[s], (kw / WS) & 1);
               ptx::tc_fence_after();
-              if (lane == 0) {
-                // hb tile holds frames t0-1 .. t0+128; tap j (offset j-1) starts at row j
+              {
+                // hb tile holds frames t0-1 .. t0+128; tap j (offset j-1) starts at row j.  Descriptors are computed by the
+                // whole warp (convergent code -> uniform registers); only the tcgen05 instructions are under the one-lane
+                // predicate (inside a divergent region every operand would need an R2UR and a waterfall loop per MMA).
                 const uint32_t a_addr = ptx::smem_u32(sA + slot * AB) + (grp < 4 ? static_cast<uint32_t>(j * 128) : 0u);
                 const uint64_t da = ptx::make_desc_k_sw128(a_addr);
                 const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sW + s * WB));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mma(tmem_d, da + 2 * k, db + 2 * k, accum | (k != 0 ? 1u : 0u));
-                commit(&w_empty[s]);
+                for (int k = 0; k < 4; ++k)
+                  if (el) mma(tmem_d, da + 2 * k, db + 2 * k, accum | (k != 0 ? 1u : 0u));
+                if (el) commit(&w_empty[s]);
               }
               accum = 1;
               __syncwarp();
             }
-            if (lane == 0) commit(&a_empty[slot]);
+            if (el) commit(&a_empty[slot]);
             __syncwarp();
           }
-          if (lane == 0) commit(&acc_full[buf]);
+          if (el) commit(&acc_full[buf]);
           if (dm) dm[half * 2 + 1] = clock64();             // all MMAs of the job issued
           __syncwarp();
         }
@@ -235,16 +239,17 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
             const int s = kw % WS;
             ptx::mbar_wait(&w_full[s], (kw / WS) & 1);
             ptx::tc_fence_after();
-            if (lane == 0) {
+            {
               const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(sU + kb * 16384));
               const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sW + s * WB));
 #pragma unroll
-              for (int k = 0; k < 4; ++k) mma(tmem_d, da + 2 * k, db + 2 * k, (kb | k) != 0 ? 1u : 0u);
-              commit(&w_empty[s]);
+              for (int k = 0; k < 4; ++k)
+                if (el) mma(tmem_d, da + 2 * k, db + 2 * k, (kb | k) != 0 ? 1u : 0u);
+              if (el) commit(&w_empty[s]);
             }
             __syncwarp();
           }
-          if (lane == 0) {
+          if (el) {
             commit(u_empty);
             commit(&acc_full[buf]);
           }

@@ -208,21 +208,23 @@ inline ConvGemmParams make_params(int B, int Trows, int Tsrc, int C0, int ntaps,
   return p;
 }
 
-// Switch a parameter block to the shared-A schedule (source-0 tile loaded once per channel block with the
-// tap halo; taps read row-shifted descriptors).  The A0 tensor map must have been made with rows = Rrows.
-inline bool enable_shared_a(ConvGemmParams& p) {
+// Switch a parameter block to the shared-A schedule: each channel block of source 0 is loaded once per job (128*MT rows
+// plus the tap halo, as nload boxes of Rbox rows) and every (tap, sub-tile) reads a row-shifted descriptor of that copy.
+// The A0 tensor map must be made with rows = p.Rbox.  Measured on B200: the swizzle is a function of the absolute smem
+// address, so a row-shifted start needs NO descriptor base-offset (tools/shared_a_check.py).
+inline bool enable_shared_a(ConvGemmParams& p, int MT = 1) {
   int lo = p.tap_off[0], hi = p.tap_off[0];
   for (int i = 1; i < p.ntaps; ++i) { lo = p.tap_off[i] < lo ? p.tap_off[i] : lo; hi = p.tap_off[i] > hi ? p.tap_off[i] : hi; }
-  const int R = kTileM + hi - lo;
-  if (p.ntaps < 2 || R > 256) return false;
-  p.shared_a = 1; p.off_min = lo; p.Rrows = R; p.bo_mode = 0;   // measured on B200: the swizzle is a function of the
-  // absolute smem address, so a row-shifted start needs NO descriptor base-offset (tools/shared_a_check.py)
+  if (p.ntaps < 2 || MT < 1 || (MT > 1 && p.nkb1 > 0)) return false;
+  const int need = kTileM * MT + hi - lo;
+  int nload = (need + 255) / 256, box = 0;
+  for (;; ++nload) {
+    box = ((need + nload - 1) / nload + 7) / 8 * 8;       // boxes start on a swizzle-atom boundary (8 rows)
+    if (box <= 256) break;
+  }
+  if (static_cast<size_t>(box) * nload * p.KB * 2 > 100 * 1024) return false;     // two slots must fit next to the weight ring
+  p.shared_a = 1; p.MT = MT; p.off_min = lo; p.Rrows = need; p.Rbox = box; p.nload = nload; p.bo_mode = 0;
   return true;
-}
-inline int shared_a_rows(int ntaps, const int* offs) {
-  int lo = offs[0], hi = offs[0];
-  for (int i = 1; i < ntaps; ++i) { lo = offs[i] < lo ? offs[i] : lo; hi = offs[i] > hi ? offs[i] : hi; }
-  return kTileM + hi - lo;
 }
 
 template <int KB, int CH, class Epi>
@@ -230,14 +232,18 @@ inline int launch_tc(const ConvGemmParams& p, const GemmOperands& op, const Epi&
   static bool attr_set = false;
   const int nkb = p.ntaps * p.nkb0 + p.nkb1;
   int stages, a_slots, a_slot_bytes;
+  constexpr int scratch = (CH == 32 && epi_transposed<Epi>::value) ? kEpiScratchBytes : 0;
+  const int budget = 225 * 1024 - scratch;
   if (p.shared_a) {
-    a_slot_bytes = static_cast<int>(align_up(static_cast<size_t>(p.Rrows > kTileM ? p.Rrows : kTileM) * KB * 2, 1024));
-    a_slots = p.nkb0 + p.nkb1 < 3 ? p.nkb0 + p.nkb1 : 3;
-    stages = (225 * 1024 - a_slots * a_slot_bytes) / tc_b_stage_bytes(op.BN, KB);
+    const int rows = p.Rbox * p.nload > kTileM ? p.Rbox * p.nload : kTileM;
+    a_slot_bytes = static_cast<int>(align_up(static_cast<size_t>(rows) * KB * 2, 1024));
+    a_slots = p.nkb0 + p.nkb1 < 2 ? 2 : (p.nkb0 + p.nkb1 < 3 ? p.nkb0 + p.nkb1 : 3);   // >= 2: the next job's load overlaps this job's MMAs
+    while (a_slots > 2 && budget - a_slots * a_slot_bytes < 3 * tc_b_stage_bytes(op.BN, KB)) --a_slots;
+    stages = (budget - a_slots * a_slot_bytes) / tc_b_stage_bytes(op.BN, KB);
     if (stages > 8) stages = 8;
   } else {
     a_slot_bytes = tc_a_stage_bytes(KB) * (p.MT > 0 ? p.MT : 1);
-    stages = (225 * 1024) / (a_slot_bytes + tc_b_stage_bytes(op.BN, KB));
+    stages = budget / (a_slot_bytes + tc_b_stage_bytes(op.BN, KB));
     if (stages > 6) stages = 6;
     a_slots = 0;   // = stages, set below
   }
@@ -249,14 +255,14 @@ inline int launch_tc(const ConvGemmParams& p, const GemmOperands& op, const Epi&
     FSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const size_t smem = tc_smem_bytes(op.BN, KB, stages, a_slots, a_slot_bytes);
+  const size_t smem = tc_smem_bytes(op.BN, KB, stages, a_slots, a_slot_bytes, scratch);
   static int num_sms = 0;
   if (num_sms == 0) {
     int dev = 0;
     FSE_CUDA(cudaGetDevice(&dev));
     FSE_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int tile_rows = kTileM * (p.shared_a ? 1 : (p.MT > 0 ? p.MT : 1));
+  const int tile_rows = kTileM * (p.MT > 0 ? p.MT : 1);
   const int total_tiles = p.B * ((p.Trows + tile_rows - 1) / tile_rows) * (p.N / op.BN);
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);   // persistent: one CTA per SM
   const CUtensorMap* mA1 = op.mA1 ? op.mA1 : op.mA0;
@@ -270,7 +276,7 @@ inline int launch_tc(const ConvGemmParams& p, const GemmOperands& op, const Epi&
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FSE_CUDA(cudaLaunchKernelEx(&cfg, kern, *op.mA0, *mA1, *op.mW, p, op.BN, stages, a_slots, a_slot_bytes, epi));
+  FSE_CUDA(cudaLaunchKernelEx(&cfg, kern, *op.mA0, *mA1, *op.mW, p, op.BN, stages, a_slots, a_slot_bytes, scratch, epi));
   FSE_CUDA(cudaGetLastError());
   return FSE_OK;
 }

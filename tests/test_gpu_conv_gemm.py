@@ -83,3 +83,30 @@ def test_conv_gemm_shared_a_schedule(lib_built, B, T, C0, offs, N, BN, KB):
     assert np.isfinite(tc).all()
     err = np.abs(tc - ref)
     assert err.max() < 1e-3, f"max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"
+
+
+def _taps(k, d):
+    return [(j - (k - 1) // 2) * d for j in range(k)]
+
+
+SHARED_MT_CASES = [
+    # B,  T,    C0,  offsets,       N,   BN,  KB, MT      (the HiFi-GAN resblock shapes: one n-tile, MT sub-tiles per job)
+    (2, 2500, 32, _taps(11, 5), 32, 32, 32, 8),           # stage 4: 1074 job rows arrive as 5 boxes of 216
+    (1, 1100, 32, _taps(3, 1), 32, 32, 32, 8),
+    (2, 1300, 64, _taps(7, 3), 64, 64, 64, 4),            # stage 3
+    (1, 700, 128, _taps(11, 5), 128, 128, 64, 2),         # stage 2: two channel blocks
+    (1, 300, 256, _taps(7, 5), 256, 256, 64, 1),          # stage 1: span 30, MT = 1
+]
+
+
+@pytest.mark.parametrize("B,T,C0,offs,N,BN,KB,MT", SHARED_MT_CASES)
+def test_conv_gemm_shared_a_multi_tile(lib_built, B, T, C0, offs, N, BN, KB, MT):
+    """Shared-A schedule with MT 128-frame sub-tiles per job: the job's rows (128*MT + tap span) are loaded once per
+    channel block as several TMA boxes laid end to end, every (tap, sub-tile) is a row-shifted descriptor."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    A, W, ref = _operands(B, T, C0, offs, N, KB)
+    tc = run("tc_bf16", A, W, B, T, C0, offs, N, BN, KB, shared_a=1 + 16 * (MT - 1))
+    assert np.isfinite(tc).all()
+    err = np.abs(tc - ref)
+    assert err.max() < 1e-3, f"max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)}"
