@@ -77,6 +77,7 @@ __device__ __forceinline__ void st_vec_stream(__nv_bfloat16* p, const float* v) 
 template <typename TOp>
 struct EpiIn {
   static constexpr int kAux = 0;
+  static constexpr bool kTransposed = true;
   const float* bias;   // [C]
   float* h;            // [B*T, C] fp32 residual stream
   TOp* hb;             // [B*T, C] operand copy
@@ -179,6 +180,7 @@ struct EpiRes {
 template <typename TOp>
 struct EpiSkip {
   static constexpr int kAux = 0;
+  static constexpr bool kTransposed = true;
   const float* bias;
   TOp* rb;   // [B*T, C]
   int C, T;

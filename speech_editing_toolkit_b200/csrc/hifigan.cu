@@ -117,26 +117,37 @@ struct EpiResAdd {
 };
 
 // conv_post (C -> 1, k taps) + tanh on the already-activated fp32 stage output (hifigan.py:138-140)
+// One block = 256 consecutive samples of one item.  The (256 + k - 1) x C input rows are staged in shared memory with
+// coalesced loads (row stride C + 1: lane-per-row reads are bank-conflict free); the per-sample accumulation order (taps
+// outer, channels inner, sequential fma) is that of a plain loop, so results do not depend on the staging.
 __global__ void __launch_bounds__(256) conv_post_kernel(const float* __restrict__ xin, const float* __restrict__ w,
                                                         float bias, float* __restrict__ wav, int C, int T, int k) {
-  extern __shared__ float sw[];   // [k][C]
-  for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = w[i];
-  __syncthreads();
+  extern __shared__ float sw[];   // [k][C] weights, then [256 + k - 1][C + 1] input rows
+  float* tile = sw + k * C;
   const int b = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t0 = blockIdx.x * blockDim.x;
+  const int half = (k - 1) / 2;
+  const int R = blockDim.x + k - 1, C4 = C / 4, ld = C + 1;
+  for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < R * C4; i += blockDim.x) {
+    const int row = i / C4, c4 = i - row * C4;
+    const int tt = t0 - half + row;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);     // zero padding (hifigan.py:138-139, padding = 3)
+    if (tt >= 0 && tt < T) v = __ldg(reinterpret_cast<const float4*>(xin + (static_cast<size_t>(b) * T + tt) * C) + c4);
+    float* d = tile + row * ld + 4 * c4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
   if (t >= T) return;
   float acc = 0.f;
-  const int half = (k - 1) / 2;
   for (int j = 0; j < k; ++j) {
     const int tt = t + j - half;
     if (tt < 0 || tt >= T) continue;
-    const float4* row = reinterpret_cast<const float4*>(xin + (static_cast<size_t>(b) * T + tt) * C);
+    const float* row = tile + (threadIdx.x + j) * ld;
     const float* wj = sw + j * C;
-    for (int c = 0; c < C / 4; ++c) {
-      const float4 v = __ldg(row + c);
-      acc = fmaf(v.x, wj[4 * c], acc); acc = fmaf(v.y, wj[4 * c + 1], acc);
-      acc = fmaf(v.z, wj[4 * c + 2], acc); acc = fmaf(v.w, wj[4 * c + 3], acc);
-    }
+#pragma unroll 8
+    for (int c = 0; c < C; ++c) acc = fmaf(row[c], wj[c], acc);
   }
   wav[static_cast<size_t>(b) * T + t] = tanhf(acc + bias);
 }
@@ -377,7 +388,12 @@ int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, voi
   }
   const int Cl = stage_channels(h, nu - 1);
   h->prof.begin(4, st);
-  conv_post_kernel<<<dim3((Tin + 255) / 256, B), 256, h->post_k * Cl * sizeof(float), st>>>(w.xs, h->post_w, h->post_b, wav, Cl, Tin, h->post_k);
+  const size_t post_smem = (static_cast<size_t>(h->post_k) * Cl + (256 + h->post_k - 1) * (Cl + 1)) * sizeof(float);
+  if (post_smem > 48 * 1024) {
+    if (post_smem > 200 * 1024) return fail(FSE_EINVAL, "conv_post: %d channels x %d taps do not fit shared memory", Cl, h->post_k);
+    FSE_CUDA(cudaFuncSetAttribute(conv_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(post_smem)));
+  }
+  conv_post_kernel<<<dim3((Tin + 255) / 256, B), 256, post_smem, st>>>(w.xs, h->post_w, h->post_b, wav, Cl, Tin, h->post_k);
   h->prof.end(st);
   FSE_CUDA(cudaGetLastError());
   ++h->launches;
