@@ -50,6 +50,22 @@ struct ConvGemmParams {
   long long* dbg;  // optional [32] clock64 phase stamps of CTA 0 (test hook), else null
 };
 
+// Epilogue functors that set `static constexpr bool kTransposed = true` are run through a per-warp shared-memory
+// transposition (conv_gemm_tc_kernel, CH == 32): 8 lanes cover 32 consecutive channels of one frame, so every global
+// load / store instruction touches 4 row segments of 64-128 contiguous bytes instead of 32 rows x 16 bytes.
+template <class E, class = void>
+struct epi_transposed : std::false_type {};
+template <class E>
+struct epi_transposed<E, std::void_t<decltype(E::kTransposed)>> : std::bool_constant<E::kTransposed> {};
+// `static constexpr int kLate = n`: the functor has n more operand sets that depend on stores of this very launch pattern
+// (read-modify-write buffers) and are therefore fetched right before apply instead of one chunk ahead:
+// load_late<NV>(b, t, n0, dst) fills aux[NV*kAux .. NV*(kAux+kLate)).
+template <class E, class = void>
+struct epi_late : std::integral_constant<int, 0> {};
+template <class E>
+struct epi_late<E, std::void_t<decltype(E::kLate)>> : std::integral_constant<int, E::kLate> {};
+constexpr int kEpiScratchBytes = 8 * 32 * 32 * 4;     // kEpiWarps x [32 frames][32 fp32]
+
 // ------------------------------------------------------------------------------------------
 // small vector store helpers
 // ------------------------------------------------------------------------------------------
@@ -160,8 +176,9 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(ConvGemmParams p, c
     for (int i = 0; i < 4; ++i) {
       const int t = t0 + ty * 4 + i;
       if (t < p.Trows) {
-        float aux[4 * (Epi::kAux > 0 ? Epi::kAux : 1)];
+        float aux[4 * (Epi::kAux + epi_late<Epi>::value > 0 ? Epi::kAux + epi_late<Epi>::value : 1)];
         if constexpr (Epi::kAux > 0) epi.template load_aux<4>(b, t, n, aux);
+        if constexpr (epi_late<Epi>::value > 0) epi.template load_late<4>(b, t, n, aux + 4 * Epi::kAux);
         epi.template apply<4>(b, t, n, acc[i], aux);
       }
     }
@@ -181,15 +198,6 @@ __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(ConvGemmParams p, c
 constexpr int kEpiWarps = 8;
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr int kTileM = 128;       // frames per tile = TMEM lanes
-
-// Epilogue functors that set `static constexpr bool kTransposed = true` are run through a per-warp shared-memory
-// transposition (conv_gemm_tc_kernel, CH == 32): 8 lanes cover 32 consecutive channels of one frame, so every global
-// load / store instruction touches 4 row segments of 64-128 contiguous bytes instead of 32 rows x 16 bytes.
-template <class E, class = void>
-struct epi_transposed : std::false_type {};
-template <class E>
-struct epi_transposed<E, std::void_t<decltype(E::kTransposed)>> : std::bool_constant<E::kTransposed> {};
-constexpr int kEpiScratchBytes = 8 * 32 * 32 * 4;     // kEpiWarps x [32 frames][32 fp32]
 
 __host__ __device__ inline int tc_b_stage_bytes(int BN, int KB) { return ((BN * KB * 2 + 1023) / 1024) * 1024; }
 __host__ __device__ inline int tc_a_stage_bytes(int KB) { return kTileM * KB * 2; }
@@ -434,7 +442,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       // the NEXT chunk are requested while the current one is processed (first chunk: before the accumulator is awaited).
       float* stg = reinterpret_cast<float*>(sScratch) + ew * 1024;
       const int cq = lane & 7, r0 = lane >> 3;
-      constexpr int AX = Epi::kAux > 0 ? 4 * Epi::kAux : 1;
+      constexpr int AP = Epi::kAux > 0 ? 4 * Epi::kAux : 1;                                   // prefetched part
+      constexpr int AX = Epi::kAux + epi_late<Epi>::value > 0 ? 4 * (Epi::kAux + epi_late<Epi>::value) : 1;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
@@ -444,7 +453,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         auto T_OF = [&](int c, int i) { return tq + (c / cpb) * kTileM + 4 * i; };
         auto N_OF = [&](int c) { return n0 + (c % cpb) * CH + cq * 4; };
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * MT * BN);
-        float aux[8][AX], aux_next[8][AX];
+        float aux[8][AX], aux_next[8][AP];
         if constexpr (Epi::kAux > 0) {
           if (half < nchunks) {
 #pragma unroll
@@ -471,6 +480,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             *reinterpret_cast<uint4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
           __syncwarp();
           const int nn = N_OF(c);
+          if constexpr (epi_late<Epi>::value > 0) {     // all of the chunk's late reads before its first store
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (T_OF(c, i) < p.Trows) epi.template load_late<4>(b, T_OF(c, i), nn, aux[i] + 4 * Epi::kAux);
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rloc = 4 * i + r0;
@@ -486,7 +500,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-              for (int j = 0; j < AX; ++j) aux[i][j] = aux_next[i][j];
+              for (int j = 0; j < AP; ++j) aux[i][j] = aux_next[i][j];
           }
         }
         ptx::tc_fence_before();
@@ -496,6 +510,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       }
     } else {
     constexpr int AUXN = CH * (Epi::kAux > 0 ? Epi::kAux : 1);
+    auto apply_chunk = [&](int bb, int t, int nn, const float* v, const float* auxp) {
+      if constexpr (epi_late<Epi>::value > 0) {
+        float comb[CH * (Epi::kAux + epi_late<Epi>::value)];
+#pragma unroll
+        for (int j = 0; j < CH * Epi::kAux; ++j) comb[j] = auxp[j];
+        epi.template load_late<CH>(bb, t, nn, comb + CH * Epi::kAux);
+        epi.template apply<CH>(bb, t, nn, v, comb);
+      } else {
+        epi.template apply<CH>(bb, t, nn, v, auxp);
+      }
+    };
     // Residual operands: when a warp owns at most kMaxPre chunks of a tile and they fit in 64 registers, ALL of
     // them are requested before the accumulator is awaited (one exposed memory latency per tile); otherwise the
     // next chunk's operands are requested while the current chunk is processed (when they fit in 32 registers).
@@ -554,12 +579,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
               // static register indexing: pick the pre-loaded set of this chunk
 #pragma unroll
               for (int i = 0; i < kMaxPre; ++i)
-                if (i == ci) epi.template apply<CH>(b, t, N_OF(c), v, aux[i]);
+                if (i == ci) apply_chunk(b, t, N_OF(c), v, aux[i]);
             } else {
-              epi.template apply<CH>(b, t, N_OF(c), v, aux[0]);
+              apply_chunk(b, t, N_OF(c), v, aux[0]);
             }
           } else {
-            epi.template apply<CH>(b, t, N_OF(c), v, aux_here);
+            apply_chunk(b, t, N_OF(c), v, aux_here);
           }
         }
         if constexpr (kChunkAhead) {

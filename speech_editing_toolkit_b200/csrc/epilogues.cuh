@@ -221,6 +221,18 @@ struct EpiOut {
     if (n0 >= M) return;
     const size_t row = static_cast<size_t>(b) * T + t;
     float v[NV];
+    // All global reads first: x_t / noise may alias x_out as far as the compiler knows, so a load placed after a store of
+    // the previous element is not hoisted and every element would pay its own memory round trip.
+    float xt[NV], zn[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      xt[i] = 0.f; zn[i] = 0.f;
+      if (mode == 1 && n0 + i < M) {
+        const size_t idx = (static_cast<size_t>(b) * M + n0 + i) * T + t;
+        xt[i] = __ldg(x_t + idx);
+        if (noise) zn[i] = __ldg(noise + idx);
+      }
+    }
 #pragma unroll
     for (int g = 0; g < NV / 4; ++g) {
       float z[4] = {0.f, 0.f, 0.f, 0.f};
@@ -232,20 +244,21 @@ struct EpiOut {
         const int m = n0 + i;
         float val = 0.f;
         if (m < M) {
-          const size_t idx = (static_cast<size_t>(b) * M + m) * T + t;
           const float x0 = acc[i] + __ldg(bias + m);
           if (mode == 0) {
             val = x0;
           } else {
-            const float zz = noise ? __ldg(noise + idx) : z[q];
-            const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, __ldg(x_t + idx)));
+            const float zz = noise ? zn[i] : z[q];
+            const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xt[i]));
             val = __fadd_rn(mean, __fmul_rn(sigma, zz));
           }
-          x_out[idx] = val;
         }
         v[i] = val;
       }
     }
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (n0 + i < M) x_out[(static_cast<size_t>(b) * M + n0 + i) * T + t] = v[i];
     if (n0 + NV <= M) {
       if (xb) st_vec<NV>(xb + row * M + n0, v);
       if (mel_out) {

@@ -61,9 +61,10 @@ struct EpiUp {
 
 // ResBlock1 convs2 + residual (hifigan.py:56-57); the last pair of each block also folds the
 // mean over the parallel blocks (hifigan.py:131-137) and the activation feeding the next stage.
-template <typename TOp>
+template <typename TOp, bool kSum>     // kSum: kinds 2 and 3 (needs the running sum); kinds 0 and 1 use the leaner kSum = false
 struct EpiResAdd {
   static constexpr int kAux = 1;       // per column: the residual input (prefetched one chunk ahead)
+  static constexpr int kLate = kSum ? 1 : 0;   // ... and the running sum over the parallel resblocks (read-modify-write)
   static constexpr bool kTransposed = true;
   const float* bias;
   const float* res;    // [B*T, N] fp32 residual input
@@ -85,6 +86,15 @@ struct EpiResAdd {
     }
   }
   template <int NV>
+  __device__ __forceinline__ void load_late(int b, int t, int n0, float* dst) const {
+    const size_t o = (static_cast<size_t>(b) * T + t) * N + n0;
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+      const float4 v = reinterpret_cast<const float4*>(xs + o)[i];
+      dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+    }
+  }
+  template <int NV>
   __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float* aux) const {
     const size_t o = (static_cast<size_t>(b) * T + t) * N + n0;
     float v[NV];
@@ -98,11 +108,9 @@ struct EpiResAdd {
     } else if (kind == 1) {
       st_vec<NV>(xs + o, v);
     } else {
-      // the running sum over the parallel resblocks is read here (2 of the 9 conv pairs of a stage)
+      if constexpr (kSum) {               // (kSum = false reaches here only with a single resblock per stage: the mean is v itself)
 #pragma unroll
-      for (int i = 0; i < NV / 4; ++i) {
-        const float4 s4 = reinterpret_cast<const float4*>(xs + o)[i];
-        v[4 * i] = s4.x + v[4 * i]; v[4 * i + 1] = s4.y + v[4 * i + 1]; v[4 * i + 2] = s4.z + v[4 * i + 2]; v[4 * i + 3] = s4.w + v[4 * i + 3];
+        for (int i = 0; i < NV; ++i) v[i] = aux[NV + i] + v[i];
       }
       if (kind == 2) {
         st_vec<NV>(xs + o, v);
@@ -373,14 +381,24 @@ int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, voi
           FSE_TRY((run_conv<TOp>(h, a, m == 0 ? w.xa : w.ya, B, Tout, Tout, epi, st, 2)));
         }
         {
-          EpiResAdd<TOp> epi{};
-          epi.bias = c.bias; epi.res = m == 0 ? w.x : w.y; epi.y = w.y; epi.ya = static_cast<TOp*>(w.ya);
-          epi.xs = w.xs; epi.next_a = static_cast<TOp*>(w.ua); epi.final_f32 = last_stage ? w.xs : nullptr;
-          epi.N = Cout; epi.T = Tout;
-          epi.kind = m < 2 ? 0 : (nk == 1 ? 3 : (j == 0 ? 1 : (j == nk - 1 ? 3 : 2)));
-          epi.num_kernels = static_cast<float>(nk);
-          epi.slope_next = last_stage ? 0.01f : 0.1f;   // F.leaky_relu default slope before conv_post (hifigan.py:138)
-          FSE_TRY((run_conv<TOp>(h, c, w.tmp, B, Tout, Tout, epi, st, 3)));
+          const int kind = m < 2 ? 0 : (nk == 1 ? 3 : (j == 0 ? 1 : (j == nk - 1 ? 3 : 2)));
+          auto fill = [&](auto& epi) {
+            epi.bias = c.bias; epi.res = m == 0 ? w.x : w.y; epi.y = w.y; epi.ya = static_cast<TOp*>(w.ya);
+            epi.xs = w.xs; epi.next_a = static_cast<TOp*>(w.ua); epi.final_f32 = last_stage ? w.xs : nullptr;
+            epi.N = Cout; epi.T = Tout;
+            epi.kind = kind;
+            epi.num_kernels = static_cast<float>(nk);
+            epi.slope_next = last_stage ? 0.01f : 0.1f;   // F.leaky_relu default slope before conv_post (hifigan.py:138)
+          };
+          if (kind >= 2 && !(kind == 3 && nk == 1)) {
+            EpiResAdd<TOp, true> epi{};
+            fill(epi);
+            FSE_TRY((run_conv<TOp>(h, c, w.tmp, B, Tout, Tout, epi, st, 3)));
+          } else {
+            EpiResAdd<TOp, false> epi{};
+            fill(epi);
+            FSE_TRY((run_conv<TOp>(h, c, w.tmp, B, Tout, Tout, epi, st, 3)));
+          }
         }
       }
     }

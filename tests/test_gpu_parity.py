@@ -247,3 +247,25 @@ def test_hifigan_tc_matches_simt_on_batch(lib_built):
         outs[mode] = v.forward(cu(mel)).cpu().numpy()
     assert outs["tc_bf16"].shape == (2, 37 * 256)
     assert rel_l1(outs["tc_bf16"], outs["simt_bf16"]) < 5e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernels", [[3], [3, 5]])
+def test_hifigan_other_resblock_counts(lib_built, kernels):
+    """Generators with one or two parallel resblocks per stage (hifigan.py:131-137: xs = mean over the blocks): the
+    running-sum epilogue variants (first / middle / last block) must also hold when there is no middle or no sum at all."""
+    from oracle import fluentspeech_oracle as O
+    from speech_editing_toolkit_b200 import synth
+    from speech_editing_toolkit_b200.engine import Vocoder
+    cfg = dict(upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4], upsample_initial_channel=128, resblock="1",
+               resblock_kernel_sizes=kernels, resblock_dilation_sizes=[[1, 3, 5]] * len(kernels))
+    sd = synth.hifigan_state_dict(11, cfg)
+    rs = np.random.RandomState(12)
+    mel = np.clip(rs.standard_normal((2, 150, 80)) * 1.5 - 3, -6, 1.5).astype(np.float32)
+    ref = O.hifigan_forward(sd, cfg, mel.transpose(0, 2, 1), gemm_dtype="f32")[:, 0]
+    v32 = Vocoder(cfg, mode="simt_f32"); v32.load_state_dict(sd)
+    assert np.abs(v32.forward(cu(mel)).cpu().numpy() - ref).max() < TOL_F32_ABS
+    vtc = Vocoder(cfg, mode="tc_bf16"); vtc.load_state_dict(sd)
+    wav = vtc.forward(cu(mel)).cpu().numpy()
+    assert wav.shape == (2, 150 * 8) and np.isfinite(wav).all()
+    assert rel_l1(wav, ref) < 3e-2
