@@ -240,7 +240,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   const int nkb_src0 = p.ntaps * p.nkb0;
   const int nkb = nkb_src0 + p.nkb1;
   uint32_t ncols = 32;
-  while (static_cast<int>(ncols) < 2 * MT * BN) ncols <<= 1;
+  // two accumulator buffers (the epilogue of job i overlaps the MMAs of job i+1) when they fit the 512 TMEM columns, else one
+  const int nacc = 2 * MT * BN <= 512 ? 2 : 1;
+  while (static_cast<int>(ncols) < nacc * MT * BN) ncols <<= 1;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&mapA0);
@@ -343,8 +345,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     if (p.shared_a) {
       const int ngroups = p.nkb0 + p.nkb1;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u);
+        const int buf = nacc == 2 ? (it & 1) : 0, use = nacc == 2 ? (it >> 1) : it;
+        ptx::mbar_wait(&acc_empty[buf], (use & 1) ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * MT * BN);
         uint32_t accum = 0;
@@ -393,8 +395,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       }
     } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u);
+      const int buf = nacc == 2 ? (it & 1) : 0, use = nacc == 2 ? (it >> 1) : it;
+      ptx::mbar_wait(&acc_empty[buf], (use & 1) ^ 1u);
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * MT * BN);
       for (int kb = 0; kb < nkb; ++kb, ++kbg) {
@@ -446,7 +448,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       constexpr int AX = Epi::kAux + epi_late<Epi>::value > 0 ? 4 * (Epi::kAux + epi_late<Epi>::value) : 1;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
+        const int buf = nacc == 2 ? (it & 1) : 0, use = nacc == 2 ? (it >> 1) : it;
         const int m = tile / n_tiles, n0 = (tile % n_tiles) * BN;
         const int b = p.b_off + m / tiles_per_item, t0 = (m % tiles_per_item) * tile_rows;
         const int tq = t0 + q * 32 + r0;          // frame of iteration 0 in sub-tile 0; iteration i adds 4*i, sub-tile st adds 128*st
@@ -461,7 +463,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
               if (T_OF(half, i) < p.Trows) epi.template load_aux<4>(b, T_OF(half, i), N_OF(half), aux[i]);
           }
         }
-        ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+        ptx::mbar_wait(&acc_full[buf], use & 1);
         ptx::tc_fence_after();
         if (dbg && ew == 0 && lane == 0 && it == 0) dbg[5] = clock64();   // first accumulator complete
         for (int c = half; c < nchunks; c += 2) {
@@ -530,7 +532,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     const bool pre_all = kMaxPre > 0 && my_chunks <= kMaxPre;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
+      const int buf = nacc == 2 ? (it & 1) : 0, use = nacc == 2 ? (it >> 1) : it;
       const int m = tile / n_tiles, n0 = (tile % n_tiles) * BN;
       const int b = p.b_off + m / tiles_per_item, t0 = (m % tiles_per_item) * tile_rows;
       const int tl0 = t0 + q * 32 + lane;      // frame of this lane in sub-tile 0; chunk c lives in sub-tile c / cpb
@@ -547,7 +549,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           epi.template load_aux<CH>(b, T_OF(half), N_OF(half), aux[0]);
         }
       }
-      ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      ptx::mbar_wait(&acc_full[buf], use & 1);
       ptx::tc_fence_after();
       if (dbg && ew == 0 && lane == 0 && it == 0) dbg[5] = clock64();   // first accumulator complete
       int ci = 0;

@@ -203,6 +203,7 @@ struct fse_denoiser {
     CUtensorMap m_hb1{};                        // 128-row box of the second hb buffer
   } plan;
   long long launches = 0;
+  int skip_mt = 2;         // sub-tiles per job of the folded skip GEMM (FSE_SKIP_MT)
   int batch_chunk = 0;     // utterances per L2-resident chunk (0 = whole batch); FSE_BATCH_CHUNK overrides
   long long* dbg_buf = nullptr;   // FSE_DBG_STAMPS=1: clock64 phase stamps of layer-3 kernels (developer aid)
   Profiler prof;
@@ -411,6 +412,9 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
     ConvGemmParams p = make_params(Bc, T, T, L * C, 1, &zero, 0, C, 64); p.b_off = b0;
     GemmOperands op; op.A0 = w.u; op.W = h->W_skip; op.mA0 = &h->plan.m_u; op.mW = &h->mW_skip;
     op.BN = C % 256 == 0 ? 256 : (C % 128 == 0 ? 128 : 64);
+    // K = L*C is long and the weight tile is re-read by every job: two 128-frame sub-tiles per job halve that traffic
+    // (one 512-column accumulator, the short epilogue is not overlapped).  FSE_SKIP_MT=1: one sub-tile, two accumulators.
+    if (tc && T > kTileM) p.MT = h->skip_mt;
     EpiSkip<TOp> epi{h->b_skip, static_cast<TOp*>(w.rb), C, T};
     FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 3})));
   }
@@ -554,6 +558,7 @@ int fse_denoiser_create(const fse_denoiser_config* cfg, fse_denoiser** out) {
   h->cfg = *cfg;
   h->bf16 = cfg->mode != FSE_MODE_SIMT_F32;
   if (const char* e = getenv("FSE_BATCH_CHUNK")) h->batch_chunk = atoi(e);
+  if (const char* e = getenv("FSE_SKIP_MT")) h->skip_mt = atoi(e) == 1 ? 1 : 2;
   // The fused multi-layer kernel covers the shipped configurations (256 residual channels, dilation 1, <= 256
   // condition channels); anything else runs the per-layer kernels.  FSE_FUSED=0 forces the per-layer path.
   h->fused = cfg->mode == FSE_MODE_TC_BF16 && cfg->channels == kFC && cfg->dilation_cycle_length == 1 && cfg->hidden <= 256 &&

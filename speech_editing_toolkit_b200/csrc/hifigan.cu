@@ -330,7 +330,8 @@ int run_conv(fse_vocoder* h, const ConvW& cw, const void* A, int B, int Trows, i
     // narrow layers (C_out <= 128, one n-tile): one job = several 128-frame sub-tiles against the same weight tiles
     int rows = kTileM, mt = 1;
     if (h->multi_tile && cw.BN == cw.N) {
-      if (h->multi_tile_level >= 2) mt = cw.BN <= 32 ? 8 : (cw.BN <= 64 ? 4 : (cw.BN <= 128 ? 2 : 1));
+      if (h->multi_tile_level >= 3) mt = cw.BN <= 32 ? 8 : (cw.BN <= 64 ? 4 : (cw.BN <= 128 ? 4 : 2));   // wide layers: one accumulator
+      else if (h->multi_tile_level >= 2) mt = cw.BN <= 32 ? 8 : (cw.BN <= 64 ? 4 : (cw.BN <= 128 ? 2 : 1));
       else mt = cw.BN <= 32 ? 4 : (cw.BN <= 128 ? 2 : 1);
     }
     if (h->shared_a && cw.ntaps >= 3 && enable_shared_a(p, mt)) rows = p.Rbox;
