@@ -294,7 +294,8 @@ def run_b200(args):
         fused = prof_d["res_gemm"][1] == 0
         if fused:   # one launch = all 20 residual layers: per layer gate GEMM 0.983 MFLOP/frame + residual GEMM 0.131 MFLOP/frame
             flops = 20 * 2.0 * B * T * (512 * 960 + 256 * 256)
-            kname = "denoiser_layers_kernel<pair> (20 x [k=3 conv + cond 1x1 + gate -> residual 1x1]; persistent, cta_group::2)"
+            kname = ("denoiser_stream_kernel<pair> (20 x [k=3 conv + cond 1x1 + gate -> residual 1x1] as one stream of (layer, unit) "
+                     "items; persistent, cta_group::2)")
         else:
             flops = 2.0 * B * T * 512 * 960                  # algorithmic: 0.983 MFLOP/frame (k=3 conv 512x768 + cond 512x192)
             kname = "conv_gemm_tc_kernel<EpiGate> (dilated k=3 conv + conditioner 1x1 + gate)"
@@ -303,8 +304,10 @@ def run_b200(args):
                     "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
                     "peak_source": pk["src"] + ", sustained bf16",
                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this shape, from the committed
-                    # `ncu --set full` capture (profiles/r01_ncu_fused_pair_kernel.md); null for the per-layer fallback kernels
-                    "traffic": 969868288 if (fused and (B, T) == (32, 1024)) else None, "traffic_unit": "bytes/launch (ncu)",
+                    # `ncu --set full` capture (profiles/r01_ncu_stream_kernel.md); null for the other kernels / shapes
+                    "traffic": 1149497600 if (fused and (B, T) == (32, 1024) and os.environ.get("FSE_FUSED_STREAM", "1") != "0"
+                                              and os.environ.get("FSE_FUSED", "2") not in ("0", "1")) else None,
+                    "traffic_unit": "bytes/launch (ncu)",
                     "avg_launch_us": g_ms / g_n * 1e3 if g_n else None, "launches_timed": g_n,
                     "flops_per_launch": flops}
     breakdown = {}

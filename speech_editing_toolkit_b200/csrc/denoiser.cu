@@ -347,14 +347,24 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
       h->prof.begin(1, st);
       if (h->fused_pair) {
         int grid = (tiles + 1) / 2 * 2;                      // whole clusters of 2
-        const int max_grid = h->num_sms / 2 * 2;
-        if (grid > max_grid) grid = max_grid;
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(stream ? kStreamThreads : kTcThreads); cfg.dynamicSmemBytes = kFusedSmemBytes; cfg.stream = st;
+        cfg.gridDim = dim3(h->num_sms / 2 * 2); cfg.blockDim = dim3(stream ? kStreamThreads : kTcThreads); cfg.dynamicSmemBytes = kFusedSmemBytes; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
+        // The CTAs wait for each other (layer dependencies / grid barrier): every cluster of the grid must be resident at once.
+        // A GPC with an odd number of usable SMs leaves one SM without a partner, so ask the driver instead of assuming SMs / 2.
+        static int max_clusters[2] = {0, 0};
+        if (max_clusters[stream] == 0) {
+          int n = 0;
+          if (stream) FSE_CUDA(cudaOccupancyMaxActiveClusters(&n, denoiser_stream_kernel<true>, &cfg));
+          else FSE_CUDA(cudaOccupancyMaxActiveClusters(&n, denoiser_layers_kernel<true, true>, &cfg));
+          if (n < 1) return fail(FSE_ECUDA, "no resident CTA pair possible for the fused residual-layer kernel");
+          max_clusters[stream] = n;
+        }
+        if (grid > 2 * max_clusters[stream]) grid = 2 * max_clusters[stream];
+        cfg.gridDim = dim3(grid);
         if (stream)
           FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_stream_kernel<true>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp));
         else if (h->fused_shared_a)

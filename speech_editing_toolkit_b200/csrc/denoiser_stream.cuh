@@ -70,8 +70,8 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
   uint64_t* w_empty = w_full + WS;
   uint64_t* acc_full = w_empty + WS;              // [2]
   uint64_t* acc_empty = acc_full + 2;             // [2]
-  uint64_t* u_full = acc_empty + 2;
-  uint64_t* u_empty = u_full + 1;
+  uint64_t* u_full = acc_empty + 2;               // [2]: u k-blocks 0,1 (first gate half) / 2,3 (second half) are in shared memory
+  uint64_t* u_empty = u_full + 2;
   uint64_t* pub_bar = u_empty + 1;                // this CTA's epilogue warps have stored their h / hb rows of the item
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pub_bar + 1);
 
@@ -100,7 +100,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
       for (int i = 0; i < AS; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
       for (int i = 0; i < WS; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
       for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kEpiWarps * kMul); }
-      ptx::mbar_init(u_full, 2 * kEpiWarps * kMul);
+      for (int i = 0; i < 2; ++i) ptx::mbar_init(&u_full[i], kEpiWarps * kMul);
       ptx::mbar_init(u_empty, 1);
       ptx::mbar_init(pub_bar, kEpiWarps);
       ptx::fence_barrier_init();
@@ -231,11 +231,15 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           const int job = 3 * it + 2, buf = job & 1;
           ptx::mbar_wait(&acc_empty[buf], ((job >> 1) & 1) ^ 1u);
           if (dm) dm[4] = clock64();
-          ptx::mbar_wait(u_full, it & 1);                 // both halves of u are in shared memory
-          ptx::tc_fence_after();
-          if (dm) dm[5] = clock64();
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * 256);
           for (int kb = 0; kb < 4; ++kb, ++kw) {
+            if ((kb & 1) == 0) {
+              // the first half of the residual GEMM (u k-blocks 0,1) only needs the FIRST gate epilogue, which finished while
+              // the second gate job was running; only k-blocks 2,3 wait for the second gate epilogue
+              ptx::mbar_wait(&u_full[kb >> 1], it & 1);
+              ptx::tc_fence_after();
+              if (dm && kb == 2) dm[5] = clock64();
+            }
             const int s = kw % WS;
             ptx::mbar_wait(&w_full[s], (kw / WS) & 1);
             ptx::tc_fence_after();
@@ -379,7 +383,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
         __syncwarp();
         if (lane == 0) {
           arrive_leader(&acc_empty[buf]);
-          arrive_leader(u_full);
+          arrive_leader(&u_full[half]);
         }
         if (de) de[half * 2 + 1] = clock64();             // gate epilogue of this half done
       }
