@@ -37,6 +37,7 @@ extern "C" {
 
 typedef struct fse_denoiser fse_denoiser;
 typedef struct fse_vocoder fse_vocoder;
+typedef struct fse_mel_encoder fse_mel_encoder;
 
 /* Hyper-parameters of DiffNet (diffnet.py:84-108) as read from egs/spec_denoiser.yaml:76-81,128. */
 typedef struct fse_denoiser_config {
@@ -144,6 +145,28 @@ int fse_vocoder_forward(fse_vocoder* h, const float* mel, float* wav, int32_t B,
 /* Host-buffer convenience (HifiGAN.spec2wav, tasks/tts/vocoder_infer/hifigan.py:23-31) */
 int fse_vocoder_forward_host(fse_vocoder* h, const float* mel, float* wav, int32_t B, int32_t T);
 int64_t fse_vocoder_last_launches(const fse_vocoder* h);
+
+/* --- MelEncoder (modules/speech_editing/commons/mel_encoder.py:3-19) ----------------------------
+ * The context-mel branch of the condition: three Linear layers (ReLU after the first two) over
+ * x = ref_mels * (1 - time_mel_masks).  Weight names are the module's state_dict keys:
+ * encoder.0.{weight,bias}, encoder.2.{weight,bias}, fc_out.{weight,bias}. */
+typedef struct fse_mel_encoder_config {
+  int32_t n_mels;   /* audio_num_mel_bins, 80 */
+  int32_t hidden;   /* hidden_size, 192 (multiple of 32, <= 256) */
+  int32_t mode;     /* FSE_MODE_* */
+} fse_mel_encoder_config;
+/* replaces MelEncoder.__init__ (mel_encoder.py:4-13) */
+int fse_mel_encoder_create(const fse_mel_encoder_config* cfg, fse_mel_encoder** out);
+void fse_mel_encoder_destroy(fse_mel_encoder* h);
+/* replaces load_ckpt for the mel_encoder.* keys (utils/commons/ckpt_utils.py:26-66) */
+int fse_mel_encoder_load_weights(fse_mel_encoder* h, const fse_tensor* tensors, int32_t n);
+int64_t fse_mel_encoder_workspace_bytes(const fse_mel_encoder* h, int32_t B, int32_t T);
+/* replaces MelEncoder.forward (mel_encoder.py:15-19): x [B, T, n_mels] fp32 device -> out [B, T, hidden] fp32 device.
+ * With add / scale non-null it also performs the call site's arithmetic (spec_denoiser.py:162-164):
+ *   out = add + MelEncoder(x) * scale[b, t]      (add = decoder_inp [B, T, hidden], scale = tgt_nonpadding [B, T]) */
+int fse_mel_encoder_forward(fse_mel_encoder* h, const float* x, const float* add, const float* scale, float* out,
+                            int32_t B, int32_t T, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t fse_mel_encoder_last_launches(const fse_mel_encoder* h);
 
 /* --- kernel timing (opt-in) -------------------------------------------------------------------
  * When enabled, every kernel the handle launches is bracketed by CUDA events on the launch stream;

@@ -110,5 +110,34 @@ def main():
     print("hifigan", wav.shape, float(np.abs(wav).mean()), float(np.abs(wav).max()))
 
 
+def mel_encoder_fixture():
+    """MelEncoder.forward (mel_encoder.py:15-19) and its call site's arithmetic (spec_denoiser.py:162-164) from the
+    unmodified reference module: `python oracle/make_golden.py mel_encoder` writes only this fixture."""
+    os.makedirs(OUT, exist_ok=True)
+    refshim.install("egs/spec_denoiser.yaml", overrides="timesteps=10")
+    from modules.speech_editing.commons.mel_encoder import MelEncoder
+    sd = synth.mel_encoder_state_dict(SEED)
+    enc = MelEncoder(80, 192).eval()
+    enc.load_state_dict(to_torch(sd), strict=True)
+    B, T = 2, 72
+    ref, mask = synth.synthetic_ref_and_mask(SEED, B, T)
+    rs = np.random.RandomState(SEED + 3)
+    decoder_inp = rs.standard_normal((B, T, 192)).astype(np.float32)
+    nonpad = np.ones((B, T, 1), dtype=np.float32)
+    nonpad[1, 60:] = 0.0                                       # trailing padding frames of the second item (mel2ph == 0)
+    with torch.no_grad():
+        x = torch.from_numpy(ref) * (1 - torch.from_numpy(mask))
+        out = enc(x)
+        cond = torch.from_numpy(decoder_inp.copy())
+        cond += out * torch.from_numpy(nonpad)                  # spec_denoiser.py:164
+    np.savez_compressed(os.path.join(OUT, "mel_encoder.npz"), seed=SEED, B=B, T=T, decoder_inp=decoder_inp, nonpad=nonpad,
+                        out=out.numpy(), cond=cond.numpy())
+    print("mel_encoder", out.shape, float(np.abs(out.numpy()).mean()))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "mel_encoder":
+        mel_encoder_fixture()
+    else:
+        main()
+        mel_encoder_fixture()

@@ -30,6 +30,10 @@ class VocoderConfig(C.Structure):
                 ("resblock_dilations", (C.c_int32 * 3) * 4), ("mode", C.c_int32)]
 
 
+class MelEncoderConfig(C.Structure):
+    _fields_ = [("n_mels", C.c_int32), ("hidden", C.c_int32), ("mode", C.c_int32)]
+
+
 class Tensor(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.POINTER(C.c_float)), ("numel", C.c_int64)]
 
@@ -58,6 +62,12 @@ SIGNATURES = {
     "fse_vocoder_forward": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "fse_vocoder_forward_host": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32]),
     "fse_vocoder_last_launches": (C.c_int64, [_P]),
+    "fse_mel_encoder_create": (C.c_int, [C.POINTER(MelEncoderConfig), C.POINTER(_P)]),
+    "fse_mel_encoder_destroy": (None, [_P]),
+    "fse_mel_encoder_load_weights": (C.c_int, [_P, C.POINTER(Tensor), C.c_int32]),
+    "fse_mel_encoder_workspace_bytes": (C.c_int64, [_P, C.c_int32, C.c_int32]),
+    "fse_mel_encoder_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
+    "fse_mel_encoder_last_launches": (C.c_int64, [_P]),
     "fse_denoiser_profile": (C.c_int, [_P, C.c_int32]),
     "fse_denoiser_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "fse_vocoder_profile": (C.c_int, [_P, C.c_int32]),

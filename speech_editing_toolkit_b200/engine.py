@@ -240,3 +240,49 @@ class Vocoder:
         wav = np.empty((B, T * self.hop), dtype=np.float32)
         check(_lib.lib().fse_vocoder_forward_host(self._h, C.c_void_p(mel.ctypes.data), C.c_void_p(wav.ctypes.data), B, T))
         return wav
+
+
+
+class MelEncoderKernel:
+    """Handle of the context-mel encoder (fse_mel_encoder_*; mel_encoder.py:3-19)."""
+
+    def __init__(self, n_mels: int = 80, hidden: int = 192, mode="tc_bf16"):
+        cfg = _lib.MelEncoderConfig()
+        cfg.n_mels, cfg.hidden, cfg.mode = n_mels, hidden, MODES[mode]
+        self.cfg, self.mode, self.hidden = cfg, mode, hidden
+        self._h = C.c_void_p()
+        check(_lib.lib().fse_mel_encoder_create(C.byref(cfg), C.byref(self._h)))
+        self._ws = _Workspace()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _lib.lib().fse_mel_encoder_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd: Dict[str, object]):
+        arr, n, keep = _tensor_table(sd)
+        check(_lib.lib().fse_mel_encoder_load_weights(self._h, arr, n))
+        del keep
+
+    @property
+    def last_launches(self) -> int:
+        return int(_lib.lib().fse_mel_encoder_last_launches(self._h))
+
+    def forward(self, x: torch.Tensor, add: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x[B,T,M] fp32 cuda (= ref_mels * (1 - mask)) -> [B,T,hidden]; with add / scale: add + MelEncoder(x) * scale[B,T]."""
+        _need_cuda(x, add, scale)
+        B, T, M = x.shape
+        x = x.contiguous().float()
+        if add is not None:
+            add = add.contiguous().float()
+            assert add.shape == (B, T, self.hidden)
+        if scale is not None:
+            scale = scale.reshape(B, T).contiguous().float()
+        out = torch.empty(B, T, self.hidden, dtype=torch.float32, device=x.device)
+        nbytes = _lib.lib().fse_mel_encoder_workspace_bytes(self._h, B, T)
+        ws, nbytes = self._ws.get(nbytes, x.device)
+        check(_lib.lib().fse_mel_encoder_forward(self._h, _ptr(x), _ptr(add), _ptr(scale), _ptr(out), B, T, ws, nbytes, _stream()))
+        return out

@@ -2,7 +2,7 @@
 
   DiffNetB200            <-> modules/speech_editing/spec_denoiser/diffnet.py::DiffNet          (:84-132)
   GaussianDiffusionB200  <-> modules/speech_editing/spec_denoiser/spec_denoiser.py::GaussianDiffusion (:16-185)
-  MelEncoder             <-> modules/speech_editing/commons/mel_encoder.py::MelEncoder        (:3-19)
+  MelEncoderB200         <-> modules/speech_editing/commons/mel_encoder.py::MelEncoder        (:3-19)
 
 Same constructor arguments, same state_dict keys/shapes (reference checkpoints load unchanged), same
 forward() signatures and return values.  The nn.Modules only OWN the parameters; every forward goes
@@ -17,7 +17,7 @@ import torch
 from torch import nn
 
 from . import schedule as _schedule
-from .engine import Denoiser
+from .engine import Denoiser, MelEncoderKernel
 from .hparams import hparams as _global_hparams
 
 
@@ -83,16 +83,38 @@ class DiffNetB200(nn.Module):
         return x0[:, None, :, :]
 
 
-class MelEncoder(nn.Module):
-    """mel_encoder.py:3-19 — kept in torch (runs once per utterance; 'next' row f.1 of SURVEY §8)."""
+class MelEncoderB200(nn.Module):
+    """Drop-in for MelEncoder (mel_encoder.py:3-19): same constructor, state_dict keys (encoder.0 / encoder.2 / fc_out) and
+    forward(x[B,T,M]) -> [B,T,H].  The module only owns the parameters; forward runs three tensor-core GEMM launches behind
+    fse_mel_encoder_forward.  `fused(x, add, scale)` also performs the call site's `add + out * scale` (spec_denoiser.py:164)
+    in the last epilogue."""
 
-    def __init__(self, mel_bins=80, hidden_size=192):
+    def __init__(self, mel_bins=80, hidden_size=192, mode="tc_bf16"):
         super().__init__()
+        self.mel_bins, self.hidden_size, self.mode = mel_bins, hidden_size, mode
         self.encoder = nn.Sequential(nn.Linear(mel_bins, hidden_size), nn.ReLU(), nn.Linear(hidden_size, hidden_size), nn.ReLU())
         self.fc_out = nn.Linear(hidden_size, hidden_size)
+        self._engine: Optional[MelEncoderKernel] = None
+        self._engine_key = None
 
+    def engine(self) -> MelEncoderKernel:
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._engine is None or key != self._engine_key:
+            eng = MelEncoderKernel(self.mel_bins, self.hidden_size, self.mode)
+            eng.load_state_dict(self.state_dict())
+            self._engine, self._engine_key = eng, key
+        return self._engine
+
+    @torch.no_grad()
     def forward(self, x):
-        return self.fc_out(self.encoder(x))
+        return self.engine().forward(x)
+
+    @torch.no_grad()
+    def fused(self, x, add, scale):
+        return self.engine().forward(x, add, scale)
+
+
+MelEncoder = MelEncoderB200     # the name the reference uses
 
 
 class GaussianDiffusionB200(nn.Module):
@@ -110,7 +132,8 @@ class GaussianDiffusionB200(nn.Module):
         hp = _global_hparams if hparams is None else hparams
         self.denoise_fn = denoise_fn
         self.fs = fs
-        self.mel_encoder = mel_encoder if mel_encoder is not None else MelEncoder(out_dims, hp.get("hidden_size", 192))
+        self.mel_encoder = mel_encoder if mel_encoder is not None else MelEncoderB200(out_dims, hp.get("hidden_size", 192),
+                                                                                      hp.get("b200_mode", "tc_bf16"))
         self.mel_bins = out_dims
         self.time_scale = time_scale
         self.num_timesteps = int(timesteps)
@@ -131,15 +154,17 @@ class GaussianDiffusionB200(nn.Module):
 
     @classmethod
     def from_reference(cls, ref_model, mode: str = "tc_bf16"):
-        """Wrap an instantiated reference GaussianDiffusion: shares its fs / mel_encoder, copies denoise_fn weights."""
+        """Wrap an instantiated reference GaussianDiffusion: shares its fs, copies the denoise_fn / mel_encoder weights."""
         rd = ref_model.denoise_fn
         hp = dict(hidden_size=rd.params.encoder_hidden, residual_layers=rd.params.residual_layers,
                   residual_channels=rd.params.residual_channels, dilation_cycle_length=rd.params.dilation_cycle_length,
                   b200_mode=mode, keep_bins=ref_model.mel_bins)
         den = DiffNetB200(ref_model.mel_bins, hp)
         den.load_state_dict(rd.state_dict())
+        enc = MelEncoderB200(ref_model.mel_bins, rd.params.encoder_hidden, mode)
+        enc.load_state_dict(ref_model.mel_encoder.state_dict())
         new = cls(None, ref_model.mel_bins, den, timesteps=ref_model.num_timesteps, time_scale=ref_model.time_scale,
-                  loss_type=ref_model.loss_type, fs=ref_model.fs, mel_encoder=ref_model.mel_encoder, hparams=hp)
+                  loss_type=ref_model.loss_type, fs=ref_model.fs, mel_encoder=enc, hparams=hp)
         for name, buf in ref_model.named_buffers(recurse=False):     # the reference's own float64-derived schedule, bit for bit
             if name in new._buffers:
                 new._buffers[name] = buf.detach().clone()
@@ -191,7 +216,10 @@ class GaussianDiffusionB200(nn.Module):
                       use_pred_mel2ph=use_pred_mel2ph, use_pred_pitch=use_pred_pitch)
         decoder_inp = ret["decoder_inp"]
         tgt_nonpadding = (mel2ph > 0).float()[:, :, None]
-        decoder_inp = decoder_inp + self.mel_encoder(ref_mels * (1 - time_mel_masks)) * tgt_nonpadding
+        if isinstance(self.mel_encoder, MelEncoderB200):     # add + MelEncoder(x) * nonpadding in the last GEMM's epilogue
+            decoder_inp = self.mel_encoder.fused(ref_mels * (1 - time_mel_masks), decoder_inp, tgt_nonpadding)
+        else:
+            decoder_inp = decoder_inp + self.mel_encoder(ref_mels * (1 - time_mel_masks)) * tgt_nonpadding
         ret["decoder_inp"] = decoder_inp
         if seed is None:
             seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())      # follows torch.manual_seed like the reference's randn

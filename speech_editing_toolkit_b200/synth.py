@@ -84,6 +84,28 @@ def hifigan_state_dict(seed: int = 1234, config: dict = None, n_mels: int = 80) 
     return sd
 
 
+def mel_encoder_state_dict(seed: int = 1234, n_mels: int = 80, hidden: int = 192) -> Dict[str, np.ndarray]:
+    """Random MelEncoder state_dict (mel_encoder.py:4-13): encoder.0 / encoder.2 / fc_out Linear layers."""
+    rs = np.random.RandomState(seed + 29)
+    sd: Dict[str, np.ndarray] = {}
+    for name, (n, c) in (("encoder.0", (hidden, n_mels)), ("encoder.2", (hidden, hidden)), ("fc_out", (hidden, hidden))):
+        sd[name + ".weight"] = (rs.standard_normal((n, c)) / math.sqrt(c)).astype(F32)
+        sd[name + ".bias"] = (rs.standard_normal((n,)) * 0.1).astype(F32)
+    return sd
+
+
+def synthetic_ref_and_mask(seed: int, B: int, T: int, n_mels: int = 80):
+    """ref_mels ~ clip(N(-3, 1.5), -6, 1.5) and a contiguous 30 % edit span per item."""
+    rs = np.random.RandomState(seed + 31)
+    ref = np.clip(rs.standard_normal((B, T, n_mels)) * 1.5 - 3.0, -6.0, 1.5).astype(F32)
+    mask = np.zeros((B, T, 1), dtype=F32)
+    for b in range(B):
+        n = max(1, int(round(0.3 * T)))
+        s0 = int(rs.randint(0, T - n + 1))
+        mask[b, s0:s0 + n] = 1.0
+    return ref, mask
+
+
 def synthetic_cond(seed: int, B: int, T: int, hidden: int = 192) -> np.ndarray:
     """Stand-in for the condition-encoder output decoder_inp[B,T,H] (spec_denoiser.py:159-167)."""
     rs = np.random.RandomState(seed + 17)

@@ -269,3 +269,45 @@ def test_hifigan_other_resblock_counts(lib_built, kernels):
     wav = vtc.forward(cu(mel)).cpu().numpy()
     assert wav.shape == (2, 150 * 8) and np.isfinite(wav).all()
     assert rel_l1(wav, ref) < 3e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["simt_f32", "tc_bf16"])
+def test_mel_encoder_vs_reference_fixture(lib_built, mode):
+    """fse_mel_encoder_forward against the unmodified reference MelEncoder (tests/golden/mel_encoder.npz), plain and with
+    the call site's `decoder_inp + out * tgt_nonpadding` fused into the last epilogue (spec_denoiser.py:162-164)."""
+    from speech_editing_toolkit_b200 import synth
+    from speech_editing_toolkit_b200.engine import MelEncoderKernel
+    g = golden("mel_encoder.npz")
+    B, T = int(g["B"]), int(g["T"])
+    enc = MelEncoderKernel(80, 192, mode=mode)
+    enc.load_state_dict(synth.mel_encoder_state_dict(int(g["seed"])))
+    ref, mask = synth.synthetic_ref_and_mask(int(g["seed"]), B, T)
+    x = cu(ref * (1 - mask))
+    out = enc.forward(x).cpu().numpy()
+    cond = enc.forward(x, cu(g["decoder_inp"]), cu(g["nonpad"])).cpu().numpy()
+    assert enc.last_launches == (3 if mode == "simt_f32" else 4)
+    if mode == "simt_f32":
+        assert np.abs(out - g["out"]).max() < TOL_F32_ABS
+        assert np.abs(cond - g["cond"]).max() < TOL_F32_ABS
+    else:
+        assert rel_l1(out, g["out"]) < 1e-2
+        assert rel_l1(cond, g["cond"]) < 1e-2
+    assert np.array_equal(cond[1, 60:], g["decoder_inp"][1, 60:])      # padding frames: decoder_inp bit for bit
+
+
+@pytest.mark.gpu
+def test_mel_encoder_module_matches_oracle_on_batch(lib_built):
+    """The nn.Module drop-in (same state_dict keys as the reference MelEncoder) on a ragged multi-tile batch."""
+    from oracle import fluentspeech_oracle as O
+    from speech_editing_toolkit_b200 import synth
+    from speech_editing_toolkit_b200.modules import MelEncoderB200
+    sd = synth.mel_encoder_state_dict(5)
+    m = MelEncoderB200(80, 192).cuda()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    assert sorted(m.state_dict()) == sorted(sd)
+    ref, mask = synth.synthetic_ref_and_mask(6, 3, 333)
+    x = ref * (1 - mask)
+    out = m(cu(x)).cpu().numpy()
+    assert out.shape == (3, 333, 192)
+    assert rel_l1(out, O.mel_encoder_forward(sd, x)) < 1e-2

@@ -83,7 +83,11 @@ def test_state_dict_keys_match_live_reference_modules():
     for k in rsd:
         if not k.startswith(("fs.", "mel_encoder.", "denoise_fn.")):
             assert torch.equal(rsd[k], osd[k]), k
-    assert wrapped.fs is ref.fs and wrapped.mel_encoder is ref.mel_encoder
+    assert wrapped.fs is ref.fs                                      # the condition encoder is shared ...
+    from speech_editing_toolkit_b200.modules import MelEncoderB200
+    assert isinstance(wrapped.mel_encoder, MelEncoderB200)           # ... the context-mel encoder is the native drop-in
+    for k, v in ref.mel_encoder.state_dict().items():
+        assert torch.equal(v, wrapped.mel_encoder.state_dict()[k]), k
 
 
 def test_registries_and_plugin_surface():

@@ -103,3 +103,16 @@ def test_oracle_against_live_reference_random_shapes():
         with torch.no_grad():
             ref = net(torch.from_numpy(x)[:, None], torch.from_numpy(t), torch.from_numpy(cond))[:, 0].numpy()
         assert np.abs(O.diffnet_forward(sd, x, t, cond) - ref).max() < 2e-5
+
+
+def test_mel_encoder_matches_reference_fixture():
+    """MelEncoder.forward and `decoder_inp += out * tgt_nonpadding` (mel_encoder.py:15-19, spec_denoiser.py:162-164)."""
+    from speech_editing_toolkit_b200 import synth
+    g = golden("mel_encoder.npz")
+    sd = synth.mel_encoder_state_dict(int(g["seed"]))
+    ref, mask = synth.synthetic_ref_and_mask(int(g["seed"]), int(g["B"]), int(g["T"]))
+    out = O.mel_encoder_forward(sd, ref * (1 - mask))
+    assert np.abs(out - g["out"]).max() < 2e-5
+    cond = g["decoder_inp"] + out * g["nonpad"]
+    assert np.abs(cond - g["cond"]).max() < 2e-5
+    assert np.array_equal(cond[1, 60:], g["decoder_inp"][1, 60:])      # padding frames keep decoder_inp bit for bit
