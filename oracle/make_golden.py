@@ -135,9 +135,85 @@ def mel_encoder_fixture():
     print("mel_encoder", out.shape, float(np.abs(out.numpy()).mean()))
 
 
+def cond_encoder_fixture():
+    """FastSpeech.forward(skip_decoder=True) (fs.py:83-105), its parts as the inference script calls them
+    (inference/tts/spec_denoiser.py:84-98: encoder, forward_style_embed, forward_dur with masked_dur + LengthRegulator) and
+    the whole GaussianDiffusion.forward(infer=True) (spec_denoiser.py:154-185) from the unmodified reference on a ragged
+    batch: `python oracle/make_golden.py cond_encoder` writes tests/golden/cond_encoder.npz and fluentspeech_e2e.npz."""
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(SEED)
+    hp = refshim.install("egs/spec_denoiser.yaml", overrides="timesteps=4")
+    from modules.speech_editing.spec_denoiser.fs import FastSpeech
+    from modules.speech_editing.spec_denoiser.diffnet import DiffNet
+    from modules.speech_editing.spec_denoiser import spec_denoiser as sdmod
+    from utils.audio.pitch.utils import f0_to_coarse
+    vocab = 80
+    fs = FastSpeech(vocab, hp).eval()
+    fsd = synth.fastspeech_state_dict(SEED, vocab)
+    missing, unexpected = fs.load_state_dict(to_torch(fsd), strict=False)
+    assert not unexpected and all(k.startswith(("decoder.", "mel_out.")) for k in missing), (missing, unexpected)
+    B, T = 2, 80
+    batch = synth.pad_edit_batch(synth.synthetic_edit_batch(SEED, B, T, vocab=vocab), item=1, n_tokens=3)
+    tb = {k: torch.from_numpy(v) for k, v in batch.items()}
+    mask3 = tb["time_mel_masks"][:, :, None]
+    out = dict(seed=SEED, B=B, T=T, vocab=vocab)
+    with torch.no_grad():
+        out["encoder_out"] = fs.encoder(tb["txt_tokens"]).numpy()
+        out["style_embed"] = fs.forward_style_embed(tb["spk_embed"], None).numpy()
+        for flag in (False, True):
+            ret = fs(tb["txt_tokens"], mask3, tb["mel2ph"], tb["spk_embed"], tb["f0"], tb["uv"], skip_decoder=True, infer=True,
+                     use_pred_pitch=flag)
+            sfx = "_predpitch" if flag else ""
+            for k in ("decoder_inp", "dur", "pitch_pred", "f0_denorm", "f0_denorm_pred", "mel2ph"):
+                out[k + sfx] = ret[k].numpy()
+            out["pitch" + sfx] = f0_to_coarse(ret["f0_denorm"]).numpy()
+        # the inference script's use of forward_dur: explicit masked_dur, predicted mel2ph (LengthRegulator)
+        src_nonpadding = (tb["txt_tokens"] > 0).float()[:, :, None]
+        dur_inp = (torch.from_numpy(out["encoder_out"]) + torch.from_numpy(out["style_embed"])) * src_nonpadding
+        masked_dur = torch.from_numpy(np.random.RandomState(SEED + 7).randint(0, 12, size=batch["txt_tokens"].shape)) * (tb["txt_tokens"] > 0)
+        r2 = {}
+        mel2ph_pred = fs.forward_dur(dur_inp, tb["time_mel_masks"], tb["mel2ph"].clone(), tb["txt_tokens"], r2, masked_dur=masked_dur,
+                                     use_pred_mel2ph=True)
+        out["masked_dur_in"] = masked_dur.numpy()
+        out["dur_masked_dur"] = r2["dur"].numpy()
+        out["mel2ph_pred"] = mel2ph_pred.numpy()
+    np.savez_compressed(os.path.join(OUT, "cond_encoder.npz"), **out)
+    print("cond_encoder", out["decoder_inp"].shape, float(np.abs(out["decoder_inp"]).mean()), "dur", out["dur"][0, :6],
+          "mel2ph_pred", out["mel2ph_pred"].shape, "pitch bins", np.unique(out["pitch_predpitch"]).size)
+
+    # ---- whole model, S = 4, noise injected (x_S via torch.randn, per-step draws via noise_like) ----
+    S, L = 4, 4
+    from utils.commons.hparams import hparams as ref_hparams      # DiffNet reads the module-global dict (diffnet.py:9,89-92)
+    ref_hparams["residual_layers"] = hp["residual_layers"] = L
+    net = DiffNet(hp["audio_num_mel_bins"]).eval()
+    net.load_state_dict(to_torch(synth.denoiser_state_dict(SEED, layers=L)), strict=True)
+    model = sdmod.GaussianDiffusion(phone_encoder=list(range(vocab)), out_dims=80, denoise_fn=net, timesteps=S,
+                                    time_scale=hp["timescale"], loss_type=hp["diff_loss_type"], spec_min=hp["spec_min"],
+                                    spec_max=hp["spec_max"]).eval()
+    model.fs.load_state_dict(to_torch(fsd), strict=False)
+    model.mel_encoder.load_state_dict(to_torch(synth.mel_encoder_state_dict(SEED)), strict=True)
+    noise = synth.synthetic_noise(SEED + 5, S, B, T)
+    draws = iter(torch.from_numpy(noise[1:]))
+    orig_nl, orig_randn = sdmod.noise_like, torch.randn
+    sdmod.noise_like = lambda shape, device, repeat=False: next(draws)[:, None]
+    torch.randn = lambda *a, **k: torch.from_numpy(noise[0])[:, None]
+    try:
+        with torch.no_grad():
+            ret = model(tb["txt_tokens"], mask3, tb["mel2ph"], tb["spk_embed"], tb["ref_mels"], tb["f0"], tb["uv"], infer=True,
+                        use_pred_pitch=True)
+    finally:
+        sdmod.noise_like, torch.randn = orig_nl, orig_randn
+    np.savez_compressed(os.path.join(OUT, "fluentspeech_e2e.npz"), seed=SEED, B=B, T=T, S=S, layers=L, vocab=vocab,
+                        mel_out=ret["mel_out"].numpy(), decoder_inp=ret["decoder_inp"].numpy(), dur=ret["dur"].numpy())
+    print("fluentspeech_e2e", ret["mel_out"].shape, float(np.abs(ret["mel_out"].numpy()).mean()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "mel_encoder":
         mel_encoder_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "cond_encoder":
+        cond_encoder_fixture()
     else:
         main()
         mel_encoder_fixture()
+        cond_encoder_fixture()

@@ -136,3 +136,75 @@ def synthetic_edit_batch(seed: int, B: int, T: int, n_mels: int = 80, vocab: int
     uv = (rs.uniform(size=(B, T)) < 0.3).astype(F32)
     spk = (rs.standard_normal((B, 256)) / 16).astype(F32)
     return dict(txt_tokens=txt, mel2ph=mel2ph, ref_mels=ref, time_mel_masks=mask, f0=f0, uv=uv, spk_embed=spk)
+
+
+FS_DEFAULTS = dict(hidden_size=192, enc_dilations=[1, 1, 1, 1], enc_kernel_size=5, layers_in_block=2, enc_post_net_kernel=3,
+                   dur_predictor_layers=3, dur_predictor_kernel=5, predictor_kernel=5, pitch_predictor_layers=5,
+                   use_pitch_embed=True, use_uv=True, pitch_type="frame", use_spk_embed=True, frames_multiple=1)
+
+
+def fastspeech_state_dict(seed: int = 1234, vocab: int = 80, hp: dict = None) -> Dict[str, np.ndarray]:
+    """Random `fs.*` state_dict (keys without the `fs.` prefix) of the condition encoder as the hot path uses it
+    (fs.py:49-82 with encoder_type 'conv'): TextConvEncoder, spk_embed_proj, dur_embed / dur_predictor, pitch_embed /
+    pitch_predictor.  The unused `decoder.*` / `mel_out.*` entries (skip_decoder=True) are not generated.
+    LayerNorm affine parameters and all biases are randomised so that parity checks are not vacuous; the predictor heads
+    are biased so that durations round to 1-4 frames and predicted log2-f0 lands in the voiced range."""
+    hp = {**FS_DEFAULTS, **(hp or {})}
+    rs = np.random.RandomState(seed + 53)
+    H = hp["hidden_size"]
+    sd: Dict[str, np.ndarray] = {}
+
+    def conv(name, co, ci, k, gain=1.0):
+        sd[name + ".weight"] = (rs.standard_normal((co, ci, k)) * (gain / math.sqrt(ci * k))).astype(F32)
+        sd[name + ".bias"] = (rs.standard_normal((co,)) * 0.1).astype(F32)
+
+    def ln(name, c):
+        sd[name + ".weight"] = (1.0 + 0.1 * rs.standard_normal((c,))).astype(F32)
+        sd[name + ".bias"] = (0.1 * rs.standard_normal((c,))).astype(F32)
+
+    def emb(name, n, c):
+        w = (rs.standard_normal((n, c)) * c ** -0.5).astype(F32)
+        w[0] = 0.0                                                      # padding_idx = 0 (layers.py:45-50)
+        sd[name + ".weight"] = w
+
+    k = hp["enc_kernel_size"]
+    for i in range(len(hp["enc_dilations"])):
+        for j in range(hp["layers_in_block"]):
+            p = f"encoder.res_blocks.{i}.blocks.{j}."
+            ln(p + "0", H)
+            conv(p + "1", 2 * H, H, k, gain=1.6)
+            conv(p + "4", H, 2 * H, 1)
+    ln("encoder.last_norm", H)
+    conv("encoder.post_net1", H, H, hp["enc_post_net_kernel"])
+    emb("encoder.embed_tokens", vocab, H)
+    sd["spk_embed_proj.weight"] = (rs.standard_normal((H, 256)) / 16.0).astype(F32)
+    sd["spk_embed_proj.bias"] = (rs.standard_normal((H,)) * 0.1).astype(F32)
+    emb("dur_embed", 2000, H)
+    for i in range(hp["dur_predictor_layers"]):
+        conv(f"dur_predictor.conv.{i}.0", H, H, hp["dur_predictor_kernel"], gain=1.4)
+        ln(f"dur_predictor.conv.{i}.2", H)
+    sd["dur_predictor.linear.0.weight"] = (rs.standard_normal((1, H)) * (0.8 / math.sqrt(H))).astype(F32)
+    sd["dur_predictor.linear.0.bias"] = np.array([2.0], dtype=F32)
+    if hp["use_pitch_embed"]:
+        emb("pitch_embed", 300, H)
+        for i in range(hp["pitch_predictor_layers"]):
+            conv(f"pitch_predictor.conv.{i}.0", H, H, hp["predictor_kernel"], gain=1.4)
+            ln(f"pitch_predictor.conv.{i}.2", H)
+        sd["pitch_predictor.linear.weight"] = (rs.standard_normal((2, H)) * (0.7 / math.sqrt(H))).astype(F32)
+        sd["pitch_predictor.linear.bias"] = np.array([7.5, 0.0], dtype=F32)
+    return sd
+
+
+def pad_edit_batch(batch: dict, item: int, n_tokens: int, frames_per_phone: int = 8) -> dict:
+    """Turn the tail of one item into padding (txt token 0, mel2ph 0) as collated ragged batches have it
+    (tasks/speech_editing/dataset_utils.py:148-170): the last `n_tokens` phones and their frames."""
+    out = {k: v.copy() for k, v in batch.items()}
+    Tt = out["txt_tokens"].shape[1]
+    keep = Tt - n_tokens
+    out["txt_tokens"][item, keep:] = 0
+    pad = out["mel2ph"][item] > keep
+    out["mel2ph"][item, pad] = 0
+    for k in ("time_mel_masks", "f0", "uv"):
+        out[k][item, pad] = 0
+    out["ref_mels"][item, pad] = 0
+    return out
