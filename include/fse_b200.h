@@ -168,6 +168,81 @@ int fse_mel_encoder_forward(fse_mel_encoder* h, const float* x, const float* add
                             int32_t B, int32_t T, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t fse_mel_encoder_last_launches(const fse_mel_encoder* h);
 
+/* --- condition encoder: FastSpeech.forward(skip_decoder=True) --------------------------------------
+ * modules/speech_editing/spec_denoiser/fs.py:49-189 with encoder_type 'conv' (egs/spec_denoiser.yaml:105-137):
+ * TextConvEncoder (modules/commons/conv.py:24-139), spk_embed_proj, dur_embed + DurationPredictor + LengthRegulator
+ * (modules/commons/nar_tts_modules.py:8-72), expand_states (modules/tts/commons/align_ops.py:21-25), pitch_embed +
+ * PitchPredictor (nar_tts_modules.py:75-100), f0_to_coarse / denorm_f0 (utils/audio/pitch/utils.py:17-28,71-82),
+ * mel2token_to_dur (utils/audio/align.py:71-90).  Runs once per batch in front of the sampling loop.
+ * The entry points are the pieces the reference itself calls separately (fs.py:83-105 in order; the inference script
+ * calls encoder / forward_style_embed / forward_dur on their own, inference/tts/spec_denoiser.py:84-98).
+ * Weight names are the reference's `fs.*` state_dict keys without the `fs.` prefix; the
+ * unused `decoder.*` / `mel_out.*` entries are ignored.  All tensors are device pointers, integer tensors int64.
+ * Every Conv1d is a tensor-core conv-GEMM launch (bf16 operands, fp32 accumulate; fp32 CUDA cores in FSE_MODE_SIMT_F32);
+ * LayerNorm / GELU / embedding adds / the 192->1 and 192->2 heads / the integer ops are fp32 / int64 CUDA-core kernels. */
+typedef struct fse_cond_encoder fse_cond_encoder;
+typedef struct fse_cond_encoder_config {
+  int32_t hidden;                  /* hidden_size, 192 (multiple of 64, <= 512) */
+  int32_t vocab;                   /* rows of encoder.embed_tokens (len(phone_encoder)) */
+  int32_t enc_layers;              /* len(enc_dilations), <= 8 */
+  int32_t enc_dilations[8];        /* enc_dilations, shipped: 1,1,1,1 */
+  int32_t enc_kernel_size;         /* 5 (odd) */
+  int32_t layers_in_block;         /* 2 */
+  int32_t enc_post_net_kernel;     /* 3 */
+  int32_t dur_predictor_layers;    /* 3 */
+  int32_t dur_predictor_kernel;    /* 5 */
+  int32_t pitch_predictor_layers;  /* 5 (fs.py:76) */
+  int32_t predictor_kernel;        /* 5 */
+  int32_t use_pitch_embed;         /* egs/spec_denoiser.yaml: 1; egs/spec_denoiser_libritts.yaml: 0 */
+  int32_t use_uv;                  /* pitch_type == 'frame' and use_uv (fs.py:156) */
+  int32_t spk_embed_dim;           /* 256 with use_spk_embed, 0 without */
+  int32_t mode;                    /* FSE_MODE_* */
+} fse_cond_encoder_config;
+
+/* replaces FastSpeech.__init__ (fs.py:49-82) */
+int fse_cond_encoder_create(const fse_cond_encoder_config* cfg, fse_cond_encoder** out);
+void fse_cond_encoder_destroy(fse_cond_encoder* h);
+/* replaces load_ckpt for the `fs.*` keys (utils/commons/ckpt_utils.py:26-66) */
+int fse_cond_encoder_load_weights(fse_cond_encoder* h, const fse_tensor* tensors, int32_t n);
+/* workspace for a batch of B items, Tt tokens and T frames each (any of the calls below) */
+int64_t fse_cond_encoder_workspace_bytes(const fse_cond_encoder* h, int32_t B, int32_t Tt, int32_t T);
+int64_t fse_cond_encoder_last_launches(const fse_cond_encoder* h);
+
+/* replaces TextConvEncoder.forward (conv.py:130-139 -> :99-116): txt [B,Tt] int64 -> encoder_out [B,Tt,hidden] fp32 */
+int fse_cond_text_encoder(fse_cond_encoder* h, const int64_t* txt, float* encoder_out, int32_t B, int32_t Tt, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+/* replaces FastSpeech.forward_style_embed (fs.py:114-121): spk_embed [B,spk_embed_dim] -> style [B,hidden] */
+int fse_cond_style_embed(fse_cond_encoder* h, const float* spk_embed, float* style, int32_t B, void* stream);
+/* fs.py:90 / inference/tts/spec_denoiser.py:93: dur_inp = (encoder_out + style) * (txt > 0); style may be NULL */
+int fse_cond_dur_input(fse_cond_encoder* h, const float* encoder_out, const float* style, const int64_t* txt, float* dur_inp,
+                       int32_t B, int32_t Tt, void* stream);
+/* fs.py:136-138 (integer, bit-exact): masked_dur = mel2token_to_dur(mel2ph * (1 - mask).long(), Tt) * (txt != 0)
+ * mel2ph [B,T] int64, mask [B,T] fp32 0/1 (NULL = no mask), masked_dur [B,Tt] int64 (out) */
+int fse_cond_masked_dur(fse_cond_encoder* h, const int64_t* mel2ph, const float* mask, const int64_t* txt, int64_t* masked_dur,
+                        int32_t B, int32_t T, int32_t Tt, void* stream);
+/* replaces the rest of FastSpeech.forward_dur (fs.py:139-148): dur = DurationPredictor(dur_inp + dur_embed(masked_dur),
+ * txt == 0) (nar_tts_modules.py:24-34); dur [B,Tt] fp32 (out) */
+int fse_cond_duration(fse_cond_encoder* h, const float* dur_inp, const int64_t* masked_dur, const int64_t* txt, float* dur,
+                      int32_t B, int32_t Tt, void* workspace, int64_t workspace_bytes, void* stream);
+/* replaces LengthRegulator.forward (nar_tts_modules.py:42-72), alpha = 1, in two calls because the output length is data
+ * dependent (the reference synchronises on dur.sum(-1).max() too):
+ *   _cumsum: cumsum [B,Tt] int64 = cumsum(round_half_even(dur) * (txt != 0)), totals [B] int64 = frames per item
+ *   _fill:   mel2ph [B,Tmax] int64: 1-based token index of every frame, 0 past an item's end (Tmax >= max(totals)) */
+int fse_cond_length_cumsum(fse_cond_encoder* h, const float* dur, const int64_t* txt, int64_t* cumsum, int64_t* totals, int32_t B,
+                           int32_t Tt, void* stream);
+int fse_cond_length_fill(fse_cond_encoder* h, const int64_t* cumsum, int64_t* mel2ph, int32_t B, int32_t Tt, int32_t Tmax,
+                         void* stream);
+/* replaces fs.py:93-102: tgt_nonpadding, expand_states, forward_pitch (fs.py:153-189) and the final
+ * decoder_inp = (expand(encoder_out) [+ pitch_embed] + style) * (mel2ph > 0).
+ *   encoder_out [B,Tt,hidden], style [B,hidden] or NULL, mel2ph [B,T] int64, mask [B,T] fp32 0/1 (time_mel_masks),
+ *   f0 / uv [B,T] fp32 (ignored without use_pitch_embed), use_pred_pitch as the reference flag
+ *   out: decoder_inp [B,T,hidden]; with use_pitch_embed also pitch_pred [B,T,2], f0_denorm [B,T], f0_denorm_pred [B,T]
+ *        and (optional, may be NULL) pitch [B,T] int64 = f0_to_coarse(f0_denorm), the embedded bins */
+int fse_cond_frames(fse_cond_encoder* h, const float* encoder_out, const float* style, const int64_t* mel2ph, const float* mask,
+                    const float* f0, const float* uv, int32_t use_pred_pitch, float* decoder_inp, float* pitch_pred,
+                    float* f0_denorm, float* f0_denorm_pred, int64_t* pitch, int32_t B, int32_t Tt, int32_t T, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+
 /* --- kernel timing (opt-in) -------------------------------------------------------------------
  * When enabled, every kernel the handle launches is bracketed by CUDA events on the launch stream;
  * *_profile_read waits for them and returns the summed device time (ms) and launch count per kind

@@ -34,6 +34,14 @@ class MelEncoderConfig(C.Structure):
     _fields_ = [("n_mels", C.c_int32), ("hidden", C.c_int32), ("mode", C.c_int32)]
 
 
+class CondEncoderConfig(C.Structure):
+    _fields_ = [("hidden", C.c_int32), ("vocab", C.c_int32), ("enc_layers", C.c_int32), ("enc_dilations", C.c_int32 * 8),
+                ("enc_kernel_size", C.c_int32), ("layers_in_block", C.c_int32), ("enc_post_net_kernel", C.c_int32),
+                ("dur_predictor_layers", C.c_int32), ("dur_predictor_kernel", C.c_int32), ("pitch_predictor_layers", C.c_int32),
+                ("predictor_kernel", C.c_int32), ("use_pitch_embed", C.c_int32), ("use_uv", C.c_int32),
+                ("spk_embed_dim", C.c_int32), ("mode", C.c_int32)]
+
+
 class Tensor(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.POINTER(C.c_float)), ("numel", C.c_int64)]
 
@@ -68,6 +76,20 @@ SIGNATURES = {
     "fse_mel_encoder_workspace_bytes": (C.c_int64, [_P, C.c_int32, C.c_int32]),
     "fse_mel_encoder_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "fse_mel_encoder_last_launches": (C.c_int64, [_P]),
+    "fse_cond_encoder_create": (C.c_int, [C.POINTER(CondEncoderConfig), C.POINTER(_P)]),
+    "fse_cond_encoder_destroy": (None, [_P]),
+    "fse_cond_encoder_load_weights": (C.c_int, [_P, C.POINTER(Tensor), C.c_int32]),
+    "fse_cond_encoder_workspace_bytes": (C.c_int64, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "fse_cond_encoder_last_launches": (C.c_int64, [_P]),
+    "fse_cond_text_encoder": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
+    "fse_cond_style_embed": (C.c_int, [_P, _P, _P, C.c_int32, _P]),
+    "fse_cond_dur_input": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "fse_cond_masked_dur": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "fse_cond_duration": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
+    "fse_cond_length_cumsum": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P]),
+    "fse_cond_length_fill": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "fse_cond_frames": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,
+                                  _P, C.c_int64, _P]),
     "fse_denoiser_profile": (C.c_int, [_P, C.c_int32]),
     "fse_denoiser_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "fse_vocoder_profile": (C.c_int, [_P, C.c_int32]),

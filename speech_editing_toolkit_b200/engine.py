@@ -286,3 +286,160 @@ class MelEncoderKernel:
         ws, nbytes = self._ws.get(nbytes, x.device)
         check(_lib.lib().fse_mel_encoder_forward(self._h, _ptr(x), _ptr(add), _ptr(scale), _ptr(out), B, T, ws, nbytes, _stream()))
         return out
+
+
+class CondEncoderKernel:
+    """Handle of the condition encoder (fse_cond_*; FastSpeech.forward(skip_decoder=True), fs.py:83-189).  One method per
+    C-ABI entry point; every tensor stays on the device and integer tensors are int64 as in the reference."""
+
+    def __init__(self, vocab: int, hidden: int = 192, enc_dilations=(1, 1, 1, 1), enc_kernel_size: int = 5, layers_in_block: int = 2,
+                 enc_post_net_kernel: int = 3, dur_predictor_layers: int = 3, dur_predictor_kernel: int = 5,
+                 pitch_predictor_layers: int = 5, predictor_kernel: int = 5, use_pitch_embed: bool = True, use_uv: bool = True,
+                 spk_embed_dim: int = 256, mode="tc_bf16"):
+        cfg = _lib.CondEncoderConfig()
+        cfg.hidden, cfg.vocab, cfg.enc_layers = hidden, vocab, len(enc_dilations)
+        if len(enc_dilations) > 8:
+            raise FseError("at most 8 encoder blocks (enc_dilations)")
+        for i, d in enumerate(enc_dilations):
+            cfg.enc_dilations[i] = int(d)
+        cfg.enc_kernel_size, cfg.layers_in_block, cfg.enc_post_net_kernel = enc_kernel_size, layers_in_block, enc_post_net_kernel
+        cfg.dur_predictor_layers, cfg.dur_predictor_kernel = dur_predictor_layers, dur_predictor_kernel
+        cfg.pitch_predictor_layers, cfg.predictor_kernel = pitch_predictor_layers, predictor_kernel
+        cfg.use_pitch_embed, cfg.use_uv, cfg.spk_embed_dim, cfg.mode = int(use_pitch_embed), int(use_uv), spk_embed_dim, MODES[mode]
+        self.cfg, self.mode, self.hidden, self.use_pitch_embed = cfg, mode, hidden, bool(use_pitch_embed)
+        self._h = C.c_void_p()
+        check(_lib.lib().fse_cond_encoder_create(C.byref(cfg), C.byref(self._h)))
+        self._ws = _Workspace()
+        self.launches = 0          # kernels enqueued since the last reset_launches()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _lib.lib().fse_cond_encoder_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd: Dict[str, object]):
+        """`fs.*` entries of a reference checkpoint without the prefix; decoder.* / mel_out.* (unused with skip_decoder) are skipped."""
+        sd = {k: v for k, v in sd.items() if not k.startswith(("decoder.", "mel_out."))}
+        arr, n, keep = _tensor_table(sd)
+        check(_lib.lib().fse_cond_encoder_load_weights(self._h, arr, n))
+        del keep
+
+    def reset_launches(self):
+        self.launches = 0
+
+    def _done(self):
+        self.launches += int(_lib.lib().fse_cond_encoder_last_launches(self._h))
+
+    def _workspace(self, B, Tt, T, device):
+        nbytes = _lib.lib().fse_cond_encoder_workspace_bytes(self._h, B, Tt, T)
+        return self._ws.get(nbytes, device)
+
+    @staticmethod
+    def _i64(t):
+        return t.contiguous().long()
+
+    @staticmethod
+    def _f32(t):
+        return None if t is None else t.contiguous().float()
+
+    def text_encoder(self, txt: torch.Tensor) -> torch.Tensor:
+        """txt[B,Tt] int64 -> encoder_out[B,Tt,H]   (TextConvEncoder.forward, conv.py:130-139)"""
+        _need_cuda(txt)
+        B, Tt = txt.shape
+        txt = self._i64(txt)
+        out = torch.empty(B, Tt, self.hidden, dtype=torch.float32, device=txt.device)
+        ws, nbytes = self._workspace(B, Tt, 0, txt.device)
+        check(_lib.lib().fse_cond_text_encoder(self._h, _ptr(txt), _ptr(out), B, Tt, ws, nbytes, _stream()))
+        self._done()
+        return out
+
+    def style_embed(self, spk_embed: torch.Tensor) -> torch.Tensor:
+        """spk_embed[B,D] -> [B,H]   (fs.py:117-118)"""
+        _need_cuda(spk_embed)
+        spk_embed = self._f32(spk_embed)
+        B = spk_embed.shape[0]
+        out = torch.empty(B, self.hidden, dtype=torch.float32, device=spk_embed.device)
+        check(_lib.lib().fse_cond_style_embed(self._h, _ptr(spk_embed), _ptr(out), B, _stream()))
+        self._done()
+        return out
+
+    def dur_input(self, encoder_out, style, txt) -> torch.Tensor:
+        """(encoder_out + style) * (txt > 0)   (fs.py:90)"""
+        _need_cuda(encoder_out, style, txt)
+        B, Tt, _ = encoder_out.shape
+        encoder_out, style, txt = self._f32(encoder_out), self._f32(style), self._i64(txt)
+        out = torch.empty_like(encoder_out)
+        check(_lib.lib().fse_cond_dur_input(self._h, _ptr(encoder_out), _ptr(style), _ptr(txt), _ptr(out), B, Tt, _stream()))
+        self._done()
+        return out
+
+    def masked_dur(self, mel2ph, mask, txt) -> torch.Tensor:
+        """mel2token_to_dur(mel2ph * (1 - mask).long(), Tt) * (txt != 0)   (fs.py:136-138), int64 [B,Tt]"""
+        _need_cuda(mel2ph, mask, txt)
+        B, T = mel2ph.shape
+        Tt = txt.shape[1]
+        mel2ph, txt = self._i64(mel2ph), self._i64(txt)
+        mask = None if mask is None else self._f32(mask.reshape(B, T))
+        out = torch.empty(B, Tt, dtype=torch.int64, device=txt.device)
+        check(_lib.lib().fse_cond_masked_dur(self._h, _ptr(mel2ph), _ptr(mask), _ptr(txt), _ptr(out), B, T, Tt, _stream()))
+        self._done()
+        return out
+
+    def duration(self, dur_inp, masked_dur, txt) -> torch.Tensor:
+        """DurationPredictor(dur_inp + dur_embed(masked_dur), txt == 0) -> dur[B,Tt]   (fs.py:139-148)"""
+        _need_cuda(dur_inp, masked_dur, txt)
+        B, Tt, _ = dur_inp.shape
+        dur_inp, masked_dur, txt = self._f32(dur_inp), self._i64(masked_dur), self._i64(txt)
+        out = torch.empty(B, Tt, dtype=torch.float32, device=txt.device)
+        ws, nbytes = self._workspace(B, Tt, 0, txt.device)
+        check(_lib.lib().fse_cond_duration(self._h, _ptr(dur_inp), _ptr(masked_dur), _ptr(txt), _ptr(out), B, Tt, ws, nbytes, _stream()))
+        self._done()
+        return out
+
+    def length_regulate(self, dur, txt=None) -> torch.Tensor:
+        """LengthRegulator.forward (nar_tts_modules.py:42-72): dur[B,Tt] -> mel2ph[B, max total] int64.  One host sync for the
+        data-dependent output length, as in the reference (`dur.sum(-1).max()` sizes an arange)."""
+        _need_cuda(dur, txt)
+        B, Tt = dur.shape
+        dur = self._f32(dur)
+        txt = None if txt is None else self._i64(txt)
+        cumsum = torch.empty(B, Tt, dtype=torch.int64, device=dur.device)
+        totals = torch.empty(B, dtype=torch.int64, device=dur.device)
+        check(_lib.lib().fse_cond_length_cumsum(self._h, _ptr(dur), _ptr(txt), _ptr(cumsum), _ptr(totals), B, Tt, _stream()))
+        self._done()
+        tmax = int(totals.max().item())
+        out = torch.zeros(B, max(tmax, 0), dtype=torch.int64, device=dur.device)
+        if tmax > 0:
+            check(_lib.lib().fse_cond_length_fill(self._h, _ptr(cumsum), _ptr(out), B, Tt, tmax, _stream()))
+            self._done()
+        return out
+
+    def frames(self, encoder_out, style, mel2ph, mask, f0, uv, use_pred_pitch: bool):
+        """fs.py:93-102 -> dict(decoder_inp[B,T,H], and with use_pitch_embed pitch_pred[B,T,2], f0_denorm, f0_denorm_pred, pitch)"""
+        _need_cuda(encoder_out, style, mel2ph, mask, f0, uv)
+        B, Tt, _ = encoder_out.shape
+        T = mel2ph.shape[1]
+        dev = encoder_out.device
+        encoder_out, style, mel2ph = self._f32(encoder_out), self._f32(style), self._i64(mel2ph)
+        mask = None if mask is None else self._f32(mask.reshape(B, T))
+        ret = {"decoder_inp": torch.empty(B, T, self.hidden, dtype=torch.float32, device=dev)}
+        pp = fd = fdp = pitch = None
+        if self.use_pitch_embed:
+            if f0 is None or uv is None:
+                raise FseError("use_pitch_embed: f0 and uv are required")
+            f0, uv = self._f32(f0), self._f32(uv)
+            ret["pitch_pred"] = pp = torch.empty(B, T, 2, dtype=torch.float32, device=dev)
+            ret["f0_denorm"] = fd = torch.empty(B, T, dtype=torch.float32, device=dev)
+            ret["f0_denorm_pred"] = fdp = torch.empty(B, T, dtype=torch.float32, device=dev)
+            ret["pitch"] = pitch = torch.empty(B, T, dtype=torch.int64, device=dev)
+        else:
+            f0 = uv = None
+        ws, nbytes = self._workspace(B, Tt, T, dev)
+        check(_lib.lib().fse_cond_frames(self._h, _ptr(encoder_out), _ptr(style), _ptr(mel2ph), _ptr(mask), _ptr(f0), _ptr(uv),
+                                         int(bool(use_pred_pitch)), _ptr(ret["decoder_inp"]), _ptr(pp), _ptr(fd), _ptr(fdp), _ptr(pitch),
+                                         B, Tt, T, ws, nbytes, _stream()))
+        self._done()
+        return ret

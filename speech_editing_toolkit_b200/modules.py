@@ -3,6 +3,7 @@
   DiffNetB200            <-> modules/speech_editing/spec_denoiser/diffnet.py::DiffNet          (:84-132)
   GaussianDiffusionB200  <-> modules/speech_editing/spec_denoiser/spec_denoiser.py::GaussianDiffusion (:16-185)
   MelEncoderB200         <-> modules/speech_editing/commons/mel_encoder.py::MelEncoder        (:3-19)
+  FastSpeechB200         <-> modules/speech_editing/spec_denoiser/fs.py::FastSpeech           (:49-189, skip_decoder=True)
 
 Same constructor arguments, same state_dict keys/shapes (reference checkpoints load unchanged), same
 forward() signatures and return values.  The nn.Modules only OWN the parameters; every forward goes
@@ -17,7 +18,7 @@ import torch
 from torch import nn
 
 from . import schedule as _schedule
-from .engine import Denoiser, MelEncoderKernel
+from .engine import CondEncoderKernel, Denoiser, MelEncoderKernel
 from .hparams import hparams as _global_hparams
 
 
@@ -117,13 +118,165 @@ class MelEncoderB200(nn.Module):
 MelEncoder = MelEncoderB200     # the name the reference uses
 
 
+class _ConvBlocksParams(nn.Module):
+    """Parameter container with the names/shapes of ConvBlocks (modules/commons/conv.py:68-97, norm_type 'ln'):
+    res_blocks.{i}.blocks.{j}.{0: LayerNorm, 1: Conv1d(C, 2C, k), 4: Conv1d(2C, C, 1)}, last_norm, post_net1."""
+
+    def __init__(self, hidden, dilations, kernel_size, layers_in_block=2, post_net_kernel=3):
+        super().__init__()
+
+        class _Block(nn.Module):
+            def __init__(self, d):
+                super().__init__()
+                self.blocks = nn.ModuleList([
+                    nn.Sequential(nn.LayerNorm(hidden, eps=1e-5),
+                                  nn.Conv1d(hidden, 2 * hidden, kernel_size, dilation=d, padding=d * (kernel_size - 1) // 2),
+                                  nn.Identity(), nn.Identity(),          # indices 2, 3: the k^-0.5 scale and GELU (no parameters)
+                                  nn.Conv1d(2 * hidden, hidden, 1, dilation=d))
+                    for _ in range(layers_in_block)])
+
+        self.res_blocks = nn.Sequential(*[_Block(d) for d in dilations])
+        self.last_norm = nn.LayerNorm(hidden, eps=1e-5)
+        self.post_net1 = nn.Conv1d(hidden, hidden, kernel_size=post_net_kernel, padding=post_net_kernel // 2)
+        for m in self.modules():                                        # init_weights_func (conv.py:18-21)
+            if isinstance(m, nn.Conv1d):
+                nn.init.xavier_uniform_(m.weight)
+
+
+def _embedding(n, dim, padding_idx=None):
+    """modules/commons/layers.py:45-50."""
+    m = nn.Embedding(n, dim, padding_idx=padding_idx)
+    nn.init.normal_(m.weight, mean=0, std=dim ** -0.5)
+    if padding_idx is not None:
+        nn.init.constant_(m.weight[padding_idx], 0)
+    return m
+
+
+class _PredictorParams(nn.Module):
+    """conv.{i}.{0: Conv1d, 2: LayerNorm} + linear, the layout shared by DurationPredictor and PitchPredictor
+    (modules/commons/nar_tts_modules.py:8-22, 75-88)."""
+
+    def __init__(self, idim, n_layers, n_chans, kernel_size, odim, dur: bool):
+        super().__init__()
+        self.conv = nn.ModuleList([
+            nn.Sequential(nn.Conv1d(idim if i == 0 else n_chans, n_chans, kernel_size, padding=kernel_size // 2), nn.Identity(),
+                          nn.LayerNorm(n_chans), nn.Identity()) for i in range(n_layers)])
+        self.linear = nn.Sequential(nn.Linear(n_chans, odim), nn.Identity()) if dur else nn.Linear(n_chans, odim)
+
+
+class FastSpeechB200(nn.Module):
+    """Drop-in for the reference's condition encoder `FastSpeech` (fs.py:49-189) on the path the speech-editing model uses:
+    encoder_type 'conv', skip_decoder=True.  Same constructor (dict_size, hparams, out_dims), same state_dict keys and shapes
+    (the unused `decoder.*` / `mel_out.*` parameters are kept so reference checkpoints strict-load), same methods with the same
+    arguments — forward, forward_style_embed, forward_dur (incl. the inference script's masked_dur / use_pred_mel2ph call,
+    inference/tts/spec_denoiser.py:84-98) — and `self.encoder(txt_tokens)` is callable.  The module only owns the parameters:
+    every tensor operation is a kernel behind the fse_cond_* C ABI (no torch arithmetic, no CPU fallback)."""
+
+    def __init__(self, dict_size, hparams: Optional[dict] = None, out_dims=None):
+        super().__init__()
+        hp = dict(_global_hparams if hparams is None else hparams)
+        self.hparams = hp
+        H = self.hidden_size = hp["hidden_size"]
+        if hp.get("encoder_type", "conv") != "conv":
+            raise NotImplementedError("FastSpeechB200 implements encoder_type 'conv' (egs/spec_denoiser*.yaml); other encoders are "
+                                      "other model families (SURVEY.md section 2 row 21)")
+        if hp.get("use_spk_id", False):
+            raise NotImplementedError("use_spk_id is false in the speech-editing configs; only the spk_embed branch is native")
+        self.dict_size = dict_size
+        self.mode = hp.get("b200_mode", "tc_bf16")
+        self.encoder = _ConvBlocksParams(H, hp.get("enc_dilations", [1, 1, 1, 1]), hp.get("enc_kernel_size", 5),
+                                         hp.get("layers_in_block", 2), hp.get("enc_post_net_kernel", 3))
+        self.encoder.embed_tokens = _embedding(dict_size, H, 0)
+        self.encoder.forward = self._encode                     # `model.fs.encoder(txt_tokens)` (inference/tts/spec_denoiser.py:84)
+        if hp.get("decoder_type", "conv") == "conv":            # unused with skip_decoder=True; kept for checkpoint compatibility
+            self.decoder = _ConvBlocksParams(H, hp.get("dec_dilations", [1, 1, 1, 1]), hp.get("dec_kernel_size", 5),
+                                             hp.get("layers_in_block", 2), hp.get("dec_post_net_kernel", 3))
+        self.out_dims = hp.get("audio_num_mel_bins", 80) if out_dims is None else out_dims
+        self.mel_out = nn.Linear(H, self.out_dims, bias=True)
+        self.use_spk_embed = bool(hp.get("use_spk_embed", True))
+        if self.use_spk_embed:
+            self.spk_embed_proj = nn.Linear(256, H, bias=True)
+        ph = hp.get("predictor_hidden", -1)
+        if ph > 0 and ph != H:
+            raise NotImplementedError("predictor_hidden must equal hidden_size (-1 in the shipped configs)")
+        self.dur_embed = _embedding(2000, H, 0)
+        self.dur_predictor = _PredictorParams(H, hp.get("dur_predictor_layers", 3), H, hp.get("dur_predictor_kernel", 5), 1, dur=True)
+        self.use_pitch_embed = bool(hp.get("use_pitch_embed", True))
+        if self.use_pitch_embed:
+            self.pitch_embed = _embedding(300, H, 0)
+            self.pitch_predictor = _PredictorParams(H, 5, H, hp.get("predictor_kernel", 5), 2, dur=False)
+        self._engine: Optional[CondEncoderKernel] = None
+        self._engine_key = None
+
+    def engine(self) -> CondEncoderKernel:
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._engine is None or key != self._engine_key:
+            hp = self.hparams
+            use_uv = hp.get("pitch_type", "frame") == "frame" and bool(hp.get("use_uv", True))
+            eng = CondEncoderKernel(self.dict_size, self.hidden_size, tuple(hp.get("enc_dilations", [1, 1, 1, 1])),
+                                    hp.get("enc_kernel_size", 5), hp.get("layers_in_block", 2), hp.get("enc_post_net_kernel", 3),
+                                    hp.get("dur_predictor_layers", 3), hp.get("dur_predictor_kernel", 5), 5, hp.get("predictor_kernel", 5),
+                                    self.use_pitch_embed, use_uv, 256 if self.use_spk_embed else 0, self.mode)
+            eng.load_state_dict(self.state_dict())
+            self._engine, self._engine_key = eng, key
+        return self._engine
+
+    # -- the reference's methods -----------------------------------------------------------------
+    @torch.no_grad()
+    def _encode(self, txt_tokens):
+        return self.engine().text_encoder(txt_tokens)
+
+    @torch.no_grad()
+    def forward_style_embed(self, spk_embed=None, spk_id=None):
+        """fs.py:114-121 -> [B,1,H] (0 without a speaker embedding)."""
+        if not self.use_spk_embed:
+            return 0
+        return self.engine().style_embed(spk_embed)[:, None, :]
+
+    @torch.no_grad()
+    def forward_dur(self, dur_input, time_mel_masks, mel2ph, txt_tokens, ret, masked_dur=None, use_pred_mel2ph=False):
+        """fs.py:123-151."""
+        eng = self.engine()
+        if masked_dur is None:
+            masked_dur = eng.masked_dur(mel2ph, time_mel_masks, txt_tokens)
+        ret["dur"] = dur = eng.duration(dur_input, masked_dur, txt_tokens)
+        if use_pred_mel2ph:
+            mel2ph = eng.length_regulate(dur, txt_tokens)
+        fm = self.hparams.get("frames_multiple", 1)                       # clip_mel2token_to_multiple (align_ops.py:15-18)
+        ret["mel2ph"] = mel2ph = mel2ph[:, :mel2ph.shape[1] // fm * fm]
+        return mel2ph
+
+    @torch.no_grad()
+    def forward(self, txt_tokens, time_mel_masks, mel2ph, spk_embed, f0, uv, spk_id=None, skip_decoder=True, infer=False,
+                use_pred_mel2ph=False, use_pred_pitch=False, **kwargs):
+        """fs.py:83-105 with skip_decoder=True: returns the reference's dict (decoder_inp, dur, mel2ph, pitch_pred, f0_denorm,
+        f0_denorm_pred)."""
+        if not skip_decoder:
+            raise NotImplementedError("the speech-editing model calls FastSpeech with skip_decoder=True (spec_denoiser.py:159-161); "
+                                      "the FastSpeech mel decoder is not on this path")
+        eng = self.engine()
+        ret = {}
+        encoder_out = eng.text_encoder(txt_tokens)
+        style = eng.style_embed(spk_embed) if self.use_spk_embed else None
+        dur_inp = eng.dur_input(encoder_out, style, txt_tokens)
+        mel2ph = self.forward_dur(dur_inp, time_mel_masks, mel2ph, txt_tokens, ret, use_pred_mel2ph=use_pred_mel2ph)
+        out = eng.frames(encoder_out, style, mel2ph, time_mel_masks, f0, uv, use_pred_pitch)
+        for k in ("pitch_pred", "f0_denorm", "f0_denorm_pred", "decoder_inp"):
+            if k in out:
+                ret[k] = out[k]
+        return ret
+
+
+FastSpeech = FastSpeechB200     # the name the reference uses
+
+
 class GaussianDiffusionB200(nn.Module):
     """Drop-in for GaussianDiffusion on the inference path.
 
-    `fs` (the FastSpeech condition encoder, fs.py:49-112) and `mel_encoder` are injected: inside the reference
-    tree they are the reference's own modules (see `from_reference` / INTEGRATION.md); they run once per
-    batch and stay PyTorch.  Everything from `cond` on — x_S draw, the S p_sample iterations
-    and the mask compositing — is one C-ABI call (fse_sample)."""
+    `fs` (the FastSpeech condition encoder, fs.py:49-112) defaults to the native FastSpeechB200 and `mel_encoder` to
+    MelEncoderB200, so the whole forward(infer=True) — text tokens to mel — runs behind the C ABI; a reference FastSpeech
+    module may still be injected (`fs=`, `from_reference(native_fs=False)`).  Everything from `cond` on — x_S draw, the S
+    p_sample iterations and the mask compositing — is one C-ABI call (fse_sample)."""
 
     def __init__(self, phone_encoder, out_dims, denoise_fn, timesteps=1000, time_scale=1, loss_type="l1", betas=None,
                  spec_min=None, spec_max=None, fs: Optional[nn.Module] = None, mel_encoder: Optional[nn.Module] = None,
@@ -131,6 +284,8 @@ class GaussianDiffusionB200(nn.Module):
         super().__init__()
         hp = _global_hparams if hparams is None else hparams
         self.denoise_fn = denoise_fn
+        if fs is None and phone_encoder is not None:            # as the reference: self.fs = FastSpeech(len(phone_encoder), hparams)
+            fs = FastSpeechB200(len(phone_encoder), hp, out_dims)
         self.fs = fs
         self.mel_encoder = mel_encoder if mel_encoder is not None else MelEncoderB200(out_dims, hp.get("hidden_size", 192),
                                                                                       hp.get("b200_mode", "tc_bf16"))
@@ -153,8 +308,9 @@ class GaussianDiffusionB200(nn.Module):
         self._sched_key = None
 
     @classmethod
-    def from_reference(cls, ref_model, mode: str = "tc_bf16"):
-        """Wrap an instantiated reference GaussianDiffusion: shares its fs, copies the denoise_fn / mel_encoder weights."""
+    def from_reference(cls, ref_model, mode: str = "tc_bf16", native_fs: bool = True):
+        """Convert an instantiated reference GaussianDiffusion: copies the denoise_fn / mel_encoder / fs weights into the native
+        drop-ins (native_fs=False keeps the reference's own FastSpeech module as the condition encoder)."""
         rd = ref_model.denoise_fn
         hp = dict(hidden_size=rd.params.encoder_hidden, residual_layers=rd.params.residual_layers,
                   residual_channels=rd.params.residual_channels, dilation_cycle_length=rd.params.dilation_cycle_length,
@@ -163,8 +319,14 @@ class GaussianDiffusionB200(nn.Module):
         den.load_state_dict(rd.state_dict())
         enc = MelEncoderB200(ref_model.mel_bins, rd.params.encoder_hidden, mode)
         enc.load_state_dict(ref_model.mel_encoder.state_dict())
+        fs = ref_model.fs
+        if native_fs:
+            fhp = dict(ref_model.fs.hparams)
+            fhp["b200_mode"] = mode
+            fs = FastSpeechB200(ref_model.fs.encoder.embed_tokens.num_embeddings, fhp, ref_model.fs.out_dims)
+            fs.load_state_dict(ref_model.fs.state_dict(), strict=True)
         new = cls(None, ref_model.mel_bins, den, timesteps=ref_model.num_timesteps, time_scale=ref_model.time_scale,
-                  loss_type=ref_model.loss_type, fs=ref_model.fs, mel_encoder=enc, hparams=hp)
+                  loss_type=ref_model.loss_type, fs=fs, mel_encoder=enc, hparams=hp)
         for name, buf in ref_model.named_buffers(recurse=False):     # the reference's own float64-derived schedule, bit for bit
             if name in new._buffers:
                 new._buffers[name] = buf.detach().clone()

@@ -186,7 +186,11 @@ def fastspeech_state_dict(seed: int = 1234, vocab: int = 80, hp: dict = None) ->
     sd["dur_predictor.linear.0.weight"] = (rs.standard_normal((1, H)) * (0.8 / math.sqrt(H))).astype(F32)
     sd["dur_predictor.linear.0.bias"] = np.array([2.0], dtype=F32)
     if hp["use_pitch_embed"]:
-        emb("pitch_embed", 300, H)
+        # rows vary smoothly with the pitch bin (a random walk), as a trained table does: a bin that flips by one under
+        # bf16 arithmetic then moves the condition by a few percent of a row, not by a whole independent row
+        walk = np.cumsum(rs.standard_normal((300, H)) * (0.15 * H ** -0.5), axis=0) + rs.standard_normal((1, H)) * H ** -0.5
+        walk[0] = 0.0
+        sd["pitch_embed.weight"] = walk.astype(F32)
         for i in range(hp["pitch_predictor_layers"]):
             conv(f"pitch_predictor.conv.{i}.0", H, H, hp["predictor_kernel"], gain=1.4)
             ln(f"pitch_predictor.conv.{i}.2", H)

@@ -1,0 +1,178 @@
+"""Parity of the native condition encoder (fse_cond_*; FastSpeechB200) on the GPU against
+  * tests/golden/cond_encoder.npz / fluentspeech_e2e.npz — outputs of the unmodified reference FastSpeech / GaussianDiffusion
+    (oracle/make_golden.py cond_encoder), and
+  * oracle/cond_encoder_oracle.py on a larger ragged multi-tile batch.
+Stated tolerances: FSE_MODE_SIMT_F32 max-abs <= 2e-4 on every float output; FSE_MODE_TC_BF16 relative L1 <= 2e-2 vs the fp32
+reference and <= 8e-3 vs the bf16-operand oracle; integer outputs (masked durations, length regulator, mel2ph) bit-exact;
+pitch bins bit-exact in fp32 mode given the reference's own pitch prediction is not involved (use_pred_pitch=False).
+(The file sorts last on purpose: it is the newest GPU surface of the round.)"""
+import numpy as np
+import pytest
+
+from conftest import golden, rel_l1
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL_F32_ABS = 2e-4
+HP = dict(audio_num_mel_bins=80, hidden_size=192, residual_layers=4, residual_channels=256, dilation_cycle_length=1,
+          timesteps=4, timescale=1, diff_loss_type="l1", spec_min=[], spec_max=[], keep_bins=80, schedule_type="vpsde",
+          diff_decoder_type="wavenet_b200", b200_mode="tc_bf16")
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _case():
+    from speech_editing_toolkit_b200 import synth
+    g = golden("cond_encoder.npz")
+    seed, B, T, vocab = int(g["seed"]), int(g["B"]), int(g["T"]), int(g["vocab"])
+    batch = synth.pad_edit_batch(synth.synthetic_edit_batch(seed, B, T, vocab=vocab), item=1, n_tokens=3)
+    return g, synth.fastspeech_state_dict(seed, vocab), batch, vocab
+
+
+def _module(sd, vocab, mode):
+    from speech_editing_toolkit_b200.modules import FastSpeechB200
+    fs = FastSpeechB200(vocab, dict(HP, b200_mode=mode)).cuda()
+    fs.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    return fs
+
+
+@pytest.mark.parametrize("mode", ["simt_f32", "tc_bf16"])
+def test_text_encoder_style_and_duration_vs_reference_fixture(lib_built, mode):
+    _need_gpu()
+    g, sd, batch, vocab = _case()
+    fs = _module(sd, vocab, mode)
+    txt = cu(batch["txt_tokens"])
+    enc = fs.encoder(txt).cpu().numpy()
+    style = fs.forward_style_embed(cu(batch["spk_embed"])).cpu().numpy()
+    assert enc.shape == g["encoder_out"].shape and style.shape == g["style_embed"].shape
+    assert np.abs(style - g["style_embed"]).max() < 1e-5
+    assert np.abs(enc[1, -3:]).max() == 0.0                                          # padded tokens stay exactly zero
+    # the inference script's forward_dur call: explicit masked_dur, predicted mel2ph (inference/tts/spec_denoiser.py:84-98)
+    dur_inp = (cu(g["encoder_out"]) + cu(g["style_embed"])) * (txt > 0).float()[:, :, None]
+    ret = {}
+    mel2ph_pred = fs.forward_dur(dur_inp, cu(batch["time_mel_masks"]), cu(batch["mel2ph"]), txt, ret, masked_dur=cu(g["masked_dur_in"]),
+                                 use_pred_mel2ph=True)
+    dur = ret["dur"].cpu().numpy()
+    if mode == "simt_f32":
+        assert np.abs(enc - g["encoder_out"]).max() < TOL_F32_ABS
+        assert np.abs(dur - g["dur_masked_dur"]).max() < TOL_F32_ABS
+        assert np.array_equal(mel2ph_pred.cpu().numpy(), g["mel2ph_pred"])            # integer: bit-exact
+    else:
+        assert rel_l1(enc, g["encoder_out"]) < 2e-2
+        assert rel_l1(dur, g["dur_masked_dur"]) < 2e-2
+    # the length regulator alone on the reference's own durations: bit-exact in every mode
+    lr = fs.engine().length_regulate(cu(g["dur_masked_dur"]), txt).cpu().numpy()
+    assert np.array_equal(lr, g["mel2ph_pred"])
+
+
+@pytest.mark.parametrize("mode", ["simt_f32", "tc_bf16"])
+@pytest.mark.parametrize("use_pred_pitch", [False, True])
+def test_fastspeech_forward_vs_reference_fixture(lib_built, mode, use_pred_pitch):
+    _need_gpu()
+    g, sd, batch, vocab = _case()
+    fs = _module(sd, vocab, mode)
+    sfx = "_predpitch" if use_pred_pitch else ""
+    ret = fs(cu(batch["txt_tokens"]), cu(batch["time_mel_masks"])[:, :, None], cu(batch["mel2ph"]), cu(batch["spk_embed"]), cu(batch["f0"]),
+             cu(batch["uv"]), skip_decoder=True, infer=True, use_pred_pitch=use_pred_pitch)
+    out = {k: v.cpu().numpy() for k, v in ret.items()}
+    assert set(out) == {"decoder_inp", "dur", "mel2ph", "pitch_pred", "f0_denorm", "f0_denorm_pred"}
+    assert np.array_equal(out["mel2ph"], g["mel2ph" + sfx])
+    assert np.abs(out["decoder_inp"][1, -24:]).max() == 0.0                           # padded frames exactly zero
+    if mode == "simt_f32":
+        for k in ("decoder_inp", "dur", "pitch_pred"):
+            assert np.abs(out[k] - g[k + sfx]).max() < TOL_F32_ABS, k
+        for k in ("f0_denorm", "f0_denorm_pred"):
+            assert np.abs(out[k] - g[k + sfx]).max() < 0.05, k                        # Hz (values up to 900)
+    else:
+        assert rel_l1(out["decoder_inp"], g["decoder_inp" + sfx]) < (4e-2 if use_pred_pitch else 2e-2)   # a flipped pitch bin swaps an embedding row
+        assert rel_l1(out["dur"], g["dur" + sfx]) < 2e-2
+        assert rel_l1(out["pitch_pred"], g["pitch_pred" + sfx]) < 2e-2
+
+
+@pytest.mark.parametrize("mode", ["simt_f32", "tc_bf16"])
+def test_integer_ops_bit_exact(lib_built, mode):
+    """masked durations (scatter_add histogram), pitch bins of given f0 (f0_to_coarse o denorm_f0) and the gather by mel2ph."""
+    _need_gpu()
+    from oracle import cond_encoder_oracle as CO
+    g, sd, batch, vocab = _case()
+    fs = _module(sd, vocab, mode)
+    eng = fs.engine()
+    txt, mel2ph, mask = cu(batch["txt_tokens"]), cu(batch["mel2ph"]), cu(batch["time_mel_masks"])
+    md = eng.masked_dur(mel2ph, mask, txt).cpu().numpy()
+    assert md.dtype == np.int64 and np.array_equal(md, CO.masked_dur_gt(batch["mel2ph"], batch["time_mel_masks"], batch["txt_tokens"]))
+    assert np.array_equal(eng.masked_dur(mel2ph, None, txt).cpu().numpy(),
+                          CO.masked_dur_gt(batch["mel2ph"], np.zeros_like(batch["time_mel_masks"]), batch["txt_tokens"]))
+    enc = cu(g["encoder_out"])
+    out = eng.frames(enc, cu(g["style_embed"][:, 0]), mel2ph, mask, cu(batch["f0"]), cu(batch["uv"]), False)
+    assert np.array_equal(out["pitch"].cpu().numpy(), g["pitch"])                      # bins of the given f0/uv: bit-exact
+    # known answers of SURVEY appendix A through the same kernels (f0 given in log2 Hz, uv = 0)
+    hz = np.array([[50, 80, 100, 220, 440, 600, 900, 1200]], dtype=np.float32)
+    one = eng.frames(enc[:1], None, torch.ones(1, 8, dtype=torch.int64, device="cuda"), None, cu(np.log2(hz)), cu(np.zeros_like(hz)), False)
+    assert np.array_equal(one["pitch"].cpu().numpy(), [[1, 14, 23, 69, 141, 185, 255, 255]])
+    lr = eng.length_regulate(cu(np.array([[2.4, 0.6, 3.5], [0.5, 1.5, 2.5]], dtype=np.float32))).cpu().numpy()
+    assert np.array_equal(lr, [[1, 1, 2, 3, 3, 3, 3], [2, 2, 3, 3, 0, 0, 0]])           # round half to even; zero past the end
+
+
+def test_multi_tile_ragged_batch_vs_oracle(lib_built):
+    """3 items x 330 frames / 82 tokens (three 128-row tiles per item in the frame branch), ragged tails, against the numpy
+    oracle in both arithmetic contracts."""
+    _need_gpu()
+    from oracle import cond_encoder_oracle as CO
+    from speech_editing_toolkit_b200 import synth
+    vocab, B, T = 60, 3, 330
+    sd = synth.fastspeech_state_dict(77, vocab)
+    batch = synth.synthetic_edit_batch(78, B, T, vocab=vocab, frames_per_phone=4)
+    batch = synth.pad_edit_batch(synth.pad_edit_batch(batch, 1, 20, 4), 2, 5, 4)
+    args = (batch["txt_tokens"], batch["time_mel_masks"], batch["mel2ph"], batch["spk_embed"], batch["f0"], batch["uv"])
+    ref32 = CO.fastspeech_forward(sd, *args, use_pred_pitch=False)
+    refbf = CO.fastspeech_forward(sd, *args, use_pred_pitch=False, gemm_dtype="bf16")
+    for mode in ("simt_f32", "tc_bf16"):
+        fs = _module(sd, vocab, mode)
+        ret = fs(cu(batch["txt_tokens"]), cu(batch["time_mel_masks"])[:, :, None], cu(batch["mel2ph"]), cu(batch["spk_embed"]),
+                 cu(batch["f0"]), cu(batch["uv"]), skip_decoder=True, infer=True, use_pred_pitch=False)
+        out = {k: v.cpu().numpy() for k, v in ret.items()}
+        if mode == "simt_f32":
+            for k in ("decoder_inp", "dur", "pitch_pred"):
+                assert np.abs(out[k] - ref32[k]).max() < TOL_F32_ABS, k
+        else:
+            for k in ("decoder_inp", "dur", "pitch_pred"):
+                assert rel_l1(out[k], ref32[k]) < 2e-2, k
+                assert rel_l1(out[k], refbf[k]) < 8e-3, k
+        assert fs.engine().launches > 0
+
+
+def test_whole_model_text_to_mel_vs_reference_fixture(lib_built):
+    """GaussianDiffusionB200.forward(infer=True) with every sub-module native (FastSpeechB200 + MelEncoderB200 + DiffNetB200)
+    against the unmodified reference GaussianDiffusion.forward on the same weights, inputs and injected noise."""
+    _need_gpu()
+    from speech_editing_toolkit_b200 import plugin, synth
+    from speech_editing_toolkit_b200.modules import FastSpeechB200, MelEncoderB200
+    g = golden("fluentspeech_e2e.npz")
+    seed, B, T, S, L, vocab = (int(g[k]) for k in ("seed", "B", "T", "S", "layers", "vocab"))
+    batch = synth.pad_edit_batch(synth.synthetic_edit_batch(seed, B, T, vocab=vocab), item=1, n_tokens=3)
+    noise = synth.synthetic_noise(seed + 5, S, B, T)
+    for mode, tol in (("simt_f32", None), ("tc_bf16", 3e-2)):
+        model = plugin.build_diffusion(dict(HP, timesteps=S, residual_layers=L, b200_mode=mode), phone_encoder=list(range(vocab)))
+        assert isinstance(model.fs, FastSpeechB200) and isinstance(model.mel_encoder, MelEncoderB200)
+        model.fs.load_state_dict({k: torch.from_numpy(v) for k, v in synth.fastspeech_state_dict(seed, vocab).items()}, strict=False)
+        model.mel_encoder.load_state_dict({k: torch.from_numpy(v) for k, v in synth.mel_encoder_state_dict(seed).items()})
+        model.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in synth.denoiser_state_dict(seed, layers=L).items()})
+        model = model.cuda().eval()
+        ret = model(cu(batch["txt_tokens"]), cu(batch["time_mel_masks"])[:, :, None], cu(batch["mel2ph"]), cu(batch["spk_embed"]),
+                    cu(batch["ref_mels"]), cu(batch["f0"]), cu(batch["uv"]), infer=True, use_pred_pitch=True, noise=cu(noise))
+        mel, cond = ret["mel_out"].cpu().numpy(), ret["decoder_inp"].cpu().numpy()
+        assert mel.shape == g["mel_out"].shape
+        if tol is None:
+            assert np.abs(cond - g["decoder_inp"]).max() < 5e-4
+            assert np.abs(mel - g["mel_out"]).max() < 2e-3
+        else:
+            assert rel_l1(cond, g["decoder_inp"]) < tol
+            assert rel_l1(mel, g["mel_out"]) < tol

@@ -83,9 +83,12 @@ def test_state_dict_keys_match_live_reference_modules():
     for k in rsd:
         if not k.startswith(("fs.", "mel_encoder.", "denoise_fn.")):
             assert torch.equal(rsd[k], osd[k]), k
-    assert wrapped.fs is ref.fs                                      # the condition encoder is shared ...
-    from speech_editing_toolkit_b200.modules import MelEncoderB200
-    assert isinstance(wrapped.mel_encoder, MelEncoderB200)           # ... the context-mel encoder is the native drop-in
+    from speech_editing_toolkit_b200.modules import FastSpeechB200, MelEncoderB200
+    assert isinstance(wrapped.fs, FastSpeechB200)                    # the condition encoder is the native drop-in ...
+    for k, v in ref.fs.state_dict().items():                         # ... strict-loaded from the reference module (147 keys)
+        assert torch.equal(v, wrapped.fs.state_dict()[k]), k
+    assert GaussianDiffusionB200.from_reference(ref, native_fs=False).fs is ref.fs     # or the reference's own module, shared
+    assert isinstance(wrapped.mel_encoder, MelEncoderB200)           # the context-mel encoder is the native drop-in
     for k, v in ref.mel_encoder.state_dict().items():
         assert torch.equal(v, wrapped.mel_encoder.state_dict()[k]), k
 
@@ -115,3 +118,39 @@ def test_vocoder_checkpoint_layout(tmp_path):
     if not torch.cuda.is_available():
         with pytest.raises(FseError):                 # files are found and parsed; only the CUDA handle cannot be made here
             HifiGANB200(str(tmp_path))
+
+
+def test_fastspeech_drop_in_surface_and_state_dict():
+    """FastSpeechB200 mirrors fs.py:49-189: constructor (dict_size, hparams), the reference's 147 state_dict keys (incl. the unused
+    decoder / mel_out), forward / forward_style_embed / forward_dur and a callable `.encoder`."""
+    from speech_editing_toolkit_b200.modules import FastSpeechB200, GaussianDiffusionB200, DiffNetB200
+    fs = FastSpeechB200(80, HP)
+    sd = synth.fastspeech_state_dict(3, 80)
+    own = {k: tuple(v.shape) for k, v in fs.state_dict().items()}
+    assert all(own[k] == v.shape for k, v in sd.items())
+    assert all(k.startswith(("decoder.", "mel_out.")) for k in set(own) - set(sd))
+    missing, unexpected = fs.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+    assert not unexpected and all(k.startswith(("decoder.", "mel_out.")) for k in missing)
+    assert float(fs.dur_embed.weight[0].abs().sum()) == 0.0 and float(fs.encoder.embed_tokens.weight[0].abs().sum()) == 0.0
+    for meth in ("forward", "forward_style_embed", "forward_dur", "engine"):
+        assert callable(getattr(fs, meth))
+    assert callable(fs.encoder)
+    with pytest.raises(NotImplementedError):
+        FastSpeechB200(80, dict(HP, encoder_type="fft"))
+    with pytest.raises(NotImplementedError):
+        fs(None, None, None, None, None, None, skip_decoder=False)
+    model = GaussianDiffusionB200(list(range(80)), 80, DiffNetB200(80, HP), timesteps=8, hparams=HP)    # as build_tts_model does
+    assert isinstance(model.fs, FastSpeechB200) and model.fs.dict_size == 80
+    libritts = FastSpeechB200(80, dict(HP, use_pitch_embed=False))                                       # egs/spec_denoiser_libritts.yaml:169
+    assert not hasattr(libritts, "pitch_embed") and not any(k.startswith("pitch_") for k in libritts.state_dict())
+
+
+@needs_ref
+def test_fastspeech_state_dict_matches_live_reference():
+    hp = refshim.install("egs/spec_denoiser.yaml")
+    from modules.speech_editing.spec_denoiser.fs import FastSpeech
+    from speech_editing_toolkit_b200.modules import FastSpeechB200
+    ref = FastSpeech(80, hp)
+    ours = FastSpeechB200(80, dict(hp))
+    assert {k: tuple(v.shape) for k, v in ours.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    ours.load_state_dict(ref.state_dict(), strict=True)
