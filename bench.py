@@ -229,6 +229,43 @@ def run_b200(args):
             wav_h.copy_(voc.forward(mel), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
+    # the whole model behind the reference's own call (GaussianDiffusion.forward(infer=True), spec_denoiser.py:154-185):
+    # text tokens -> condition encoder -> MelEncoder -> S-step sampling (+ mask compositing), then the vocoder
+    model, txt_host = None, None
+    if not args.no_e2e or not args.no_kernel_timing:
+        from speech_editing_toolkit_b200 import plugin
+        hp = dict(audio_num_mel_bins=80, hidden_size=192, residual_layers=20, residual_channels=256, dilation_cycle_length=1,
+                  timesteps=S, timescale=1, diff_loss_type="l1", spec_min=[], spec_max=[], keep_bins=80, schedule_type="vpsde",
+                  diff_decoder_type="wavenet_b200", b200_mode=args.mode)
+        model = plugin.build_diffusion(hp, phone_encoder=list(range(80)))
+        t_ = lambda sd: {k: torch.from_numpy(v) for k, v in sd.items()}
+        model.fs.load_state_dict(t_(synth.fastspeech_state_dict(1234, 80)), strict=False)       # decoder.* / mel_out.* unused (skip_decoder)
+        model.mel_encoder.load_state_dict(t_(synth.mel_encoder_state_dict(1234)))
+        model.denoise_fn.load_state_dict(t_(synth.denoiser_state_dict(1234)))
+        model = model.to(dev).eval()
+        txt_host = {k: torch.from_numpy(batch[k]).pin_memory() for k in ("txt_tokens", "mel2ph", "time_mel_masks", "spk_embed", "ref_mels", "f0", "uv")}
+        txt_dev = {k: v.to(dev) for k, v in txt_host.items()}
+
+    def text_to_mel(t, i):
+        ret = model(t["txt_tokens"], t["time_mel_masks"][:, :, None], t["mel2ph"], t["spk_embed"], t["ref_mels"], t["f0"], t["uv"],
+                    infer=True, use_pred_pitch=True, seed=i, composite=True)
+        return ret["mel_out"]
+
+    def step_e2e_text(i):
+        t = {k: v.to(dev, non_blocking=True) for k, v in txt_host.items()}
+        mel = text_to_mel(t, i)
+        mel_h.copy_(mel, non_blocking=True)
+        if voc:
+            wav_h.copy_(voc.forward(mel), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def step_cond_encoder(i):                       # condition encoder + MelEncoder alone, inputs resident (for the breakdown)
+        t = txt_dev
+        ret = model.fs(t["txt_tokens"], t["time_mel_masks"][:, :, None], t["mel2ph"], t["spk_embed"], t["f0"], t["uv"], None,
+                       skip_decoder=True, infer=True, use_pred_pitch=True)
+        model.mel_encoder.fused(t["ref_mels"] * (1 - t["time_mel_masks"][:, :, None]), ret["decoder_inp"],
+                                (t["mel2ph"] > 0).float()[:, :, None])
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -275,13 +312,27 @@ def run_b200(args):
     ms_noprof = timed(step_resident, args.steps, profile=False) / args.steps if use_prof else ms_step
 
     e2e = None
+    cond_ms = None
     if not args.no_e2e:
-        step_e2e(0)
-        ms_e2e = timed(step_e2e, args.steps) / args.steps
-        h2d = cond_h.numel() * 4 + ref_h.numel() * 4 + mask_h.numel() * 4
         d2h = mel_h.numel() * 4 + (wav_h.numel() * 4 if voc else 0)
+        step_e2e(0)
+        ms_cond = timed(step_e2e, args.steps) / args.steps
+        h2d_cond = cond_h.numel() * 4 + ref_h.numel() * 4 + mask_h.numel() * 4
+        from_cond = {"value": frames_total / (ms_cond / 1e3), "unit": "mel-frames/s", "h2d_bytes_per_step": h2d_cond,
+                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_cond,
+                     "api": "Denoiser.sample + Vocoder.forward (ctypes -> fse_sample / fse_vocoder_forward) from a ready cond[B,T,192], pinned host in/out"}
+        step_e2e_text(0)
+        ms_e2e = timed(step_e2e_text, args.steps) / args.steps
+        h2d = sum(v.numel() * v.element_size() for v in txt_host.values())
         e2e = {"value": frames_total / (ms_e2e / 1e3), "unit": "mel-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": ms_e2e, "api": "Denoiser.sample + Vocoder.forward (ctypes -> fse_sample / fse_vocoder_forward), pinned host in/out"}
+               "ms_per_step": ms_e2e,
+               "api": "GaussianDiffusionB200.forward(txt_tokens, time_mel_masks, mel2ph, spk_embed, ref_mels, f0, uv, infer=True, "
+                      "use_pred_pitch=True) + Vocoder.forward: text tokens -> wav, every sub-module native "
+                      "(ctypes -> fse_cond_* / fse_mel_encoder_forward / fse_sample / fse_vocoder_forward), pinned host in/out",
+               "from_cond": from_cond}
+    if use_prof and model is not None:
+        step_cond_encoder(0)
+        cond_ms = timed(step_cond_encoder, args.steps) / args.steps
 
     if rank != 0:
         if world > 1:
@@ -315,6 +366,8 @@ def run_b200(args):
         breakdown["denoiser_ms_per_step"] = {k: v[0] / args.steps for k, v in prof_d.items()}
     if prof_v:
         breakdown["vocoder_ms_per_step"] = {k: v[0] / args.steps for k, v in prof_v.items()}
+    if cond_ms is not None:      # once per batch, in front of the loop: part of e2e, not of the resident `value` step (sampling + vocoder)
+        breakdown["cond_encoder_plus_mel_encoder_ms"] = cond_ms
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cpu = cpu_sample(S, B * T)

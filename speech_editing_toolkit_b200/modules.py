@@ -367,8 +367,11 @@ class GaussianDiffusionB200(nn.Module):
         return self._engine().sample(cond_bth, noise, seed, ref_mels if mask is not None else None, mask)
 
     def forward(self, txt_tokens, time_mel_masks, mel2ph, spk_embed, ref_mels, f0, uv, energy=None, infer=False,
-                use_pred_mel2ph=False, use_pred_pitch=False, noise=None, seed=None):
-        """spec_denoiser.py:154-185, infer=True branch.  Returns the reference's dict (mel_out[B,T,M], ...)."""
+                use_pred_mel2ph=False, use_pred_pitch=False, noise=None, seed=None, composite=False):
+        """spec_denoiser.py:154-185, infer=True branch.  Returns the reference's dict (mel_out[B,T,M], ...).
+        Extras over the reference signature: `noise` ([(S+1),B,M,T] injected draws, tests), `seed` (Philox key) and `composite`
+        (mel_out * mask + ref_mels * (1 - mask), the call sites' next line — tasks/speech_editing/spec_denoiser.py:53,84,
+        inference/tts/spec_denoiser.py:136 — done in the last step's epilogue)."""
         if not infer:
             raise NotImplementedError("GaussianDiffusionB200 implements the sampling path (infer=True); training stays on the "
                                       "reference's GaussianDiffusion (SURVEY.md §8f row 3)")
@@ -385,7 +388,11 @@ class GaussianDiffusionB200(nn.Module):
         ret["decoder_inp"] = decoder_inp
         if seed is None:
             seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())      # follows torch.manual_seed like the reference's randn
-        x = self._engine().sample(decoder_inp.contiguous(), noise, seed)  # = x[:, 0].transpose(1, 2) of the reference loop
+        if composite:
+            B, T = decoder_inp.shape[:2]
+            x = self._engine().sample(decoder_inp.contiguous(), noise, seed, ref_mels, time_mel_masks.reshape(B, T))
+        else:
+            x = self._engine().sample(decoder_inp.contiguous(), noise, seed)  # = x[:, 0].transpose(1, 2) of the reference loop
         ret["mel_out"] = x
         return ret
 

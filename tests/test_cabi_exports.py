@@ -53,3 +53,37 @@ def test_no_cpu_fallback_without_gpu(lib_built):
     from speech_editing_toolkit_b200.engine import Denoiser
     with pytest.raises(FseError):
         Denoiser()
+
+
+def test_cond_encoder_config_validation_happens_before_any_device_call(lib_built):
+    """Argument checks of fse_cond_encoder_create (include/fse_b200.h) return FSE_EINVAL with a message and never reach the
+    device, so they can be exercised without a GPU; a valid config then fails loudly (FSE_ECUDA) when no sm_100 device exists."""
+    import ctypes as C
+    import torch
+    from speech_editing_toolkit_b200 import _lib
+    L = _lib.lib()
+
+    def cfg(**kw):
+        c = _lib.CondEncoderConfig()
+        c.hidden, c.vocab, c.enc_layers, c.enc_kernel_size, c.layers_in_block, c.enc_post_net_kernel = 192, 80, 4, 5, 2, 3
+        for i in range(4):
+            c.enc_dilations[i] = 1
+        c.dur_predictor_layers, c.dur_predictor_kernel, c.pitch_predictor_layers, c.predictor_kernel = 3, 5, 5, 5
+        c.use_pitch_embed, c.use_uv, c.spk_embed_dim, c.mode = 1, 1, 256, 0
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+    for bad, word in ((dict(hidden=200), b"hidden"), (dict(hidden=1024), b"hidden"), (dict(vocab=0), b"vocab"), (dict(enc_layers=9), b"enc_layers"),
+                      (dict(mode=7), b"mode"), (dict(dur_predictor_layers=0), b"predictor"), (dict(spk_embed_dim=-1), b"spk_embed_dim")):
+        h = C.c_void_p()
+        assert L.fse_cond_encoder_create(C.byref(cfg(**bad)), C.byref(h)) == -1, bad
+        assert word in L.fse_last_error(), (bad, L.fse_last_error())
+    c = cfg()
+    c.enc_dilations[2] = 0
+    assert L.fse_cond_encoder_create(C.byref(c), C.byref(C.c_void_p())) == -1
+    assert L.fse_cond_encoder_create(None, None) == -1
+    assert L.fse_cond_encoder_workspace_bytes(None, 1, 1, 1) == 0 and L.fse_cond_encoder_last_launches(None) == 0
+    assert L.fse_cond_text_encoder(None, None, None, 1, 1, None, 0, None) == -1
+    if not torch.cuda.is_available():
+        assert L.fse_cond_encoder_create(C.byref(cfg()), C.byref(C.c_void_p())) == -2         # no device: FSE_ECUDA, no fallback
