@@ -208,12 +208,39 @@ def cond_encoder_fixture():
     print("fluentspeech_e2e", ret["mel_out"].shape, float(np.abs(ret["mel_out"].numpy()).mean()))
 
 
+def campnet_fixture():
+    """CampNet.forward (modules/speech_editing/campnet/campnet.py:40-69) from the unmodified reference on a ragged batch:
+    `python oracle/make_golden.py campnet` writes tests/golden/campnet.npz."""
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(SEED)
+    hp = refshim.install("egs/campnet.yaml")
+    from modules.speech_editing.campnet.campnet import CampNet
+    vocab = 80
+    net = CampNet(vocab, 100, hp).eval()
+    sd = synth.campnet_state_dict(SEED, vocab)
+    missing, unexpected = net.load_state_dict(to_torch(sd), strict=False)
+    assert not unexpected, unexpected
+    assert all(k.startswith(("encoder.pre_net.", "mel_out.")) or k.endswith("_float_tensor") for k in missing), missing
+    B, T = 2, 160
+    batch = synth.synthetic_campnet_batch(SEED, B, T, vocab=vocab, pad_items=[(1, 4)])
+    with torch.no_grad():
+        ret = net(torch.from_numpy(batch["txt_tokens"]), mels=torch.from_numpy(batch["mels"]),
+                  time_mel_masks=torch.from_numpy(batch["time_mel_masks"]), infer=True)
+        enc, _ = net.run_text_encoder(torch.from_numpy(batch["txt_tokens"]), {})
+    np.savez_compressed(os.path.join(OUT, "campnet.npz"), seed=SEED, B=B, T=T, vocab=vocab, mel_out_coarse=ret["mel_out_coarse"].numpy(),
+                        mel_out_fine=ret["mel_out_fine"].numpy(), attn=ret["attn"].numpy().astype(np.float16), encoder_out=enc.numpy())
+    print("campnet", ret["mel_out_fine"].shape, float(np.abs(ret["mel_out_fine"].numpy()).mean()), "attn", ret["attn"].shape)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "mel_encoder":
         mel_encoder_fixture()
     elif len(sys.argv) > 1 and sys.argv[1] == "cond_encoder":
         cond_encoder_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "campnet":
+        campnet_fixture()
     else:
         main()
         mel_encoder_fixture()
         cond_encoder_fixture()
+        campnet_fixture()

@@ -212,3 +212,71 @@ def pad_edit_batch(batch: dict, item: int, n_tokens: int, frames_per_phone: int 
         out[k][item, pad] = 0
     out["ref_mels"][item, pad] = 0
     return out
+
+
+def campnet_state_dict(seed: int = 1234, vocab: int = 80, hidden: int = 192, n_mels: int = 80, enc_layers: int = 3, dec_layers: int = 6,
+                       ffn_kernel: int = 9, fine_blocks: int = 5) -> Dict[str, np.ndarray]:
+    """Random CampNet state_dict (modules/speech_editing/campnet/campnet.py:14-38) with the reference's keys/shapes for every
+    tensor the forward uses: encoder (embed_tokens + 3 EncSALayers + layer_norm), mel_encoder, decoder_coarse (6 DecSALayers),
+    decoder_fine (ConvBlocks), mel_out_coarse / mel_out_fine, mask_emb.  Unused entries (encoder.pre_net.*, mel_out.*, the
+    _float_tensor buffers) are not generated."""
+    rs = np.random.RandomState(seed + 97)
+    C = hidden
+    sd: Dict[str, np.ndarray] = {}
+
+    def mat(name, co, ci, gain=1.0, bias=True):
+        sd[name + ".weight"] = (rs.standard_normal((co, ci)) * (gain / math.sqrt(ci))).astype(F32)
+        if bias:
+            sd[name + ".bias"] = (rs.standard_normal((co,)) * 0.1).astype(F32)
+
+    def conv(name, co, ci, k, gain=1.0):
+        sd[name + ".weight"] = (rs.standard_normal((co, ci, k)) * (gain / math.sqrt(ci * k))).astype(F32)
+        sd[name + ".bias"] = (rs.standard_normal((co,)) * 0.1).astype(F32)
+
+    def ln(name):
+        sd[name + ".weight"] = (1.0 + 0.1 * rs.standard_normal((C,))).astype(F32)
+        sd[name + ".bias"] = (0.1 * rs.standard_normal((C,))).astype(F32)
+
+    def attn(name):
+        sd[name + ".in_proj_weight"] = (rs.standard_normal((3 * C, C)) * (1.5 / math.sqrt(C))).astype(F32)
+        sd[name + ".out_proj.weight"] = (rs.standard_normal((C, C)) / math.sqrt(C)).astype(F32)
+
+    sd["mask_emb"] = (rs.standard_normal((1, 1, n_mels)) * 0.5).astype(F32)
+    w = (rs.standard_normal((vocab, C)) * C ** -0.5).astype(F32)
+    w[0] = 0.0
+    sd["encoder.embed_tokens.weight"] = w
+    for i in range(enc_layers):
+        p = f"encoder.layers.{i}.op."
+        ln(p + "layer_norm1"); attn(p + "self_attn"); ln(p + "layer_norm2")
+        conv(p + "ffn.ffn_1", 4 * C, C, ffn_kernel, gain=1.5)
+        mat(p + "ffn.ffn_2", C, 4 * C)
+    ln("encoder.layer_norm")
+    for name, (n, c) in (("mel_encoder.encoder.0", (C, n_mels)), ("mel_encoder.encoder.2", (C, C)), ("mel_encoder.fc_out", (C, C))):
+        mat(name, n, c)
+    sd["decoder_coarse.pos_embed_alpha"] = np.array([0.8], dtype=F32)
+    for i in range(dec_layers):
+        p = f"decoder_coarse.layers.{i}.op."
+        ln(p + "layer_norm1"); attn(p + "self_attn"); ln(p + "layer_norm2"); attn(p + "encoder_attn"); ln(p + "layer_norm3")
+        conv(p + "ffn.ffn_1.1", 4 * C, C, ffn_kernel, gain=1.5)           # 'LEFT' padding: Sequential(ConstantPad1d, Conv1d)
+        mat(p + "ffn.ffn_2", C, 4 * C)
+    ln("decoder_coarse.layer_norm")
+    for i in range(fine_blocks):
+        for j in range(2):
+            p = f"decoder_fine.res_blocks.{i}.blocks.{j}."
+            ln(p + "0")
+            conv(p + "1", 2 * C, C, 5, gain=1.6)
+            conv(p + "4", C, 2 * C, 1)
+    ln("decoder_fine.last_norm")
+    conv("decoder_fine.post_net1", C, C, 3)
+    mat("mel_out_coarse", n_mels, C, bias=False)
+    mat("mel_out_fine", n_mels, C, bias=False)
+    return sd
+
+
+def synthetic_campnet_batch(seed: int, B: int, T: int, vocab: int = 80, frames_per_phone: int = 8, pad_items=()):
+    """(txt_tokens, mels, time_mel_masks) of the CampNet mask-predict forward (tasks/speech_editing/campnet.py:52-80);
+    `pad_items` = [(item, n_tokens)] turns tails into padding (token 0 / all-zero mel frames)."""
+    b = synthetic_edit_batch(seed, B, T, vocab=vocab, frames_per_phone=frames_per_phone)
+    for item, n in pad_items:
+        b = pad_edit_batch(b, item, n, frames_per_phone)
+    return dict(txt_tokens=b["txt_tokens"], mels=b["ref_mels"], time_mel_masks=b["time_mel_masks"][:, :, None].copy())
