@@ -243,6 +243,41 @@ int fse_cond_frames(fse_cond_encoder* h, const float* encoder_out, const float* 
                     float* f0_denorm, float* f0_denorm_pred, int64_t* pitch, int32_t B, int32_t Tt, int32_t T, void* workspace,
                     int64_t workspace_bytes, void* stream);
 
+/* --- CampNet mask-predict forward (BASELINE configs[3]) -------------------------------------------
+ * modules/speech_editing/campnet/campnet.py:14-69: TransformerEncoder (3 EncSALayers) over the phonemes, MelEncoder over the
+ * masked mel (mask_emb on the masked frames), TransformerDecoder (6 DecSALayers: self-attention, encoder-decoder attention,
+ * causal-padded conv FFN; modules/speech_editing/commons/transformer.py:489-812) -> mel_out_coarse, then MelEncoder +
+ * ConvBlocks (decoder_fine, modules/commons/conv.py:68-116) -> mel_out_fine.  Weight names are the reference CampNet's
+ * state_dict keys (unused entries — encoder.pre_net.*, mel_out.*, *._float_tensor — are ignored). */
+typedef struct fse_campnet fse_campnet;
+typedef struct fse_campnet_config {
+  int32_t hidden;       /* hidden_size, 192 (= heads * 96) */
+  int32_t vocab;        /* ph_dict_size */
+  int32_t n_mels;       /* audio_num_mel_bins, 80 */
+  int32_t enc_layers;   /* 3 (campnet.py:17-19) */
+  int32_t dec_layers;   /* 6 (campnet.py:26-28) */
+  int32_t heads;        /* 2 */
+  int32_t ffn_kernel;   /* dec_ffn_kernel_size, 9 */
+  int32_t fine_blocks;  /* 5 (campnet.py:29-31) */
+  int32_t fine_kernel;  /* 5 */
+  int32_t mode;         /* FSE_MODE_* */
+} fse_campnet_config;
+/* replaces CampNet.__init__ (campnet.py:14-38) */
+int fse_campnet_create(const fse_campnet_config* cfg, fse_campnet** out);
+void fse_campnet_destroy(fse_campnet* h);
+/* replaces load_ckpt(model, ..., 'model') for a CampNet checkpoint (utils/commons/ckpt_utils.py:26-66) */
+int fse_campnet_load_weights(fse_campnet* h, const fse_tensor* tensors, int32_t n);
+/* valid after load_weights */
+int64_t fse_campnet_workspace_bytes(const fse_campnet* h, int32_t B, int32_t Tt, int32_t T);
+int64_t fse_campnet_last_launches(const fse_campnet* h);
+/* replaces CampNet.forward (campnet.py:40-69):
+ *   txt [B,Tt] int64, mels [B,T,n_mels] fp32 (all-zero frames = padding), time_mel_masks [B,T] fp32 0/1
+ *   out: mel_out_coarse, mel_out_fine [B,T,n_mels]; optional (may be NULL): attn [B,T,Tt] = head-averaged encoder-decoder
+ *        attention of decoder layer 0 (the `attn` entry of the reference's dict), encoder_out [B,Tt,hidden] */
+int fse_campnet_forward(fse_campnet* h, const int64_t* txt, const float* mels, const float* time_mel_masks, float* mel_out_coarse,
+                        float* mel_out_fine, float* attn, float* encoder_out, int32_t B, int32_t Tt, int32_t T, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+
 /* --- kernel timing (opt-in) -------------------------------------------------------------------
  * When enabled, every kernel the handle launches is bracketed by CUDA events on the launch stream;
  * *_profile_read waits for them and returns the summed device time (ms) and launch count per kind

@@ -42,6 +42,11 @@ class CondEncoderConfig(C.Structure):
                 ("spk_embed_dim", C.c_int32), ("mode", C.c_int32)]
 
 
+class CampNetConfig(C.Structure):
+    _fields_ = [("hidden", C.c_int32), ("vocab", C.c_int32), ("n_mels", C.c_int32), ("enc_layers", C.c_int32), ("dec_layers", C.c_int32),
+                ("heads", C.c_int32), ("ffn_kernel", C.c_int32), ("fine_blocks", C.c_int32), ("fine_kernel", C.c_int32), ("mode", C.c_int32)]
+
+
 class Tensor(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.POINTER(C.c_float)), ("numel", C.c_int64)]
 
@@ -90,6 +95,12 @@ SIGNATURES = {
     "fse_cond_length_fill": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "fse_cond_frames": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32,
                                   _P, C.c_int64, _P]),
+    "fse_campnet_create": (C.c_int, [C.POINTER(CampNetConfig), C.POINTER(_P)]),
+    "fse_campnet_destroy": (None, [_P]),
+    "fse_campnet_load_weights": (C.c_int, [_P, C.POINTER(Tensor), C.c_int32]),
+    "fse_campnet_workspace_bytes": (C.c_int64, [_P, C.c_int32, C.c_int32, C.c_int32]),
+    "fse_campnet_last_launches": (C.c_int64, [_P]),
+    "fse_campnet_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "fse_denoiser_profile": (C.c_int, [_P, C.c_int32]),
     "fse_denoiser_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "fse_vocoder_profile": (C.c_int, [_P, C.c_int32]),

@@ -13,113 +13,11 @@
 // regulator, pitch bins) are small fp32 / int64 CUDA-core kernels.  The path runs once per batch in front of the
 // sampling loop (~2 MFLOP per frame against 25 MFLOP per frame and diffusion step), so the goal here is that no torch
 // arithmetic is left between the text tokens and `cond`, not peak throughput.
-#include <cmath>
-#include <deque>
-
-#include <cuda_bf16.h>
-#include <cuda_runtime.h>
-
-#include "fse_common.cuh"
+#include "rowwise.cuh"
 
 namespace fse {
 namespace {
 
-constexpr int kMaxPerLane = 16;   // channels per lane in the warp-per-row kernels: C <= 512, C % 32 == 0
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ void store_op(float* p, float v) { *p = v; }
-__device__ __forceinline__ void store_op(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
-
-// ---------------------------------------------------------------------------------------------- GEMM epilogues
-// ResidualBlock: gelu((conv_k(LN(x)) + b) * k^-0.5)   (conv.py:42-48; torch.nn.GELU() is the exact erf form)
-template <typename TOp>
-struct EpiGeluScale {
-  static constexpr int kAux = 0;
-  static constexpr bool kTransposed = true;
-  const float* bias;
-  TOp* out;   // [B*T, N]
-  int N, T;
-  float scale;
-  template <int NV>
-  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float*) const {
-    float v[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const float y = __fmul_rn(acc[i] + __ldg(bias + n0 + i), scale);
-      v[i] = 0.5f * y * (1.0f + erff(y * 0.70710678118654752f));
-    }
-    st_vec<NV>(out + (static_cast<size_t>(b) * T + t) * N + n0, v);
-  }
-};
-
-// ResidualBlock tail: x = (x + (conv_1x1(.) + b)) * nonpadding   (conv.py:59-64), x fp32 in place
-struct EpiResidualMask {
-  static constexpr int kAux = 1;
-  static constexpr bool kTransposed = true;
-  const float* bias;
-  float* x;            // [B*T, N] fp32 residual stream (read as aux, written here)
-  const float* mask;   // [B*T]
-  int N, T;
-  template <int NV>
-  __device__ __forceinline__ void load_aux(int b, int t, int n0, float* aux) const {
-    const size_t o = (static_cast<size_t>(b) * T + t) * N + n0;
-#pragma unroll
-    for (int i = 0; i < NV / 4; ++i) {
-      const float4 v = reinterpret_cast<const float4*>(x + o)[i];
-      aux[4 * i] = v.x; aux[4 * i + 1] = v.y; aux[4 * i + 2] = v.z; aux[4 * i + 3] = v.w;
-    }
-  }
-  template <int NV>
-  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float* aux) const {
-    const size_t row = static_cast<size_t>(b) * T + t;
-    const float m = __ldg(mask + row);
-    float v[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = __fmul_rn(__fadd_rn(aux[i], acc[i] + __ldg(bias + n0 + i)), m);
-    st_vec<NV>(x + row * N + n0, v);
-  }
-};
-
-// predictor layers: relu(conv_k(.) + b) in fp32 (LayerNorm follows; nar_tts_modules.py:16-21, 83-88)
-struct EpiReluF32 {
-  static constexpr int kAux = 0;
-  static constexpr bool kTransposed = true;
-  const float* bias;
-  float* out;   // [B*T, N]
-  int N, T;
-  template <int NV>
-  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float*) const {
-    float v[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = fmaxf(acc[i] + __ldg(bias + n0 + i), 0.f);
-    st_vec<NV>(out + (static_cast<size_t>(b) * T + t) * N + n0, v);
-  }
-};
-
-// post_net1: (conv_k(.) + b) * nonpadding   (conv.py:113)
-struct EpiBiasMaskF32 {
-  static constexpr int kAux = 0;
-  static constexpr bool kTransposed = true;
-  const float* bias;
-  const float* mask;   // [B*T]
-  float* out;          // [B*T, N]
-  int N, T;
-  template <int NV>
-  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float*) const {
-    const size_t row = static_cast<size_t>(b) * T + t;
-    const float m = __ldg(mask + row);
-    float v[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = __fmul_rn(acc[i] + __ldg(bias + n0 + i), m);
-    st_vec<NV>(out + row * N + n0, v);
-  }
-};
-
-// ---------------------------------------------------------------------------------------------- warp-per-row kernels
 // x = embed_scale * embed_tokens(txt) (conv.py:138) and the ConvBlocks-level nonpadding (|x|.sum(c) > 0, conv.py:104)
 __global__ void __launch_bounds__(256) cond_embed_tokens_kernel(const int64_t* __restrict__ txt, const float* __restrict__ table,
                                                                 float* __restrict__ x, float* __restrict__ mask0, int rows, int C,
@@ -137,56 +35,6 @@ __global__ void __launch_bounds__(256) cond_embed_tokens_kernel(const int64_t* _
   }
   sa = warp_sum(sa);
   if (lane == 0) mask0[row] = sa > 0.f ? 1.f : 0.f;
-}
-
-// channel LayerNorm of one row (layers.py:5-24; biased variance, eps inside the sqrt), two-pass in registers.
-//   in_scale[row]  (optional) multiplies the input first       (ConvBlocks: res_blocks(x) * nonpadding, conv.py:111)
-//   out_scale[row] (optional) multiplies the output            (last_norm(x) * nonpadding; predictor padding masks)
-//   mask_out[row]  (optional) receives (sum_c |input| > 0)     (ResidualBlock's own nonpadding, conv.py:58)
-//   out_op: operand of the next GEMM (bf16 / fp32 by mode); out_f32: fp32 copy for a CUDA-core head; either may be null
-template <typename TOp>
-__global__ void __launch_bounds__(256) cond_layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, const float* __restrict__ in_scale,
-                                                              const float* __restrict__ out_scale, float* __restrict__ mask_out,
-                                                              TOp* __restrict__ out_op, float* __restrict__ out_f32, int rows, int C,
-                                                              float eps) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float* xr = x + static_cast<size_t>(row) * C;
-  const int n = C >> 5;
-  const float si = in_scale ? __ldg(in_scale + row) : 1.f;
-  float v[kMaxPerLane];
-  float s = 0.f, sa = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
-    v[i] = 0.f;
-    if (i < n) {
-      float t = xr[lane + 32 * i];
-      if (in_scale) t = __fmul_rn(t, si);
-      v[i] = t; s += t; sa += fabsf(t);
-    }
-  }
-  s = warp_sum(s);
-  sa = warp_sum(sa);
-  const float mean = s / static_cast<float>(C);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i)
-    if (i < n) { const float d = v[i] - mean; q = fmaf(d, d, q); }
-  q = warp_sum(q);
-  const float rstd = 1.0f / sqrtf(q / static_cast<float>(C) + eps);
-  if (mask_out && lane == 0) mask_out[row] = sa > 0.f ? 1.f : 0.f;
-  const float so = out_scale ? __ldg(out_scale + row) : 1.f;
-#pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) {
-    if (i < n) {
-      const int c = lane + 32 * i;
-      float y = (v[i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-      if (out_scale) y = __fmul_rn(y, so);
-      if (out_op) store_op(out_op + static_cast<size_t>(row) * C + c, y);
-      if (out_f32) out_f32[static_cast<size_t>(row) * C + c] = y;
-    }
-  }
 }
 
 // dur_inp = (encoder_out + style) * (txt > 0)   (fs.py:90)
@@ -404,14 +252,6 @@ __global__ void __launch_bounds__(256) cond_frames_finish_kernel(const float* __
   }
 }
 
-// ---------------------------------------------------------------------------------------------- host side
-struct ConvW {
-  void* W = nullptr; float* bias = nullptr; CUtensorMap map{};
-  int Cin = 0, N = 0, ntaps = 0, KB = 64, Kp = 0, BN = 0;
-  int offs[kMaxTaps] = {};
-};
-struct LNW { float* g = nullptr; float* b = nullptr; };
-
 }  // namespace
 }  // namespace fse
 
@@ -419,12 +259,10 @@ using namespace fse;
 
 struct fse_cond_encoder {
   fse_cond_encoder_config cfg{};
-  bool bf16 = true, loaded = false;
+  LayerCtx ctx;
+  bool loaded = false;
   float* embed_tokens = nullptr;
-  std::vector<LNW> enc_ln;              // [layer * layers_in_block + j]
-  std::vector<ConvW> enc_c1, enc_c2;
-  LNW last_norm;
-  ConvW post;
+  ConvBlocksW enc;                      // TextConvEncoder's ConvBlocks
   float *spk_w = nullptr, *spk_b = nullptr;
   float* dur_embed = nullptr; int n_dur = 0;
   std::vector<ConvW> dur_conv; std::vector<LNW> dur_ln;
@@ -433,122 +271,13 @@ struct fse_cond_encoder {
   std::vector<ConvW> pitch_conv; std::vector<LNW> pitch_ln;
   float *pitch_lin_w = nullptr, *pitch_lin_b = nullptr;
   PitchConst pc{};
-  struct MapEntry { const void* buf; int C, T, B, KB; CUtensorMap map; };
-  std::deque<MapEntry> cache;
-  std::vector<void*> owned;             // every device allocation of the handle
-  long long launches = 0;
 };
 
 namespace {
 
-struct CWs { float* x32; float* tmp32; float* y32; void* opA; void* opB; float* m0; float* m1; size_t bytes; };
-CWs ccarve(const fse_cond_encoder* h, void* base, size_t rows) {
-  const size_t H = static_cast<size_t>(h->cfg.hidden), es = h->bf16 ? 2 : 4;
-  size_t off = 0;
-  auto take = [&](size_t b) { size_t o = off; off += align_up(b, 1024); return o; };
-  uint8_t* p = static_cast<uint8_t*>(base);
-  CWs w{};
-  w.x32 = reinterpret_cast<float*>(p + take(rows * H * 4));
-  w.tmp32 = reinterpret_cast<float*>(p + take(rows * H * 4));
-  w.y32 = reinterpret_cast<float*>(p + take(rows * H * 4));
-  w.opA = p + take(rows * H * es);
-  w.opB = p + take(rows * 2 * H * es);
-  w.m0 = reinterpret_cast<float*>(p + take(rows * 4));
-  w.m1 = reinterpret_cast<float*>(p + take(rows * 4));
-  w.bytes = off;
-  return w;
-}
-
-int dev_f32(fse_cond_encoder* h, const float* src, size_t n, float** out) {
-  FSE_TRY(upload_f32(std::vector<float>(src, src + n), out));
-  h->owned.push_back(*out);
-  return FSE_OK;
-}
-
-int load_vec(fse_cond_encoder* h, const TensorTable& tt, const std::string& name, int64_t numel, float** out) {
-  int rc = FSE_OK;
-  const float* p = tt.get(name, numel, &rc);
-  if (rc) return rc;
-  return dev_f32(h, p, static_cast<size_t>(numel), out);
-}
-
-// embedding table with a row count taken from the checkpoint (dur_embed: 2000 rows, pitch_embed: 300, fs.py:67,74)
-int load_table(fse_cond_encoder* h, const TensorTable& tt, const std::string& name, int C, float** out, int* rows) {
-  auto it = tt.map.find(name);
-  if (it == tt.map.end()) return fail(FSE_EINVAL, "missing weight tensor '%s'", name.c_str());
-  const int64_t numel = it->second->numel;
-  if (numel <= 0 || numel % C != 0) return fail(FSE_EINVAL, "weight '%s' has %lld elements, not a multiple of hidden %d", name.c_str(),
-                                                static_cast<long long>(numel), C);
-  *rows = static_cast<int>(numel / C);
-  return dev_f32(h, it->second->data, static_cast<size_t>(numel), out);
-}
-
-int load_ln(fse_cond_encoder* h, const TensorTable& tt, const std::string& name, int C, LNW& ln) {
-  FSE_TRY(load_vec(h, tt, name + ".weight", C, &ln.g));
-  return load_vec(h, tt, name + ".bias", C, &ln.b);
-}
-
-// Conv1d weight [Cout, Cin, k] (dilation dil, "same" padding) -> packed [Cout, k * nkb * KB], tap j at offset (j - (k-1)/2) dil
-int pack_conv(fse_cond_encoder* h, const TensorTable& tt, const std::string& name, int Cout, int Cin, int k, int dil, ConvW& cw) {
-  int rc = FSE_OK;
-  const float* w = tt.get(name + ".weight", static_cast<int64_t>(Cout) * Cin * k, &rc);
-  if (rc) return rc;
-  const float* bias = tt.get(name + ".bias", Cout, &rc);
-  if (rc) return rc;
-  if (k > kMaxTaps || k % 2 == 0) return fail(FSE_EINVAL, "%s: kernel size %d unsupported (odd, <= %d)", name.c_str(), k, kMaxTaps);
-  cw.Cin = Cin; cw.N = Cout; cw.ntaps = k; cw.KB = 64;
-  const int nkb = (Cin + 63) / 64;
-  cw.Kp = k * nkb * 64;
-  cw.BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32));   // tile widths exercised by tests/test_gpu_conv_gemm.py
-  if (Cout % cw.BN != 0) return fail(FSE_EINVAL, "%s: %d output channels is not a multiple of 32", name.c_str(), Cout);
-  for (int j = 0; j < k; ++j) cw.offs[j] = (j - (k - 1) / 2) * dil;
-  std::vector<float> p(static_cast<size_t>(Cout) * cw.Kp, 0.f);
-  for (int o = 0; o < Cout; ++o)
-    for (int c = 0; c < Cin; ++c)
-      for (int j = 0; j < k; ++j) p[static_cast<size_t>(o) * cw.Kp + j * nkb * 64 + c] = w[(static_cast<size_t>(o) * Cin + c) * k + j];
-  FSE_TRY(upload_operand(p, h->bf16, &cw.W));
-  h->owned.push_back(cw.W);
-  FSE_TRY(dev_f32(h, bias, Cout, &cw.bias));
-  if (h->cfg.mode == FSE_MODE_TC_BF16) FSE_TRY(make_map_w(&cw.map, cw.W, cw.Kp, cw.N, cw.KB, cw.BN));
-  return FSE_OK;
-}
-
-int get_act_map(fse_cond_encoder* h, const void* buf, int C, int T, int B, int KB, const CUtensorMap** out) {
-  for (auto& e : h->cache)
-    if (e.buf == buf && e.C == C && e.T == T && e.B == B && e.KB == KB) { *out = &e.map; return FSE_OK; }
-  if (h->cache.size() >= 64) h->cache.clear();      // maps are copied into the launch, dropping them is safe
-  h->cache.emplace_back();
-  auto& e = h->cache.back();
-  e.buf = buf; e.C = C; e.T = T; e.B = B; e.KB = KB;
-  const int rc = make_map_act(&e.map, buf, C, T, B, KB);
-  if (rc != FSE_OK) { h->cache.pop_back(); return rc; }
-  *out = &e.map;
-  return FSE_OK;
-}
-
-template <typename TOp, class Epi>
-int run_conv(fse_cond_encoder* h, const ConvW& cw, const void* A, int B, int T, const Epi& epi, cudaStream_t st) {
-  ConvGemmParams p = make_params(B, T, T, cw.Cin, cw.ntaps, cw.offs, 0, cw.N, cw.KB);
-  GemmOperands op; op.A0 = A; op.W = cw.W; op.mW = &cw.map; op.BN = cw.BN;
-  if (h->cfg.mode == FSE_MODE_TC_BF16) FSE_TRY(get_act_map(h, A, cw.Cin, T, B, cw.KB, &op.mA0));
-  return run_conv_gemm<TOp>(h->cfg.mode, p, op, epi, st, LaunchCtx{&h->launches, nullptr, 0});
-}
-
-inline unsigned row_blocks(size_t rows) { return static_cast<unsigned>((rows + 7) / 8); }
-
-template <typename TOp>
-int layer_norm(fse_cond_encoder* h, const float* x, const LNW& ln, const float* in_scale, const float* out_scale, float* mask_out,
-               void* out_op, float* out_f32, size_t rows, cudaStream_t st) {
-  cond_layer_norm_kernel<TOp><<<row_blocks(rows), 256, 0, st>>>(x, ln.g, ln.b, in_scale, out_scale, mask_out, static_cast<TOp*>(out_op),
-                                                               out_f32, static_cast<int>(rows), h->cfg.hidden, 1e-5f);
-  FSE_CUDA(cudaGetLastError());
-  ++h->launches;
-  return FSE_OK;
-}
-
 // conv -> ReLU -> LayerNorm [-> * keep] stack of the two predictors; the last layer's output goes to y32 (fp32) for the head
 template <typename TOp>
-int predictor_stack(fse_cond_encoder* h, const std::vector<ConvW>& convs, const std::vector<LNW>& lns, const CWs& w, const float* keep,
+int predictor_stack(fse_cond_encoder* h, const std::vector<ConvW>& convs, const std::vector<LNW>& lns, const RowBufs& w, const float* keep,
                     int B, int T, cudaStream_t st) {
   const size_t rows = static_cast<size_t>(B) * T;
   const int L = static_cast<int>(convs.size());
@@ -556,9 +285,9 @@ int predictor_stack(fse_cond_encoder* h, const std::vector<ConvW>& convs, const 
   void* out = w.opB;
   for (int i = 0; i < L; ++i) {
     EpiReluF32 epi{convs[i].bias, w.tmp32, convs[i].N, T};
-    FSE_TRY((run_conv<TOp>(h, convs[i], in, B, T, epi, st)));
+    FSE_TRY((run_conv<TOp>(&h->ctx, convs[i], in, B, T, epi, st)));
     const bool last = i == L - 1;
-    FSE_TRY((layer_norm<TOp>(h, w.tmp32, lns[i], nullptr, keep, nullptr, last ? nullptr : out, last ? w.y32 : nullptr, rows, st)));
+    FSE_TRY((layer_norm<TOp>(&h->ctx, w.tmp32, lns[i], nullptr, keep, nullptr, last ? nullptr : out, last ? w.y32 : nullptr, rows, st)));
     void* t = in; in = out; out = t;
   }
   return FSE_OK;
@@ -567,43 +296,30 @@ int predictor_stack(fse_cond_encoder* h, const std::vector<ConvW>& convs, const 
 template <typename TOp>
 int text_encoder_impl(fse_cond_encoder* h, const int64_t* txt, float* enc_out, int B, int Tt, void* ws, cudaStream_t st) {
   const size_t rows = static_cast<size_t>(B) * Tt;
-  const CWs w = ccarve(h, ws, rows);
-  const int H = h->cfg.hidden, k = h->cfg.enc_kernel_size;
+  const RowBufs w = carve_rows(h->ctx, ws, rows);
+  const int H = h->cfg.hidden;
   cond_embed_tokens_kernel<<<row_blocks(rows), 256, 0, st>>>(txt, h->embed_tokens, w.x32, w.m0, static_cast<int>(rows), H, h->cfg.vocab,
                                                             sqrtf(static_cast<float>(H)));
   FSE_CUDA(cudaGetLastError());
-  ++h->launches;
-  const float kscale = static_cast<float>(std::pow(static_cast<double>(k), -0.5));
-  for (int i = 0; i < h->cfg.enc_layers; ++i) {
-    for (int j = 0; j < h->cfg.layers_in_block; ++j) {
-      const int q = i * h->cfg.layers_in_block + j;
-      // the block's nonpadding comes from its own input: computed by the first LayerNorm pass over it
-      FSE_TRY((layer_norm<TOp>(h, w.x32, h->enc_ln[q], nullptr, nullptr, j == 0 ? w.m1 : nullptr, w.opA, nullptr, rows, st)));
-      EpiGeluScale<TOp> e1{h->enc_c1[q].bias, static_cast<TOp*>(w.opB), h->enc_c1[q].N, Tt, kscale};
-      FSE_TRY((run_conv<TOp>(h, h->enc_c1[q], w.opA, B, Tt, e1, st)));
-      EpiResidualMask e2{h->enc_c2[q].bias, w.x32, w.m1, H, Tt};
-      FSE_TRY((run_conv<TOp>(h, h->enc_c2[q], w.opB, B, Tt, e2, st)));
-    }
-  }
-  FSE_TRY((layer_norm<TOp>(h, w.x32, h->last_norm, w.m0, w.m0, nullptr, w.opA, nullptr, rows, st)));
-  EpiBiasMaskF32 e3{h->post.bias, w.m0, enc_out, H, Tt};
-  return run_conv<TOp>(h, h->post, w.opA, B, Tt, e3, st);
+  ++h->ctx.launches;
+  EpiBiasMaskF32 e3{h->enc.post.bias, w.m0, enc_out, H, Tt};
+  return conv_blocks_forward<TOp>(&h->ctx, h->enc, w, B, Tt, e3, st);
 }
 
 template <typename TOp>
 int duration_impl(fse_cond_encoder* h, const float* dur_inp, const int64_t* masked_dur, const int64_t* txt, float* dur, int B, int Tt,
                   void* ws, cudaStream_t st) {
   const size_t rows = static_cast<size_t>(B) * Tt;
-  const CWs w = ccarve(h, ws, rows);
+  const RowBufs w = carve_rows(h->ctx, ws, rows);
   cond_dur_embed_add_kernel<TOp><<<row_blocks(rows), 256, 0, st>>>(dur_inp, masked_dur, h->dur_embed, h->n_dur, txt,
                                                                   static_cast<TOp*>(w.opA), w.m0, static_cast<int>(rows), h->cfg.hidden);
   FSE_CUDA(cudaGetLastError());
-  ++h->launches;
+  ++h->ctx.launches;
   FSE_TRY((predictor_stack<TOp>(h, h->dur_conv, h->dur_ln, w, w.m0, B, Tt, st)));
   cond_head_kernel<true><<<row_blocks(rows), 256, 0, st>>>(w.y32, h->dur_lin_w, h->dur_lin_b, w.m0, dur, static_cast<int>(rows),
                                                           h->cfg.hidden, 1);
   FSE_CUDA(cudaGetLastError());
-  ++h->launches;
+  ++h->ctx.launches;
   return FSE_OK;
 }
 
@@ -612,30 +328,30 @@ int frames_impl(fse_cond_encoder* h, const float* enc, const float* style, const
                 const float* uv, int use_pred_pitch, float* decoder_inp, float* pitch_pred, float* f0_denorm, float* f0_denorm_pred,
                 int64_t* pitch, int B, int Tt, int T, void* ws, cudaStream_t st) {
   const size_t rows = static_cast<size_t>(B) * T;
-  const CWs w = ccarve(h, ws, rows);
+  const RowBufs w = carve_rows(h->ctx, ws, rows);
   const int H = h->cfg.hidden, up = h->cfg.use_pitch_embed, uu = h->cfg.use_uv;
   cond_frames_prepare_kernel<TOp><<<row_blocks(rows), 256, 0, st>>>(enc, style, mel2ph, mask, f0, uv, h->pitch_embed, w.x32,
                                                                    static_cast<TOp*>(w.opA), static_cast<int>(rows), T, Tt, H, up, uu, h->pc);
   FSE_CUDA(cudaGetLastError());
-  ++h->launches;
+  ++h->ctx.launches;
   if (up) {
     FSE_TRY((predictor_stack<TOp>(h, h->pitch_conv, h->pitch_ln, w, nullptr, B, T, st)));
     cond_head_kernel<false><<<row_blocks(rows), 256, 0, st>>>(w.y32, h->pitch_lin_w, h->pitch_lin_b, nullptr, pitch_pred,
                                                              static_cast<int>(rows), H, 2);
     FSE_CUDA(cudaGetLastError());
-    ++h->launches;
+    ++h->ctx.launches;
   }
   cond_frames_finish_kernel<<<row_blocks(rows), 256, 0, st>>>(w.x32, style, mel2ph, mask, f0, uv, pitch_pred, h->pitch_embed, decoder_inp,
                                                              f0_denorm, f0_denorm_pred, pitch, static_cast<int>(rows), T, H, up, uu,
                                                              use_pred_pitch, h->pc);
   FSE_CUDA(cudaGetLastError());
-  ++h->launches;
+  ++h->ctx.launches;
   return FSE_OK;
 }
 
 int check_ws(const fse_cond_encoder* h, void* ws, int64_t ws_bytes, size_t rows) {
   if (!ws || (reinterpret_cast<uintptr_t>(ws) & 1023)) return fail(FSE_EINVAL, "workspace must be non-null and 1024-byte aligned");
-  if (ws_bytes < static_cast<int64_t>(ccarve(h, nullptr, rows).bytes)) return fail(FSE_EINVAL, "workspace too small");
+  if (ws_bytes < static_cast<int64_t>(carve_rows(h->ctx, nullptr, rows).bytes)) return fail(FSE_EINVAL, "workspace too small");
   return FSE_OK;
 }
 int check_ready(const fse_cond_encoder* h) {
@@ -666,7 +382,9 @@ int fse_cond_encoder_create(const fse_cond_encoder_config* cfg, fse_cond_encoder
   if (prop.major != 10) return fail(FSE_ECUDA, "device is sm_%d%d; this library is built for sm_100a only (no fallback)", prop.major, prop.minor);
   auto* h = new fse_cond_encoder();
   h->cfg = *cfg;
-  h->bf16 = cfg->mode != FSE_MODE_SIMT_F32;
+  h->ctx.mode = cfg->mode;
+  h->ctx.bf16 = cfg->mode != FSE_MODE_SIMT_F32;
+  h->ctx.hidden = cfg->hidden;
   const double mel_min = 1127.0 * std::log(1.0 + 50.0 / 700.0), mel_max = 1127.0 * std::log(1.0 + 900.0 / 700.0);
   h->pc.mel_min = static_cast<float>(mel_min);
   h->pc.mel_rng = static_cast<float>(mel_max - mel_min);
@@ -676,7 +394,7 @@ int fse_cond_encoder_create(const fse_cond_encoder_config* cfg, fse_cond_encoder
 
 void fse_cond_encoder_destroy(fse_cond_encoder* h) {
   if (!h) return;
-  for (void* p : h->owned) cudaFree(p);
+  h->ctx.release();
   delete h;
 }
 
@@ -685,43 +403,34 @@ int fse_cond_encoder_load_weights(fse_cond_encoder* h, const fse_tensor* tensors
   if (h->loaded) return fail(FSE_ESTATE, "weights already loaded");
   TensorTable tt(tensors, n);
   const auto& c = h->cfg;
-  const int H = c.hidden, nsub = c.enc_layers * c.layers_in_block;
-  FSE_TRY(load_vec(h, tt, "encoder.embed_tokens.weight", static_cast<int64_t>(c.vocab) * H, &h->embed_tokens));
-  h->enc_ln.resize(nsub); h->enc_c1.resize(nsub); h->enc_c2.resize(nsub);
-  for (int i = 0; i < c.enc_layers; ++i)
-    for (int j = 0; j < c.layers_in_block; ++j) {
-      const int q = i * c.layers_in_block + j;
-      const std::string pre = "encoder.res_blocks." + std::to_string(i) + ".blocks." + std::to_string(j) + ".";
-      FSE_TRY(load_ln(h, tt, pre + "0", H, h->enc_ln[q]));
-      FSE_TRY(pack_conv(h, tt, pre + "1", 2 * H, H, c.enc_kernel_size, c.enc_dilations[i], h->enc_c1[q]));
-      FSE_TRY(pack_conv(h, tt, pre + "4", H, 2 * H, 1, 1, h->enc_c2[q]));
-    }
-  FSE_TRY(load_ln(h, tt, "encoder.last_norm", H, h->last_norm));
-  FSE_TRY(pack_conv(h, tt, "encoder.post_net1", H, H, c.enc_post_net_kernel, 1, h->post));
+  const int H = c.hidden;
+  LayerCtx* ctx = &h->ctx;
+  FSE_TRY(load_vec(ctx, tt, "encoder.embed_tokens.weight", static_cast<int64_t>(c.vocab) * H, &h->embed_tokens));
+  FSE_TRY(load_conv_blocks(ctx, tt, "encoder.", c.enc_layers, c.enc_dilations, c.layers_in_block, c.enc_kernel_size, c.enc_post_net_kernel, h->enc));
   if (c.spk_embed_dim > 0) {
-    FSE_TRY(load_vec(h, tt, "spk_embed_proj.weight", static_cast<int64_t>(H) * c.spk_embed_dim, &h->spk_w));
-    FSE_TRY(load_vec(h, tt, "spk_embed_proj.bias", H, &h->spk_b));
+    FSE_TRY(load_vec(ctx, tt, "spk_embed_proj.weight", static_cast<int64_t>(H) * c.spk_embed_dim, &h->spk_w));
+    FSE_TRY(load_vec(ctx, tt, "spk_embed_proj.bias", H, &h->spk_b));
   }
-  FSE_TRY(load_table(h, tt, "dur_embed.weight", H, &h->dur_embed, &h->n_dur));
+  FSE_TRY(load_table(ctx, tt, "dur_embed.weight", H, &h->dur_embed, &h->n_dur));
   h->dur_conv.resize(c.dur_predictor_layers); h->dur_ln.resize(c.dur_predictor_layers);
   for (int i = 0; i < c.dur_predictor_layers; ++i) {
     const std::string pre = "dur_predictor.conv." + std::to_string(i) + ".";
-    FSE_TRY(pack_conv(h, tt, pre + "0", H, H, c.dur_predictor_kernel, 1, h->dur_conv[i]));
-    FSE_TRY(load_ln(h, tt, pre + "2", H, h->dur_ln[i]));
+    FSE_TRY(pack_conv(ctx, tt, pre + "0", H, H, c.dur_predictor_kernel, 1, h->dur_conv[i]));
+    FSE_TRY(load_ln(ctx, tt, pre + "2", H, h->dur_ln[i]));
   }
-  FSE_TRY(load_vec(h, tt, "dur_predictor.linear.0.weight", H, &h->dur_lin_w));
-  FSE_TRY(load_vec(h, tt, "dur_predictor.linear.0.bias", 1, &h->dur_lin_b));
+  FSE_TRY(load_vec(ctx, tt, "dur_predictor.linear.0.weight", H, &h->dur_lin_w));
+  FSE_TRY(load_vec(ctx, tt, "dur_predictor.linear.0.bias", 1, &h->dur_lin_b));
   if (c.use_pitch_embed) {
-    FSE_TRY(load_table(h, tt, "pitch_embed.weight", H, &h->pitch_embed, &h->n_pitch));
+    FSE_TRY(load_table(ctx, tt, "pitch_embed.weight", H, &h->pitch_embed, &h->n_pitch));
     if (h->n_pitch < 256) return fail(FSE_EINVAL, "pitch_embed has %d rows; f0_to_coarse produces bins up to 255", h->n_pitch);
     h->pitch_conv.resize(c.pitch_predictor_layers); h->pitch_ln.resize(c.pitch_predictor_layers);
     for (int i = 0; i < c.pitch_predictor_layers; ++i) {
       const std::string pre = "pitch_predictor.conv." + std::to_string(i) + ".";
-      FSE_TRY(pack_conv(h, tt, pre + "0", H, H, c.predictor_kernel, 1, h->pitch_conv[i]));
-      FSE_TRY(load_ln(h, tt, pre + "2", H, h->pitch_ln[i]));
+      FSE_TRY(pack_conv(ctx, tt, pre + "0", H, H, c.predictor_kernel, 1, h->pitch_conv[i]));
+      FSE_TRY(load_ln(ctx, tt, pre + "2", H, h->pitch_ln[i]));
     }
-    FSE_TRY(load_vec(h, tt, "pitch_predictor.linear.weight", 2 * static_cast<int64_t>(H), &h->pitch_lin_w));
-    FSE_TRY(load_vec(h, tt, "pitch_predictor.linear.bias", 2, &h->pitch_lin_b));
+    FSE_TRY(load_vec(ctx, tt, "pitch_predictor.linear.weight", 2 * static_cast<int64_t>(H), &h->pitch_lin_w));
+    FSE_TRY(load_vec(ctx, tt, "pitch_predictor.linear.bias", 2, &h->pitch_lin_b));
   }
   h->loaded = true;
   return FSE_OK;
@@ -730,10 +439,10 @@ int fse_cond_encoder_load_weights(fse_cond_encoder* h, const fse_tensor* tensors
 int64_t fse_cond_encoder_workspace_bytes(const fse_cond_encoder* h, int32_t B, int32_t Tt, int32_t T) {
   if (!h || B <= 0 || (Tt <= 0 && T <= 0)) return 0;
   const size_t rows = static_cast<size_t>(B) * static_cast<size_t>(Tt > T ? Tt : T);
-  return static_cast<int64_t>(ccarve(h, nullptr, rows).bytes);
+  return static_cast<int64_t>(carve_rows(h->ctx, nullptr, rows).bytes);
 }
 
-int64_t fse_cond_encoder_last_launches(const fse_cond_encoder* h) { return h ? h->launches : 0; }
+int64_t fse_cond_encoder_last_launches(const fse_cond_encoder* h) { return h ? h->ctx.launches : 0; }
 
 int fse_cond_text_encoder(fse_cond_encoder* h, const int64_t* txt, float* encoder_out, int32_t B, int32_t Tt, void* workspace,
                           int64_t workspace_bytes, void* stream) {
@@ -741,9 +450,9 @@ int fse_cond_text_encoder(fse_cond_encoder* h, const int64_t* txt, float* encode
   if (!txt || !encoder_out) return fail(FSE_EINVAL, "null argument");
   if (B <= 0 || Tt <= 0) return fail(FSE_EINVAL, "B and Tt must be positive");
   FSE_TRY(check_ws(h, workspace, workspace_bytes, static_cast<size_t>(B) * Tt));
-  h->launches = 0;
+  h->ctx.launches = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return h->bf16 ? text_encoder_impl<__nv_bfloat16>(h, txt, encoder_out, B, Tt, workspace, st)
+  return h->ctx.bf16 ? text_encoder_impl<__nv_bfloat16>(h, txt, encoder_out, B, Tt, workspace, st)
                  : text_encoder_impl<float>(h, txt, encoder_out, B, Tt, workspace, st);
 }
 
@@ -752,7 +461,7 @@ int fse_cond_style_embed(fse_cond_encoder* h, const float* spk_embed, float* sty
   if (!spk_embed || !style) return fail(FSE_EINVAL, "null argument");
   if (B <= 0) return fail(FSE_EINVAL, "B must be positive");
   if (h->cfg.spk_embed_dim <= 0) return fail(FSE_ESTATE, "handle was created without a speaker embedding (spk_embed_dim = 0)");
-  h->launches = 1;
+  h->ctx.launches = 1;
   cond_style_kernel<<<B, 192, 0, static_cast<cudaStream_t>(stream)>>>(spk_embed, h->spk_w, h->spk_b, style, h->cfg.spk_embed_dim, h->cfg.hidden);
   FSE_CUDA(cudaGetLastError());
   return FSE_OK;
@@ -764,7 +473,7 @@ int fse_cond_dur_input(fse_cond_encoder* h, const float* encoder_out, const floa
   if (!encoder_out || !txt || !dur_inp) return fail(FSE_EINVAL, "null argument");
   if (B <= 0 || Tt <= 0) return fail(FSE_EINVAL, "B and Tt must be positive");
   const size_t rows = static_cast<size_t>(B) * Tt;
-  h->launches = 1;
+  h->ctx.launches = 1;
   cond_dur_input_kernel<<<row_blocks(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(encoder_out, style, txt, dur_inp,
                                                                                          static_cast<int>(rows), Tt, h->cfg.hidden);
   FSE_CUDA(cudaGetLastError());
@@ -779,7 +488,7 @@ int fse_cond_masked_dur(fse_cond_encoder* h, const int64_t* mel2ph, const float*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   FSE_CUDA(cudaMemsetAsync(masked_dur, 0, static_cast<size_t>(B) * Tt * sizeof(int64_t), st));
   const size_t n = static_cast<size_t>(B) * T;
-  h->launches = 1;
+  h->ctx.launches = 1;
   cond_masked_dur_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(mel2ph, mask, txt, masked_dur, B, T, Tt);
   FSE_CUDA(cudaGetLastError());
   return FSE_OK;
@@ -791,9 +500,9 @@ int fse_cond_duration(fse_cond_encoder* h, const float* dur_inp, const int64_t* 
   if (!dur_inp || !masked_dur || !txt || !dur) return fail(FSE_EINVAL, "null argument");
   if (B <= 0 || Tt <= 0) return fail(FSE_EINVAL, "B and Tt must be positive");
   FSE_TRY(check_ws(h, workspace, workspace_bytes, static_cast<size_t>(B) * Tt));
-  h->launches = 0;
+  h->ctx.launches = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return h->bf16 ? duration_impl<__nv_bfloat16>(h, dur_inp, masked_dur, txt, dur, B, Tt, workspace, st)
+  return h->ctx.bf16 ? duration_impl<__nv_bfloat16>(h, dur_inp, masked_dur, txt, dur, B, Tt, workspace, st)
                  : duration_impl<float>(h, dur_inp, masked_dur, txt, dur, B, Tt, workspace, st);
 }
 
@@ -802,7 +511,7 @@ int fse_cond_length_cumsum(fse_cond_encoder* h, const float* dur, const int64_t*
   if (!h) return fail(FSE_EINVAL, "null handle");
   if (!dur || !cumsum || !totals) return fail(FSE_EINVAL, "null argument");
   if (B <= 0 || Tt <= 0) return fail(FSE_EINVAL, "B and Tt must be positive");
-  h->launches = 1;
+  h->ctx.launches = 1;
   cond_length_cumsum_kernel<<<(B + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(dur, txt, cumsum, totals, B, Tt);
   FSE_CUDA(cudaGetLastError());
   return FSE_OK;
@@ -813,7 +522,7 @@ int fse_cond_length_fill(fse_cond_encoder* h, const int64_t* cumsum, int64_t* me
   if (!cumsum || !mel2ph) return fail(FSE_EINVAL, "null argument");
   if (B <= 0 || Tt <= 0 || Tmax <= 0) return fail(FSE_EINVAL, "B, Tt and Tmax must be positive");
   const size_t n = static_cast<size_t>(B) * Tmax;
-  h->launches = 1;
+  h->ctx.launches = 1;
   cond_length_fill_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(cumsum, mel2ph, B, Tt, Tmax);
   FSE_CUDA(cudaGetLastError());
   return FSE_OK;
@@ -829,9 +538,9 @@ int fse_cond_frames(fse_cond_encoder* h, const float* encoder_out, const float* 
   if (h->cfg.use_pitch_embed && (!f0 || !uv || !pitch_pred || !f0_denorm || !f0_denorm_pred))
     return fail(FSE_EINVAL, "use_pitch_embed: f0, uv, pitch_pred, f0_denorm and f0_denorm_pred are required");
   FSE_TRY(check_ws(h, workspace, workspace_bytes, static_cast<size_t>(B) * T));
-  h->launches = 0;
+  h->ctx.launches = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return h->bf16 ? frames_impl<__nv_bfloat16>(h, encoder_out, style, mel2ph, mask, f0, uv, use_pred_pitch, decoder_inp, pitch_pred, f0_denorm,
+  return h->ctx.bf16 ? frames_impl<__nv_bfloat16>(h, encoder_out, style, mel2ph, mask, f0, uv, use_pred_pitch, decoder_inp, pitch_pred, f0_denorm,
                                               f0_denorm_pred, pitch, B, Tt, T, workspace, st)
                  : frames_impl<float>(h, encoder_out, style, mel2ph, mask, f0, uv, use_pred_pitch, decoder_inp, pitch_pred, f0_denorm,
                                       f0_denorm_pred, pitch, B, Tt, T, workspace, st);

@@ -443,3 +443,57 @@ class CondEncoderKernel:
                                          B, Tt, T, ws, nbytes, _stream()))
         self._done()
         return ret
+
+
+class CampNetKernel:
+    """Handle of the CampNet mask-predict forward (fse_campnet_*; modules/speech_editing/campnet/campnet.py:14-69)."""
+
+    def __init__(self, vocab: int, hidden: int = 192, n_mels: int = 80, enc_layers: int = 3, dec_layers: int = 6, heads: int = 2,
+                 ffn_kernel: int = 9, fine_blocks: int = 5, fine_kernel: int = 5, mode="tc_bf16"):
+        cfg = _lib.CampNetConfig()
+        cfg.hidden, cfg.vocab, cfg.n_mels, cfg.enc_layers, cfg.dec_layers = hidden, vocab, n_mels, enc_layers, dec_layers
+        cfg.heads, cfg.ffn_kernel, cfg.fine_blocks, cfg.fine_kernel, cfg.mode = heads, ffn_kernel, fine_blocks, fine_kernel, MODES[mode]
+        self.cfg, self.mode, self.hidden, self.n_mels = cfg, mode, hidden, n_mels
+        self._h = C.c_void_p()
+        check(_lib.lib().fse_campnet_create(C.byref(cfg), C.byref(self._h)))
+        self._ws = _Workspace()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _lib.lib().fse_campnet_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def load_state_dict(self, sd: Dict[str, object]):
+        """A reference CampNet state_dict; entries the forward never reads (encoder.pre_net.*, mel_out.*, *._float_tensor) are skipped."""
+        sd = {k: v for k, v in sd.items() if not (k.startswith(("encoder.pre_net.", "mel_out.")) or k.endswith("_float_tensor"))}
+        arr, n, keep = _tensor_table(sd)
+        check(_lib.lib().fse_campnet_load_weights(self._h, arr, n))
+        del keep
+
+    @property
+    def last_launches(self) -> int:
+        return int(_lib.lib().fse_campnet_last_launches(self._h))
+
+    def forward(self, txt: torch.Tensor, mels: torch.Tensor, time_mel_masks: torch.Tensor, need_attn: bool = True, need_encoder_out: bool = False):
+        """txt[B,Tt] int64, mels[B,T,M], time_mel_masks[B,T(,1)] 0/1 -> dict(mel_out_coarse, mel_out_fine [B,T,M], attn [B,T,Tt])"""
+        _need_cuda(txt, mels, time_mel_masks)
+        B, Tt = txt.shape
+        T = mels.shape[1]
+        dev = mels.device
+        txt, mels = txt.contiguous().long(), mels.contiguous().float()
+        mask = time_mel_masks.reshape(B, T).contiguous().float()
+        coarse = torch.empty(B, T, self.n_mels, dtype=torch.float32, device=dev)
+        fine = torch.empty_like(coarse)
+        attn = torch.empty(B, T, Tt, dtype=torch.float32, device=dev) if need_attn else None
+        enc = torch.empty(B, Tt, self.hidden, dtype=torch.float32, device=dev) if need_encoder_out else None
+        nbytes = _lib.lib().fse_campnet_workspace_bytes(self._h, B, Tt, T)
+        ws, nbytes = self._ws.get(nbytes, dev)
+        check(_lib.lib().fse_campnet_forward(self._h, _ptr(txt), _ptr(mels), _ptr(mask), _ptr(coarse), _ptr(fine), _ptr(attn), _ptr(enc),
+                                             B, Tt, T, ws, nbytes, _stream()))
+        ret = {"mel_out_coarse": coarse, "mel_out_fine": fine, "attn": attn}
+        if need_encoder_out:
+            ret["encoder_out"] = enc
+        return ret

@@ -4,6 +4,7 @@
   GaussianDiffusionB200  <-> modules/speech_editing/spec_denoiser/spec_denoiser.py::GaussianDiffusion (:16-185)
   MelEncoderB200         <-> modules/speech_editing/commons/mel_encoder.py::MelEncoder        (:3-19)
   FastSpeechB200         <-> modules/speech_editing/spec_denoiser/fs.py::FastSpeech           (:49-189, skip_decoder=True)
+  CampNetB200            <-> modules/speech_editing/campnet/campnet.py::CampNet               (:14-69)
 
 Same constructor arguments, same state_dict keys/shapes (reference checkpoints load unchanged), same
 forward() signatures and return values.  The nn.Modules only OWN the parameters; every forward goes
@@ -18,7 +19,7 @@ import torch
 from torch import nn
 
 from . import schedule as _schedule
-from .engine import CondEncoderKernel, Denoiser, MelEncoderKernel
+from .engine import CampNetKernel, CondEncoderKernel, Denoiser, MelEncoderKernel
 from .hparams import hparams as _global_hparams
 
 
@@ -268,6 +269,110 @@ class FastSpeechB200(nn.Module):
 
 
 FastSpeech = FastSpeechB200     # the name the reference uses
+
+
+class _MHAParams(nn.Module):
+    """MultiheadAttention with bias=False (speech_editing/commons/transformer.py:160-174): in_proj_weight [3C, C], out_proj.weight."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * c, c))
+        self.out_proj = nn.Linear(c, c, bias=False)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.xavier_uniform_(self.out_proj.weight)
+
+
+class _FFNParams(nn.Module):
+    """TransformerFFNLayer (transformer.py:74-90): ffn_1 = Conv1d ('SAME') or Sequential(ConstantPad1d, Conv1d) ('LEFT'), ffn_2 = Linear."""
+
+    def __init__(self, c, k, left):
+        super().__init__()
+        conv = nn.Conv1d(c, 4 * c, k, padding=0 if left else k // 2)
+        self.ffn_1 = nn.Sequential(nn.Identity(), conv) if left else conv
+        self.ffn_2 = nn.Linear(4 * c, c)
+
+
+class _SALayerParams(nn.Module):
+    """EncSALayer / DecSALayer parameters under `.op` (transformer.py:489-546, 611-636)."""
+
+    def __init__(self, c, k, decoder):
+        super().__init__()
+        op = nn.Module()
+        op.layer_norm1 = nn.LayerNorm(c)
+        op.self_attn = _MHAParams(c)
+        op.layer_norm2 = nn.LayerNorm(c)
+        if decoder:
+            op.encoder_attn = _MHAParams(c)
+            op.layer_norm3 = nn.LayerNorm(c)
+        op.ffn = _FFNParams(c, k, left=decoder)
+        self.op = op
+
+
+class _PosEmbedParams(nn.Module):
+    """SinusoidalPositionalEmbedding keeps one persistent buffer, `_float_tensor` (transformer.py:30)."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("_float_tensor", torch.zeros(1))
+
+
+class CampNetB200(nn.Module):
+    """Drop-in for the reference's CampNet on its forward (campnet.py:14-69): same constructor (ph_dict_size, word_dict_size,
+    hparams, out_dims), the same 237 state_dict keys and shapes (unused ones included, so checkpoints strict-load) and
+    forward(txt_tokens, spk_embed=None, spk_id=None, mels=None, stutter_mel_masks=None, time_mel_masks=None, infer=False,
+    global_step=None) -> dict(mel_out_coarse, mel_out_fine, attn).  The module only owns the parameters; the forward is one
+    C-ABI call (fse_campnet_forward)."""
+
+    def __init__(self, ph_dict_size, word_dict_size=None, hparams: Optional[dict] = None, out_dims=None):
+        super().__init__()
+        hp = dict(_global_hparams if hparams is None else hparams)
+        self.hparams = hp
+        C_ = self.hidden_size = hp["hidden_size"]
+        k = self.ffn_kernel = hp.get("dec_ffn_kernel_size", 9)
+        self.out_dims = hp.get("audio_num_mel_bins", 80) if out_dims is None else out_dims
+        self.ph_dict_size = ph_dict_size
+        self.mode = hp.get("b200_mode", "tc_bf16")
+        enc = nn.Module()
+        enc.layers = nn.ModuleList([_SALayerParams(C_, k, decoder=False) for _ in range(3)])
+        enc.layer_norm = nn.LayerNorm(C_)
+        enc.embed_tokens = _embedding(ph_dict_size, C_, 0)
+        enc.pre_net = _ConvBlocksParams(C_, [1] * 3, 1, 2, 3)            # constructed by the reference, never called (transformer.py:751)
+        enc.embed_positions = _PosEmbedParams()
+        self.encoder = enc
+        self.mel_out = nn.Linear(C_, self.out_dims, bias=True)             # inherited from FastSpeech, unused
+        self.mel_encoder = nn.Module()
+        self.mel_encoder.encoder = nn.Sequential(nn.Linear(self.out_dims, C_), nn.ReLU(), nn.Linear(C_, C_), nn.ReLU())
+        self.mel_encoder.fc_out = nn.Linear(C_, C_)
+        dec = nn.Module()
+        dec.pos_embed_alpha = nn.Parameter(torch.ones(1))
+        dec.embed_positions = _PosEmbedParams()
+        dec.layers = nn.ModuleList([_SALayerParams(C_, k, decoder=True) for _ in range(6)])
+        dec.layer_norm = nn.LayerNorm(C_)
+        self.decoder_coarse = dec
+        self.decoder_fine = _ConvBlocksParams(C_, [1] * 5, 5, 2, 3)
+        self.mel_out_coarse = nn.Linear(C_, self.out_dims, bias=False)
+        self.mel_out_fine = nn.Linear(C_, self.out_dims, bias=False)
+        self.mask_emb = nn.Parameter(torch.zeros(1, 1, self.out_dims))
+        self._engine: Optional[CampNetKernel] = None
+        self._engine_key = None
+
+    def engine(self) -> CampNetKernel:
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._engine is None or key != self._engine_key:
+            eng = CampNetKernel(self.ph_dict_size, self.hidden_size, self.out_dims, 3, 6, 2, self.ffn_kernel, 5, 5, self.mode)
+            eng.load_state_dict(self.state_dict())
+            self._engine, self._engine_key = eng, key
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, txt_tokens, spk_embed=None, spk_id=None, mels=None, stutter_mel_masks=None, time_mel_masks=None, infer=False,
+                global_step=None, *args, **kwargs):
+        """campnet.py:40-45 (spk_embed / spk_id / stutter_mel_masks are accepted and ignored, as in the reference)."""
+        out = self.engine().forward(txt_tokens, mels, time_mel_masks)
+        return {"mel_out_coarse": out["mel_out_coarse"], "mel_out_fine": out["mel_out_fine"], "attn": out["attn"]}
+
+
+CampNet = CampNetB200     # the name the reference uses
 
 
 class GaussianDiffusionB200(nn.Module):

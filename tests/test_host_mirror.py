@@ -154,3 +154,29 @@ def test_fastspeech_state_dict_matches_live_reference():
     ours = FastSpeechB200(80, dict(hp))
     assert {k: tuple(v.shape) for k, v in ours.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
     ours.load_state_dict(ref.state_dict(), strict=True)
+
+
+def test_campnet_drop_in_surface_and_state_dict():
+    """CampNetB200 mirrors campnet.py:14-69: constructor (ph_dict_size, word_dict_size, hparams), every tensor of the synthetic
+    checkpoint at the reference's key / shape, forward signature of the reference."""
+    import inspect
+    from speech_editing_toolkit_b200.modules import CampNetB200
+    net = CampNetB200(80, 100, dict(hidden_size=192, dec_ffn_kernel_size=9, audio_num_mel_bins=80))
+    own = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    sd = synth.campnet_state_dict(3, 80)
+    assert all(own[k] == v.shape for k, v in sd.items())
+    assert all(k.startswith(("encoder.pre_net.", "mel_out.")) or k.endswith("_float_tensor") for k in set(own) - set(sd))
+    assert len(own) == 237
+    params = list(inspect.signature(net.forward).parameters)
+    assert params[:8] == ["txt_tokens", "spk_embed", "spk_id", "mels", "stutter_mel_masks", "time_mel_masks", "infer", "global_step"]
+
+
+@needs_ref
+def test_campnet_state_dict_matches_live_reference():
+    hp = refshim.install("egs/campnet.yaml")
+    from modules.speech_editing.campnet.campnet import CampNet
+    from speech_editing_toolkit_b200.modules import CampNetB200
+    ref = CampNet(80, 100, hp)
+    ours = CampNetB200(80, 100, dict(hp))
+    assert {k: tuple(v.shape) for k, v in ours.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    ours.load_state_dict(ref.state_dict(), strict=True)
