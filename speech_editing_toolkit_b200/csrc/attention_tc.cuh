@@ -1,0 +1,259 @@
+// Tensor-core attention for sm_100a: O = softmax(Q K^T) V per (item, head), head_dim 96, bf16 operands, fp32 softmax.
+// (MultiheadAttention.forward of the reference, modules/speech_editing/commons/transformer.py:365-407; q carries head_dim^-0.5.)
+//
+// One CTA = 128 queries of one (item, head); keys / values stream through shared memory in tiles of 128 keys.
+//   warp 0   TMA producer: Q once; per tile K [128 keys x 96] and V^T [96 x 128 keys] (two 64-column boxes each, 128B swizzle,
+//            out-of-range rows / keys zero-filled), double buffered
+//   warp 1   tcgen05.mma issuer + TMEM owner:  S_j = Q K_j^T (M 128 x N 128, K = 96 as 4 + 2 UMMA_K steps) into one of two
+//            TMEM buffers, then O_j = P_j V_j (M 128 x N 96, K = 128 keys) into a third; S_{j+1} is issued before P_j is awaited
+//   warps 2-5 softmax: thread = query row = TMEM lane.  Two passes over the S row in TMEM (max, then exp / sum), P written to
+//            shared memory as bf16 in the UMMA K-major 128B-swizzled layout (the A operand of the P.V MMA), running
+//            (max, sum) per row, O accumulated in registers: o = o * alpha + O_j read back from TMEM (no TMEM read-modify-write)
+// Masking as in the reference: padded keys get -1e8 (exp underflows to exactly 0), keys past Tk are excluded.
+// V^T ([B * heads * 96, Tkp] bf16, keys contiguous) is written by the q/k/v projection's epilogue (EpiScaleCols::vt), so both
+// MMA operands are K-major and the verified descriptor forms of conv_gemm.cuh apply unchanged.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "fse_common.cuh"
+
+namespace fse {
+namespace {
+
+constexpr int kAttD = 96;            // head_dim (hidden 192 / 2 heads)
+constexpr int kAtcM = 128;           // queries per CTA (TMEM lanes)
+constexpr int kAtcN = 128;           // keys per tile
+constexpr int kAtcKB = 16384;        // one 64-column k-block of a 128-row operand tile: 128 rows x 128 B
+constexpr int kAtcVB = 12288;        // one 64-key k-block of the V^T tile: 96 rows x 128 B
+constexpr int kAtcThreads = 192;
+constexpr int kAtcSmemBytes = 1024 /*alignment slack*/ + 2 * kAtcKB /*Q*/ + 2 * 2 * kAtcKB /*K x2*/ + 2 * 2 * kAtcVB /*V^T x2*/ +
+                              2 * kAtcKB /*P*/ + 2 * kAtcN * 4 /*key flags x2*/ + 256 /*barriers + TMEM slot*/;
+
+struct AttnTcParams {
+  int Tq, Tk, heads;
+  int qoff, koff;              // first column of head 0's queries / keys inside their rows
+  int ldo;                     // row stride of O in elements
+  const float* key_keep;       // [B, Tk] 1 = attend, 0 = padded key; or null
+  __nv_bfloat16* O;            // [B, Tq, ldo], head h at columns h*96
+};
+
+__global__ void __launch_bounds__(kAtcThreads, 1) camp_attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ,
+                                                                           const __grid_constant__ CUtensorMap mapK,
+                                                                           const __grid_constant__ CUtensorMap mapVt, AttnTcParams p) {
+  extern __shared__ uint8_t atc_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(atc_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = base;
+  uint8_t* sK = sQ + 2 * kAtcKB;
+  uint8_t* sV = sK + 4 * kAtcKB;
+  uint8_t* sP = sV + 4 * kAtcVB;
+  float* sKeep = reinterpret_cast<float*>(sP + 2 * kAtcKB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKeep + 2 * kAtcN);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;    // [2]
+  uint64_t* kv_empty = bars + 3;   // [2]
+  uint64_t* s_full = bars + 5;     // [2]
+  uint64_t* s_empty = bars + 7;    // [2]
+  uint64_t* p_full = bars + 9;
+  uint64_t* p_empty = bars + 10;
+  uint64_t* o_full = bars + 11;
+  uint64_t* o_empty = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kAtcM, h = blockIdx.y, b = blockIdx.z;
+  const int ntiles = (p.Tk + kAtcN - 1) / kAtcN;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&mapQ);
+    ptx::prefetch_tensormap(&mapK);
+    ptx::prefetch_tensormap(&mapVt);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      ptx::mbar_init(q_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        ptx::mbar_init(&kv_full[i], 1);
+        ptx::mbar_init(&kv_empty[i], 1);
+        ptx::mbar_init(&s_full[i], 1);
+        ptx::mbar_init(&s_empty[i], 4);      // one arrival per softmax warp
+      }
+      ptx::mbar_init(p_full, 4);
+      ptx::mbar_init(p_empty, 1);
+      ptx::mbar_init(o_full, 1);
+      ptx::mbar_init(o_empty, 4);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_slot, 512);         // S buffers at columns 0 and 128, O_j at 256
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(q_full, 2 * kAtcKB);
+      ptx::tma_load_3d(sQ, &mapQ, q_full, p.qoff + h * kAttD, q0, b);
+      ptx::tma_load_3d(sQ + kAtcKB, &mapQ, q_full, p.qoff + h * kAttD + 64, q0, b);     // columns 64..95 are read, the rest ignored
+      for (int j = 0; j < ntiles; ++j) {
+        const int buf = j & 1, u = j >> 1, k0 = j * kAtcN;
+        ptx::mbar_wait(&kv_empty[buf], (u & 1) ^ 1u);
+        ptx::mbar_arrive_expect_tx(&kv_full[buf], 2 * kAtcKB + 2 * kAtcVB);
+        uint8_t* dk = sK + buf * 2 * kAtcKB;
+        uint8_t* dv = sV + buf * 2 * kAtcVB;
+        ptx::tma_load_3d(dk, &mapK, &kv_full[buf], p.koff + h * kAttD, k0, b);
+        ptx::tma_load_3d(dk + kAtcKB, &mapK, &kv_full[buf], p.koff + h * kAttD + 64, k0, b);
+        ptx::tma_load_2d(dv, &mapVt, &kv_full[buf], k0, (b * p.heads + h) * kAttD);
+        ptx::tma_load_2d(dv + kAtcVB, &mapVt, &kv_full[buf], k0 + 64, (b * p.heads + h) * kAttD);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idS = ptx::make_idesc_bf16_f32(kAtcM, kAtcN), idO = ptx::make_idesc_bf16_f32(kAtcM, kAttD);
+    const bool el = ptx::elect_one();
+    ptx::mbar_wait(q_full, 0);
+    ptx::tc_fence_after();
+    auto issue_S = [&](int j) {
+      const int buf = j & 1, u = j >> 1;
+      ptx::mbar_wait(&kv_full[buf], u & 1);
+      ptx::mbar_wait(&s_empty[buf], (u & 1) ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t td = tmem_base + static_cast<uint32_t>(buf * kAtcN);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(sQ + kb * kAtcKB));
+        const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sK + buf * 2 * kAtcKB + kb * kAtcKB));
+        const int nsteps = kb == 0 ? 4 : 2;                       // head_dim 96 = 64 + 32
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < nsteps && el) ptx::mma_f16_ss(td, da + 2 * k, db + 2 * k, idS, (kb | k) != 0 ? 1u : 0u);
+      }
+      if (el) ptx::mma_commit(&s_full[buf]);
+      __syncwarp();
+    };
+    issue_S(0);
+    for (int j = 0; j < ntiles; ++j) {
+      if (j + 1 < ntiles) issue_S(j + 1);
+      const int buf = j & 1;
+      ptx::mbar_wait(p_full, j & 1);
+      ptx::mbar_wait(o_empty, (j & 1) ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t td = tmem_base + 256u;
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(sP + kb * kAtcKB));
+        const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sV + buf * 2 * kAtcVB + kb * kAtcVB));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (el) ptx::mma_f16_ss(td, da + 2 * k, db + 2 * k, idO, (kb | k) != 0 ? 1u : 0u);
+      }
+      if (el) {
+        ptx::mma_commit(o_full);
+        ptx::mma_commit(p_empty);
+        ptx::mma_commit(&kv_empty[buf]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------ softmax + output: thread = query row
+    const int qw = warp & 3;                       // TMEM lane quarter this warp may read
+    const int r = qw * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(qw * 32) << 16);
+    float o[kAttD];
+#pragma unroll
+    for (int i = 0; i < kAttD; ++i) o[i] = 0.f;
+    float mrow = -INFINITY, lrow = 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      const int buf = j & 1, u = j >> 1, k0 = j * kAtcN;
+      {
+        const int k = k0 + r;
+        sKeep[buf * kAtcN + r] = k >= p.Tk ? -1.f : (p.key_keep ? p.key_keep[static_cast<size_t>(b) * p.Tk + k] : 1.f);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");            // the four softmax warps
+      const float* flags = sKeep + buf * kAtcN;
+      ptx::mbar_wait(&s_full[buf], u & 1);
+      ptx::tc_fence_after();
+      const uint32_t s_addr = lane_addr + static_cast<uint32_t>(buf * kAtcN);
+      uint32_t rr[32];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        ptx::tmem_ld_32x32b_x32(s_addr + c * 32, rr);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float f = flags[c * 32 + i];
+          const float sv = f < 0.f ? -INFINITY : (f == 0.f ? -1e8f : __uint_as_float(rr[i]));
+          mx = fmaxf(mx, sv);
+        }
+      }
+      const float mnew = fmaxf(mrow, mx);          // finite: key k0 of every tile is < Tk
+      const float alpha = expf(mrow - mnew);       // exp(-inf) = 0 on the first tile
+      ptx::mbar_wait(p_empty, (j & 1) ^ 1u);       // the previous P.V MMA has read sP
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        ptx::tmem_ld_32x32b_x32(s_addr + c * 32, rr);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float f = flags[c * 32 + g * 8 + i];
+            const float sv = f == 0.f ? -1e8f : __uint_as_float(rr[g * 8 + i]);
+            pv[i] = f < 0.f ? 0.f : expf(sv - mnew);
+            sum += pv[i];
+          }
+          const int kc = c * 32 + g * 8;             // first key column of this 16-byte chunk
+          uint8_t* dst = sP + (kc >> 6) * kAtcKB + r * 128 + ((((kc & 63) >> 3) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]),
+                                                      pack_bf16x2(pv[6], pv[7]));
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async_smem();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&s_empty[buf]);
+        ptx::mbar_arrive(p_full);
+      }
+      lrow = lrow * alpha + sum;
+      mrow = mnew;
+      ptx::mbar_wait(o_full, j & 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        ptx::tmem_ld_32x32b_x32(lane_addr + 256u + c * 32, rr);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(rr[i]));
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(o_empty);
+    }
+    const int q = q0 + r;
+    if (q < p.Tq) {
+      const float inv = 1.0f / lrow;
+      __nv_bfloat16* dst = p.O + (static_cast<size_t>(b) * p.Tq + q) * p.ldo + h * kAttD;
+#pragma unroll
+      for (int c = 0; c < kAttD / 8; ++c)
+        reinterpret_cast<uint4*>(dst)[c] = make_uint4(pack_bf16x2(o[8 * c] * inv, o[8 * c + 1] * inv), pack_bf16x2(o[8 * c + 2] * inv, o[8 * c + 3] * inv),
+                                                     pack_bf16x2(o[8 * c + 4] * inv, o[8 * c + 5] * inv), pack_bf16x2(o[8 * c + 6] * inv, o[8 * c + 7] * inv));
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+}  // namespace fse

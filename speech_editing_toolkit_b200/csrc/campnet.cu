@@ -14,15 +14,19 @@
 // Attention (softmax(QK^T)V per item and head) is a flash-style tiled kernel with an online fp32 softmax.  In this first
 // version its two contractions run on CUDA cores over the stored (bf16 / fp32) q, k, v: it is the kernel to move onto
 // tcgen05 next (S tile in TMEM, P through shared memory as the A operand of the PV MMA); everything around it already is.
+#include <cstdlib>
+
 #include "rowwise.cuh"
+#include "attention_tc.cuh"
 
 namespace fse {
 namespace {
 
-constexpr int kAttD = 96;          // head_dim (hidden 192 / 2 heads)
-constexpr int kAttTile = 64;       // queries per block and keys per tile
+constexpr int kAttTile = 64;       // queries per block and keys per tile of the CUDA-core attention kernel
 
-// q/k/v projection without bias: columns < nscaled (the query part) are multiplied by head_dim^-0.5 (transformer.py:296)
+// q/k/v projection without bias: columns < nscaled (the query part) are multiplied by head_dim^-0.5 (transformer.py:296).
+// With vt != null the value columns (n >= vstart) are ALSO stored transposed, vt[(b*heads + head)*D + c][t] (row length Tkp):
+// the K-major B operand of the tensor-core P.V contraction (attention_tc.cuh).
 template <typename TOp>
 struct EpiScaleCols {
   static constexpr int kAux = 0;
@@ -30,12 +34,21 @@ struct EpiScaleCols {
   TOp* out;   // [B*T, N]
   int N, T, nscaled;
   float scale;
+  TOp* vt;    // or null
+  int vstart, Tkp, heads;
   template <int NV>
   __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float*) const {
     float v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = n0 + i < nscaled ? __fmul_rn(acc[i], scale) : acc[i];
     st_vec<NV>(out + (static_cast<size_t>(b) * T + t) * N + n0, v);
+    if (vt && n0 >= vstart) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = n0 + i - vstart;
+        store_op(vt + (static_cast<size_t>(b) * heads * kAttD + c) * Tkp + t, v[i]);      // c = head * D + channel
+      }
+    }
   }
 };
 
@@ -158,7 +171,8 @@ __global__ void __launch_bounds__(256) camp_mel_input_kernel(const float* __rest
 template <typename TOp>
 __global__ void __launch_bounds__(256) camp_attention_kernel(const TOp* __restrict__ Q, int ldq, int qoff, const TOp* __restrict__ K,
                                                              const TOp* __restrict__ V, int ldkv, int koff, int voff,
-                                                             const float* __restrict__ key_keep, TOp* __restrict__ O, int ldo, int Tq, int Tk) {
+                                                             const float* __restrict__ key_keep, TOp* __restrict__ O, int ldo, int Tq, int Tk,
+                                                             float* __restrict__ probs, float probs_scale) {
   constexpr int D = kAttD, TQ = kAttTile, TK = kAttTile, QS = D + 1, PS = TK + 1, NC = D / 16;
   extern __shared__ float smem[];
   float* Qs = smem;                 // [TQ][QS]
@@ -257,47 +271,47 @@ __global__ void __launch_bounds__(256) camp_attention_kernel(const TOp* __restri
 #pragma unroll
     for (int c = 0; c < NC; ++c) store_op(dst + c, o[i][c] * inv);
   }
-}
-
-// head-averaged attention probabilities of one query row, [B, Tq, Tk] fp32 (the `attn` entry of CampNet's output dict:
-// layer 0 of decoder_coarse, transformer.py:410-416, :803).  One block per (item, query); scores live in shared memory.
-template <typename TOp>
-__global__ void __launch_bounds__(128) camp_attn_probs_kernel(const TOp* __restrict__ Q, int ldq, const TOp* __restrict__ K, int ldkv,
-                                                              const float* __restrict__ key_keep, float* __restrict__ out, int Tq, int Tk,
-                                                              int heads) {
-  constexpr int D = kAttD;
-  extern __shared__ float sm[];
-  float* qv = sm;                    // [heads * D]
-  float* sc = qv + heads * D;        // [Tk]
-  __shared__ float red[4];
-  const int q = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  for (int i = tid; i < heads * D; i += 128) qv[i] = to_f32(Q[(static_cast<size_t>(b) * Tq + q) * ldq + i]);
-  float* dst = out + (static_cast<size_t>(b) * Tq + q) * Tk;
-  for (int h = 0; h < heads; ++h) {
+  if (probs == nullptr) return;
+  // second pass (the `attn` entry of CampNet's output dict: head-averaged probabilities of decoder layer 0, transformer.py:
+  // 410-416, :803): with the final (max, sum) of every row known, recompute the score tiles and accumulate
+  // p / heads into probs[B, Tq, Tk] (zeroed by the caller; one atomicAdd per head and element, order-independent for 2 heads)
+  for (int k0 = 0; k0 < Tk; k0 += TK) {
     __syncthreads();
-    float mx = -INFINITY;
-    for (int k = tid; k < Tk; k += 128) {
-      const TOp* kr = K + (static_cast<size_t>(b) * Tk + k) * ldkv + h * D;
-      float s = 0.f;
-      for (int c = 0; c < D; ++c) s = fmaf(qv[h * D + c], to_f32(kr[c]), s);
-      if (key_keep && key_keep[static_cast<size_t>(b) * Tk + k] == 0.f) s = -1e8f;
-      sc[k] = s;
-      mx = fmaxf(mx, s);
+    for (int i = tid; i < TK * D; i += 256) {
+      const int r = i / D, c = i % D, k = k0 + r;
+      Ks[r * QS + c] = k < Tk ? to_f32(K[(static_cast<size_t>(b) * Tk + k) * ldkv + h * D + c + koff]) : 0.f;
+    }
+    __syncthreads();
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < D; ++c) {
+      float a[4], kk[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = Qs[(4 * ty + i) * QS + c];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) kk[j] = Ks[(tx + 16 * j) * QS + c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] = fmaf(a[i], kk[j], s[i][j]);
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
-    if ((tid & 31) == 0) red[tid >> 5] = mx;
-    __syncthreads();
-    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-    __syncthreads();
-    float sum = 0.f;
-    for (int k = tid; k < Tk; k += 128) { const float p = expf(sc[k] - mx); sc[k] = p; sum += p; }
-    sum = warp_sum(sum);
-    if ((tid & 31) == 0) red[tid >> 5] = sum;
-    __syncthreads();
-    sum = red[0] + red[1] + red[2] + red[3];
-    const float w = 1.0f / (sum * static_cast<float>(heads));
-    for (int k = tid; k < Tk; k += 128) dst[k] = h == 0 ? sc[k] * w : dst[k] + sc[k] * w;
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tx + 16 * j;
+      if (k >= Tk) continue;
+      const bool padded = key_keep && key_keep[static_cast<size_t>(b) * Tk + k] == 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int q = q0 + 4 * ty + i;
+        if (q >= Tq) continue;
+        const float pr = expf((padded ? -1e8f : s[i][j]) - mrow[i]) / lrow[i];
+        atomicAdd(probs + (static_cast<size_t>(b) * Tq + q) * Tk + k, pr * probs_scale);
+      }
+    }
   }
 }
 
@@ -324,6 +338,8 @@ struct fse_campnet {
   ConvBlocksW fine;
   ConvW out_coarse, out_fine;
   fse_mel_encoder* mel = nullptr;
+  bool attn_tc = false;                 // tcgen05 attention (FSE_MODE_TC_BF16; FSE_CAMP_ATTN=simt selects the CUDA-core kernel)
+  struct VtMap { const void* buf = nullptr; int Tkp = 0, B = 0; CUtensorMap map{}; } vtmap;
 };
 
 namespace {
@@ -332,6 +348,8 @@ struct KWs {
   RowBufs r;            // x32 / tmp32 / y32 / opA / opB (4H wide) / m0 / m1 over R = B * max(T, Tt) rows
   void* qkv;            // [R, 3H] operand
   void* kvx;            // [B*Tt, 2H] operand
+  void* vt;             // [B*H, Tp] operand: V^T of the current attention (tensor-core attention only), Tp = max(T, Tt) rounded up to 8
+  size_t vt_bytes;
   float* enc32;         // [B*Tt, H]
   void* encop;          // [B*Tt, H] operand
   float* enc_keep;      // [B*Tt]
@@ -352,6 +370,9 @@ KWs kcarve(const fse_campnet* h, void* base, int B, int Tt, int T) {
   uint8_t* p = static_cast<uint8_t*>(base);
   w.qkv = p + take(R * 3 * H * es);
   w.kvx = p + take(Rt * 2 * H * es);
+  const size_t Tp = static_cast<size_t>(((T > Tt ? T : Tt) + 7) / 8 * 8);
+  w.vt_bytes = h->attn_tc ? static_cast<size_t>(B) * H * Tp * 2 : 0;
+  w.vt = p + take(w.vt_bytes);
   w.enc32 = reinterpret_cast<float*>(p + take(Rt * H * 4));
   w.encop = p + take(Rt * H * es);
   w.enc_keep = reinterpret_cast<float*>(p + take(Rt * 4));
@@ -398,7 +419,31 @@ int load_attn(fse_campnet* h, const TensorTable& tt, const std::string& pre, boo
 
 template <typename TOp>
 int attention(fse_campnet* h, const void* Q, int ldq, int qoff, const void* K, const void* V, int ldkv, int koff, int voff,
-              const float* key_keep, void* O, int B, int Tq, int Tk, cudaStream_t st) {
+              const float* key_keep, void* O, int B, int Tq, int Tk, float* probs, const void* vt, int Tkp, cudaStream_t st) {
+  if constexpr (std::is_same<TOp, __nv_bfloat16>::value) {
+    if (h->attn_tc && vt != nullptr && probs == nullptr) {
+      // tensor cores: S = Q K^T and O = P V as tcgen05.mma, V^T from the projection's epilogue (attention_tc.cuh)
+      static bool tc_attr = false;
+      if (!tc_attr) {
+        FSE_CUDA(cudaFuncSetAttribute(camp_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtcSmemBytes));
+        tc_attr = true;
+      }
+      const CUtensorMap *mq = nullptr, *mk = nullptr;
+      FSE_TRY(get_act_map(&h->ctx, Q, ldq, Tq, B, 64, &mq));
+      const CUtensorMap q_map = *mq;                     // by value: the second lookup may recycle the cache
+      FSE_TRY(get_act_map(&h->ctx, K, ldkv, Tk, B, 64, &mk));
+      if (!(h->vtmap.buf == vt && h->vtmap.Tkp == Tkp && h->vtmap.B == B)) {
+        FSE_TRY(make_map_w(&h->vtmap.map, vt, Tkp, B * h->cfg.hidden, 64, kAttD));
+        h->vtmap.buf = vt; h->vtmap.Tkp = Tkp; h->vtmap.B = B;
+      }
+      AttnTcParams ap{Tq, Tk, h->cfg.heads, qoff, koff, h->cfg.hidden, key_keep, static_cast<__nv_bfloat16*>(O)};
+      dim3 grid((Tq + kAtcM - 1) / kAtcM, h->cfg.heads, B);
+      camp_attention_tc_kernel<<<grid, kAtcThreads, kAtcSmemBytes, st>>>(q_map, *mk, h->vtmap.map, ap);
+      FSE_CUDA(cudaGetLastError());
+      ++h->ctx.launches;
+      return FSE_OK;
+    }
+  }
   constexpr size_t smem = (2 * kAttTile * (kAttD + 1) + kAttTile * kAttD + kAttTile * (kAttTile + 1)) * sizeof(float);
   static bool attr_set = false;
   auto kern = camp_attention_kernel<TOp>;
@@ -406,9 +451,10 @@ int attention(fse_campnet* h, const void* Q, int ldq, int qoff, const void* K, c
     FSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     attr_set = true;
   }
+  if (probs) FSE_CUDA(cudaMemsetAsync(probs, 0, static_cast<size_t>(B) * Tq * Tk * sizeof(float), st));
   dim3 grid((Tq + kAttTile - 1) / kAttTile, h->cfg.heads, B);
   kern<<<grid, 256, smem, st>>>(static_cast<const TOp*>(Q), ldq, qoff, static_cast<const TOp*>(K), static_cast<const TOp*>(V), ldkv, koff,
-                                voff, key_keep, static_cast<TOp*>(O), h->cfg.hidden, Tq, Tk);
+                                voff, key_keep, static_cast<TOp*>(O), h->cfg.hidden, Tq, Tk, probs, 1.0f / static_cast<float>(h->cfg.heads));
   FSE_CUDA(cudaGetLastError());
   ++h->ctx.launches;
   return FSE_OK;
@@ -424,6 +470,10 @@ int forward_impl(fse_campnet* h, const int64_t* txt, const float* mels, const fl
   const float qscale = 1.0f / sqrtf(static_cast<float>(kAttD));
   const float fscale = static_cast<float>(std::pow(static_cast<double>(k), -0.5));
   auto launched = [&]() -> int { FSE_CUDA(cudaGetLastError()); ++ctx->launches; return FSE_OK; };
+  // V^T rows are padded to a multiple of 8 keys (16-byte TMA strides); the pad columns must be finite zeros (P = 0 there)
+  TOp* vt = h->attn_tc ? static_cast<TOp*>(w.vt) : nullptr;
+  const int TpT = (Tt + 7) / 8 * 8, TpF = (T + 7) / 8 * 8;
+  if (vt) FSE_CUDA(cudaMemsetAsync(w.vt, 0, w.vt_bytes, st));
 
   // ---- text encoder (TransformerEncoder.forward): keep = m0 = (txt != 0)
   camp_positions_kernel<<<(B + 63) / 64, 64, 0, st>>>(txt, nullptr, w.pos, B, Tt);
@@ -433,9 +483,9 @@ int forward_impl(fse_campnet* h, const int64_t* txt, const float* mels, const fl
   FSE_TRY(launched());
   for (const EncLayerW& L : h->enc) {
     FSE_TRY((layer_norm<TOp>(ctx, w.r.x32, L.ln1, nullptr, nullptr, nullptr, w.r.opA, nullptr, Rt, st)));
-    EpiScaleCols<TOp> eq{static_cast<TOp*>(w.qkv), 3 * H, Tt, H, qscale};
+    EpiScaleCols<TOp> eq{static_cast<TOp*>(w.qkv), 3 * H, Tt, H, qscale, vt, 2 * H, TpT, h->cfg.heads};
     FSE_TRY((run_conv<TOp>(ctx, L.self.qkv, w.r.opA, B, Tt, eq, st)));
-    FSE_TRY((attention<TOp>(h, w.qkv, 3 * H, 0, w.qkv, w.qkv, 3 * H, H, 2 * H, w.r.m0, w.r.opA, B, Tt, Tt, st)));
+    FSE_TRY((attention<TOp>(h, w.qkv, 3 * H, 0, w.qkv, w.qkv, 3 * H, H, 2 * H, w.r.m0, w.r.opA, B, Tt, Tt, nullptr, vt, TpT, st)));
     EpiResidualMask eo{L.self.out.bias, w.r.x32, w.r.m0, H, Tt};
     FSE_TRY((run_conv<TOp>(ctx, L.self.out, w.r.opA, B, Tt, eo, st)));
     FSE_TRY((layer_norm<TOp>(ctx, w.r.x32, L.ln2, nullptr, nullptr, nullptr, w.r.opA, nullptr, Rt, st)));
@@ -465,25 +515,21 @@ int forward_impl(fse_campnet* h, const int64_t* txt, const float* mels, const fl
   bool first_layer = true;
   for (const DecLayerW& L : h->dec) {
     FSE_TRY((layer_norm<TOp>(ctx, w.r.x32, L.ln1, nullptr, nullptr, nullptr, w.r.opA, nullptr, Rf, st)));
-    EpiScaleCols<TOp> eq{static_cast<TOp*>(w.qkv), 3 * H, T, H, qscale};
+    EpiScaleCols<TOp> eq{static_cast<TOp*>(w.qkv), 3 * H, T, H, qscale, vt, 2 * H, TpF, h->cfg.heads};
     FSE_TRY((run_conv<TOp>(ctx, L.self.qkv, w.r.opA, B, T, eq, st)));
-    FSE_TRY((attention<TOp>(h, w.qkv, 3 * H, 0, w.qkv, w.qkv, 3 * H, H, 2 * H, nullptr, w.r.opA, B, T, T, st)));
+    FSE_TRY((attention<TOp>(h, w.qkv, 3 * H, 0, w.qkv, w.qkv, 3 * H, H, 2 * H, nullptr, w.r.opA, B, T, T, nullptr, vt, TpF, st)));
     EpiResidualMask eo{L.self.out.bias, w.r.x32, nullptr, H, T};
     FSE_TRY((run_conv<TOp>(ctx, L.self.out, w.r.opA, B, T, eo, st)));
 
     FSE_TRY((layer_norm<TOp>(ctx, w.r.x32, L.ln2, nullptr, nullptr, nullptr, w.r.opA, nullptr, Rf, st)));
-    EpiScaleCols<TOp> ecq{static_cast<TOp*>(w.qkv), H, T, H, qscale};                 // q of the cross attention: [B*T, H]
+    EpiScaleCols<TOp> ecq{static_cast<TOp*>(w.qkv), H, T, H, qscale, nullptr, 0, 0, 0};          // q of the cross attention: [B*T, H]
     FSE_TRY((run_conv<TOp>(ctx, L.cross.q, w.r.opA, B, T, ecq, st)));
-    EpiScaleCols<TOp> ekv{static_cast<TOp*>(w.kvx), 2 * H, Tt, 0, 1.f};
+    EpiScaleCols<TOp> ekv{static_cast<TOp*>(w.kvx), 2 * H, Tt, 0, 1.f, vt, H, TpT, h->cfg.heads};
     FSE_TRY((run_conv<TOp>(ctx, L.cross.kv, w.encop, B, Tt, ekv, st)));
-    if (first_layer && attn_out) {
-      const size_t sm = (static_cast<size_t>(h->cfg.heads) * kAttD + Tt) * sizeof(float);
-      camp_attn_probs_kernel<TOp><<<dim3(T, B), 128, sm, st>>>(static_cast<const TOp*>(w.qkv), H, static_cast<const TOp*>(w.kvx), 2 * H,
-                                                              w.enc_keep, attn_out, T, Tt, h->cfg.heads);
-      FSE_TRY(launched());
-    }
+    // layer 0 also reports its head-averaged probabilities (the CUDA-core kernel's second pass)
+    float* probs = first_layer ? attn_out : nullptr;
     first_layer = false;
-    FSE_TRY((attention<TOp>(h, w.qkv, H, 0, w.kvx, w.kvx, 2 * H, 0, H, w.enc_keep, w.r.opA, B, T, Tt, st)));
+    FSE_TRY((attention<TOp>(h, w.qkv, H, 0, w.kvx, w.kvx, 2 * H, 0, H, w.enc_keep, w.r.opA, B, T, Tt, probs, vt, TpT, st)));
     EpiResidualMask ex{L.cross.out.bias, w.r.x32, nullptr, H, T};
     FSE_TRY((run_conv<TOp>(ctx, L.cross.out, w.r.opA, B, T, ex, st)));
 
@@ -535,6 +581,8 @@ int fse_campnet_create(const fse_campnet_config* cfg, fse_campnet** out) {
   h->ctx.mode = cfg->mode;
   h->ctx.bf16 = cfg->mode != FSE_MODE_SIMT_F32;
   h->ctx.hidden = cfg->hidden;
+  const char* sel = std::getenv("FSE_CAMP_ATTN");                 // "tc" | "simt"; default: tensor cores in FSE_MODE_TC_BF16
+  h->attn_tc = cfg->mode == FSE_MODE_TC_BF16 && !(sel && std::string(sel) == "simt");
   *out = h;
   return FSE_OK;
 }

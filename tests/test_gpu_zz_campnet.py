@@ -83,3 +83,30 @@ def test_campnet_multi_tile_ragged_batch_vs_oracle(lib_built):
             for k in ("mel_out_coarse", "mel_out_fine"):
                 assert rel_l1(out[k] * m, ref32[k] * m) < 3e-2, k
                 assert rel_l1(out[k] * m, refbf[k] * m) < 1.5e-2, k
+
+
+def test_tensor_core_attention_matches_cuda_core_attention(lib_built, monkeypatch):
+    """The tcgen05 attention kernel (attention_tc.cuh: S = Q K^T and O = P V as tcgen05.mma, softmax out of TMEM) against the
+    CUDA-core flash kernel on the same bf16 q / k / v, through the whole forward: 3 query tiles x 3 key tiles per (item, head)
+    in the decoder, masked keys in the encoder / cross attention, ragged tails."""
+    _need_gpu()
+    from oracle import campnet_oracle as KO
+    from speech_editing_toolkit_b200 import synth
+    vocab, B, T = 60, 2, 330
+    sd = synth.campnet_state_dict(17, vocab)
+    b = synth.synthetic_campnet_batch(18, B, T, vocab=vocab, frames_per_phone=4, pad_items=[(1, 9)])
+    m = b["time_mel_masks"]
+    outs = {}
+    for sel in ("simt", "tc"):
+        monkeypatch.setenv("FSE_CAMP_ATTN", sel)
+        eng = _module(sd, vocab, "tc_bf16").engine()
+        outs[sel] = {k: v.cpu().numpy() for k, v in eng.forward(cu(b["txt_tokens"]), cu(b["mels"]), cu(m), need_encoder_out=True).items()}
+        assert all(np.isfinite(v).all() for v in outs[sel].values()), sel
+    ref = KO.campnet_forward(sd, b["txt_tokens"], b["mels"], m)
+    # two different kernels really ran: the tensor-core path rounds P to bf16, so the results agree closely but not bit for bit
+    assert not np.array_equal(outs["tc"]["encoder_out"], outs["simt"]["encoder_out"])
+    for k in ("encoder_out", "mel_out_coarse", "mel_out_fine"):
+        w = m if k != "encoder_out" else 1.0
+        assert rel_l1(outs["tc"][k] * w, outs["simt"][k] * w) < 1.5e-2, k          # P is rounded to bf16 on the tensor-core path
+        assert rel_l1(outs["tc"][k] * w, ref[k] * w) < 3e-2, k
+    assert np.abs(outs["tc"]["attn"] - ref["attn"]).max() < 5e-2
