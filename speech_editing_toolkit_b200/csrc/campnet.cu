@@ -339,6 +339,7 @@ struct fse_campnet {
   ConvW out_coarse, out_fine;
   fse_mel_encoder* mel = nullptr;
   bool attn_tc = false;                 // tcgen05 attention (FSE_MODE_TC_BF16; FSE_CAMP_ATTN=simt selects the CUDA-core kernel)
+  bool attn_tc2 = false;                // ... its two-query-tile schedule (the default; FSE_CAMP_ATTN=tc selects one tile per CTA)
   struct VtMap { const void* buf = nullptr; int Tkp = 0, B = 0; CUtensorMap map{}; } vtmap;
 };
 
@@ -437,6 +438,18 @@ int attention(fse_campnet* h, const void* Q, int ldq, int qoff, const void* K, c
         h->vtmap.buf = vt; h->vtmap.Tkp = Tkp; h->vtmap.B = B;
       }
       AttnTcParams ap{Tq, Tk, h->cfg.heads, qoff, koff, h->cfg.hidden, key_keep, static_cast<__nv_bfloat16*>(O)};
+      if (h->attn_tc2) {       // two query tiles per CTA, two softmax warp groups (second schedule of attention_tc.cuh)
+        static bool tc2_attr = false;
+        if (!tc2_attr) {
+          FSE_CUDA(cudaFuncSetAttribute(camp_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtc2SmemBytes));
+          tc2_attr = true;
+        }
+        dim3 grid2((Tq + 2 * kAtcM - 1) / (2 * kAtcM), h->cfg.heads, B);
+        camp_attention_tc2_kernel<<<grid2, kAtc2Threads, kAtc2SmemBytes, st>>>(q_map, *mk, h->vtmap.map, ap);
+        FSE_CUDA(cudaGetLastError());
+        ++h->ctx.launches;
+        return FSE_OK;
+      }
       dim3 grid((Tq + kAtcM - 1) / kAtcM, h->cfg.heads, B);
       camp_attention_tc_kernel<<<grid, kAtcThreads, kAtcSmemBytes, st>>>(q_map, *mk, h->vtmap.map, ap);
       FSE_CUDA(cudaGetLastError());
@@ -581,8 +594,10 @@ int fse_campnet_create(const fse_campnet_config* cfg, fse_campnet** out) {
   h->ctx.mode = cfg->mode;
   h->ctx.bf16 = cfg->mode != FSE_MODE_SIMT_F32;
   h->ctx.hidden = cfg->hidden;
-  const char* sel = std::getenv("FSE_CAMP_ATTN");                 // "tc" | "simt"; default: tensor cores in FSE_MODE_TC_BF16
+  // FSE_CAMP_ATTN = "tc2" (default in FSE_MODE_TC_BF16: tcgen05, two query tiles per CTA) | "tc" (one tile per CTA) | "simt"
+  const char* sel = std::getenv("FSE_CAMP_ATTN");
   h->attn_tc = cfg->mode == FSE_MODE_TC_BF16 && !(sel && std::string(sel) == "simt");
+  h->attn_tc2 = h->attn_tc && !(sel && std::string(sel) == "tc");
   *out = h;
   return FSE_OK;
 }

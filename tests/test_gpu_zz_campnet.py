@@ -110,3 +110,28 @@ def test_tensor_core_attention_matches_cuda_core_attention(lib_built, monkeypatc
         assert rel_l1(outs["tc"][k] * w, outs["simt"][k] * w) < 1.5e-2, k          # P is rounded to bf16 on the tensor-core path
         assert rel_l1(outs["tc"][k] * w, ref[k] * w) < 3e-2, k
     assert np.abs(outs["tc"]["attn"] - ref["attn"]).max() < 5e-2
+
+
+def test_two_tile_attention_schedule_matches(lib_built, monkeypatch):
+    """FSE_CAMP_ATTN=tc2: two query tiles per CTA, two softmax warp groups sharing the K / V^T tiles, mask-free fast path and
+    ex2.approx (attention_tc.cuh, second schedule) against the CUDA-core kernel and the oracle; odd tile counts on both axes
+    (330 queries = 2 CTAs of 256 with a ragged second tile; 3 key tiles; 82-key cross attention with padded keys)."""
+    _need_gpu()
+    from oracle import campnet_oracle as KO
+    from speech_editing_toolkit_b200 import synth
+    vocab, B, T = 60, 2, 330
+    sd = synth.campnet_state_dict(17, vocab)
+    b = synth.synthetic_campnet_batch(18, B, T, vocab=vocab, frames_per_phone=4, pad_items=[(1, 9)])
+    m = b["time_mel_masks"]
+    outs = {}
+    for sel in ("simt", "tc2"):
+        monkeypatch.setenv("FSE_CAMP_ATTN", sel)
+        eng = _module(sd, vocab, "tc_bf16").engine()
+        outs[sel] = {k: v.cpu().numpy() for k, v in eng.forward(cu(b["txt_tokens"]), cu(b["mels"]), cu(m), need_encoder_out=True).items()}
+        assert all(np.isfinite(v).all() for v in outs[sel].values()), sel
+    ref = KO.campnet_forward(sd, b["txt_tokens"], b["mels"], m)
+    assert not np.array_equal(outs["tc2"]["encoder_out"], outs["simt"]["encoder_out"])
+    for k in ("encoder_out", "mel_out_coarse", "mel_out_fine"):
+        w = m if k != "encoder_out" else 1.0
+        assert rel_l1(outs["tc2"][k] * w, outs["simt"][k] * w) < 1.5e-2, k
+        assert rel_l1(outs["tc2"][k] * w, ref[k] * w) < 3e-2, k
