@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--eager-gpu-baseline", action="store_true",
+                    help="also time the eager-PyTorch port of the reference path on this GPU (cuDNN/cuBLAS; opt-in, rank 0, N=1)")
     return ap.parse_args()
 
 
@@ -168,6 +170,40 @@ def run_reference(args):
             "e2e": {"value": v, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": wall}
     print(json.dumps(line))
+
+
+def eager_gpu_sample(timesteps, B, T, dev):
+    """The reference's own way of running this path on a GPU — eager PyTorch, one cuDNN / ATen launch per op, fp32 with TF32
+    convolutions (torch default) — through the validated functional port (oracle/torch_port.py; the reference tree cannot travel
+    to the GPU box).  Times 3 diffusion iterations at the full batch and the vocoder on a bounded batch, extrapolates to S
+    iterations + vocoder: the "reference single-GPU PyTorch" figure north_star compares against.  Reported, never the product path."""
+    import torch
+    from oracle import fluentspeech_oracle as O
+    from oracle import torch_port as P
+    from speech_editing_toolkit_b200 import schedule, synth
+    p = {k: v.to(dev) for k, v in P.to_torch(synth.denoiser_state_dict(1234)).items()}
+    hp = {k: v.to(dev) for k, v in P.to_torch(synth.hifigan_state_dict(1234)).items()}
+    sched = {k: torch.from_numpy(v).to(dev) for k, v in schedule.diffusion_buffers(timesteps).items()}
+    cond = torch.from_numpy(synth.synthetic_cond(1, B, T)).to(dev).transpose(1, 2).contiguous()
+    it, Bv = 3, min(B, 4)                       # the eager vocoder holds fp32 activations of every stage: bound its batch
+    mel = P.sample_loop(p, sched, cond, timesteps, steps=2)            # warm-up (cuDNN heuristics, allocator)
+    P.hifigan_forward(hp, O.HIFIGAN_V1, mel[:Bv].transpose(1, 2).contiguous())
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    mel = P.sample_loop(p, sched, cond, timesteps, steps=it)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ev[2].record()
+    P.hifigan_forward(hp, O.HIFIGAN_V1, mel[:Bv].transpose(1, 2).contiguous())
+    ev[3].record()
+    torch.cuda.synchronize()
+    s_iter = ev[0].elapsed_time(ev[1]) / 1e3 / (it * B * T)            # seconds per frame and diffusion iteration
+    s_voc = ev[2].elapsed_time(ev[3]) / 1e3 / (Bv * T)                 # seconds per frame
+    sec_per_frame = s_iter * timesteps + s_voc
+    return {"value": 1.0 / sec_per_frame, "unit": "mel-frames/s", "rtf": sec_per_frame / (HOP / SR), "kind": "port (eager torch on cuda, TF32 convs)",
+            "sample": f"oracle/torch_port.py on this GPU: denoiser B={B}xT={T} for {it} of {timesteps} iterations "
+                      f"({s_iter * 1e9:.2f} ns/frame-iteration) + HiFi-GAN B={Bv}xT={T} ({s_voc * 1e6:.2f} us/frame), extrapolated"}
 
 
 # ------------------------------------------------------------------ B200 arm
@@ -368,6 +404,12 @@ def run_b200(args):
         breakdown["vocoder_ms_per_step"] = {k: v[0] / args.steps for k, v in prof_v.items()}
     if cond_ms is not None:      # once per batch, in front of the loop: part of e2e, not of the resident `value` step (sampling + vocoder)
         breakdown["cond_encoder_plus_mel_encoder_ms"] = cond_ms
+    eager = None
+    if args.eager_gpu_baseline and world == 1:
+        try:
+            eager = eager_gpu_sample(S, B, T, dev)
+        except Exception as e:                       # a reported extra: never takes the bench line down
+            eager = {"error": repr(e)}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cpu = cpu_sample(S, B * T)
@@ -386,6 +428,8 @@ def run_b200(args):
         "gpu_launches": int(launches * args.steps), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
         "breakdown": breakdown,
     }
+    if eager is not None:
+        line["eager_gpu_baseline"] = eager
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

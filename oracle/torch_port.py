@@ -1,5 +1,7 @@
 """CPU port of the reference path in plain torch functional ops (fp32, torch's own oneDNN/ATen CPU
-kernels — the same library calls the reference's CPU path ends in).
+kernels — the same library calls the reference's CPU path ends in).  The functions are device-agnostic: on CUDA tensors the
+same code is the reference's eager GPU path (cuDNN / cuBLAS, TF32 convolutions by default), which `bench.py
+--eager-gpu-baseline` times as the "reference single-GPU PyTorch" figure of BASELINE.json's north_star.
 
 TEST / BASELINE INFRASTRUCTURE — NOT PRODUCT CODE.  Used by bench.py's `cpu_baseline` leg and
 `--impl reference` arm on the GPU box, where the reference tree itself cannot travel; validated
@@ -63,12 +65,13 @@ def sample_loop(p, sched: Dict[str, torch.Tensor], cond: torch.Tensor, timesteps
     q_posterior_sample (:95-101).  `steps` bounds the number of iterations actually run (for timing)."""
     B, H, T = cond.shape
     M = p["output_projection.weight"].shape[0]
-    x = noise[0] if noise is not None else torch.randn(B, M, T)
+    dev = cond.device
+    x = noise[0] if noise is not None else torch.randn(B, M, T, device=dev)
     it = list(reversed(range(timesteps)))
     if steps is not None:
         it = it[:steps]
     for k, i in enumerate(it):
-        t = torch.full((B,), i, dtype=torch.long)
+        t = torch.full((B,), i, dtype=torch.long, device=dev)
         x0 = diffnet_forward(p, x, t, cond)
         c1 = sched["posterior_mean_coef1"][t][:, None, None]
         c2 = sched["posterior_mean_coef2"][t][:, None, None]

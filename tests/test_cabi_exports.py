@@ -87,3 +87,27 @@ def test_cond_encoder_config_validation_happens_before_any_device_call(lib_built
     assert L.fse_cond_text_encoder(None, None, None, 1, 1, None, 0, None) == -1
     if not torch.cuda.is_available():
         assert L.fse_cond_encoder_create(C.byref(cfg()), C.byref(C.c_void_p())) == -2         # no device: FSE_ECUDA, no fallback
+
+
+def test_campnet_config_validation_happens_before_any_device_call(lib_built):
+    import ctypes as C
+    import torch
+    from speech_editing_toolkit_b200 import _lib
+    L = _lib.lib()
+
+    def cfg(**kw):
+        c = _lib.CampNetConfig()
+        c.hidden, c.vocab, c.n_mels, c.enc_layers, c.dec_layers, c.heads, c.ffn_kernel, c.fine_blocks, c.fine_kernel, c.mode = 192, 80, 80, 3, 6, 2, 9, 5, 5, 0
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+    for bad, word in ((dict(hidden=256), b"heads"), (dict(heads=0), b"heads"), (dict(vocab=0), b"vocab"), (dict(n_mels=81), b"n_mels"),
+                      (dict(ffn_kernel=8), b"ffn_kernel"), (dict(fine_kernel=13), b"fine_kernel"), (dict(dec_layers=0), b"layer"), (dict(mode=9), b"mode")):
+        assert L.fse_campnet_create(C.byref(cfg(**bad)), C.byref(C.c_void_p())) == -1, bad
+        assert word in L.fse_last_error(), (bad, L.fse_last_error())
+    assert L.fse_campnet_create(None, None) == -1
+    assert L.fse_campnet_workspace_bytes(None, 1, 1, 1) == 0 and L.fse_campnet_last_launches(None) == 0
+    assert L.fse_campnet_forward(None, None, None, None, None, None, None, None, 1, 1, 1, None, 0, None) == -1
+    if not torch.cuda.is_available():
+        assert L.fse_campnet_create(C.byref(cfg()), C.byref(C.c_void_p())) == -2              # no device: FSE_ECUDA, no fallback

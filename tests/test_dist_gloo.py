@@ -49,3 +49,41 @@ def test_run_sharded_world2_gloo(n):
         p.join(60)
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] for r in res) and all(r[2] == (n, 3, 2) for r in res)
+
+
+def _text_worker(rank, world, port, n, q):
+    """The editing batch as the reference collates it (int64 tokens / alignment next to fp32 frames): every tensor is sliced on
+    the batch axis with the same bounds and the per-rank mels are gathered once."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from speech_editing_toolkit_b200 import synth
+        b = synth.synthetic_edit_batch(3, n, 16, n_mels=4, vocab=20, frames_per_phone=4)
+        keys = ("txt_tokens", "mel2ph", "time_mel_masks", "ref_mels", "f0")
+        inputs = [torch.from_numpy(b[k]) for k in keys]
+
+        def fake_model(txt, mel2ph, mask, ref, f0):            # stand-in for GaussianDiffusionB200.forward on the rank's shard
+            assert txt.dtype == torch.int64 and mel2ph.dtype == torch.int64 and txt.shape[0] == ref.shape[0]
+            return ref * (1 - mask[:, :, None]) + (f0 * mel2ph.float())[:, :, None] * mask[:, :, None] + txt.float().sum(1)[:, None, None]
+
+        out = fdist.run_sharded(fake_model, inputs)
+        q.put((rank, bool(torch.equal(out, fake_model(*inputs))), tuple(out.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [6, 7])
+def test_text_batch_sharding_world2_gloo(n):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_text_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] for r in res) and all(r[2] == (n, 16, 4) for r in res)
