@@ -176,3 +176,32 @@ def test_whole_model_text_to_mel_vs_reference_fixture(lib_built):
         else:
             assert rel_l1(cond, g["decoder_inp"]) < tol
             assert rel_l1(mel, g["mel_out"]) < tol
+
+
+def test_libritts_config_without_pitch_embed(lib_built):
+    """egs/spec_denoiser_libritts.yaml:169 (BASELINE configs[1]) sets use_pitch_embed: false: f0 / uv are None, forward_pitch is
+    skipped (fs.py:97-99) and decoder_inp = (expand_states(encoder_out, mel2ph) + style) * tgt_nonpadding."""
+    _need_gpu()
+    from oracle import cond_encoder_oracle as CO
+    from speech_editing_toolkit_b200 import synth
+    from speech_editing_toolkit_b200.modules import FastSpeechB200
+    vocab, B, T = 50, 2, 200
+    hp = {"use_pitch_embed": False}
+    sd = synth.fastspeech_state_dict(31, vocab, hp)
+    assert not any(k.startswith("pitch_") for k in sd)
+    batch = synth.pad_edit_batch(synth.synthetic_edit_batch(32, B, T, vocab=vocab), item=1, n_tokens=4)
+    ref = CO.fastspeech_forward(sd, batch["txt_tokens"], batch["time_mel_masks"], batch["mel2ph"], batch["spk_embed"], None, None, hp=hp)
+    for mode in ("simt_f32", "tc_bf16"):
+        fs = FastSpeechB200(vocab, dict(HP, b200_mode=mode, use_pitch_embed=False)).cuda()
+        fs.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=False)
+        ret = fs(cu(batch["txt_tokens"]), cu(batch["time_mel_masks"])[:, :, None], cu(batch["mel2ph"]), cu(batch["spk_embed"]), None, None,
+                 skip_decoder=True, infer=True)
+        assert set(ret) == {"decoder_inp", "dur", "mel2ph"}
+        out = {k: v.cpu().numpy() for k, v in ret.items()}
+        assert np.abs(out["decoder_inp"][1, -32:]).max() == 0.0
+        if mode == "simt_f32":
+            assert np.abs(out["decoder_inp"] - ref["decoder_inp"]).max() < TOL_F32_ABS
+            assert np.abs(out["dur"] - ref["dur"]).max() < TOL_F32_ABS
+        else:
+            assert rel_l1(out["decoder_inp"], ref["decoder_inp"]) < 2e-2
+            assert rel_l1(out["dur"], ref["dur"]) < 2e-2
