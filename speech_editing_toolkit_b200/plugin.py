@@ -6,6 +6,7 @@
   SpecDenoiserInferB200               class + method surface of inference/tts/spec_denoiser.py::SpecDenoiserInfer
                                       (build_model / build_vocoder / run_vocoder / forward_model / infer_once)
   install_into_reference()            registers the B200 denoiser / vocoder in the reference's own registries
+  CampNetTaskB200                     inference side of tasks/speech_editing/campnet.py::CampNetTask (build_tts_model / run_model)
 
 Text / MFA / pitch front-ends (g2p_en, MFA binary, parselmouth, resemblyzer) are outside the hot path; these
 classes take tensors at the `GaussianDiffusion.forward` boundary, like the benchmark does.
@@ -22,7 +23,7 @@ import torch
 from . import synth
 from .ckpt import load_ckpt
 from .hparams import hparams, set_hparams
-from .modules import DiffNetB200, GaussianDiffusionB200
+from .modules import CampNetB200, DiffNetB200, GaussianDiffusionB200
 from .vocoder import HifiGANB200, get_vocoder_cls, register_vocoder  # noqa: F401
 
 DIFF_DECODERS = {
@@ -168,6 +169,57 @@ class SpeechDenoiserTaskB200:
         audio = B * T * hp.get("hop_size", 256) / hp.get("audio_sample_rate", 22050)
         print(f"| B200 spec_denoiser: {B}x{T} frames, {hp['timesteps']} steps + vocoder in {dt * 1e3:.1f} ms "
               f"({B * T / dt:.0f} mel-frames/s, RTF {dt / audio:.5f}); mel {tuple(out['mel_out'].shape)} wav {tuple(out['wav_out'].shape)}")
+        return out
+
+
+class CampNetTaskB200:
+    """Inference side of tasks/speech_editing/campnet.py::CampNetTask for
+    `--config egs/campnet.yaml -hp task_cls=speech_editing_toolkit_b200.plugin.CampNetTaskB200`:
+    build_tts_model (:27-31) and run_model(infer=True) (:52-90: model forward, then mel_out = mel_out_fine * mask + mels * (1 - mask)).
+    `start()` runs one synthetic batch of the configured shape (max_sentences x b200_frames) and reports throughput."""
+
+    def __init__(self, ph_dict_size: Optional[int] = None, word_dict_size: Optional[int] = None):
+        self.hparams = hparams
+        self.ph_dict_size = int(ph_dict_size if ph_dict_size is not None else hparams.get("b200_vocab", 80))
+        self.word_dict_size = word_dict_size
+        self.model = None
+
+    def build_tts_model(self):
+        self.model = CampNetB200(self.ph_dict_size, self.word_dict_size, self.hparams)
+        return self.model
+
+    @torch.no_grad()
+    def run_model(self, sample: dict, infer: bool = True, *args, **kwargs):
+        if not infer:
+            raise NotImplementedError("CampNetTaskB200 provides the inference side; training stays on the reference task")
+        time_mel_masks = sample["time_mel_masks"][:, :, None] if sample["time_mel_masks"].dim() == 2 else sample["time_mel_masks"]
+        output = self.model(sample["txt_tokens"], spk_embed=sample.get("spk_embed"), spk_id=sample.get("spk_ids"), mels=sample["mels"],
+                            stutter_mel_masks=None, time_mel_masks=time_mel_masks, infer=True)
+        output["mel_out"] = output["mel_out_fine"] * time_mel_masks + sample["mels"] * (1 - time_mel_masks)
+        return {}, output
+
+    @classmethod
+    def start(cls):
+        import time
+        task = cls()
+        hp = task.hparams
+        model = task.build_tts_model().cuda().eval()
+        if hp.get("work_dir") and os.path.isdir(hp["work_dir"]):
+            load_ckpt(model, hp["work_dir"], "model", force=False, strict=False)
+        else:
+            model.load_state_dict({k: torch.from_numpy(v) for k, v in synth.campnet_state_dict(hp.get("seed", 1234), task.ph_dict_size,
+                                                                                             hp["hidden_size"]).items()}, strict=False)
+        B, T = int(hp.get("max_sentences", 16)), int(hp.get("b200_frames", 1024))
+        b = synth.synthetic_campnet_batch(hp.get("seed", 1234), B, T, vocab=task.ph_dict_size)
+        sample = {k: torch.from_numpy(v).cuda() for k, v in b.items()}
+        task.run_model(sample)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, out = task.run_model(sample)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        print(f"| B200 CampNet: {B}x{T} frames mask-predict forward in {dt * 1e3:.1f} ms ({B * T / dt:.0f} mel-frames/s); "
+              f"mel_out {tuple(out['mel_out'].shape)} attn {tuple(out['attn'].shape)}")
         return out
 
 

@@ -103,6 +103,13 @@ def test_registries_and_plugin_surface():
     for meth in ("build_model", "build_vocoder", "run_vocoder", "forward_model", "infer_once"):
         assert hasattr(plugin.SpecDenoiserInferB200, meth)
     assert hasattr(plugin.SpeechDenoiserTaskB200, "start") and callable(plugin.run_task)
+    for meth in ("build_tts_model", "run_model", "start"):                # tasks/speech_editing/campnet.py::CampNetTask
+        assert hasattr(plugin.CampNetTaskB200, meth)
+    task = plugin.CampNetTaskB200(ph_dict_size=33)
+    task.hparams = dict(hidden_size=192, dec_ffn_kernel_size=9, audio_num_mel_bins=80)
+    assert type(task.build_tts_model()).__name__ == "CampNetB200" and task.model.encoder.embed_tokens.num_embeddings == 33
+    with pytest.raises(NotImplementedError):
+        task.run_model({}, infer=False)
 
 
 def test_vocoder_checkpoint_layout(tmp_path):
