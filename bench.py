@@ -11,7 +11,6 @@ followed by the vocoder forward (79 kernels).  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys

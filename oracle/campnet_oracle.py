@@ -28,7 +28,7 @@ from typing import Dict
 import numpy as np
 
 from .cond_encoder_oracle import gelu, layer_norm_c
-from .fluentspeech_oracle import F32, _q, conv1d, linear, mel_encoder_forward
+from .fluentspeech_oracle import F32, _q, conv1d, linear
 
 HEADS = 2
 

@@ -17,7 +17,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import cond_encoder_oracle as CO          # noqa: E402
-from oracle import fluentspeech_oracle as O           # noqa: E402
 from speech_editing_toolkit_b200 import _lib, synth   # noqa: E402
 
 T0 = time.time()
