@@ -111,3 +111,26 @@ def test_campnet_config_validation_happens_before_any_device_call(lib_built):
     assert L.fse_campnet_forward(None, None, None, None, None, None, None, None, 1, 1, 1, None, 0, None) == -1
     if not torch.cuda.is_available():
         assert L.fse_campnet_create(C.byref(cfg()), C.byref(C.c_void_p())) == -2              # no device: FSE_ECUDA, no fallback
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(lib_built, tmp_path):
+    """The boundary is a C ABI: include/fse_b200.h compiles as C99 (no C++-isms, no torch types) and a plain C program links
+    against libfse_b200.so and gets an FSE_EINVAL + message back from an argument check (no device needed)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(inc, "fse_b200.h")], check=True)
+    src = tmp_path / "demo.c"
+    src.write_text('#include "fse_b200.h"\n#include <string.h>\n'
+                   "int main(void) {\n"
+                   "  fse_campnet_config c; fse_campnet* h = 0; memset(&c, 0, sizeof c);\n"
+                   "  int rc = fse_campnet_create(&c, &h);\n"
+                   "  return (rc == FSE_EINVAL && strlen(fse_last_error()) > 0 && fse_version() >= 100) ? 0 : 1;\n"
+                   "}\n")
+    exe = tmp_path / "demo"
+    libdir = os.path.dirname(lib_built)
+    subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-L", libdir, "-lfse_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
