@@ -64,15 +64,21 @@ def build_diffusion(hp: dict, phone_encoder=None, fs=None, mel_encoder=None) -> 
 class SpecDenoiserInferB200:
     """inference/tts/spec_denoiser.py::SpecDenoiserInfer from the tensor boundary on."""
 
-    def __init__(self, hparams_: dict, device=None, fs=None, vocoder: Optional[HifiGANB200] = None):
+    def __init__(self, hparams_: dict, device=None, fs=None, vocoder: Optional[HifiGANB200] = None, phone_encoder=None):
+        """`phone_encoder`: anything with len() = phone vocabulary (the reference's `self.ph_encoder`, inference/tts/spec_denoiser.py:38-41);
+        with it (or hparams['b200_vocab']) the native FastSpeechB200 condition encoder is built like the reference builds `fs`;
+        `fs=` injects a ready module instead."""
         self.hparams = hparams_
         self.device = torch.device(device or "cuda")
         self._fs = fs
+        if phone_encoder is None and fs is None and hparams_.get("b200_vocab"):
+            phone_encoder = range(int(hparams_["b200_vocab"]))
+        self.ph_encoder = phone_encoder
         self.model = self.build_model()
         self.vocoder = vocoder if vocoder is not None else self.build_vocoder()
 
     def build_model(self):
-        model = build_diffusion(self.hparams, fs=self._fs)
+        model = build_diffusion(self.hparams, phone_encoder=None if self._fs is not None else self.ph_encoder, fs=self._fs)
         work_dir = self.hparams.get("work_dir", "")
         if work_dir and os.path.isdir(work_dir):
             load_ckpt(model, work_dir, "model", force=False, strict=False)     # schedule buffers depend on `timesteps`
@@ -123,7 +129,10 @@ class SpeechDenoiserTaskB200:
         self.vocoder = None
 
     def build_model(self):
-        self.model = build_diffusion(self.hparams).cuda().eval()
+        """build_tts_model (tasks/speech_editing/spec_denoiser.py:29-36); the phone vocabulary comes from the dataset's
+        phone_set.json in the reference — here from hparams['b200_vocab'] when given (native condition encoder), else none."""
+        vocab = self.hparams.get("b200_vocab")
+        self.model = build_diffusion(self.hparams, phone_encoder=range(int(vocab)) if vocab else None).cuda().eval()
         return self.model
 
     def build_vocoder(self):
@@ -140,7 +149,13 @@ class SpeechDenoiserTaskB200:
         dev = torch.device("cuda")
         ref = sample["mels"].to(dev)
         mask = sample["time_mel_masks"].to(dev)
-        mel = self.model.sample(sample["cond"].to(dev), None, int(sample.get("seed", batch_idx)), ref, mask)
+        seed = int(sample.get("seed", batch_idx))
+        if "cond" in sample:                                       # a ready condition [B,T,H]
+            mel = self.model.sample(sample["cond"].to(dev), None, seed, ref, mask)
+        else:                                                      # the reference's sample dict: run_model(infer=True), :39-62
+            g = lambda k: None if sample.get(k) is None else sample[k].to(dev)
+            mel = self.model(g("txt_tokens"), mask.reshape(ref.shape[0], ref.shape[1], 1), g("mel2ph"), g("spk_embed"), ref, g("f0"), g("uv"),
+                             infer=True, use_pred_pitch=bool(sample.get("use_pred_pitch", False)), seed=seed, composite=True)["mel_out"]
         wav = self.vocoder(mel)
         return {"mel_out": mel, "wav_out": wav}
 

@@ -103,6 +103,9 @@ def test_registries_and_plugin_surface():
     for meth in ("build_model", "build_vocoder", "run_vocoder", "forward_model", "infer_once"):
         assert hasattr(plugin.SpecDenoiserInferB200, meth)
     assert hasattr(plugin.SpeechDenoiserTaskB200, "start") and callable(plugin.run_task)
+    from speech_editing_toolkit_b200.modules import FastSpeechB200
+    m2 = plugin.build_diffusion(HP, phone_encoder=range(41))               # as SpecDenoiserInferB200(phone_encoder=...) / b200_vocab do
+    assert isinstance(m2.fs, FastSpeechB200) and m2.fs.dict_size == 41 and m.fs is None
     for meth in ("build_tts_model", "run_model", "start"):                # tasks/speech_editing/campnet.py::CampNetTask
         assert hasattr(plugin.CampNetTaskB200, meth)
     task = plugin.CampNetTaskB200(ph_dict_size=33)
