@@ -82,3 +82,41 @@ def test_campnet_oracle_vs_live_campnet(seed, B, T, fpp, pads):
     assert np.abs(ours["mel_out_coarse"] - ret["mel_out_coarse"].numpy()).max() < 2e-4
     assert np.abs(ours["mel_out_fine"] - ret["mel_out_fine"].numpy()).max() < 2e-4
     assert np.abs(ours["attn"] - ret["attn"].numpy()).max() < 2e-5
+
+
+def test_integer_helpers_vs_live_reference_on_random_inputs():
+    """mel2token_to_dur, f0_to_coarse o denorm_f0, LengthRegulator, expand_states: bit-exact against the reference's own functions
+    over a few hundred random inputs (fixed seeds), including the boundaries (unvoiced frames, clamps, .5 durations, padding)."""
+    refshim.install("egs/spec_denoiser.yaml")
+    from modules.commons.nar_tts_modules import LengthRegulator
+    from modules.tts.commons.align_ops import expand_states
+    from utils.audio.align import mel2token_to_dur
+    from utils.audio.pitch.utils import denorm_f0, f0_to_coarse
+    from oracle import fluentspeech_oracle as O
+    rs = np.random.RandomState(123)
+    lr = LengthRegulator()
+    for _ in range(40):
+        B, Tt = int(rs.randint(1, 4)), int(rs.randint(1, 30))
+        dur = np.round(rs.uniform(0, 6, (B, Tt)) * 2) / 2                           # many exact .5 values: round half to even
+        dur = dur.astype(np.float32)
+        pad = rs.uniform(size=(B, Tt)) < 0.15
+        if dur[~pad].sum() == 0:
+            continue
+        want = lr(torch.from_numpy(dur), torch.from_numpy(pad)).numpy()
+        got = CO.length_regulator(dur, pad)
+        assert np.array_equal(got, want)
+        T = got.shape[1]
+        if T == 0:
+            continue
+        assert np.array_equal(O.mel2token_to_dur(got, Tt), mel2token_to_dur(torch.from_numpy(got), Tt).numpy())
+        h = rs.standard_normal((B, Tt, 5)).astype(np.float32)
+        assert np.array_equal(O.expand_states(h, got), expand_states(torch.from_numpy(h), torch.from_numpy(got)).numpy())
+    for _ in range(40):
+        n = int(rs.randint(1, 400))
+        f0 = rs.uniform(4.5, 10.5, n).astype(np.float32)                             # log2 Hz: below 50 Hz .. above 900 Hz
+        uv = (rs.uniform(size=n) < 0.3).astype(np.float32)
+        pad = rs.uniform(size=n) < 0.1
+        want_d = denorm_f0(torch.from_numpy(f0.copy()), torch.from_numpy(uv), pitch_padding=torch.from_numpy(pad))
+        got_d = CO.denorm_f0(f0, uv, pad)
+        assert np.abs(got_d - want_d.numpy()).max() < 2e-3
+        assert np.array_equal(O.f0_to_coarse(want_d.numpy()), f0_to_coarse(want_d).numpy())   # same input -> same bins, bit-exact
