@@ -3,7 +3,7 @@ WITHOUT torch: ctypes on libfse_b200.so + libcudart, numpy, and the numpy oracle
 (no `import torch` page-in), never aborts on a mismatch and prints one line per output with the error against the
 reference fixture and against the oracle, so that one short GPU call yields a full diagnosis.
 
-    python tools/cond_check.py [simt_f32 tc_bf16 ...] | tee gpurun_out/cond_check.txt
+    python tests/tools/cond_check.py [simt_f32 tc_bf16 ...] | tee gpurun_out/cond_check.txt
 
 TEST TOOL (imports oracle/): not part of the shipped path."""
 import ctypes as C
@@ -14,7 +14,7 @@ import traceback
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import cond_encoder_oracle as CO          # noqa: E402
 from speech_editing_toolkit_b200 import _lib, synth   # noqa: E402

@@ -1,7 +1,7 @@
 """Print the measured parity margins of the tensor-core path (relative mel-L1) against the reference fixtures and
 the bf16-operand oracle — the numbers the tolerances in tests/test_gpu_parity.py are set from."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import torch
