@@ -3,6 +3,7 @@ provides the CUDA stream; all arithmetic of the hot path happens inside libfse_b
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -29,6 +30,25 @@ def _tensor_table(sd: Dict[str, object], skip_suffixes=()):
         arr[i].data = a.ctypes.data_as(C.POINTER(C.c_float))
         arr[i].numel = a.size
     return arr, len(names), keep
+
+
+class _Range:
+    """NVTX range around a C-ABI call when FSE_NVTX=1 (the reference's only hook of this kind is Timer('hifigan') around the
+    vocoder, tasks/tts/vocoder_infer/hifigan.py:28); a no-op otherwise."""
+    enabled = os.environ.get("FSE_NVTX", "0") == "1"
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _Range.enabled:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if _Range.enabled:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -144,8 +164,9 @@ class Denoiser:
         mel = torch.empty(B, T, M, dtype=torch.float32, device=cond.device)
         xs = torch.empty(S, B, M, T, dtype=torch.float32, device=cond.device) if trace else None
         ws, nbytes = self._workspace(B, T, cond.device)
-        check(_lib.lib().fse_sample(self._h, _ptr(cond), _ptr(noise), seed, _ptr(ref_mel), _ptr(mask), _ptr(mel), _ptr(xs),
-                                    B, T, ws, nbytes, _stream()))
+        with _Range("fse_sample"):
+            check(_lib.lib().fse_sample(self._h, _ptr(cond), _ptr(noise), seed, _ptr(ref_mel), _ptr(mask), _ptr(mel), _ptr(xs),
+                                        B, T, ws, nbytes, _stream()))
         return (mel, xs) if trace else mel
 
     def sample_host(self, cond: np.ndarray, noise=None, seed: int = 0, ref_mel=None, mask=None) -> np.ndarray:
@@ -231,7 +252,8 @@ class Vocoder:
         wav = torch.empty(B, T * self.hop, dtype=torch.float32, device=mel.device)
         nbytes = _lib.lib().fse_vocoder_workspace_bytes(self._h, B, T)
         ws, nbytes = self._ws.get(nbytes, mel.device)
-        check(_lib.lib().fse_vocoder_forward(self._h, _ptr(mel), _ptr(wav), B, T, ws, nbytes, _stream()))
+        with _Range("fse_vocoder_forward"):
+            check(_lib.lib().fse_vocoder_forward(self._h, _ptr(mel), _ptr(wav), B, T, ws, nbytes, _stream()))
         return wav
 
     def forward_host(self, mel: np.ndarray) -> np.ndarray:
@@ -491,8 +513,9 @@ class CampNetKernel:
         enc = torch.empty(B, Tt, self.hidden, dtype=torch.float32, device=dev) if need_encoder_out else None
         nbytes = _lib.lib().fse_campnet_workspace_bytes(self._h, B, Tt, T)
         ws, nbytes = self._ws.get(nbytes, dev)
-        check(_lib.lib().fse_campnet_forward(self._h, _ptr(txt), _ptr(mels), _ptr(mask), _ptr(coarse), _ptr(fine), _ptr(attn), _ptr(enc),
-                                             B, Tt, T, ws, nbytes, _stream()))
+        with _Range("fse_campnet_forward"):
+            check(_lib.lib().fse_campnet_forward(self._h, _ptr(txt), _ptr(mels), _ptr(mask), _ptr(coarse), _ptr(fine), _ptr(attn), _ptr(enc),
+                                                 B, Tt, T, ws, nbytes, _stream()))
         ret = {"mel_out_coarse": coarse, "mel_out_fine": fine, "attn": attn}
         if need_encoder_out:
             ret["encoder_out"] = enc
