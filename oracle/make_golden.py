@@ -232,6 +232,81 @@ def campnet_fixture():
     print("campnet", ret["mel_out_fine"].shape, float(np.abs(ret["mel_out_fine"].numpy()).mean()), "attn", ret["attn"].shape)
 
 
+def edit_region_fixture():
+    """The region surgery of the inference script, from the reference's OWN code: inference/tts/spec_denoiser.py cannot be
+    imported (inference_acl, resemblyzer, g2p_en, ... are absent), so `SpecDenoiserInfer.forward_model` (:63-149) is cut out of
+    the source file with ast and run unmodified against a stand-in `self` whose model.fs is the real reference FastSpeech; the
+    tensors it hands to forward_dur and to the model are recorded.  `python oracle/make_golden.py edit_region` writes
+    tests/golden/edit_region.npz (three utterances: edit in the middle, at the end (no tail), longer replacement)."""
+    import ast
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(SEED)
+    hp = refshim.install("egs/spec_denoiser.yaml")
+    from modules.speech_editing.spec_denoiser.fs import FastSpeech
+    src_path = os.path.join(refshim.REF_ROOT, "inference", "tts", "spec_denoiser.py")
+    tree = ast.parse(open(src_path).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "SpecDenoiserInfer")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "forward_model")
+    ns = {"torch": torch, "np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), src_path, "exec"), ns)          # the reference's code, unmodified
+    forward_model = ns["forward_model"]
+    vocab = 80
+    fs = FastSpeech(vocab, hp).eval()
+    fs.load_state_dict(to_torch(synth.fastspeech_state_dict(SEED, vocab)), strict=False)
+
+    class Model:
+        def __init__(self):
+            self.fs, self.calls, self.dur_calls = fs, [], []
+            real = fs.forward_dur
+
+            def spy(dur_inp, masks, mel2ph, txt, ret, masked_dur=None, use_pred_mel2ph=False):
+                out = real(dur_inp, masks, mel2ph, txt, ret, masked_dur=masked_dur, use_pred_mel2ph=use_pred_mel2ph)
+                self.dur_calls.append(dict(masked_dur=masked_dur.clone(), masked_mel2ph=mel2ph.clone(), time_mel_masks_orig=masks.clone(),
+                                           edited_mel2ph=out.clone()))
+                return out
+            fs.forward_dur = spy
+
+        def __call__(self, txt, **kw):
+            self.calls.append(dict(kw, txt=txt))
+            return {"mel_out": torch.zeros(1, kw["mel2ph"].shape[1], 80)}
+
+    class Self:
+        device = "cpu"
+
+        def __init__(self, sample):
+            self.model, self._sample = Model(), sample
+
+        def input_to_batch(self, inp):
+            return self._sample
+
+        def run_vocoder(self, c):
+            return torch.zeros(1, 8)
+
+    out = {"seed": SEED, "vocab": vocab}
+    cases = [dict(seed=SEED, n_words=9, edit_span=(3, 4), new_span_phones=(2, 3, 1)),
+             dict(seed=SEED + 1, n_words=7, edit_span=(6, 7), new_span_phones=(4,)),                 # edit at the end: no tail
+             dict(seed=SEED + 2, n_words=8, edit_span=(1, 2), new_span_phones=(3, 3, 2, 2))]          # edit at the start: no head
+    for i, kw in enumerate(cases):
+        item = synth.synthetic_edit_item(vocab=vocab, **kw)
+        lt = lambda k: torch.from_numpy(item[k])[None]
+        sample = {"edited_txt_tokens": lt("edited_ph_token"), "mel": lt("mel"), "mel2ph": lt("mel2ph").clone(), "mel2word": lt("mel2word"),
+                  "dur": lt("dur"), "ph2word": lt("ph2word"), "edited_ph2word": lt("edited_ph2word"), "f0": lt("f0"), "uv": lt("uv"),
+                  "words_region": item["words_region"], "edited_words_region": item["edited_words_region"], "text": ["synthetic"],
+                  "spk_embed": lt("spk_embed")}
+        me = Self(sample)
+        with torch.no_grad():
+            forward_model(me, None)
+        call, dcall = me.model.calls[0], me.model.dur_calls[0]
+        assert call["use_pred_pitch"] is True and call["infer"] is True
+        for k, v in (("masked_dur", dcall["masked_dur"]), ("masked_mel2ph", dcall["masked_mel2ph"]), ("time_mel_masks_orig", dcall["time_mel_masks_orig"]),
+                     ("edited_mel2ph_pred", dcall["edited_mel2ph"]), ("mel2ph", call["mel2ph"]), ("ref_mels", call["ref_mels"]), ("f0", call["f0"]),
+                     ("uv", call["uv"]), ("time_mel_masks", call["time_mel_masks"])):
+            out[f"c{i}_{k}"] = v[0].numpy()
+        out[f"c{i}_kw"] = np.array([kw["seed"], kw["n_words"], *kw["edit_span"], len(kw["new_span_phones"]), *kw["new_span_phones"]], dtype=np.int64)
+        print("edit_region case", i, "T", item["mel2ph"].shape[0], "->", call["mel2ph"].shape[1], "masked frames", int(call["time_mel_masks"].sum()))
+    np.savez_compressed(os.path.join(OUT, "edit_region.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "mel_encoder":
         mel_encoder_fixture()
@@ -239,8 +314,11 @@ if __name__ == "__main__":
         cond_encoder_fixture()
     elif len(sys.argv) > 1 and sys.argv[1] == "campnet":
         campnet_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "edit_region":
+        edit_region_fixture()
     else:
         main()
         mel_encoder_fixture()
         cond_encoder_fixture()
         campnet_fixture()
+        edit_region_fixture()

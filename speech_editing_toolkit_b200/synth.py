@@ -280,3 +280,33 @@ def synthetic_campnet_batch(seed: int, B: int, T: int, vocab: int = 80, frames_p
     for item, n in pad_items:
         b = pad_edit_batch(b, item, n, frames_per_phone)
     return dict(txt_tokens=b["txt_tokens"], mels=b["ref_mels"], time_mel_masks=b["time_mel_masks"][:, :, None].copy())
+
+
+def synthetic_edit_item(seed: int, n_words: int = 9, n_mels: int = 80, vocab: int = 80, edit_span=(3, 4), new_span_phones=(2, 3, 1)):
+    """One utterance as inference/tts/spec_denoiser.py::preprocess_input produces it (:151-196), synthetic: words of 1-4
+    phones, phones of 2-7 frames (1-based ph2word / mel2ph / mel2word), an edit that replaces the words `edit_span` (1-based,
+    inclusive) by len(new_span_phones) new words with that many phones each."""
+    rs = np.random.RandomState(seed + 71)
+    phones_per_word = rs.randint(1, 5, size=n_words)
+    ph2word = np.repeat(np.arange(1, n_words + 1), phones_per_word).astype(np.int64)
+    Tp = len(ph2word)
+    dur = rs.randint(2, 8, size=Tp).astype(np.int64)
+    mel2ph = np.repeat(np.arange(1, Tp + 1), dur).astype(np.int64)
+    mel2word = ph2word[mel2ph - 1]
+    T = len(mel2ph)
+    w0, w1 = edit_span
+    head_words, tail_words = w0 - 1, n_words - w1
+    new_ppw = np.concatenate([phones_per_word[:head_words], np.asarray(new_span_phones), phones_per_word[w1:]])
+    edited_ph2word = np.repeat(np.arange(1, len(new_ppw) + 1), new_ppw).astype(np.int64)
+    c0, c1 = w0, w0 + len(new_span_phones) - 1
+    ph_token = rs.randint(3, vocab, size=Tp).astype(np.int64)
+    n_head_ph, n_tail_ph = int(phones_per_word[:head_words].sum()), int(phones_per_word[w1:].sum())
+    edited_ph_token = np.concatenate([ph_token[:n_head_ph], rs.randint(3, vocab, size=int(np.sum(new_span_phones))),
+                                      ph_token[Tp - n_tail_ph:] if n_tail_ph else ph_token[:0]]).astype(np.int64)
+    mel = np.clip(rs.standard_normal((T, n_mels)) * 1.5 - 3.0, -6.0, 1.5).astype(F32)
+    f0 = rs.uniform(6.5, 8.5, T).astype(F32)
+    uv = (rs.uniform(size=T) < 0.3).astype(F32)
+    spk = (rs.standard_normal(256) / 16).astype(F32)
+    assert len(edited_ph_token) == len(edited_ph2word) and tail_words >= 0
+    return dict(ph2word=ph2word, edited_ph2word=edited_ph2word, mel2ph=mel2ph, mel2word=mel2word, dur=dur, ph_token=ph_token,
+                edited_ph_token=edited_ph_token, words_region=[(w0, w1)], edited_words_region=[(c0, c1)], mel=mel, f0=f0, uv=uv, spk_embed=spk)
