@@ -278,6 +278,32 @@ int fse_campnet_forward(fse_campnet* h, const int64_t* txt, const float* mels, c
                         float* mel_out_fine, float* attn, float* encoder_out, int32_t B, int32_t Tt, int32_t T, void* workspace,
                         int64_t workspace_bytes, void* stream);
 
+/* --- region surgery of the inference script (inference/tts/spec_denoiser.py:88-131) ------------------
+ * The integer / index work between the forced alignment of the original utterance and the model call: the reference does
+ * it for one utterance with host-side tensor slicing; these three calls do it on the device for a padded batch (per-item
+ * lengths and regions), bit-exactly.  All pointers are device pointers, integer tensors int64 unless noted; *_len may be
+ * NULL (= every item uses the full padded length).  regions [B,4] = (w0, w1, c0, c1): the edited word span in the original
+ * words and the span that replaces it in the edited words (1-based, inclusive: words_region[0], edited_words_region[0]).
+ * Stateless (no handle); asynchronous on the passed stream. */
+/* :88-97   masked_dur [B,Tpe] (durations of the phones before / after the span, for forward_dur(masked_dur=...)),
+ *          masked_mel2ph [B,T] (0 inside the span), time_mel_masks_orig [B,T] fp32 (1 inside the span) */
+int fse_edit_prepare(const int64_t* mel2ph, const int64_t* mel2word, const int64_t* T_len, const int64_t* ph2word, const int64_t* dur,
+                     const int64_t* Tp_len, const int64_t* Tpe_len, const int64_t* regions, int64_t* masked_dur, int64_t* masked_mel2ph,
+                     float* time_mel_masks_orig, int32_t B, int32_t T, int32_t Tp, int32_t Tpe, void* stream);
+/* :99-110  from the predicted alignment edited_mel2ph [B,Te] of the edited text (forward_dur(..., use_pred_mel2ph=True)):
+ *          plan [B,8] int64 = (Tn, head_idx, tail_idx, length_edited, n_edit, n_tail, tail_shift, has_tail) and the two
+ *          order-preserving selections sel_edit [B,Te] / sel_tail [B,T] (int32) the assembly copies from.  The caller reads
+ *          plan[:,0] (one host sync, as the reference's own slicing implies) to size the outputs of fse_edit_assemble. */
+int fse_edit_plan(const int64_t* mel2ph, const int64_t* mel2word, const int64_t* T_len, const int64_t* edited_ph2word, const int64_t* Tpe_len,
+                  const int64_t* regions, const int64_t* edited_mel2ph, const int64_t* Te_len, int32_t* sel_edit, int32_t* sel_tail, int64_t* plan,
+                  int32_t B, int32_t T, int32_t Tpe, int32_t Te, void* stream);
+/* :103-131 the model inputs, padded to Tn = max(plan[:,0]): mel2ph [B,Tn] (head copy, edited span, re-based tail), ref_mels
+ *          [B,Tn,n_mels] / f0 / uv [B,Tn] (head + tail copies, zeros inside the span), time_mel_masks [B,Tn] fp32 */
+int fse_edit_assemble(const int64_t* mel2ph, const int64_t* T_len, const int64_t* regions, const int64_t* plan, const int64_t* edited_mel2ph,
+                      const int32_t* sel_edit, const int32_t* sel_tail, const float* mel, const float* f0, const float* uv, int64_t* out_mel2ph,
+                      float* out_ref_mels, float* out_f0, float* out_uv, float* out_time_mel_masks, int32_t B, int32_t T, int32_t Te, int32_t Tn,
+                      int32_t n_mels, void* stream);
+
 /* --- kernel timing (opt-in) -------------------------------------------------------------------
  * When enabled, every kernel the handle launches is bracketed by CUDA events on the launch stream;
  * *_profile_read waits for them and returns the summed device time (ms) and launch count per kind

@@ -101,6 +101,9 @@ SIGNATURES = {
     "fse_campnet_workspace_bytes": (C.c_int64, [_P, C.c_int32, C.c_int32, C.c_int32]),
     "fse_campnet_last_launches": (C.c_int64, [_P]),
     "fse_campnet_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
+    "fse_edit_prepare": (C.c_int, [_P] * 11 + [C.c_int32] * 4 + [_P]),
+    "fse_edit_plan": (C.c_int, [_P] * 11 + [C.c_int32] * 4 + [_P]),
+    "fse_edit_assemble": (C.c_int, [_P] * 15 + [C.c_int32] * 5 + [_P]),
     "fse_denoiser_profile": (C.c_int, [_P, C.c_int32]),
     "fse_denoiser_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "fse_vocoder_profile": (C.c_int, [_P, C.c_int32]),

@@ -520,3 +520,55 @@ class CampNetKernel:
         if need_encoder_out:
             ret["encoder_out"] = enc
         return ret
+
+
+# ---------------------------------------------------------------------------------------------- region surgery (stateless)
+def _i64(t):
+    return None if t is None else t.contiguous().long()
+
+
+def edit_prepare(mel2ph, mel2word, ph2word, dur, regions, n_edited_phones: int, T_len=None, Tp_len=None, Tpe_len=None):
+    """inference/tts/spec_denoiser.py:88-97 for a padded batch -> (masked_dur [B,Tpe], masked_mel2ph [B,T], time_mel_masks_orig [B,T]).
+    regions [B,4] int64 = (w0, w1, c0, c1)."""
+    _need_cuda(mel2ph, mel2word, ph2word, dur, regions, T_len, Tp_len, Tpe_len)
+    B, T = mel2ph.shape
+    Tp, Tpe = ph2word.shape[1], int(n_edited_phones)
+    mel2ph, mel2word, ph2word, dur, regions = _i64(mel2ph), _i64(mel2word), _i64(ph2word), _i64(dur), _i64(regions)
+    T_len, Tp_len, Tpe_len = _i64(T_len), _i64(Tp_len), _i64(Tpe_len)
+    dev = mel2ph.device
+    masked_dur = torch.empty(B, Tpe, dtype=torch.int64, device=dev)
+    masked_mel2ph = torch.empty(B, T, dtype=torch.int64, device=dev)
+    mask_orig = torch.empty(B, T, dtype=torch.float32, device=dev)
+    check(_lib.lib().fse_edit_prepare(_ptr(mel2ph), _ptr(mel2word), _ptr(T_len), _ptr(ph2word), _ptr(dur), _ptr(Tp_len), _ptr(Tpe_len), _ptr(regions),
+                                      _ptr(masked_dur), _ptr(masked_mel2ph), _ptr(mask_orig), B, T, Tp, Tpe, _stream()))
+    return masked_dur, masked_mel2ph, mask_orig
+
+
+def edit_assemble(mel2ph, mel2word, edited_ph2word, edited_mel2ph, regions, mel, f0, uv, T_len=None, Tpe_len=None, Te_len=None):
+    """:99-131 for a padded batch -> dict(mel2ph [B,Tn] int64, ref_mels [B,Tn,M], f0, uv, time_mel_masks [B,Tn], plan [B,8] (host)).
+    One host sync reads the per-item output lengths (the reference's own slicing implies the same)."""
+    _need_cuda(mel2ph, mel2word, edited_ph2word, edited_mel2ph, regions, mel, f0, uv, T_len, Tpe_len, Te_len)
+    B, T = mel2ph.shape
+    Tpe, Te, M = edited_ph2word.shape[1], edited_mel2ph.shape[1], mel.shape[2]
+    mel2ph, mel2word, edited_ph2word, edited_mel2ph, regions = _i64(mel2ph), _i64(mel2word), _i64(edited_ph2word), _i64(edited_mel2ph), _i64(regions)
+    T_len, Tpe_len, Te_len = _i64(T_len), _i64(Tpe_len), _i64(Te_len)
+    mel = mel.contiguous().float()
+    f0 = None if f0 is None else f0.contiguous().float()
+    uv = None if uv is None else uv.contiguous().float()
+    dev = mel2ph.device
+    sel_edit = torch.empty(B, Te, dtype=torch.int32, device=dev)
+    sel_tail = torch.empty(B, T, dtype=torch.int32, device=dev)
+    plan = torch.empty(B, 8, dtype=torch.int64, device=dev)
+    check(_lib.lib().fse_edit_plan(_ptr(mel2ph), _ptr(mel2word), _ptr(T_len), _ptr(edited_ph2word), _ptr(Tpe_len), _ptr(regions), _ptr(edited_mel2ph),
+                                   _ptr(Te_len), _ptr(sel_edit), _ptr(sel_tail), _ptr(plan), B, T, Tpe, Te, _stream()))
+    plan_h = plan.cpu()
+    Tn = int(plan_h[:, 0].max().item())
+    if Tn <= 0:
+        raise FseError("region surgery produced an empty sequence")
+    out = dict(mel2ph=torch.empty(B, Tn, dtype=torch.int64, device=dev), ref_mels=torch.empty(B, Tn, M, dtype=torch.float32, device=dev),
+               f0=torch.empty(B, Tn, dtype=torch.float32, device=dev), uv=torch.empty(B, Tn, dtype=torch.float32, device=dev),
+               time_mel_masks=torch.empty(B, Tn, dtype=torch.float32, device=dev), plan=plan_h)
+    check(_lib.lib().fse_edit_assemble(_ptr(mel2ph), _ptr(T_len), _ptr(regions), _ptr(plan), _ptr(edited_mel2ph), _ptr(sel_edit), _ptr(sel_tail),
+                                       _ptr(mel), _ptr(f0), _ptr(uv), _ptr(out["mel2ph"]), _ptr(out["ref_mels"]), _ptr(out["f0"]), _ptr(out["uv"]),
+                                       _ptr(out["time_mel_masks"]), B, T, Te, Tn, M, _stream()))
+    return out

@@ -99,6 +99,8 @@ class SpecDenoiserInferB200:
         """`inp` holds the tensors the reference builds just before calling the model
         (inference/tts/spec_denoiser.py:133-138): either the full condition-encoder inputs (needs `fs`) or a
         ready `cond[B,T,H]`.  Returns (wav_out, mel_out) like the reference's first two outputs per item."""
+        if "edited_txt_tokens" in inp:
+            return self.edit_forward(inp)
         dev = self.device
         ref = inp["ref_mels"].to(dev)
         mask = inp["time_mel_masks"].to(dev).reshape(ref.shape[0], ref.shape[1], 1)
@@ -112,8 +114,44 @@ class SpecDenoiserInferB200:
         wav = self.run_vocoder(mel)
         return wav, mel
 
+    @torch.no_grad()
+    def edit_forward(self, sample: dict):
+        """The reference's forward_model from its `sample` batch on (inference/tts/spec_denoiser.py:63-149, after input_to_batch):
+        encoder / style / forward_dur on the EDITED text with the unedited phones' durations given (:84-98), the region surgery
+        (:99-131, fse_edit_*), the model call and compositing (:133-136), the vocoder (:137).  `sample` holds the reference's keys
+        (edited_txt_tokens, mel, mel2ph, mel2word, dur, ph2word, edited_ph2word, f0, uv, spk_embed, words_region,
+        edited_words_region), every tensor with a leading batch axis; B > 1 is allowed when the items share their padded
+        lengths (`*_len` tensors may carry the real ones).  Returns (wav_out, mel_out, aux dict)."""
+        from . import engine as E
+        dev = self.device
+        g = lambda k: sample[k].to(dev)
+        txt, mel, mel2ph, mel2word = g("edited_txt_tokens"), g("mel"), g("mel2ph"), g("mel2word")
+        B = txt.shape[0]
+        wr, er = sample["words_region"], sample["edited_words_region"]
+        if torch.is_tensor(wr):
+            regions = torch.cat([wr.reshape(B, 2), er.reshape(B, 2)], 1).long().to(dev)
+        else:                                                   # the reference's list-of-tuples form, one region per item
+            regions = torch.tensor([[*wr[b if len(wr) > 1 else 0], *er[b if len(er) > 1 else 0]] for b in range(B)], dtype=torch.int64, device=dev)
+        fs = self.model.fs
+        encoder_out = fs.encoder(txt)
+        style = fs.forward_style_embed(g("spk_embed"), None)
+        masked_dur, masked_mel2ph, mask_orig = E.edit_prepare(mel2ph, mel2word, g("ph2word"), g("dur"), regions, txt.shape[1],
+                                                               sample.get("T_len"), sample.get("Tp_len"), sample.get("Tpe_len"))
+        dur_inp = fs.engine().dur_input(encoder_out, None if isinstance(style, int) else style[:, 0], txt)
+        ret = {}
+        edited_mel2ph = fs.forward_dur(dur_inp, mask_orig, masked_mel2ph, txt, ret, masked_dur=masked_dur, use_pred_mel2ph=True)
+        out = E.edit_assemble(mel2ph, mel2word, g("edited_ph2word"), edited_mel2ph, regions, mel, g("f0"), g("uv"), sample.get("T_len"),
+                              sample.get("Tpe_len"), sample.get("Te_len"))
+        mask = out["time_mel_masks"][:, :, None]
+        res = self.model(txt, time_mel_masks=mask, mel2ph=out["mel2ph"], spk_embed=g("spk_embed"), ref_mels=out["ref_mels"], f0=out["f0"],
+                         uv=out["uv"], energy=None, infer=True, use_pred_pitch=True, seed=sample.get("seed"), composite=True)
+        mel_out = res["mel_out"]                                # already mel_out * mask + ref_mels * (1 - mask)  (:136)
+        wav_out = self.run_vocoder(mel_out)
+        return wav_out, mel_out, dict(out, dur=ret["dur"], edited_mel2ph_pred=edited_mel2ph, masked_dur=masked_dur,
+                                      time_mel_masks_orig=mask_orig)
+
     def infer_once(self, inp: dict):
-        wav, mel = self.forward_model(inp)
+        wav, mel = self.forward_model(inp)[:2]
         return wav.cpu().numpy(), mel.cpu().numpy()
 
 

@@ -205,3 +205,52 @@ def test_libritts_config_without_pitch_embed(lib_built):
         else:
             assert rel_l1(out["decoder_inp"], ref["decoder_inp"]) < 2e-2
             assert rel_l1(out["dur"], ref["dur"]) < 2e-2
+
+
+UNVERIFIED = pytest.mark.skipif(__import__("os").environ.get("FSE_TEST_UNVERIFIED") != "1",
+                                reason="written after round 1's GPU budget ended: first GPU contact pending (set FSE_TEST_UNVERIFIED=1)")
+
+
+@UNVERIFIED
+def test_region_surgery_kernels_vs_reference_code_fixture(lib_built):
+    """fse_edit_prepare / fse_edit_plan / fse_edit_assemble (inference/tts/spec_denoiser.py:88-131) against the tensors recorded from
+    the reference's own forward_model code; the per-item logic is already checked on the host (tests/test_edit_region_core.py)."""
+    _need_gpu()
+    from speech_editing_toolkit_b200 import engine as E
+    from test_edit_region_oracle import case
+    g = golden("edit_region.npz")
+    for i in range(3):
+        item, want = case(g, i)
+        b = lambda k, dt=None: cu(item[k] if dt is None else item[k].astype(dt))[None]
+        regions = cu(np.array([[*item["words_region"][0], *item["edited_words_region"][0]]], dtype=np.int64))
+        md, mm, mo = E.edit_prepare(b("mel2ph"), b("mel2word"), b("ph2word"), b("dur"), regions, len(item["edited_ph2word"]))
+        assert np.array_equal(md[0].cpu().numpy(), want["masked_dur"]) and np.array_equal(mm[0].cpu().numpy(), want["masked_mel2ph"])
+        assert np.array_equal(mo[0].cpu().numpy(), want["time_mel_masks_orig"].astype(np.float32))
+        out = E.edit_assemble(b("mel2ph"), b("mel2word"), b("edited_ph2word"), cu(want["edited_mel2ph_pred"])[None], regions, b("mel"), b("f0"), b("uv"))
+        assert np.array_equal(out["mel2ph"][0].cpu().numpy(), want["mel2ph"])
+        assert np.array_equal(out["time_mel_masks"][0].cpu().numpy(), want["time_mel_masks"][:, 0])
+        for k in ("ref_mels", "f0", "uv"):
+            assert np.array_equal(out[k][0].cpu().numpy(), want[k]), k
+
+
+@UNVERIFIED
+def test_edit_forward_end_to_end_shapes(lib_built):
+    """SpecDenoiserInferB200.forward_model on the reference's `sample` batch: edited text -> durations -> surgery -> model -> vocoder."""
+    _need_gpu()
+    from speech_editing_toolkit_b200 import plugin, synth
+    from speech_editing_toolkit_b200.vocoder import HifiGANB200
+    item = synth.synthetic_edit_item(3, n_words=9, edit_span=(3, 4), new_span_phones=(2, 3, 1))
+    hp = dict(HP, timesteps=4, residual_layers=4, vocoder_ckpt="", work_dir="")
+    inf = plugin.SpecDenoiserInferB200(hp, vocoder=HifiGANB200(state_dict=synth.hifigan_state_dict(1)), phone_encoder=range(80))
+    t_ = lambda sd: {k: torch.from_numpy(v) for k, v in sd.items()}
+    inf.model.fs.load_state_dict(t_(synth.fastspeech_state_dict(1, 80)), strict=False)
+    inf.model.mel_encoder.load_state_dict(t_(synth.mel_encoder_state_dict(1)))
+    inf.model.denoise_fn.load_state_dict(t_(synth.denoiser_state_dict(1, layers=4)))
+    sample = {k: torch.from_numpy(item[k])[None] for k in ("mel", "mel2ph", "mel2word", "dur", "ph2word", "edited_ph2word", "f0", "uv", "spk_embed")}
+    sample.update(edited_txt_tokens=torch.from_numpy(item["edited_ph_token"])[None], words_region=item["words_region"],
+                  edited_words_region=item["edited_words_region"], seed=5)
+    wav, mel, aux = inf.forward_model(sample)
+    Tn = int(aux["plan"][0, 0])
+    assert mel.shape == (1, Tn, 80) and wav.shape == (1, Tn * 256) and torch.isfinite(wav).all()
+    m = aux["time_mel_masks"][0].bool()
+    assert torch.equal(mel[0][~m], aux["ref_mels"][0][~m])                      # unedited frames: the original mel, bit for bit
