@@ -134,3 +134,22 @@ def test_header_is_plain_c_and_links_from_a_c_program(lib_built, tmp_path):
     libdir = os.path.dirname(lib_built)
     subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-L", libdir, "-lfse_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_edit_region_argument_checks_without_device(lib_built):
+    """fse_edit_* validate pointers and sizes before touching the device; with valid arguments and no GPU they fail loudly."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from speech_editing_toolkit_b200 import _lib
+    L = _lib.lib()
+    a = np.zeros(8, dtype=np.int64)
+    f = np.zeros(8, dtype=np.float32)
+    P = lambda x: C.c_void_p(x.ctypes.data)
+    assert L.fse_edit_prepare(None, None, None, None, None, None, None, None, None, None, None, 1, 1, 1, 1, None) == -1
+    assert L.fse_edit_prepare(P(a), P(a), None, P(a), P(a), None, None, P(a), P(a), P(a), P(f), 1, 0, 1, 1, None) == -1
+    assert b"positive" in L.fse_last_error()
+    assert L.fse_edit_plan(P(a), P(a), None, P(a), None, P(a), None, None, P(a), P(a), P(a), 1, 4, 4, 4, None) == -1      # edited_mel2ph missing
+    assert L.fse_edit_assemble(P(a), None, P(a), P(a), P(a), P(a), P(a), None, None, None, P(a), P(f), P(f), P(f), P(f), 1, 4, 4, 4, 8, None) == -1
+    if not torch.cuda.is_available():    # host pointers are never dereferenced: the device check comes first and fails with FSE_ECUDA
+        assert L.fse_edit_prepare(P(a), P(a), None, P(a), P(a), None, None, P(a), P(a), P(a), P(f), 1, 4, 4, 4, None) == -2
