@@ -304,6 +304,32 @@ int fse_edit_assemble(const int64_t* mel2ph, const int64_t* T_len, const int64_t
                       float* out_ref_mels, float* out_f0, float* out_uv, float* out_time_mel_masks, int32_t B, int32_t T, int32_t Te, int32_t Tn,
                       int32_t n_mels, void* stream);
 
+/* --- mel front-end of the inference entry point: wav -> log10-mel -----------------------------------
+ * utils/audio/__init__.py:34-81 `librosa_wav2spec` (inference/tts/spec_denoiser.py:258: fmin 55, fmax 7600, sr 22050, fft 1024,
+ * hop 256, Hann, 80 mels, eps 1e-6): librosa.stft(center=True, pad_mode="constant") -> |.| -> librosa.filters.mel (Slaney) ->
+ * log10(max(eps, .)).  The windowed DFT is a (fft_size / hop_size)-tap conv-GEMM over the waveform viewed as rows of hop_size
+ * samples, the mel projection a second GEMM; both on fp32 CUDA cores (low-energy bins need fp32 operands). */
+typedef struct fse_mel_frontend fse_mel_frontend;
+typedef struct fse_mel_frontend_config {
+  int32_t sample_rate;   /* audio_sample_rate, 22050 */
+  int32_t fft_size;      /* 1024: an even multiple of hop_size */
+  int32_t hop_size;      /* 256 */
+  int32_t win_length;    /* win_size, 1024 (must equal fft_size) */
+  int32_t num_mels;      /* audio_num_mel_bins, 80 */
+  float fmin, fmax;      /* 55, 7600; -1 = 0 / sample_rate/2 as in the reference (:63-64) */
+  float eps;             /* 1e-6 */
+} fse_mel_frontend_config;
+int fse_mel_frontend_create(const fse_mel_frontend_config* cfg, fse_mel_frontend** out);
+void fse_mel_frontend_destroy(fse_mel_frontend* h);
+/* 1 + n_samples / hop_size (librosa's frame count with center=True) */
+int64_t fse_mel_frontend_frames(const fse_mel_frontend* h, int64_t n_samples);
+int64_t fse_mel_frontend_workspace_bytes(const fse_mel_frontend* h, int32_t B, int64_t n_samples);
+/* wav [B, n_samples] fp32 device (n_samples a multiple of hop_size: pad with zeros, as librosa's own padding is zeros) ->
+ * mel [B, frames, num_mels] fp32 device = librosa_wav2spec(...)['mel'] per item */
+int fse_mel_frontend_forward(fse_mel_frontend* h, const float* wav, float* mel, int32_t B, int64_t n_samples, void* workspace,
+                             int64_t workspace_bytes, void* stream);
+int64_t fse_mel_frontend_last_launches(const fse_mel_frontend* h);
+
 /* --- kernel timing (opt-in) -------------------------------------------------------------------
  * When enabled, every kernel the handle launches is bracketed by CUDA events on the launch stream;
  * *_profile_read waits for them and returns the summed device time (ms) and launch count per kind

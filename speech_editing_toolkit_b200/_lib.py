@@ -47,6 +47,11 @@ class CampNetConfig(C.Structure):
                 ("heads", C.c_int32), ("ffn_kernel", C.c_int32), ("fine_blocks", C.c_int32), ("fine_kernel", C.c_int32), ("mode", C.c_int32)]
 
 
+class MelFrontendConfig(C.Structure):
+    _fields_ = [("sample_rate", C.c_int32), ("fft_size", C.c_int32), ("hop_size", C.c_int32), ("win_length", C.c_int32), ("num_mels", C.c_int32),
+                ("fmin", C.c_float), ("fmax", C.c_float), ("eps", C.c_float)]
+
+
 class Tensor(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.POINTER(C.c_float)), ("numel", C.c_int64)]
 
@@ -104,6 +109,12 @@ SIGNATURES = {
     "fse_edit_prepare": (C.c_int, [_P] * 11 + [C.c_int32] * 4 + [_P]),
     "fse_edit_plan": (C.c_int, [_P] * 11 + [C.c_int32] * 4 + [_P]),
     "fse_edit_assemble": (C.c_int, [_P] * 15 + [C.c_int32] * 5 + [_P]),
+    "fse_mel_frontend_create": (C.c_int, [C.POINTER(MelFrontendConfig), C.POINTER(_P)]),
+    "fse_mel_frontend_destroy": (None, [_P]),
+    "fse_mel_frontend_frames": (C.c_int64, [_P, C.c_int64]),
+    "fse_mel_frontend_workspace_bytes": (C.c_int64, [_P, C.c_int32, C.c_int64]),
+    "fse_mel_frontend_forward": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, _P, C.c_int64, _P]),
+    "fse_mel_frontend_last_launches": (C.c_int64, [_P]),
     "fse_denoiser_profile": (C.c_int, [_P, C.c_int32]),
     "fse_denoiser_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "fse_vocoder_profile": (C.c_int, [_P, C.c_int32]),

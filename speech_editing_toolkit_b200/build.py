@@ -10,8 +10,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libfse_b200.so")
-SOURCES = ["denoiser.cu", "hifigan.cu", "mel_encoder.cu", "cond_encoder.cu", "campnet.cu", "edit_region.cu", "debug.cu"]
-HEADERS = ["conv_gemm.cuh", "epilogues.cuh", "fse_common.cuh", "ptx_sm100.cuh", "denoiser_fused.cuh", "denoiser_stream.cuh", "rowwise.cuh", "attention_tc.cuh", "edit_region_core.h",
+SOURCES = ["denoiser.cu", "hifigan.cu", "mel_encoder.cu", "cond_encoder.cu", "campnet.cu", "edit_region.cu", "mel_frontend.cu", "debug.cu"]
+HEADERS = ["conv_gemm.cuh", "epilogues.cuh", "fse_common.cuh", "ptx_sm100.cuh", "denoiser_fused.cuh", "denoiser_stream.cuh", "rowwise.cuh", "attention_tc.cuh", "edit_region_core.h", "mel_frontend_weights.h",
            "../../include/fse_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -572,3 +572,47 @@ def edit_assemble(mel2ph, mel2word, edited_ph2word, edited_mel2ph, regions, mel,
                                        _ptr(mel), _ptr(f0), _ptr(uv), _ptr(out["mel2ph"]), _ptr(out["ref_mels"]), _ptr(out["f0"]), _ptr(out["uv"]),
                                        _ptr(out["time_mel_masks"]), B, T, Te, Tn, M, _stream()))
     return out
+
+
+class MelFrontend:
+    """Handle of the wav -> log10-mel front-end (fse_mel_frontend_*; utils/audio/__init__.py:34-81 `librosa_wav2spec`)."""
+
+    def __init__(self, sample_rate: int = 22050, fft_size: int = 1024, hop_size: int = 256, win_length: int = 1024, num_mels: int = 80,
+                 fmin: float = 80, fmax: float = -1, eps: float = 1e-6):
+        cfg = _lib.MelFrontendConfig()
+        cfg.sample_rate, cfg.fft_size, cfg.hop_size, cfg.win_length, cfg.num_mels = sample_rate, fft_size, hop_size, win_length, num_mels
+        cfg.fmin, cfg.fmax, cfg.eps = float(fmin), float(fmax), float(eps)
+        self.cfg, self.hop, self.num_mels = cfg, hop_size, num_mels
+        self._h = C.c_void_p()
+        check(_lib.lib().fse_mel_frontend_create(C.byref(cfg), C.byref(self._h)))
+        self._ws = _Workspace()
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                _lib.lib().fse_mel_frontend_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    @property
+    def last_launches(self) -> int:
+        return int(_lib.lib().fse_mel_frontend_last_launches(self._h))
+
+    def forward(self, wav: torch.Tensor) -> torch.Tensor:
+        """wav[B, n] fp32 cuda -> mel[B, 1 + n // hop, num_mels] (librosa's frame count; the tail is zero-padded to a multiple of hop,
+        which is what librosa's own centre padding would read there)."""
+        _need_cuda(wav)
+        B, n = wav.shape
+        wav = wav.contiguous().float()
+        pad = (-n) % self.hop
+        if pad:
+            wav = torch.nn.functional.pad(wav, (0, pad))
+        npad = n + pad
+        frames = 1 + npad // self.hop
+        mel = torch.empty(B, frames, self.num_mels, dtype=torch.float32, device=wav.device)
+        nbytes = _lib.lib().fse_mel_frontend_workspace_bytes(self._h, B, npad)
+        ws, nbytes = self._ws.get(nbytes, wav.device)
+        with _Range("fse_mel_frontend_forward"):
+            check(_lib.lib().fse_mel_frontend_forward(self._h, _ptr(wav), _ptr(mel), B, npad, ws, nbytes, _stream()))
+        return mel[:, :1 + n // self.hop]

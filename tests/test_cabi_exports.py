@@ -153,3 +153,25 @@ def test_edit_region_argument_checks_without_device(lib_built):
     assert L.fse_edit_assemble(P(a), None, P(a), P(a), P(a), P(a), P(a), None, None, None, P(a), P(f), P(f), P(f), P(f), 1, 4, 4, 4, 8, None) == -1
     if not torch.cuda.is_available():    # host pointers are never dereferenced: the device check comes first and fails with FSE_ECUDA
         assert L.fse_edit_prepare(P(a), P(a), None, P(a), P(a), None, None, P(a), P(a), P(a), P(f), 1, 4, 4, 4, None) == -2
+
+
+def test_mel_frontend_config_validation_without_device(lib_built):
+    import ctypes as C
+    import torch
+    from speech_editing_toolkit_b200 import _lib
+    L = _lib.lib()
+
+    def cfg(**kw):
+        c = _lib.MelFrontendConfig()
+        c.sample_rate, c.fft_size, c.hop_size, c.win_length, c.num_mels, c.fmin, c.fmax, c.eps = 22050, 1024, 256, 1024, 80, 55.0, 7600.0, 1e-6
+        for k, v in kw.items():
+            setattr(c, k, v)
+        return c
+
+    for bad, word in ((dict(hop_size=100), b"hop_size"), (dict(fft_size=1000), b"fft_size"), (dict(win_length=800), b"win_length"),
+                      (dict(num_mels=81), b"num_mels"), (dict(fmin=8000.0), b"fmin"), (dict(fmax=20000.0), b"fmax"), (dict(eps=0.0), b"eps")):
+        assert L.fse_mel_frontend_create(C.byref(cfg(**bad)), C.byref(C.c_void_p())) == -1, bad
+        assert word in L.fse_last_error(), (bad, L.fse_last_error())
+    assert L.fse_mel_frontend_frames(None, 100) == 0 and L.fse_mel_frontend_workspace_bytes(None, 1, 256) == 0
+    if not torch.cuda.is_available():
+        assert L.fse_mel_frontend_create(C.byref(cfg()), C.byref(C.c_void_p())) == -2

@@ -254,3 +254,24 @@ def test_edit_forward_end_to_end_shapes(lib_built):
     assert mel.shape == (1, Tn, 80) and wav.shape == (1, Tn * 256) and torch.isfinite(wav).all()
     m = aux["time_mel_masks"][0].bool()
     assert torch.equal(mel[0][~m], aux["ref_mels"][0][~m])                      # unedited frames: the original mel, bit for bit
+
+
+@UNVERIFIED
+def test_mel_frontend_vs_oracle(lib_built):
+    """fse_mel_frontend_forward (wav -> log10-mel, utils/audio/__init__.py:34-81) against oracle/mel_frontend_oracle.py: noise-like
+    signals within 1e-4 in log10; a pure tone within 1e-5 of the frame's strongest band in the linear domain (fp32 floor)."""
+    _need_gpu()
+    from oracle import mel_frontend_oracle as MO
+    from speech_editing_toolkit_b200 import audio
+    rs = np.random.RandomState(3)
+    for n in (256 * 37, 256 * 5 + 77, 300):
+        wav = (rs.standard_normal(n) * 0.2).astype(np.float32)
+        res = audio.wav2spec(wav, fmin=55, fmax=7600, sample_rate=22050)
+        want = MO.wav2mel(wav)
+        assert res["mel"].shape == want.shape == (1 + n // 256, 80) and len(res["wav"]) == want.shape[0] * 256
+        assert np.abs(res["mel"] - want).max() < 1e-4
+    t = np.arange(22050) / 22050
+    tone = (0.4 * np.sin(2 * np.pi * 440.0 * t)).astype(np.float32)
+    got, want = audio.wav2spec(tone, fmin=55, fmax=7600)["mel"].astype(np.float64), MO.wav2mel(tone).astype(np.float64)
+    assert (np.abs(10 ** got - 10 ** want) <= 1e-5 * (10 ** want).max(axis=1, keepdims=True) + 1e-7).all()
+    assert audio.wav2spec(np.zeros(2560, dtype=np.float32))["mel"].max() == -6.0

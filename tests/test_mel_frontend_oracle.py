@@ -1,0 +1,44 @@
+"""oracle/mel_frontend_oracle.py restates librosa's stft + Slaney mel filterbank (utils/audio/__init__.py:34-81 calls them).
+PARITY UNPINNED against the reference itself (librosa is absent here); these tests are the secondary pins named in the oracle's
+header: torch.stft as an independent implementation of the transform, and the filterbank's defining invariants."""
+import numpy as np
+import torch
+
+from oracle import mel_frontend_oracle as MO
+
+
+def test_stft_magnitude_agrees_with_torch_stft():
+    rs = np.random.RandomState(0)
+    for n in (256 * 20, 256 * 7 + 100, 5000):
+        wav = (rs.standard_normal(n) * 0.1).astype(np.float32)
+        ours = MO.stft_mag(wav)
+        ref = torch.stft(torch.from_numpy(wav), 1024, 256, 1024, torch.hann_window(1024, periodic=True), center=True, pad_mode="constant",
+                         return_complex=True).abs().T.numpy()
+        assert ours.shape == ref.shape == (1 + n // 256, 513)
+        assert np.abs(ours - ref).max() < 2e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_slaney_filterbank_invariants():
+    w = MO.mel_basis()
+    assert w.shape == (80, 513) and w.dtype == np.float32 and (w >= 0).all()
+    freqs = np.linspace(0, 11025, 513)
+    assert w[:, freqs < 55 - 1e-6].sum() == 0 and w[:, freqs > 7600 + 1e-6].sum() == 0          # nothing outside [fmin, fmax]
+    edges = MO.mel_to_hz(np.linspace(MO.hz_to_mel(55.0), MO.hz_to_mel(7600.0), 82))
+    assert abs(edges[0] - 55) < 1e-9 and abs(edges[-1] - 7600) < 1e-6 and (np.diff(edges) > 0).all()
+    assert abs(MO.hz_to_mel(1000.0) - 15.0) < 1e-12 and abs(MO.mel_to_hz(MO.hz_to_mel(4321.0)) - 4321.0) < 1e-9   # Slaney scale: 1 kHz = mel 15
+    peak = freqs[w.argmax(1)]
+    assert (np.abs(peak - edges[1:-1]) <= (11025 / 512)).all()                                  # each triangle peaks at its centre edge
+    # Slaney normalisation: every triangle has (continuous) unit area -> its Riemann sum over the bin grid is ~1 for the wide bands
+    area = w.sum(1) * (11025 / 512)
+    assert np.abs(area[40:] - 1).max() < 0.05
+
+
+def test_wav2mel_shapes_floor_and_a_pure_tone():
+    sr = 22050
+    t = np.arange(sr) / sr
+    tone = (0.5 * np.sin(2 * np.pi * 1000.0 * t)).astype(np.float32)
+    mel = MO.wav2mel(tone)
+    assert mel.shape == (1 + len(tone) // 256, 80) and mel.dtype == np.float32
+    centres = MO.mel_to_hz(np.linspace(MO.hz_to_mel(55.0), MO.hz_to_mel(7600.0), 82))[1:-1]
+    assert abs(centres[mel[40].argmax()] - 1000.0) < 60                                         # energy lands in the 1 kHz band
+    assert MO.wav2mel(np.zeros(2560, dtype=np.float32)).max() == -6.0                           # log10(eps) floor (mel_vmin: -6)
