@@ -42,3 +42,31 @@ def test_wav2mel_shapes_floor_and_a_pure_tone():
     centres = MO.mel_to_hz(np.linspace(MO.hz_to_mel(55.0), MO.hz_to_mel(7600.0), 82))[1:-1]
     assert abs(centres[mel[40].argmax()] - 1000.0) < 60                                         # energy lands in the 1 kHz band
     assert MO.wav2mel(np.zeros(2560, dtype=np.float32)).max() == -6.0                           # log10(eps) floor (mel_vmin: -6)
+
+
+def test_wav2spec_wrapper_padding_and_frame_count(monkeypatch):
+    """speech_editing_toolkit_b200.audio.wav2spec (mirror of librosa_wav2spec for arrays) with the device transform replaced by the
+    oracle: frame count 1 + n // hop for any n, the returned wav padded / trimmed as utils/audio/__init__.py:73-75 does."""
+    from speech_editing_toolkit_b200 import audio
+
+    class Fake:
+        hop = 256
+
+        def forward(self, wav):                      # the engine pads to a multiple of hop and trims to 1 + n // hop frames
+            return torch.from_numpy(np.stack([MO.wav2mel(w.numpy(), fmin=55.0, fmax=7600.0) for w in wav]))
+
+    key = (22050, 1024, 256, 1024, 80, 55.0, 7600.0, 1e-6)
+    monkeypatch.setitem(audio._CACHE, key, Fake())
+    rs = np.random.RandomState(2)
+    for n in (256 * 9, 256 * 9 + 1, 256 * 9 + 255, 100):
+        wav = (rs.standard_normal(n) * 0.1).astype(np.float32)
+        res = audio.wav2spec(wav, fmin=55, fmax=7600, sample_rate=22050, device="cpu")
+        T = 1 + n // 256
+        assert res["mel"].shape == (T, 80)
+        # reference: wav = pad(wav, (0, (n // hop + 1) * hop - n))[:T * hop]
+        assert len(res["wav"]) == T * 256 and np.array_equal(res["wav"][:n], wav) and np.abs(res["wav"][n:]).max(initial=0.0) == 0.0
+    import pytest
+    with pytest.raises(NotImplementedError):
+        audio.wav2spec("file.wav")
+    with pytest.raises(NotImplementedError):
+        audio.wav2spec(np.zeros(512, dtype=np.float32), loud_norm=True)
