@@ -190,3 +190,23 @@ def test_campnet_state_dict_matches_live_reference():
     ours = CampNetB200(80, 100, dict(hp))
     assert {k: tuple(v.shape) for k, v in ours.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
     ours.load_state_dict(ref.state_dict(), strict=True)
+
+
+def test_campnet_task_run_model_composites_like_the_reference():
+    """tasks/speech_editing/campnet.py:86: output['mel_out'] = mel_out_fine * mask + mels * (1 - mask), with a stand-in model."""
+    from speech_editing_toolkit_b200 import plugin
+    task = plugin.CampNetTaskB200(ph_dict_size=20)
+    B, T = 2, 6
+    fine = torch.full((B, T, 80), 2.0)
+    seen = {}
+
+    def fake(txt, **kw):
+        seen.update(kw)
+        return {"mel_out_coarse": fine * 0, "mel_out_fine": fine, "attn": torch.zeros(B, T, 3)}
+
+    task.model = fake
+    mels = torch.randn(B, T, 80)
+    mask = torch.zeros(B, T); mask[:, 2:4] = 1
+    _, out = task.run_model({"txt_tokens": torch.ones(B, 3, dtype=torch.long), "mels": mels, "time_mel_masks": mask})
+    assert seen["time_mel_masks"].shape == (B, T, 1) and seen["infer"] is True and seen["stutter_mel_masks"] is None
+    assert torch.equal(out["mel_out"][:, 2:4], fine[:, 2:4]) and torch.equal(out["mel_out"][:, :2], mels[:, :2])
