@@ -3,7 +3,6 @@ tasks/tts/vocoder_infer/hifigan.py:11-31, inference/tts/base_tts_infer.py:36-47)
 from __future__ import annotations
 
 import glob
-import os
 import re
 
 import numpy as np
@@ -31,6 +30,16 @@ class BaseVocoder:
     def spec2wav(self, mel):
         """mel [T, 80] -> wav [T * hop]"""
         raise NotImplementedError
+
+    @staticmethod
+    def wav2spec(wav):
+        """tasks/tts/vocoder_infer/base_vocoder.py:30-47 for an array of samples (reading a file needs librosa): -> (wav, mel [T, 80]),
+        the transform on the GPU (audio.wav2spec -> fse_mel_frontend_forward), parameters from the same hparams keys."""
+        from .audio import wav2spec as _wav2spec
+        d = _wav2spec(wav, fft_size=hparams["fft_size"], hop_size=hparams["hop_size"], win_length=hparams["win_size"],
+                      num_mels=hparams["audio_num_mel_bins"], fmin=hparams["fmin"], fmax=hparams["fmax"],
+                      sample_rate=hparams["audio_sample_rate"], loud_norm=hparams["loud_norm"])
+        return d["wav"], d["mel"]
 
 
 def _generator_config(cfg: dict) -> dict:
