@@ -40,8 +40,9 @@ def parse():
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--eager-gpu-baseline", action="store_true",
-                    help="also time the eager-PyTorch port of the reference path on this GPU (cuDNN/cuBLAS; opt-in, rank 0, N=1)")
+    ap.add_argument("--eager-gpu-baseline", action="store_true", help="(default at N=1; kept for compatibility)")
+    ap.add_argument("--no-eager-gpu-baseline", action="store_true",
+                    help="skip timing the reference's own modules eagerly on this GPU (cuDNN/cuBLAS; rank 0, N=1)")
     return ap.parse_args()
 
 
@@ -98,52 +99,90 @@ def peaks():
     return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
 
 
-# ------------------------------------------------------------------ CPU arm (torch port of the reference path)
-def cpu_sample(timesteps, full_frames, threads=None):
-    """Bounded CPU sample of the same workload: B=2 x T=1024 for 2 diffusion iterations + vocoder on
-    B=1 x T=128, extrapolated to frames/s of the full (S-step + vocoder) pipeline."""
+# ------------------------------------------------------------------ reference arm (the reference's own modules)
+_REF_MODELS = {}
+
+
+def _ref_models(timesteps, device):
+    from oracle import ref_runner as R
+    key = (timesteps, str(device))
+    if key not in _REF_MODELS:
+        _REF_MODELS[key] = R.build_models(timesteps, device)
+    return _REF_MODELS[key]
+
+
+def _pick_threads(timesteps):
+    """"All the host threads it can use": the box may expose more logical CPUs than the container's quota, and oversubscribed
+    OpenMP teams collapse, so probe a few team sizes on one p_sample iteration and keep the fastest."""
     import torch
+    from oracle import ref_runner as R
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    model, _ = _ref_models(timesteps, "cpu")
+    tb = R.synthetic_inputs(2, 1024, "cpu")
+    best = None
+    with torch.no_grad():
+        cond = R.run_condition(model, tb)
+        x = torch.randn(2, 1, 80, 1024)
+        t = torch.full((2,), timesteps - 1, dtype=torch.long)
+        for n in sorted({avail, max(avail // 2, 1), 32, 16, 8}):
+            if n > avail:
+                continue
+            torch.set_num_threads(n)
+            model.p_sample(x, t, cond)
+            t0 = time.perf_counter()
+            model.p_sample(x, t, cond)
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, n)
+    return best[1]
+
+
+def cpu_sample(timesteps, threads=None, B=4, T=1024, iters=3, Bv=1, Tv=256):
+    """Bounded CPU sample of the same workload on the reference's OWN modules (oracle/ref_runner.py): condition encoder
+    (fs + mel_encoder) and `iters` p_sample iterations at B x T, HifiGanGenerator at Bv x Tv, extrapolated to
+    cond + S iterations + vocoder per frame.  Falls back to the validated torch port only when neither
+    /root/reference nor oracle/_ref exists (kind "port")."""
+    import torch
+    from oracle import ref_runner as R
+    if R.available():
+        if threads is None:
+            threads = _pick_threads(timesteps)
+        r = R.time_reference(B, T, timesteps, iters=iters, Bv=Bv, Tv=Tv, device="cpu", threads=threads, models=_ref_models(timesteps, "cpu"))
+        return {"value": r["frames_per_s"], "unit": "mel-frames/s", "cores": int(threads), "kind": "reference", "sample": r["sample"],
+                "per_frame_s": r["per_frame"]}
     from oracle import fluentspeech_oracle as O
     from oracle import torch_port as P
     from speech_editing_toolkit_b200 import schedule, synth
     p = P.to_torch(synth.denoiser_state_dict(1234))
     hp = P.to_torch(synth.hifigan_state_dict(1234))
     sched = {k: torch.from_numpy(v) for k, v in schedule.diffusion_buffers(timesteps).items()}
-    B, T, it = 2, 1024, 2
     cond = torch.from_numpy(synth.synthetic_cond(1, B, T)).transpose(1, 2).contiguous()
-    if threads is None:
-        # "all the host threads it can use": the box may expose more logical CPUs than the container's quota, and
-        # oversubscribed OpenMP teams collapse, so probe a few team sizes on one iteration and keep the fastest.
-        avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        best = None
-        for n in sorted({avail, max(avail // 2, 1), 32, 16, 8}):
-            if n > avail:
-                continue
-            torch.set_num_threads(n)
-            P.sample_loop(p, sched, cond, timesteps, steps=1)
-            t0 = time.perf_counter()
-            P.sample_loop(p, sched, cond, timesteps, steps=1)
-            dt = time.perf_counter() - t0
-            if best is None or dt < best[0]:
-                best = (dt, n)
-        threads = best[1]
-    cores = threads
-    torch.set_num_threads(cores)
+    threads = threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    torch.set_num_threads(threads)
     P.sample_loop(p, sched, cond, timesteps, steps=1)                  # warm-up
     t0 = time.perf_counter()
-    P.sample_loop(p, sched, cond, timesteps, steps=it)
-    t_fs = (time.perf_counter() - t0) / (B * T * it)                   # seconds per frame-iteration
-    Bv, Tv = 1, 128
+    P.sample_loop(p, sched, cond, timesteps, steps=iters)
+    t_fs = (time.perf_counter() - t0) / (B * T * iters)                # seconds per frame-iteration
     mel = torch.randn(Bv, 80, Tv) - 3
     P.hifigan_forward(hp, O.HIFIGAN_V1, mel[:, :, :32])
     t0 = time.perf_counter()
     P.hifigan_forward(hp, O.HIFIGAN_V1, mel)
     t_voc = (time.perf_counter() - t0) / (Bv * Tv)
     sec_per_frame = t_fs * timesteps + t_voc
-    return {"value": 1.0 / sec_per_frame, "unit": "mel-frames/s", "cores": cores, "kind": "port",
-            "sample": f"torch CPU port (oracle/torch_port.py): denoiser B=2xT=1024 for 2 of {timesteps} iterations "
-                      f"({t_fs * 1e6:.2f} us/frame-iteration) + HiFi-GAN B=1xT=128 ({t_voc * 1e6:.1f} us/frame), extrapolated",
-            "sec_per_frame_denoiser_iter": t_fs, "sec_per_frame_vocoder": t_voc}
+    return {"value": 1.0 / sec_per_frame, "unit": "mel-frames/s", "cores": threads, "kind": "port",
+            "sample": f"torch CPU port (oracle/torch_port.py; no reference tree on this box): denoiser B={B}xT={T} for {iters} of {timesteps} "
+                      f"iterations ({t_fs * 1e6:.2f} us/frame-iteration) + HiFi-GAN B={Bv}xT={Tv} ({t_voc * 1e6:.1f} us/frame), extrapolated",
+            "per_frame_s": {"cond": 0.0, "iter": t_fs, "vocoder": t_voc}}
+
+
+def cpu_baseline_record(timesteps):
+    """cpu_baseline of the B200 line: all-cores row (the value) + the as-shipped OMP_NUM_THREADS=1 row (tasks/run.py:3)."""
+    allc = cpu_sample(timesteps)
+    one = cpu_sample(timesteps, threads=1, B=1, T=1024, iters=2, Bv=1, Tv=128)
+    rec = {k: allc[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    rec["single_thread_as_shipped"] = {"value": one["value"], "unit": "mel-frames/s", "cores": 1, "sample": one["sample"],
+                                       "note": "tasks/run.py:3 sets OMP_NUM_THREADS=1 for the reference CLI"}
+    return rec
 
 
 def run_reference(args):
@@ -151,58 +190,49 @@ def run_reference(args):
     if rank != 0:
         return
     vals = []
-    for _ in range(args.warmup and 1):
-        cpu_sample(args.timesteps, args.batch * args.frames)
+    threads = None
+    for _ in range(min(args.warmup, 1)):
+        threads = cpu_sample(args.timesteps)["cores"]
     t0 = time.perf_counter()
     for _ in range(max(args.steps, 1)):
-        vals.append(cpu_sample(args.timesteps, args.batch * args.frames))
+        vals.append(cpu_sample(args.timesteps, threads=threads))
+        threads = vals[-1]["cores"]
     wall = time.perf_counter() - t0
     best = max(vals, key=lambda v: v["value"])
-    v = float(np.mean([x["value"] for x in vals]))
+    xs = [x["value"] for x in vals]
+    v = float(np.mean(xs))
     frames = args.batch * args.frames
     line = {"impl": "reference", "metric": "mel-frames/sec (100-step sampling + HiFi-GAN)", "value": v, "unit": "mel-frames/s",
             "rtf": (1.0 / v) / (HOP / SR), "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": frames / v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "timesteps": args.timesteps,
-                                                             "note": "CPU arm: each step is a bounded sample, extrapolated; ms_per_step is the extrapolated full-batch time"},
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": args.batch, "frames": args.frames, "timesteps": args.timesteps,
+                       "vocoder": "HiFi-GAN V1 (assumed config, SURVEY fact 4)",
+                       "note": "CPU arm: the reference's own modules on the host cores; each step is a bounded sample (B=4 x T=1024, 3 of S "
+                               "iterations + condition encoder + vocoder B=1 x T=256), extrapolated; ms_per_step is the extrapolated full-batch time"},
             "cpu_baseline": {k: best[k] for k in ("cores", "kind", "sample")} | {"value": v, "unit": "mel-frames/s"},
+            "spread": {"min": float(min(xs)), "max": float(max(xs)), "rel": float((max(xs) - min(xs)) / v)},
             "e2e": {"value": v, "unit": "mel-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": wall}
     print(json.dumps(line))
 
 
 def eager_gpu_sample(timesteps, B, T, dev):
-    """The reference's own way of running this path on a GPU — eager PyTorch, one cuDNN / ATen launch per op, fp32 with TF32
-    convolutions (torch default) — through the validated functional port (oracle/torch_port.py; the reference tree cannot travel
-    to the GPU box).  Times 3 diffusion iterations at the full batch and the vocoder on a bounded batch, extrapolates to S
-    iterations + vocoder: the "reference single-GPU PyTorch" figure north_star compares against.  Reported, never the product path."""
+    """The reference's own way of running this path on a GPU: its unmodified modules after `.cuda()` — eager PyTorch, one
+    cuDNN / ATen launch per op, fp32 with TF32 convolutions (torch default) — timed by oracle/ref_runner.py: condition encoder
+    + 3 p_sample iterations at the full batch + HifiGanGenerator on a bounded batch, extrapolated to S iterations + vocoder.
+    This is the "reference single-GPU PyTorch" figure north_star compares against.  Reported, never the product path."""
     import torch
-    from oracle import fluentspeech_oracle as O
-    from oracle import torch_port as P
-    from speech_editing_toolkit_b200 import schedule, synth
-    p = {k: v.to(dev) for k, v in P.to_torch(synth.denoiser_state_dict(1234)).items()}
-    hp = {k: v.to(dev) for k, v in P.to_torch(synth.hifigan_state_dict(1234)).items()}
-    sched = {k: torch.from_numpy(v).to(dev) for k, v in schedule.diffusion_buffers(timesteps).items()}
-    cond = torch.from_numpy(synth.synthetic_cond(1, B, T)).to(dev).transpose(1, 2).contiguous()
-    it, Bv = 3, min(B, 4)                       # the eager vocoder holds fp32 activations of every stage: bound its batch
-    mel = P.sample_loop(p, sched, cond, timesteps, steps=2)            # warm-up (cuDNN heuristics, allocator)
-    P.hifigan_forward(hp, O.HIFIGAN_V1, mel[:Bv].transpose(1, 2).contiguous())
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    ev[0].record()
-    mel = P.sample_loop(p, sched, cond, timesteps, steps=it)
-    ev[1].record()
-    torch.cuda.synchronize()
-    ev[2].record()
-    P.hifigan_forward(hp, O.HIFIGAN_V1, mel[:Bv].transpose(1, 2).contiguous())
-    ev[3].record()
-    torch.cuda.synchronize()
-    s_iter = ev[0].elapsed_time(ev[1]) / 1e3 / (it * B * T)            # seconds per frame and diffusion iteration
-    s_voc = ev[2].elapsed_time(ev[3]) / 1e3 / (Bv * T)                 # seconds per frame
-    sec_per_frame = s_iter * timesteps + s_voc
-    return {"value": 1.0 / sec_per_frame, "unit": "mel-frames/s", "rtf": sec_per_frame / (HOP / SR), "kind": "port (eager torch on cuda, TF32 convs)",
-            "sample": f"oracle/torch_port.py on this GPU: denoiser B={B}xT={T} for {it} of {timesteps} iterations "
-                      f"({s_iter * 1e9:.2f} ns/frame-iteration) + HiFi-GAN B={Bv}xT={T} ({s_voc * 1e6:.2f} us/frame), extrapolated"}
+    from oracle import ref_runner as R
+    if not R.available():
+        return {"unavailable": "no reference tree (/root/reference or oracle/_ref) on this box"}
+    Bv = min(B, 4)                               # the eager vocoder holds fp32 activations of every stage: bound its batch
+    r = R.time_reference(B, T, timesteps, iters=3, Bv=Bv, Tv=T, device=dev)
+    _REF_MODELS.clear()
+    torch.cuda.empty_cache()
+    return {"value": r["frames_per_s"], "unit": "mel-frames/s", "rtf": r["sec_per_frame"] / (HOP / SR),
+            "kind": "reference (unmodified modules, eager torch on cuda, TF32 convs as torch defaults)", "sample": r["sample"],
+            "allow_tf32": {"cudnn": bool(torch.backends.cudnn.allow_tf32), "matmul": bool(torch.backends.cuda.matmul.allow_tf32)}}
 
 
 # ------------------------------------------------------------------ B200 arm
@@ -404,15 +434,14 @@ def run_b200(args):
     if cond_ms is not None:      # once per batch, in front of the loop: part of e2e, not of the resident `value` step (sampling + vocoder)
         breakdown["cond_encoder_plus_mel_encoder_ms"] = cond_ms
     eager = None
-    if args.eager_gpu_baseline and world == 1:
+    if not args.no_eager_gpu_baseline and world == 1:
         try:
             eager = eager_gpu_sample(S, B, T, dev)
         except Exception as e:                       # a reported extra: never takes the bench line down
             eager = {"error": repr(e)}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        cpu = cpu_sample(S, B * T)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu = cpu_baseline_record(S)
     audio_s = frames_total * HOP / SR
     line = {
         "metric": "mel-frames/sec (100-step sampling + HiFi-GAN)", "value": value, "unit": "mel-frames/s",

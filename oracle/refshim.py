@@ -1,9 +1,10 @@
 """Make the UNMODIFIED reference (/root/reference) importable in the build container.
 
-TEST INFRASTRUCTURE ONLY.  Used by oracle/make_golden.py (fixture generation) and by
-the `-m "not gpu"` tests that pin the numpy oracle against the real reference when
-/root/reference is present.  /root/reference does not exist on the GPU box, so nothing
-in bench.py / smoke() / `-m gpu` tests may import this module.
+TEST / MEASUREMENT INFRASTRUCTURE ONLY.  Used by oracle/make_golden.py (fixture generation), by
+the `-m "not gpu"` tests that pin the numpy oracle against the real reference, and by bench.py's
+reference arm.  /root/reference does not exist on the GPU box: there the root is oracle/_ref, the
+verbatim git-ignored copy of the hot path's import closure made by oracle/build_ref.py (it travels
+with the snapshot like a built .so).  Never imported by the product package.
 
 The reference's math needs none of librosa / pyloudnorm / textgrid / webrtcvad /
 skimage, but `modules/speech_editing/spec_denoiser/fs.py:14-15` pulls them in
@@ -14,7 +15,19 @@ import os
 import sys
 from unittest.mock import MagicMock
 
-REF_ROOT = os.environ.get("FSE_REFERENCE_ROOT", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")      # verbatim copy made by oracle/build_ref.py
+
+
+def _pick_root() -> str:
+    env = os.environ.get("FSE_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/modules/speech_editing"):
+        return "/root/reference"
+    return _VENDORED        # the GPU box: only the git-ignored copy exists
+
+
+REF_ROOT = _pick_root()
 
 _STUBS = ["librosa", "librosa.filters", "librosa.core", "librosa.feature", "pyloudnorm", "textgrid",
           "webrtcvad", "skimage", "skimage.transform", "matplotlib", "matplotlib.pyplot"]
