@@ -35,7 +35,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
     ap.add_argument("--frames", type=int, default=1024)
     ap.add_argument("--timesteps", type=int, default=100)
-    ap.add_argument("--mode", default="tc_bf16", choices=["tc_bf16", "simt_f32", "simt_bf16"])
+    ap.add_argument("--mode", default="tc_tf32", choices=["tc_tf32", "tc_bf16", "simt_f32", "simt_bf16"],
+                    help="arithmetic of the contractions. Default tc_tf32 = tcgen05 kind::tf32, the reference's own GPU arithmetic "
+                         "(cuDNN TF32 convolutions); tc_bf16 = bf16 operands (faster, narrower than the reference: reported as a sub-record)")
+    ap.add_argument("--no-alt-mode", action="store_true", help="skip the short second measurement in the other tensor-core mode")
     ap.add_argument("--no-vocoder", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -97,6 +100,49 @@ def peaks():
         return {"bf16_sustained": d.get("bf16_tflops_sustained", 1400.0), "bf16_burst": d.get("bf16_tflops", 1590.0),
                 "hbm": d.get("hbm_gbs", 6650.0), "src": "measured (MEASURED_PEAKS.json)"}
     return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+DTYPE = {"tc_tf32": "tf32", "tc_bf16": "bf16", "simt_bf16": "bf16", "simt_f32": "f32"}
+
+
+def tensor_peak(mode, pk):
+    """Sustained tensor peak the stream kernel is measured against.  MEASURED_PEAKS.json holds the dense bf16 figure only; the
+    tf32 kind runs at half the bf16 rate on this part (B200_PROFILING.md: 1.1 vs 2.25 PFLOP/s dense), so its peak is taken as
+    half of the MEASURED sustained bf16 throughput."""
+    if mode == "tc_tf32":
+        return pk["bf16_sustained"] / 2.0, pk["src"] + ", sustained bf16 / 2 (tf32 kind = half the bf16 rate)"
+    return pk["bf16_sustained"], pk["src"] + ", sustained bf16"
+
+
+def stream_traffic(mode, B, T):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the streamed residual-layer kernel at the bench shape, read
+    from the committed ncu artefact profiles/stream_kernel_traffic.json (written by tools/ncu_traffic.py from an `ncu --set full`
+    capture of this kernel); None when no capture of this mode / shape is committed."""
+    p = os.path.join(ROOT, "profiles", "stream_kernel_traffic.json")
+    try:
+        d = json.load(open(p))
+        e = d.get(f"{mode}:{B}x{T}")
+        return (int(e["dram_bytes"]), e.get("source")) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+def roofline_record(mode, prof_d, B, T, pk):
+    g_ms, g_n = prof_d["gate_gemm"]
+    fused = prof_d["res_gemm"][1] == 0
+    if fused:   # one launch = all 20 residual layers: per layer gate GEMM 0.983 MFLOP/frame + residual GEMM 0.131 MFLOP/frame
+        flops = 20 * 2.0 * B * T * (512 * 960 + 256 * 256)
+        kname = (f"denoiser_stream_kernel<pair{', tf32' if mode == 'tc_tf32' else ''}> (20 x [k=3 conv + cond 1x1 + gate -> residual 1x1] "
+                 "as one stream of (layer, unit) items; persistent, cta_group::2)")
+    else:
+        flops = 2.0 * B * T * 512 * 960                  # algorithmic: 0.983 MFLOP/frame (k=3 conv 512x768 + cond 512x192)
+        kname = "conv_gemm_tc_kernel<EpiGate> (dilated k=3 conv + conditioner 1x1 + gate)"
+    ach = flops / (g_ms / g_n * 1e-3) / 1e12 if g_n else 0.0
+    peak, src = tensor_peak(mode, pk)
+    traffic, tsrc = stream_traffic(mode, B, T) if fused and os.environ.get("FSE_FUSED_STREAM", "1") != "0" else (None, None)
+    return {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "peak_source": src, "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+            "traffic_source": tsrc, "avg_launch_us": g_ms / g_n * 1e3 if g_n else None, "launches_timed": g_n, "flops_per_launch": flops}
 
 
 # ------------------------------------------------------------------ reference arm (the reference's own modules)
@@ -399,33 +445,51 @@ def run_b200(args):
         step_cond_encoder(0)
         cond_ms = timed(step_cond_encoder, args.steps) / args.steps
 
+    def alt_record(mode, steps=3):
+        """The same resident step in the other tensor-core mode (3 steps after 3 warm-ups, rank 0's GPU only, no collective):
+        reported next to the headline so both precisions are on the driver's record."""
+        d2 = Denoiser(mode=mode)
+        d2.load_state_dict(synth.denoiser_state_dict(1234))
+        d2.set_schedule(buf["posterior_mean_coef1"], buf["posterior_mean_coef2"], buf["posterior_log_variance_clipped"])
+        v2 = None
+        if voc:
+            v2 = Vocoder(mode=mode)
+            v2.load_state_dict(synth.hifigan_state_dict(1234))
+
+        def one(i):
+            mel = d2.sample(cond_d, None, seed=i, ref_mel=ref_d, mask=mask_d)
+            if v2:
+                v2.forward(mel)
+        for i in range(3):
+            one(i)
+        torch.cuda.synchronize()
+        d2.profile(True)
+        if v2:
+            v2.profile(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            one(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        pd = d2.profile_read()
+        pv = v2.profile_read() if v2 else None
+        rec = {"mode": mode, "dtype": DTYPE[mode], "value": B * T / (ms / 1e3), "unit": "mel-frames/s (one GPU)", "ms_per_step": ms, "steps": steps,
+               "roofline": roofline_record(mode, pd, B, T, peaks()),
+               "breakdown": {"denoiser_ms_per_step": {k: v[0] / steps for k, v in pd.items()}}}
+        if pv:
+            rec["breakdown"]["vocoder_ms_per_step"] = {k: v[0] / steps for k, v in pv.items()}
+        del d2, v2
+        torch.cuda.empty_cache()
+        return rec
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pk = peaks()
-    roofline = None
-    if prof_d:
-        g_ms, g_n = prof_d["gate_gemm"]
-        fused = prof_d["res_gemm"][1] == 0
-        if fused:   # one launch = all 20 residual layers: per layer gate GEMM 0.983 MFLOP/frame + residual GEMM 0.131 MFLOP/frame
-            flops = 20 * 2.0 * B * T * (512 * 960 + 256 * 256)
-            kname = ("denoiser_stream_kernel<pair> (20 x [k=3 conv + cond 1x1 + gate -> residual 1x1] as one stream of (layer, unit) "
-                     "items; persistent, cta_group::2)")
-        else:
-            flops = 2.0 * B * T * 512 * 960                  # algorithmic: 0.983 MFLOP/frame (k=3 conv 512x768 + cond 512x192)
-            kname = "conv_gemm_tc_kernel<EpiGate> (dilated k=3 conv + conditioner 1x1 + gate)"
-        ach = flops / (g_ms / g_n * 1e-3) / 1e12 if g_n else 0.0
-        roofline = {"kernel": kname, "bound": "tensor",
-                    "achieved": ach, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
-                    "peak_source": pk["src"] + ", sustained bf16",
-                    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at this shape, from the committed
-                    # `ncu --set full` capture (profiles/r01_ncu_stream_kernel.md); null for the other kernels / shapes
-                    "traffic": 1149497600 if (fused and (B, T) == (32, 1024) and os.environ.get("FSE_FUSED_STREAM", "1") != "0"
-                                              and os.environ.get("FSE_FUSED", "2") not in ("0", "1")) else None,
-                    "traffic_unit": "bytes/launch (ncu)",
-                    "avg_launch_us": g_ms / g_n * 1e3 if g_n else None, "launches_timed": g_n,
-                    "flops_per_launch": flops}
+    roofline = roofline_record(args.mode, prof_d, B, T, pk) if prof_d else None
     breakdown = {}
     if prof_d:
         breakdown["denoiser_ms_per_step"] = {k: v[0] / args.steps for k, v in prof_d.items()}
@@ -439,6 +503,13 @@ def run_b200(args):
             eager = eager_gpu_sample(S, B, T, dev)
         except Exception as e:                       # a reported extra: never takes the bench line down
             eager = {"error": repr(e)}
+    alt = None
+    if not args.no_alt_mode and args.mode in ("tc_tf32", "tc_bf16"):
+        alt_mode = "tc_bf16" if args.mode == "tc_tf32" else "tc_tf32"
+        try:
+            alt = alt_record(alt_mode)
+        except Exception as e:                       # a reported extra: never takes the bench line down
+            alt = {"mode": alt_mode, "error": repr(e)}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cpu = cpu_baseline_record(S)
@@ -447,7 +518,7 @@ def run_b200(args):
         "metric": "mel-frames/sec (100-step sampling + HiFi-GAN)", "value": value, "unit": "mel-frames/s",
         "rtf": (ms_step / 1e3) / audio_s, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "ms_per_step_without_kernel_events": ms_noprof, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16" if args.mode != "simt_f32" else "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": DTYPE[args.mode], "data": "synthetic",
         "config": {"workload": WORKLOAD if (B, T, S) == (32, 1024, 100) and voc else f"custom B={B} T={T} S={S} vocoder={bool(voc)}",
                    "batch_per_gpu": B, "frames": T, "timesteps": S, "vocoder": "HiFi-GAN V1 (assumed config, SURVEY fact 4)" if voc else None,
                    "mode": args.mode, "noise": "in-kernel Philox4x32-10", "weights": "seeded random (synth.py), reference state_dict layout",
@@ -456,6 +527,8 @@ def run_b200(args):
         "gpu_launches": int(launches * args.steps), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
         "breakdown": breakdown,
     }
+    if alt is not None:
+        line["alt_mode"] = alt
     if eager is not None:
         line["eager_gpu_baseline"] = eager
     print(json.dumps(line))

@@ -34,6 +34,8 @@ extern "C" {
 #define FSE_MODE_TC_BF16 0    /* tcgen05 tensor cores, bf16 operands, fp32 accumulate (default, the product) */
 #define FSE_MODE_SIMT_F32 1   /* CUDA cores, fp32 operands: the reference's exact fp32 arithmetic contract */
 #define FSE_MODE_SIMT_BF16 2  /* CUDA cores over the bf16 operands: on-device cross-check of the TC path */
+#define FSE_MODE_TC_TF32 3    /* tcgen05 tensor cores, kind::tf32: fp32 operands in memory, tf32 multiplies, fp32 accumulate -
+                                 the reference's own GPU arithmetic (cuDNN TF32 convolutions, torch default); denoiser + vocoder */
 
 typedef struct fse_denoiser fse_denoiser;
 typedef struct fse_vocoder fse_vocoder;

@@ -307,6 +307,71 @@ def edit_region_fixture():
     np.savez_compressed(os.path.join(OUT, "edit_region.npz"), **out)
 
 
+def bench_config_fixture():
+    """Parity pins AT THE BENCHMARKED SHAPES (BASELINE configs[1]/[2]/[3]: T = 1024 frames, S = 100 iterations), from the
+    unmodified reference: `python oracle/make_golden.py bench_config` writes
+      sample_s100_t1024.npz   the reference's own p_sample loop (spec_denoiser.py:177-185), B=1 x T=1024 x S=100, the 101 normal
+                              draws injected from synth.synthetic_noise(seed) (regenerated by the test; not stored)
+      hifigan_t1024.npz       HifiGanGenerator.forward (hifigan.py:126-142), B=1 x T=1024 (262 144 samples)
+      campnet_t1024.npz       CampNet.forward (campnet.py:40-69), one item of T=1024 frames / 128 tokens
+    Items are independent in every kernel (no cross-item op), so B=1 at the full T and S pins the B=32 runs
+    together with the item-independence tests."""
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(SEED)
+    torch.set_num_threads(8)
+    S, B, T = 100, 1, 1024
+    hp = refshim.install("egs/spec_denoiser.yaml", overrides=f"timesteps={S}")
+    from modules.speech_editing.spec_denoiser.diffnet import DiffNet
+    from modules.speech_editing.spec_denoiser import spec_denoiser as sdmod
+    from modules.vocoder.hifigan.hifigan import HifiGanGenerator
+    net = DiffNet(hp["audio_num_mel_bins"]).eval()
+    net.load_state_dict(to_torch(synth.denoiser_state_dict(SEED)), strict=True)
+    model = sdmod.GaussianDiffusion(phone_encoder=list(range(80)), out_dims=80, denoise_fn=net, timesteps=S, time_scale=hp["timescale"],
+                                    loss_type=hp["diff_loss_type"], spec_min=hp["spec_min"], spec_max=hp["spec_max"]).eval()
+    cond = synth.synthetic_cond(SEED + 11, B, T)
+    noise = synth.synthetic_noise(SEED + 11, S, B, T)
+    draws = iter(torch.from_numpy(noise[1:]))
+    orig = sdmod.noise_like
+    sdmod.noise_like = lambda shape, device, repeat=False: next(draws)[:, None]
+    try:
+        with torch.no_grad():
+            xt = torch.from_numpy(noise[0])[:, None]
+            cond_t = torch.from_numpy(cond).transpose(1, 2)
+            mid = {}
+            for i in reversed(range(S)):                                            # spec_denoiser.py:181-182
+                xt = model.p_sample(xt, torch.full((B,), i, dtype=torch.long), cond_t)
+                if i in (75, 50, 25):
+                    mid[i] = xt[:, 0, :, :64].numpy().copy()                         # 64 frames of the running x_t (trace spot checks)
+            mel = xt[:, 0].transpose(1, 2).numpy().copy()
+    finally:
+        sdmod.noise_like = orig
+    np.savez_compressed(os.path.join(OUT, "sample_s100_t1024.npz"), seed=SEED + 11, B=B, T=T, S=S, mel_out=mel,
+                        x_t75=mid[75], x_t50=mid[50], x_t25=mid[25])
+    print("sample_s100_t1024", mel.shape, float(np.abs(mel).mean()))
+
+    from oracle.fluentspeech_oracle import HIFIGAN_V1
+    gen = HifiGanGenerator(dict(HIFIGAN_V1)).eval()
+    gen.load_state_dict(to_torch(synth.hifigan_state_dict(SEED)), strict=True)
+    mel_in = np.clip(np.random.RandomState(SEED + 12).standard_normal((1, T, 80)) * 1.5 - 3.0, -6, 1.5).astype(np.float32)
+    with torch.no_grad():
+        wav = gen(torch.from_numpy(mel_in).transpose(1, 2)).numpy()
+    np.savez_compressed(os.path.join(OUT, "hifigan_t1024.npz"), seed=SEED + 12, B=1, T=T, wav=wav[:, 0])      # mel regenerated from the seed
+    print("hifigan_t1024", wav.shape, float(np.abs(wav).mean()))
+
+    hp = refshim.install("egs/campnet.yaml")
+    from modules.speech_editing.campnet.campnet import CampNet
+    vocab = 80
+    camp = CampNet(vocab, 100, hp).eval()
+    camp.load_state_dict(to_torch(synth.campnet_state_dict(SEED, vocab)), strict=False)
+    batch = synth.synthetic_campnet_batch(SEED + 13, 1, T, vocab=vocab)
+    with torch.no_grad():
+        ret = camp(torch.from_numpy(batch["txt_tokens"]), mels=torch.from_numpy(batch["mels"]),
+                   time_mel_masks=torch.from_numpy(batch["time_mel_masks"]), infer=True)
+    np.savez_compressed(os.path.join(OUT, "campnet_t1024.npz"), seed=SEED + 13, B=1, T=T, vocab=vocab,
+                        mel_out_coarse=ret["mel_out_coarse"].numpy().astype(np.float32), mel_out_fine=ret["mel_out_fine"].numpy().astype(np.float32))
+    print("campnet_t1024", ret["mel_out_fine"].shape, float(np.abs(ret["mel_out_fine"].numpy()).mean()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "mel_encoder":
         mel_encoder_fixture()
@@ -316,9 +381,12 @@ if __name__ == "__main__":
         campnet_fixture()
     elif len(sys.argv) > 1 and sys.argv[1] == "edit_region":
         edit_region_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "bench_config":
+        bench_config_fixture()
     else:
         main()
         mel_encoder_fixture()
         cond_encoder_fixture()
         campnet_fixture()
         edit_region_fixture()
+        bench_config_fixture()

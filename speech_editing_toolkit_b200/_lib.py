@@ -11,7 +11,8 @@ from .build import LIB_PATH
 FSE_MODE_TC_BF16 = 0
 FSE_MODE_SIMT_F32 = 1
 FSE_MODE_SIMT_BF16 = 2
-MODES = {"tc_bf16": FSE_MODE_TC_BF16, "simt_f32": FSE_MODE_SIMT_F32, "simt_bf16": FSE_MODE_SIMT_BF16}
+FSE_MODE_TC_TF32 = 3
+MODES = {"tc_bf16": FSE_MODE_TC_BF16, "simt_f32": FSE_MODE_SIMT_F32, "simt_bf16": FSE_MODE_SIMT_BF16, "tc_tf32": FSE_MODE_TC_TF32}
 
 
 class FseError(RuntimeError):

@@ -575,7 +575,7 @@ extern "C" {
 
 int fse_campnet_create(const fse_campnet_config* cfg, fse_campnet** out) {
   if (!cfg || !out) return fail(FSE_EINVAL, "null argument");
-  if (cfg->mode < 0 || cfg->mode > 2) return fail(FSE_EINVAL, "unknown mode %d", cfg->mode);
+  if (cfg->mode < 0 || cfg->mode > 3) return fail(FSE_EINVAL, "unknown mode %d", cfg->mode);
   if (cfg->heads < 1 || cfg->hidden != cfg->heads * kAttD)
     return fail(FSE_EINVAL, "hidden must equal heads * %d (head_dim of the attention kernel); got hidden %d, heads %d", kAttD, cfg->hidden, cfg->heads);
   if (cfg->hidden % 64 != 0 || cfg->hidden > 512) return fail(FSE_EINVAL, "hidden must be a multiple of 64, <= 512");
@@ -592,7 +592,7 @@ int fse_campnet_create(const fse_campnet_config* cfg, fse_campnet** out) {
   auto* h = new fse_campnet();
   h->cfg = *cfg;
   h->ctx.mode = cfg->mode;
-  h->ctx.bf16 = cfg->mode != FSE_MODE_SIMT_F32;
+  h->ctx.bf16 = mode_is_bf16(cfg->mode);       // FSE_MODE_TC_TF32: tf32 tensor-core GEMMs over fp32 rows, fp32 CUDA-core attention
   h->ctx.hidden = cfg->hidden;
   // FSE_CAMP_ATTN = "tc2" (default in FSE_MODE_TC_BF16: tcgen05, two query tiles per CTA) | "tc" (one tile per CTA) | "simt"
   const char* sel = std::getenv("FSE_CAMP_ATTN");

@@ -366,7 +366,7 @@ extern "C" {
 
 int fse_cond_encoder_create(const fse_cond_encoder_config* cfg, fse_cond_encoder** out) {
   if (!cfg || !out) return fail(FSE_EINVAL, "null argument");
-  if (cfg->mode < 0 || cfg->mode > 2) return fail(FSE_EINVAL, "unknown mode %d", cfg->mode);
+  if (cfg->mode < 0 || cfg->mode > 3) return fail(FSE_EINVAL, "unknown mode %d", cfg->mode);
   if (cfg->hidden <= 0 || cfg->hidden % 64 != 0 || cfg->hidden > 32 * kMaxPerLane)
     return fail(FSE_EINVAL, "hidden must be a multiple of 64, <= %d", 32 * kMaxPerLane);
   if (cfg->vocab <= 0) return fail(FSE_EINVAL, "vocab must be positive");
@@ -383,7 +383,7 @@ int fse_cond_encoder_create(const fse_cond_encoder_config* cfg, fse_cond_encoder
   auto* h = new fse_cond_encoder();
   h->cfg = *cfg;
   h->ctx.mode = cfg->mode;
-  h->ctx.bf16 = cfg->mode != FSE_MODE_SIMT_F32;
+  h->ctx.bf16 = mode_is_bf16(cfg->mode);
   h->ctx.hidden = cfg->hidden;
   const double mel_min = 1127.0 * std::log(1.0 + 50.0 / 700.0), mel_max = 1127.0 * std::log(1.0 + 900.0 / 700.0);
   h->pc.mel_min = static_cast<float>(mel_min);

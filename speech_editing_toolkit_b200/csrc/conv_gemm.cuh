@@ -199,24 +199,32 @@ constexpr int kEpiWarps = 8;
 constexpr int kTcThreads = 64 + 32 * kEpiWarps;
 constexpr int kTileM = 128;       // frames per tile = TMEM lanes
 
-__host__ __device__ inline int tc_b_stage_bytes(int BN, int KB) { return ((BN * KB * 2 + 1023) / 1024) * 1024; }
-__host__ __device__ inline int tc_a_stage_bytes(int KB) { return kTileM * KB * 2; }
-__host__ inline size_t tc_smem_bytes(int BN, int KB, int stages, int a_slots, int a_slot_bytes, int scratch_bytes = 0) {
-  return 1024 + static_cast<size_t>(a_slots) * a_slot_bytes + static_cast<size_t>(stages) * tc_b_stage_bytes(BN, KB) + scratch_bytes +
+// rb = bytes of one k-block row = KB elements x sizeof(operand): 128 (128B swizzle) or 64 (64B swizzle)
+__host__ __device__ inline int tc_b_stage_bytes(int BN, int rb) { return ((BN * rb + 1023) / 1024) * 1024; }
+__host__ __device__ inline int tc_a_stage_bytes(int rb) { return kTileM * rb; }
+__host__ inline size_t tc_smem_bytes(int BN, int rb, int stages, int a_slots, int a_slot_bytes, int scratch_bytes = 0) {
+  return 1024 + static_cast<size_t>(a_slots) * a_slot_bytes + static_cast<size_t>(stages) * tc_b_stage_bytes(BN, rb) + scratch_bytes +
          8 * (2 * stages + 4 + 2 * a_slots) + 16;
 }
 
-template <int KB, int CH, class Epi>
+// TOp = __nv_bfloat16: tcgen05 kind::f16 (bf16 x bf16 -> fp32), K-blocks of 64 / 32 channels.
+// TOp = float:         tcgen05 kind::tf32 (the reference's own GPU arithmetic: cuDNN TF32 convolutions), fp32 operands in
+//                      HBM and shared memory, K-blocks of 32 / 16 channels.  Same bytes per k-block row (128 / 64), same
+//                      swizzle atoms, same descriptors; one MMA instruction covers 32 bytes of K in both kinds.
+template <typename TOp, int KB, int CH, class Epi>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapW, ConvGemmParams p, int BN, int stages, int a_slots,
                     int a_slot_bytes, int scratch_bytes, Epi epi) {
-  static_assert(KB == 64 || KB == 32, "k-block");
+  constexpr int ES = static_cast<int>(sizeof(TOp));
+  constexpr int RB = KB * ES;                 // bytes per k-block row
+  constexpr bool kTF32 = std::is_same<TOp, float>::value;
+  static_assert(RB == 128 || RB == 64, "k-block row must be 128 or 64 bytes");
   static_assert(CH == 32 || CH == 16, "epilogue chunk");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int A_BYTES = a_slot_bytes;        // non-shared mode: a_slots == stages, one A tile per W stage
-  const int B_BYTES = tc_b_stage_bytes(BN, KB);
+  const int B_BYTES = tc_b_stage_bytes(BN, RB);
   uint8_t* sA = smem;
   uint8_t* sB = smem + a_slots * A_BYTES;
   uint8_t* sScratch = sB + stages * B_BYTES;       // transposed epilogue: [kEpiWarps][32][32] fp32
@@ -291,8 +299,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           const int slot = ga % a_slots;
           ptx::mbar_wait(&a_empty[slot], ((ga / a_slots) & 1) ^ 1u);
           const bool src0 = g < p.nkb0;
-          const int box_bytes = p.Rbox * KB * 2;
-          ptx::mbar_arrive_expect_tx(&a_full[slot], static_cast<uint32_t>(src0 ? p.nload * box_bytes : kTileM * KB * 2));
+          const int box_bytes = p.Rbox * RB;
+          ptx::mbar_arrive_expect_tx(&a_full[slot], static_cast<uint32_t>(src0 ? p.nload * box_bytes : kTileM * RB));
           if (src0) {
             for (int i = 0; i < p.nload; ++i)
               ptx::tma_load_3d(sA + slot * A_BYTES + i * box_bytes, &mapA0, &a_full[slot], p.c_off0 + g * KB, t0 + p.off_min + i * p.Rbox, b);
@@ -303,7 +311,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           for (int j = 0; j < ntap; ++j, ++kbg) {
             const int s = kbg % stages;
             ptx::mbar_wait(&empty[s], ((kbg / stages) & 1) ^ 1u);
-            ptx::mbar_arrive_expect_tx(&full[s], static_cast<uint32_t>(BN * KB * 2));
+            ptx::mbar_arrive_expect_tx(&full[s], static_cast<uint32_t>(BN * RB));
             const int kb = src0 ? j * p.nkb0 + g : nkb_src0 + (g - p.nkb0);
             ptx::tma_load_2d(sB + s * B_BYTES, &mapW, &full[s], kb * KB, n0);
           }
@@ -311,8 +319,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         if (dbg && tile == blockIdx.x) dbg[2] = clock64();
       }
     } else if (lane == 0) {
-      constexpr int A1 = kTileM * KB * 2;            // one 128-frame activation tile
-      const uint32_t tx_bytes = static_cast<uint32_t>(MT * A1 + BN * KB * 2);
+      constexpr int A1 = kTileM * RB;            // one 128-frame activation tile
+      const uint32_t tx_bytes = static_cast<uint32_t>(MT * A1 + BN * RB);
       int kbg = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m = tile / n_tiles, n0 = (tile % n_tiles) * BN;
@@ -339,7 +347,10 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     __syncwarp();   // reconverge: bar.sync below must be reached by whole warps
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = ptx::make_idesc_bf16_f32(kTileM, BN);
+    const uint32_t idesc = kTF32 ? ptx::make_idesc_tf32_f32(kTileM, BN) : ptx::make_idesc_bf16_f32(kTileM, BN);
+    auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+      if constexpr (kTF32) ptx::mma_tf32_ss(d, da, db, idesc, acc); else ptx::mma_f16_ss(d, da, db, idesc, acc);
+    };
     const bool el = ptx::elect_one();      // the one lane that issues every tcgen05.mma / commit of this CTA
     int kbg = 0, it = 0, ga = 0;
     if (p.shared_a) {
@@ -366,17 +377,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
               // instructions sit under the one-lane predicate (a divergent region would cost ~7 R2UR + a waterfall per MMA).
               const int shift = src0 ? p.tap_off[j] - p.off_min : 0;
               const uint32_t b_addr = ptx::smem_u32(sB + s * B_BYTES);
-              const uint64_t db = (KB == 64) ? ptx::make_desc_k_sw128(b_addr) : ptx::make_desc_k_sw64(b_addr);
-              const uint32_t a_base = ptx::smem_u32(sA + slot * A_BYTES) + static_cast<uint32_t>(shift * KB * 2);
+              const uint64_t db = (RB == 128) ? ptx::make_desc_k_sw128(b_addr) : ptx::make_desc_k_sw64(b_addr);
+              const uint32_t a_base = ptx::smem_u32(sA + slot * A_BYTES) + static_cast<uint32_t>(shift * RB);
               for (int mt = 0; mt < MT; ++mt) {
-                const uint32_t a_addr = a_base + static_cast<uint32_t>(mt * kTileM * KB * 2);
-                const uint32_t bo = p.bo_mode ? ((a_addr >> 7) & (KB == 64 ? 7u : 3u)) : 0u;
-                const uint64_t da = ((KB == 64) ? ptx::make_desc_k_sw128(a_addr) : ptx::make_desc_k_sw64(a_addr)) |
+                const uint32_t a_addr = a_base + static_cast<uint32_t>(mt * kTileM * RB);
+                const uint32_t bo = p.bo_mode ? ((a_addr >> 7) & (RB == 128 ? 7u : 3u)) : 0u;
+                const uint64_t da = ((RB == 128) ? ptx::make_desc_k_sw128(a_addr) : ptx::make_desc_k_sw64(a_addr)) |
                                     (static_cast<uint64_t>(bo) << 49);
                 const uint32_t td = tmem_d + static_cast<uint32_t>(mt * BN);
 #pragma unroll
-                for (int k = 0; k < KB / 16; ++k)
-                  if (el) ptx::mma_f16_ss(td, da + 2 * k, db + 2 * k, idesc, accum | (k != 0 ? 1u : 0u));
+                for (int k = 0; k < RB / 32; ++k)
+                  if (el) mma(td, da + 2 * k, db + 2 * k, accum | (k != 0 ? 1u : 0u));
               }
               if (el) ptx::mma_commit(&empty[s]);
             }
@@ -407,16 +418,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
         if (dbg && lane == 0 && kbg == 0) dbg[3] = clock64();   // first k-block landed
         {
           const uint32_t b_addr = ptx::smem_u32(sB + s * B_BYTES);
-          const uint64_t db = (KB == 64) ? ptx::make_desc_k_sw128(b_addr) : ptx::make_desc_k_sw64(b_addr);
+          const uint64_t db = (RB == 128) ? ptx::make_desc_k_sw128(b_addr) : ptx::make_desc_k_sw64(b_addr);
           const uint32_t a_base = ptx::smem_u32(sA + s * A_BYTES);
           const uint32_t acc = kb != 0 ? 1u : 0u;
           for (int mt = 0; mt < MT; ++mt) {          // the same weight tile against MT activation sub-tiles
-            const uint32_t a_addr = a_base + static_cast<uint32_t>(mt * (kTileM * KB * 2));
-            const uint64_t da = (KB == 64) ? ptx::make_desc_k_sw128(a_addr) : ptx::make_desc_k_sw64(a_addr);
+            const uint32_t a_addr = a_base + static_cast<uint32_t>(mt * (kTileM * RB));
+            const uint64_t da = (RB == 128) ? ptx::make_desc_k_sw128(a_addr) : ptx::make_desc_k_sw64(a_addr);
             const uint32_t td = tmem_d + static_cast<uint32_t>(mt * BN);
 #pragma unroll
-            for (int k = 0; k < KB / 16; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the addr>>4 field
-              if (el) ptx::mma_f16_ss(td, da + 2 * k, db + 2 * k, idesc, k != 0 ? 1u : acc);
+            for (int k = 0; k < RB / 32; ++k)   // +32 bytes along K inside the swizzle atom = +2 in the addr>>4 field
+              if (el) mma(td, da + 2 * k, db + 2 * k, k != 0 ? 1u : acc);
           }
           if (el) {
             ptx::mma_commit(&empty[s]);

@@ -169,7 +169,9 @@ using namespace fse;
 // ------------------------------------------------------------------ handle
 struct fse_denoiser {
   fse_denoiser_config cfg{};
-  bool bf16 = true;
+  bool bf16 = true;          // operand element type: bf16 (FSE_MODE_TC_BF16 / SIMT_BF16) or fp32 (SIMT_F32 / TC_TF32)
+  bool tc = true;            // tensor-core back end (tcgen05 kind::f16 or kind::tf32)
+  int KB = 64;               // k-block width in channels = 128 bytes of the operand type
   bool loaded = false;
   int device = 0;
   // packed weights
@@ -195,6 +197,8 @@ struct fse_denoiser {
   bool fused_pair = false;   // default when fused: CTA pairs (tcgen05 cta_group::2), each CTA loads half of every weight tile
   CUtensorMap* d_mW1 = nullptr; CUtensorMap* d_mW2f = nullptr; CUtensorMap* d_mW1p = nullptr; CUtensorMap* d_mW2p = nullptr;
   unsigned int* d_grid_bar = nullptr;
+  bool fused_attr_set = false;       // function attributes of the fused kernels set on this handle's device
+  int max_clusters[3] = {0, 0, 0};   // co-resident CTA pairs: lock-step / streamed bf16 / streamed tf32 kernel
   int num_sms = 0;
   struct Plan {
     const void* ws = nullptr; const void* cond = nullptr; int B = 0, T = 0;
@@ -258,19 +262,19 @@ int check_device() {
 }
 
 int build_plan(fse_denoiser* h, const Workspace& w, const void* ws, const void* cond, int B, int T) {
-  if (h->cfg.mode != FSE_MODE_TC_BF16) return FSE_OK;
+  if (!h->tc) return FSE_OK;
   auto& pl = h->plan;
   if (pl.ws == ws && pl.B == B && pl.T == T && pl.cond == cond) return FSE_OK;
-  const int C = h->cfg.channels;
-  FSE_TRY(make_map_act(&pl.m_xb, w.xb, h->cfg.n_mels, T, B, 64));
-  FSE_TRY(make_map_act(&pl.m_hb, w.hb, C, T, B, 64));
-  FSE_TRY(make_map_act(&pl.m_cond, w.condb, h->cfg.hidden, T, B, 64));
-  FSE_TRY(make_map_act(&pl.m_u, w.u, h->cfg.layers * C, T, B, 64));
-  FSE_TRY(make_map_act(&pl.m_rb, w.rb, C, T, B, 64));
+  const int C = h->cfg.channels, KB = h->KB, es = h->bf16 ? 2 : 4;
+  FSE_TRY(make_map_act(&pl.m_xb, w.xb, h->cfg.n_mels, T, B, KB, kTileM, es));
+  FSE_TRY(make_map_act(&pl.m_hb, w.hb, C, T, B, KB, kTileM, es));
+  FSE_TRY(make_map_act(&pl.m_cond, h->bf16 ? w.condb : cond, h->cfg.hidden, T, B, KB, kTileM, es));   // fp32 operands: the caller's cond
+  FSE_TRY(make_map_act(&pl.m_u, w.u, h->cfg.layers * C, T, B, KB, kTileM, es));
+  FSE_TRY(make_map_act(&pl.m_rb, w.rb, C, T, B, KB, kTileM, es));
   if (h->fused) {
-    FSE_TRY(make_map_act(&pl.m_hb0_halo, w.hb, C, T, B, 64, 130));
-    FSE_TRY(make_map_act(&pl.m_hb1_halo, w.hb1, C, T, B, 64, 130));
-    FSE_TRY(make_map_act(&pl.m_hb1, w.hb1, C, T, B, 64));
+    FSE_TRY(make_map_act(&pl.m_hb0_halo, w.hb, C, T, B, KB, 130, es));
+    FSE_TRY(make_map_act(&pl.m_hb1_halo, w.hb1, C, T, B, KB, 130, es));
+    FSE_TRY(make_map_act(&pl.m_hb1, w.hb1, C, T, B, KB, kTileM, es));
   }
   pl.ws = ws; pl.B = B; pl.T = T; pl.cond = cond;
   return FSE_OK;
@@ -289,6 +293,79 @@ int run_time_tables(fse_denoiser* h, const Workspace& w, int nT, cudaStream_t st
   return FSE_OK;
 }
 
+// All L residual layers in one persistent launch (denoiser_stream.cuh; the lock-step predecessor denoiser_fused.cuh behind
+// FSE_FUSED_STREAM=0).  The CTAs of these kernels wait for each other (per-unit flags / grid barrier), so the grid is capped by
+// what the driver says can be co-resident; the function attributes and that cap are cached in the handle (one handle = one device).
+int run_fused_layers(fse_denoiser* h, const Workspace& w, int Bc, int b0, int T, int tidx_base, int tidx_bstride, cudaStream_t st) {
+  const int C = h->cfg.channels, H = h->cfg.hidden, L = h->cfg.layers;
+  const bool tf32 = h->cfg.mode == FSE_MODE_TC_TF32;
+  FusedParams fp{};
+  fp.B = Bc; fp.b_off = b0; fp.T = T; fp.L = L; fp.H = H;
+  fp.h = w.h; fp.hb0 = static_cast<__nv_bfloat16*>(w.hb); fp.hb1 = static_cast<__nv_bfloat16*>(w.hb1);
+  fp.hf0 = static_cast<float*>(w.hb); fp.hf1 = static_cast<float*>(w.hb1);
+  fp.u_all = static_cast<__nv_bfloat16*>(w.u);
+  fp.dbias = w.dbias + static_cast<size_t>(tidx_base) * L * 3 * 2 * C;
+  fp.dbias_bstride = static_cast<long long>(tidx_bstride) * L * 3 * 2 * C;
+  fp.b2 = h->b2; fp.grid_bar = h->d_grid_bar; fp.done = w.done; fp.mW1 = h->d_mW1; fp.mW2 = h->d_mW2f;
+  fp.mW1p = h->d_mW1p; fp.mW2p = h->d_mW2p;
+  fp.dbg = h->dbg_buf;
+  if (!h->fused_attr_set) {
+    FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
+    FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
+    FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
+    FSE_CUDA(cudaFuncSetAttribute(denoiser_stream_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
+    FSE_CUDA(cudaFuncSetAttribute(denoiser_stream_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
+    FSE_CUDA(cudaFuncSetAttribute(denoiser_stream_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kStreamTf32SmemBytes)));
+    h->fused_attr_set = true;
+  }
+  const int tiles = Bc * ((T + kTileM - 1) / kTileM);
+  const bool stream = tf32 || (h->fused_stream && h->fused_shared_a);
+  if (stream) FSE_CUDA(cudaMemsetAsync(w.done, 0, static_cast<size_t>(L) * tiles * sizeof(unsigned int), st));
+  else FSE_CUDA(cudaMemsetAsync(h->d_grid_bar, 0, sizeof(unsigned int), st));
+  ++h->launches;
+  h->prof.begin(1, st);
+  if (h->fused_pair) {
+    int grid = (tiles + 1) / 2 * 2;                      // whole clusters of 2
+    const size_t smem = tf32 ? kStreamTf32SmemBytes : kFusedSmemBytes;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(h->num_sms / 2 * 2); cfg.blockDim = dim3(stream ? kStreamThreads : kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    // Every cluster of the grid must be resident at once.  A GPC with an odd number of usable SMs leaves one SM without a
+    // partner, so ask the driver instead of assuming SMs / 2.
+    const int which = tf32 ? 2 : (stream ? 1 : 0);
+    if (h->max_clusters[which] == 0) {
+      int n = 0;
+      if (tf32) FSE_CUDA(cudaOccupancyMaxActiveClusters(&n, denoiser_stream_kernel<true, true>, &cfg));
+      else if (stream) FSE_CUDA(cudaOccupancyMaxActiveClusters(&n, denoiser_stream_kernel<true, false>, &cfg));
+      else FSE_CUDA(cudaOccupancyMaxActiveClusters(&n, denoiser_layers_kernel<true, true>, &cfg));
+      if (n < 1) return fail(FSE_ECUDA, "no resident CTA pair possible for the fused residual-layer kernel");
+      h->max_clusters[which] = n;
+    }
+    if (grid > 2 * h->max_clusters[which]) grid = 2 * h->max_clusters[which];
+    cfg.gridDim = dim3(grid);
+    if (tf32)
+      FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_stream_kernel<true, true>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp));
+    else if (stream)
+      FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_stream_kernel<true, false>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp));
+    else if (h->fused_shared_a)
+      FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_layers_kernel<true, true>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp));
+    else
+      FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_layers_kernel<true, false>, h->plan.m_hb, h->plan.m_hb1, h->plan.m_cond, fp));
+  } else if (stream) {
+    denoiser_stream_kernel<false, false><<<tiles < h->num_sms ? tiles : h->num_sms, kStreamThreads, kFusedSmemBytes, st>>>(
+        h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp);
+  } else {
+    denoiser_layers_kernel<false, true><<<tiles < h->num_sms ? tiles : h->num_sms, kTcThreads, kFusedSmemBytes, st>>>(
+        h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp);
+  }
+  h->prof.end(st);
+  FSE_CUDA(cudaGetLastError());
+  return FSE_OK;
+}
+
 struct OutSpec {
   int mode; const float* x_t; float* x_out; const float* noise; unsigned long long seed; unsigned step;
   float c1, c2, sigma; float* mel_out; const float* ref; const float* mask; bool write_xb;
@@ -301,7 +378,9 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
   const int C = h->cfg.channels, H = h->cfg.hidden, M = h->cfg.n_mels, L = h->cfg.layers, mode = h->cfg.mode;
   const size_t es = sizeof(TOp);
   const int zero = 0;
-  const bool tc = mode == FSE_MODE_TC_BF16;
+  const bool tc = h->tc;
+  const bool fast = mode == FSE_MODE_TC_BF16;     // tanh.approx gate / multiply by 1/sqrt(2): only where bf16 operands bound the accuracy anyway
+  const int KB = h->KB;
   // The batch is walked in chunks of `chunk` utterances through ALL layers, so that the per-chunk working
   // set (h, S fp32 + hb, u, cond operand copies, ~3.5 KB/frame) stays resident in the 126 MB L2 instead of
   // streaming from HBM once per layer.
@@ -310,7 +389,7 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
   const int Bc = std::min(chunk, B - b0);
   // input projection
   {
-    ConvGemmParams p = make_params(Bc, T, T, M, 1, &zero, 0, C, 64); p.b_off = b0;
+    ConvGemmParams p = make_params(Bc, T, T, M, 1, &zero, 0, C, KB); p.b_off = b0;
     GemmOperands op; op.A0 = w.xb; op.W = h->W_in; op.mA0 = &h->plan.m_xb; op.mW = &h->mW_in; op.BN = 256;
     if (C % 256 != 0) op.BN = C % 128 == 0 ? 128 : 64;
     EpiIn<TOp> epi{h->b_in, w.h, static_cast<TOp*>(w.hb), C, T};
@@ -318,83 +397,20 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
   }
   const int bn2 = (2 * C) % 256 == 0 ? 256 : 128;
   const int bnr = C % 128 == 0 ? 128 : 64;      // residual GEMM: finer tiles balance better over the SMs
-  if constexpr (std::is_same<TOp, __nv_bfloat16>::value) {
-    if (h->fused) {
-      // all L residual layers in one persistent launch (denoiser_fused.cuh)
-      FusedParams fp{};
-      fp.B = Bc; fp.b_off = b0; fp.T = T; fp.L = L; fp.H = H;
-      fp.h = w.h; fp.hb0 = static_cast<__nv_bfloat16*>(w.hb); fp.hb1 = static_cast<__nv_bfloat16*>(w.hb1);
-      fp.u_all = static_cast<__nv_bfloat16*>(w.u);
-      fp.dbias = w.dbias + static_cast<size_t>(tidx_base) * L * 3 * 2 * C;
-      fp.dbias_bstride = static_cast<long long>(tidx_bstride) * L * 3 * 2 * C;
-      fp.b2 = h->b2; fp.grid_bar = h->d_grid_bar; fp.done = w.done; fp.mW1 = h->d_mW1; fp.mW2 = h->d_mW2f;
-      fp.mW1p = h->d_mW1p; fp.mW2p = h->d_mW2p;
-      fp.dbg = h->dbg_buf;
-      static bool attr_set = false;
-      if (!attr_set) {
-        FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
-        FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
-        FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
-        FSE_CUDA(cudaFuncSetAttribute(denoiser_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
-        FSE_CUDA(cudaFuncSetAttribute(denoiser_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
-        attr_set = true;
-      }
-      const int tiles = Bc * ((T + kTileM - 1) / kTileM);
-      const bool stream = h->fused_stream && h->fused_shared_a;
-      if (stream) FSE_CUDA(cudaMemsetAsync(w.done, 0, static_cast<size_t>(L) * tiles * sizeof(unsigned int), st));
-      else FSE_CUDA(cudaMemsetAsync(h->d_grid_bar, 0, sizeof(unsigned int), st));
-      ++h->launches;
-      h->prof.begin(1, st);
-      if (h->fused_pair) {
-        int grid = (tiles + 1) / 2 * 2;                      // whole clusters of 2
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(h->num_sms / 2 * 2); cfg.blockDim = dim3(stream ? kStreamThreads : kTcThreads); cfg.dynamicSmemBytes = kFusedSmemBytes; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        // The CTAs wait for each other (layer dependencies / grid barrier): every cluster of the grid must be resident at once.
-        // A GPC with an odd number of usable SMs leaves one SM without a partner, so ask the driver instead of assuming SMs / 2.
-        static int max_clusters[2] = {0, 0};
-        if (max_clusters[stream] == 0) {
-          int n = 0;
-          if (stream) FSE_CUDA(cudaOccupancyMaxActiveClusters(&n, denoiser_stream_kernel<true>, &cfg));
-          else FSE_CUDA(cudaOccupancyMaxActiveClusters(&n, denoiser_layers_kernel<true, true>, &cfg));
-          if (n < 1) return fail(FSE_ECUDA, "no resident CTA pair possible for the fused residual-layer kernel");
-          max_clusters[stream] = n;
-        }
-        if (grid > 2 * max_clusters[stream]) grid = 2 * max_clusters[stream];
-        cfg.gridDim = dim3(grid);
-        if (stream)
-          FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_stream_kernel<true>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp));
-        else if (h->fused_shared_a)
-          FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_layers_kernel<true, true>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp));
-        else
-          FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_layers_kernel<true, false>, h->plan.m_hb, h->plan.m_hb1, h->plan.m_cond, fp));
-      } else if (stream) {
-        denoiser_stream_kernel<false><<<tiles < h->num_sms ? tiles : h->num_sms, kStreamThreads, kFusedSmemBytes, st>>>(
-            h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp);
-      } else {
-        denoiser_layers_kernel<false, true><<<tiles < h->num_sms ? tiles : h->num_sms, kTcThreads, kFusedSmemBytes, st>>>(
-            h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp);
-      }
-      h->prof.end(st);
-      FSE_CUDA(cudaGetLastError());
-    }
-  }
+  if (h->fused) FSE_TRY(run_fused_layers(h, w, Bc, b0, T, tidx_base, tidx_bstride, st));
   if (!h->fused)
   for (int l = 0; l < L; ++l) {
     const int dil = 1 << (l % h->cfg.dilation_cycle_length);
     const int offs[3] = {-dil, 0, dil};
     {
-      ConvGemmParams p = make_params(Bc, T, T, C, 3, offs, H, 2 * C, 64); p.b_off = b0;
+      ConvGemmParams p = make_params(Bc, T, T, C, 3, offs, H, 2 * C, KB); p.b_off = b0;
       if (h->dbg_buf && l == 3) p.dbg = h->dbg_buf;
       GemmOperands op; op.A0 = w.hb; op.A1 = cond_op;
       op.W = static_cast<const uint8_t*>(h->W1) + static_cast<size_t>(l) * 2 * C * h->Kp1 * es;
       op.mA0 = &h->plan.m_hb; op.mA1 = &h->plan.m_cond; op.mW = tc ? &h->mW1[l] : nullptr; op.BN = bn2;
       const float* db = w.dbias + (static_cast<size_t>(tidx_base) * L + l) * 3 * 2 * C;
       const long long bstride = static_cast<long long>(tidx_bstride) * L * 3 * 2 * C;
-      if (tc) {
+      if (fast) {
         EpiGate<TOp, true> epi{db, bstride, static_cast<TOp*>(w.u), 2 * C, T, dil, L * C, l * C};
         FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 1})));
       } else {
@@ -403,13 +419,13 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
       }
     }
     {
-      ConvGemmParams p = make_params(Bc, T, T, C, 1, &zero, 0, C, 64); p.b_off = b0;
+      ConvGemmParams p = make_params(Bc, T, T, C, 1, &zero, 0, C, KB); p.b_off = b0;
       p.c_off0 = l * C; p.ld0 = L * C;
       if (h->dbg_buf && l == 3) p.dbg = h->dbg_buf + 32;
       GemmOperands op; op.A0 = w.u;
       op.W = static_cast<const uint8_t*>(h->W2) + static_cast<size_t>(l) * C * C * es;
       op.mA0 = &h->plan.m_u; op.mW = tc ? &h->mW2[l] : nullptr; op.BN = bnr;
-      if (tc) {
+      if (fast) {
         EpiRes<TOp, true> epi{h->b2 + static_cast<size_t>(l) * C, w.h, static_cast<TOp*>(w.hb), C, T};
         FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 2})));
       } else {
@@ -419,7 +435,7 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
     }
   }
   {
-    ConvGemmParams p = make_params(Bc, T, T, L * C, 1, &zero, 0, C, 64); p.b_off = b0;
+    ConvGemmParams p = make_params(Bc, T, T, L * C, 1, &zero, 0, C, KB); p.b_off = b0;
     GemmOperands op; op.A0 = w.u; op.W = h->W_skip; op.mA0 = &h->plan.m_u; op.mW = &h->mW_skip;
     op.BN = C % 256 == 0 ? 256 : (C % 128 == 0 ? 128 : 64);
     // K = L*C is long and the weight tile is re-read by every job: two 128-frame sub-tiles per job halve that traffic
@@ -429,7 +445,7 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
     FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 3})));
   }
   {
-    ConvGemmParams p = make_params(Bc, T, T, C, 1, &zero, 0, M, 64); p.b_off = b0;
+    ConvGemmParams p = make_params(Bc, T, T, C, 1, &zero, 0, M, KB); p.b_off = b0;
     GemmOperands op; op.A0 = w.rb; op.W = h->W_out; op.mA0 = &h->plan.m_rb; op.mW = &h->mW_out; op.BN = M;
     EpiOut<TOp> epi{h->b_out, M, T, out.mode, out.x_t, out.x_out, out.write_xb ? static_cast<TOp*>(w.xb) : nullptr,
                     out.noise, out.seed, out.step, out.c1, out.c2, out.sigma, out.mel_out, out.ref, out.mask};
@@ -562,18 +578,20 @@ int fse_denoiser_create(const fse_denoiser_config* cfg, fse_denoiser** out) {
   if (cfg->channels <= 0 || cfg->channels % 64 != 0) return fail(FSE_EINVAL, "channels must be a multiple of 64");
   if (cfg->hidden <= 0 || cfg->hidden % 8 != 0) return fail(FSE_EINVAL, "hidden must be a multiple of 8");
   if (cfg->layers <= 0 || cfg->dilation_cycle_length <= 0) return fail(FSE_EINVAL, "layers / dilation_cycle_length must be positive");
-  if (cfg->mode < 0 || cfg->mode > 2) return fail(FSE_EINVAL, "unknown mode %d", cfg->mode);
+  if (cfg->mode < 0 || cfg->mode > 3) return fail(FSE_EINVAL, "unknown mode %d", cfg->mode);
   FSE_TRY(check_device());
   auto* h = new fse_denoiser();
   h->cfg = *cfg;
-  h->bf16 = cfg->mode != FSE_MODE_SIMT_F32;
+  h->bf16 = mode_is_bf16(cfg->mode);
+  h->tc = mode_is_tc(cfg->mode);
+  h->KB = mode_kb(cfg->mode);
   if (const char* e = getenv("FSE_BATCH_CHUNK")) h->batch_chunk = atoi(e);
   if (const char* e = getenv("FSE_SKIP_MT")) h->skip_mt = atoi(e) == 1 ? 1 : 2;
   // The fused multi-layer kernel covers the shipped configurations (256 residual channels, dilation 1, <= 256
   // condition channels); anything else runs the per-layer kernels.  FSE_FUSED=0 forces the per-layer path.
-  h->fused = cfg->mode == FSE_MODE_TC_BF16 && cfg->channels == kFC && cfg->dilation_cycle_length == 1 && cfg->hidden <= 256 &&
+  h->fused = mode_is_tc(cfg->mode) && cfg->channels == kFC && cfg->dilation_cycle_length == 1 && cfg->hidden <= 256 &&
              cfg->hidden % 64 == 0 && !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 0);
-  h->fused_pair = h->fused && !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 1);   // FSE_FUSED=1: single-CTA variant
+  h->fused_pair = h->fused && (cfg->mode == FSE_MODE_TC_TF32 || !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 1));   // FSE_FUSED=1: single-CTA variant (bf16 only)
   h->fused_stream = !(getenv("FSE_FUSED_STREAM") && atoi(getenv("FSE_FUSED_STREAM")) == 0);
   h->fused_shared_a = !(getenv("FSE_FUSED_SHARED_A") && atoi(getenv("FSE_FUSED_SHARED_A")) == 0);   // measured: 92.3 vs 95.3 ms/step
   if (getenv("FSE_DBG_STAMPS")) { cudaMalloc(reinterpret_cast<void**>(&h->dbg_buf), 64 * 8); cudaMemset(h->dbg_buf, 0, 64 * 8); }
@@ -601,14 +619,16 @@ int fse_denoiser_load_weights(fse_denoiser* h, const fse_tensor* tensors, int32_
   auto G = [&](const std::string& name, int64_t numel) { return rc == FSE_OK ? tt.get(name, numel, &rc) : nullptr; };
 
   // input projection [C, M, 1] -> [C, Kp_in]
-  h->Kp_in = (M + 63) / 64 * 64;
+  const int KB = h->KB, es = h->bf16 ? 2 : 4;
+  const bool tf32 = h->cfg.mode == FSE_MODE_TC_TF32;
+  h->Kp_in = (M + KB - 1) / KB * KB;
   {
     const float* w = G("input_projection.weight", (int64_t)C * M);
     const float* b = G("input_projection.bias", C);
     if (rc) return rc;
     std::vector<float> p(static_cast<size_t>(C) * h->Kp_in, 0.f);
     for (int o = 0; o < C; ++o) for (int c = 0; c < M; ++c) p[(size_t)o * h->Kp_in + c] = w[(size_t)o * M + c];
-    FSE_TRY(upload_operand(p, h->bf16, &h->W_in));
+    FSE_TRY(upload_operand(p, h->bf16, &h->W_in, tf32));
     FSE_TRY(upload_f32(std::vector<float>(b, b + C), &h->b_in));
   }
   {
@@ -620,8 +640,8 @@ int fse_denoiser_load_weights(fse_denoiser* h, const fse_tensor* tensors, int32_
     FSE_TRY(upload_f32(std::vector<float>(w2, w2 + (size_t)4 * C * C), &h->mlp2_w));
     FSE_TRY(upload_f32(std::vector<float>(b2, b2 + C), &h->mlp2_b));
   }
-  const int nkbC = C / 64, nkbH = (H + 63) / 64;
-  h->Kp1 = (3 * nkbC + nkbH) * 64;
+  const int nkbC = C / KB, nkbH = (H + KB - 1) / KB;
+  h->Kp1 = (3 * nkbC + nkbH) * KB;
   const int N2 = 2 * C;
   std::vector<float> W1((size_t)L * N2 * h->Kp1, 0.f), W2((size_t)L * C * C), b2v((size_t)L * C);
   std::vector<const float*> wop_all(L), bop_all(L);
@@ -645,12 +665,12 @@ int fse_denoiser_load_weights(fse_denoiser* h, const fse_tensor* tensors, int32_
       float* rcc = &Wmac[(((size_t)l * 3 + 2) * N2 + np) * C];
       for (int c = 0; c < C; ++c) {
         const float* k3 = wdc + ((size_t)r * C + c) * 3;
-        for (int j = 0; j < 3; ++j) row[j * nkbC * 64 + c] = k3[j];
+        for (int j = 0; j < 3; ++j) row[j * nkbC * KB + c] = k3[j];
         rm[c] = static_cast<float>(static_cast<double>(k3[0]) + k3[1] + k3[2]);
         ra[c] = k3[0];
         rcc[c] = k3[2];
       }
-      for (int c = 0; c < H; ++c) row[3 * nkbC * 64 + c] = wcp[(size_t)r * H + c];
+      for (int c = 0; c < H; ++c) row[3 * nkbC * KB + c] = wcp[(size_t)r * H + c];
       bmac[(size_t)l * N2 + np] = bdc[r] + bcp[r];
     }
     memcpy(&W2[(size_t)l * C * C], wop, sizeof(float) * C * C);      // residual half = first C rows (diffnet.py:80 chunk order)
@@ -659,8 +679,8 @@ int fse_denoiser_load_weights(fse_denoiser* h, const fse_tensor* tensors, int32_
     memcpy(&Wdp[(size_t)l * C * C], wdp, sizeof(float) * C * C);
     memcpy(&bdp[(size_t)l * C], bd, sizeof(float) * C);
   }
-  FSE_TRY(upload_operand(W1, h->bf16, &h->W1));
-  FSE_TRY(upload_operand(W2, h->bf16, &h->W2));
+  FSE_TRY(upload_operand(W1, h->bf16, &h->W1, tf32));
+  FSE_TRY(upload_operand(W2, h->bf16, &h->W2, tf32));
   FSE_TRY(upload_f32(b2v, &h->b2));
   FSE_TRY(upload_f32(Wmac, &h->Wmac));
   FSE_TRY(upload_f32(bmac, &h->bmac));
@@ -692,26 +712,26 @@ int fse_denoiser_load_weights(fse_denoiser* h, const fse_tensor* tensors, int32_
         for (int c = 0; c < C; ++c) dst[c] = static_cast<float>(row[c] * inv);
       }
     }
-    FSE_TRY(upload_operand(Wc, h->bf16, &h->W_skip));
+    FSE_TRY(upload_operand(Wc, h->bf16, &h->W_skip, tf32));
     FSE_TRY(upload_f32(bc, &h->b_skip));
-    FSE_TRY(upload_operand(std::vector<float>(wo, wo + (size_t)M * C), h->bf16, &h->W_out));
+    FSE_TRY(upload_operand(std::vector<float>(wo, wo + (size_t)M * C), h->bf16, &h->W_out, tf32));
     FSE_TRY(upload_f32(std::vector<float>(bo, bo + M), &h->b_out));
   }
-  if (h->cfg.mode == FSE_MODE_TC_BF16) {
+  if (h->tc) {
     const int bnC = C % 256 == 0 ? 256 : (C % 128 == 0 ? 128 : 64);
     const int bn2 = N2 % 256 == 0 ? 256 : 128;
     const int bnr = C % 128 == 0 ? 128 : 64;
-    FSE_TRY(make_map_w(&h->mW_in, h->W_in, h->Kp_in, C, 64, bnC));
-    FSE_TRY(make_map_w(&h->mW_skip, h->W_skip, L * C, C, 64, bnC));
-    FSE_TRY(make_map_w(&h->mW_out, h->W_out, C, M, 64, M));
+    FSE_TRY(make_map_w(&h->mW_in, h->W_in, h->Kp_in, C, KB, bnC, es));
+    FSE_TRY(make_map_w(&h->mW_skip, h->W_skip, L * C, C, KB, bnC, es));
+    FSE_TRY(make_map_w(&h->mW_out, h->W_out, C, M, KB, M, es));
     h->mW1.resize(L); h->mW2.resize(L);
     for (int l = 0; l < L; ++l) {
-      FSE_TRY(make_map_w(&h->mW1[l], static_cast<uint8_t*>(h->W1) + (size_t)l * N2 * h->Kp1 * 2, h->Kp1, N2, 64, bn2));
-      FSE_TRY(make_map_w(&h->mW2[l], static_cast<uint8_t*>(h->W2) + (size_t)l * C * C * 2, C, C, 64, bnr));
+      FSE_TRY(make_map_w(&h->mW1[l], static_cast<uint8_t*>(h->W1) + (size_t)l * N2 * h->Kp1 * es, h->Kp1, N2, KB, bn2, es));
+      FSE_TRY(make_map_w(&h->mW2[l], static_cast<uint8_t*>(h->W2) + (size_t)l * C * C * es, C, C, KB, bnr, es));
     }
     if (h->fused) {
       std::vector<CUtensorMap> w2f(L);
-      for (int l = 0; l < L; ++l) FSE_TRY(make_map_w(&w2f[l], static_cast<uint8_t*>(h->W2) + (size_t)l * C * C * 2, C, C, 64, 256));
+      for (int l = 0; l < L; ++l) FSE_TRY(make_map_w(&w2f[l], static_cast<uint8_t*>(h->W2) + (size_t)l * C * C * es, C, C, KB, 256, es));
       FSE_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_mW1), sizeof(CUtensorMap) * L));
       FSE_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_mW2f), sizeof(CUtensorMap) * L));
       FSE_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_grid_bar), 256));
@@ -719,8 +739,8 @@ int fse_denoiser_load_weights(fse_denoiser* h, const fse_tensor* tensors, int32_
       FSE_CUDA(cudaMemcpy(h->d_mW2f, w2f.data(), sizeof(CUtensorMap) * L, cudaMemcpyHostToDevice));
       std::vector<CUtensorMap> w1p(L), w2p(L);
       for (int l = 0; l < L; ++l) {
-        FSE_TRY(make_map_w(&w1p[l], static_cast<uint8_t*>(h->W1) + (size_t)l * N2 * h->Kp1 * 2, h->Kp1, N2, 64, 128));
-        FSE_TRY(make_map_w(&w2p[l], static_cast<uint8_t*>(h->W2) + (size_t)l * C * C * 2, C, C, 64, 128));
+        FSE_TRY(make_map_w(&w1p[l], static_cast<uint8_t*>(h->W1) + (size_t)l * N2 * h->Kp1 * es, h->Kp1, N2, KB, 128, es));
+        FSE_TRY(make_map_w(&w2p[l], static_cast<uint8_t*>(h->W2) + (size_t)l * C * C * es, C, C, KB, 128, es));
       }
       FSE_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_mW1p), sizeof(CUtensorMap) * L));
       FSE_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->d_mW2p), sizeof(CUtensorMap) * L));

@@ -30,6 +30,8 @@ struct FusedParams {
   float* h;                       // [*, 256] fp32 residual stream, updated in place
   __nv_bfloat16* hb0;             // operand copy read by even layers / written by odd layers
   __nv_bfloat16* hb1;             // ... and vice versa
+  float* hf0;                     // tf32 streamed kernel: fp32 residual stream = operand, read by even / written by odd layers
+  float* hf1;                     // ... and vice versa
   __nv_bfloat16* u_all;           // [*, L*256]
   const float* dbias;             // timestep tables of this call: [.., L, 3, 512]
   long long dbias_bstride;        // elements between consecutive items' tables (0: shared)

@@ -48,23 +48,41 @@ __device__ __forceinline__ void stream_wait_done(const unsigned int* flag, unsig
 
 constexpr int kStreamThreads = kTcThreads + 32;     // + the publisher warp
 
-template <bool kPair>
+// kTF32 (CTA pairs only): the same schedule on tcgen05 kind::tf32 — the reference's own GPU arithmetic (cuDNN TF32 convolutions).
+// Every operand is fp32 in HBM and shared memory, so a k-block is 32 channels (128-byte rows as before) and there are twice as
+// many of them: 8 hb blocks + H/32 cond blocks per gate job, 8 u blocks for the residual GEMM.  The residual stream IS the
+// operand (no bf16 copy): layer l reads hf[l & 1] (TMA halo tiles + the epilogue's own rows) and writes hf[(l + 1) & 1]; u is
+// rounded to tf32 once (cvt.rna) and kept as a 128 KB fp32 tile in shared memory (2 activation slots + 3 weight stages fit
+// next to it); u_all is fp32.  Gate non-linearities use ex2/rcp at fp32 accuracy instead of tanh.approx.
+constexpr int kStreamTf32ASlots = 2, kStreamTf32WStages = 3;
+constexpr int kStreamTf32UBytes = 8 * 128 * 128;
+constexpr size_t kStreamTf32SmemBytes = 1024 + kStreamTf32ASlots * kFusedASlotBytes + kStreamTf32WStages * 128 * 128 + kStreamTf32UBytes + kFusedBiasBytes + 256;
+static_assert(kStreamTf32SmemBytes <= 227 * 1024, "tf32 stream kernel: shared memory");
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_acc(float x) { return fmaf(2.0f, sigmoid_acc(2.0f * x), -1.0f); }
+
+template <bool kPair, bool kTF32 = false>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_constant__ CUtensorMap mapHb1,
                        const __grid_constant__ CUtensorMap mapCond, FusedParams p) {
+  static_assert(kPair || !kTF32, "the tf32 schedule exists for CTA pairs only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int WB = kPair ? 128 * 128 : 256 * 128;     // bytes of one weight stage (128 or 256 rows x 64 bf16)
-  constexpr int AS = kFusedASlots;                      // 130-row activation tiles; taps = row-shifted descriptors
+  constexpr int WB = kPair ? 128 * 128 : 256 * 128;     // bytes of one weight stage (128 or 256 rows x 128 B)
+  constexpr int AS = kTF32 ? kStreamTf32ASlots : kFusedASlots;     // 130-row activation tiles; taps = row-shifted descriptors
   constexpr int AB = kFusedASlotBytes;
-  constexpr int WS = kPair ? 6 : kFusedWStages;
-  static_assert(AS * AB + WS * WB <= kFusedASlots * kFusedASlotBytes + kFusedWStages * kFusedWStageBytes, "smem budget");
+  constexpr int WS = kTF32 ? kStreamTf32WStages : (kPair ? 6 : kFusedWStages);
+  constexpr int KC = kTF32 ? 32 : 64;                   // channels per k-block (128 bytes)
+  constexpr int NHB = kFC / KC;                         // hb channel blocks = u k-blocks: 4 (bf16) or 8 (tf32)
+  constexpr int UB = kTF32 ? kStreamTf32UBytes : kFusedUBytes;
+  static_assert(kTF32 || AS * AB + WS * WB <= kFusedASlots * kFusedASlotBytes + kFusedWStages * kFusedWStageBytes, "smem budget");
   constexpr uint32_t kMul = kPair ? 2u : 1u;
   uint8_t* sA = smem;
   uint8_t* sW = sA + AS * AB;
   uint8_t* sU = sW + WS * WB;
-  float* sBias = reinterpret_cast<float*>(sU + kFusedUBytes);          // [3][512] timestep tables + [256] residual bias of the layer
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sU + kFusedUBytes + kFusedBiasBytes);
+  float* sBias = reinterpret_cast<float*>(sU + UB);          // [3][512] timestep tables + [256] residual bias of the layer
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sU + UB + kFusedBiasBytes);
   uint64_t* a_empty = a_full + AS;
   uint64_t* w_full = a_empty + AS;
   uint64_t* w_empty = w_full + WS;
@@ -87,8 +105,8 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
   const int total_units = kPair ? (total_tiles + 1) / 2 : total_tiles;
   const int total_items = p.L * total_units;
   const unsigned int done_target = kEpiWarps * kMul;     // epilogue warps that store one unit
-  const int nkbH = (p.H + 63) / 64;
-  const int ngroups = 4 + nkbH;                    // 4 hb channel blocks (3 taps each) + cond blocks (1 tap)
+  const int nkbH = (p.H + KC - 1) / KC;
+  const int ngroups = NHB + nkbH;                  // hb channel blocks (3 taps each) + cond blocks (1 tap)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&mapHb0);
@@ -145,9 +163,9 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
             const int slot = ga % AS;
             ptx::mbar_wait(&a_empty[slot], ((ga / AS) & 1) ^ 1u);
             // pair mode: both CTAs' loads signal the LEADER's barrier, which expects the bytes of both
-            const bool is_hb = grp < 4;
+            const bool is_hb = grp < NHB;
             const uint32_t rows = is_hb ? 130u : 128u;
-            const int c0 = is_hb ? grp * 64 : (grp - 4) * 64;
+            const int c0 = is_hb ? grp * KC : (grp - NHB) * KC;
             const int tt = is_hb ? t0 - 1 : t0;
             if (leader) ptx::mbar_arrive_expect_tx(&a_full[slot], rows * 128u * kMul);
             if constexpr (kPair) {
@@ -160,27 +178,29 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
               const int s = kw % WS;
               ptx::mbar_wait(&w_empty[s], ((kw / WS) & 1) ^ 1u);
               if (leader) ptx::mbar_arrive_expect_tx(&w_full[s], static_cast<uint32_t>(WB) * kMul);
-              const int kb = is_hb ? j * 4 + grp : 12 + (grp - 4);      // weight k-blocks are packed tap-major
-              if constexpr (kPair) ptx::tma_load_2d_pair(sW + s * WB, mW1, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * 64, half * 256 + nrow);
-              else ptx::tma_load_2d(sW + s * WB, mW1, &w_full[s], kb * 64, half * 256);
+              const int kb = is_hb ? j * NHB + grp : 3 * NHB + (grp - NHB);      // weight k-blocks are packed tap-major
+              if constexpr (kPair) ptx::tma_load_2d_pair(sW + s * WB, mW1, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * KC, half * 256 + nrow);
+              else ptx::tma_load_2d(sW + s * WB, mW1, &w_full[s], kb * KC, half * 256);
             }
           }
         }
-        for (int kb = 0; kb < 4; ++kb, ++kw) {          // residual GEMM weights (its A operand is the smem copy of u)
+        for (int kb = 0; kb < NHB; ++kb, ++kw) {          // residual GEMM weights (its A operand is the smem copy of u)
           const int s = kw % WS;
           ptx::mbar_wait(&w_empty[s], ((kw / WS) & 1) ^ 1u);
           if (leader) ptx::mbar_arrive_expect_tx(&w_full[s], static_cast<uint32_t>(WB) * kMul);
-          if constexpr (kPair) ptx::tma_load_2d_pair(sW + s * WB, mW2, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * 64, nrow);
-          else ptx::tma_load_2d(sW + s * WB, mW2, &w_full[s], kb * 64, 0);
+          if constexpr (kPair) ptx::tma_load_2d_pair(sW + s * WB, mW2, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * KC, nrow);
+          else ptx::tma_load_2d(sW + s * WB, mW2, &w_full[s], kb * KC, 0);
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    const uint32_t idesc = ptx::make_idesc_bf16_f32(kPair ? 2 * kTileM : kTileM, 256);
+    const uint32_t idesc = kTF32 ? ptx::make_idesc_tf32_f32(kPair ? 2 * kTileM : kTileM, 256) : ptx::make_idesc_bf16_f32(kPair ? 2 * kTileM : kTileM, 256);
     auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
-      if constexpr (kPair) ptx::mma_f16_ss_pair(d, da, db, idesc, acc); else ptx::mma_f16_ss(d, da, db, idesc, acc);
+      if constexpr (kTF32) ptx::mma_tf32_ss_pair(d, da, db, idesc, acc);
+      else if constexpr (kPair) ptx::mma_f16_ss_pair(d, da, db, idesc, acc);
+      else ptx::mma_f16_ss(d, da, db, idesc, acc);
     };
     auto commit = [&](uint64_t* bar) {
       if constexpr (kPair) ptx::mma_commit_pair(bar); else ptx::mma_commit(bar);
@@ -200,7 +220,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           for (int grp = 0; grp < ngroups; ++grp, ++ga) {
             const int slot = ga % AS;
             ptx::mbar_wait(&a_full[slot], (ga / AS) & 1);
-            const int ntap = grp < 4 ? 3 : 1;
+            const int ntap = grp < NHB ? 3 : 1;
             for (int j = 0; j < ntap; ++j, ++kw) {
               const int s = kw % WS;
               ptx::mbar_wait(&w_full[s], (kw / WS) & 1);
@@ -209,7 +229,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
                 // hb tile holds frames t0-1 .. t0+128; tap j (offset j-1) starts at row j.  Descriptors are computed by the
                 // whole warp (convergent code -> uniform registers); only the tcgen05 instructions are under the one-lane
                 // predicate (inside a divergent region every operand would need an R2UR and a waterfall loop per MMA).
-                const uint32_t a_addr = ptx::smem_u32(sA + slot * AB) + (grp < 4 ? static_cast<uint32_t>(j * 128) : 0u);
+                const uint32_t a_addr = ptx::smem_u32(sA + slot * AB) + (grp < NHB ? static_cast<uint32_t>(j * 128) : 0u);
                 const uint64_t da = ptx::make_desc_k_sw128(a_addr);
                 const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sW + s * WB));
 #pragma unroll
@@ -232,13 +252,13 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           ptx::mbar_wait(&acc_empty[buf], ((job >> 1) & 1) ^ 1u);
           if (dm) dm[4] = clock64();
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * 256);
-          for (int kb = 0; kb < 4; ++kb, ++kw) {
-            if ((kb & 1) == 0) {
-              // the first half of the residual GEMM (u k-blocks 0,1) only needs the FIRST gate epilogue, which finished while
-              // the second gate job was running; only k-blocks 2,3 wait for the second gate epilogue
-              ptx::mbar_wait(&u_full[kb >> 1], it & 1);
+          for (int kb = 0; kb < NHB; ++kb, ++kw) {
+            if (kb % (NHB / 2) == 0) {
+              // the first half of the residual GEMM (first half of the u k-blocks) only needs the FIRST gate epilogue, which
+              // finished while the second gate job was running; only the second half waits for the second gate epilogue
+              ptx::mbar_wait(&u_full[kb / (NHB / 2)], it & 1);
               ptx::tc_fence_after();
-              if (dm && kb == 2) dm[5] = clock64();
+              if (dm && kb == NHB / 2) dm[5] = clock64();
             }
             const int s = kw % WS;
             ptx::mbar_wait(&w_full[s], (kw / WS) & 1);
@@ -310,6 +330,9 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
         cur_l = l;
       }
       __nv_bfloat16* hb_out = (l & 1) ? p.hb0 : p.hb1;
+      // tf32: the fp32 residual stream ping-pongs (layer l reads hf[l & 1], writes hf[(l + 1) & 1]); bf16: h in place + bf16 copy
+      const float* h_in = kTF32 ? ((l & 1) ? p.hf1 : p.hf0) : p.h;
+      float* h_out = kTF32 ? ((l & 1) ? p.hf0 : p.hf1) : p.h;
       const int tile = kPair ? 2 * unit + static_cast<int>(rank) : unit;
       const int b = p.b_off + tile / tiles_per_item, t0 = (tile % tiles_per_item) * kTileM;
       const int r = q * 32 + lane;                    // row inside the tile = TMEM lane
@@ -350,13 +373,31 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
 #pragma unroll
             for (int i = 0; i < 32; ++i) y[i] -= m[1024 + i];
           }
+          const int ucol = half * 128 + c * 16;
+          if constexpr (kTF32) {
+            uint32_t uf[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) uf[j] = __float_as_uint(ptx::round_tf32(sigmoid_acc(y[2 * j]) * tanh_acc(y[2 * j + 1])));
+            if (row_ok) {
+              float* up = reinterpret_cast<float*>(p.u_all) + row * static_cast<size_t>(p.L * kFC) + l * kFC + ucol;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(up + 4 * j), "r"(uf[4 * j]), "r"(uf[4 * j + 1]), "r"(uf[4 * j + 2]), "r"(uf[4 * j + 3]) : "memory");
+            }
+            // A operand of the residual GEMM: k-block = 32 fp32 channels, 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
+            uint8_t* ub = sU + (ucol >> 5) * 16384 + r * 128;
+            const int ch = (ucol & 31) >> 2;             // first of the four 16-byte chunks
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(ub + (((ch + j) ^ (r & 7)) << 4)) = make_uint4(uf[4 * j], uf[4 * j + 1], uf[4 * j + 2], uf[4 * j + 3]);
+            return;
+          }
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             pk[j] = pack_bf16x2(sigmoid_f<true>(y[4 * j]) * tanh_f<true>(y[4 * j + 1]),
                                 sigmoid_f<true>(y[4 * j + 2]) * tanh_f<true>(y[4 * j + 3]));
           // u columns [ucol, ucol+16): HBM copy for the folded skip GEMM ...
-          const int ucol = half * 128 + c * 16;
           if (row_ok) {
             __nv_bfloat16* up = p.u_all + row * static_cast<size_t>(p.L * kFC) + l * kFC + ucol;
             asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(up), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
@@ -395,12 +436,14 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
         // ahead of the global traffic: the buffer goes back to the MMA warp after ~40 % of this epilogue (the next item's
         // second gate job was waiting for exactly that).
         const int job = 3 * it + 2, buf = job & 1;
-        float* stgA = reinterpret_cast<float*>(sU + half2 * 16384 + q * 4096);
-        float* stgB = reinterpret_cast<float*>(sU + (2 + half2) * 16384 + q * 4096);
+        // (tf32: this warp wrote rows q*32.. of u k-blocks {2*half2, 2*half2+1} and {4+2*half2, 4+2*half2+1})
+        float* stgA = reinterpret_cast<float*>(sU + (kTF32 ? 2 * half2 : half2) * 16384 + q * 4096);
+        float* stgB = reinterpret_cast<float*>(sU + (kTF32 ? 4 + 2 * half2 : 2 + half2) * 16384 + q * 4096);
         const int cq = lane & 7, r0 = lane >> 3;
         const int tq = tile < total_tiles ? t0 + q * 32 + r0 : p.T;   // frame of iteration 0; iteration i adds 4*i
         const size_t rowq = static_cast<size_t>(b) * p.T + tq;
-        float* hq = p.h + rowq * kFC + cq * 4;
+        const float* hq = h_in + rowq * kFC + cq * 4;
+        float* hoq = h_out + rowq * kFC + cq * 4;
         __nv_bfloat16* hbq = hb_out + rowq * kFC + cq * 4;
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * 256);
         auto load_h = [&](int c, float4 (&hx)[8]) {                 // this lane's part of residual-stream chunk c
@@ -429,8 +472,8 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
               v[1] = (hx[i].y + (a.y + bv.y)) * 0.70710678118654752440f;
               v[2] = (hx[i].z + (a.z + bv.z)) * 0.70710678118654752440f;
               v[3] = (hx[i].w + (a.w + bv.w)) * 0.70710678118654752440f;
-              st_vec<4>(hq + static_cast<size_t>(4 * i) * kFC + c * 32, v);
-              st_vec<4>(hbq + static_cast<size_t>(4 * i) * kFC + c * 32, v);
+              st_vec<4>(hoq + static_cast<size_t>(4 * i) * kFC + c * 32, v);
+              if constexpr (!kTF32) st_vec<4>(hbq + static_cast<size_t>(4 * i) * kFC + c * 32, v);
             }
           }
           __syncwarp();                                             // all lanes have read the scratch

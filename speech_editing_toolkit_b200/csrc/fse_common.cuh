@@ -72,8 +72,27 @@ inline uint16_t f32_to_bf16_rne(float f) {
   return static_cast<uint16_t>(u >> 16);
 }
 
-// Upload a host fp32 matrix as the operand type of the mode (bf16 or fp32).
-inline int upload_operand(const std::vector<float>& host, bool bf16, void** dptr) {
+// fp32 -> tf32 (10 explicit mantissa bits), round to nearest even, kept in an fp32 container: the tensor core ignores the low
+// 13 bits, so rounding the (constant) weights once at load time halves their representation error versus truncation.
+inline float f32_to_tf32_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return f;
+  u += 0xFFFu + ((u >> 13) & 1u);
+  u &= 0xFFFFE000u;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// Upload a host fp32 matrix as the operand type of the mode (bf16 or fp32; tf32 = fp32 rounded to tf32).
+inline int upload_operand(const std::vector<float>& host, bool bf16, void** dptr, bool tf32 = false) {
+  if (tf32) {
+    std::vector<float> tmp(host.size());
+    for (size_t i = 0; i < host.size(); ++i) tmp[i] = f32_to_tf32_rne(host[i]);
+    FSE_CUDA(cudaMalloc(dptr, tmp.size() * 4));
+    FSE_CUDA(cudaMemcpy(*dptr, tmp.data(), tmp.size() * 4, cudaMemcpyHostToDevice));
+    return FSE_OK;
+  }
   if (bf16) {
     std::vector<uint16_t> tmp(host.size());
     for (size_t i = 0; i < host.size(); ++i) tmp[i] = f32_to_bf16_rne(host[i]);
@@ -107,30 +126,36 @@ inline int get_encode_fn(PFN_tmapEncodeTiled* out) {
   *out = fn;
   return FSE_OK;
 }
-// bf16 activation [B, T, C] channels-last: dims (C, T, B), box (KB, 128, 1); out-of-range frames/channels read 0.
-inline int make_map_act(CUtensorMap* m, const void* ptr, int C, int T, int B, int KB, int rows = kTileM) {
+inline bool mode_is_tc(int mode) { return mode == FSE_MODE_TC_BF16 || mode == FSE_MODE_TC_TF32; }
+inline bool mode_is_bf16(int mode) { return mode == FSE_MODE_TC_BF16 || mode == FSE_MODE_SIMT_BF16; }
+// widest k-block (in channels) of an operand type: 128 bytes of K per row
+inline int mode_kb(int mode) { return mode_is_bf16(mode) ? 64 : 32; }
+
+// activation [B, T, C] channels-last (bf16, es = 2; fp32 for the tf32 kind, es = 4): dims (C, T, B), box (KB, rows, 1);
+// out-of-range frames/channels read 0.
+inline int make_map_act(CUtensorMap* m, const void* ptr, int C, int T, int B, int KB, int rows = kTileM, int es = 2) {
   PFN_tmapEncodeTiled enc;
   FSE_TRY(get_encode_fn(&enc));
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(B)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(T) * C * 2};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(C) * es, static_cast<cuuint64_t>(T) * C * es};
   cuuint32_t box[3] = {static_cast<cuuint32_t>(KB), static_cast<cuuint32_t>(rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+  CUresult r = enc(m, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, KB * es == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(FSE_ECUDA, "cuTensorMapEncodeTiled(act C=%d T=%d B=%d) failed: %d", C, T, B, (int)r);
   return FSE_OK;
 }
-// bf16 packed weight [N, Kp] row-major (K contiguous): dims (Kp, N), box (KB, BN).
-inline int make_map_w(CUtensorMap* m, const void* ptr, int Kp, int N, int KB, int BN) {
+// packed weight [N, Kp] row-major (K contiguous; bf16 or fp32): dims (Kp, N), box (KB, BN).
+inline int make_map_w(CUtensorMap* m, const void* ptr, int Kp, int N, int KB, int BN, int es = 2) {
   PFN_tmapEncodeTiled enc;
   FSE_TRY(get_encode_fn(&enc));
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(Kp), static_cast<cuuint64_t>(N)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(Kp) * 2};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(Kp) * es};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(KB), static_cast<cuuint32_t>(BN)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+  CUresult r = enc(m, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, KB * es == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(FSE_ECUDA, "cuTensorMapEncodeTiled(w Kp=%d N=%d) failed: %d", Kp, N, (int)r);
   return FSE_OK;
@@ -184,6 +209,14 @@ struct LaunchCtx {
   int kind = 0;
 };
 
+constexpr int kMaxDevices = 64;
+inline int device_sm_count(int dev) {
+  static int sms[kMaxDevices] = {};
+  if (dev < 0 || dev >= kMaxDevices) return 0;
+  if (sms[dev] == 0 && cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms[dev] = 0;
+  return sms[dev];
+}
+
 // ------------------------------------------------------------------ conv_gemm launcher
 struct GemmOperands {
   const void* A0 = nullptr;   // [B, Tsrc, C0] operand type
@@ -222,46 +255,46 @@ inline bool enable_shared_a(ConvGemmParams& p, int MT = 1) {
     box = ((need + nload - 1) / nload + 7) / 8 * 8;       // boxes start on a swizzle-atom boundary (8 rows)
     if (box <= 256) break;
   }
-  if (static_cast<size_t>(box) * nload * p.KB * 2 > 100 * 1024) return false;     // two slots must fit next to the weight ring
+  if (static_cast<size_t>(box) * nload * 128 > 100 * 1024) return false;     // two slots (<= 128-byte rows) must fit next to the weight ring
   p.shared_a = 1; p.MT = MT; p.off_min = lo; p.Rrows = need; p.Rbox = box; p.nload = nload; p.bo_mode = 0;
   return true;
 }
 
-template <int KB, int CH, class Epi>
+template <typename TOp, int KB, int CH, class Epi>
 inline int launch_tc(const ConvGemmParams& p, const GemmOperands& op, const Epi& epi, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set[kMaxDevices] = {};       // per device ordinal: function attributes are per context
+  int dev = 0;
+  FSE_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return fail(FSE_EINVAL, "device ordinal %d out of range", dev);
+  constexpr int RB = KB * static_cast<int>(sizeof(TOp));
   const int nkb = p.ntaps * p.nkb0 + p.nkb1;
   int stages, a_slots, a_slot_bytes;
   constexpr int scratch = (CH == 32 && epi_transposed<Epi>::value) ? kEpiScratchBytes : 0;
   const int budget = 225 * 1024 - scratch;
   if (p.shared_a) {
     const int rows = p.Rbox * p.nload > kTileM ? p.Rbox * p.nload : kTileM;
-    a_slot_bytes = static_cast<int>(align_up(static_cast<size_t>(rows) * KB * 2, 1024));
+    a_slot_bytes = static_cast<int>(align_up(static_cast<size_t>(rows) * RB, 1024));
     a_slots = p.nkb0 + p.nkb1 < 2 ? 2 : (p.nkb0 + p.nkb1 < 3 ? p.nkb0 + p.nkb1 : 3);   // >= 2: the next job's load overlaps this job's MMAs
-    while (a_slots > 2 && budget - a_slots * a_slot_bytes < 3 * tc_b_stage_bytes(op.BN, KB)) --a_slots;
-    stages = (budget - a_slots * a_slot_bytes) / tc_b_stage_bytes(op.BN, KB);
+    while (a_slots > 2 && budget - a_slots * a_slot_bytes < 3 * tc_b_stage_bytes(op.BN, RB)) --a_slots;
+    stages = (budget - a_slots * a_slot_bytes) / tc_b_stage_bytes(op.BN, RB);
     if (stages > 8) stages = 8;
   } else {
-    a_slot_bytes = tc_a_stage_bytes(KB) * (p.MT > 0 ? p.MT : 1);
-    stages = budget / (a_slot_bytes + tc_b_stage_bytes(op.BN, KB));
+    a_slot_bytes = tc_a_stage_bytes(RB) * (p.MT > 0 ? p.MT : 1);
+    stages = budget / (a_slot_bytes + tc_b_stage_bytes(op.BN, RB));
     if (stages > 6) stages = 6;
     a_slots = 0;   // = stages, set below
   }
   if (stages > nkb) stages = nkb;
   if (stages < 1) return fail(FSE_EINVAL, "conv_gemm: tile does not fit shared memory");
   if (!p.shared_a) a_slots = stages;
-  auto kern = conv_gemm_tc_kernel<KB, CH, Epi>;
-  if (!attr_set) {
+  auto kern = conv_gemm_tc_kernel<TOp, KB, CH, Epi>;
+  if (!attr_set[dev]) {
     FSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_set[dev] = true;
   }
-  const size_t smem = tc_smem_bytes(op.BN, KB, stages, a_slots, a_slot_bytes, scratch);
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    FSE_CUDA(cudaGetDevice(&dev));
-    FSE_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const size_t smem = tc_smem_bytes(op.BN, RB, stages, a_slots, a_slot_bytes, scratch);
+  const int num_sms = device_sm_count(dev);
+  if (num_sms <= 0) return fail(FSE_ECUDA, "cannot query the SM count of device %d", dev);
   const int tile_rows = kTileM * (p.MT > 0 ? p.MT : 1);
   const int total_tiles = p.B * ((p.Trows + tile_rows - 1) / tile_rows) * (p.N / op.BN);
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);   // persistent: one CTA per SM
@@ -289,11 +322,24 @@ inline int run_conv_gemm_impl(int mode, const ConvGemmParams& p, const GemmOpera
       if (p.N % op.BN != 0 || op.BN % 16 != 0 || op.BN > 256) return fail(FSE_EINVAL, "conv_gemm: bad BN %d for N %d", op.BN, p.N);
       if (!op.mA0 || !op.mW) return fail(FSE_ESTATE, "conv_gemm: tensor maps missing");
       if (p.KB == 64) {
-        if (op.BN % 32 == 0) return launch_tc<64, 32, Epi>(p, op, epi, st);
-        return launch_tc<64, 16, Epi>(p, op, epi, st);
+        if (op.BN % 32 == 0) return launch_tc<TOp, 64, 32, Epi>(p, op, epi, st);
+        return launch_tc<TOp, 64, 16, Epi>(p, op, epi, st);
       } else {
-        if (op.BN % 32 == 0) return launch_tc<32, 32, Epi>(p, op, epi, st);
-        return launch_tc<32, 16, Epi>(p, op, epi, st);
+        if (op.BN % 32 == 0) return launch_tc<TOp, 32, 32, Epi>(p, op, epi, st);
+        return launch_tc<TOp, 32, 16, Epi>(p, op, epi, st);
+      }
+    }
+  } else {
+    if (mode == FSE_MODE_TC_TF32) {        // fp32 operands on the tensor cores (kind::tf32): k-blocks of 32 (128 B) or 16 (64 B) channels
+      if (p.N % op.BN != 0 || op.BN % 16 != 0 || op.BN > 256) return fail(FSE_EINVAL, "conv_gemm: bad BN %d for N %d", op.BN, p.N);
+      if (!op.mA0 || !op.mW) return fail(FSE_ESTATE, "conv_gemm: tensor maps missing");
+      if (p.KB != 32 && p.KB != 16) return fail(FSE_EINVAL, "conv_gemm(tf32): k-block must be 32 or 16 channels, got %d", p.KB);
+      if (p.KB == 32) {
+        if (op.BN % 32 == 0) return launch_tc<TOp, 32, 32, Epi>(p, op, epi, st);
+        return launch_tc<TOp, 32, 16, Epi>(p, op, epi, st);
+      } else {
+        if (op.BN % 32 == 0) return launch_tc<TOp, 16, 32, Epi>(p, op, epi, st);
+        return launch_tc<TOp, 16, 16, Epi>(p, op, epi, st);
       }
     }
   }

@@ -182,7 +182,7 @@ using namespace fse;
 
 struct fse_vocoder {
   fse_vocoder_config cfg{};
-  bool bf16 = true, loaded = false;
+  bool bf16 = true, tc = true, loaded = false;     // operand type / tensor-core back end (fse_common.cuh: mode_is_bf16, mode_is_tc)
   int hop = 1;
   ConvW pre;
   std::vector<ConvW> ups;
@@ -256,9 +256,9 @@ std::vector<float> fold_wn(const TensorTable& tt, const std::string& name, int64
 }
 
 int finish_convw(fse_vocoder* h, ConvW& cw, const std::vector<float>& packed, const float* bias, int nbias) {
-  FSE_TRY(upload_operand(packed, h->bf16, &cw.W));
+  FSE_TRY(upload_operand(packed, h->bf16, &cw.W, h->cfg.mode == FSE_MODE_TC_TF32));
   FSE_TRY(upload_f32(std::vector<float>(bias, bias + nbias), &cw.bias));
-  if (h->cfg.mode == FSE_MODE_TC_BF16) FSE_TRY(make_map_w(&cw.map, cw.W, cw.Kp, cw.N, cw.KB, cw.BN));
+  if (h->tc) FSE_TRY(make_map_w(&cw.map, cw.W, cw.Kp, cw.N, cw.KB, cw.BN, h->bf16 ? 2 : 4));
   return FSE_OK;
 }
 
@@ -270,7 +270,8 @@ int pack_conv(fse_vocoder* h, const TensorTable& tt, const std::string& name, in
   const float* bias = tt.get(name + ".bias", Cout, &rc);
   if (rc) return rc;
   if (k > kMaxTaps || k % 2 == 0) return fail(FSE_EINVAL, "%s: kernel size %d unsupported", name.c_str(), k);
-  cw.Cin = Cin; cw.N = Cout; cw.ntaps = k; cw.KB = Cin % 64 == 0 || Cin > 64 ? 64 : 32;
+  const int kbw = mode_kb(h->cfg.mode);           // widest k-block of the operand type (128-byte rows), else half of it
+  cw.Cin = Cin; cw.N = Cout; cw.ntaps = k; cw.KB = Cin % kbw == 0 || Cin > kbw ? kbw : kbw / 2;
   const int nkb = (Cin + cw.KB - 1) / cw.KB;
   cw.Kp = k * nkb * cw.KB;
   cw.BN = Cout <= 256 ? Cout : 256;
@@ -291,9 +292,10 @@ int pack_up(fse_vocoder* h, const TensorTable& tt, const std::string& name, int 
   if (rc) return rc;
   const int ntaps = (k + u - 1) / u;
   if (ntaps > kMaxTaps) return fail(FSE_EINVAL, "%s: too many taps", name.c_str());
-  cw.Cin = Cin; cw.N = u * Cout; cw.ntaps = ntaps; cw.KB = 64;
-  const int nkb = (Cin + 63) / 64;
-  cw.Kp = ntaps * nkb * 64;
+  const int KB = mode_kb(h->cfg.mode);
+  cw.Cin = Cin; cw.N = u * Cout; cw.ntaps = ntaps; cw.KB = KB;
+  const int nkb = (Cin + KB - 1) / KB;
+  cw.Kp = ntaps * nkb * KB;
   cw.BN = cw.N % 256 == 0 ? 256 : (cw.N % 128 == 0 ? 128 : (cw.N % 64 == 0 ? 64 : 32));
   for (int m = 0; m < ntaps; ++m) cw.offs[m] = -m;
   std::vector<float> p(static_cast<size_t>(cw.N) * cw.Kp, 0.f);
@@ -303,7 +305,7 @@ int pack_up(fse_vocoder* h, const TensorTable& tt, const std::string& name, int 
         const int j = r + m * u;
         if (j >= k) continue;
         for (int ci = 0; ci < Cin; ++ci)
-          p[(static_cast<size_t>(r) * Cout + co) * cw.Kp + m * nkb * 64 + ci] = w[(static_cast<size_t>(ci) * Cout + co) * k + j];
+          p[(static_cast<size_t>(r) * Cout + co) * cw.Kp + m * nkb * KB + ci] = w[(static_cast<size_t>(ci) * Cout + co) * k + j];
       }
   return finish_convw(h, cw, p, bias, Cout);
 }
@@ -312,10 +314,11 @@ int pack_up(fse_vocoder* h, const TensorTable& tt, const std::string& name, int 
 int get_act_map(fse_vocoder* h, const void* buf, int C, int T, int B, int KB, int rows, const CUtensorMap** out) {
   for (auto& e : h->plan.cache)
     if (e.buf == buf && e.C == C && e.T == T && e.KB == KB && e.rows == rows) { *out = &e.map; return FSE_OK; }
+  if (h->plan.cache.size() > 256) h->plan.cache.clear();     // caller-owned operands (fp32 mel) may move between calls
   h->plan.cache.emplace_back();
   auto& e = h->plan.cache.back();
   e.buf = buf; e.C = C; e.T = T; e.KB = KB; e.rows = rows;
-  FSE_TRY(make_map_act(&e.map, buf, C, T, B, KB, rows));
+  FSE_TRY(make_map_act(&e.map, buf, C, T, B, KB, rows, h->bf16 ? 2 : 4));
   *out = &e.map;
   return FSE_OK;
 }
@@ -324,7 +327,7 @@ template <typename TOp, class Epi>
 int run_conv(fse_vocoder* h, const ConvW& cw, const void* A, int B, int Trows, int Tsrc, const Epi& epi, cudaStream_t st, int kind) {
   ConvGemmParams p = make_params(B, Trows, Tsrc, cw.Cin, cw.ntaps, cw.offs, 0, cw.N, cw.KB);
   GemmOperands op; op.A0 = A; op.W = cw.W; op.mW = &cw.map; op.BN = cw.BN;
-  if (h->cfg.mode == FSE_MODE_TC_BF16) {
+  if (h->tc) {
     // every tap of a conv reads the same activation tile shifted by whole frames: load it once per channel block
     // (with the tap halo) and feed the taps from row-shifted descriptors -> activation ingest / ntaps
     // narrow layers (C_out <= 128, one n-tile): one job = several 128-frame sub-tiles against the same weight tiles
@@ -345,7 +348,7 @@ template <typename TOp>
 int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, void* ws, cudaStream_t st) {
   VWs w = vcarve(h, ws, B, T);
   const auto& cfg = h->cfg;
-  const bool tc = cfg.mode == FSE_MODE_TC_BF16;
+  const bool tc = h->tc;
   const int nu = cfg.num_upsamples, nk = cfg.num_kernels;
   if (tc && !(h->plan.ws == ws && h->plan.B == B && h->plan.T == T)) {
     h->plan.cache.clear();
@@ -428,7 +431,7 @@ int fse_vocoder_create(const fse_vocoder_config* cfg, fse_vocoder** out) {
   if (cfg->num_upsamples <= 0 || cfg->num_upsamples > 8 || cfg->num_kernels <= 0 || cfg->num_kernels > 4)
     return fail(FSE_EINVAL, "num_upsamples / num_kernels out of range");
   if (cfg->n_mels % 8 != 0) return fail(FSE_EINVAL, "n_mels must be a multiple of 8");
-  if (cfg->mode < 0 || cfg->mode > 2) return fail(FSE_EINVAL, "unknown mode %d", cfg->mode);
+  if (cfg->mode < 0 || cfg->mode > 3) return fail(FSE_EINVAL, "unknown mode %d", cfg->mode);
   int hop = 1;
   for (int i = 0; i < cfg->num_upsamples; ++i) {
     const int u = cfg->upsample_rates[i], k = cfg->upsample_kernel_sizes[i];
@@ -444,7 +447,8 @@ int fse_vocoder_create(const fse_vocoder_config* cfg, fse_vocoder** out) {
   if (prop.major != 10) return fail(FSE_ECUDA, "device is sm_%d%d; this library is built for sm_100a only (no fallback)", prop.major, prop.minor);
   auto* h = new fse_vocoder();
   h->cfg = *cfg;
-  h->bf16 = cfg->mode != FSE_MODE_SIMT_F32;
+  h->bf16 = mode_is_bf16(cfg->mode);
+  h->tc = mode_is_tc(cfg->mode);
   h->hop = hop;
   if (const char* e = getenv("FSE_VOC_SHARED_A")) h->shared_a = atoi(e) != 0;
   if (const char* e = getenv("FSE_VOC_MT")) { h->multi_tile = atoi(e) != 0; h->multi_tile_level = atoi(e); }

@@ -88,7 +88,7 @@ struct fse_mel_encoder {
   fse_mel_encoder_config cfg{};
   bool bf16 = true, loaded = false;
   Layer l[3];
-  struct Plan { const void* ws = nullptr; int B = 0, T = 0; CUtensorMap mx{}, m1{}, m2{}; } plan;
+  struct Plan { const void* ws = nullptr; const void* x = nullptr; int B = 0, T = 0; CUtensorMap mx{}, m1{}, m2{}; } plan;
   long long launches = 0;
 };
 
@@ -115,13 +115,14 @@ int pack_linear(fse_mel_encoder* h, const TensorTable& tt, const std::string& na
   if (rc) return rc;
   const float* b = tt.get(name + ".bias", N, &rc);
   if (rc) return rc;
-  L.Cin = Cin; L.N = N; L.Kp = (Cin + 63) / 64 * 64; L.BN = N;
+  const int KB = mode_kb(h->cfg.mode);
+  L.Cin = Cin; L.N = N; L.Kp = (Cin + KB - 1) / KB * KB; L.BN = N;
   std::vector<float> p(static_cast<size_t>(N) * L.Kp, 0.f);
   for (int o = 0; o < N; ++o)
     for (int c = 0; c < Cin; ++c) p[static_cast<size_t>(o) * L.Kp + c] = w[static_cast<size_t>(o) * Cin + c];
-  FSE_TRY(upload_operand(p, h->bf16, &L.W));
+  FSE_TRY(upload_operand(p, h->bf16, &L.W, h->cfg.mode == FSE_MODE_TC_TF32));
   FSE_TRY(upload_f32(std::vector<float>(b, b + N), &L.bias));
-  if (h->cfg.mode == FSE_MODE_TC_BF16) FSE_TRY(make_map_w(&L.map, L.W, L.Kp, N, 64, L.BN));
+  if (mode_is_tc(h->cfg.mode)) FSE_TRY(make_map_w(&L.map, L.W, L.Kp, N, KB, L.BN, h->bf16 ? 2 : 4));
   return FSE_OK;
 }
 
@@ -129,13 +130,14 @@ template <typename TOp>
 int forward_impl(fse_mel_encoder* h, const float* x, const float* add, const float* scale, float* out, int B, int T, void* ws, cudaStream_t st) {
   MWs w = mcarve(h, ws, B, T);
   const int M = h->cfg.n_mels, H = h->cfg.hidden, mode = h->cfg.mode;
-  const bool tc = mode == FSE_MODE_TC_BF16;
-  const int zero = 0;
-  if (tc && !(h->plan.ws == ws && h->plan.B == B && h->plan.T == T)) {
-    FSE_TRY(make_map_act(&h->plan.mx, w.xb, M, T, B, 64));
-    FSE_TRY(make_map_act(&h->plan.m1, w.a1, H, T, B, 64));
-    FSE_TRY(make_map_act(&h->plan.m2, w.a2, H, T, B, 64));
-    h->plan.ws = ws; h->plan.B = B; h->plan.T = T;
+  const bool tc = mode_is_tc(mode);
+  const int zero = 0, KB = mode_kb(mode), es = h->bf16 ? 2 : 4;
+  const void* x_src = h->bf16 ? w.xb : static_cast<const void*>(x);       // fp32 operands: the caller's tensor is the operand
+  if (tc && !(h->plan.ws == ws && h->plan.B == B && h->plan.T == T && h->plan.x == x_src)) {
+    FSE_TRY(make_map_act(&h->plan.mx, x_src, M, T, B, KB, kTileM, es));
+    FSE_TRY(make_map_act(&h->plan.m1, w.a1, H, T, B, KB, kTileM, es));
+    FSE_TRY(make_map_act(&h->plan.m2, w.a2, H, T, B, KB, kTileM, es));
+    h->plan.ws = ws; h->plan.B = B; h->plan.T = T; h->plan.x = x_src;
   }
   const void* x_op = x;
   if constexpr (std::is_same<TOp, __nv_bfloat16>::value) {
@@ -146,19 +148,19 @@ int forward_impl(fse_mel_encoder* h, const float* x, const float* add, const flo
     x_op = w.xb;
   }
   {
-    ConvGemmParams p = make_params(B, T, T, M, 1, &zero, 0, H, 64);
+    ConvGemmParams p = make_params(B, T, T, M, 1, &zero, 0, H, KB);
     GemmOperands op; op.A0 = x_op; op.W = h->l[0].W; op.mA0 = &h->plan.mx; op.mW = &h->l[0].map; op.BN = h->l[0].BN;
     EpiRelu<TOp> epi{h->l[0].bias, static_cast<TOp*>(w.a1), H, T};
     FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, nullptr, 0})));
   }
   {
-    ConvGemmParams p = make_params(B, T, T, H, 1, &zero, 0, H, 64);
+    ConvGemmParams p = make_params(B, T, T, H, 1, &zero, 0, H, KB);
     GemmOperands op; op.A0 = w.a1; op.W = h->l[1].W; op.mA0 = &h->plan.m1; op.mW = &h->l[1].map; op.BN = h->l[1].BN;
     EpiRelu<TOp> epi{h->l[1].bias, static_cast<TOp*>(w.a2), H, T};
     FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, nullptr, 0})));
   }
   {
-    ConvGemmParams p = make_params(B, T, T, H, 1, &zero, 0, H, 64);
+    ConvGemmParams p = make_params(B, T, T, H, 1, &zero, 0, H, KB);
     GemmOperands op; op.A0 = w.a2; op.W = h->l[2].W; op.mA0 = &h->plan.m2; op.mW = &h->l[2].map; op.BN = h->l[2].BN;
     EpiCond epi{h->l[2].bias, add, scale, out, H, T};
     FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, nullptr, 0})));
@@ -172,7 +174,7 @@ extern "C" {
 
 int fse_mel_encoder_create(const fse_mel_encoder_config* cfg, fse_mel_encoder** out) {
   if (!cfg || !out) return fail(FSE_EINVAL, "null argument");
-  if (cfg->mode < 0 || cfg->mode > 2) return fail(FSE_EINVAL, "unknown mode %d", cfg->mode);
+  if (cfg->mode < 0 || cfg->mode > 3) return fail(FSE_EINVAL, "unknown mode %d", cfg->mode);
   if (cfg->n_mels <= 0 || cfg->n_mels % 8 != 0) return fail(FSE_EINVAL, "n_mels must be a positive multiple of 8");
   if (cfg->hidden <= 0 || cfg->hidden % 32 != 0 || cfg->hidden > 256) return fail(FSE_EINVAL, "hidden must be a multiple of 32, <= 256");
   int dev = 0;
@@ -182,7 +184,7 @@ int fse_mel_encoder_create(const fse_mel_encoder_config* cfg, fse_mel_encoder** 
   if (prop.major != 10) return fail(FSE_ECUDA, "device is sm_%d%d; this library is built for sm_100a only (no fallback)", prop.major, prop.minor);
   auto* h = new fse_mel_encoder();
   h->cfg = *cfg;
-  h->bf16 = cfg->mode != FSE_MODE_SIMT_F32;
+  h->bf16 = mode_is_bf16(cfg->mode);
   *out = h;
   return FSE_OK;
 }

@@ -252,17 +252,18 @@ inline int load_ln(LayerCtx* ctx, const TensorTable& tt, const std::string& name
 inline int pack_conv_raw(LayerCtx* ctx, const std::string& name, const float* w, const float* bias, int Cout, int Cin, int k, const int* offs,
                          ConvW& cw) {
   if (k > kMaxTaps || k < 1) return fail(FSE_EINVAL, "%s: %d taps unsupported (1..%d)", name.c_str(), k, kMaxTaps);
-  cw.Cin = Cin; cw.N = Cout; cw.ntaps = k; cw.KB = 64;
-  const int nkb = (Cin + 63) / 64;
-  cw.Kp = k * nkb * 64;
+  const int KB = mode_kb(ctx->mode);                  // 128 bytes of K per row: 64 bf16 or 32 fp32 (tf32) channels
+  cw.Cin = Cin; cw.N = Cout; cw.ntaps = k; cw.KB = KB;
+  const int nkb = (Cin + KB - 1) / KB;
+  cw.Kp = k * nkb * KB;
   cw.BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : (Cout % 32 == 0 ? 32 : (Cout % 16 == 0 && Cout <= 256 ? Cout : 0))));
   if (cw.BN == 0) return fail(FSE_EINVAL, "%s: %d output channels is not a multiple of 16", name.c_str(), Cout);
   for (int j = 0; j < k; ++j) cw.offs[j] = offs[j];
   std::vector<float> p(static_cast<size_t>(Cout) * cw.Kp, 0.f);
   for (int o = 0; o < Cout; ++o)
     for (int c = 0; c < Cin; ++c)
-      for (int j = 0; j < k; ++j) p[static_cast<size_t>(o) * cw.Kp + j * nkb * 64 + c] = w[(static_cast<size_t>(o) * Cin + c) * k + j];
-  FSE_TRY(upload_operand(p, ctx->bf16, &cw.W));
+      for (int j = 0; j < k; ++j) p[static_cast<size_t>(o) * cw.Kp + j * nkb * KB + c] = w[(static_cast<size_t>(o) * Cin + c) * k + j];
+  FSE_TRY(upload_operand(p, ctx->bf16, &cw.W, ctx->mode == FSE_MODE_TC_TF32));
   ctx->owned.push_back(cw.W);
   if (bias) {
     FSE_TRY(dev_f32(ctx, bias, Cout, &cw.bias));
@@ -270,7 +271,7 @@ inline int pack_conv_raw(LayerCtx* ctx, const std::string& name, const float* w,
     std::vector<float> z(Cout, 0.f);
     FSE_TRY(dev_f32(ctx, z.data(), Cout, &cw.bias));
   }
-  if (ctx->mode == FSE_MODE_TC_BF16) FSE_TRY(make_map_w(&cw.map, cw.W, cw.Kp, cw.N, cw.KB, cw.BN));
+  if (mode_is_tc(ctx->mode)) FSE_TRY(make_map_w(&cw.map, cw.W, cw.Kp, cw.N, cw.KB, cw.BN, ctx->bf16 ? 2 : 4));
   return FSE_OK;
 }
 // Conv1d(k, dilation dil) from a state_dict: "same" padding (tap j at (j - (k-1)/2) dil) or, with left = true, the causal
@@ -295,7 +296,7 @@ inline int get_act_map(LayerCtx* ctx, const void* buf, int C, int T, int B, int 
   ctx->cache.emplace_back();
   auto& e = ctx->cache.back();
   e.buf = buf; e.C = C; e.T = T; e.B = B; e.KB = KB;
-  const int rc = make_map_act(&e.map, buf, C, T, B, KB);
+  const int rc = make_map_act(&e.map, buf, C, T, B, KB, kTileM, ctx->bf16 ? 2 : 4);
   if (rc != FSE_OK) { ctx->cache.pop_back(); return rc; }
   *out = &e.map;
   return FSE_OK;
@@ -306,7 +307,7 @@ template <typename TOp, class Epi>
 inline int run_conv(LayerCtx* ctx, const ConvW& cw, const void* A, int B, int T, const Epi& epi, cudaStream_t st) {
   ConvGemmParams p = make_params(B, T, T, cw.Cin, cw.ntaps, cw.offs, 0, cw.N, cw.KB);
   GemmOperands op; op.A0 = A; op.W = cw.W; op.mW = &cw.map; op.BN = cw.BN;
-  if (ctx->mode == FSE_MODE_TC_BF16) FSE_TRY(get_act_map(ctx, A, cw.Cin, T, B, cw.KB, &op.mA0));
+  if (mode_is_tc(ctx->mode)) FSE_TRY(get_act_map(ctx, A, cw.Cin, T, B, cw.KB, &op.mA0));
   return run_conv_gemm<TOp>(ctx->mode, p, op, epi, st, LaunchCtx{&ctx->launches, nullptr, 0});
 }
 

@@ -159,7 +159,7 @@ def test_whole_model_text_to_mel_vs_reference_fixture(lib_built):
     seed, B, T, S, L, vocab = (int(g[k]) for k in ("seed", "B", "T", "S", "layers", "vocab"))
     batch = synth.pad_edit_batch(synth.synthetic_edit_batch(seed, B, T, vocab=vocab), item=1, n_tokens=3)
     noise = synth.synthetic_noise(seed + 5, S, B, T)
-    for mode, tol in (("simt_f32", None), ("tc_bf16", 3e-2)):
+    for mode, tol in (("simt_f32", None), ("tc_bf16", 3e-2), ("tc_tf32", 4e-3)):
         model = plugin.build_diffusion(dict(HP, timesteps=S, residual_layers=L, b200_mode=mode), phone_encoder=list(range(vocab)))
         assert isinstance(model.fs, FastSpeechB200) and isinstance(model.mel_encoder, MelEncoderB200)
         model.fs.load_state_dict({k: torch.from_numpy(v) for k, v in synth.fastspeech_state_dict(seed, vocab).items()}, strict=False)
@@ -174,6 +174,7 @@ def test_whole_model_text_to_mel_vs_reference_fixture(lib_built):
             assert np.abs(cond - g["decoder_inp"]).max() < 5e-4
             assert np.abs(mel - g["mel_out"]).max() < 2e-3
         else:
+            print(f"[margin] text -> mel {mode}: decoder_inp rel-L1 {rel_l1(cond, g['decoder_inp']):.3e}, mel rel-L1 {rel_l1(mel, g['mel_out']):.3e}")
             assert rel_l1(cond, g["decoder_inp"]) < tol
             assert rel_l1(mel, g["mel_out"]) < tol
 
