@@ -7,7 +7,11 @@ numpy restatement of inference/tts/spec_denoiser.py:88-131 (reference tree, Zain
 one utterance (the reference runs batch 1):
   :88-91   masked_dur: durations of the phones before / after the edited word span
   :94-97   masked mel2ph / time mask of the original frames inside the span
-  :99      edited_mel2word = edited_ph2word[edited_mel2ph - 1]
+  :99      # Deliberate divergence for PADDING: a predicted phone index 0 (a padded frame of a B > 1 batch; the reference runs batch 1, where
+    # LengthRegulator emits no zeros) maps to word 0, i.e. to no word, instead of Python's negative-index wrap to the LAST word
+    # (`edited_ph2word[-1]`), which would pull padding frames into the edited span whenever that span ends the utterance.  For
+    # every index >= 1 this is the reference expression edited_ph2word[p - 1] (:99); the device core does the same.
+    edited_mel2word = np.where(edited_mel2ph >= 1, edited_ph2word[np.maximum(edited_mel2ph, 1) - 1], 0)
   :100-110 length_edited, head_idx, tail_idx, edited_mel2ph_ (head copy, edited span, tail re-based by
            - min(tail) + max(edited span) + 2)
   :117-131 ref_mels / f0 / uv head + tail copies, time_mel_masks
@@ -41,7 +45,11 @@ def assemble(mel2ph, mel2word, edited_ph2word, edited_mel2ph, words_region, edit
     """:99-131 -> dict(mel2ph [Tn] int64, ref_mels [Tn,M], f0 [Tn], uv [Tn], time_mel_masks [Tn], plan=(Tn, head_idx, tail_idx, length_edited))."""
     w0, w1 = words_region
     c0, c1 = edited_words_region
-    edited_mel2word = edited_ph2word[edited_mel2ph - 1]
+    # Deliberate divergence for PADDING: a predicted phone index 0 (a padded frame of a B > 1 batch; the reference runs batch 1, where
+    # LengthRegulator emits no zeros) maps to word 0, i.e. to no word, instead of Python's negative-index wrap to the LAST word
+    # (`edited_ph2word[-1]`), which would pull padding frames into the edited span whenever that span ends the utterance.  For
+    # every index >= 1 this is the reference expression edited_ph2word[p - 1] (:99); the device core does the same.
+    edited_mel2word = np.where(edited_mel2ph >= 1, edited_ph2word[np.maximum(edited_mel2ph, 1) - 1], 0)
     sel_edit = (edited_mel2word >= c0) & (edited_mel2word <= c1)
     region = (mel2word >= w0) & (mel2word <= w1)
     length_edited = int(sel_edit.sum()) - int(region.sum())

@@ -34,8 +34,19 @@ def extract_state_dict(checkpoint: dict, model_name: str = "model") -> dict:
     return {k[len(rest) + 1:]: v for k, v in sd[base].items() if k.startswith(f"{rest}.")}
 
 
-def load_ckpt(cur_model, ckpt_base_dir, model_name="model", force=True, strict=True):
-    """Same call as the reference's load_ckpt: newest checkpoint of a directory (or a file) into `cur_model`."""
+# buffers of GaussianDiffusion whose LENGTH is timesteps + 1 (spec_denoiser.py:47-69): a checkpoint trained with timesteps = 8 cannot be
+# strict-loaded into a 100-step model; they are functions of `timesteps` alone and are rebuilt by the module.
+SCHEDULE_BUFFERS = ("timesteps", "betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+                    "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_variance",
+                    "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2")
+
+
+def load_ckpt(cur_model, ckpt_base_dir, model_name="model", force=True, strict=True, drop_keys=()):
+    """Same call and behaviour as the reference's load_ckpt (utils/commons/ckpt_utils.py:26-66): newest checkpoint of a directory (or a
+    file) into `cur_model`; strict by default; a missing checkpoint is an error when `force`; in non-strict mode shape-mismatched keys
+    are printed and dropped, and the keys `load_state_dict` reports as missing / unexpected are printed too (never silent).
+    `drop_keys` (an addition): names removed from the checkpoint before loading — pass SCHEDULE_BUFFERS to load a checkpoint trained with
+    another `timesteps` strictly in everything else."""
     if os.path.isfile(ckpt_base_dir):
         ckpt_path, checkpoint = ckpt_base_dir, torch.load(ckpt_base_dir, map_location="cpu", weights_only=False)
     else:
@@ -46,10 +57,25 @@ def load_ckpt(cur_model, ckpt_base_dir, model_name="model", force=True, strict=T
             raise FileNotFoundError(msg)
         print(msg)
         return None
-    sd = extract_state_dict(checkpoint, model_name)
+    sd = dict(extract_state_dict(checkpoint, model_name))
+    own = cur_model.state_dict()
+    dropped = [k for k in drop_keys if k in sd]
+    for k in dropped:
+        del sd[k]
     if not strict:
-        own = cur_model.state_dict()
-        sd = {k: v for k, v in sd.items() if k in own and own[k].shape == v.shape}
-    cur_model.load_state_dict(sd, strict=strict)
-    print(f"| load '{model_name}' from '{ckpt_path}'.")
+        for k in [k for k, v in sd.items() if k in own and own[k].shape != v.shape]:
+            print("| Unmatched keys: ", k, tuple(own[k].shape), tuple(sd[k].shape))
+            del sd[k]
+        res = cur_model.load_state_dict(sd, strict=False)
+        if res.missing_keys:
+            print("| Missing keys (left at their initial values): ", list(res.missing_keys))
+        if res.unexpected_keys:
+            print("| Unexpected keys (ignored): ", list(res.unexpected_keys))
+    else:
+        res = cur_model.load_state_dict(sd, strict=False)
+        missing = [k for k in res.missing_keys if k not in dropped]
+        if missing or res.unexpected_keys:
+            raise RuntimeError(f"Error(s) in loading state_dict for {type(cur_model).__name__} from '{ckpt_path}': missing keys {missing}, "
+                               f"unexpected keys {list(res.unexpected_keys)}")
+    print(f"| load '{model_name}' from '{ckpt_path}'." + (f" (rebuilt from `timesteps`, not loaded: {dropped})" if dropped else ""))
     return ckpt_path

@@ -347,16 +347,16 @@ int run_fused_layers(fse_denoiser* h, const Workspace& w, int Bc, int b0, int T,
     if (grid > 2 * h->max_clusters[which]) grid = 2 * h->max_clusters[which];
     cfg.gridDim = dim3(grid);
     if (tf32)
-      FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_stream_kernel<true, true>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp));
+      FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_stream_kernel<true, true>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, h->plan.m_u, fp));
     else if (stream)
-      FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_stream_kernel<true, false>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp));
+      FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_stream_kernel<true, false>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, h->plan.m_u, fp));
     else if (h->fused_shared_a)
       FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_layers_kernel<true, true>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp));
     else
       FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_layers_kernel<true, false>, h->plan.m_hb, h->plan.m_hb1, h->plan.m_cond, fp));
   } else if (stream) {
     denoiser_stream_kernel<false, false><<<tiles < h->num_sms ? tiles : h->num_sms, kStreamThreads, kFusedSmemBytes, st>>>(
-        h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp);
+        h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, h->plan.m_u, fp);
   } else {
     denoiser_layers_kernel<false, true><<<tiles < h->num_sms ? tiles : h->num_sms, kTcThreads, kFusedSmemBytes, st>>>(
         h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, fp);
@@ -392,7 +392,8 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
     ConvGemmParams p = make_params(Bc, T, T, M, 1, &zero, 0, C, KB); p.b_off = b0;
     GemmOperands op; op.A0 = w.xb; op.W = h->W_in; op.mA0 = &h->plan.m_xb; op.mW = &h->mW_in; op.BN = 256;
     if (C % 256 != 0) op.BN = C % 128 == 0 ? 128 : 64;
-    EpiIn<TOp> epi{h->b_in, w.h, static_cast<TOp*>(w.hb), C, T};
+    // tf32 streamed kernel: the fp32 operand copy IS the residual stream (hf0 = w.hb), no separate h
+    EpiIn<TOp> epi{h->b_in, (h->fused && mode == FSE_MODE_TC_TF32) ? nullptr : w.h, static_cast<TOp*>(w.hb), C, T};
     FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 0})));
   }
   const int bn2 = (2 * C) % 256 == 0 ? 256 : 128;

@@ -59,13 +59,22 @@ constexpr int kStreamTf32UBytes = 8 * 128 * 128;
 constexpr size_t kStreamTf32SmemBytes = 1024 + kStreamTf32ASlots * kFusedASlotBytes + kStreamTf32WStages * 128 * 128 + kStreamTf32UBytes + kFusedBiasBytes + 256;
 static_assert(kStreamTf32SmemBytes <= 227 * 1024, "tf32 stream kernel: shared memory");
 
-__device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh_acc(float x) { return fmaf(2.0f, sigmoid_acc(2.0f * x), -1.0f); }
+// sigmoid(g) * tanh(f) = (1 - E2) / ((1 + E1) (1 + E2)) with E1 = exp(-g), E2 = exp(-2 f): two ex2 and ONE reciprocal per element at
+// fp32 accuracy (ex2.approx / rcp.approx are good to ~1 ulp); the arguments are clamped where both functions have long saturated in
+// fp32 (|f| > 9 => tanh = +-1, sigmoid(-30) = 9e-14), which keeps every intermediate finite.
+__device__ __forceinline__ float gate_acc(float g, float f) {
+  g = fminf(fmaxf(g, -30.f), 30.f);
+  f = fminf(fmaxf(f, -15.f), 15.f);
+  float e1, e2;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(g * -1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(f * -2.8853900817779268f));
+  return __fdividef(1.0f - e2, (1.0f + e1) * (1.0f + e2));
+}
 
 template <bool kPair, bool kTF32 = false>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_constant__ CUtensorMap mapHb1,
-                       const __grid_constant__ CUtensorMap mapCond, FusedParams p) {
+                       const __grid_constant__ CUtensorMap mapCond, const __grid_constant__ CUtensorMap mapU, FusedParams p) {
   static_assert(kPair || !kTF32, "the tf32 schedule exists for CTA pairs only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -91,7 +100,9 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
   uint64_t* u_full = acc_empty + 2;               // [2]: u k-blocks 0,1 (first gate half) / 2,3 (second half) are in shared memory
   uint64_t* u_empty = u_full + 2;
   uint64_t* pub_bar = u_empty + 1;                // this CTA's epilogue warps have stored their h / hb rows of the item
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pub_bar + 1);
+  uint64_t* ust_full = pub_bar + 1;               // [2]: this CTA's half of the u tile is complete in shared memory -> TMA store to u_all
+  uint64_t* ust_done = ust_full + 2;              // the TMA stores of the item have read the u tile (it may be reused as scratch)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ust_done + 1);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -112,6 +123,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
     ptx::prefetch_tensormap(&mapHb0);
     ptx::prefetch_tensormap(&mapHb1);
     ptx::prefetch_tensormap(&mapCond);
+    ptx::prefetch_tensormap(&mapU);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -121,6 +133,8 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
       for (int i = 0; i < 2; ++i) ptx::mbar_init(&u_full[i], kEpiWarps * kMul);
       ptx::mbar_init(u_empty, 1);
       ptx::mbar_init(pub_bar, kEpiWarps);
+      for (int i = 0; i < 2; ++i) ptx::mbar_init(&ust_full[i], kEpiWarps);
+      ptx::mbar_init(ust_done, 1);
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -289,13 +303,33 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
     //   epilogue stores -> mbarrier.arrive (release.cta)  =>  try_wait (acquire.cta) -> fence.acq_rel.gpu -> atomicAdd
     // (the cumulativity pattern of a grid sync: bar.sync, then ONE thread fences and signals for the whole CTA).
     // The consumers need the flag ~1.7 item periods later, and an item lasts >10x the fence, so the parity wait cannot lap.
+    // The same thread moves the item's gate outputs u (needed later by the folded skip GEMM) from the shared-memory u tile to
+    // u_all with TMA stores: the tile is already in the 128B-swizzled box layout of the tensor map, so the epilogue warps issue
+    // no global store for it at all (they used to spend a quarter of the gate epilogue in the LSU queue on 16-byte row pieces).
     if (lane == 0) {
+      const uint64_t pol = ptx::l2_policy_evict_first();          // write-once data, read once by the skip GEMM after the launch
       int it = 0;
       for (int g = pair0; g < total_items; g += npairs, ++it) {
+        const int l = g / total_units, unit = g - l * total_units;
+        const int tile = kPair ? 2 * unit + static_cast<int>(rank) : unit;
+        const int b = p.b_off + tile / tiles_per_item, t0 = (tile % tiles_per_item) * kTileM;
+        for (int half = 0; half < 2; ++half) {
+          ptx::mbar_wait(&ust_full[half], it & 1);                // epilogue warps: st.shared + fence.proxy.async + arrive
+          if (tile < total_tiles) {
+            for (int j = 0; j < NHB / 2; ++j) {
+              const int kb = half * (NHB / 2) + j;
+              ptx::tma_store_3d(&mapU, sU + kb * 16384, l * kFC + kb * KC, t0, b, pol);      // rows >= T are clipped
+            }
+          }
+        }
+        ptx::bulk_commit_group();
+        ptx::bulk_wait_group_read0();                             // the u tile has been read: scratch of the residual epilogue
+        ptx::mbar_arrive(ust_done);
         ptx::mbar_wait(pub_bar, it & 1);
         __threadfence();
         atomicAdd(p.done + g, static_cast<unsigned int>(kEpiWarps));     // g == l * total_units + unit
       }
+      ptx::bulk_wait_group0();                                    // all u_all writes performed before the CTA retires
     }
     __syncwarp();
   } else {
@@ -377,13 +411,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           if constexpr (kTF32) {
             uint32_t uf[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) uf[j] = __float_as_uint(ptx::round_tf32(sigmoid_acc(y[2 * j]) * tanh_acc(y[2 * j + 1])));
-            if (row_ok) {
-              float* up = reinterpret_cast<float*>(p.u_all) + row * static_cast<size_t>(p.L * kFC) + l * kFC + ucol;
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(up + 4 * j), "r"(uf[4 * j]), "r"(uf[4 * j + 1]), "r"(uf[4 * j + 2]), "r"(uf[4 * j + 3]) : "memory");
-            }
+            for (int j = 0; j < 16; ++j) uf[j] = __float_as_uint(ptx::round_tf32(gate_acc(y[2 * j], y[2 * j + 1])));
             // A operand of the residual GEMM: k-block = 32 fp32 channels, 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
             uint8_t* ub = sU + (ucol >> 5) * 16384 + r * 128;
             const int ch = (ucol & 31) >> 2;             // first of the four 16-byte chunks
@@ -397,13 +425,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           for (int j = 0; j < 8; ++j)
             pk[j] = pack_bf16x2(sigmoid_f<true>(y[4 * j]) * tanh_f<true>(y[4 * j + 1]),
                                 sigmoid_f<true>(y[4 * j + 2]) * tanh_f<true>(y[4 * j + 3]));
-          // u columns [ucol, ucol+16): HBM copy for the folded skip GEMM ...
-          if (row_ok) {
-            __nv_bfloat16* up = p.u_all + row * static_cast<size_t>(p.L * kFC) + l * kFC + ucol;
-            asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(up), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-            asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(up + 8), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
-          }
-          // ... and the A operand of the residual GEMM: K-major, 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
+          // u columns [ucol, ucol+16) -> the A operand of the residual GEMM (and, from there, to u_all by TMA store: publisher warp): K-major, 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
           uint8_t* ub = sU + (ucol >> 6) * 16384 + r * 128;
           const int ch = (ucol & 63) >> 3;               // first of the two 16-byte chunks
           *reinterpret_cast<uint4*>(ub + (((ch) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -425,6 +447,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
         if (lane == 0) {
           arrive_leader(&acc_empty[buf]);
           arrive_leader(&u_full[half]);
+          ptx::mbar_arrive(&ust_full[half]);              // this CTA's own publisher thread stores the half tile to u_all
         }
         if (de) de[half * 2 + 1] = clock64();             // gate epilogue of this half done
       }
@@ -486,7 +509,28 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
         load_h(cb + 1, h1);
         ptx::mbar_wait(&acc_full[buf], (job >> 1) & 1);
         ptx::tc_fence_after();
+        ptx::mbar_wait(ust_done, it & 1);                           // the TMA stores to u_all have read the u tile: it is scratch now
         if (de) de[4] = clock64();
+        if constexpr (kTF32) {
+          // fp32 u tile: this warp owns 4 x 4 KB of it (its rows of four k-blocks) = its whole share of the accumulator, so the
+          // accumulator leaves TMEM in one go and goes back to the MMA warp before any global traffic of this epilogue.
+          float* stgC = stgA + 16384 / 4;                           // k-blocks 2*half2 + 1 and 4 + 2*half2 + 1
+          float* stgD = stgB + 16384 / 4;
+          stage(cb, stgA);
+          stage(cb + 1, stgC);
+          stage(cb + 2, stgB);
+          stage(cb + 3, stgD);
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) arrive_leader(&acc_empty[buf]);            // accumulator drained
+          if (de) de[6] = clock64();
+          load_h(cb + 2, h2);
+          finish(cb, stgA, h0);
+          load_h(cb + 3, h0);
+          finish(cb + 1, stgC, h1);
+          finish(cb + 2, stgB, h2);
+          finish(cb + 3, stgD, h0);
+        } else {
         stage(cb, stgA);
         stage(cb + 1, stgB);
         load_h(cb + 2, h2);
@@ -501,6 +545,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
         if (de) de[6] = clock64();
         finish(cb + 2, stgA, h2);
         finish(cb + 3, stgB, h0);
+        }
         if (lane == 0) ptx::mbar_arrive(pub_bar);                   // (finish ends with __syncwarp) -> publisher warp
         if (de) de[5] = clock64();
       }

@@ -62,7 +62,9 @@ FSE_HD void plan_item(const Item& it, const int64_t* edited_mel2ph, int Te, int3
   int64_t edit_max = 0, tail_min = 0, wmax = 0;
   for (int i = 0; i < Te; ++i) {
     const int64_t ph = edited_mel2ph[i];
-    const int64_t w = (ph >= 1 && ph <= it.Tpe) ? it.edited_ph2word[ph - 1] : 0;       // edited_mel2word (:99)
+    // edited_mel2word (:99).  ph == 0 is a PADDED frame of a B > 1 batch (the reference runs batch 1 and never sees one): it belongs
+    // to no word here, whereas Python's edited_ph2word[p - 1] would wrap to the last word; the oracle restates the same rule.
+    const int64_t w = (ph >= 1 && ph <= it.Tpe) ? it.edited_ph2word[ph - 1] : 0;
     if (w >= it.c0 && w <= it.c1) {
       if (n_edit == 0 || ph > edit_max) edit_max = ph;
       sel_edit[n_edit++] = i;

@@ -88,7 +88,7 @@ struct EpiIn {
     float v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = fmaxf(acc[i] + __ldg(bias + n0 + i), 0.f);
-    st_vec<NV>(h + o, v);
+    if (h) st_vec<NV>(h + o, v);
     st_vec<NV>(hb + o, v);
   }
 };

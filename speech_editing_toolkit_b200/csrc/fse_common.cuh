@@ -245,7 +245,7 @@ inline ConvGemmParams make_params(int B, int Trows, int Tsrc, int C0, int ntaps,
 // plus the tap halo, as nload boxes of Rbox rows) and every (tap, sub-tile) reads a row-shifted descriptor of that copy.
 // The A0 tensor map must be made with rows = p.Rbox.  Measured on B200: the swizzle is a function of the absolute smem
 // address, so a row-shifted start needs NO descriptor base-offset (tools/shared_a_check.py).
-inline bool enable_shared_a(ConvGemmParams& p, int MT = 1) {
+inline bool enable_shared_a(ConvGemmParams& p, int MT = 1, int es = 2) {      // es = bytes per operand element (2: bf16, 4: fp32 / tf32)
   int lo = p.tap_off[0], hi = p.tap_off[0];
   for (int i = 1; i < p.ntaps; ++i) { lo = p.tap_off[i] < lo ? p.tap_off[i] : lo; hi = p.tap_off[i] > hi ? p.tap_off[i] : hi; }
   if (p.ntaps < 2 || MT < 1 || (MT > 1 && p.nkb1 > 0)) return false;
@@ -255,7 +255,7 @@ inline bool enable_shared_a(ConvGemmParams& p, int MT = 1) {
     box = ((need + nload - 1) / nload + 7) / 8 * 8;       // boxes start on a swizzle-atom boundary (8 rows)
     if (box <= 256) break;
   }
-  if (static_cast<size_t>(box) * nload * 128 > 100 * 1024) return false;     // two slots (<= 128-byte rows) must fit next to the weight ring
+  if (static_cast<size_t>(box) * nload * p.KB * es > 100 * 1024) return false;     // two slots must fit next to the weight ring
   p.shared_a = 1; p.MT = MT; p.off_min = lo; p.Rrows = need; p.Rbox = box; p.nload = nload; p.bo_mode = 0;
   return true;
 }

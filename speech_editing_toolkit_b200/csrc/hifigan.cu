@@ -337,7 +337,7 @@ int run_conv(fse_vocoder* h, const ConvW& cw, const void* A, int B, int Trows, i
       else if (h->multi_tile_level >= 2) mt = cw.BN <= 32 ? 8 : (cw.BN <= 64 ? 4 : (cw.BN <= 128 ? 2 : 1));
       else mt = cw.BN <= 32 ? 4 : (cw.BN <= 128 ? 2 : 1);
     }
-    if (h->shared_a && cw.ntaps >= 3 && enable_shared_a(p, mt)) rows = p.Rbox;
+    if (h->shared_a && cw.ntaps >= 3 && enable_shared_a(p, mt, h->bf16 ? 2 : 4)) rows = p.Rbox;
     else p.MT = mt;
     FSE_TRY(get_act_map(h, A, cw.Cin, Tsrc, B, cw.KB, rows, &op.mA0));
   }

@@ -80,8 +80,12 @@ class SpecDenoiserInferB200:
     def build_model(self):
         model = build_diffusion(self.hparams, phone_encoder=None if self._fs is not None else self.ph_encoder, fs=self._fs)
         work_dir = self.hparams.get("work_dir", "")
-        if work_dir and os.path.isdir(work_dir):
-            load_ckpt(model, work_dir, "model", force=False, strict=False)     # schedule buffers depend on `timesteps`
+        if work_dir:
+            # as the reference (inference/tts/spec_denoiser.py:58: load_ckpt(model, work_dir, 'model'), strict, forced): a missing
+            # checkpoint or any missing / unexpected / mis-shaped weight is an error, never a silent random initialisation.  Only
+            # the schedule buffers, whose length is `timesteps` + 1, are exempt (a -hp timesteps=100 run of an 8-step checkpoint).
+            from .ckpt import SCHEDULE_BUFFERS
+            load_ckpt(model, work_dir, "model", force=True, strict=True, drop_keys=SCHEDULE_BUFFERS)
         return model.to(self.device).eval()
 
     def build_vocoder(self):
@@ -127,6 +131,7 @@ class SpecDenoiserInferB200:
         g = lambda k: sample[k].to(dev)
         txt, mel, mel2ph, mel2word = g("edited_txt_tokens"), g("mel"), g("mel2ph"), g("mel2word")
         B = txt.shape[0]
+        lens = {k: (sample[k].to(dev) if torch.is_tensor(sample.get(k)) else sample.get(k)) for k in ("T_len", "Tp_len", "Tpe_len", "Te_len")}
         wr, er = sample["words_region"], sample["edited_words_region"]
         if torch.is_tensor(wr):
             regions = torch.cat([wr.reshape(B, 2), er.reshape(B, 2)], 1).long().to(dev)
@@ -136,12 +141,12 @@ class SpecDenoiserInferB200:
         encoder_out = fs.encoder(txt)
         style = fs.forward_style_embed(g("spk_embed"), None)
         masked_dur, masked_mel2ph, mask_orig = E.edit_prepare(mel2ph, mel2word, g("ph2word"), g("dur"), regions, txt.shape[1],
-                                                               sample.get("T_len"), sample.get("Tp_len"), sample.get("Tpe_len"))
+                                                               lens["T_len"], lens["Tp_len"], lens["Tpe_len"])
         dur_inp = fs.engine().dur_input(encoder_out, None if isinstance(style, int) else style[:, 0], txt)
         ret = {}
         edited_mel2ph = fs.forward_dur(dur_inp, mask_orig, masked_mel2ph, txt, ret, masked_dur=masked_dur, use_pred_mel2ph=True)
-        out = E.edit_assemble(mel2ph, mel2word, g("edited_ph2word"), edited_mel2ph, regions, mel, g("f0"), g("uv"), sample.get("T_len"),
-                              sample.get("Tpe_len"), sample.get("Te_len"))
+        out = E.edit_assemble(mel2ph, mel2word, g("edited_ph2word"), edited_mel2ph, regions, mel, g("f0"), g("uv"), lens["T_len"],
+                              lens["Tpe_len"], lens["Te_len"])
         mask = out["time_mel_masks"][:, :, None]
         res = self.model(txt, time_mel_masks=mask, mel2ph=out["mel2ph"], spk_embed=g("spk_embed"), ref_mels=out["ref_mels"], f0=out["f0"],
                          uv=out["uv"], energy=None, infer=True, use_pred_pitch=True, seed=sample.get("seed"), composite=True)
@@ -197,18 +202,49 @@ class SpeechDenoiserTaskB200:
         wav = self.vocoder(mel)
         return {"mel_out": mel, "wav_out": wav}
 
+    @torch.no_grad()
+    def test(self, samples, gen_dir: Optional[str] = None):
+        """The reference's test loop over a dataloader / iterable of sample dicts (Trainer.evaluate(test=True) ->
+        SpeechEditingBaseTask.test_step, utils/commons/trainer.py:203-251, speech_editing_base.py:151-192): sample -> composite ->
+        vocoder per batch; with `gen_dir` the generated mels / wavs are written as `<item_name>.npy` / `<item_name>.wav` (the
+        reference writes wav + png through a process pool; plots are out of scope).  Returns the list of per-batch outputs."""
+        outs = []
+        if gen_dir:
+            os.makedirs(gen_dir, exist_ok=True)
+        for batch_idx, sample in enumerate(samples):
+            out = self.test_step(sample, batch_idx)
+            outs.append(out)
+            if gen_dir:
+                import numpy as np
+                from scipy.io import wavfile
+                names = sample.get("item_name") or [f"b{batch_idx:04d}_{i}" for i in range(out["mel_out"].shape[0])]
+                sr = int(self.hparams.get("audio_sample_rate", 22050))
+                for i, name in enumerate(names):
+                    np.save(os.path.join(gen_dir, f"{name}.npy"), out["mel_out"][i].cpu().numpy())
+                    wavfile.write(os.path.join(gen_dir, f"{name}.wav"), sr, out["wav_out"][i].cpu().numpy())
+        return outs
+
     @classmethod
     def start(cls):
+        """Without a dataset this is a SYNTHETIC THROUGHPUT RUN (one seeded batch of max_sentences x b200_frames), not the reference's
+        trainer loop; with `-hp b200_test_samples=<file>` (a torch.save'd list of the reference's sample dicts) and `--infer` it
+        runs `test()` over them, which is the part of `tasks/run.py --infer` this drop-in covers."""
         import time
         task = cls()
         hp = task.hparams
         task.build_model()
         if hp.get("work_dir") and os.path.isdir(hp["work_dir"]):
-            load_ckpt(task.model, hp["work_dir"], "model", force=False, strict=False)
+            from .ckpt import SCHEDULE_BUFFERS
+            load_ckpt(task.model, hp["work_dir"], "model", force=True, strict=True, drop_keys=SCHEDULE_BUFFERS)
         else:
             task.model.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in synth.denoiser_state_dict(
                 hp.get("seed", 1234), hp["audio_num_mel_bins"], hp["hidden_size"], hp["residual_channels"], hp["residual_layers"]).items()})
         task.build_vocoder()
+        if hp.get("b200_test_samples"):
+            samples = torch.load(hp["b200_test_samples"], map_location="cpu", weights_only=False)
+            outs = task.test(samples, gen_dir=hp.get("b200_gen_dir") or None)
+            print(f"| B200 spec_denoiser: test loop over {len(outs)} batches done")
+            return outs
         B, T = int(hp.get("max_sentences", 16)), int(hp.get("b200_frames", 1024))
         batch = synth.synthetic_edit_batch(hp.get("seed", 1234), B, T, hp["audio_num_mel_bins"])
         sample = {"cond": torch.from_numpy(synth.synthetic_cond(hp.get("seed", 1234), B, T, hp["hidden_size"])),
@@ -249,7 +285,7 @@ class CampNetTaskB200:
         output = self.model(sample["txt_tokens"], spk_embed=sample.get("spk_embed"), spk_id=sample.get("spk_ids"), mels=sample["mels"],
                             stutter_mel_masks=None, time_mel_masks=time_mel_masks, infer=True)
         output["mel_out"] = output["mel_out_fine"] * time_mel_masks + sample["mels"] * (1 - time_mel_masks)
-        return {}, output
+        return output          # infer=True returns the output dict alone (tasks/speech_editing/campnet.py:77-88; test_step indexes it)
 
     @classmethod
     def start(cls):
@@ -258,7 +294,7 @@ class CampNetTaskB200:
         hp = task.hparams
         model = task.build_tts_model().cuda().eval()
         if hp.get("work_dir") and os.path.isdir(hp["work_dir"]):
-            load_ckpt(model, hp["work_dir"], "model", force=False, strict=False)
+            load_ckpt(model, hp["work_dir"], "model", force=True, strict=True)
         else:
             model.load_state_dict({k: torch.from_numpy(v) for k, v in synth.campnet_state_dict(hp.get("seed", 1234), task.ph_dict_size,
                                                                                              hp["hidden_size"]).items()}, strict=False)
@@ -268,7 +304,7 @@ class CampNetTaskB200:
         task.run_model(sample)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        _, out = task.run_model(sample)
+        out = task.run_model(sample)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         print(f"| B200 CampNet: {B}x{T} frames mask-predict forward in {dt * 1e3:.1f} ms ({B * T / dt:.0f} mel-frames/s); "

@@ -207,6 +207,6 @@ def test_campnet_task_run_model_composites_like_the_reference():
     task.model = fake
     mels = torch.randn(B, T, 80)
     mask = torch.zeros(B, T); mask[:, 2:4] = 1
-    _, out = task.run_model({"txt_tokens": torch.ones(B, 3, dtype=torch.long), "mels": mels, "time_mel_masks": mask})
+    out = task.run_model({"txt_tokens": torch.ones(B, 3, dtype=torch.long), "mels": mels, "time_mel_masks": mask})
     assert seen["time_mel_masks"].shape == (B, T, 1) and seen["infer"] is True and seen["stutter_mel_masks"] is None
     assert torch.equal(out["mel_out"][:, 2:4], fine[:, 2:4]) and torch.equal(out["mel_out"][:, :2], mels[:, :2])
