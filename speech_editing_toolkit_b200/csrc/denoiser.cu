@@ -104,8 +104,9 @@ __global__ void __launch_bounds__(256) x_to_rows_kernel(const float* __restrict_
   }
 }
 // x_S: copy of noise[0] or Philox normals (step id 0); writes x[B,M,T] and xb[B*T,M]
+__global__ void set_seed_kernel(unsigned long long* dst, unsigned long long seed) { *dst = seed; }
 template <typename TOp>
-__global__ void __launch_bounds__(256) init_x_kernel(const float* __restrict__ noise0, unsigned long long seed,
+__global__ void __launch_bounds__(256) init_x_kernel(const float* __restrict__ noise0, const unsigned long long* __restrict__ seedp,
                                                      float* __restrict__ x, TOp* __restrict__ xb, int M, int T) {
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256) init_x_kernel(const float* __restrict__ n
 #pragma unroll
       for (int q = 0; q < 4; ++q) v[q] = noise0[(static_cast<size_t>(b) * M + m + q) * T + t];
     } else {
-      philox_normal4(seed, 0u, static_cast<uint32_t>(row), static_cast<uint32_t>(m >> 2), v);
+      philox_normal4(__ldg(seedp), 0u, static_cast<uint32_t>(row), static_cast<uint32_t>(m >> 2), v);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) x[(static_cast<size_t>(b) * M + m + q) * T + t] = v[q];
@@ -207,6 +208,18 @@ struct fse_denoiser {
     CUtensorMap m_hb1{};                        // 128-row box of the second hb buffer
   } plan;
   long long launches = 0;
+  unsigned long long* d_seed = nullptr;     // Philox seed of the current fse_sample call (device memory: graph replays read it)
+  // CUDA graphs of the sampling loop (S x [input projection, flag reset, streamed layers, skip GEMM, output projection + posterior]):
+  // a call signature seen for the second time is captured once and replayed afterwards (FSE_GRAPH=0 disables).
+  struct GraphEntry {
+    const void* ws; const void* cond; const void* noise; const void* ref; const void* mask; const void* mel; const void* trace;
+    int B, T, S; int seen; long long launches; cudaGraphExec_t exec;
+  };
+  std::vector<GraphEntry> graphs;
+  bool use_graph = true;
+  // The caller's stream may be the legacy default stream (PyTorch's default), which cannot be captured: the loop is captured and
+  // replayed on this handle-owned non-blocking stream, fenced by events on both sides so that it stays ordered in the caller's stream.
+  cudaStream_t gstream = nullptr; cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   int skip_mt = 2;         // sub-tiles per job of the folded skip GEMM (FSE_SKIP_MT)
   int batch_chunk = 0;     // utterances per L2-resident chunk (0 = whole batch); FSE_BATCH_CHUNK overrides
   long long* dbg_buf = nullptr;   // FSE_DBG_STAMPS=1: clock64 phase stamps of layer-3 kernels (developer aid)
@@ -367,7 +380,7 @@ int run_fused_layers(fse_denoiser* h, const Workspace& w, int Bc, int b0, int T,
 }
 
 struct OutSpec {
-  int mode; const float* x_t; float* x_out; const float* noise; unsigned long long seed; unsigned step;
+  int mode; const float* x_t; float* x_out; const float* noise; const unsigned long long* seedp; unsigned step;
   float c1, c2, sigma; float* mel_out; const float* ref; const float* mask; bool write_xb;
 };
 
@@ -449,7 +462,7 @@ int run_step(fse_denoiser* h, const Workspace& w, const void* cond_op, int B, in
     ConvGemmParams p = make_params(Bc, T, T, C, 1, &zero, 0, M, KB); p.b_off = b0;
     GemmOperands op; op.A0 = w.rb; op.W = h->W_out; op.mA0 = &h->plan.m_rb; op.mW = &h->mW_out; op.BN = M;
     EpiOut<TOp> epi{h->b_out, M, T, out.mode, out.x_t, out.x_out, out.write_xb ? static_cast<TOp*>(w.xb) : nullptr,
-                    out.noise, out.seed, out.step, out.c1, out.c2, out.sigma, out.mel_out, out.ref, out.mask};
+                    out.noise, out.seedp, out.step, out.c1, out.c2, out.sigma, out.mel_out, out.ref, out.mask};
     FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, 4})));
   }
   }  // batch chunk
@@ -486,12 +499,12 @@ int denoise_step_impl(fse_denoiser* h, const float* x_t, const float* cond, cons
   x_to_rows_kernel<TOp><<<dim3((T + 255) / 256, B), 256, 0, st>>>(x_t, static_cast<TOp*>(w.xb), M, T);
   FSE_CUDA(cudaGetLastError());
   ++h->launches;
-  OutSpec out{0, nullptr, x0, nullptr, 0ull, 0u, 0.f, 0.f, 0.f, nullptr, nullptr, nullptr, false};
+  OutSpec out{0, nullptr, x0, nullptr, h->d_seed, 0u, 0.f, 0.f, 0.f, nullptr, nullptr, nullptr, false};
   return run_step<TOp>(h, w, cond_op, B, T, 0, 1, out, st);
 }
 
 template <typename TOp>
-int sample_impl(fse_denoiser* h, const float* cond, const float* noise, uint64_t seed, const float* ref, const float* mask,
+int sample_impl(fse_denoiser* h, const float* cond, const float* noise, const float* ref, const float* mask,
                 float* mel_out, float* x_trace, int B, int T, void* ws, cudaStream_t st) {
   Workspace w = carve(h, ws, B, T);
   FSE_TRY(build_plan(h, w, ws, cond, B, T));
@@ -503,7 +516,7 @@ int sample_impl(fse_denoiser* h, const float* cond, const float* noise, uint64_t
   FSE_TRY(run_time_tables(h, w, S, st));
   const void* cond_op = nullptr;
   FSE_TRY(prepare_cond<TOp>(h, w, cond, B, T, st, &cond_op));
-  init_x_kernel<TOp><<<dim3((T + 255) / 256, B), 256, 0, st>>>(noise, seed, w.xa, static_cast<TOp*>(w.xb), M, T);
+  init_x_kernel<TOp><<<dim3((T + 255) / 256, B), 256, 0, st>>>(noise, h->d_seed, w.xa, static_cast<TOp*>(w.xb), M, T);
   FSE_CUDA(cudaGetLastError());
   ++h->launches;
   float* x_cur = w.xa;
@@ -513,7 +526,7 @@ int sample_impl(fse_denoiser* h, const float* cond, const float* noise, uint64_t
     OutSpec out{};
     out.mode = 1; out.x_t = x_cur; out.x_out = x_next;
     out.noise = noise ? noise + static_cast<size_t>(1 + k) * xsz : nullptr;
-    out.seed = seed; out.step = static_cast<unsigned>(k + 1);
+    out.seedp = h->d_seed; out.step = static_cast<unsigned>(k + 1);
     out.c1 = h->coef1[t]; out.c2 = h->coef2[t];
     out.sigma = t == 0 ? 0.f : expf(0.5f * h->logvar[t]);      // nonzero_mask * exp(0.5 logvar) (:100-101)
     const bool last = k == S - 1;
@@ -526,7 +539,7 @@ int sample_impl(fse_denoiser* h, const float* cond, const float* noise, uint64_t
     long long d[64];
     cudaStreamSynchronize(st);
     cudaMemcpy(d, h->dbg_buf, sizeof(d), cudaMemcpyDeviceToHost);
-    const bool stream = h->fused_stream && h->fused_shared_a;
+    const bool stream = h->cfg.mode == FSE_MODE_TC_TF32 || (h->fused_stream && h->fused_shared_a);
     // lock step: CTA 0's two tiles of layer 3, cycles since it left the barrier before layer 3; streamed: items 6, 7 of CTA 0
     // (last DiffNet evaluation), cycles since kernel start
     const long long t0 = stream ? d[0] : d[42];
@@ -538,6 +551,8 @@ int sample_impl(fse_denoiser* h, const float* cond, const float* noise, uint64_t
               tl, m[0] - t0, m[1] - t0, m[2] - t0, m[3] - t0, m[4] - t0, m[5] - t0, m[6] - t0, e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0, e[4] - t0, e[5] - t0);
       if (stream) fprintf(stderr, "        producer: dependency wait %lld..%lld | e2 released its TMEM buffer at %lld\n", d[40 + 2 * tl] - t0, d[41 + 2 * tl] - t0, e[6] - t0);
     }
+    if (stream) fprintf(stderr, "  CTA0 MMA warp over the launch: %lld items in %lld cycles; waiting for accumulators %lld, activation tiles %lld, weight stages %lld, u %lld cycles\n",
+                        d[53], d[52], d[48], d[49], d[50], d[51]);
     if (!stream) fprintf(stderr, "  layer3 end: syncthreads passed=%lld grid barrier passed=%lld\n", d[40] - t0, d[41] - t0);
   } else if (h->dbg_buf) {
     long long d[64];
@@ -595,6 +610,9 @@ int fse_denoiser_create(const fse_denoiser_config* cfg, fse_denoiser** out) {
   h->fused_pair = h->fused && (cfg->mode == FSE_MODE_TC_TF32 || !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 1));   // FSE_FUSED=1: single-CTA variant (bf16 only)
   h->fused_stream = !(getenv("FSE_FUSED_STREAM") && atoi(getenv("FSE_FUSED_STREAM")) == 0);
   h->fused_shared_a = !(getenv("FSE_FUSED_SHARED_A") && atoi(getenv("FSE_FUSED_SHARED_A")) == 0);   // measured: 92.3 vs 95.3 ms/step
+  if (const char* e = getenv("FSE_GRAPH")) h->use_graph = atoi(e) != 0;
+  if (cudaMalloc(reinterpret_cast<void**>(&h->d_seed), 8) != cudaSuccess) { delete h; return fail(FSE_ECUDA, "cudaMalloc(seed) failed"); }
+  cudaMemset(h->d_seed, 0, 8);
   if (getenv("FSE_DBG_STAMPS")) { cudaMalloc(reinterpret_cast<void**>(&h->dbg_buf), 64 * 8); cudaMemset(h->dbg_buf, 0, 64 * 8); }
   cudaGetDevice(&h->device);
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, h->device);
@@ -608,6 +626,11 @@ void fse_denoiser_destroy(fse_denoiser* h) {
                   h->Wdp, h->bdp, h->mlp0_w, h->mlp0_b, h->mlp2_w, h->mlp2_b, h->d_coef1, h->d_coef2, h->d_logvar, h->host_ws,
                   h->d_mW1, h->d_mW2f, h->d_mW1p, h->d_mW2p, h->d_grid_bar};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->d_seed) cudaFree(h->d_seed);
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
+  if (h->gstream) cudaStreamDestroy(h->gstream);
   delete h;
 }
 
@@ -764,6 +787,8 @@ int fse_denoiser_set_schedule(fse_denoiser* h, int32_t timesteps, const float* c
   FSE_TRY(upload_f32(h->coef2, &h->d_coef2));
   FSE_TRY(upload_f32(h->logvar, &h->d_logvar));
   h->plan.ws = nullptr;
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);      // captured loops bake the schedule coefficients in
+  h->graphs.clear();
   return FSE_OK;
 }
 
@@ -802,8 +827,56 @@ int fse_sample(fse_denoiser* h, const float* cond, const float* noise, uint64_t 
   if ((ref_mel == nullptr) != (mask == nullptr)) return fail(FSE_EINVAL, "ref_mel and mask must be given together");
   h->launches = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return h->bf16 ? sample_impl<__nv_bfloat16>(h, cond, noise, seed, ref_mel, mask, mel_out, x_trace, B, T, workspace, st)
-                 : sample_impl<float>(h, cond, noise, seed, ref_mel, mask, mel_out, x_trace, B, T, workspace, st);
+  set_seed_kernel<<<1, 1, 0, st>>>(h->d_seed, seed);
+  FSE_CUDA(cudaGetLastError());
+  auto run_on = [&](cudaStream_t s) {
+    return h->bf16 ? sample_impl<__nv_bfloat16>(h, cond, noise, ref_mel, mask, mel_out, x_trace, B, T, workspace, s)
+                   : sample_impl<float>(h, cond, noise, ref_mel, mask, mel_out, x_trace, B, T, workspace, s);
+  };
+  auto run = [&]() { return run_on(st); };
+  // Graph path: everything fse_sample launches depends only on the call's pointers and shapes (the seed lives in device memory),
+  // so the second call with the same signature is captured and every later one is a single cudaGraphLaunch.  Not used while the
+  // per-kernel event profiler or the debug stamps are on, or when the caller is itself capturing this stream.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  FSE_CUDA(cudaStreamIsCapturing(st, &cap));
+  if (!h->use_graph || h->prof.on || h->dbg_buf || cap != cudaStreamCaptureStatusNone) return run();
+  fse_denoiser::GraphEntry* ge = nullptr;
+  for (auto& g : h->graphs)
+    if (g.ws == workspace && g.cond == cond && g.noise == noise && g.ref == ref_mel && g.mask == mask && g.mel == mel_out && g.trace == x_trace &&
+        g.B == B && g.T == T && g.S == h->S) { ge = &g; break; }
+  if (!ge) {
+    if (h->graphs.size() >= 8) {                       // bounded cache: drop the oldest signature
+      if (h->graphs.front().exec) cudaGraphExecDestroy(h->graphs.front().exec);
+      h->graphs.erase(h->graphs.begin());
+    }
+    h->graphs.push_back({workspace, cond, noise, ref_mel, mask, mel_out, x_trace, B, T, h->S, 1, 0, nullptr});
+    return run();                                      // first sight: eager (also performs every one-time initialisation)
+  }
+  if (!h->gstream) {
+    FSE_CUDA(cudaStreamCreateWithFlags(&h->gstream, cudaStreamNonBlocking));
+    FSE_CUDA(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+    FSE_CUDA(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+  }
+  cudaStream_t gs = h->gstream;
+  FSE_CUDA(cudaEventRecord(h->ev_in, st));             // everything the caller queued before this call (inputs, the seed) ...
+  FSE_CUDA(cudaStreamWaitEvent(gs, h->ev_in, 0));      // ... happens before the loop
+  if (!ge->exec) {
+    cudaGraph_t graph = nullptr;
+    FSE_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_on(gs);
+    const cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+    if (rc != FSE_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(FSE_ECUDA, "graph capture of the sampling loop failed: %s", cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&ge->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { ge->exec = nullptr; return fail(FSE_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+    ge->launches = h->launches;
+  }
+  h->launches = ge->launches;
+  FSE_CUDA(cudaGraphLaunch(ge->exec, gs));
+  FSE_CUDA(cudaEventRecord(h->ev_out, gs));
+  FSE_CUDA(cudaStreamWaitEvent(st, h->ev_out, 0));     // the caller's stream continues after the loop
+  return FSE_OK;
 }
 
 int fse_sample_host(fse_denoiser* h, const float* cond, const float* noise, uint64_t seed, const float* ref_mel, const float* mask,

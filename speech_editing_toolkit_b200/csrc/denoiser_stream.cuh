@@ -52,10 +52,15 @@ constexpr int kStreamThreads = kTcThreads + 32;     // + the publisher warp
 // Every operand is fp32 in HBM and shared memory, so a k-block is 32 channels (128-byte rows as before) and there are twice as
 // many of them: 8 hb blocks + H/32 cond blocks per gate job, 8 u blocks for the residual GEMM.  The residual stream IS the
 // operand (no bf16 copy): layer l reads hf[l & 1] (TMA halo tiles + the epilogue's own rows) and writes hf[(l + 1) & 1]; u is
-// rounded to tf32 once (cvt.rna) and kept as a 128 KB fp32 tile in shared memory (2 activation slots + 3 weight stages fit
-// next to it); u_all is fp32.  Gate non-linearities use ex2/rcp at fp32 accuracy instead of tanh.approx.
-constexpr int kStreamTf32ASlots = 2, kStreamTf32WStages = 3;
-constexpr int kStreamTf32UBytes = 8 * 128 * 128;
+// rounded to tf32 once (cvt.rna); u_all is fp32.  Gate non-linearities use ex2/rcp at fp32 accuracy instead of tanh.approx.
+// Shared memory: a whole fp32 u tile would be 128 KB and leave room for only 2 activation slots + 3 weight stages; measured
+// (FSE_DBG_STAMPS): the MMA warp then waits 60 % of the launch for operands (82 KB in flight against ~3 k cycles of loaded TMA
+// latency).  So the tile holds ONE half of u (64 KB): the residual GEMM is split in two K halves, its first half (u of gate
+// job a) is issued in the middle of gate job b (after the conv k-blocks, before the cond k-blocks: the first gate epilogue has
+// long finished by then), and gate epilogue b overwrites the tile for the second half.  That restores the bf16 schedule's ring:
+// 3 activation slots + 6 weight stages.
+constexpr int kStreamTf32ASlots = 3, kStreamTf32WStages = 6;
+constexpr int kStreamTf32UBytes = 4 * 128 * 128;
 constexpr size_t kStreamTf32SmemBytes = 1024 + kStreamTf32ASlots * kFusedASlotBytes + kStreamTf32WStages * 128 * 128 + kStreamTf32UBytes + kFusedBiasBytes + 256;
 static_assert(kStreamTf32SmemBytes <= 227 * 1024, "tf32 stream kernel: shared memory");
 
@@ -101,8 +106,9 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
   uint64_t* u_empty = u_full + 2;
   uint64_t* pub_bar = u_empty + 1;                // this CTA's epilogue warps have stored their h / hb rows of the item
   uint64_t* ust_full = pub_bar + 1;               // [2]: this CTA's half of the u tile is complete in shared memory -> TMA store to u_all
-  uint64_t* ust_done = ust_full + 2;              // the TMA stores of the item have read the u tile (it may be reused as scratch)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ust_done + 1);
+  uint64_t* ust_done = ust_full + 2;              // the TMA stores have read the u tile (bf16: once per item; tf32: once per half)
+  uint64_t* ua_empty = ust_done + 1;              // tf32: the first half of the residual GEMM has read the u tile (gate epilogue b may overwrite it)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ua_empty + 1);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
@@ -135,6 +141,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
       ptx::mbar_init(pub_bar, kEpiWarps);
       for (int i = 0; i < 2; ++i) ptx::mbar_init(&ust_full[i], kEpiWarps);
       ptx::mbar_init(ust_done, 1);
+      ptx::mbar_init(ua_empty, 1);
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -172,8 +179,18 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           asm volatile("fence.proxy.async;" ::: "memory");      // other CTAs' generic-proxy stores -> our TMA (async proxy) loads
           if (dp) dp[1] = clock64();
         }
+        auto load_w2 = [&](int kb0, int kb1) {          // residual GEMM weights (its A operand is the smem copy of u)
+          for (int kb = kb0; kb < kb1; ++kb, ++kw) {
+            const int s = kw % WS;
+            ptx::mbar_wait(&w_empty[s], ((kw / WS) & 1) ^ 1u);
+            if (leader) ptx::mbar_arrive_expect_tx(&w_full[s], static_cast<uint32_t>(WB) * kMul);
+            if constexpr (kPair) ptx::tma_load_2d_pair(sW + s * WB, mW2, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * KC, nrow);
+            else ptx::tma_load_2d(sW + s * WB, mW2, &w_full[s], kb * KC, 0);
+          }
+        };
         for (int half = 0; half < 2; ++half) {
           for (int grp = 0; grp < ngroups; ++grp, ++ga) {
+            if constexpr (kTF32) { if (half == 1 && grp == NHB) load_w2(0, NHB / 2); }     // same order as the MMA warp consumes the ring
             const int slot = ga % AS;
             ptx::mbar_wait(&a_empty[slot], ((ga / AS) & 1) ^ 1u);
             // pair mode: both CTAs' loads signal the LEADER's barrier, which expects the bytes of both
@@ -198,13 +215,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
             }
           }
         }
-        for (int kb = 0; kb < NHB; ++kb, ++kw) {          // residual GEMM weights (its A operand is the smem copy of u)
-          const int s = kw % WS;
-          ptx::mbar_wait(&w_empty[s], ((kw / WS) & 1) ^ 1u);
-          if (leader) ptx::mbar_arrive_expect_tx(&w_full[s], static_cast<uint32_t>(WB) * kMul);
-          if constexpr (kPair) ptx::tma_load_2d_pair(sW + s * WB, mW2, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * KC, nrow);
-          else ptx::tma_load_2d(sW + s * WB, mW2, &w_full[s], kb * KC, 0);
-        }
+        load_w2(kTF32 ? NHB / 2 : 0, NHB);
       }
     }
     __syncwarp();
@@ -222,22 +233,67 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
     if (leader) {
       const bool el = ptx::elect_one();      // the one lane that issues every tcgen05.mma / commit of the pair
       int ga = 0, kw = 0, it = 0;
+      // developer aid (FSE_DBG_STAMPS=1): cycles CTA 0's MMA warp spends waiting for accumulators / activation tiles / weight stages / u
+      const bool acct = p.dbg && blockIdx.x == 0;
+      long long w_acc = 0, w_a = 0, w_w = 0, w_u = 0;
+      auto timed_wait = [&](uint64_t* bar, uint32_t parity, long long& sum) {
+        if (acct) { const long long c0 = clock64(); ptx::mbar_wait(bar, parity); sum += clock64() - c0; }
+        else ptx::mbar_wait(bar, parity);
+      };
       for (int g = pair0; g < total_items; g += npairs, ++it) {
         long long* dm = (p.dbg && blockIdx.x == 0 && lane == 0 && it >= kDbgItem && it < kDbgItem + 2) ? p.dbg + 1 + (it - kDbgItem) * 8 : nullptr;
+        // residual GEMM k-blocks [kb0, kb1): A = the u tile in shared memory (tf32: the tile holds one K half at a time)
+        const int job2 = 3 * it + 2, buf2 = job2 & 1;
+        const uint32_t tmem_d2 = tmem_base + static_cast<uint32_t>(buf2 * 256);
+        auto res_gemm = [&](int kb0, int kb1) {
+          for (int kb = kb0; kb < kb1; ++kb, ++kw) {
+            if (kb % (NHB / 2) == 0) {
+              // the first half of the residual GEMM (first half of the u k-blocks) only needs the FIRST gate epilogue, which
+              // finished while the second gate job was running; only the second half waits for the second gate epilogue
+              timed_wait(&u_full[kb / (NHB / 2)], it & 1, w_u);
+              ptx::tc_fence_after();
+              if (dm && kb == NHB / 2) dm[5] = clock64();
+            }
+            const int s = kw % WS;
+            timed_wait(&w_full[s], (kw / WS) & 1, w_w);
+            ptx::tc_fence_after();
+            {
+              const int ukb = kTF32 ? kb % (NHB / 2) : kb;
+              const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(sU + ukb * 16384));
+              const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sW + s * WB));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (el) mma(tmem_d2, da + 2 * k, db + 2 * k, (kb | k) != 0 ? 1u : 0u);
+              if (el) commit(&w_empty[s]);
+            }
+            __syncwarp();
+          }
+        };
         for (int half = 0; half < 2; ++half) {
           const int job = 3 * it + half, buf = job & 1;
-          ptx::mbar_wait(&acc_empty[buf], ((job >> 1) & 1) ^ 1u);
+          timed_wait(&acc_empty[buf], ((job >> 1) & 1) ^ 1u, w_acc);
           ptx::tc_fence_after();
           if (dm) dm[half * 2] = clock64();                 // job may start (buffer free)
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * 256);
           uint32_t accum = 0;
           for (int grp = 0; grp < ngroups; ++grp, ++ga) {
+            if constexpr (kTF32) {
+              if (half == 1 && grp == NHB) {
+                // first K half of the residual GEMM, between the conv and the cond k-blocks of gate job b: its accumulator (the
+                // buffer gate job a used) and the u half tile were both released by gate epilogue a several thousand cycles ago
+                timed_wait(&acc_empty[buf2], ((job2 >> 1) & 1) ^ 1u, w_acc);
+                ptx::tc_fence_after();
+                res_gemm(0, NHB / 2);
+                if (el) commit(ua_empty);                   // -> gate epilogue b may overwrite the tile (both CTAs)
+                __syncwarp();
+              }
+            }
             const int slot = ga % AS;
-            ptx::mbar_wait(&a_full[slot], (ga / AS) & 1);
+            timed_wait(&a_full[slot], (ga / AS) & 1, w_a);
             const int ntap = grp < NHB ? 3 : 1;
             for (int j = 0; j < ntap; ++j, ++kw) {
               const int s = kw % WS;
-              ptx::mbar_wait(&w_full[s], (kw / WS) & 1);
+              timed_wait(&w_full[s], (kw / WS) & 1, w_w);
               ptx::tc_fence_after();
               {
                 // hb tile holds frames t0-1 .. t0+128; tap j (offset j-1) starts at row j.  Descriptors are computed by the
@@ -262,39 +318,21 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           __syncwarp();
         }
         {
-          const int job = 3 * it + 2, buf = job & 1;
-          ptx::mbar_wait(&acc_empty[buf], ((job >> 1) & 1) ^ 1u);
-          if (dm) dm[4] = clock64();
-          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(buf * 256);
-          for (int kb = 0; kb < NHB; ++kb, ++kw) {
-            if (kb % (NHB / 2) == 0) {
-              // the first half of the residual GEMM (first half of the u k-blocks) only needs the FIRST gate epilogue, which
-              // finished while the second gate job was running; only the second half waits for the second gate epilogue
-              ptx::mbar_wait(&u_full[kb / (NHB / 2)], it & 1);
-              ptx::tc_fence_after();
-              if (dm && kb == NHB / 2) dm[5] = clock64();
-            }
-            const int s = kw % WS;
-            ptx::mbar_wait(&w_full[s], (kw / WS) & 1);
+          if constexpr (!kTF32) {
+            timed_wait(&acc_empty[buf2], ((job2 >> 1) & 1) ^ 1u, w_acc);
             ptx::tc_fence_after();
-            {
-              const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(sU + kb * 16384));
-              const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(sW + s * WB));
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (el) mma(tmem_d, da + 2 * k, db + 2 * k, (kb | k) != 0 ? 1u : 0u);
-              if (el) commit(&w_empty[s]);
-            }
-            __syncwarp();
           }
+          if (dm) dm[4] = clock64();
+          res_gemm(kTF32 ? NHB / 2 : 0, NHB);
           if (el) {
             commit(u_empty);
-            commit(&acc_full[buf]);
+            commit(&acc_full[buf2]);
           }
           if (dm) dm[6] = clock64();
           __syncwarp();
         }
       }
+      if (acct && lane == 0) { p.dbg[48] = w_acc; p.dbg[49] = w_a; p.dbg[50] = w_w; p.dbg[51] = w_u; p.dbg[52] = clock64() - p.dbg[0]; p.dbg[53] = it; }
     }
   } else if (warp == 2 + kEpiWarps) {
     // ---------------------------------------------------------------- publisher
@@ -317,14 +355,16 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
           ptx::mbar_wait(&ust_full[half], it & 1);                // epilogue warps: st.shared + fence.proxy.async + arrive
           if (tile < total_tiles) {
             for (int j = 0; j < NHB / 2; ++j) {
-              const int kb = half * (NHB / 2) + j;
-              ptx::tma_store_3d(&mapU, sU + kb * 16384, l * kFC + kb * KC, t0, b, pol);      // rows >= T are clipped
+              const int kb = half * (NHB / 2) + j;                // u k-block; tf32: the tile holds the current half only
+              ptx::tma_store_3d(&mapU, sU + (kTF32 ? j : kb) * 16384, l * kFC + kb * KC, t0, b, pol);      // rows >= T are clipped
             }
           }
+          if (kTF32 || half == 1) {
+            ptx::bulk_commit_group();
+            ptx::bulk_wait_group_read0();                         // the tile has been read: it may be overwritten / used as scratch
+            ptx::mbar_arrive(ust_done);                           // tf32: phase 2 it (first half), 2 it + 1 (second half); bf16: phase it
+          }
         }
-        ptx::bulk_commit_group();
-        ptx::bulk_wait_group_read0();                             // the u tile has been read: scratch of the residual epilogue
-        ptx::mbar_arrive(ust_done);
         ptx::mbar_wait(pub_bar, it & 1);
         __threadfence();
         atomicAdd(p.done + g, static_cast<unsigned int>(kEpiWarps));     // g == l * total_units + unit
@@ -381,6 +421,12 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
         const int job = 3 * it + half, buf = job & 1;
         ptx::mbar_wait(&acc_full[buf], (job >> 1) & 1);
         ptx::tc_fence_after();
+        if constexpr (kTF32) {
+          if (half == 1) {          // the half tile is rewritten: the residual GEMM's first K half and the TMA store have read it
+            ptx::mbar_wait(ua_empty, it & 1);
+            ptx::mbar_wait(ust_done, 0);
+          }
+        }
         if (de) de[half * 2] = clock64();                 // accumulator ready
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(buf * 256);
         // accumulator chunks are fetched one ahead: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
@@ -412,8 +458,9 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
             uint32_t uf[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) uf[j] = __float_as_uint(ptx::round_tf32(gate_acc(y[2 * j], y[2 * j + 1])));
-            // A operand of the residual GEMM: k-block = 32 fp32 channels, 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7)
-            uint8_t* ub = sU + (ucol >> 5) * 16384 + r * 128;
+            // A operand of the residual GEMM: k-block = 32 fp32 channels, 128-byte rows, 16-byte chunks XOR-swizzled by (row & 7);
+            // the tile holds this half's 128 u channels (4 k-blocks)
+            uint8_t* ub = sU + ((ucol & 127) >> 5) * 16384 + r * 128;
             const int ch = (ucol & 31) >> 2;             // first of the four 16-byte chunks
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -459,9 +506,9 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
         // ahead of the global traffic: the buffer goes back to the MMA warp after ~40 % of this epilogue (the next item's
         // second gate job was waiting for exactly that).
         const int job = 3 * it + 2, buf = job & 1;
-        // (tf32: this warp wrote rows q*32.. of u k-blocks {2*half2, 2*half2+1} and {4+2*half2, 4+2*half2+1})
+        // (tf32: this warp wrote rows q*32.. of k-blocks 2*half2 and 2*half2 + 1 of the half tile)
         float* stgA = reinterpret_cast<float*>(sU + (kTF32 ? 2 * half2 : half2) * 16384 + q * 4096);
-        float* stgB = reinterpret_cast<float*>(sU + (kTF32 ? 4 + 2 * half2 : 2 + half2) * 16384 + q * 4096);
+        float* stgB = reinterpret_cast<float*>(sU + (kTF32 ? 2 * half2 + 1 : 2 + half2) * 16384 + q * 4096);
         const int cq = lane & 7, r0 = lane >> 3;
         const int tq = tile < total_tiles ? t0 + q * 32 + r0 : p.T;   // frame of iteration 0; iteration i adds 4*i
         const size_t rowq = static_cast<size_t>(b) * p.T + tq;
@@ -509,28 +556,9 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
         load_h(cb + 1, h1);
         ptx::mbar_wait(&acc_full[buf], (job >> 1) & 1);
         ptx::tc_fence_after();
-        ptx::mbar_wait(ust_done, it & 1);                           // the TMA stores to u_all have read the u tile: it is scratch now
+        ptx::mbar_wait(ust_done, kTF32 ? 1u : static_cast<uint32_t>(it & 1));   // the TMA stores to u_all have read the u tile: it is scratch now
         if (de) de[4] = clock64();
-        if constexpr (kTF32) {
-          // fp32 u tile: this warp owns 4 x 4 KB of it (its rows of four k-blocks) = its whole share of the accumulator, so the
-          // accumulator leaves TMEM in one go and goes back to the MMA warp before any global traffic of this epilogue.
-          float* stgC = stgA + 16384 / 4;                           // k-blocks 2*half2 + 1 and 4 + 2*half2 + 1
-          float* stgD = stgB + 16384 / 4;
-          stage(cb, stgA);
-          stage(cb + 1, stgC);
-          stage(cb + 2, stgB);
-          stage(cb + 3, stgD);
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) arrive_leader(&acc_empty[buf]);            // accumulator drained
-          if (de) de[6] = clock64();
-          load_h(cb + 2, h2);
-          finish(cb, stgA, h0);
-          load_h(cb + 3, h0);
-          finish(cb + 1, stgC, h1);
-          finish(cb + 2, stgB, h2);
-          finish(cb + 3, stgD, h0);
-        } else {
+        {
         stage(cb, stgA);
         stage(cb + 1, stgB);
         load_h(cb + 2, h2);

@@ -210,7 +210,7 @@ struct EpiOut {
   float* x_out;          // [B, M, T]  (mode 0: receives x0)
   TOp* xb;               // [B*T, M] or null
   const float* noise;    // [B, M, T] or null -> Philox
-  unsigned long long seed;
+  const unsigned long long* seedp;   // Philox seed in device memory (so a captured CUDA graph of the sampling loop is seed-independent)
   unsigned step;
   float c1, c2, sigma;
   float* mel_out;        // [B, T, M] or null
@@ -237,7 +237,7 @@ struct EpiOut {
     for (int g = 0; g < NV / 4; ++g) {
       float z[4] = {0.f, 0.f, 0.f, 0.f};
       if (mode == 1 && noise == nullptr && sigma != 0.f)
-        philox_normal4(seed, step, static_cast<uint32_t>(row), static_cast<uint32_t>((n0 >> 2) + g), z);
+        philox_normal4(__ldg(seedp), step, static_cast<uint32_t>(row), static_cast<uint32_t>((n0 >> 2) + g), z);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int i = 4 * g + q;
