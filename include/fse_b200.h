@@ -129,8 +129,9 @@ typedef struct fse_vocoder_config {
   int32_t upsample_kernel_sizes[8];
   int32_t num_kernels;               /* <= 4 */
   int32_t resblock_kernel_sizes[4];
-  int32_t resblock_dilations[4][3];  /* ResBlock1: three dilations per block */
+  int32_t resblock_dilations[4][3];  /* ResBlock1: three dilations per block; ResBlock2: the first two */
   int32_t mode;                      /* FSE_MODE_* */
+  int32_t resblock;                  /* config['resblock']: 1 (also when 0) = ResBlock1 (hifigan.py:27-64), 2 = ResBlock2 (:67-88) */
 } fse_vocoder_config;
 
 /* replaces HifiGanGenerator.__init__ (hifigan.py:101-124) */

@@ -280,8 +280,9 @@ def _wn(p, name):
 
 
 def hifigan_forward(p: Dict[str, np.ndarray], cfg: dict, mel: np.ndarray, gemm_dtype: str = "f32") -> np.ndarray:
-    """HifiGanGenerator.forward (hifigan.py:126-142), ResBlock1.forward (:51-58).  mel[B,80,T] -> wav[B,1,T*prod(rates)]."""
-    assert cfg["resblock"] == "1", "oracle restates ResBlock1 (HiFi-GAN V1) only"
+    """HifiGanGenerator.forward (hifigan.py:126-142), ResBlock1.forward (:51-58) / ResBlock2.forward (:80-85).
+    mel[B,80,T] -> wav[B,1,T*prod(rates)]."""
+    rb2 = str(cfg["resblock"]) == "2"
     nk = len(cfg["resblock_kernel_sizes"])
     x = conv1d(mel, _wn(p, "conv_pre"), p["conv_pre.bias"], padding=3, gemm_dtype=gemm_dtype)
     for i, (u, k) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
@@ -294,6 +295,11 @@ def hifigan_forward(p: Dict[str, np.ndarray], cfg: dict, mel: np.ndarray, gemm_d
             y = x
             for m, d in enumerate(rd):
                 yt = leaky_relu(y, 0.1)
+                if rb2:                                   # ResBlock2: x = c(lrelu(x)) + x  (:81-84)
+                    yt = conv1d(yt, _wn(p, pre + f"convs.{m}"), p[pre + f"convs.{m}.bias"], dilation=d, padding=(rk * d - d) // 2,
+                                gemm_dtype=gemm_dtype)
+                    y = (yt + y).astype(F32)
+                    continue
                 yt = conv1d(yt, _wn(p, pre + f"convs1.{m}"), p[pre + f"convs1.{m}.bias"], dilation=d,
                             padding=(rk * d - d) // 2, gemm_dtype=gemm_dtype)
                 yt = leaky_relu(yt, 0.1)

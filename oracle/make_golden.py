@@ -372,6 +372,51 @@ def bench_config_fixture():
     print("campnet_t1024", ret["mel_out_fine"].shape, float(np.abs(ret["mel_out_fine"].numpy()).mean()))
 
 
+def mel_frontend_fixture():
+    """tests/golden/mel_frontend.npz WITHOUT the oracle's own transform: `scipy.signal.stft` (an independent implementation: Hann
+    window from scipy.signal.get_window(fftbins=True), zero boundary = librosa's center=True / pad_mode="constant") gives |X|, and the
+    Slaney filterbank is built here from librosa's documented definition (Slaney scale 200/3 Hz per mel below 1 kHz, log step
+    ln(6.4)/27 above; triangles between n_mels + 2 band edges; area normalisation) after checking the scale against the constants
+    published in librosa's documentation (mel_frequencies(n_mels=40) example, hz_to_mel(60) = 0.9, mel_to_hz(3) = 200).  librosa
+    itself is absent from the container and from /root/reference, so this is the strongest pin available:
+    `python oracle/make_golden.py mel_frontend`."""
+    import scipy.signal as ss
+    os.makedirs(OUT, exist_ok=True)
+    sr, n_fft, hop, n_mels, fmin, fmax, eps = 22050, 1024, 256, 80, 55.0, 7600.0, 1e-6
+    f_sp, min_log_hz = 200.0 / 3, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, np.log(6.4) / 27.0
+    h2m = lambda f: np.where(np.asarray(f, float) >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-12) / min_log_hz) / logstep, np.asarray(f, float) / f_sp)
+    m2h = lambda m: np.where(np.asarray(m, float) >= min_log_mel, min_log_hz * np.exp(logstep * (np.asarray(m, float) - min_log_mel)), f_sp * np.asarray(m, float))
+    doc = np.array([0., 85.317, 170.635, 255.952, 341.269, 426.586, 511.904, 597.221, 682.538, 767.855, 853.173, 938.49, 1024.856, 1119.114,
+                    1222.042, 1334.436, 1457.167, 1591.187, 1737.532, 1897.337, 2071.84, 2262.393, 2470.47, 2697.686, 2945.799, 3216.731,
+                    3512.582, 3835.643, 4188.417, 4573.636, 4994.285, 5453.621, 5955.205, 6502.92, 7101.009, 7754.107, 8467.272, 9246.028,
+                    10096.408, 11025.])            # librosa documentation: librosa.mel_frequencies(n_mels=40)
+    assert np.abs(m2h(np.linspace(h2m(0.0), h2m(11025.0), 40)) - doc).max() < 1e-3
+    assert abs(float(h2m(60.0)) - 0.9) < 1e-12 and abs(float(m2h(3.0)) - 200.0) < 1e-9
+    freqs = np.linspace(0, sr / 2.0, n_fft // 2 + 1)
+    edges = m2h(np.linspace(h2m(fmin), h2m(fmax), n_mels + 2))
+    fb = np.zeros((n_mels, len(freqs)))
+    for i in range(n_mels):
+        up = (freqs - edges[i]) / (edges[i + 1] - edges[i])
+        down = (edges[i + 2] - freqs) / (edges[i + 2] - edges[i + 1])
+        fb[i] = np.maximum(0.0, np.minimum(up, down)) * 2.0 / (edges[i + 2] - edges[i])
+    fb = fb.astype(np.float32)
+    rs = np.random.RandomState(SEED + 21)
+    n = hop * 41 + 77
+    t = np.arange(n) / sr
+    wav = (0.1 * rs.standard_normal(n) + 0.3 * np.sin(2 * np.pi * 440.0 * t) * (t > 0.2)).astype(np.float32)
+    win = ss.get_window("hann", n_fft, fftbins=True)
+    _, _, Z = ss.stft(wav.astype(np.float64), fs=sr, window=win, nperseg=n_fft, noverlap=n_fft - hop, nfft=n_fft, boundary="zeros", padded=False,
+                      return_onesided=True, scaling="spectrum")
+    T = 1 + n // hop
+    mag = (np.abs(Z).T * win.sum())[:T].astype(np.float32)          # undo scipy's 1 / sum(window) scaling; librosa emits 1 + n // hop frames
+    assert mag.shape == (T, n_fft // 2 + 1)
+    mel = np.log10(np.maximum(eps, mag.astype(np.float64) @ fb.astype(np.float64).T)).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "mel_frontend.npz"), seed=SEED + 21, wav=wav, mel=mel, mel_basis_row0=fb[0], mel_basis_row40=fb[40],
+                        mel_basis_row79=fb[79], band_edges=edges)
+    print("mel_frontend", mel.shape, float(mel.mean()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "mel_encoder":
         mel_encoder_fixture()
@@ -383,6 +428,8 @@ if __name__ == "__main__":
         edit_region_fixture()
     elif len(sys.argv) > 1 and sys.argv[1] == "bench_config":
         bench_config_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mel_frontend":
+        mel_frontend_fixture()
     else:
         main()
         mel_encoder_fixture()
@@ -390,3 +437,4 @@ if __name__ == "__main__":
         campnet_fixture()
         edit_region_fixture()
         bench_config_fixture()
+        mel_frontend_fixture()

@@ -28,7 +28,7 @@ class VocoderConfig(C.Structure):
     _fields_ = [("n_mels", C.c_int32), ("upsample_initial_channel", C.c_int32), ("num_upsamples", C.c_int32),
                 ("upsample_rates", C.c_int32 * 8), ("upsample_kernel_sizes", C.c_int32 * 8),
                 ("num_kernels", C.c_int32), ("resblock_kernel_sizes", C.c_int32 * 4),
-                ("resblock_dilations", (C.c_int32 * 3) * 4), ("mode", C.c_int32)]
+                ("resblock_dilations", (C.c_int32 * 3) * 4), ("mode", C.c_int32), ("resblock", C.c_int32)]
 
 
 class MelEncoderConfig(C.Structure):

@@ -190,6 +190,8 @@ struct fse_vocoder {
   float* post_w = nullptr; float post_b = 0.f; int post_k = 7;
   struct MapEntry { const void* buf; int C, T, KB, rows; CUtensorMap map; };
   struct Plan { const void* ws = nullptr; int B = 0, T = 0; std::deque<MapEntry> cache; } plan;
+  bool rb2 = false;       // ResBlock2 generator: each block is `x = conv_m(lrelu(x)) + x` for two dilated convs (hifigan.py:80-85)
+  int nconv = 3;          // convs per block on the residual path: 3 conv pairs (ResBlock1) or 2 single convs (ResBlock2)
   bool multi_tile = true; // FSE_VOC_MT=0 disables multi-sub-tile jobs for narrow layers; FSE_VOC_MT=2: larger jobs
   int multi_tile_level = 2;
   bool shared_a = true;   // shared-activation schedule: a job's rows (128*MT + tap halo) are loaded once per channel block and the
@@ -377,15 +379,16 @@ int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, voi
     }
     const bool last_stage = i == nu - 1;
     for (int j = 0; j < nk; ++j) {
-      for (int m = 0; m < 3; ++m) {
+      for (int m = 0; m < h->nconv; ++m) {
         const ConvW& a = h->c1[(i * nk + j) * 3 + m];
-        const ConvW& c = h->c2[(i * nk + j) * 3 + m];
-        {
+        const ConvW& c = h->rb2 ? a : h->c2[(i * nk + j) * 3 + m];
+        if (!h->rb2) {
           EpiAct<TOp> epi{a.bias, static_cast<TOp*>(w.tmp), Cout, Tout, 0.1f};
           FSE_TRY((run_conv<TOp>(h, a, m == 0 ? w.xa : w.ya, B, Tout, Tout, epi, st, 2)));
         }
+        const void* src2 = h->rb2 ? (m == 0 ? w.xa : w.ya) : w.tmp;      // ResBlock2: the dilated conv itself carries the residual add
         {
-          const int kind = m < 2 ? 0 : (nk == 1 ? 3 : (j == 0 ? 1 : (j == nk - 1 ? 3 : 2)));
+          const int kind = m < h->nconv - 1 ? 0 : (nk == 1 ? 3 : (j == 0 ? 1 : (j == nk - 1 ? 3 : 2)));
           auto fill = [&](auto& epi) {
             epi.bias = c.bias; epi.res = m == 0 ? w.x : w.y; epi.y = w.y; epi.ya = static_cast<TOp*>(w.ya);
             epi.xs = w.xs; epi.next_a = static_cast<TOp*>(w.ua); epi.final_f32 = last_stage ? w.xs : nullptr;
@@ -397,11 +400,11 @@ int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, voi
           if (kind >= 2 && !(kind == 3 && nk == 1)) {
             EpiResAdd<TOp, true> epi{};
             fill(epi);
-            FSE_TRY((run_conv<TOp>(h, c, w.tmp, B, Tout, Tout, epi, st, 3)));
+            FSE_TRY((run_conv<TOp>(h, c, src2, B, Tout, Tout, epi, st, 3)));
           } else {
             EpiResAdd<TOp, false> epi{};
             fill(epi);
-            FSE_TRY((run_conv<TOp>(h, c, w.tmp, B, Tout, Tout, epi, st, 3)));
+            FSE_TRY((run_conv<TOp>(h, c, src2, B, Tout, Tout, epi, st, 3)));
           }
         }
       }
@@ -431,6 +434,7 @@ int fse_vocoder_create(const fse_vocoder_config* cfg, fse_vocoder** out) {
   if (cfg->num_upsamples <= 0 || cfg->num_upsamples > 8 || cfg->num_kernels <= 0 || cfg->num_kernels > 4)
     return fail(FSE_EINVAL, "num_upsamples / num_kernels out of range");
   if (cfg->n_mels % 8 != 0) return fail(FSE_EINVAL, "n_mels must be a multiple of 8");
+  if (cfg->resblock < 0 || cfg->resblock > 2) return fail(FSE_EINVAL, "resblock must be 1 or 2 (got %d)", cfg->resblock);
   if (cfg->mode < 0 || cfg->mode > 3) return fail(FSE_EINVAL, "unknown mode %d", cfg->mode);
   int hop = 1;
   for (int i = 0; i < cfg->num_upsamples; ++i) {
@@ -450,6 +454,8 @@ int fse_vocoder_create(const fse_vocoder_config* cfg, fse_vocoder** out) {
   h->bf16 = mode_is_bf16(cfg->mode);
   h->tc = mode_is_tc(cfg->mode);
   h->hop = hop;
+  h->rb2 = cfg->resblock == 2;
+  h->nconv = h->rb2 ? 2 : 3;
   if (const char* e = getenv("FSE_VOC_SHARED_A")) h->shared_a = atoi(e) != 0;
   if (const char* e = getenv("FSE_VOC_MT")) { h->multi_tile = atoi(e) != 0; h->multi_tile_level = atoi(e); }
   *out = h;
@@ -481,8 +487,13 @@ int fse_vocoder_load_weights(fse_vocoder* h, const fse_tensor* tensors, int32_t 
     const int Cout = stage_channels(h, i);
     FSE_TRY(pack_up(h, tt, "ups." + std::to_string(i), Cin, Cout, cfg.upsample_kernel_sizes[i], cfg.upsample_rates[i], h->ups[i]));
     for (int j = 0; j < nk; ++j)
-      for (int m = 0; m < 3; ++m) {
+      for (int m = 0; m < h->nconv; ++m) {
         const std::string pre = "resblocks." + std::to_string(i * nk + j) + ".";
+        if (h->rb2) {        // ResBlock2.convs (hifigan.py:71-76)
+          FSE_TRY(pack_conv(h, tt, pre + "convs." + std::to_string(m), Cout, Cout, cfg.resblock_kernel_sizes[j],
+                            cfg.resblock_dilations[j][m], h->c1[(i * nk + j) * 3 + m]));
+          continue;
+        }
         FSE_TRY(pack_conv(h, tt, pre + "convs1." + std::to_string(m), Cout, Cout, cfg.resblock_kernel_sizes[j],
                           cfg.resblock_dilations[j][m], h->c1[(i * nk + j) * 3 + m]));
         FSE_TRY(pack_conv(h, tt, pre + "convs2." + std::to_string(m), Cout, Cout, cfg.resblock_kernel_sizes[j], 1,

@@ -193,8 +193,9 @@ class Vocoder:
 
     def __init__(self, config: dict = None, n_mels: int = 80, mode="tc_bf16"):
         config = dict(HIFIGAN_V1 if config is None else config)
-        if str(config.get("resblock", "1")) != "1":
-            raise FseError("only ResBlock1 generators (HiFi-GAN V1/V2 family) are implemented")
+        rb = str(config.get("resblock", "1"))
+        if rb not in ("1", "2"):
+            raise FseError(f"config['resblock'] must be '1' or '2' (hifigan.py:109), got {rb!r}")
         cfg = _lib.VocoderConfig()
         cfg.n_mels = n_mels
         cfg.upsample_initial_channel = config["upsample_initial_channel"]
@@ -207,10 +208,11 @@ class Vocoder:
         cfg.num_kernels = len(rks)
         for j, (k, ds) in enumerate(zip(rks, rds)):
             cfg.resblock_kernel_sizes[j] = k
-            assert len(ds) == 3, "ResBlock1 has three dilations"
+            assert len(ds) == (3 if rb == "1" else 2), "ResBlock1 has three dilations per block, ResBlock2 two"
             for m, d in enumerate(ds):
                 cfg.resblock_dilations[j][m] = d
         cfg.mode = MODES[mode]
+        cfg.resblock = int(rb)
         self.cfg, self.config, self.mode = cfg, config, mode
         self.hop = int(np.prod(rates))
         self._h = C.c_void_p()

@@ -73,9 +73,10 @@ def hifigan_state_dict(seed: int = 1234, config: dict = None, n_mels: int = 80) 
         cin, ch = ch, c0 // (2 ** (i + 1))
         wn(f"ups.{i}", (cin, ch, k), cin * k / u, gain=1.4)           # ConvTranspose1d weight is [C_in, C_out, k]
         sd[f"ups.{i}.bias"] = (rs.standard_normal((ch,)) * 0.02).astype(F32)
+        rb2 = str(cfg.get("resblock", "1")) == "2"
         for j, rk in enumerate(cfg["resblock_kernel_sizes"]):
-            for m in range(3):
-                for part in ("convs1", "convs2"):
+            for m in range(2 if rb2 else 3):
+                for part in (("convs",) if rb2 else ("convs1", "convs2")):
                     name = f"resblocks.{i * nk + j}.{part}.{m}"
                     wn(name, (ch, ch, rk), ch * rk, gain=0.7)
                     sd[name + ".bias"] = (rs.standard_normal((ch,)) * 0.02).astype(F32)

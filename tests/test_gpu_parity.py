@@ -288,6 +288,30 @@ def test_hifigan_other_resblock_counts(lib_built, kernels):
 
 
 @pytest.mark.gpu
+def test_hifigan_resblock2_generator(lib_built):
+    """config['resblock'] == '2' (hifigan.py:67-88: two dilated convs per block, each `x = c(lrelu(x)) + x`; HiFi-GAN V3-style
+    config) against the oracle, which tests/test_oracles_vs_live_reference.py pins to the live reference generator."""
+    from oracle import fluentspeech_oracle as O
+    from speech_editing_toolkit_b200 import synth
+    from speech_editing_toolkit_b200.engine import Vocoder
+    cfg = dict(upsample_rates=[8, 8, 4], upsample_kernel_sizes=[16, 16, 8], upsample_initial_channel=256, resblock="2",
+               resblock_kernel_sizes=[3, 5, 7], resblock_dilation_sizes=[[1, 2], [2, 6], [3, 12]])
+    sd = synth.hifigan_state_dict(17, cfg)
+    assert any(".convs.1." in k for k in sd) and not any("convs1" in k for k in sd)
+    mel = np.clip(np.random.RandomState(18).standard_normal((2, 45, 80)) * 1.5 - 3.0, -6, 1.5).astype(np.float32)
+    ref = O.hifigan_forward(sd, cfg, mel.transpose(0, 2, 1))[:, 0]
+    for mode, tol in (("simt_f32", None), ("tc_bf16", 3e-2), ("tc_tf32", 5e-3)):
+        v = Vocoder(cfg, mode=mode)
+        v.load_state_dict(sd)
+        wav = v.forward(cu(mel)).cpu().numpy()
+        assert wav.shape == ref.shape == (2, 45 * 256) and np.isfinite(wav).all()
+        if tol is None:
+            assert np.abs(wav - ref).max() < TOL_F32_ABS
+        else:
+            assert rel_l1(wav, ref) < tol, mode
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("mode", ["simt_f32", "tc_bf16", "tc_tf32"])
 def test_mel_encoder_vs_reference_fixture(lib_built, mode):
     """fse_mel_encoder_forward against the unmodified reference MelEncoder (tests/golden/mel_encoder.npz), plain and with

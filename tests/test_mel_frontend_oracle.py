@@ -70,3 +70,23 @@ def test_wav2spec_wrapper_padding_and_frame_count(monkeypatch):
         audio.wav2spec("file.wav")
     with pytest.raises(NotImplementedError):
         audio.wav2spec(np.zeros(512, dtype=np.float32), loud_norm=True)
+
+
+def test_oracle_against_the_independent_fixture_and_librosa_published_constants():
+    """tests/golden/mel_frontend.npz was produced WITHOUT this oracle (oracle/make_golden.py mel_frontend: scipy.signal.stft + a Slaney
+    filterbank written from librosa's documented definition and checked against the constants in librosa's documentation).  The
+    oracle must reproduce it, and its mel scale must reproduce the published constants itself."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mel_frontend.npz"))
+    mel = MO.wav2mel(g["wav"])
+    assert mel.shape == g["mel"].shape
+    assert np.abs(mel - g["mel"]).max() < 2e-5
+    fb = MO.mel_basis()
+    for i in (0, 40, 79):
+        assert np.abs(fb[i] - g[f"mel_basis_row{i}"]).max() < 1e-9
+    doc40 = np.array([0., 85.317, 170.635, 255.952, 341.269, 426.586, 511.904, 597.221, 682.538, 767.855, 853.173, 938.49, 1024.856])
+    ours = MO.mel_to_hz(np.linspace(MO.hz_to_mel(0.0), MO.hz_to_mel(11025.0), 40))[:13]
+    assert np.abs(ours - doc40).max() < 1e-3                     # librosa docs: mel_frequencies(n_mels=40)
+    assert abs(float(MO.hz_to_mel(60.0)) - 0.9) < 1e-12          # librosa docs: hz_to_mel(60) -> 0.9
+    assert np.allclose(MO.hz_to_mel(np.array([110.0, 220.0, 440.0])), [1.65, 3.3, 6.6])
+    assert np.allclose(MO.mel_to_hz(np.array([1.0, 2, 3, 4, 5])), [66.667, 133.333, 200.0, 266.667, 333.333], atol=1e-3)

@@ -120,3 +120,21 @@ def test_integer_helpers_vs_live_reference_on_random_inputs():
         got_d = CO.denorm_f0(f0, uv, pad)
         assert np.abs(got_d - want_d.numpy()).max() < 2e-3
         assert np.array_equal(O.f0_to_coarse(want_d.numpy()), f0_to_coarse(want_d).numpy())   # same input -> same bins, bit-exact
+
+
+def test_hifigan_resblock2_oracle_vs_live_generator():
+    """ResBlock2 generators (hifigan.py:67-88; HiFi-GAN V3-style config): the oracle against the live HifiGanGenerator."""
+    refshim.install("egs/spec_denoiser.yaml")
+    from modules.vocoder.hifigan.hifigan import HifiGanGenerator
+    from oracle import fluentspeech_oracle as O
+    cfg = dict(upsample_rates=[8, 8, 4], upsample_kernel_sizes=[16, 16, 8], upsample_initial_channel=256, resblock="2",
+               resblock_kernel_sizes=[3, 5, 7], resblock_dilation_sizes=[[1, 2], [2, 6], [3, 12]])
+    sd = synth.hifigan_state_dict(17, cfg)
+    gen = HifiGanGenerator(dict(cfg)).eval()
+    gen.load_state_dict(_t(sd), strict=True)
+    mel = np.clip(np.random.RandomState(18).standard_normal((2, 19, 80)) * 1.5 - 3.0, -6, 1.5).astype(np.float32)
+    with torch.no_grad():
+        want = gen(torch.from_numpy(mel).transpose(1, 2)).numpy()
+    ours = O.hifigan_forward(sd, cfg, mel.transpose(0, 2, 1))
+    assert ours.shape == want.shape == (2, 1, 19 * 256)
+    assert np.abs(ours - want).max() < 2e-5
