@@ -11,6 +11,7 @@
 
 #include "epilogues.cuh"
 #include "fse_common.cuh"
+#include "resblock_fused.cuh"
 
 namespace fse {
 
@@ -197,6 +198,8 @@ struct fse_vocoder {
   bool shared_a = true;   // shared-activation schedule: a job's rows (128*MT + tap halo) are loaded once per channel block and the
                           // k (tap, sub-tile) operands are row-shifted descriptors of it (FSE_VOC_SHARED_A=0: one load per tap).
                           // Measured (B=32 x T=1024): vocoder 54 -> 46 ms once MMA issue and the epilogue stores were fixed.
+  bool fuse_pair = true;  // ResBlock1 conv pairs as one kernel (resblock_fused.cuh) where the job fits shared memory / TMEM
+                          // (FSE_VOC_FUSE=0: always two conv_gemm launches per pair)
   long long launches = 0;
   Profiler prof;
   void* host_ws = nullptr; size_t host_ws_bytes = 0;
@@ -207,7 +210,7 @@ namespace {
 int stage_channels(const fse_vocoder* h, int i) { return h->cfg.upsample_initial_channel >> (i + 1); }
 
 struct VWs {
-  void* melb; void* ua; float* x; void* xa; float* y; void* ya; void* tmp; float* xs;
+  void* melb; void* ua; float* x; void* xa; float* y; void* ya; void* tmp; float* xs; float* y2; void* ya2;
   size_t bytes;
 };
 VWs vcarve(const fse_vocoder* h, void* base, int B, int T) {
@@ -232,6 +235,11 @@ VWs vcarve(const fse_vocoder* h, void* base, int B, int T) {
   o = take(maxel * es); w.ya = p + o;
   o = take(maxel * es); w.tmp = p + o;
   o = take(maxel * 4);  w.xs = reinterpret_cast<float*>(p + o);
+  // second (y, ya) pair: inside a resblock the convs ping-pong (x, xa) -> (y, ya) -> (y2, ya2) -> sum.  The fused pair kernel reads
+  // its input rows (with the conv halo) while other jobs of the SAME launch already write their output rows, so a conv pair must
+  // never update its input in place.
+  o = take(maxel * 4);  w.y2 = reinterpret_cast<float*>(p + o);
+  o = take(maxel * es); w.ya2 = p + o;
   w.bytes = off;
   return w;
 }
@@ -346,6 +354,95 @@ int run_conv(fse_vocoder* h, const ConvW& cw, const void* A, int B, int Trows, i
   return run_conv_gemm<TOp>(h->cfg.mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, kind});
 }
 
+// Shape of a fused conv-pair job (resblock_fused.cuh): the largest MT whose two accumulators fit the 512 TMEM columns and whose
+// tiles (2 input slots with the conv1 halo, the intermediate U, >= 3 weight stages, the epilogue scratch) fit shared memory.
+bool plan_pair(int C, int k, int dil, int KB, int es, PairParams* out) {
+  const int RB = KB * es;
+  if (C % 32 != 0 || C > 256 || k < 1 || k > kMaxTaps || (RB != 128 && RB != 64)) return false;
+  const int nkb = (C + KB - 1) / KB;
+  const int h2 = (k - 1) / 2, h1 = h2 * dil;
+  const int budget = 225 * 1024 - kEpiScratchBytes - 256;
+  for (int MT = 8; MT >= 1; MT >>= 1) {
+    if (2 * MT * C > 512) continue;
+    const int need = kTileM * MT + 2 * h1;
+    int nload = (need + 255) / 256, box = 0;
+    for (;; ++nload) {
+      box = ((need + nload - 1) / nload + 7) / 8 * 8;
+      if (box <= 256) break;
+    }
+    const int a_slot = static_cast<int>(align_up(static_cast<size_t>(box) * nload * RB, 1024));
+    const int u_rows = (kTileM * MT + k - 1 + 7) / 8 * 8;
+    const int u_kb = static_cast<int>(align_up(static_cast<size_t>(u_rows) * RB, 1024));
+    const int w_stage = tc_b_stage_bytes(C, RB);
+    const int left = budget - 2 * a_slot - nkb * u_kb;
+    if (left < 3 * w_stage) continue;
+    PairParams p{};
+    p.C = C; p.k = k; p.dil = dil; p.nkb = nkb; p.MT = MT; p.Rout = kTileM * MT - (k - 1);
+    p.Rbox = box; p.nload = nload; p.a_slots = 2; p.a_slot_bytes = a_slot;
+    p.stages = left / w_stage > 8 ? 8 : left / w_stage; p.w_stage_bytes = w_stage; p.u_kb_bytes = u_kb;
+    p.slope1 = 0.1f;
+    *out = p;
+    return true;
+  }
+  return false;
+}
+
+template <typename TOp, int KB, class Epi>
+int launch_pair(fse_vocoder* h, const PairParams& p, const CUtensorMap* mA, const ConvW& c1, const ConvW& c2, const Epi& epi, cudaStream_t st) {
+  static bool attr_set[kMaxDevices] = {};
+  int dev = 0;
+  FSE_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices) return fail(FSE_EINVAL, "device ordinal %d out of range", dev);
+  auto kern = resblock_pair_kernel<TOp, KB, Epi>;
+  if (!attr_set[dev]) {
+    FSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[dev] = true;
+  }
+  const size_t smem = 1024 + static_cast<size_t>(p.a_slots) * p.a_slot_bytes + static_cast<size_t>(p.stages) * p.w_stage_bytes +
+                      static_cast<size_t>(p.nkb) * p.u_kb_bytes + kEpiScratchBytes + 256;
+  const int jobs = p.B * ((p.T + p.Rout - 1) / p.Rout);
+  const int num_sms = device_sm_count(dev);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(jobs < num_sms ? jobs : num_sms);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FSE_CUDA(cudaLaunchKernelEx(&cfg, kern, *mA, c1.map, c2.map, p, static_cast<const float*>(c1.bias), epi));
+  FSE_CUDA(cudaGetLastError());
+  return FSE_OK;
+}
+
+// y = x + conv2(lrelu(conv1(xa))) as one launch when the job fits; *fused tells the caller whether it ran
+template <typename TOp, class Epi>
+int run_pair(fse_vocoder* h, const ConvW& c1, const ConvW& c2, const void* A, int B, int T, const Epi& epi, cudaStream_t st, bool* fused) {
+  *fused = false;
+  if (!h->tc || !h->fuse_pair || c1.KB != c2.KB || c1.ntaps != c2.ntaps || c1.ntaps < 2 || c1.N != c1.Cin || c2.N != c1.N) return FSE_OK;
+  const int es = h->bf16 ? 2 : 4;
+  const int dil = c1.ntaps > 1 ? c1.offs[1] - c1.offs[0] : 1;
+  PairParams p{};
+  if (!plan_pair(c1.N, c1.ntaps, dil, c1.KB, es, &p)) return FSE_OK;
+  p.B = B; p.T = T;
+  const CUtensorMap* mA = nullptr;
+  FSE_TRY(get_act_map(h, A, c1.Cin, T, B, c1.KB, p.Rbox, &mA));
+  ++h->launches;
+  h->prof.begin(3, st);
+  int rc = FSE_OK;
+  if constexpr (std::is_same<TOp, __nv_bfloat16>::value) {
+    rc = c1.KB == 64 ? launch_pair<TOp, 64, Epi>(h, p, mA, c1, c2, epi, st) : launch_pair<TOp, 32, Epi>(h, p, mA, c1, c2, epi, st);
+  } else {
+    if (c1.KB != 32) { h->prof.end(st); --h->launches; return FSE_OK; }
+    rc = launch_pair<TOp, 32, Epi>(h, p, mA, c1, c2, epi, st);
+  }
+  h->prof.end(st);
+  *fused = rc == FSE_OK;
+  return rc;
+}
+
 template <typename TOp>
 int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, void* ws, cudaStream_t st) {
   VWs w = vcarve(h, ws, B, T);
@@ -382,29 +479,45 @@ int forward_impl(fse_vocoder* h, const float* mel, float* wav, int B, int T, voi
       for (int m = 0; m < h->nconv; ++m) {
         const ConvW& a = h->c1[(i * nk + j) * 3 + m];
         const ConvW& c = h->rb2 ? a : h->c2[(i * nk + j) * 3 + m];
-        if (!h->rb2) {
-          EpiAct<TOp> epi{a.bias, static_cast<TOp*>(w.tmp), Cout, Tout, 0.1f};
-          FSE_TRY((run_conv<TOp>(h, a, m == 0 ? w.xa : w.ya, B, Tout, Tout, epi, st, 2)));
-        }
-        const void* src2 = h->rb2 ? (m == 0 ? w.xa : w.ya) : w.tmp;      // ResBlock2: the dilated conv itself carries the residual add
+        const void* src1 = m == 0 ? w.xa : (m == 1 ? w.ya : w.ya2);
+        const float* res_in = m == 0 ? w.x : (m == 1 ? w.y : w.y2);
+        float* y_out = m == 0 ? w.y : w.y2;
+        void* ya_out = m == 0 ? w.ya : w.ya2;
+        const void* src2 = h->rb2 ? src1 : w.tmp;      // ResBlock2: the dilated conv itself carries the residual add
         {
           const int kind = m < h->nconv - 1 ? 0 : (nk == 1 ? 3 : (j == 0 ? 1 : (j == nk - 1 ? 3 : 2)));
           auto fill = [&](auto& epi) {
-            epi.bias = c.bias; epi.res = m == 0 ? w.x : w.y; epi.y = w.y; epi.ya = static_cast<TOp*>(w.ya);
+            epi.bias = c.bias; epi.res = res_in; epi.y = y_out; epi.ya = static_cast<TOp*>(ya_out);
             epi.xs = w.xs; epi.next_a = static_cast<TOp*>(w.ua); epi.final_f32 = last_stage ? w.xs : nullptr;
             epi.N = Cout; epi.T = Tout;
             epi.kind = kind;
             epi.num_kernels = static_cast<float>(nk);
             epi.slope_next = last_stage ? 0.01f : 0.1f;   // F.leaky_relu default slope before conv_post (hifigan.py:138)
           };
+          // ResBlock1: conv1 -> lrelu -> conv2 -> + residual as ONE kernel when the job fits (resblock_fused.cuh), else conv1 to
+          // `tmp` (EpiAct) followed by conv2 with the residual epilogue
+          auto conv1_unfused = [&]() -> int {
+            if (h->rb2) return FSE_OK;
+            EpiAct<TOp> e1{a.bias, static_cast<TOp*>(w.tmp), Cout, Tout, 0.1f};
+            return run_conv<TOp>(h, a, src1, B, Tout, Tout, e1, st, 2);
+          };
+          bool fused = false;
           if (kind >= 2 && !(kind == 3 && nk == 1)) {
             EpiResAdd<TOp, true> epi{};
             fill(epi);
-            FSE_TRY((run_conv<TOp>(h, c, src2, B, Tout, Tout, epi, st, 3)));
+            if (!h->rb2) FSE_TRY((run_pair<TOp>(h, a, c, src1, B, Tout, epi, st, &fused)));
+            if (!fused) {
+              FSE_TRY(conv1_unfused());
+              FSE_TRY((run_conv<TOp>(h, c, src2, B, Tout, Tout, epi, st, 3)));
+            }
           } else {
             EpiResAdd<TOp, false> epi{};
             fill(epi);
-            FSE_TRY((run_conv<TOp>(h, c, src2, B, Tout, Tout, epi, st, 3)));
+            if (!h->rb2) FSE_TRY((run_pair<TOp>(h, a, c, src1, B, Tout, epi, st, &fused)));
+            if (!fused) {
+              FSE_TRY(conv1_unfused());
+              FSE_TRY((run_conv<TOp>(h, c, src2, B, Tout, Tout, epi, st, 3)));
+            }
           }
         }
       }
@@ -457,6 +570,7 @@ int fse_vocoder_create(const fse_vocoder_config* cfg, fse_vocoder** out) {
   h->rb2 = cfg->resblock == 2;
   h->nconv = h->rb2 ? 2 : 3;
   if (const char* e = getenv("FSE_VOC_SHARED_A")) h->shared_a = atoi(e) != 0;
+  if (const char* e = getenv("FSE_VOC_FUSE")) h->fuse_pair = atoi(e) != 0;
   if (const char* e = getenv("FSE_VOC_MT")) { h->multi_tile = atoi(e) != 0; h->multi_tile_level = atoi(e); }
   *out = h;
   return FSE_OK;
