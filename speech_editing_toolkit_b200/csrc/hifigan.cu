@@ -85,6 +85,9 @@ struct EpiResAdd {
       const float4 v = reinterpret_cast<const float4*>(res + o)[i];
       aux[4 * i] = v.x; aux[4 * i + 1] = v.y; aux[4 * i + 2] = v.z; aux[4 * i + 3] = v.w;
     }
+    // the running sum is read right before it is updated (load_late), a chunk after this call: pull its lines into L2 now so that
+    // read is not a DRAM round trip per chunk (measured: the end-of-block pairs took 1.5-1.9x the time of the others)
+    if constexpr (kSum) asm volatile("prefetch.global.L2 [%0];" ::"l"(xs + o));
   }
   template <int NV>
   __device__ __forceinline__ void load_late(int b, int t, int n0, float* dst) const {
@@ -198,6 +201,7 @@ struct fse_vocoder {
   bool shared_a = true;   // shared-activation schedule: a job's rows (128*MT + tap halo) are loaded once per channel block and the
                           // k (tap, sub-tile) operands are row-shifted descriptors of it (FSE_VOC_SHARED_A=0: one load per tap).
                           // Measured (B=32 x T=1024): vocoder 54 -> 46 ms once MMA issue and the epilogue stores were fixed.
+  bool fuse_all = false;
   bool fuse_pair = true;  // ResBlock1 conv pairs as one kernel (resblock_fused.cuh) where the job fits shared memory / TMEM
                           // (FSE_VOC_FUSE=0: always two conv_gemm launches per pair)
   long long launches = 0;
@@ -354,16 +358,18 @@ int run_conv(fse_vocoder* h, const ConvW& cw, const void* A, int B, int Trows, i
   return run_conv_gemm<TOp>(h->cfg.mode, p, op, epi, st, LaunchCtx{&h->launches, &h->prof, kind});
 }
 
-// Shape of a fused conv-pair job (resblock_fused.cuh): the largest MT whose two accumulators fit the 512 TMEM columns and whose
-// tiles (2 input slots with the conv1 halo, the intermediate U, >= 3 weight stages, the epilogue scratch) fit shared memory.
+// Shape of a fused conv-pair job (resblock_fused.cuh) for TWO resident CTAs per SM: the largest MT whose two accumulators fit 256
+// TMEM columns and whose tiles (input slot(s) with the conv1 halo, the intermediate U which doubles as the E2 scratch, >= 3 weight
+// stages) fit 112 KB of shared memory.  No such shape (C = 256; C = 128 with fp32 operands) -> the pair runs as two conv_gemm launches.
+constexpr int kPairNE = 4;
 bool plan_pair(int C, int k, int dil, int KB, int es, PairParams* out) {
   const int RB = KB * es;
-  if (C % 32 != 0 || C > 256 || k < 1 || k > kMaxTaps || (RB != 128 && RB != 64)) return false;
+  if (C % 32 != 0 || C > 256 || k < 2 || k > kMaxTaps || (RB != 128 && RB != 64)) return false;
   const int nkb = (C + KB - 1) / KB;
   const int h2 = (k - 1) / 2, h1 = h2 * dil;
-  const int budget = 225 * 1024 - kEpiScratchBytes - 256;
-  for (int MT = 8; MT >= 1; MT >>= 1) {
-    if (2 * MT * C > 512) continue;
+  const int budget = 112 * 1024 - 1024 - 256;
+  for (int MT = 4; MT >= 1; MT >>= 1) {
+    if (2 * MT * C > 256) continue;
     const int need = kTileM * MT + 2 * h1;
     int nload = (need + 255) / 256, box = 0;
     for (;; ++nload) {
@@ -373,13 +379,15 @@ bool plan_pair(int C, int k, int dil, int KB, int es, PairParams* out) {
     const int a_slot = static_cast<int>(align_up(static_cast<size_t>(box) * nload * RB, 1024));
     const int u_rows = (kTileM * MT + k - 1 + 7) / 8 * 8;
     const int u_kb = static_cast<int>(align_up(static_cast<size_t>(u_rows) * RB, 1024));
+    if (nkb * u_kb < kPairNE * 4096) continue;                 // U doubles as the transposition scratch of E2
     const int w_stage = tc_b_stage_bytes(C, RB);
-    const int left = budget - 2 * a_slot - nkb * u_kb;
+    const int a_slots = nkb >= 2 ? 2 : 1;                      // one channel block per conv: the next job's load follows C1 directly
+    const int left = budget - a_slots * a_slot - nkb * u_kb;
     if (left < 3 * w_stage) continue;
     PairParams p{};
     p.C = C; p.k = k; p.dil = dil; p.nkb = nkb; p.MT = MT; p.Rout = kTileM * MT - (k - 1);
-    p.Rbox = box; p.nload = nload; p.a_slots = 2; p.a_slot_bytes = a_slot;
-    p.stages = left / w_stage > 8 ? 8 : left / w_stage; p.w_stage_bytes = w_stage; p.u_kb_bytes = u_kb;
+    p.Rbox = box; p.nload = nload; p.a_slots = a_slots; p.a_slot_bytes = a_slot;
+    p.stages = left / w_stage > 6 ? 6 : left / w_stage; p.w_stage_bytes = w_stage; p.u_kb_bytes = u_kb;
     p.slope1 = 0.1f;
     *out = p;
     return true;
@@ -393,18 +401,19 @@ int launch_pair(fse_vocoder* h, const PairParams& p, const CUtensorMap* mA, cons
   int dev = 0;
   FSE_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= kMaxDevices) return fail(FSE_EINVAL, "device ordinal %d out of range", dev);
-  auto kern = resblock_pair_kernel<TOp, KB, Epi>;
+  auto kern = resblock_pair_kernel<TOp, KB, kPairNE, Epi>;
   if (!attr_set[dev]) {
-    FSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    FSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set[dev] = true;
   }
   const size_t smem = 1024 + static_cast<size_t>(p.a_slots) * p.a_slot_bytes + static_cast<size_t>(p.stages) * p.w_stage_bytes +
-                      static_cast<size_t>(p.nkb) * p.u_kb_bytes + kEpiScratchBytes + 256;
+                      static_cast<size_t>(p.nkb) * p.u_kb_bytes + 256;
   const int jobs = p.B * ((p.T + p.Rout - 1) / p.Rout);
   const int num_sms = device_sm_count(dev);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(jobs < num_sms ? jobs : num_sms);
-  cfg.blockDim = dim3(kTcThreads);
+  cfg.gridDim = dim3(jobs < 2 * num_sms ? jobs : 2 * num_sms);     // persistent: two CTAs per SM
+  cfg.blockDim = dim3(64 + 32 * kPairNE);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -423,6 +432,11 @@ int run_pair(fse_vocoder* h, const ConvW& c1, const ConvW& c2, const void* A, in
   *fused = false;
   if (!h->tc || !h->fuse_pair || c1.KB != c2.KB || c1.ntaps != c2.ntaps || c1.ntaps < 2 || c1.N != c1.Cin || c2.N != c1.N) return FSE_OK;
   const int es = h->bf16 ? 2 : 4;
+  // Measured per stage on B200 (profiles/r02_vocoder_launches_*.csv): the fused kernel wins where the two-kernel form is bound by
+  // HBM bytes or by its single MMA-issue chain on narrow tiles (C = 32 in both kinds: 2.0-2.4x with fp32 operands; C = 64 with
+  // bf16), and is ~10 % slower for C = 64 with fp32 operands, where only MT = 1 fits next to a second resident CTA.
+  // FSE_VOC_FUSE=2 fuses every pair that has a shape.
+  if (!h->fuse_all && c1.N * es > 128) return FSE_OK;
   const int dil = c1.ntaps > 1 ? c1.offs[1] - c1.offs[0] : 1;
   PairParams p{};
   if (!plan_pair(c1.N, c1.ntaps, dil, c1.KB, es, &p)) return FSE_OK;
@@ -570,7 +584,7 @@ int fse_vocoder_create(const fse_vocoder_config* cfg, fse_vocoder** out) {
   h->rb2 = cfg->resblock == 2;
   h->nconv = h->rb2 ? 2 : 3;
   if (const char* e = getenv("FSE_VOC_SHARED_A")) h->shared_a = atoi(e) != 0;
-  if (const char* e = getenv("FSE_VOC_FUSE")) h->fuse_pair = atoi(e) != 0;
+  if (const char* e = getenv("FSE_VOC_FUSE")) { h->fuse_pair = atoi(e) != 0; h->fuse_all = atoi(e) == 2; }
   if (const char* e = getenv("FSE_VOC_MT")) { h->multi_tile = atoi(e) != 0; h->multi_tile_level = atoi(e); }
   *out = h;
   return FSE_OK;

@@ -18,9 +18,13 @@
 //   E2  the pair's residual epilogue (EpiResAdd of hifigan.cu: + bias + fp32 residual, running sum / mean over the parallel
 //       blocks, activation for the next layer), transposed through shared memory so that global accesses are coalesced.
 //
-// Warp roles as in conv_gemm_tc_kernel (warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, 8 epilogue warps); C1 of job i+1
-// runs on the tensor pipe while the epilogue warps are in E2 of job i.  Both operand kinds of the library: bf16 (kind::f16) and
-// fp32 containers (kind::tf32).
+// Warp roles as in conv_gemm_tc_kernel (warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, NE epilogue warps); C1 of job i+1
+// runs on the tensor pipe while the epilogue warps are in E2 of job i.  Within one CTA the four phases of a job are a chain
+// (C1 -> E1 -> C2 -> E2), so the kernel is shaped to run TWO CTAs per SM (NE = 4, <= 112 KB shared memory, <= 256 TMEM columns
+// each): while one CTA's epilogue warps wait for memory the other one's tensor-core phase runs (measured first with one
+// 8-epilogue-warp CTA per SM: no faster than the two-kernel form).  The E2 transposition scratch aliases U, which is dead between
+// C2's completion and the next E1 (a named barrier keeps a fast warp's next E1 away from a slow warp's scratch).
+// Both operand kinds of the library: bf16 (kind::f16) and fp32 containers (kind::tf32).
 #pragma once
 #include "conv_gemm.cuh"
 
@@ -42,8 +46,8 @@ struct PairParams {
 
 __device__ __forceinline__ float lrelu_f(float x, float slope) { return x >= 0.f ? x : x * slope; }
 
-template <typename TOp, int KB, class Epi>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <typename TOp, int KB, int NE, class Epi>
+__global__ void __launch_bounds__(64 + 32 * NE, NE == 4 ? 2 : 1)
 resblock_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW1,
                      const __grid_constant__ CUtensorMap mapW2, PairParams p, const float* __restrict__ bias1, Epi epi) {
   constexpr int ES = static_cast<int>(sizeof(TOp));
@@ -52,13 +56,14 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   constexpr int CH = 32;
   static_assert(RB == 128 || RB == 64, "k-block row must be 128 or 64 bytes");
   static_assert(epi_transposed<Epi>::value, "the pair's second epilogue is the transposed one");
+  static_assert(NE == 4 || NE == 8, "epilogue warps: one or two per TMEM lane quarter");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sW = sA + p.a_slots * p.a_slot_bytes;
   uint8_t* sU = sW + p.stages * p.w_stage_bytes;
-  uint8_t* sScratch = sU + p.nkb * p.u_kb_bytes;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sScratch + kEpiScratchBytes);
+  uint8_t* sScratch = sU;                        // E2's per-warp 4 KB transposition scratch aliases U (NE * 4 KB <= nkb * u_kb_bytes)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sU + p.nkb * p.u_kb_bytes);
   uint64_t* empty = full + p.stages;
   uint64_t* a_full = empty + p.stages;
   uint64_t* a_empty = a_full + p.a_slots;
@@ -86,8 +91,8 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     if (lane == 0) {
       for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
       for (int i = 0; i < p.a_slots; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
-      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kEpiWarps); }
-      ptx::mbar_init(u_full, kEpiWarps);
+      for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], NE); }
+      ptx::mbar_init(u_full, NE);
       ptx::mbar_init(u_empty, 1);
       ptx::fence_barrier_init();
     }
@@ -211,7 +216,8 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     // ------------------------------------------------------------ epilogue warps
     const int ew = warp - 2;
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
-    const int half = ew >> 2;                // two warps share a quarter and split the column chunks
+    constexpr int kSplit = NE / 4;           // warps per lane quarter: they split the column chunks
+    const int half = ew >> 2;
     const int cpb = C / CH;                  // chunks per 128-frame sub-tile
     const int nchunks = MT * cpb;
     float* stg = reinterpret_cast<float*>(sScratch) + ew * 1024;
@@ -224,8 +230,11 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       // ---- E1: accumulator 1 -> bias + lrelu -> operand type -> U (lane = frame = TMEM lane, 32 channels per tcgen05.ld)
       ptx::mbar_wait(&acc_full[0], it & 1);
       ptx::tc_fence_after();
-      if (it > 0) ptx::mbar_wait(u_empty, (it - 1) & 1);          // conv2 of the previous job has read U
-      for (int c = half; c < nchunks; c += 2) {
+      if (it > 0) {
+        ptx::mbar_wait(u_empty, (it - 1) & 1);                     // conv2 of the previous job has read U
+        asm volatile("bar.sync 1, %0;" ::"n"(NE * 32) : "memory");   // ... and every epilogue warp is done with its E2 scratch (= U)
+      }
+      for (int c = half; c < nchunks; c += kSplit) {
         const int mt = c / cpb, n0 = (c % cpb) * CH;
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(mt * C + n0), r);
@@ -283,15 +292,15 @@ resblock_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       }
       ptx::mbar_wait(&acc_full[1], it & 1);
       ptx::tc_fence_after();
-      for (int c = half; c < nchunks; c += 2) {
+      for (int c = half; c < nchunks; c += kSplit) {
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(lane_base + c * CH, r);
         ptx::tmem_wait_ld();
         if constexpr (Epi::kAux > 0) {
-          if (c + 2 < nchunks) {
+          if (c + kSplit < nchunks) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              if (VALID(c + 2, i)) epi.template load_aux<4>(b, o0 + R_OF(c + 2, i), N_OF(c + 2), aux_next[i]);
+              if (VALID(c + kSplit, i)) epi.template load_aux<4>(b, o0 + R_OF(c + kSplit, i), N_OF(c + kSplit), aux_next[i]);
           }
         }
 #pragma unroll
