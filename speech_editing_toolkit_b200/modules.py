@@ -22,6 +22,11 @@ from .engine import CampNetKernel, CondEncoderKernel, Denoiser, MelEncoderKernel
 from .hparams import hparams as _global_hparams
 
 
+# Arithmetic of the FluentSpeech path when hparams['b200_mode'] is not given: tcgen05 kind::tf32, the reference's own GPU arithmetic
+# (cuDNN TF32 convolutions).  'tc_bf16' is ~1.6x faster at ~6x the error; 'simt_f32' is the exact-fp32 checking mode.  CampNet keeps
+# 'tc_bf16' as its default (its tensor-core attention kernel is bf16).
+DEFAULT_MODE = "tc_tf32"
+
 class _ResidualBlockParams(nn.Module):
     """Parameter container with the reference ResidualBlock's names/shapes (diffnet.py:60-66)."""
 
@@ -48,7 +53,7 @@ class DiffNetB200(nn.Module):
         self.n_layers = hp["residual_layers"]
         self.channels = C = hp["residual_channels"]
         self.dilation_cycle_length = hp["dilation_cycle_length"]
-        self.mode = hp.get("b200_mode", "tc_bf16")
+        self.mode = hp.get("b200_mode", DEFAULT_MODE)
         self.input_projection = nn.Conv1d(in_dims, C, 1)
         nn.init.kaiming_normal_(self.input_projection.weight)
         self.mlp = nn.Sequential(nn.Linear(C, C * 4), nn.Identity(), nn.Linear(C * 4, C))   # index 1 is Mish (no params)
@@ -183,7 +188,7 @@ class FastSpeechB200(nn.Module):
         if hp.get("use_spk_id", False):
             raise NotImplementedError("use_spk_id is false in the speech-editing configs; only the spk_embed branch is native")
         self.dict_size = dict_size
-        self.mode = hp.get("b200_mode", "tc_bf16")
+        self.mode = hp.get("b200_mode", DEFAULT_MODE)
         self.encoder = _ConvBlocksParams(H, hp.get("enc_dilations", [1, 1, 1, 1]), hp.get("enc_kernel_size", 5),
                                          hp.get("layers_in_block", 2), hp.get("enc_post_net_kernel", 3))
         self.encoder.embed_tokens = _embedding(dict_size, H, 0)
@@ -392,7 +397,7 @@ class GaussianDiffusionB200(nn.Module):
             fs = FastSpeechB200(len(phone_encoder), hp, out_dims)
         self.fs = fs
         self.mel_encoder = mel_encoder if mel_encoder is not None else MelEncoderB200(out_dims, hp.get("hidden_size", 192),
-                                                                                      hp.get("b200_mode", "tc_bf16"))
+                                                                                      hp.get("b200_mode", DEFAULT_MODE))
         self.mel_bins = out_dims
         self.time_scale = time_scale
         self.num_timesteps = int(timesteps)
@@ -412,7 +417,7 @@ class GaussianDiffusionB200(nn.Module):
         self._sched_key = None
 
     @classmethod
-    def from_reference(cls, ref_model, mode: str = "tc_bf16", native_fs: bool = True):
+    def from_reference(cls, ref_model, mode: str = DEFAULT_MODE, native_fs: bool = True):
         """Convert an instantiated reference GaussianDiffusion: copies the denoise_fn / mel_encoder / fs weights into the native
         drop-ins (native_fs=False keeps the reference's own FastSpeech module as the condition encoder)."""
         rd = ref_model.denoise_fn

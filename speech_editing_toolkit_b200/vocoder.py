@@ -55,7 +55,7 @@ class HifiGANB200(BaseVocoder):
     newest `model_ckpt_steps_*.ckpt` (state_dict['model_gen'], weight_g / weight_v pairs)."""
 
     def __init__(self, base_dir: str = None, config: dict = None, state_dict: dict = None, mode: str = None):
-        mode = mode or hparams.get("b200_mode", "tc_bf16")
+        mode = mode or hparams.get("b200_mode", "tc_tf32")      # the reference's GPU arithmetic (see modules.DEFAULT_MODE)
         if state_dict is None:
             base_dir = base_dir or hparams["vocoder_ckpt"]
             with open(f"{base_dir}/config.yaml") as f:
