@@ -333,6 +333,33 @@ int fse_mel_frontend_forward(fse_mel_frontend* h, const float* wav, float* mel, 
                              int64_t workspace_bytes, void* stream);
 int64_t fse_mel_frontend_last_launches(const fse_mel_frontend* h);
 
+/* --- training-mode DiffNet (BASELINE configs[4]) -----------------------------------------
+ * The denoiser call of GaussianDiffusion.forward(infer=False) (spec_denoiser.py:168-176: x_0_pred = denoise_fn(x_t, t, cond)) with
+ * the activations its backward needs kept in the workspace, and the activation-gradient chain of that backward; every GEMM of both
+ * is a conv-GEMM launch of this library.  The weight gradients are plain GEMMs over tensors left in the workspace (fse_train_layout)
+ * and are taken by the caller with library GEMMs, as are the losses, the optimizer and the gradient all-reduce
+ * (speech_editing_toolkit_b200/train.py).  mode: FSE_MODE_TC_BF16 | FSE_MODE_TC_TF32 | FSE_MODE_SIMT_F32. */
+typedef struct fse_trainer fse_trainer;
+int fse_train_create(const fse_denoiser_config* cfg, fse_trainer** out);
+void fse_train_destroy(fse_trainer* h);
+/* the `denoise_fn.*` parameter tensors as they sit on the DEVICE (fse_tensor.data = device pointers, which must stay valid and
+ * are read again by forward / backward for the biases): repacked into operand layouts by device kernels on `stream`; call after
+ * every optimizer step */
+int fse_train_load_weights_device(fse_trainer* h, const fse_tensor* tensors, int32_t n, void* stream);
+int64_t fse_train_workspace_bytes(const fse_trainer* h, int32_t B, int32_t T);
+/* byte offsets inside the workspace of the 18 buffers listed in csrc/denoiser_train.cuh (TrainWs): 0 x_rows, 1 h0, 2 h, 3 S, 4 y,
+ * 5 hin[L], 6 sg[L], 7 tf[L], 8 u[L], 9 s, 10 r, 11 cond (bf16 copy), 12 dx_rows, 13 dz, 14 dS, 15 dh, 16 dres[L], 17 dy[B*T, L*2C] */
+int fse_train_layout(const fse_trainer* h, int32_t B, int32_t T, int64_t* offsets, int32_t n);
+/* replaces DiffNet.forward under autograd (diffnet.py:110-132): x_t [B,M,T], cond [B,T,H] (physical layout), d [L,B,C] =
+ * diffusion_projection_l(mlp(SinusoidalPosEmb(t))) computed by the caller (a [B,256] problem) -> x0 [B,M,T] */
+int fse_train_forward(fse_trainer* h, const float* x_t, const float* cond, const float* d, float* x0, int32_t B, int32_t T,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+/* replaces the activation-gradient part of autograd's backward through DiffNet: dx0 [B,M,T] -> dcond [B,T,H]; leaves dz, dS, dh
+ * (= gradient of h_0), dres[l], dy[l] in the workspace for the caller's weight-gradient GEMMs */
+int fse_train_backward(fse_trainer* h, const float* dx0, float* dcond, int32_t B, int32_t T, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+int64_t fse_train_last_launches(const fse_trainer* h);
+
 /* --- kernel timing (opt-in) -------------------------------------------------------------------
  * When enabled, every kernel the handle launches is bracketed by CUDA events on the launch stream;
  * *_profile_read waits for them and returns the summed device time (ms) and launch count per kind

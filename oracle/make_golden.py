@@ -417,6 +417,38 @@ def mel_frontend_fixture():
     print("mel_frontend", mel.shape, float(mel.mean()))
 
 
+def train_fixture():
+    """Gradients of the UNMODIFIED reference DiffNet under torch.autograd (diffnet.py:60-132; the denoiser call of
+    GaussianDiffusion.forward(infer=False), spec_denoiser.py:168-176): `python oracle/make_golden.py train` writes
+    tests/golden/diffnet_train.npz: x0 for seeded (x_t, t, cond), and for a seeded upstream gradient dx0 the gradient of cond and of
+    every parameter (small ones whole, large ones as every 61st element + their L2 norm)."""
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(SEED)
+    torch.set_num_threads(8)
+    L, B, T = 4, 2, 80
+    hp = refshim.install("egs/spec_denoiser.yaml", overrides=f"timesteps=100,residual_layers={L}")
+    from utils.commons.hparams import hparams as ref_hparams
+    ref_hparams["residual_layers"] = L
+    from modules.speech_editing.spec_denoiser.diffnet import DiffNet
+    net = DiffNet(hp["audio_num_mel_bins"]).train()
+    net.load_state_dict(to_torch(synth.denoiser_state_dict(SEED + 31, layers=L)), strict=True)
+    rs = np.random.RandomState(SEED + 32)
+    x = rs.standard_normal((B, 80, T)).astype(np.float32)
+    cond = synth.synthetic_cond(SEED + 33, B, T)                       # [B, T, H]
+    t = np.array([7, 93], dtype=np.int64)
+    dx0 = (rs.standard_normal((B, 80, T)) * 0.1).astype(np.float32)
+    cond_t = torch.from_numpy(cond).requires_grad_(True)
+    x0 = net(torch.from_numpy(x)[:, None], torch.from_numpy(t), cond_t.transpose(1, 2))[:, 0]
+    x0.backward(torch.from_numpy(dx0))
+    out = dict(seed=SEED + 31, B=B, T=T, layers=L, x=x, t=t, dx0=dx0, x0=x0.detach().numpy(), dcond=cond_t.grad.numpy())
+    for name, p in net.named_parameters():
+        g = p.grad.numpy().reshape(-1)
+        out["gnorm__" + name] = np.float64(np.sqrt((g.astype(np.float64) ** 2).sum()))
+        out["g__" + name] = g if g.size <= 4096 else g[::61].copy()
+    np.savez_compressed(os.path.join(OUT, "diffnet_train.npz"), **out)
+    print("diffnet_train", x0.shape, float(np.abs(out["dcond"]).mean()), len([k for k in out if k.startswith("g__")]), "parameter gradients")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "mel_encoder":
         mel_encoder_fixture()
@@ -430,6 +462,8 @@ if __name__ == "__main__":
         bench_config_fixture()
     elif len(sys.argv) > 1 and sys.argv[1] == "mel_frontend":
         mel_frontend_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "train":
+        train_fixture()
     else:
         main()
         mel_encoder_fixture()
@@ -438,3 +472,4 @@ if __name__ == "__main__":
         edit_region_fixture()
         bench_config_fixture()
         mel_frontend_fixture()
+        train_fixture()

@@ -116,6 +116,14 @@ SIGNATURES = {
     "fse_mel_frontend_workspace_bytes": (C.c_int64, [_P, C.c_int32, C.c_int64]),
     "fse_mel_frontend_forward": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, _P, C.c_int64, _P]),
     "fse_mel_frontend_last_launches": (C.c_int64, [_P]),
+    "fse_train_create": (C.c_int, [C.POINTER(DenoiserConfig), C.POINTER(_P)]),
+    "fse_train_destroy": (None, [_P]),
+    "fse_train_load_weights_device": (C.c_int, [_P, C.POINTER(Tensor), C.c_int32, _P]),
+    "fse_train_workspace_bytes": (C.c_int64, [_P, C.c_int32, C.c_int32]),
+    "fse_train_layout": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int32]),
+    "fse_train_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
+    "fse_train_backward": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
+    "fse_train_last_launches": (C.c_int64, [_P]),
     "fse_denoiser_profile": (C.c_int, [_P, C.c_int32]),
     "fse_denoiser_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "fse_vocoder_profile": (C.c_int, [_P, C.c_int32]),

@@ -931,3 +931,5 @@ int fse_denoiser_profile_read(fse_denoiser* h, double* ms_by_kind, int64_t* laun
 }
 
 }  // extern "C"
+
+#include "denoiser_train.cuh"

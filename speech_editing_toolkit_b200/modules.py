@@ -82,6 +82,11 @@ class DiffNetB200(nn.Module):
 
     def forward(self, spec: torch.Tensor, diffusion_step: torch.Tensor, cond: torch.Tensor) -> torch.Tensor:
         """spec[B,1,M,T], diffusion_step[B], cond[B,H,T] -> [B,1,M,T]   (diffnet.py:110-132)"""
+        if torch.is_grad_enabled() and (cond.requires_grad or spec.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
+            # training (GaussianDiffusion.forward(infer=False), spec_denoiser.py:168-176): native forward + activation-gradient chain,
+            # weight gradients by library GEMMs (train.py)
+            from .train import diffnet_train_forward
+            return diffnet_train_forward(self, spec, diffusion_step.reshape(-1).long(), cond)
         x = spec[:, 0]
         # the reference hands over cond as decoder_inp.transpose(1,2): its physical layout is already [B,T,H]
         cond_bth = cond.transpose(1, 2).contiguous()

@@ -1,0 +1,88 @@
+"""Training-mode DiffNet: forward and gradients of `DiffNetB200` under autograd — native forward and
+activation-gradient chain (fse_train_*), weight gradients by library GEMMs — against tests/golden/diffnet_train.npz, the gradients
+torch.autograd computes through the UNMODIFIED reference DiffNet (oracle/make_golden.py train).
+
+Stated tolerances: FSE_MODE_SIMT_F32 relative L2 <= 1e-4 on every gradient; FSE_MODE_TC_TF32 <= 5e-3; FSE_MODE_TC_BF16 <= 3e-2
+(bf16 operands in the forward, in the saved activations and in the weight-gradient GEMMs)."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+HP = dict(audio_num_mel_bins=80, hidden_size=192, residual_channels=256, dilation_cycle_length=1)
+TOL = {"simt_f32": 1e-4, "tc_tf32": 5e-3, "tc_bf16": 3e-2}
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.sqrt(((a - b) ** 2).sum()) / max(np.sqrt((b ** 2).sum()), 1e-30))
+
+
+def _module(g, mode):
+    from speech_editing_toolkit_b200 import synth
+    from speech_editing_toolkit_b200.modules import DiffNetB200
+    L = int(g["layers"])
+    net = DiffNetB200(80, dict(HP, residual_layers=L, b200_mode=mode)).cuda().train()
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in synth.denoiser_state_dict(int(g["seed"]), layers=L).items()})
+    return net
+
+
+@pytest.mark.parametrize("mode", ["simt_f32", "tc_tf32", "tc_bf16"])
+def test_diffnet_gradients_vs_reference_autograd_fixture(lib_built, mode):
+    _need_gpu()
+    from speech_editing_toolkit_b200 import synth
+    g = golden("diffnet_train.npz")
+    B, T = int(g["B"]), int(g["T"])
+    net = _module(g, mode)
+    cond = torch.from_numpy(synth.synthetic_cond(int(g["seed"]) + 2, B, T)).cuda().requires_grad_(True)
+    x = torch.from_numpy(g["x"]).cuda()
+    x0 = net(x[:, None], torch.from_numpy(g["t"]).cuda(), cond.transpose(1, 2))[:, 0]
+    x0.backward(torch.from_numpy(g["dx0"]).cuda())
+    tol = TOL[mode]
+    e_fwd, e_cond = rel_l2(x0.detach().cpu().numpy(), g["x0"]), rel_l2(cond.grad.cpu().numpy(), g["dcond"])
+    worst = ("", 0.0)
+    for name, p in net.named_parameters():
+        assert p.grad is not None, name
+        got = p.grad.detach().cpu().numpy().reshape(-1)
+        want = g["g__" + name]
+        got_s = got if got.size <= 4096 else got[::61]
+        e = rel_l2(got_s, want)
+        n = float(np.sqrt((got.astype(np.float64) ** 2).sum()))
+        assert abs(n - float(g["gnorm__" + name])) <= 2 * tol * float(g["gnorm__" + name]) + 1e-12, (name, n, float(g["gnorm__" + name]))
+        if e > worst[1]:
+            worst = (name, e)
+        assert e < tol, (name, e)
+    print(f"[margin] DiffNet training {mode}: x0 rel-L2 {e_fwd:.3e}, dcond {e_cond:.3e}, worst parameter gradient {worst[0]} {worst[1]:.3e}")
+    assert e_fwd < tol and e_cond < tol
+
+
+def test_train_step_decreases_the_loss_and_is_deterministic(lib_built):
+    """A few AdamW steps of the denoiser branch of the training step (train.train_step: q_sample, DiffNet, masked l1 + ssim, backward,
+    optimizer) on one synthetic batch with fixed t / noise: the loss goes down, and two runs from the same state give the same losses."""
+    _need_gpu()
+    from speech_editing_toolkit_b200 import schedule, synth, train
+    from speech_editing_toolkit_b200.modules import DiffNetB200
+    L, B, T = 4, 2, 256
+    sched = {k: torch.from_numpy(v).cuda() for k, v in schedule.diffusion_buffers(100).items()}
+    batch = synth.synthetic_edit_batch(5, B, T)
+    data = {"ref_mels": torch.from_numpy(batch["ref_mels"]).cuda(), "time_mel_masks": torch.from_numpy(batch["time_mel_masks"]).cuda(),
+            "cond": torch.from_numpy(synth.synthetic_cond(5, B, T)).cuda()}
+    t = torch.tensor([10, 60], device="cuda")
+    noise = torch.randn(B, 1, 80, T, generator=torch.Generator().manual_seed(0)).cuda()
+    runs = []
+    for _ in range(2):
+        net = DiffNetB200(80, dict(HP, residual_layers=L, b200_mode="tc_bf16")).cuda().train()
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in synth.denoiser_state_dict(9, layers=L).items()})
+        opt = torch.optim.AdamW(net.parameters(), lr=2e-3, betas=(0.9, 0.98), weight_decay=0.0)
+        runs.append([train.train_step(net, sched, data, opt, t=t, noise=noise)["total"] for _ in range(8)])
+    assert runs[0][-1] < 0.9 * runs[0][0], runs[0]
+    assert runs[0] == runs[1]
+    print(f"[margin] train_step: loss {runs[0][0]:.4f} -> {runs[0][-1]:.4f} in 8 steps")
