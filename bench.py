@@ -40,6 +40,7 @@ def parse():
                          "(cuDNN TF32 convolutions); tc_bf16 = bf16 operands (faster, narrower than the reference: reported as a sub-record)")
     ap.add_argument("--no-alt-mode", action="store_true", help="skip the short second measurement in the other tensor-core mode")
     ap.add_argument("--no-campnet", action="store_true", help="skip the CampNet (BASELINE configs[3]) sub-record")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step (BASELINE configs[4]) sub-record")
     ap.add_argument("--no-vocoder", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -488,6 +489,54 @@ def run_b200(args):
         step_cond_encoder(0)
         cond_ms = timed(step_cond_encoder, args.steps) / args.steps
 
+    def train_record(steps=5, mode="tc_bf16"):
+        """BASELINE configs[4]: the denoiser branch of the FluentSpeech training step in bf16, data-parallel over the ranks of this
+        launch (one bucketed NCCL all-reduce per residual layer, overlapped with the remaining weight-gradient GEMMs), 32 x 1024-frame
+        synthetic batches per GPU: q_sample, DiffNet forward + backward (native data path, library-GEMM weight gradients), masked
+        l1 + ssim loss, fused AdamW.  The condition encoder's forward / backward is not part of it (cond is a resident input)."""
+        from speech_editing_toolkit_b200 import train
+        from speech_editing_toolkit_b200.modules import DiffNetB200
+        hp_t = dict(audio_num_mel_bins=80, hidden_size=192, residual_layers=20, residual_channels=256, dilation_cycle_length=1, b200_mode=mode)
+        net = DiffNetB200(80, hp_t).to(dev).train()
+        net.load_state_dict({k: torch.from_numpy(v) for k, v in synth.denoiser_state_dict(1234).items()})
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-4, betas=(0.9, 0.98), weight_decay=0.0, fused=True)
+        sched = {k: torch.from_numpy(v).to(dev) for k, v in schedule.diffusion_buffers(S).items()}
+        data = {"ref_mels": ref_d, "time_mel_masks": mask_d, "cond": cond_d}
+        red = train.BucketedAllReduce(dict(net.named_parameters())) if world > 1 else None
+        losses = None
+        for _ in range(2):
+            losses = train.train_step(net, sched, data, opt, reducer=red)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            losses = train.train_step(net, sched, data, opt, reducer=red)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            tt_ = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt_, op=dist.ReduceOp.MAX)
+            ms = float(tt_.item())
+        flops = 3 * 25.13e6 * B * T                      # forward + backward = 3 x the forward's algorithmic FLOPs (BASELINE.md)
+        rec = {"workload": f"FluentSpeech training step, denoiser branch (DiffNet fwd + bwd, masked l1 + ssim, AdamW), {B} x {T} frames per GPU, "
+                           f"DDP x{world} (BASELINE configs[4])", "mode": mode, "dtype": DTYPE[mode], "ms_per_step": ms, "steps": steps,
+               "value": world * B * T / (ms / 1e3), "unit": "mel-frames/s (training)", "n_gpus": world,
+               "achieved_tflops_per_gpu": flops / (ms / 1e3) / 1e12, "loss": losses,
+               "allreduce": "one async NCCL all-reduce per residual layer's gradients, overlapped with the following layers' weight-gradient GEMMs" if world > 1 else None}
+        del net, opt
+        torch.cuda.empty_cache()
+        return rec
+
+    train_rec = None
+    if not args.no_train:
+        try:
+            train_rec = train_record()
+        except Exception as e:                           # a reported extra: never takes the bench line down
+            train_rec = {"error": repr(e)}
+            if world > 1:
+                raise
+
     def alt_record(mode, steps=3):
         """The same resident step in the other tensor-core mode (3 steps after 3 warm-ups, rank 0's GPU only, no collective):
         reported next to the headline so both precisions are on the driver's record."""
@@ -585,6 +634,8 @@ def run_b200(args):
         line["alt_mode"] = alt
     if camp is not None:
         line["campnet"] = camp
+    if train_rec is not None:
+        line["train_step"] = train_rec
     if eager is not None:
         line["eager_gpu_baseline"] = eager
     print(json.dumps(line))

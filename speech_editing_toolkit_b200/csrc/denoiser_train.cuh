@@ -12,7 +12,7 @@
 //
 //   forward, per layer l:   hin = h + d_l                      (add_bcast_cast_kernel; d_l = diffusion_projection(temb), given)
 //                           y   = conv_k3(hin) + W_cp cond + b (GEMM, K = 3C + H, fp32 out)
-//                           u   = sigmoid(y[:, :C]) * tanh(y[:, C:])      (gate_fwd_kernel; sigmoid / tanh values kept)
+//                           u   = sigmoid(y[:, :C]) * tanh(y[:, C:])      (gate_fwd_kernel; du/dg and du/df kept)
 //                           o   = W_op u + b;  h <- (h + o[:, :C]) / sqrt(2);  S += o[:, C:]     (GEMM, EpiResSkip)
 //            tail:          x0  = W_out relu(W_skip (S / sqrt(L)) + b) + b
 //   backward, given dx0:    dz = (W_out^T dx0) * [r > 0];  dS = W_skip^T dz / sqrt(L)
@@ -26,6 +26,18 @@
 #pragma once
 
 namespace fse {
+
+// Operand copies written for a kind::tf32 GEMM are rounded to tf32 (round-to-nearest) here: the tensor core would otherwise
+// TRUNCATE the fp32 container, a one-sided error twice as large (measured on the gradient fixture: 2.1e-2 -> see the test).
+template <int NV>
+__device__ __forceinline__ void st_operand(float* p, const float* v, bool rnd) {
+  float w[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) w[i] = rnd ? ptx::round_tf32(v[i]) : v[i];
+  st_vec<NV>(p, w);
+}
+template <int NV>
+__device__ __forceinline__ void st_operand(__nv_bfloat16* p, const float* v, bool) { st_vec<NV>(p, v); }
 
 // ------------------------------------------------------------------ epilogues
 template <typename TOp>
@@ -89,13 +101,14 @@ struct EpiReluBwd {
   const TOp* r;         // [B*T, N]
   TOp* out;             // [B*T, N]
   int N, T;
+  bool rnd;
   template <int NV>
   __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float*) const {
     const size_t o = (static_cast<size_t>(b) * T + t) * N + n0;
     float v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = to_f32(r[o + i]) > 0.f ? acc[i] : 0.f;
-    st_vec<NV>(out + o, v);
+    st_operand<NV>(out + o, v, rnd);
   }
 };
 
@@ -106,36 +119,38 @@ struct EpiScaleCast {                      // out = op(acc * scale)
   TOp* out;
   int N, T;
   float scale;
+  bool rnd;
   template <int NV>
   __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float*) const {
     float v[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = acc[i] * scale;
-    st_vec<NV>(out + (static_cast<size_t>(b) * T + t) * N + n0, v);
+    st_operand<NV>(out + (static_cast<size_t>(b) * T + t) * N + n0, v, rnd);
   }
 };
 
-// du -> dy = [dg | df]:  dg = du tanh(f) sg (1 - sg),  df = du sg (1 - tanh(f)^2)   (backward of u = sigmoid(g) tanh(f))
+// du -> dy = [dg | df]:  dg = du * (tanh(f) sg (1 - sg)),  df = du * (sg (1 - tanh(f)^2))   (backward of u = sigmoid(g) tanh(f);
+// the two factors were formed in fp32 by gate_fwd_kernel)
 template <typename TOp>
 struct EpiGateBwd {
   static constexpr int kAux = 0;
   static constexpr bool kTransposed = true;
-  const TOp* sg;        // [B*T, C] sigmoid(gate) of this layer
-  const TOp* tf;        // [B*T, C] tanh(filter)
+  const TOp* sg;        // [B*T, C] du/dg of this layer
+  const TOp* tf;        // [B*T, C] du/df
   TOp* dy;              // [B*T, ld] rows; this layer's 2C columns start at col0
   int C, T, ld, col0;
+  bool rnd;
   template <int NV>
   __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float*) const {
     const size_t row = static_cast<size_t>(b) * T + t;
     float dg[NV], df[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const float s = to_f32(sg[row * C + n0 + i]), th = to_f32(tf[row * C + n0 + i]);
-      dg[i] = acc[i] * th * s * (1.f - s);
-      df[i] = acc[i] * s * (1.f - th * th);
+      dg[i] = acc[i] * to_f32(sg[row * C + n0 + i]);
+      df[i] = acc[i] * to_f32(tf[row * C + n0 + i]);
     }
-    st_vec<NV>(dy + row * ld + col0 + n0, dg);
-    st_vec<NV>(dy + row * ld + col0 + C + n0, df);
+    st_operand<NV>(dy + row * ld + col0 + n0, dg, rnd);
+    st_operand<NV>(dy + row * ld + col0 + C + n0, df, rnd);
   }
 };
 
@@ -147,6 +162,7 @@ struct EpiDh {
   float* dh;            // [B*T, C]
   TOp* dres_below;      // [B*T, C] or null (layer 0)
   int C, T;
+  bool rnd;
   template <int NV>
   __device__ __forceinline__ void load_aux(int b, int t, int n0, float* aux) const {
     const float4* p = reinterpret_cast<const float4*>(dh + (static_cast<size_t>(b) * T + t) * C + n0);
@@ -166,7 +182,7 @@ struct EpiDh {
     if (dres_below) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) v[i] *= 0.70710678118654752440f;
-      st_vec<NV>(dres_below + o, v);
+      st_operand<NV>(dres_below + o, v, rnd);
     }
   }
 };
@@ -174,7 +190,7 @@ struct EpiDh {
 // ------------------------------------------------------------------ elementwise kernels
 template <typename TOp>
 __global__ void __launch_bounds__(256) add_bcast_cast_kernel(const float* __restrict__ h, const float* __restrict__ d, TOp* __restrict__ out,
-                                                             int T, int C, size_t n4) {
+                                                             int T, int C, size_t n4, bool rnd) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const size_t e = i * 4, row = e / C;
@@ -182,12 +198,12 @@ __global__ void __launch_bounds__(256) add_bcast_cast_kernel(const float* __rest
   const float4 hv = reinterpret_cast<const float4*>(h)[i];
   const float4 dv = *reinterpret_cast<const float4*>(d + static_cast<size_t>(b) * C + c);
   const float v[4] = {hv.x + dv.x, hv.y + dv.y, hv.z + dv.z, hv.w + dv.w};
-  st_vec<4>(out + e, v);
+  st_operand<4>(out + e, v, rnd);
 }
 
 template <typename TOp, bool Fast>
 __global__ void __launch_bounds__(256) gate_fwd_kernel(const float* __restrict__ y, TOp* __restrict__ sg, TOp* __restrict__ tf, TOp* __restrict__ u,
-                                                       int C, size_t n4) {
+                                                       int C, size_t n4, bool rnd) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const size_t e = i * 4, row = e / C;
@@ -196,19 +212,27 @@ __global__ void __launch_bounds__(256) gate_fwd_kernel(const float* __restrict__
   const float4 f = *reinterpret_cast<const float4*>(y + row * 2 * C + C + c);
   const float gs[4] = {sigmoid_f<Fast>(g.x), sigmoid_f<Fast>(g.y), sigmoid_f<Fast>(g.z), sigmoid_f<Fast>(g.w)};
   const float ts[4] = {tanh_f<Fast>(f.x), tanh_f<Fast>(f.y), tanh_f<Fast>(f.z), tanh_f<Fast>(f.w)};
-  const float us[4] = {gs[0] * ts[0], gs[1] * ts[1], gs[2] * ts[2], gs[3] * ts[3]};
-  st_vec<4>(sg + e, gs);
-  st_vec<4>(tf + e, ts);
-  st_vec<4>(u + e, us);
+  float us[4], da[4], db[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    us[q] = gs[q] * ts[q];
+    // kept for the backward: the two derivative factors themselves, formed in fp32 BEFORE rounding to the operand type
+    // (1 - tanh^2 of a bf16-rounded tanh near +-1 would lose every significant bit)
+    da[q] = ts[q] * gs[q] * (1.f - gs[q]);              // du/dg
+    db[q] = gs[q] * (1.f - ts[q] * ts[q]);              // du/df
+  }
+  st_vec<4>(sg + e, da);
+  st_vec<4>(tf + e, db);
+  st_operand<4>(u + e, us, rnd);
 }
 
 template <typename TOp>
-__global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict__ src, TOp* __restrict__ dst, float scale, size_t n4) {
+__global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict__ src, TOp* __restrict__ dst, float scale, size_t n4, bool rnd) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const float4 s = reinterpret_cast<const float4*>(src)[i];
   const float v[4] = {s.x * scale, s.y * scale, s.z * scale, s.w * scale};
-  st_vec<4>(dst + 4 * i, v);
+  st_operand<4>(dst + 4 * i, v, rnd);
 }
 
 // dst[r * ldd + col0 + j * cblk + c] = op(src[r * sr + c * sc + j * sj])   (weight repacking on the device, once per optimizer step)
@@ -285,8 +309,8 @@ TrainWs tcarve(const fse_trainer* h, void* base, int B, int T) {
   w.S = reinterpret_cast<float*>(take(N * C * 4));               // 3  skip sum (fp32)
   w.y = reinterpret_cast<float*>(take(N * 2 * C * 4));           // 4  scratch: pre-activation of the current layer
   w.hin = take(N * C * es * L);                                  // 5  [L][B*T, C] h + d_l                   (operand type)
-  w.sg = take(N * C * es * L);                                   // 6  [L][B*T, C] sigmoid(gate)
-  w.tf = take(N * C * es * L);                                   // 7  [L][B*T, C] tanh(filter)
+  w.sg = take(N * C * es * L);                                   // 6  [L][B*T, C] du/dg = tanh(f) sg (1 - sg)
+  w.tf = take(N * C * es * L);                                   // 7  [L][B*T, C] du/df = sg (1 - tanh(f)^2)
   w.u = take(N * C * es * L);                                    // 8  [L][B*T, C] gate output
   w.s_op = take(N * C * es);                                     // 9  S / sqrt(L)
   w.r_op = take(N * C * es);                                     // 10 relu(skip_projection(.))
@@ -333,6 +357,7 @@ int train_forward_impl(fse_trainer* h, const float* x_t, const float* cond, cons
   const int C = h->cfg.channels, H = h->cfg.hidden, M = h->cfg.n_mels, L = h->cfg.layers, KB = h->KB, mode = h->cfg.mode;
   const size_t N = static_cast<size_t>(B) * T, es = sizeof(TOp);
   const bool fast = mode == FSE_MODE_TC_BF16;
+  const bool rnd = mode == FSE_MODE_TC_TF32;
   const int zero = 0;
   LaunchCtx ctx{&h->launches, nullptr, 0};
   const void* cond_op = cond;
@@ -358,7 +383,7 @@ int train_forward_impl(fse_trainer* h, const float* x_t, const float* cond, cons
     TOp* sg = reinterpret_cast<TOp*>(static_cast<uint8_t*>(w.sg) + lo);
     TOp* tf = reinterpret_cast<TOp*>(static_cast<uint8_t*>(w.tf) + lo);
     TOp* u = reinterpret_cast<TOp*>(static_cast<uint8_t*>(w.u) + lo);
-    add_bcast_cast_kernel<TOp><<<eb, 256, 0, st>>>(w.h, d + static_cast<size_t>(l) * B * C, hin, T, C, N * C / 4);
+    add_bcast_cast_kernel<TOp><<<eb, 256, 0, st>>>(w.h, d + static_cast<size_t>(l) * B * C, hin, T, C, N * C / 4, rnd);
     FSE_CUDA(cudaGetLastError());
     const int dil = 1 << (l % h->cfg.dilation_cycle_length);
     const int offs[3] = {-dil, 0, dil};
@@ -369,8 +394,8 @@ int train_forward_impl(fse_trainer* h, const float* x_t, const float* cond, cons
       EpiStoreF32<TOp> epi{h->b_y + static_cast<size_t>(l) * 2 * C, nullptr, w.y, 2 * C, T};
       FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, ctx)));
     }
-    if (fast) gate_fwd_kernel<TOp, true><<<eb, 256, 0, st>>>(w.y, sg, tf, u, C, N * C / 4);
-    else gate_fwd_kernel<TOp, false><<<eb, 256, 0, st>>>(w.y, sg, tf, u, C, N * C / 4);
+    if (fast) gate_fwd_kernel<TOp, true><<<eb, 256, 0, st>>>(w.y, sg, tf, u, C, N * C / 4, rnd);
+    else gate_fwd_kernel<TOp, false><<<eb, 256, 0, st>>>(w.y, sg, tf, u, C, N * C / 4, rnd);
     FSE_CUDA(cudaGetLastError());
     {
       ConvGemmParams p = make_params(B, T, T, C, 1, &zero, 0, 2 * C, KB);
@@ -386,7 +411,7 @@ int train_forward_impl(fse_trainer* h, const float* x_t, const float* cond, cons
     }
     h->launches += 2;
   }
-  scale_cast_kernel<TOp><<<eb, 256, 0, st>>>(w.S, static_cast<TOp*>(w.s_op), static_cast<float>(1.0 / std::sqrt(static_cast<double>(L))), N * C / 4);
+  scale_cast_kernel<TOp><<<eb, 256, 0, st>>>(w.S, static_cast<TOp*>(w.s_op), static_cast<float>(1.0 / std::sqrt(static_cast<double>(L))), N * C / 4, rnd);
   FSE_CUDA(cudaGetLastError());
   {  // r = relu(skip_projection(S / sqrt(L)))   (diffnet.py:128-130)
     ConvGemmParams p = make_params(B, T, T, C, 1, &zero, 0, C, KB);
@@ -410,19 +435,20 @@ int train_backward_impl(fse_trainer* h, const float* dx0, float* dcond, int B, i
   const int C = h->cfg.channels, H = h->cfg.hidden, M = h->cfg.n_mels, L = h->cfg.layers, KB = h->KB, mode = h->cfg.mode;
   const size_t N = static_cast<size_t>(B) * T, es = sizeof(TOp);
   const int zero = 0;
+  const bool rnd = mode == FSE_MODE_TC_TF32;
   LaunchCtx ctx{&h->launches, nullptr, 0};
   x_to_rows_kernel<TOp><<<dim3((T + 255) / 256, B), 256, 0, st>>>(dx0, static_cast<TOp*>(w.dx_rows), M, T);
   FSE_CUDA(cudaGetLastError());
   {  // dz = (W_out^T dx0) * [r > 0]
     ConvGemmParams p = make_params(B, T, T, M, 1, &zero, 0, C, KB);
     GemmOperands op; op.A0 = w.dx_rows; op.W = h->WoutT; op.mA0 = &h->plan.m_dx; op.mW = &h->mWoutT; op.BN = 256;
-    EpiReluBwd<TOp> epi{static_cast<const TOp*>(w.r_op), static_cast<TOp*>(w.dz), C, T};
+    EpiReluBwd<TOp> epi{static_cast<const TOp*>(w.r_op), static_cast<TOp*>(w.dz), C, T, rnd};
     FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, ctx)));
   }
   {  // dS = W_skip^T dz / sqrt(L): the gradient of EVERY layer's skip output
     ConvGemmParams p = make_params(B, T, T, C, 1, &zero, 0, C, KB);
     GemmOperands op; op.A0 = w.dz; op.W = h->WskipT; op.mA0 = &h->plan.m_dz; op.mW = &h->mWskipT; op.BN = 256;
-    EpiScaleCast<TOp> epi{static_cast<TOp*>(w.dS), C, T, static_cast<float>(1.0 / std::sqrt(static_cast<double>(L)))};
+    EpiScaleCast<TOp> epi{static_cast<TOp*>(w.dS), C, T, static_cast<float>(1.0 / std::sqrt(static_cast<double>(L))), rnd};
     FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, ctx)));
   }
   FSE_CUDA(cudaMemsetAsync(w.dh, 0, N * C * 4, st));                                          // nothing reads h_L
@@ -436,7 +462,7 @@ int train_backward_impl(fse_trainer* h, const float* dx0, float* dcond, int B, i
       GemmOperands op; op.A0 = static_cast<uint8_t*>(w.dres) + lo; op.A1 = w.dS;
       op.W = static_cast<uint8_t*>(h->WoT) + static_cast<size_t>(l) * C * 2 * C * es;
       op.mA0 = &h->plan.m_dres[l]; op.mA1 = &h->plan.m_dS; op.mW = h->tc ? &h->mWoT[l] : nullptr; op.BN = 256;
-      EpiGateBwd<TOp> epi{sg, tf, static_cast<TOp*>(w.dy), C, T, L * 2 * C, l * 2 * C};
+      EpiGateBwd<TOp> epi{sg, tf, static_cast<TOp*>(w.dy), C, T, L * 2 * C, l * 2 * C, rnd};
       FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, ctx)));
     }
     {  // dh <- dh / sqrt(2) + conv_k3^T(dy_l); the layer below gets dres = dh / sqrt(2)
@@ -446,7 +472,7 @@ int train_backward_impl(fse_trainer* h, const float* dx0, float* dcond, int B, i
       p.c_off0 = l * 2 * C; p.ld0 = L * 2 * C;
       GemmOperands op; op.A0 = w.dy; op.W = static_cast<uint8_t*>(h->WyT) + static_cast<size_t>(l) * C * 6 * C * es;
       op.mA0 = &h->plan.m_dy; op.mW = h->tc ? &h->mWyT[l] : nullptr; op.BN = 256;
-      EpiDh<TOp> epi{w.dh, l > 0 ? reinterpret_cast<TOp*>(static_cast<uint8_t*>(w.dres) + lo - N * C * es) : nullptr, C, T};
+      EpiDh<TOp> epi{w.dh, l > 0 ? reinterpret_cast<TOp*>(static_cast<uint8_t*>(w.dres) + lo - N * C * es) : nullptr, C, T, rnd};
       FSE_TRY((run_conv_gemm<TOp>(mode, p, op, epi, st, ctx)));
     }
   }
