@@ -360,6 +360,19 @@ int fse_train_backward(fse_trainer* h, const float* dx0, float* dcond, int32_t B
                        void* stream);
 int64_t fse_train_last_launches(const fse_trainer* h);
 
+/* --- mel losses of the training step ------------------------------------------------------
+ * SpeechBaseTask.add_mel_loss with `mel_losses: l1:0.5|ssim:0.5` (tasks/tts/speech_base.py:219-257; utils/metrics/ssim.py:24-44):
+ * the weights_nonzero_speech-weighted L1 and 1 - SSIM (11 x 11 Gaussian window, bias 6) means over mel_out / target [B,T,n_mels] fp32,
+ * and their gradient with respect to mel_out.  forward writes losses[0] = lambda_l1 * l1, losses[1] = lambda_ssim * ssim (device
+ * floats) and, with want_grad, keeps three derivative fields in the workspace; backward (same workspace, same mel_out / target)
+ * writes grad = dlosses[0] * d losses[0] / d mel_out + dlosses[1] * d losses[1] / d mel_out (dlosses: 2 device floats).
+ * Deterministic (no floating-point atomics).  csrc/mel_loss.cu */
+int64_t fse_mel_loss_workspace_bytes(int32_t B, int32_t T, int32_t n_mels);
+int fse_mel_loss_forward(const float* mel_out, const float* target, float lambda_l1, float lambda_ssim, float* losses, int32_t want_grad,
+                         int32_t B, int32_t T, int32_t n_mels, void* workspace, int64_t workspace_bytes, void* stream);
+int fse_mel_loss_backward(const float* mel_out, const float* target, const float* dlosses, float lambda_l1, float lambda_ssim, float* grad,
+                          int32_t B, int32_t T, int32_t n_mels, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* --- kernel timing (opt-in) -------------------------------------------------------------------
  * When enabled, every kernel the handle launches is bracketed by CUDA events on the launch stream;
  * *_profile_read waits for them and returns the summed device time (ms) and launch count per kind

@@ -449,6 +449,48 @@ def train_fixture():
     print("diffnet_train", x0.shape, float(np.abs(out["dcond"]).mean()), len([k for k in out if k.startswith("g__")]), "parameter gradients")
 
 
+def mel_loss_fixture():
+    """Mel losses of the training step and their gradient from the reference's OWN methods: SpeechBaseTask.l1_loss / ssim_loss are cut
+    out of tasks/tts/speech_base.py with ast (the task module cannot be imported: matplotlib, librosa, ...) and run over the
+    reference's ssim() and weights_nonzero_speech under torch.autograd.  `python oracle/make_golden.py mel_loss` writes
+    tests/golden/mel_loss.npz: a ragged, partly masked batch (padding frames and unmasked frames are zero rows of the target, weight 0),
+    losses (fp32 as the reference computes them, and an fp64 run of the same code as the arbiter of rounding) and d(0.5 l1 + 0.5 ssim)/d mel_out."""
+    import ast
+    os.makedirs(OUT, exist_ok=True)
+    refshim.install("egs/spec_denoiser.yaml")
+    import utils.metrics.ssim as ref_ssim
+    from utils.nn.seq_utils import weights_nonzero_speech
+    import torch.nn.functional as F
+    src = open(os.path.join(refshim.REF_ROOT, "tasks", "tts", "speech_base.py")).read()
+    cls = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "SpeechBaseTask")
+    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in ("l1_loss", "ssim_loss")]
+    ns = {"F": F, "ssim": ref_ssim.ssim, "weights_nonzero_speech": weights_nonzero_speech, "torch": torch}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "speech_base.py", "exec"), ns)
+    rs = np.random.RandomState(SEED + 41)
+    B, T, M = 3, 70, 80
+    target = np.clip(rs.standard_normal((B, T, M)) * 1.5 - 3.0, -6.0, 1.5).astype(np.float32)
+    out = (target + rs.standard_normal((B, T, M)) * 0.4).astype(np.float32)
+    mask = np.zeros((B, T, 1), np.float32)
+    mask[0, 10:45] = 1
+    mask[1, 0:20] = 1                    # region touching the first frame (zero padding of the window)
+    mask[2, 50:70] = 1                   # ... and the last
+    mask[2, 58:60] = 0                   # a hole inside a region
+    out[0, 20, 7] = target[0, 20, 7]     # an exact tie: sign(0) = 0 in the l1 gradient
+    res = {}
+    for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        ref_ssim.window = None           # the module caches its window (and its dtype) in a global
+        a = torch.from_numpy(out * mask).to(dt).requires_grad_(True)
+        b = torch.from_numpy(target * mask).to(dt)
+        l1 = ns["l1_loss"](None, a, b) * 0.5
+        ss = ns["ssim_loss"](None, a, b) * 0.5
+        (l1 + ss).backward()
+        res["l1_" + tag], res["ssim_" + tag], res["grad_" + tag] = l1.detach().numpy(), ss.detach().numpy(), a.grad.numpy()
+    ref_ssim.window = None
+    np.savez_compressed(os.path.join(OUT, "mel_loss.npz"), mel_out=out * mask, target=target * mask, lambda_l1=0.5, lambda_ssim=0.5, **res)
+    print("mel_loss", float(res["l1_f32"]), float(res["ssim_f32"]), float(res["l1_f64"]), float(res["ssim_f64"]),
+          float(np.abs(res["grad_f32"] - res["grad_f64"]).max()), float(np.abs(res["grad_f64"]).max()))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "mel_encoder":
         mel_encoder_fixture()
@@ -464,6 +506,8 @@ if __name__ == "__main__":
         mel_frontend_fixture()
     elif len(sys.argv) > 1 and sys.argv[1] == "train":
         train_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mel_loss":
+        mel_loss_fixture()
     else:
         main()
         mel_encoder_fixture()

@@ -91,3 +91,58 @@ class TorchTrainer:
     def views(self):
         b = self.buf
         return {k: b[k] for k in ("x_rows", "h0", "hin", "u", "s", "r", "cond", "dx_rows", "dz", "dS", "dh0", "dres", "dy")}
+
+
+def mel_losses_torch(mel_out: torch.Tensor, target: torch.Tensor, lambdas=(("l1", 0.5), ("ssim", 0.5))):
+    """Torch restatement of SpeechBaseTask.add_mel_loss with `mel_losses: l1:0.5|ssim:0.5` (tasks/tts/speech_base.py:219-257: l1_loss,
+    ssim_loss, weights_nonzero_speech) over utils/metrics/ssim.py:12-44 (window, _ssim); its autograd gradient is the expected value
+    of fse_mel_loss_backward.  Pinned to the reference's own methods by tests/test_train_oracle.py."""
+    weights = (target.abs().sum(-1, keepdim=True) > 0).to(mel_out.dtype).repeat(1, 1, target.shape[-1])
+    out = {}
+    for name, lam in lambdas:
+        if name == "l1":
+            out["l1"] = (F.l1_loss(mel_out, target, reduction="none") * weights).sum() / weights.sum() * lam
+        elif name == "ssim":
+            a, b = mel_out[:, None] + 6.0, target[:, None] + 6.0
+            k = torch.tensor([math.exp(-(x - 5) ** 2 / (2 * 1.5 ** 2)) for x in range(11)], device=a.device)
+            k = (k / k.sum())[:, None]
+            win = (k @ k.t())[None, None].to(a.dtype)
+            mu1, mu2 = F.conv2d(a, win, padding=5), F.conv2d(b, win, padding=5)
+            s1 = F.conv2d(a * a, win, padding=5) - mu1 * mu1
+            s2 = F.conv2d(b * b, win, padding=5) - mu2 * mu2
+            s12 = F.conv2d(a * b, win, padding=5) - mu1 * mu2
+            ssim_map = ((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1 * mu1 + mu2 * mu2 + 1e-4) * (s1 + s2 + 9e-4))
+            out["ssim"] = ((1 - ssim_map.mean(1)) * weights).sum() / weights.sum() * lam
+    return out
+
+
+def mel_loss_native_algebra(mel_out, target, lam_l1=0.5, lam_ssim=0.5):
+    """numpy (float64) restatement of csrc/mel_loss.cu, field for field: the forward's three derivative fields and the backward's
+    window pass — pins the kernel's closed-form gradient to the reference's autograd gradient on the CPU (tests/test_train_oracle.py).
+    Returns (lam_l1 * l1, lam_ssim * ssim, d(sum of both) / d mel_out)."""
+    import numpy as np
+    from scipy.signal import correlate2d
+    x, y = np.asarray(mel_out, np.float64), np.asarray(target, np.float64)
+    B, T, M = x.shape
+    g = np.array([math.exp(-(i - 5) ** 2 / (2 * 1.5 ** 2)) for i in range(11)])
+    g = g / g.sum()
+    W = np.outer(g, g)
+    w = (np.abs(y).sum(-1) != 0).astype(np.float64)                       # [B, T]
+    wsum = w.sum() * M
+    C1, C2 = 1e-4, 9e-4
+    conv = lambda img: correlate2d(img, W, mode="same", boundary="fill", fillvalue=0.0)
+    l1 = (np.abs(x - y) * w[:, :, None]).sum() / wsum
+    ssim_sum, grad = 0.0, np.zeros_like(x)
+    for i in range(B):
+        a, b = x[i] + 6.0, y[i] + 6.0
+        mu1, mu2, eaa, ebb, eab = conv(a), conv(b), conv(a * a), conv(b * b), conv(a * b)
+        A1, A2 = 2 * mu1 * mu2 + C1, 2 * (eab - mu1 * mu2) + C2
+        B1, B2 = mu1 ** 2 + mu2 ** 2 + C1, (eaa - mu1 ** 2) + (ebb - mu2 ** 2) + C2
+        S = A1 * A2 / (B1 * B2)
+        ssim_sum += ((1 - S) * w[i][:, None]).sum()
+        up = -w[i][:, None] / wsum
+        Gmu = up * (2 * mu2 * (A2 - A1) / (B1 * B2) - 2 * mu1 * S * (1 / B1 - 1 / B2))
+        Gaa = up * (-S / B2)
+        Gab = up * (2 * A1 / (B1 * B2))
+        grad[i] = lam_ssim * (conv(Gmu) + 2 * a * conv(Gaa) + b * conv(Gab)) + lam_l1 * np.sign(x[i] - y[i]) * w[i][:, None] / wsum
+    return lam_l1 * l1, lam_ssim * ssim_sum / wsum, grad

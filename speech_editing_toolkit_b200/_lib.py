@@ -124,6 +124,9 @@ SIGNATURES = {
     "fse_train_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "fse_train_backward": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "fse_train_last_launches": (C.c_int64, [_P]),
+    "fse_mel_loss_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "fse_mel_loss_forward": (C.c_int, [_P, _P, C.c_float, C.c_float, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
+    "fse_mel_loss_backward": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "fse_denoiser_profile": (C.c_int, [_P, C.c_int32]),
     "fse_denoiser_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "fse_vocoder_profile": (C.c_int, [_P, C.c_int32]),

@@ -255,26 +255,44 @@ class BucketedAllReduce:
         self.pending, self.seen = [], set()
 
 
+class MelLossFunction(torch.autograd.Function):
+    """[lambda_l1 * l1, lambda_ssim * ssim] of add_mel_loss (tasks/tts/speech_base.py:219-257) and their gradient with respect to
+    `mel_out`, both native (fse_mel_loss_forward / fse_mel_loss_backward, csrc/mel_loss.cu)."""
+
+    @staticmethod
+    def forward(ctx, mel_out, target, lam_l1: float, lam_ssim: float):
+        _need_cuda(mel_out, target)
+        mel_out, target = mel_out.contiguous().float(), target.contiguous().float()
+        B, T, M = mel_out.shape
+        nbytes = _lib.lib().fse_mel_loss_workspace_bytes(B, T, M)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=mel_out.device)
+        losses = torch.empty(2, dtype=torch.float32, device=mel_out.device)
+        want_grad = int(ctx.needs_input_grad[0])
+        check(_lib.lib().fse_mel_loss_forward(_ptr(mel_out), _ptr(target), lam_l1, lam_ssim, _ptr(losses), want_grad, B, T, M, _ptr(ws), nbytes, _stream()))
+        ctx.save_for_backward(mel_out, target, ws)
+        ctx.lams = (lam_l1, lam_ssim)
+        return losses
+
+    @staticmethod
+    def backward(ctx, dlosses):
+        mel_out, target, ws = ctx.saved_tensors
+        B, T, M = mel_out.shape
+        grad = torch.empty_like(mel_out)
+        dlosses = dlosses.contiguous().float()
+        check(_lib.lib().fse_mel_loss_backward(_ptr(mel_out), _ptr(target), _ptr(dlosses), ctx.lams[0], ctx.lams[1], _ptr(grad), B, T, M, _ptr(ws),
+                                                ws.numel(), _stream()))
+        return grad, None, None, None
+
+
 def mel_losses(mel_out: torch.Tensor, target: torch.Tensor, lambdas=(("l1", 0.5), ("ssim", 0.5))) -> Dict[str, torch.Tensor]:
-    """add_mel_loss with the shipped `mel_losses: l1:0.5|ssim:0.5` (tasks/tts/speech_base.py:219-257, utils/metrics/ssim.py:24-44)."""
-    F = torch.nn.functional
-    weights = (target.abs().sum(-1, keepdim=True) > 0).float().repeat(1, 1, target.shape[-1])       # weights_nonzero_speech
-    out = {}
-    for name, lam in lambdas:
-        if name == "l1":
-            out["l1"] = (F.l1_loss(mel_out, target, reduction="none") * weights).sum() / weights.sum() * lam
-        elif name == "ssim":
-            a, b = mel_out[:, None] + 6.0, target[:, None] + 6.0
-            k = torch.tensor([math.exp(-(x - 5) ** 2 / (2 * 1.5 ** 2)) for x in range(11)], device=a.device)
-            k = (k / k.sum())[:, None]
-            win = (k @ k.t())[None, None]
-            mu1, mu2 = F.conv2d(a, win, padding=5), F.conv2d(b, win, padding=5)
-            s1 = F.conv2d(a * a, win, padding=5) - mu1 * mu1
-            s2 = F.conv2d(b * b, win, padding=5) - mu2 * mu2
-            s12 = F.conv2d(a * b, win, padding=5) - mu1 * mu2
-            ssim_map = ((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1 * mu1 + mu2 * mu2 + 1e-4) * (s1 + s2 + 9e-4))
-            out["ssim"] = ((1 - ssim_map.mean(1)) * weights).sum() / weights.sum() * lam
-    return out
+    """add_mel_loss with the shipped `mel_losses: l1:0.5|ssim:0.5` (tasks/tts/speech_base.py:219-257, utils/metrics/ssim.py:24-44):
+    one native forward for both terms (a term with weight 0 / not listed is dropped from the dict, as in the reference's loop)."""
+    lam = dict(lambdas)
+    unknown = set(lam) - {"l1", "ssim"}
+    if unknown:
+        raise NotImplementedError(f"mel loss terms {sorted(unknown)}: only l1 and ssim are on the B200 path")
+    both = MelLossFunction.apply(mel_out, target, float(lam.get("l1", 0.0)), float(lam.get("ssim", 0.0)))
+    return {name: both[i] for i, name in enumerate(("l1", "ssim")) if name in lam}
 
 
 def train_step(denoise_fn, schedule: Dict[str, torch.Tensor], batch: Dict[str, torch.Tensor], optimizer, t: Optional[torch.Tensor] = None,

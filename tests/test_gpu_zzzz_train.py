@@ -1,4 +1,4 @@
-"""Training-mode DiffNet: forward and gradients of `DiffNetB200` under autograd — native forward and
+"""Training step: the native mel losses, and forward and gradients of `DiffNetB200` under autograd — native forward and
 activation-gradient chain (fse_train_*), weight gradients by library GEMMs — against tests/golden/diffnet_train.npz, the gradients
 torch.autograd computes through the UNMODIFIED reference DiffNet (oracle/make_golden.py train).
 
@@ -120,3 +120,52 @@ def test_train_step_decreases_the_loss_and_is_deterministic(lib_built):
     assert runs[0][-1] < 0.9 * runs[0][0], runs[0]
     assert np.allclose(runs[0], runs[1], rtol=1e-4), (runs[0], runs[1])
     print(f"[margin] train_step: loss {runs[0][0]:.4f} -> {runs[0][-1]:.4f} in 8 steps")
+
+
+def test_mel_loss_kernels_vs_reference_fixture(lib_built):
+    """fse_mel_loss_forward / fse_mel_loss_backward against the reference's own l1_loss / ssim_loss and their autograd gradient
+    (tests/golden/mel_loss.npz).  Stated tolerance: losses 2e-6 absolute, gradient rel-L2 1e-4 against the fp64 run of the reference code
+    (the reference's own fp32 run is printed beside it: sigma = E[a^2] - mu^2 on values near 6 cancels ~5 digits in either)."""
+    _need_gpu()
+    from speech_editing_toolkit_b200 import train
+    g = golden("mel_loss.npz")
+    a = torch.from_numpy(g["mel_out"]).cuda().requires_grad_(True)
+    out = train.mel_losses(a, torch.from_numpy(g["target"]).cuda())
+    (out["l1"] + out["ssim"]).backward()
+    e_l1, e_ss = abs(float(out["l1"]) - float(g["l1_f64"])), abs(float(out["ssim"]) - float(g["ssim_f64"]))
+    e_g = rel_l2(a.grad.cpu().numpy(), g["grad_f64"])
+    print(f"[margin] mel losses: l1 abs err {e_l1:.2e}, ssim abs err {e_ss:.2e}, gradient rel-L2 {e_g:.2e} vs the reference in fp64 "
+          f"(the reference's fp32 run: {abs(float(g['l1_f32']) - float(g['l1_f64'])):.2e}, {abs(float(g['ssim_f32']) - float(g['ssim_f64'])):.2e}, "
+          f"{rel_l2(g['grad_f32'], g['grad_f64']):.2e})")
+    assert e_l1 < 2e-6 and e_ss < 2e-6 and e_g < 1e-4
+
+
+def test_mel_loss_kernels_at_training_shape_are_deterministic_and_match_the_torch_restatement(lib_built):
+    """32 x 1024 x 80 (ragged: padded tails, masked spans) against oracle.train_oracle.mel_losses_torch in fp64 on the same device;
+    separate upstream weights for the two terms; two runs must agree bit for bit (no floating-point atomics)."""
+    _need_gpu()
+    from oracle.train_oracle import mel_losses_torch
+    from speech_editing_toolkit_b200 import train
+    B, T, M = 32, 1024, 80
+    gen = torch.Generator().manual_seed(11)
+    target = (torch.randn(B, T, M, generator=gen) * 1.5 - 3.0).clamp(-6.0, 1.5)
+    out = target + 0.3 * torch.randn(B, T, M, generator=gen)
+    mask = torch.zeros(B, T, 1)
+    for b in range(B):
+        lo = (37 * b) % 500
+        mask[b, lo:lo + 200 + 11 * b] = 1
+    mask[3] = 0                                                      # an utterance without any speech frame in the mask
+    out, target = (out * mask).cuda(), (target * mask).cuda()
+    runs = []
+    for _ in range(2):
+        a = out.clone().requires_grad_(True)
+        o = train.mel_losses(a, target)
+        (0.7 * o["l1"] + 1.3 * o["ssim"]).backward()
+        runs.append((o["l1"].item(), o["ssim"].item(), a.grad.clone()))
+    assert runs[0][0] == runs[1][0] and runs[0][1] == runs[1][1] and torch.equal(runs[0][2], runs[1][2])
+    a64 = out.double().requires_grad_(True)
+    o64 = mel_losses_torch(a64, target.double())
+    (0.7 * o64["l1"] + 1.3 * o64["ssim"]).backward()
+    e_g = rel_l2(runs[0][2].cpu().numpy(), a64.grad.cpu().numpy())
+    print(f"[margin] mel losses 32 x 1024: l1 {runs[0][0]:.6f} vs {o64['l1'].item():.6f}, ssim {runs[0][1]:.6f} vs {o64['ssim'].item():.6f}, gradient rel-L2 {e_g:.2e}")
+    assert abs(runs[0][0] - o64["l1"].item()) < 2e-6 and abs(runs[0][1] - o64["ssim"].item()) < 2e-6 and e_g < 1e-4

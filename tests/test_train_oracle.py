@@ -8,7 +8,7 @@ import torch
 
 from conftest import golden
 from oracle import refshim
-from oracle.train_oracle import TorchTrainer
+from oracle.train_oracle import TorchTrainer, mel_losses_torch
 from speech_editing_toolkit_b200 import synth, train
 from speech_editing_toolkit_b200.modules import DiffNetB200
 
@@ -42,7 +42,7 @@ def test_native_training_algebra_and_weight_gradient_code_vs_reference_autograd_
 
 @pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
 def test_mel_losses_equal_the_reference_losses():
-    """train.mel_losses against SpeechBaseTask.l1_loss / ssim_loss (tasks/tts/speech_base.py:219-257) — the task module cannot be
+    """oracle.train_oracle.mel_losses_torch (the expected value of the native loss kernels) against SpeechBaseTask.l1_loss / ssim_loss (tasks/tts/speech_base.py:219-257) — the task module cannot be
     imported (matplotlib, librosa...), so the two methods are cut out of the source and run on the reference's own ssim()."""
     import ast
     import os
@@ -62,6 +62,22 @@ def test_mel_losses_equal_the_reference_losses():
     a = torch.from_numpy(rs.standard_normal((2, 50, 80)).astype(np.float32))
     b = torch.from_numpy(rs.standard_normal((2, 50, 80)).astype(np.float32))
     m = torch.zeros(2, 50, 1); m[:, 10:30] = 1
-    ours = train.mel_losses(a * m, b * m)
+    ours = mel_losses_torch(a * m, b * m)
     assert abs(float(ours["l1"]) - 0.5 * float(ns["l1_loss"](None, a * m, b * m))) < 1e-6
     assert abs(float(ours["ssim"]) - 0.5 * float(ns["ssim_loss"](None, a * m, b * m))) < 1e-5
+
+
+def test_mel_loss_oracles_vs_reference_fixture():
+    """tests/golden/mel_loss.npz holds the reference's own l1_loss / ssim_loss and their autograd gradient (oracle/make_golden.py mel_loss).
+    Both restatements must reproduce it: the torch one (expected value of the GPU test) and the closed-form algebra of csrc/mel_loss.cu."""
+    from oracle.train_oracle import mel_loss_native_algebra
+    g = golden("mel_loss.npz")
+    a = torch.from_numpy(g["mel_out"]).requires_grad_(True)
+    out = mel_losses_torch(a, torch.from_numpy(g["target"]))
+    (out["l1"] + out["ssim"]).backward()
+    assert abs(float(out["l1"]) - float(g["l1_f32"])) < 1e-6 and abs(float(out["ssim"]) - float(g["ssim_f32"])) < 1e-6
+    assert rel_l2(a.grad.numpy(), g["grad_f32"]) < 1e-5
+    l1, ss, grad = mel_loss_native_algebra(g["mel_out"], g["target"])
+    # the reference's fp64 run still uses the fp32-rounded window (create_window builds a float tensor): 1e-7 is that rounding
+    assert abs(l1 - float(g["l1_f64"])) < 1e-9 and abs(ss - float(g["ssim_f64"])) < 1e-7
+    assert rel_l2(grad, g["grad_f64"]) < 1e-6
