@@ -135,42 +135,61 @@ class DiffNetFunction(torch.autograd.Function):
         dcond = tr.backward(dx0)
         v = tr.views()
         B, T = v["cond"].shape[:2]
+        N = B * T
         f32 = torch.float32
         grads: Dict[str, torch.Tensor] = {}
         hook = ctx.hook                                        # called with (name -> grad) groups as they become ready (all-reduce overlap)
 
-        def mm(a, b):                                          # a^T b over all rows, fp32 result
-            return torch.matmul(a.transpose(0, 1), b).to(f32)
+        def mm(a, b):                                          # a^T b over all rows: operand-dtype GEMM, fp32 accumulator written out as fp32
+            return torch.mm(a.t(), b) if a.dtype == f32 else torch.mm(a.t(), b, out_dtype=f32)
         dx_rows, r, dz, s, dS = v["dx_rows"], v["r"], v["dz"], v["s"], v["dS"]
         g = {"output_projection.weight": mm(dx_rows, r)[:, :, None], "output_projection.bias": dx0.sum((0, 2)),
-             "skip_projection.weight": mm(dz, s)[:, :, None], "skip_projection.bias": dz.to(f32).sum(0)}
+             "skip_projection.weight": mm(dz, s)[:, :, None], "skip_projection.bias": dz.sum(0, dtype=f32)}
         grads.update(g)
         if hook:
             hook(g)
-        dd = torch.empty(L, B, Cc, dtype=f32, device=dx0.device)
-        cond_op = v["cond"]
-        wdcs = ctx.saved_tensors
+        # every column sum of the backward in a handful of reductions over the whole [.., L * 2C] buffers (fp32 accumulation of the
+        # operand-dtype values, no per-layer cast copies): per-item sums of dy, its first / last `dil` frames, and the sums of dres / dS
+        dy_all = v["dy"]                                                                 # [B, T, L * 2C]
+        dysum_all = dy_all.sum(1, dtype=f32).view(B, L, 2 * Cc)                          # [B, L, 2C]
+        edge = {}
+        for dil in sorted(set(ctx.dil)):
+            edge[dil] = (dy_all[:, :dil].sum(1, dtype=f32).view(B, L, 2 * Cc), dy_all[:, T - dil:].sum(1, dtype=f32).view(B, L, 2 * Cc))
+        dres_sum = v["dres"].sum(1, dtype=f32)                                           # [L, C]
+        dS_sum = dS.sum(0, dtype=f32)
+        dy2d = dy_all.view(N, L * 2 * Cc)
+        cond2d = v["cond"].reshape(N, -1)
+        gcond_all = mm(dy2d, cond2d)                                                     # conditioner_projection of every layer: ONE GEMM [L * 2C, H]
+        # d_l enters as hin = h + d_l inside the zero padding: sum_t of the conv's input gradient, tap by tap (three batched matmuls)
+        w_all = torch.stack([w.to(f32) for w in ctx.saved_tensors])                      # [L, 2C, C, 3]
+        head_all = torch.stack([edge[ctx.dil[l]][0][:, l] for l in range(L)])            # [L, B, 2C]: frames the tap with offset -dil never reads
+        tail_all = torch.stack([edge[ctx.dil[l]][1][:, l] for l in range(L)])
+        dys = dysum_all.transpose(0, 1)                                                  # [L, B, 2C]
+        dd = torch.bmm(dys - head_all, w_all[..., 0]) + torch.bmm(dys, w_all[..., 1]) + torch.bmm(dys - tail_all, w_all[..., 2])
         for l in range(L - 1, -1, -1):
             p = f"residual_layers.{l}."
-            dy = v["dy"][:, :, l * 2 * Cc:(l + 1) * 2 * Cc]                              # [B, T, 2C] (strided view)
-            do = torch.cat([v["dres"][l], dS], dim=1)                                    # [N, 2C] gradient of o = [res | skip]
             dil = ctx.dil[l]
-            hin = v["hin"][l]
+            dy = dy2d[:, l * 2 * Cc:(l + 1) * 2 * Cc]                                    # [N, 2C], row stride L * 2C: a GEMM operand as it lies
+            dy3 = dy_all[:, :, l * 2 * Cc:(l + 1) * 2 * Cc]
+            hin = v["hin"][l]                                                            # [B, T, C]
+            hin2d = hin.reshape(N, Cc)
             gw = torch.empty(2 * Cc, Cc, 3, dtype=f32, device=dx0.device)
-            for j, off in enumerate((-dil, 0, dil)):                                     # y[t] += W_j hin[t + off]
-                lo, hi = max(0, -off), min(T, T - off)
-                gw[:, :, j] = torch.einsum("btn,btc->nc", dy[:, lo:hi], hin[:, lo + off:hi + off]).to(f32)
-            dysum = dy.to(f32).sum(1)                                                    # [B, 2C]
-            gb = dysum.sum(0)
-            # d_l enters as hin = h + d_l inside the zero padding: sum_t of the conv's input gradient, tap by tap
-            w = wdcs[l].to(f32)                                                          # [2C, C, 3]
-            head = dy[:, :dil].to(f32).sum(1)                                            # frames the tap with offset -dil never reads
-            tail = dy[:, T - dil:].to(f32).sum(1)
-            dd[l] = (dysum - head) @ w[:, :, 0] + dysum @ w[:, :, 1] + (dysum - tail) @ w[:, :, 2]
+            # y[t] += W_j hin[t + off], off = (j - 1) dil.  The shifted taps are GEMMs over the flat row sequence shifted by `dil` rows
+            # (no copies), minus the (B - 1) dil row pairs that straddle two utterances.
+            gw[:, :, 1] = mm(dy, hin2d)
+            gw[:, :, 0] = mm(dy[dil:], hin2d[:N - dil])
+            gw[:, :, 2] = mm(dy[:N - dil], hin2d[dil:])
+            if B > 1:
+                gw[:, :, 0] -= mm(dy3[1:, :dil].reshape(-1, 2 * Cc), hin[:-1, T - dil:].reshape(-1, Cc))
+                gw[:, :, 2] -= mm(dy3[:-1, T - dil:].reshape(-1, 2 * Cc), hin[1:, :dil].reshape(-1, Cc))
+            gb = dysum_all[:, l].sum(0)
+            gop = torch.empty(2 * Cc, Cc, dtype=f32, device=dx0.device)                  # gradient of o = [res | skip] against u_l
+            gop[:Cc] = mm(v["dres"][l], v["u"][l])
+            gop[Cc:] = mm(dS, v["u"][l])
             g = {p + "dilated_conv.weight": gw, p + "dilated_conv.bias": gb,
-                 p + "conditioner_projection.weight": torch.einsum("btn,bth->nh", dy, cond_op).to(f32)[:, :, None],
+                 p + "conditioner_projection.weight": gcond_all[l * 2 * Cc:(l + 1) * 2 * Cc, :, None],
                  p + "conditioner_projection.bias": gb,
-                 p + "output_projection.weight": mm(do, v["u"][l])[:, :, None], p + "output_projection.bias": do.to(f32).sum(0)}
+                 p + "output_projection.weight": gop[:, :, None], p + "output_projection.bias": torch.cat([dres_sum[l], dS_sum])}
             grads.update(g)
             if hook:
                 hook(g)
