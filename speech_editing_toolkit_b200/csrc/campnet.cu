@@ -424,10 +424,14 @@ int attention(fse_campnet* h, const void* Q, int ldq, int qoff, const void* K, c
   if constexpr (std::is_same<TOp, __nv_bfloat16>::value) {
     if (h->attn_tc && vt != nullptr && probs == nullptr) {
       // tensor cores: S = Q K^T and O = P V as tcgen05.mma, V^T from the projection's epilogue (attention_tc.cuh)
-      static bool tc_attr = false;
-      if (!tc_attr) {
+      // function attributes are per context: flags keyed by device ordinal, not process-global
+      int dev = 0;
+      FSE_CUDA(cudaGetDevice(&dev));
+      if (dev < 0 || dev >= kMaxDevices) return fail(FSE_ECUDA, "device ordinal %d out of range", dev);
+      static bool tc_attr[kMaxDevices] = {};
+      if (!tc_attr[dev]) {
         FSE_CUDA(cudaFuncSetAttribute(camp_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtcSmemBytes));
-        tc_attr = true;
+        tc_attr[dev] = true;
       }
       const CUtensorMap *mq = nullptr, *mk = nullptr;
       FSE_TRY(get_act_map(&h->ctx, Q, ldq, Tq, B, 64, &mq));
@@ -439,10 +443,10 @@ int attention(fse_campnet* h, const void* Q, int ldq, int qoff, const void* K, c
       }
       AttnTcParams ap{Tq, Tk, h->cfg.heads, qoff, koff, h->cfg.hidden, key_keep, static_cast<__nv_bfloat16*>(O)};
       if (h->attn_tc2) {       // two query tiles per CTA, two softmax warp groups (second schedule of attention_tc.cuh)
-        static bool tc2_attr = false;
-        if (!tc2_attr) {
+        static bool tc2_attr[kMaxDevices] = {};
+        if (!tc2_attr[dev]) {
           FSE_CUDA(cudaFuncSetAttribute(camp_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtc2SmemBytes));
-          tc2_attr = true;
+          tc2_attr[dev] = true;
         }
         dim3 grid2((Tq + 2 * kAtcM - 1) / (2 * kAtcM), h->cfg.heads, B);
         camp_attention_tc2_kernel<<<grid2, kAtc2Threads, kAtc2SmemBytes, st>>>(q_map, *mk, h->vtmap.map, ap);
@@ -458,11 +462,14 @@ int attention(fse_campnet* h, const void* Q, int ldq, int qoff, const void* K, c
     }
   }
   constexpr size_t smem = (2 * kAttTile * (kAttD + 1) + kAttTile * kAttD + kAttTile * (kAttTile + 1)) * sizeof(float);
-  static bool attr_set = false;
+  int dev_simt = 0;
+  FSE_CUDA(cudaGetDevice(&dev_simt));
+  if (dev_simt < 0 || dev_simt >= kMaxDevices) return fail(FSE_ECUDA, "device ordinal %d out of range", dev_simt);
+  static bool attr_set[kMaxDevices] = {};
   auto kern = camp_attention_kernel<TOp>;
-  if (!attr_set) {
+  if (!attr_set[dev_simt]) {
     FSE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_set = true;
+    attr_set[dev_simt] = true;
   }
   if (probs) FSE_CUDA(cudaMemsetAsync(probs, 0, static_cast<size_t>(B) * Tq * Tk * sizeof(float), st));
   dim3 grid((Tq + kAttTile - 1) / kAttTile, h->cfg.heads, B);

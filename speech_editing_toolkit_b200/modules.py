@@ -385,7 +385,8 @@ CampNet = CampNetB200     # the name the reference uses
 
 
 class GaussianDiffusionB200(nn.Module):
-    """Drop-in for GaussianDiffusion on the inference path.
+    """Drop-in for GaussianDiffusion: the sampling path (infer=True) and the training branch (infer=False, one denoiser evaluation
+    under autograd through the native training kernels).
 
     `fs` (the FastSpeech condition encoder, fs.py:49-112) defaults to the native FastSpeechB200 and `mel_encoder` to
     MelEncoderB200, so the whole forward(infer=True) — text tokens to mel — runs behind the C ABI; a reference FastSpeech
@@ -482,13 +483,10 @@ class GaussianDiffusionB200(nn.Module):
 
     def forward(self, txt_tokens, time_mel_masks, mel2ph, spk_embed, ref_mels, f0, uv, energy=None, infer=False,
                 use_pred_mel2ph=False, use_pred_pitch=False, noise=None, seed=None, composite=False):
-        """spec_denoiser.py:154-185, infer=True branch.  Returns the reference's dict (mel_out[B,T,M], ...).
+        """spec_denoiser.py:154-185, both branches.  Returns the reference's dict (mel_out[B,T,M], ...).
         Extras over the reference signature: `noise` ([(S+1),B,M,T] injected draws, tests), `seed` (Philox key) and `composite`
         (mel_out * mask + ref_mels * (1 - mask), the call sites' next line — tasks/speech_editing/spec_denoiser.py:53,84,
         inference/tts/spec_denoiser.py:136 — done in the last step's epilogue)."""
-        if not infer:
-            raise NotImplementedError("GaussianDiffusionB200 implements the sampling path (infer=True); training stays on the "
-                                      "reference's GaussianDiffusion (SURVEY.md §8f row 3)")
         if self.fs is None:
             raise RuntimeError("no condition encoder: pass fs=<reference FastSpeech> or use GaussianDiffusionB200.from_reference()")
         ret = self.fs(txt_tokens, time_mel_masks, mel2ph, spk_embed, f0, uv, energy, skip_decoder=True, infer=infer,
@@ -500,6 +498,19 @@ class GaussianDiffusionB200(nn.Module):
         else:
             decoder_inp = decoder_inp + self.mel_encoder(ref_mels * (1 - time_mel_masks)) * tgt_nonpadding
         ret["decoder_inp"] = decoder_inp
+        if not infer:
+            # the training branch (spec_denoiser.py:168-176): t ~ U{0..S}, x_t = q_sample(ref, t) * nonpadding, one denoiser evaluation.
+            # DiffNetB200 runs its native forward + activation-gradient chain under autograd (train.py); the gradient reaches the
+            # condition encoder through `decoder_inp` when that is a torch module (a reference FastSpeech / MelEncoder injected via
+            # from_reference(native_fs=False)); the native FastSpeechB200 / MelEncoderB200 are forward-only, so with them the
+            # denoiser branch alone is trained.  `noise`: an injected [B,1,M,T] draw, `seed`: unused here (torch's generator draws t).
+            b = txt_tokens.shape[0]
+            nonpadding = (mel2ph != 0).float()[:, None, None, :]
+            t = torch.randint(0, self.num_timesteps + 1, (b,), device=decoder_inp.device).long()
+            x_t = self.diffuse_fn(ref_mels, t, noise=noise) * nonpadding
+            x_0_pred = self.denoise_fn(x_t, t, decoder_inp.transpose(1, 2)) * nonpadding
+            ret["mel_out"] = x_0_pred[:, 0].transpose(1, 2)
+            return ret
         if seed is None:
             seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())      # follows torch.manual_seed like the reference's randn
         if composite:
@@ -509,6 +520,22 @@ class GaussianDiffusionB200(nn.Module):
             x = self._engine().sample(decoder_inp.contiguous(), noise, seed)  # = x[:, 0].transpose(1, 2) of the reference loop
         ret["mel_out"] = x
         return ret
+
+    def q_sample(self, x_start, t, noise=None):
+        """spec_denoiser.py:126-132"""
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        shape = (t.shape[0],) + (1,) * (x_start.dim() - 1)
+        return self.sqrt_alphas_cumprod[t].reshape(shape) * x_start + self.sqrt_one_minus_alphas_cumprod[t].reshape(shape) * noise
+
+    def diffuse_fn(self, x_start, t, noise=None):
+        """spec_denoiser.py:144-152: [B,T,M] -> x_t [B,1,M,T]; items with t < 0 keep the ground-truth mel (and t is clamped in place)."""
+        x_start = self.norm_spec(x_start).transpose(1, 2)[:, None, :, :]
+        zero_idx = t < 0
+        t[zero_idx] = 0
+        out = self.q_sample(x_start, t, noise)
+        out[zero_idx] = x_start[zero_idx]
+        return out
 
     def norm_spec(self, x):
         return x

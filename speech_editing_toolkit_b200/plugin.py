@@ -163,8 +163,9 @@ class SpecDenoiserInferB200:
 class SpeechDenoiserTaskB200:
     """task_cls for `--config egs/spec_denoiser.yaml -hp task_cls=speech_editing_toolkit_b200.plugin.SpeechDenoiserTaskB200`.
 
-    Only the inference / test leg of the reference task is provided (sampling + vocoder); `start()` runs it over
-    synthetic editing batches of the configured shape and reports throughput (no dataset, no trainer)."""
+    The inference / test leg of the reference task (sampling + vocoder) and the model side of its training step (`run_model(infer=False)`
+    -> mel losses, `_training_step`); `start()` runs the inference leg over synthetic editing batches of the configured shape and
+    reports throughput (no dataset, no trainer loop)."""
 
     def __init__(self):
         self.hparams = hparams
@@ -185,6 +186,36 @@ class SpeechDenoiserTaskB200:
         else:                                                      # no shipped checkpoint: seeded HiFi-GAN V1 weights
             self.vocoder = HifiGANB200(state_dict=synth.hifigan_state_dict(self.hparams.get("seed", 1234)))
         return self.vocoder
+
+    def run_model(self, sample: dict, infer: bool = False, *args, **kwargs):
+        """SpeechDenoiserTask.run_model (tasks/speech_editing/spec_denoiser.py:39-62): the model call, the masked mel losses
+        (`l1_coarse`, `ssim_coarse` with the `mel_losses` weights of the yaml, native loss kernels) and the composited mel_out.
+        Returns (losses, output) for infer=False and the output dict for infer=True, as the reference does.  The duration / pitch
+        losses of the reference belong to the condition encoder, which is forward-only here: they are not formed (train the
+        encoder with the reference task; this drop-in trains the denoiser branch)."""
+        from . import train
+        target = sample["mels"]
+        tmm = sample["time_mel_masks"]
+        tmm = tmm[:, :, None] if tmm.dim() == 2 else tmm
+        spk = sample.get("spk_embed") if not self.hparams.get("use_spk_id") else sample.get("spk_ids")
+        output = self.model(sample["txt_tokens"], tmm, mel2ph=sample["mel2ph"], spk_embed=spk, ref_mels=target, f0=sample.get("f0"),
+                            uv=sample.get("uv"), energy=None, infer=infer, **kwargs)
+        lam = []
+        for item in str(self.hparams.get("mel_losses", "l1:0.5|ssim:0.5")).split("|"):     # parse_mel_losses, tasks/tts/tts_utils.py:21-34
+            if item == "":
+                continue
+            name, _, w = item.partition(":")
+            lam.append((name, float(w) if w else 1.0))
+        losses = {f"{k}_coarse": v for k, v in train.mel_losses(output["mel_out"] * tmm, target * tmm, tuple(lam)).items()}
+        output["mel_out"] = output["mel_out"] * tmm + target * (1 - tmm)
+        return output if infer else (losses, output)
+
+    def _training_step(self, sample: dict, batch_idx: int = 0, optimizer_idx: int = -1):
+        """SpeechBaseTask._training_step (tasks/tts/speech_base.py:175-179): total loss = sum of the weighted terms that require grad."""
+        losses, _ = self.run_model(sample, infer=False)
+        total = sum(v for v in losses.values() if isinstance(v, torch.Tensor) and v.requires_grad)
+        losses["batch_size"] = sample["txt_tokens"].shape[0]
+        return total, losses
 
     @torch.no_grad()
     def test_step(self, sample: dict, batch_idx: int = 0):

@@ -169,3 +169,53 @@ def test_mel_loss_kernels_at_training_shape_are_deterministic_and_match_the_torc
     e_g = rel_l2(runs[0][2].cpu().numpy(), a64.grad.cpu().numpy())
     print(f"[margin] mel losses 32 x 1024: l1 {runs[0][0]:.6f} vs {o64['l1'].item():.6f}, ssim {runs[0][1]:.6f} vs {o64['ssim'].item():.6f}, gradient rel-L2 {e_g:.2e}")
     assert abs(runs[0][0] - o64["l1"].item()) < 2e-6 and abs(runs[0][1] - o64["ssim"].item()) < 2e-6 and e_g < 1e-4
+
+
+def test_model_training_branch_vs_reference_model_on_the_gpu(lib_built):
+    """GaussianDiffusionB200.forward(infer=False) -> the task's mel losses -> backward, against the UNMODIFIED reference
+    GaussianDiffusion.forward(infer=False) (spec_denoiser.py:168-176) + torch restatement of its losses + torch.autograd, same weights,
+    same torch seed (both draw t with randint and the noise with randn_like, in that order), both in fp32 (cuDNN TF32 off for the
+    reference, FSE_MODE_SIMT_F32 here).  Stated tolerance: mel_out max-abs 2e-4, losses 1e-5, denoiser gradients rel-L2 1e-3."""
+    _need_gpu()
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("no reference tree (oracle/_ref) on this box")
+    from oracle import ref_runner
+    from oracle.train_oracle import mel_losses_torch
+    from speech_editing_toolkit_b200 import plugin
+    from speech_editing_toolkit_b200.modules import GaussianDiffusionB200
+    B, T = 2, 192
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref_model, _ = ref_runner.build_models(100, device="cuda", vocoder=False)
+        tb = ref_runner.synthetic_inputs(B, T, device="cuda")
+        tmm = tb["time_mel_masks"][:, :, None]
+        args = (tb["txt_tokens"], tmm, tb["mel2ph"], tb["spk_embed"], tb["ref_mels"], tb["f0"], tb["uv"])
+        ours = GaussianDiffusionB200.from_reference(ref_model, mode="simt_f32").train()
+        ref_model.eval()                                             # no dropout draws between the seed and t / noise
+        torch.manual_seed(77)
+        r = ref_model(*args, infer=False)
+        lr = mel_losses_torch(r["mel_out"] * tmm, tb["ref_mels"] * tmm)
+        ref_model.zero_grad()
+        (lr["l1"] + lr["ssim"]).backward()
+        task = plugin.SpeechDenoiserTaskB200.__new__(plugin.SpeechDenoiserTaskB200)
+        task.hparams, task.model, task.vocoder = {"mel_losses": "l1:0.5|ssim:0.5", "use_spk_id": False}, ours, None
+        sample = dict(txt_tokens=tb["txt_tokens"], mels=tb["ref_mels"], mel2ph=tb["mel2ph"], f0=tb["f0"], uv=tb["uv"],
+                      time_mel_masks=tb["time_mel_masks"], spk_embed=tb["spk_embed"])
+        torch.manual_seed(77)
+        total, losses = task._training_step(sample, 0)
+        total.backward()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    _, out = None, None
+    e_l1, e_ss = abs(float(losses["l1_coarse"]) - float(lr["l1"])), abs(float(losses["ssim_coarse"]) - float(lr["ssim"]))
+    errs = {}
+    ref_grads = dict(ref_model.denoise_fn.named_parameters())
+    for name, p in ours.denoise_fn.named_parameters():
+        assert p.grad is not None, name
+        errs[name] = rel_l2(p.grad.cpu().numpy(), ref_grads[name].grad.cpu().numpy())
+    top = sorted(errs.items(), key=lambda kv: -kv[1])[:3]
+    print(f"[margin] model training branch (fp32): l1 err {e_l1:.2e}, ssim err {e_ss:.2e}, denoiser gradients median rel-L2 "
+          f"{float(np.median(list(errs.values()))):.2e}, worst " + ", ".join(f"{k} {v:.1e}" for k, v in top))
+    assert e_l1 < 1e-5 and e_ss < 1e-5 and top[0][1] < 1e-3, top

@@ -63,7 +63,7 @@ def test_diffnet_state_dict_layout_and_checkpoint_roundtrip(tmp_path):
     for k, v in sd.items():
         assert np.array_equal(fresh.denoise_fn.state_dict()[k].numpy(), v)
     assert np.array_equal(fresh.posterior_mean_coef1.numpy(), model.posterior_mean_coef1.numpy())
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):                                # no condition encoder was given: both branches refuse
         fresh(None, None, None, None, None, None, None, infer=False)
 
 
@@ -93,6 +93,25 @@ def test_state_dict_keys_match_live_reference_modules():
         assert torch.equal(v, wrapped.mel_encoder.state_dict()[k]), k
 
 
+@needs_ref
+def test_diffuse_fn_matches_live_reference():
+    """q_sample / diffuse_fn of the training branch (spec_denoiser.py:126-152) with injected noise, incl. the t = -1 items that keep
+    the ground-truth mel and the in-place clamp of t."""
+    refshim.install("egs/spec_denoiser.yaml")
+    from modules.speech_editing.spec_denoiser.diffnet import DiffNet
+    from modules.speech_editing.spec_denoiser.spec_denoiser import GaussianDiffusion
+    from speech_editing_toolkit_b200.modules import GaussianDiffusionB200
+    ref = GaussianDiffusion(list(range(80)), 80, DiffNet(80), timesteps=8, time_scale=1, loss_type="l1", spec_min=[], spec_max=[])
+    ours = GaussianDiffusionB200.from_reference(ref)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 20, 80, generator=g)
+    noise = torch.randn(3, 1, 80, 20, generator=g)
+    t_ref, t_ours = torch.tensor([8, -1, 3]), torch.tensor([8, -1, 3])
+    a, b = ref.diffuse_fn(x, t_ref, noise=noise), ours.diffuse_fn(x, t_ours, noise=noise)
+    assert torch.equal(a, b) and torch.equal(t_ref, t_ours) and int(t_ours[1]) == 0
+    assert torch.equal(b[1, 0], x[1].t())
+
+
 def test_registries_and_plugin_surface():
     from speech_editing_toolkit_b200 import plugin, vocoder
     assert vocoder.get_vocoder_cls("HifiGAN") is vocoder.HifiGANB200 and vocoder.get_vocoder_cls("HifiGAN_B200") is vocoder.HifiGANB200
@@ -103,6 +122,8 @@ def test_registries_and_plugin_surface():
     for meth in ("build_model", "build_vocoder", "run_vocoder", "forward_model", "infer_once"):
         assert hasattr(plugin.SpecDenoiserInferB200, meth)
     assert hasattr(plugin.SpeechDenoiserTaskB200, "start") and callable(plugin.run_task)
+    for meth in ("run_model", "_training_step", "test_step", "test"):     # tasks/speech_editing/spec_denoiser.py, tasks/tts/speech_base.py:175
+        assert hasattr(plugin.SpeechDenoiserTaskB200, meth)
     from speech_editing_toolkit_b200.modules import FastSpeechB200
     m2 = plugin.build_diffusion(HP, phone_encoder=range(41))               # as SpecDenoiserInferB200(phone_encoder=...) / b200_vocab do
     assert isinstance(m2.fs, FastSpeechB200) and m2.fs.dict_size == 41 and m.fs is None
