@@ -35,6 +35,7 @@ struct AttnTcParams {
   int ldo;                     // row stride of O in elements
   const float* key_keep;       // [B, Tk] 1 = attend, 0 = padded key; or null
   __nv_bfloat16* O;            // [B, Tq, ldo], head h at columns h*96
+  float* probs = nullptr;      // tc2 kernel, Tk <= 128 only: [B, Tq, Tk] (zeroed by the caller) += softmax row / heads
 };
 
 __global__ void __launch_bounds__(kAtcThreads, 1) camp_attention_tc_kernel(const __grid_constant__ CUtensorMap mapQ,
@@ -511,6 +512,46 @@ __global__ void __launch_bounds__(kAtc2Threads, 1) camp_attention_tc2_kernel(con
         for (int c = 0; c < kAttD / 8; ++c)
           reinterpret_cast<uint4*>(dst)[c] = make_uint4(pack_bf16x2(o[8 * c] * inv, o[8 * c + 1] * inv), pack_bf16x2(o[8 * c + 2] * inv, o[8 * c + 3] * inv),
                                                        pack_bf16x2(o[8 * c + 4] * inv, o[8 * c + 5] * inv), pack_bf16x2(o[8 * c + 6] * inv, o[8 * c + 7] * inv));
+      }
+      if (p.probs != nullptr) {
+        // Head-averaged attention probabilities (transformer.py:398-419: the decoder's first layer returns them).  Single key tile
+        // only (the host checks Tk <= 128): the score tile is still in TMEM and (mrow, lrow) are final, so the row is one more pass
+        // of ex2 over it.  One vector reduction per 4 keys into the zeroed [B, Tq, Tk] buffer; with two heads the sum of the two
+        // addends does not depend on their order.
+        const float* flags = sKeep + (g * 2) * kAtcN;
+        const bool masked = p.key_keep != nullptr || kAtcN > p.Tk;
+        const float scale = 1.0f / (lrow * static_cast<float>(p.heads)), moff = mrow * kLog2e;
+        float* prow = p.probs + (static_cast<size_t>(b) * p.Tq + (qrow < p.Tq ? qrow : 0)) * p.Tk;
+        const bool vec = (p.Tk & 3) == 0;
+        uint32_t rr[32];
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          ptx::tmem_ld_32x32b_x32(s_addr + c * 32, rr);          // warp-collective: every lane takes part, stores are predicated
+          ptx::tmem_wait_ld();
+          float pr[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float sv = __uint_as_float(rr[i]);
+            const float f = masked ? flags[c * 32 + i] : 1.f;
+            sv = f == 0.f ? -1e8f : sv;
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(sv, kLog2e, -moff)));
+            pr[i] = f < 0.f ? 0.f : e * scale;
+          }
+          if (qrow < p.Tq) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const int k = c * 32 + i;
+              if (vec && k + 3 < p.Tk) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(prow + k), "f"(pr[i]), "f"(pr[i + 1]), "f"(pr[i + 2]), "f"(pr[i + 3]) : "memory");
+              } else {
+#pragma unroll
+                for (int e4 = 0; e4 < 4; ++e4)
+                  if (k + e4 < p.Tk) atomicAdd(prow + k + e4, pr[i + e4]);
+              }
+            }
+          }
+        }
       }
     }
   }

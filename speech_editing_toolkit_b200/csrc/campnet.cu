@@ -340,6 +340,7 @@ struct fse_campnet {
   fse_mel_encoder* mel = nullptr;
   bool attn_tc = false;                 // tcgen05 attention (FSE_MODE_TC_BF16; FSE_CAMP_ATTN=simt selects the CUDA-core kernel)
   bool attn_tc2 = false;                // ... its two-query-tile schedule (the default; FSE_CAMP_ATTN=tc selects one tile per CTA)
+  bool probs_simt = false;              // FSE_CAMP_PROBS=simt: the probabilities call of layer 0 on the CUDA-core kernel (cross-check)
   struct VtMap { const void* buf = nullptr; int Tkp = 0, B = 0; CUtensorMap map{}; } vtmap;
 };
 
@@ -422,7 +423,10 @@ template <typename TOp>
 int attention(fse_campnet* h, const void* Q, int ldq, int qoff, const void* K, const void* V, int ldkv, int koff, int voff,
               const float* key_keep, void* O, int B, int Tq, int Tk, float* probs, const void* vt, int Tkp, cudaStream_t st) {
   if constexpr (std::is_same<TOp, __nv_bfloat16>::value) {
-    if (h->attn_tc && vt != nullptr && probs == nullptr) {
+    // probabilities (decoder layer 0) come out of the two-tile tensor-core kernel when the keys fit one tile (Tk <= 128: the
+    // cross-attention over the phone sequence); otherwise that call runs the CUDA-core kernel below
+    const bool probs_tc = probs != nullptr && h->attn_tc2 && Tk <= kAtcN && !h->probs_simt;
+    if (h->attn_tc && vt != nullptr && (probs == nullptr || probs_tc)) {
       // tensor cores: S = Q K^T and O = P V as tcgen05.mma, V^T from the projection's epilogue (attention_tc.cuh)
       // function attributes are per context: flags keyed by device ordinal, not process-global
       int dev = 0;
@@ -442,6 +446,10 @@ int attention(fse_campnet* h, const void* Q, int ldq, int qoff, const void* K, c
         h->vtmap.buf = vt; h->vtmap.Tkp = Tkp; h->vtmap.B = B;
       }
       AttnTcParams ap{Tq, Tk, h->cfg.heads, qoff, koff, h->cfg.hidden, key_keep, static_cast<__nv_bfloat16*>(O)};
+      if (probs_tc) {
+        FSE_CUDA(cudaMemsetAsync(probs, 0, static_cast<size_t>(B) * Tq * Tk * sizeof(float), st));
+        ap.probs = probs;
+      }
       if (h->attn_tc2) {       // two query tiles per CTA, two softmax warp groups (second schedule of attention_tc.cuh)
         static bool tc2_attr[kMaxDevices] = {};
         if (!tc2_attr[dev]) {
@@ -605,6 +613,8 @@ int fse_campnet_create(const fse_campnet_config* cfg, fse_campnet** out) {
   const char* sel = std::getenv("FSE_CAMP_ATTN");
   h->attn_tc = cfg->mode == FSE_MODE_TC_BF16 && !(sel && std::string(sel) == "simt");
   h->attn_tc2 = h->attn_tc && !(sel && std::string(sel) == "tc");
+  const char* psel = std::getenv("FSE_CAMP_PROBS");
+  h->probs_simt = psel && std::string(psel) == "simt";
   *out = h;
   return FSE_OK;
 }

@@ -3,6 +3,7 @@
 // launch context (tensor-map cache, launch counter) around the conv-as-GEMM primitive of conv_gemm.cuh.
 // Everything has internal linkage (anonymous namespace): each translation unit instantiates what it uses.
 #pragma once
+#include <cstdlib>
 #include <cmath>
 #include <deque>
 #include <string>
@@ -330,6 +331,11 @@ inline int pack_conv_raw(LayerCtx* ctx, const std::string& name, const float* w,
   const int nkb = (Cin + KB - 1) / KB;
   cw.Kp = k * nkb * KB;
   cw.BN = Cout % 256 == 0 ? 256 : (Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : (Cout % 32 == 0 ? 32 : (Cout % 16 == 0 && Cout <= 256 ? Cout : 0))));
+  // hidden 192 and its multiples (every projection / FFN of CampNet and of the condition encoder): 192-wide tiles instead of three
+  // 64-wide (or 128-wide) ones — the activation tile is read once per 192 outputs and the MMA is N = 192 (an N = 64 instruction is
+  // bound by its shared-memory operand reads).  FSE_BN192=0 restores the old choice.
+  static const bool bn192 = !(std::getenv("FSE_BN192") && std::getenv("FSE_BN192")[0] == '0');
+  if (bn192 && Cout % 192 == 0 && Cout % 256 != 0) cw.BN = 192;
   if (cw.BN == 0) return fail(FSE_EINVAL, "%s: %d output channels is not a multiple of 16", name.c_str(), Cout);
   for (int j = 0; j < k; ++j) cw.offs[j] = offs[j];
   std::vector<float> p(static_cast<size_t>(Cout) * cw.Kp, 0.f);

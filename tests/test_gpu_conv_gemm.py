@@ -31,6 +31,9 @@ CASES = [
     (2, 65, 512, [0, -1], 2048, 256, 64),                            # transposed conv as 2-tap GEMM, 8 n-tiles
     (1, 257, 64, [-3, -2, -1, 0, 1, 2, 3], 64, 64, 64),              # k=7, three tiles
     (3, 1, 128, [-1, 0, 1], 128, 128, 64),                           # T = 1
+    (2, 300, 192, [0], 192, 192, 64),                                # hidden-192 projections (CampNet / condition encoder): one 192-wide tile
+    (1, 260, 192, [-4, -3, -2, -1, 0, 1, 2, 3, 4], 384, 192, 64),    # CampNet FFN conv k=9, N = 384 as two 192-wide tiles
+    (1, 200, 384, [0], 192, 192, 64),                                # FFN 1x1 back to 192
 ]
 
 
