@@ -269,7 +269,7 @@ struct LayerCtx {
   int mode = FSE_MODE_TC_BF16;
   bool bf16 = true;
   int hidden = 0;
-  struct MapEntry { const void* buf; int C, T, B, KB; CUtensorMap map; };
+  struct MapEntry { const void* buf; int C, T, B, KB, rows = 128; CUtensorMap map; };
   std::deque<MapEntry> cache;
   std::vector<void*> owned;             // every device allocation of the handle
   long long launches = 0;
@@ -368,14 +368,14 @@ inline int pack_conv(LayerCtx* ctx, const TensorTable& tt, const std::string& na
   return pack_conv_raw(ctx, name, w, bias, Cout, Cin, k, offs, cw);
 }
 
-inline int get_act_map(LayerCtx* ctx, const void* buf, int C, int T, int B, int KB, const CUtensorMap** out) {
+inline int get_act_map(LayerCtx* ctx, const void* buf, int C, int T, int B, int KB, const CUtensorMap** out, int rows = kTileM) {
   for (auto& e : ctx->cache)
-    if (e.buf == buf && e.C == C && e.T == T && e.B == B && e.KB == KB) { *out = &e.map; return FSE_OK; }
+    if (e.buf == buf && e.C == C && e.T == T && e.B == B && e.KB == KB && e.rows == rows) { *out = &e.map; return FSE_OK; }
   if (ctx->cache.size() >= 96) ctx->cache.clear();      // maps are copied into the launch, dropping them is safe
   ctx->cache.emplace_back();
   auto& e = ctx->cache.back();
-  e.buf = buf; e.C = C; e.T = T; e.B = B; e.KB = KB;
-  const int rc = make_map_act(&e.map, buf, C, T, B, KB, kTileM, ctx->bf16 ? 2 : 4);
+  e.buf = buf; e.C = C; e.T = T; e.B = B; e.KB = KB; e.rows = rows;
+  const int rc = make_map_act(&e.map, buf, C, T, B, KB, rows, ctx->bf16 ? 2 : 4);
   if (rc != FSE_OK) { ctx->cache.pop_back(); return rc; }
   *out = &e.map;
   return FSE_OK;
@@ -386,7 +386,14 @@ template <typename TOp, class Epi>
 inline int run_conv(LayerCtx* ctx, const ConvW& cw, const void* A, int B, int T, const Epi& epi, cudaStream_t st) {
   ConvGemmParams p = make_params(B, T, T, cw.Cin, cw.ntaps, cw.offs, 0, cw.N, cw.KB);
   GemmOperands op; op.A0 = A; op.W = cw.W; op.mW = &cw.map; op.BN = cw.BN;
-  if (mode_is_tc(ctx->mode)) FSE_TRY(get_act_map(ctx, A, cw.Cin, T, B, cw.KB, &op.mA0));
+  if (mode_is_tc(ctx->mode)) {
+    // multi-tap convs (k = 9 FFN, k = 5 encoder / predictor convs): one activation load per channel block, every tap a row-shifted
+    // descriptor of that copy — the per-tap loads made the k = 9 FFN conv ingest-bound (9 x 16 KB per channel block and tile)
+    static const bool shared_ok = !(std::getenv("FSE_ROW_SHARED_A") && std::getenv("FSE_ROW_SHARED_A")[0] == '0');
+    int rows = kTileM;
+    if (shared_ok && cw.ntaps >= 2 && enable_shared_a(p, 1, ctx->bf16 ? 2 : 4)) rows = p.Rbox;
+    FSE_TRY(get_act_map(ctx, A, cw.Cin, T, B, cw.KB, &op.mA0, rows));
+  }
   return run_conv_gemm<TOp>(ctx->mode, p, op, epi, st, LaunchCtx{&ctx->launches, nullptr, 0});
 }
 

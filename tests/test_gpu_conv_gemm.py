@@ -34,6 +34,7 @@ CASES = [
     (2, 300, 192, [0], 192, 192, 64),                                # hidden-192 projections (CampNet / condition encoder): one 192-wide tile
     (1, 260, 192, [-4, -3, -2, -1, 0, 1, 2, 3, 4], 384, 192, 64),    # CampNet FFN conv k=9, N = 384 as two 192-wide tiles
     (1, 200, 384, [0], 192, 192, 64),                                # FFN 1x1 back to 192
+    (2, 150, 192, [-8, -7, -6, -5, -4, -3, -2, -1, 0], 384, 192, 64),  # CampNet decoder FFN: causal 'LEFT' taps
 ]
 
 
