@@ -336,8 +336,8 @@ int64_t fse_mel_frontend_last_launches(const fse_mel_frontend* h);
 /* --- training-mode DiffNet (BASELINE configs[4]) -----------------------------------------
  * The denoiser call of GaussianDiffusion.forward(infer=False) (spec_denoiser.py:168-176: x_0_pred = denoise_fn(x_t, t, cond)) with
  * the activations its backward needs kept in the workspace, and the activation-gradient chain of that backward; every GEMM of both
- * is a conv-GEMM launch of this library.  The weight gradients are plain GEMMs over tensors left in the workspace (fse_train_layout)
- * and are taken by the caller with library GEMMs, as are the losses, the optimizer and the gradient all-reduce
+ * is a conv-GEMM launch of this library.  The weight gradients are GEMMs over tensors left in the workspace (fse_train_layout):
+ * the caller takes them with fse_wgrad (below) and the losses with fse_mel_loss_*; optimizer and gradient all-reduce are torch
  * (speech_editing_toolkit_b200/train.py).  mode: FSE_MODE_TC_BF16 | FSE_MODE_TC_TF32 | FSE_MODE_SIMT_F32. */
 typedef struct fse_trainer fse_trainer;
 int fse_train_create(const fse_denoiser_config* cfg, fse_trainer** out);
@@ -359,6 +359,20 @@ int fse_train_forward(fse_trainer* h, const float* x_t, const float* cond, const
 int fse_train_backward(fse_trainer* h, const float* dx0, float* dcond, int32_t B, int32_t T, void* workspace, int64_t workspace_bytes,
                        void* stream);
 int64_t fse_train_last_launches(const fse_trainer* h);
+
+/* --- weight-gradient GEMM of the training step ---------------------------------------------
+ * Out[m, n, j] = sum over b, t of P[b, t, m] * Q[b, t + offs[j], n] (rows of Q outside [0, T) read as zero): the weight gradient
+ * torch.autograd forms for every Conv1d / Linear of DiffNet (diffnet.py:60-132) with P = gradient of the layer's output, Q = the layer's
+ * input, offs = the conv's tap offsets.  tcgen05 with MN-major operands straight from the [B, T, channels] buffers (no transposed
+ * copies), frames split over the SMs, slices combined in a fixed order (bit-reproducible).  csrc/wgrad.cu
+ *   mode: FSE_MODE_TC_BF16 (P, Q bf16) or FSE_MODE_TC_TF32 (P, Q fp32, kind::tf32); P: [B, T, ldp] with M columns used, Q: [B, T, ldq]
+ *   with N columns used (row pitches in elements; pointers and pitches 16-byte aligned); out fp32, element (m, n, j) at
+ *   out[m * ld_m + n * ld_n + j * ld_j].  workspace: fse_wgrad_workspace_bytes(...) bytes of scratch (the per-slice partial tiles);
+ *   it may be shared by consecutive calls on one stream. */
+int64_t fse_wgrad_workspace_bytes(int32_t mode, int32_t B, int32_t T, int32_t M, int32_t N, int32_t ntaps);
+int fse_wgrad(int32_t mode, const void* P, int64_t ldp, const void* Q, int64_t ldq, int32_t B, int32_t T, int32_t M, int32_t N,
+              const int32_t* offs, int32_t ntaps, float* out, int64_t ld_m, int64_t ld_n, int64_t ld_j, void* workspace,
+              int64_t workspace_bytes, void* stream);
 
 /* --- mel losses of the training step ------------------------------------------------------
  * SpeechBaseTask.add_mel_loss with `mel_losses: l1:0.5|ssim:0.5` (tasks/tts/speech_base.py:219-257; utils/metrics/ssim.py:24-44):

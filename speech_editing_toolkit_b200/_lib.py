@@ -124,6 +124,9 @@ SIGNATURES = {
     "fse_train_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "fse_train_backward": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "fse_train_last_launches": (C.c_int64, [_P]),
+    "fse_wgrad_workspace_bytes": (C.c_int64, [C.c_int32] * 6),
+    "fse_wgrad": (C.c_int, [C.c_int32, _P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+                            _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
     "fse_mel_loss_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "fse_mel_loss_forward": (C.c_int, [_P, _P, C.c_float, C.c_float, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "fse_mel_loss_backward": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P]),

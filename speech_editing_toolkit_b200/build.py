@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB_PATH = os.path.join(HERE, "libfse_b200.so")
-SOURCES = ["denoiser.cu", "hifigan.cu", "mel_encoder.cu", "cond_encoder.cu", "campnet.cu", "edit_region.cu", "mel_frontend.cu", "mel_loss.cu", "debug.cu"]
+SOURCES = ["denoiser.cu", "hifigan.cu", "mel_encoder.cu", "cond_encoder.cu", "campnet.cu", "edit_region.cu", "mel_frontend.cu", "mel_loss.cu", "wgrad.cu", "debug.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

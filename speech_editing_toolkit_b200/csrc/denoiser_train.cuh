@@ -5,10 +5,10 @@
 //
 // What is native here and what is not.  Native: every GEMM on the data path forwards (input projection, gated conv, output
 // projection with residual / skip accumulation, skip and output projections) and backwards (the dgrad of each of them: a
-// conv-GEMM over the transposed / tap-reversed weights), plus the elementwise pieces between them.  NOT here: the weight
-// gradients.  Each is a plain GEMM over tensors this code leaves in the workspace (dW = dY^T A with K = all frames), and is
-// taken by the caller with library GEMMs (speech_editing_toolkit_b200/train.py: torch.matmul = cuBLAS) together with the bias
-// sums, the timestep-MLP backward (a [B, 256] problem), the losses, the optimizer and the NCCL all-reduce.
+// conv-GEMM over the transposed / tap-reversed weights), plus the elementwise pieces between them.  The weight gradients are
+// GEMMs over tensors this code leaves in the workspace (dW = dY^T A with K = all frames): csrc/wgrad.cu (fse_wgrad, tcgen05 over
+// MN-major operands), called per weight by speech_editing_toolkit_b200/train.py, which also owns the bias sums, the timestep-MLP
+// backward (a [B, 256] problem), the optimizer and the NCCL all-reduce.
 //
 //   forward, per layer l:   hin = h + d_l                      (add_bcast_cast_kernel; d_l = diffusion_projection(temb), given)
 //                           y   = conv_k3(hin) + W_cp cond + b (GEMM, K = 3C + H, fp32 out)

@@ -2,10 +2,11 @@
 
 `DiffNetB200.forward` under autograd routes here: the forward and the activation-gradient chain of the backward run natively
 (`fse_train_forward` / `fse_train_backward`, csrc/denoiser_train.cuh: every data-path GEMM is a conv-GEMM launch of the library, tcgen05
-in the tensor-core modes); the weight gradients — plain GEMMs `dW = dY^T A` over tensors the native code leaves in its workspace —
-are taken here with torch.matmul (cuBLAS: the library-GEMM case), together with the bias sums and the timestep-MLP path (a [B, 256]
-problem that stays a torch graph).  Losses, optimizer and the NCCL gradient all-reduce are torch plumbing (`train_step`,
-`allreduce_grads`).
+in the tensor-core modes), and so do the weight gradients — GEMMs `dW = dY^T A` with K = all frames over tensors the native code leaves
+in its workspace, taken by `fse_wgrad` (csrc/wgrad.cu: tcgen05 with MN-major operands, no transposed copies; `FSE_TRAIN_WGRAD=lib` and
+the fp32 checking mode use torch.mm = cuBLASLt instead, the cross-check).  The bias sums and the timestep-MLP path (a [B, 256] problem)
+stay torch reductions / a torch graph; the losses are native (`fse_mel_loss_*`); optimizer and the NCCL gradient all-reduce are torch
+plumbing (`train_step`, `BucketedAllReduce`).
 
 Reference semantics: modules/speech_editing/spec_denoiser/diffnet.py:60-132 under torch.autograd; the call site is
 spec_denoiser.py:168-176 (`x_0_pred = self.denoise_fn(x_t, t, cond) * nonpadding`).
@@ -14,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -105,6 +107,41 @@ class DiffNetTrainer:
                 "dres": v(16, (L, N, Cc), op), "dy": v(17, (B, T, L * 2 * Cc), op)}
 
 
+class WeightGradGemm:
+    """`fse_wgrad` (csrc/wgrad.cu): Out[m, n, j] = sum_{b,t} P[b, t, m] Q[b, t + offs[j], n] on tcgen05 with MN-major operands, straight
+    from the [B, T, channels] buffers of the native backward (strided views included).  One workspace per device, shared by the calls of
+    a backward pass (its 4 KB head of arrival counters is zero between calls)."""
+    _ws: Dict[int, torch.Tensor] = {}
+
+    def __init__(self, mode: str):
+        self.mode = MODES[mode]
+        self.es = 2 if mode == "tc_bf16" else 4
+
+    def _workspace(self, nbytes: int, device) -> torch.Tensor:
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        ws = WeightGradGemm._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            WeightGradGemm._ws[key] = ws
+        return ws
+
+    def __call__(self, P: torch.Tensor, Q: torch.Tensor, out: torch.Tensor, offs=(0,)):
+        """P [B, T, M] and Q [B, T, N]: views with unit channel stride and a common (B, T) grid; out fp32 [M, N] or [M, N, taps] (any strides)."""
+        B, T, M = P.shape
+        N = Q.shape[2]
+        assert Q.shape[:2] == (B, T) and P.stride(2) == 1 and Q.stride(2) == 1
+        assert B == 1 or (P.stride(0) == T * P.stride(1) and Q.stride(0) == T * Q.stride(1)), "utterances must follow each other at the row pitch"
+        taps = len(offs)
+        assert out.dtype == torch.float32 and tuple(out.shape[:2]) == (M, N) and (out.dim() == 2 or out.shape[2] == taps)
+        lib = _lib.lib()
+        nbytes = lib.fse_wgrad_workspace_bytes(self.mode, B, T, M, N, taps)
+        ws = self._workspace(nbytes, P.device)
+        arr = (C.c_int32 * taps)(*[int(o) for o in offs])
+        check(lib.fse_wgrad(self.mode, _ptr(P), P.stride(1), _ptr(Q), Q.stride(1), B, T, M, N, arr, taps, _ptr(out), out.stride(0), out.stride(1),
+                            out.stride(2) if out.dim() == 3 else 0, _ptr(ws), ws.numel(), _stream()))
+        return out
+
+
 def param_names(layers: int) -> List[str]:
     """Parameters whose gradients `DiffNetFunction.backward` returns, in this order (the timestep path — mlp.*, diffusion_projection.* —
     enters through `d` and stays a torch graph)."""
@@ -140,7 +177,15 @@ class DiffNetFunction(torch.autograd.Function):
         grads: Dict[str, torch.Tensor] = {}
         hook = ctx.hook                                        # called with (name -> grad) groups as they become ready (all-reduce overlap)
 
+        # Weight gradients: native tcgen05 GEMMs over MN-major operands in the tensor-core modes (fse_wgrad); FSE_TRAIN_WGRAD=lib (and
+        # the fp32 checking mode) take them with library GEMMs instead — the cross-check of the native kernel.
+        native = tr.mode in ("tc_bf16", "tc_tf32") and dx0.is_cuda and os.environ.get("FSE_TRAIN_WGRAD", "native") != "lib"
+        wg = WeightGradGemm(tr.mode) if native else None
+
         def mm(a, b):                                          # a^T b over all rows: operand-dtype GEMM, fp32 accumulator written out as fp32
+            if native and a.dtype == tr.op_dtype and b.dtype == tr.op_dtype:
+                out = torch.empty(a.shape[1], b.shape[1], dtype=f32, device=a.device)
+                return wg(a.unsqueeze(0), b.unsqueeze(0), out)
             return torch.mm(a.t(), b) if a.dtype == f32 else torch.mm(a.t(), b, out_dtype=f32)
         dx_rows, r, dz, s, dS = v["dx_rows"], v["r"], v["dz"], v["s"], v["dS"]
         g = {"output_projection.weight": mm(dx_rows, r)[:, :, None], "output_projection.bias": dx0.sum((0, 2)),
@@ -159,7 +204,7 @@ class DiffNetFunction(torch.autograd.Function):
         dS_sum = dS.sum(0, dtype=f32)
         dy2d = dy_all.view(N, L * 2 * Cc)
         cond2d = v["cond"].reshape(N, -1)
-        gcond_all = mm(dy2d, cond2d)                                                     # conditioner_projection of every layer: ONE GEMM [L * 2C, H]
+        gcond_all = None if native else mm(dy2d, cond2d)                                 # library path: conditioner_projection of every layer as ONE GEMM [L * 2C, H]
         # d_l enters as hin = h + d_l inside the zero padding: sum_t of the conv's input gradient, tap by tap (three batched matmuls)
         w_all = torch.stack([w.to(f32) for w in ctx.saved_tensors])                      # [L, 2C, C, 3]
         head_all = torch.stack([edge[ctx.dil[l]][0][:, l] for l in range(L)])            # [L, B, 2C]: frames the tap with offset -dil never reads
@@ -176,18 +221,21 @@ class DiffNetFunction(torch.autograd.Function):
             gw = torch.empty(2 * Cc, Cc, 3, dtype=f32, device=dx0.device)
             # y[t] += W_j hin[t + off], off = (j - 1) dil.  The shifted taps are GEMMs over the flat row sequence shifted by `dil` rows
             # (no copies), minus the (B - 1) dil row pairs that straddle two utterances.
-            gw[:, :, 1] = mm(dy, hin2d)
-            gw[:, :, 0] = mm(dy[dil:], hin2d[:N - dil])
-            gw[:, :, 2] = mm(dy[:N - dil], hin2d[dil:])
-            if B > 1:
-                gw[:, :, 0] -= mm(dy3[1:, :dil].reshape(-1, 2 * Cc), hin[:-1, T - dil:].reshape(-1, Cc))
-                gw[:, :, 2] -= mm(dy3[:-1, T - dil:].reshape(-1, 2 * Cc), hin[1:, :dil].reshape(-1, Cc))
+            if native:                                                                   # the three taps as one launch: Q rows shifted by TMA
+                wg(dy3, hin, gw, offs=(-dil, 0, dil))
+            else:
+                gw[:, :, 1] = mm(dy, hin2d)
+                gw[:, :, 0] = mm(dy[dil:], hin2d[:N - dil])
+                gw[:, :, 2] = mm(dy[:N - dil], hin2d[dil:])
+                if B > 1:
+                    gw[:, :, 0] -= mm(dy3[1:, :dil].reshape(-1, 2 * Cc), hin[:-1, T - dil:].reshape(-1, Cc))
+                    gw[:, :, 2] -= mm(dy3[:-1, T - dil:].reshape(-1, 2 * Cc), hin[1:, :dil].reshape(-1, Cc))
             gb = dysum_all[:, l].sum(0)
             gop = torch.empty(2 * Cc, Cc, dtype=f32, device=dx0.device)                  # gradient of o = [res | skip] against u_l
             gop[:Cc] = mm(v["dres"][l], v["u"][l])
             gop[Cc:] = mm(dS, v["u"][l])
             g = {p + "dilated_conv.weight": gw, p + "dilated_conv.bias": gb,
-                 p + "conditioner_projection.weight": gcond_all[l * 2 * Cc:(l + 1) * 2 * Cc, :, None],
+                 p + "conditioner_projection.weight": (mm(dy, cond2d) if native else gcond_all[l * 2 * Cc:(l + 1) * 2 * Cc])[:, :, None],
                  p + "conditioner_projection.bias": gb,
                  p + "output_projection.weight": gop[:, :, None], p + "output_projection.bias": torch.cat([dres_sum[l], dS_sum])}
             grads.update(g)

@@ -1,5 +1,5 @@
 """Training step: the native mel losses, and forward and gradients of `DiffNetB200` under autograd — native forward and
-activation-gradient chain (fse_train_*), weight gradients by library GEMMs — against tests/golden/diffnet_train.npz, the gradients
+activation-gradient chain (fse_train_*), weight gradients by fse_wgrad (tcgen05, MN-major operands) — against tests/golden/diffnet_train.npz, the gradients
 torch.autograd computes through the UNMODIFIED reference DiffNet (oracle/make_golden.py train).
 
 Stated tolerances (relative L2 against the fp32 CPU autograd of the reference): FSE_MODE_SIMT_F32 <= 1e-4 on the output and on every
@@ -219,3 +219,58 @@ def test_model_training_branch_vs_reference_model_on_the_gpu(lib_built):
     print(f"[margin] model training branch (fp32): l1 err {e_l1:.2e}, ssim err {e_ss:.2e}, denoiser gradients median rel-L2 "
           f"{float(np.median(list(errs.values()))):.2e}, worst " + ", ".join(f"{k} {v:.1e}" for k, v in top))
     assert e_l1 < 1e-5 and e_ss < 1e-5 and top[0][1] < 1e-3, top
+
+
+@pytest.mark.parametrize("mode", ["tc_bf16", "tc_tf32"])
+def test_weight_gradient_gemm_vs_float64(lib_built, mode):
+    """fse_wgrad (tcgen05, MN-major operands) against a float64 evaluation over the same rounded operands: the three taps of a conv with the
+    zero padding at utterance ends (ragged T: partial K chunks), a strided P view (one layer's slice of a wider buffer), narrow M / N
+    (80 columns: the input / output projections), and the flat [1, B*T] form of a plain GEMM.  Two calls must agree bit for bit (the frame
+    slices are combined in a fixed order).  Stated tolerance: 5e-5 of the largest output element (fp32 accumulation of exact products; the measured error is printed)."""
+    _need_gpu()
+    from speech_editing_toolkit_b200 import train
+    wg = train.WeightGradGemm(mode)
+    dt = torch.bfloat16 if mode == "tc_bf16" else torch.float32
+    gen = torch.Generator().manual_seed(3)
+
+    def operand(*shape):
+        x = torch.randn(*shape, generator=gen)
+        if mode == "tc_tf32":                                         # what the tensor core keeps of an fp32 container: 10 mantissa bits
+            x = (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
+        return x.to(dt).cuda()
+
+    def ref(P, Q, offs):
+        P64, Q64 = P.double(), Q.double()
+        B, T = P.shape[:2]
+        out = torch.zeros(P.shape[2], Q.shape[2], len(offs), dtype=torch.float64, device=P.device)
+        for j, off in enumerate(offs):
+            lo, hi = max(0, -off), min(T, T - off)
+            if hi > lo:
+                out[:, :, j] = torch.einsum("btm,btn->mn", P64[:, lo:hi], Q64[:, lo + off:hi + off])
+        return out
+
+    cases = []
+    wide = operand(3, 203, 5 * 512)
+    cases.append(("conv taps, strided P", wide[:, :, 2 * 512:3 * 512], operand(3, 203, 256), (-1, 0, 1)))
+    cases.append(("dilated taps", operand(2, 130, 256), operand(2, 130, 192), (-4, 0, 4)))
+    cases.append(("narrow M", operand(2, 96, 80), operand(2, 96, 256), (0,)))
+    cases.append(("narrow N", operand(1, 77, 256), operand(1, 77, 80), (0,)))
+    cases.append(("flat rows", operand(1, 4099, 512), operand(1, 4099, 256), (0,)))
+    worst = 0.0
+    for name, P, Q, offs in cases:
+        outs = []
+        for _ in range(2):
+            out = torch.full((P.shape[2], Q.shape[2], len(offs)), float("nan"), device="cuda")
+            wg(P, Q, out, offs)
+            outs.append(out)
+        assert torch.equal(outs[0], outs[1]), name
+        want = ref(P, Q, offs)
+        err = float((outs[0].double() - want).abs().max() / want.abs().max())
+        worst = max(worst, err)
+        assert err < 5e-5, (name, err)
+    # torch-layout output with strides: [M, N, taps] viewed from a [M, N * taps] buffer and a transposed 2-D output
+    P, Q = cases[0][1], cases[0][2]
+    buf = torch.zeros(512, 256 * 3 + 5, device="cuda")
+    wg(P, Q, buf[:, :768].view(512, 256, 3), (-1, 0, 1))
+    assert float((buf[:, :768].view(512, 256, 3).double() - ref(P, Q, (-1, 0, 1))).abs().max()) < 2e-5 * float(ref(P, Q, (-1, 0, 1)).abs().max()) and float(buf[:, 768:].abs().max()) == 0.0
+    print(f"[margin] fse_wgrad {mode}: worst error {worst:.2e} of the largest element over {len(cases)} shapes, bit-identical repeats")
