@@ -492,7 +492,7 @@ def run_b200(args):
     def train_record(steps=5, mode="tc_bf16"):
         """BASELINE configs[4]: the denoiser branch of the FluentSpeech training step in bf16, data-parallel over the ranks of this
         launch (one bucketed NCCL all-reduce per residual layer, overlapped with the remaining weight-gradient GEMMs), 32 x 1024-frame
-        synthetic batches per GPU: q_sample, DiffNet forward + backward (native data path, library-GEMM weight gradients), masked
+        synthetic batches per GPU: q_sample, DiffNet forward + backward (native data path, tcgen05 weight-gradient GEMMs over MN-major operands), masked
         l1 + ssim loss, fused AdamW.  The condition encoder's forward / backward is not part of it (cond is a resident input)."""
         from speech_editing_toolkit_b200 import train
         from speech_editing_toolkit_b200.modules import DiffNetB200

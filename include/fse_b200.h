@@ -370,6 +370,18 @@ int64_t fse_train_last_launches(const fse_trainer* h);
  *   out[m * ld_m + n * ld_n + j * ld_j].  workspace: fse_wgrad_workspace_bytes(...) bytes of scratch (the per-slice partial tiles);
  *   it may be shared by consecutive calls on one stream. */
 int64_t fse_wgrad_workspace_bytes(int32_t mode, int32_t B, int32_t T, int32_t M, int32_t N, int32_t ntaps);
+/* up to 4 such GEMMs over the same (B, T) frame grid in ONE launch (the four weight gradients of a residual layer): their output tiles
+ * share the SMs and one reduction; same conventions as fse_wgrad */
+typedef struct fse_wgrad_problem {
+  const void* P; int64_t ldp;
+  const void* Q; int64_t ldq;
+  int32_t M, N;
+  const int32_t* offs; int32_t ntaps;
+  float* out; int64_t ld_m, ld_n, ld_j;
+} fse_wgrad_problem;
+int64_t fse_wgrad_group_workspace_bytes(int32_t mode, const fse_wgrad_problem* problems, int32_t n, int32_t B, int32_t T);
+int fse_wgrad_group(int32_t mode, const fse_wgrad_problem* problems, int32_t n, int32_t B, int32_t T, void* workspace,
+                    int64_t workspace_bytes, void* stream);
 int fse_wgrad(int32_t mode, const void* P, int64_t ldp, const void* Q, int64_t ldq, int32_t B, int32_t T, int32_t M, int32_t N,
               const int32_t* offs, int32_t ntaps, float* out, int64_t ld_m, int64_t ld_n, int64_t ld_j, void* workspace,
               int64_t workspace_bytes, void* stream);

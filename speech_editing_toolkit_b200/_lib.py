@@ -48,6 +48,12 @@ class CampNetConfig(C.Structure):
                 ("heads", C.c_int32), ("ffn_kernel", C.c_int32), ("fine_blocks", C.c_int32), ("fine_kernel", C.c_int32), ("mode", C.c_int32)]
 
 
+class WgradProblem(C.Structure):
+    """fse_wgrad_problem (include/fse_b200.h)"""
+    _fields_ = [("P", C.c_void_p), ("ldp", C.c_int64), ("Q", C.c_void_p), ("ldq", C.c_int64), ("M", C.c_int32), ("N", C.c_int32),
+                ("offs", C.POINTER(C.c_int32)), ("ntaps", C.c_int32), ("out", C.c_void_p), ("ld_m", C.c_int64), ("ld_n", C.c_int64), ("ld_j", C.c_int64)]
+
+
 class MelFrontendConfig(C.Structure):
     _fields_ = [("sample_rate", C.c_int32), ("fft_size", C.c_int32), ("hop_size", C.c_int32), ("win_length", C.c_int32), ("num_mels", C.c_int32),
                 ("fmin", C.c_float), ("fmax", C.c_float), ("eps", C.c_float)]
@@ -127,6 +133,8 @@ SIGNATURES = {
     "fse_wgrad_workspace_bytes": (C.c_int64, [C.c_int32] * 6),
     "fse_wgrad": (C.c_int, [C.c_int32, _P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,
                             _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
+    "fse_wgrad_group_workspace_bytes": (C.c_int64, [C.c_int32, C.POINTER(WgradProblem), C.c_int32, C.c_int32, C.c_int32]),
+    "fse_wgrad_group": (C.c_int, [C.c_int32, C.POINTER(WgradProblem), C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "fse_mel_loss_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "fse_mel_loss_forward": (C.c_int, [_P, _P, C.c_float, C.c_float, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P]),
     "fse_mel_loss_backward": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P]),

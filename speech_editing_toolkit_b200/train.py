@@ -127,19 +127,29 @@ class WeightGradGemm:
 
     def __call__(self, P: torch.Tensor, Q: torch.Tensor, out: torch.Tensor, offs=(0,)):
         """P [B, T, M] and Q [B, T, N]: views with unit channel stride and a common (B, T) grid; out fp32 [M, N] or [M, N, taps] (any strides)."""
-        B, T, M = P.shape
-        N = Q.shape[2]
-        assert Q.shape[:2] == (B, T) and P.stride(2) == 1 and Q.stride(2) == 1
-        assert B == 1 or (P.stride(0) == T * P.stride(1) and Q.stride(0) == T * Q.stride(1)), "utterances must follow each other at the row pitch"
-        taps = len(offs)
-        assert out.dtype == torch.float32 and tuple(out.shape[:2]) == (M, N) and (out.dim() == 2 or out.shape[2] == taps)
+        return self.group([(P, Q, out, offs)])[0]
+
+    def group(self, problems):
+        """Up to 4 GEMMs (P, Q, out, offs) over the same (B, T) grid in one launch (fse_wgrad_group); returns the outputs."""
+        B, T = problems[0][0].shape[:2]
+        arr = (_lib.WgradProblem * len(problems))()
+        keep = []
+        for i, (P, Q, out, offs) in enumerate(problems):
+            M, N, taps = P.shape[2], Q.shape[2], len(offs)
+            assert tuple(P.shape[:2]) == (B, T) and tuple(Q.shape[:2]) == (B, T) and P.stride(2) == 1 and Q.stride(2) == 1
+            assert B == 1 or (P.stride(0) == T * P.stride(1) and Q.stride(0) == T * Q.stride(1)), "utterances must follow each other at the row pitch"
+            assert out.dtype == torch.float32 and tuple(out.shape[:2]) == (M, N) and (out.dim() == 2 or out.shape[2] == taps)
+            o = (C.c_int32 * taps)(*[int(v) for v in offs])
+            keep.append(o)
+            a = arr[i]
+            a.P, a.ldp, a.Q, a.ldq, a.M, a.N = P.data_ptr(), P.stride(1), Q.data_ptr(), Q.stride(1), M, N
+            a.offs, a.ntaps, a.out = C.cast(o, C.POINTER(C.c_int32)), taps, out.data_ptr()
+            a.ld_m, a.ld_n, a.ld_j = out.stride(0), out.stride(1), out.stride(2) if out.dim() == 3 else 0
         lib = _lib.lib()
-        nbytes = lib.fse_wgrad_workspace_bytes(self.mode, B, T, M, N, taps)
-        ws = self._workspace(nbytes, P.device)
-        arr = (C.c_int32 * taps)(*[int(o) for o in offs])
-        check(lib.fse_wgrad(self.mode, _ptr(P), P.stride(1), _ptr(Q), Q.stride(1), B, T, M, N, arr, taps, _ptr(out), out.stride(0), out.stride(1),
-                            out.stride(2) if out.dim() == 3 else 0, _ptr(ws), ws.numel(), _stream()))
-        return out
+        nbytes = lib.fse_wgrad_group_workspace_bytes(self.mode, arr, len(problems), B, T)
+        ws = self._workspace(nbytes, problems[0][0].device)
+        check(lib.fse_wgrad_group(self.mode, arr, len(problems), B, T, _ptr(ws), ws.numel(), _stream()))
+        return [pr[2] for pr in problems]
 
 
 def param_names(layers: int) -> List[str]:
@@ -221,8 +231,14 @@ class DiffNetFunction(torch.autograd.Function):
             gw = torch.empty(2 * Cc, Cc, 3, dtype=f32, device=dx0.device)
             # y[t] += W_j hin[t + off], off = (j - 1) dil.  The shifted taps are GEMMs over the flat row sequence shifted by `dil` rows
             # (no copies), minus the (B - 1) dil row pairs that straddle two utterances.
-            if native:                                                                   # the three taps as one launch: Q rows shifted by TMA
-                wg(dy3, hin, gw, offs=(-dil, 0, dil))
+            gop = torch.empty(2 * Cc, Cc, dtype=f32, device=dx0.device)                  # gradient of o = [res | skip] against u_l
+            if native:
+                # the four weight gradients of the layer as ONE launch: the three conv taps are Q rows shifted by TMA (zero fill per
+                # utterance = the conv's padding), the strided dy view is a tensor map with a wider pitch
+                gcond = torch.empty(2 * Cc, cond2d.shape[1], dtype=f32, device=dx0.device)
+                u3 = v["u"][l].view(B, T, Cc)
+                wg.group([(dy3, hin, gw, (-dil, 0, dil)), (dy3, v["cond"].view(B, T, -1), gcond, (0,)),
+                          (v["dres"][l].view(B, T, Cc), u3, gop[:Cc], (0,)), (dS.view(B, T, Cc), u3, gop[Cc:], (0,))])
             else:
                 gw[:, :, 1] = mm(dy, hin2d)
                 gw[:, :, 0] = mm(dy[dil:], hin2d[:N - dil])
@@ -230,12 +246,12 @@ class DiffNetFunction(torch.autograd.Function):
                 if B > 1:
                     gw[:, :, 0] -= mm(dy3[1:, :dil].reshape(-1, 2 * Cc), hin[:-1, T - dil:].reshape(-1, Cc))
                     gw[:, :, 2] -= mm(dy3[:-1, T - dil:].reshape(-1, 2 * Cc), hin[1:, :dil].reshape(-1, Cc))
+                gcond = gcond_all[l * 2 * Cc:(l + 1) * 2 * Cc]
+                gop[:Cc] = mm(v["dres"][l], v["u"][l])
+                gop[Cc:] = mm(dS, v["u"][l])
             gb = dysum_all[:, l].sum(0)
-            gop = torch.empty(2 * Cc, Cc, dtype=f32, device=dx0.device)                  # gradient of o = [res | skip] against u_l
-            gop[:Cc] = mm(v["dres"][l], v["u"][l])
-            gop[Cc:] = mm(dS, v["u"][l])
             g = {p + "dilated_conv.weight": gw, p + "dilated_conv.bias": gb,
-                 p + "conditioner_projection.weight": (mm(dy, cond2d) if native else gcond_all[l * 2 * Cc:(l + 1) * 2 * Cc])[:, :, None],
+                 p + "conditioner_projection.weight": gcond[:, :, None],
                  p + "conditioner_projection.bias": gb,
                  p + "output_projection.weight": gop[:, :, None], p + "output_projection.bias": torch.cat([dres_sum[l], dS_sum])}
             grads.update(g)

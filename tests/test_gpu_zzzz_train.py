@@ -273,4 +273,14 @@ def test_weight_gradient_gemm_vs_float64(lib_built, mode):
     buf = torch.zeros(512, 256 * 3 + 5, device="cuda")
     wg(P, Q, buf[:, :768].view(512, 256, 3), (-1, 0, 1))
     assert float((buf[:, :768].view(512, 256, 3).double() - ref(P, Q, (-1, 0, 1))).abs().max()) < 2e-5 * float(ref(P, Q, (-1, 0, 1)).abs().max()) and float(buf[:, 768:].abs().max()) == 0.0
-    print(f"[margin] fse_wgrad {mode}: worst error {worst:.2e} of the largest element over {len(cases)} shapes, bit-identical repeats")
+    # four GEMMs over one (B, T) grid in one launch (the weight gradients of a residual layer) = the same four launched alone, bit for bit
+    Bq, Tq = 4, 300
+    dy, hin, cnd, dres, dSk, u = operand(Bq, Tq, 512), operand(Bq, Tq, 256), operand(Bq, Tq, 192), operand(Bq, Tq, 256), operand(Bq, Tq, 256), operand(Bq, Tq, 256)
+    probs = [(dy, hin, (-1, 0, 1), (512, 256, 3)), (dy, cnd, (0,), (512, 192)), (dres, u, (0,), (256, 256)), (dSk, u, (0,), (256, 256))]
+    alone = [wg(P, Q, torch.empty(*shape, device="cuda"), offs) for P, Q, offs, shape in probs]
+    together = wg.group([(P, Q, torch.empty(*shape, device="cuda"), offs) for P, Q, offs, shape in probs])
+    for a, b, (P, Q, offs, shape) in zip(alone, together, probs):
+        want = ref(P, Q, offs).reshape(shape)
+        assert float((b.double() - want).abs().max() / want.abs().max()) < 5e-5
+        assert float((a.double() - want).abs().max() / want.abs().max()) < 5e-5
+    print(f"[margin] fse_wgrad {mode}: worst error {worst:.2e} of the largest element over {len(cases)} shapes, bit-identical repeats, grouped launch ok")
