@@ -66,7 +66,7 @@ def _coerce(old: Any, text: str) -> Any:
 
 
 def apply_overrides(cfg: dict, spec: str) -> dict:
-    """`a=1,b.c=2,d=[1 1 1]` — keys must already exist, dotted keys descend into sub-dicts."""
+    """`a=1,b.c=2,d=[1 1 1]` — keys must already exist (except the drop-in's own `b200_*` switches), dotted keys descend into sub-dicts."""
     if not spec:
         return cfg
     depth, cur, items = 0, "", []
@@ -87,6 +87,15 @@ def apply_overrides(cfg: dict, spec: str) -> dict:
         parts = key.strip().split(".")
         for part in parts[:-1]:
             node = node[part]
+        if parts[-1] not in node and parts[-1].startswith("b200_"):
+            # the drop-in's own switches (b200_mode, b200_vocab, b200_frames, b200_train_steps, ...) are not in the reference's yaml
+            # files: they may be introduced on the command line (any other unknown key is a KeyError, as in the reference)
+            text = value.strip("'\" ")
+            try:
+                node[parts[-1]] = ast.literal_eval(text)
+            except (ValueError, SyntaxError):
+                node[parts[-1]] = text
+            continue
         node[parts[-1]] = _coerce(node[parts[-1]], value)
     return cfg
 

@@ -217,6 +217,47 @@ class SpeechDenoiserTaskB200:
         losses["batch_size"] = sample["txt_tokens"].shape[0]
         return total, losses
 
+    def train_synthetic(self, steps: int):
+        """`-hp b200_train_steps=N` (needs `b200_vocab` for the native condition encoder): N optimizer steps of the training step over one
+        seeded synthetic batch — `_training_step` (model call + native mel losses), backward through the native DiffNet chain, the optimizer
+        the reference builds (AdamW, lr / betas / weight_decay of the yaml; tasks/tts/speech_base.py:110-118), gradients all-reduced over
+        the process group when one is initialised.  A smoke run of the training leg, not the reference's Trainer (no dataset, no
+        checkpoints, no validation)."""
+        import time
+        from . import train
+        hp = self.hparams
+        assert self.model.fs is not None, "training from sample dicts needs the condition encoder: pass -hp b200_vocab=<phone vocabulary size>"
+        if not (hp.get("work_dir") and os.path.isdir(hp["work_dir"])):
+            vocab = int(hp["b200_vocab"])
+            self.model.fs.load_state_dict({k: torch.from_numpy(v) for k, v in synth.fastspeech_state_dict(hp.get("seed", 1234), vocab).items()}, strict=False)
+            self.model.mel_encoder.load_state_dict({k: torch.from_numpy(v) for k, v in synth.mel_encoder_state_dict(hp.get("seed", 1234)).items()})
+        self.model.train()
+        B, T = int(hp.get("max_sentences", 16)), int(hp.get("b200_frames", 1024))
+        b = synth.synthetic_edit_batch(hp.get("seed", 1234), B, T, hp["audio_num_mel_bins"], vocab=int(hp.get("b200_vocab", 80)))
+        sample = {k: torch.from_numpy(v).cuda() for k, v in b.items()}
+        sample["mels"] = sample.pop("ref_mels")
+        params = [p for p in self.model.denoise_fn.parameters() if p.requires_grad]
+        opt = torch.optim.AdamW(params, lr=float(hp.get("lr", 2e-4)), betas=(float(hp.get("optimizer_adam_beta1", 0.9)), float(hp.get("optimizer_adam_beta2", 0.98))),
+                                weight_decay=float(hp.get("weight_decay", 0.0)))
+        red = train.BucketedAllReduce(dict(self.model.denoise_fn.named_parameters()))
+        log = []
+        t0 = None
+        for i in range(steps + 1):
+            if i == 1:                                               # the first step pays the one-time allocations
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+            total, losses = self._training_step(sample, i)
+            opt.zero_grad(set_to_none=True)
+            total.backward()
+            red.finish() if red.active() else None
+            opt.step()
+            log.append({k: float(v) for k, v in losses.items() if isinstance(v, torch.Tensor)})
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / max(steps, 1)
+        print(f"| B200 spec_denoiser training: {steps} steps of {B}x{T} frames, {dt * 1e3:.1f} ms / step ({B * T / dt:.0f} mel-frames/s); "
+              f"losses {log[0]} -> {log[-1]}")
+        return log
+
     @torch.no_grad()
     def test_step(self, sample: dict, batch_idx: int = 0):
         """speech_editing_base.py:151-192 minus file output: sample -> composite -> vocoder."""
@@ -270,6 +311,8 @@ class SpeechDenoiserTaskB200:
         else:
             task.model.denoise_fn.load_state_dict({k: torch.from_numpy(v) for k, v in synth.denoiser_state_dict(
                 hp.get("seed", 1234), hp["audio_num_mel_bins"], hp["hidden_size"], hp["residual_channels"], hp["residual_layers"]).items()})
+        if int(hp.get("b200_train_steps", 0) or 0) > 0:
+            return task.train_synthetic(int(hp["b200_train_steps"]))
         task.build_vocoder()
         if hp.get("b200_test_samples"):
             samples = torch.load(hp["b200_test_samples"], map_location="cpu", weights_only=False)

@@ -146,3 +146,32 @@ def test_batch_sharded_sampling_two_gpus_nccl(lib_built):
     res = [q.get(timeout=600) for _ in ps]
     [p.join(60) for p in ps]
     assert all(ok for _, ok in res)
+
+
+def test_task_start_runs_the_inference_and_the_training_leg_from_the_reference_yaml(lib_built, capsys):
+    """tasks/run.py contract: hparams['task_cls'].start() with the reference's own egs/spec_denoiser.yaml (from the reference copy that travels
+    as oracle/_ref) and -hp overrides: the synthetic inference run, then `b200_train_steps=3` — three optimizer steps through
+    _training_step / the native training chain, with finite, decreasing-or-equal-order losses reported."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import os
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("no reference tree (oracle/_ref) on this box")
+    cfg = os.path.join(refshim.REF_ROOT, "egs", "spec_denoiser.yaml")
+    from speech_editing_toolkit_b200 import plugin
+    from speech_editing_toolkit_b200.hparams import set_hparams
+    cwd = os.getcwd()
+    os.chdir(refshim.REF_ROOT)                                        # base_config paths of the yaml are relative to the reference root
+    try:
+        set_hparams(cfg, hparams_str="task_cls=speech_editing_toolkit_b200.plugin.SpeechDenoiserTaskB200,timesteps=4,max_sentences=2,b200_frames=128,"
+                                     "residual_layers=4,b200_vocab=80", print_hparams=False)
+        out = plugin.SpeechDenoiserTaskB200.start()
+        assert tuple(out["mel_out"].shape) == (2, 128, 80) and tuple(out["wav_out"].shape) == (2, 128 * 256) and bool(torch.isfinite(out["wav_out"]).all())
+        set_hparams(cfg, hparams_str="task_cls=speech_editing_toolkit_b200.plugin.SpeechDenoiserTaskB200,timesteps=100,max_sentences=2,b200_frames=128,"
+                                     "residual_layers=4,b200_vocab=80,b200_train_steps=3,b200_mode=tc_bf16", print_hparams=False)
+        log = plugin.SpeechDenoiserTaskB200.start()
+    finally:
+        os.chdir(cwd)
+    assert len(log) == 4 and all(np.isfinite(list(e.values())).all() for e in log) and set(log[0]) == {"l1_coarse", "ssim_coarse"}
+    print("[margin] task start(): inference leg ok, training leg losses", log[0], "->", log[-1])

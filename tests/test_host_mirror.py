@@ -32,6 +32,11 @@ def test_set_hparams_base_chain_overrides_and_types(tmp_path, monkeypatch):
     assert yaml.safe_load(open("checkpoints/e1/config.yaml"))["a"] == 5
     again = hp_mod.set_hparams("egs/top.yaml", exp_name="e1", print_hparams=False, global_hparams=False)
     assert again["a"] == 5 and again["work_dir"] == "checkpoints/e1"
+    # unknown keys are a KeyError as in the reference (hparams.py:94-105), except the drop-in's own b200_* switches
+    with pytest.raises(KeyError):
+        hp_mod.set_hparams("egs/top.yaml", hparams_str="nope=1", print_hparams=False, global_hparams=False)
+    new = hp_mod.set_hparams("egs/top.yaml", hparams_str="b200_frames=128,b200_mode=tc_bf16", print_hparams=False, global_hparams=False)
+    assert new["b200_frames"] == 128 and new["b200_mode"] == "tc_bf16"
 
 
 @needs_ref
