@@ -87,3 +87,42 @@ def test_text_batch_sharding_world2_gloo(n):
         p.join(60)
     assert sorted(r[0] for r in res) == [0, 1]
     assert all(r[1] for r in res) and all(r[2] == (n, 16, 4) for r in res)
+
+
+def _allreduce_worker(rank, world, port, q):
+    """train.BucketedAllReduce (the DDP plumbing of the training step, utils/commons/trainer.py:475-479): gradient groups handed over by
+    the backward's hook are all-reduced asynchronously, what the hook never saw is reduced in finish(); every .grad ends as the mean."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from speech_editing_toolkit_b200 import train
+        torch.manual_seed(0)
+        params = {f"p{i}": torch.nn.Parameter(torch.zeros(3 + i, 2)) for i in range(5)}
+        local = {k: torch.full_like(p, float(rank + 1)) * (i + 1) for i, (k, p) in enumerate(params.items())}
+        for k, p in params.items():
+            p.grad = local[k].clone()
+        red = train.BucketedAllReduce(params)
+        assert red.active()
+        red({"p0": params["p0"].grad, "p1": params["p1"].grad})          # two hook calls (two "layers"), p3 / p4 never pass the hook
+        red({"p2": params["p2"].grad})
+        red.finish()
+        mean = (1 + world) / 2.0
+        ok = all(torch.allclose(p.grad, torch.full_like(p, mean * (i + 1))) for i, (k, p) in enumerate(params.items()))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_world2_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(r[0] for r in res) == [0, 1] and all(r[1] for r in res)
