@@ -278,8 +278,8 @@ int fse_mel_loss_forward(const float* mel_out, const float* target, float lambda
 
 int fse_mel_loss_backward(const float* mel_out, const float* target, const float* dlosses, float lambda_l1, float lambda_ssim, float* grad, int32_t B, int32_t T,
                           int32_t n_mels, void* workspace, int64_t workspace_bytes, void* stream) {
-  FSE_TRY(check_args(mel_out, target, grad, B, T, n_mels, workspace, workspace_bytes));
   if (!dlosses) return fail(FSE_EINVAL, "null argument");
+  FSE_TRY(check_args(mel_out, target, grad, B, T, n_mels, workspace, workspace_bytes));
   const Layout L = layout(B, T, n_mels);
   auto st = static_cast<cudaStream_t>(stream);
   char* ws = static_cast<char*>(workspace);

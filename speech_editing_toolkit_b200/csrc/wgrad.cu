@@ -363,6 +363,16 @@ int fse_wgrad_group(int32_t mode, const fse_wgrad_problem* problems, int32_t n, 
   if (B <= 0 || T <= 0) return fail(FSE_EINVAL, "B and T must be positive");
   if (mode != FSE_MODE_TC_BF16 && mode != FSE_MODE_TC_TF32) return fail(FSE_EINVAL, "fse_wgrad runs in the tensor-core modes (FSE_MODE_TC_BF16 / FSE_MODE_TC_TF32)");
   if (reinterpret_cast<uintptr_t>(workspace) % 16) return fail(FSE_EINVAL, "the workspace must be 16-byte aligned");
+  if (n < 1 || n > kWgMaxProblems) return fail(FSE_EINVAL, "1 <= number of GEMMs per launch <= %d", kWgMaxProblems);
+  const int es = mode == FSE_MODE_TC_BF16 ? 2 : 4;
+  for (int g = 0; g < n; ++g) {                          // every argument error is reported before the device is touched
+    const fse_wgrad_problem& q = problems[g];
+    if (!q.P || !q.Q || !q.out) return fail(FSE_EINVAL, "null argument (GEMM %d)", g);
+    if (q.M <= 0 || q.N <= 0 || q.ntaps <= 0 || q.ntaps > kWgMaxTaps) return fail(FSE_EINVAL, "M, N must be positive and 1 <= ntaps <= %d (GEMM %d)", kWgMaxTaps, g);
+    if (q.ldp < q.M || q.ldq < q.N) return fail(FSE_EINVAL, "row pitch smaller than the number of columns (GEMM %d)", g);
+    if ((q.ldp * es) % 16 || (q.ldq * es) % 16 || reinterpret_cast<uintptr_t>(q.P) % 16 || reinterpret_cast<uintptr_t>(q.Q) % 16)
+      return fail(FSE_EINVAL, "operands and their row pitch (bytes) must be 16-byte aligned (GEMM %d)", g);
+  }
   auto st = static_cast<cudaStream_t>(stream);
   if (mode == FSE_MODE_TC_BF16) return launch_wgrad<__nv_bfloat16>(problems, n, B, T, workspace, workspace_bytes, st);
   return launch_wgrad<float>(problems, n, B, T, workspace, workspace_bytes, st);

@@ -175,3 +175,35 @@ def test_mel_frontend_config_validation_without_device(lib_built):
     assert L.fse_mel_frontend_frames(None, 100) == 0 and L.fse_mel_frontend_workspace_bytes(None, 1, 256) == 0
     if not torch.cuda.is_available():
         assert L.fse_mel_frontend_create(C.byref(cfg()), C.byref(C.c_void_p())) == -2
+
+
+def test_training_entry_points_validate_arguments_without_device(lib_built):
+    """fse_wgrad / fse_wgrad_group / fse_mel_loss_* report argument errors before any device call; with valid arguments and no GPU they
+    fail loudly (no CPU fallback)."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from speech_editing_toolkit_b200 import _lib
+    L = _lib.lib()
+    buf = np.zeros(4096, dtype=np.float32)
+    base = (buf.ctypes.data + 15) // 16 * 16
+    P = lambda off=0: C.c_void_p(base + off)
+    TC_BF16 = _lib.MODES["tc_bf16"]
+    offs = (C.c_int32 * 1)(0)
+    args = lambda **kw: dict(dict(mode=TC_BF16, P=P(), ldp=64, Q=P(), ldq=64, B=1, T=8, M=64, N=64, offs=offs, ntaps=1, out=P(), ws=P()), **kw)
+
+    def call(a):
+        return L.fse_wgrad(a["mode"], a["P"], a["ldp"], a["Q"], a["ldq"], a["B"], a["T"], a["M"], a["N"], a["offs"], a["ntaps"], a["out"], 64, 1, 0, a["ws"], 1 << 20, None)
+    for bad, word in ((dict(P=None), b"null"), (dict(mode=_lib.MODES["simt_f32"]), b"tensor-core"), (dict(T=0), b"positive"), (dict(ntaps=17), b"ntaps"),
+                      (dict(ldp=32), b"pitch"), (dict(ldq=65), b"aligned"), (dict(P=P(2)), b"aligned")):
+        assert call(args(**bad)) == -1, bad
+        assert word in L.fse_last_error(), (bad, L.fse_last_error())
+    assert L.fse_wgrad_group(TC_BF16, None, 1, 1, 8, P(), 16, None) == -1
+    assert L.fse_wgrad_group(TC_BF16, (_lib.WgradProblem * 5)(), 5, 1, 8, P(), 16, None) == -1 and b"per launch" in L.fse_last_error()
+    assert L.fse_mel_loss_forward(None, P(), 0.5, 0.5, P(), 1, 1, 8, 80, P(), 1 << 20, None) == -1
+    assert L.fse_mel_loss_forward(P(), P(), 0.5, 0.5, P(), 1, 1, 8, 200, P(), 1 << 20, None) == -1 and b"n_mels" in L.fse_last_error()
+    assert L.fse_mel_loss_forward(P(), P(), 0.5, 0.5, P(), 1, 1, 8, 80, P(), 16, None) == -1 and b"workspace" in L.fse_last_error()
+    assert L.fse_mel_loss_backward(P(), P(), None, 0.5, 0.5, P(), 1, 8, 80, P(), 1 << 20, None) == -1
+    assert L.fse_mel_loss_workspace_bytes(0, 8, 80) == 0 and L.fse_mel_loss_workspace_bytes(2, 100, 80) > 3 * 2 * 100 * 80 * 4
+    if not torch.cuda.is_available():
+        assert call(args()) == -2 and L.fse_mel_loss_forward(P(), P(), 0.5, 0.5, P(), 1, 1, 8, 80, P(), 1 << 20, None) == -2

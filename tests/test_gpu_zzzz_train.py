@@ -284,3 +284,40 @@ def test_weight_gradient_gemm_vs_float64(lib_built, mode):
         assert float((b.double() - want).abs().max() / want.abs().max()) < 5e-5
         assert float((a.double() - want).abs().max() / want.abs().max()) < 5e-5
     print(f"[margin] fse_wgrad {mode}: worst error {worst:.2e} of the largest element over {len(cases)} shapes, bit-identical repeats, grouped launch ok")
+
+
+def test_training_kernels_edge_shapes(lib_built):
+    """Edge cases of the two training kernels: images shorter than the SSIM window, a single utterance, no speech frame at all (the
+    reference divides 0 by 0 there: NaN, reproduced), one-frame and sub-chunk GEMMs, 16-column operands."""
+    _need_gpu()
+    from oracle.train_oracle import mel_losses_torch
+    from speech_editing_toolkit_b200 import train
+    gen = torch.Generator().manual_seed(9)
+    for B, T in ((1, 1), (1, 5), (2, 11), (3, 17)):
+        tgt = (torch.randn(B, T, 80, generator=gen) * 1.5 - 3).cuda()
+        out = (tgt + 0.3 * torch.randn(B, T, 80, generator=gen).cuda()).requires_grad_(True)
+        got = train.mel_losses(out, tgt)
+        (got["l1"] + got["ssim"]).backward()
+        o64 = out.detach().double().requires_grad_(True)
+        want = mel_losses_torch(o64, tgt.double())
+        (want["l1"] + want["ssim"]).backward()
+        assert abs(got["l1"].item() - want["l1"].item()) < 2e-6 and abs(got["ssim"].item() - want["ssim"].item()) < 2e-6, (B, T)
+        assert rel_l2(out.grad.cpu().numpy(), o64.grad.cpu().numpy()) < 1e-4, (B, T)
+    z = torch.zeros(1, 20, 80, device="cuda")
+    nan = train.mel_losses(z.clone().requires_grad_(True), z)
+    assert torch.isnan(nan["l1"]) and torch.isnan(nan["ssim"])                 # weights.sum() == 0: 0 / 0, as the reference
+    for mode in ("tc_bf16", "tc_tf32"):
+        wg = train.WeightGradGemm(mode)
+        dt = torch.bfloat16 if mode == "tc_bf16" else torch.float32
+        for B, T, M, N, offs in ((1, 1, 128, 64, (0,)), (2, 3, 16, 16, (-1, 0, 1)), (1, 40, 256, 512, (0,)), (5, 9, 64, 32, (-2, 2))):
+            P = torch.randn(B, T, M, generator=gen).to(dt).cuda()
+            Q = torch.randn(B, T, N, generator=gen).to(dt).cuda()
+            if mode == "tc_tf32":
+                P, Q = [(x.view(torch.int32) & ~0x1FFF).view(torch.float32) for x in (P, Q)]
+            got = wg(P, Q, torch.full((M, N, len(offs)), float("nan"), device="cuda"), offs)
+            want = torch.zeros(M, N, len(offs), dtype=torch.float64, device="cuda")
+            for j, off in enumerate(offs):
+                lo, hi = max(0, -off), min(T, T - off)
+                if hi > lo:
+                    want[:, :, j] = torch.einsum("btm,btn->mn", P.double()[:, lo:hi], Q.double()[:, lo + off:hi + off])
+            assert float((got.double() - want).abs().max()) <= 5e-5 * max(float(want.abs().max()), 1.0), (mode, B, T, M, N, offs)
