@@ -39,6 +39,25 @@ __device__ __forceinline__ void st_operand(float* p, const float* v, bool rnd) {
 template <int NV>
 __device__ __forceinline__ void st_operand(__nv_bfloat16* p, const float* v, bool) { st_vec<NV>(p, v); }
 
+// NV consecutive operand-type values -> fp32 (vector loads: NV is a multiple of 4)
+template <int NV>
+__device__ __forceinline__ void ld_operand(const float* p, float* out) {
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) {
+    const float4 v = reinterpret_cast<const float4*>(p)[i];
+    out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
+  }
+}
+template <int NV>
+__device__ __forceinline__ void ld_operand(const __nv_bfloat16* p, float* out) {
+#pragma unroll
+  for (int i = 0; i < NV / 4; ++i) {
+    const uint2 w = reinterpret_cast<const uint2*>(p)[i];
+    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&w.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&w.y);
+    out[4 * i] = __low2float(lo); out[4 * i + 1] = __high2float(lo); out[4 * i + 2] = __low2float(hi); out[4 * i + 3] = __high2float(hi);
+  }
+}
+
 // ------------------------------------------------------------------ epilogues
 template <typename TOp>
 struct EpiStoreF32 {                       // out = acc + bias (fp32 rows)
@@ -133,7 +152,13 @@ struct EpiScaleCast {                      // out = op(acc * scale)
 // the two factors were formed in fp32 by gate_fwd_kernel)
 template <typename TOp>
 struct EpiGateBwd {
+  // The two derivative factors are "late" operands (kLate = 2 per column): the epilogue issues the loads of a whole chunk (8 x 4 frames)
+  // together, as 8-byte vectors, before the chunk's first store (inside apply() they were 2-byte scalar loads, 4x the L1 sectors, that
+  // cannot move above the previous iteration's stores).  Measured: no change in the launch time (72 us in the step, 55 us under ncu for
+  // 15 us of traffic; profiles/r02l_ncu_train_backward_kernels.md): 61 % of the stall samples are the epilogue warps waiting for exactly
+  // these loads either way, and prefetching them a chunk ahead (kAux = 2) was slower - the cause is not found; open.
   static constexpr int kAux = 0;
+  static constexpr int kLate = 2;
   static constexpr bool kTransposed = true;
   const TOp* sg;        // [B*T, C] du/dg of this layer
   const TOp* tf;        // [B*T, C] du/df
@@ -141,13 +166,19 @@ struct EpiGateBwd {
   int C, T, ld, col0;
   bool rnd;
   template <int NV>
-  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float*) const {
+  __device__ __forceinline__ void load_late(int b, int t, int n0, float* dst) const {
+    const size_t o = (static_cast<size_t>(b) * T + t) * C + n0;
+    ld_operand<NV>(sg + o, dst);
+    ld_operand<NV>(tf + o, dst + NV);
+  }
+  template <int NV>
+  __device__ __forceinline__ void apply(int b, int t, int n0, const float* acc, const float* aux) const {
     const size_t row = static_cast<size_t>(b) * T + t;
     float dg[NV], df[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      dg[i] = acc[i] * to_f32(sg[row * C + n0 + i]);
-      df[i] = acc[i] * to_f32(tf[row * C + n0 + i]);
+      dg[i] = acc[i] * aux[i];
+      df[i] = acc[i] * aux[NV + i];
     }
     st_operand<NV>(dy + row * ld + col0 + n0, dg, rnd);
     st_operand<NV>(dy + row * ld + col0 + C + n0, df, rnd);
