@@ -228,9 +228,7 @@ class DiffNetFunction(torch.autograd.Function):
             dy3 = dy_all[:, :, l * 2 * Cc:(l + 1) * 2 * Cc]
             hin = v["hin"][l]                                                            # [B, T, C]
             hin2d = hin.reshape(N, Cc)
-            gw = torch.empty(2 * Cc, Cc, 3, dtype=f32, device=dx0.device)
-            # y[t] += W_j hin[t + off], off = (j - 1) dil.  The shifted taps are GEMMs over the flat row sequence shifted by `dil` rows
-            # (no copies), minus the (B - 1) dil row pairs that straddle two utterances.
+            gw = torch.empty(2 * Cc, Cc, 3, dtype=f32, device=dx0.device)                # y[t] += W_j hin[t + off], off = (j - 1) dil
             gop = torch.empty(2 * Cc, Cc, dtype=f32, device=dx0.device)                  # gradient of o = [res | skip] against u_l
             if native:
                 # the four weight gradients of the layer as ONE launch: the three conv taps are Q rows shifted by TMA (zero fill per
@@ -240,6 +238,8 @@ class DiffNetFunction(torch.autograd.Function):
                 wg.group([(dy3, hin, gw, (-dil, 0, dil)), (dy3, v["cond"].view(B, T, -1), gcond, (0,)),
                           (v["dres"][l].view(B, T, Cc), u3, gop[:Cc], (0,)), (dS.view(B, T, Cc), u3, gop[Cc:], (0,))])
             else:
+                # library GEMMs: the shifted taps over the flat row sequence shifted by `dil` rows (no copies), minus the (B - 1) dil row
+                # pairs that straddle two utterances
                 gw[:, :, 1] = mm(dy, hin2d)
                 gw[:, :, 0] = mm(dy[dil:], hin2d[:N - dil])
                 gw[:, :, 2] = mm(dy[:N - dil], hin2d[dil:])
