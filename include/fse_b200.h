@@ -14,6 +14,10 @@
  *   - all device work is enqueued on the passed cudaStream_t (as void*); no host synchronisation inside,
  *     except in the fse_*_host convenience calls which take HOST buffers and synchronise before returning.
  *   - one handle per device; not thread-safe per handle; re-entrant across handles.
+ *   - the persistent denoiser kernels (fse_denoise_step / fse_sample in the tensor-core modes) have CTAs that wait for each other
+ *     through flags in global memory: their grid is sized to be fully resident on an otherwise idle device (occupancy query per
+ *     handle), so do not run two of them, or one of them next to another kernel that pins SMs for long, concurrently on one device
+ *     (separate streams of one process, MPS): a partially resident grid would spin until its bounded wait traps.
  *   - there is NO CPU fallback: every compute call fails with FSE_ECUDA when no sm_100 device is usable.
  */
 #ifndef FSE_B200_H
