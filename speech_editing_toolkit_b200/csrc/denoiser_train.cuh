@@ -39,20 +39,21 @@ __device__ __forceinline__ void st_operand(float* p, const float* v, bool rnd) {
 template <int NV>
 __device__ __forceinline__ void st_operand(__nv_bfloat16* p, const float* v, bool) { st_vec<NV>(p, v); }
 
-// NV consecutive operand-type values -> fp32 (vector loads: NV is a multiple of 4)
+// NV consecutive operand-type values -> fp32 (vector loads: NV is a multiple of 4).  The loads carry the L2::256B prefetch hint: an
+// epilogue chunk touches only 64 (bf16) or 128 (fp32) bytes of a frame's row, the neighbouring pieces of the row are read by later
+// chunks - fetched piecewise from DRAM, every piece re-opens the DRAM page (measured: 1.35 TB/s for the whole launch).
 template <int NV>
 __device__ __forceinline__ void ld_operand(const float* p, float* out) {
 #pragma unroll
-  for (int i = 0; i < NV / 4; ++i) {
-    const float4 v = reinterpret_cast<const float4*>(p)[i];
-    out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
-  }
+  for (int i = 0; i < NV / 4; ++i)
+    asm volatile("ld.global.L2::256B.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(out[4 * i]), "=f"(out[4 * i + 1]), "=f"(out[4 * i + 2]), "=f"(out[4 * i + 3]) : "l"(p + 4 * i));
 }
 template <int NV>
 __device__ __forceinline__ void ld_operand(const __nv_bfloat16* p, float* out) {
 #pragma unroll
   for (int i = 0; i < NV / 4; ++i) {
-    const uint2 w = reinterpret_cast<const uint2*>(p)[i];
+    uint2 w;
+    asm volatile("ld.global.L2::256B.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(p + 4 * i));
     const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&w.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&w.y);
     out[4 * i] = __low2float(lo); out[4 * i + 1] = __high2float(lo); out[4 * i + 2] = __low2float(hi); out[4 * i + 3] = __high2float(hi);
   }
@@ -153,10 +154,11 @@ struct EpiScaleCast {                      // out = op(acc * scale)
 template <typename TOp>
 struct EpiGateBwd {
   // The two derivative factors are "late" operands (kLate = 2 per column): the epilogue issues the loads of a whole chunk (8 x 4 frames)
-  // together, as 8-byte vectors, before the chunk's first store (inside apply() they were 2-byte scalar loads, 4x the L1 sectors, that
-  // cannot move above the previous iteration's stores).  Measured: no change in the launch time (72 us in the step, 55 us under ncu for
-  // 15 us of traffic; profiles/r02l_ncu_train_backward_kernels.md): 61 % of the stall samples are the epilogue warps waiting for exactly
-  // these loads either way, and prefetching them a chunk ahead (kAux = 2) was slower - the cause is not found; open.
+  // together, as 8-byte vectors with the L2::256B prefetch hint, before the chunk's first store.  ncu (profiles/
+  // r02l_ncu_train_backward_kernels.md): 61 % of the stall samples are the epilogue warps waiting for these loads and the whole launch
+  // moves 1.35 TB/s - every chunk touches 64 bytes of each frame's 512-byte row, piecewise DRAM fetches of rows written 20 layers ago.
+  // Vector loads alone changed nothing (72 us per launch), prefetching a chunk ahead (kAux = 2) was slower (registers), the 256-byte L2
+  // fetch took it to 65 us; a full-row mapping of the epilogue is what would fix it.
   static constexpr int kAux = 0;
   static constexpr int kLate = 2;
   static constexpr bool kTransposed = true;
