@@ -79,3 +79,39 @@ def load_ckpt(cur_model, ckpt_base_dir, model_name="model", force=True, strict=T
                                f"unexpected keys {list(res.unexpected_keys)}")
     print(f"| load '{model_name}' from '{ckpt_path}'." + (f" (rebuilt from `timesteps`, not loaded: {dropped})" if dropped else ""))
     return ckpt_path
+
+
+def save_ckpt(model, work_dir, global_step, optimizer=None, epoch=0, best_val=None, num_ckpt_keep=3, model_name="model"):
+    """Write `<work_dir>/model_ckpt_steps_<global_step>.ckpt` in the layout the reference's Trainer writes and its `load_ckpt` /
+    `restore_weights` / `restore_opt_state` read (utils/commons/trainer.py:431-470): {'state_dict': {model_name: sd}, 'global_step',
+    'epoch', 'checkpoint_callback_best', 'optimizer_states'}; atomically (`.part` then rename, :451-455), then all but the newest
+    `num_ckpt_keep` checkpoints are removed (:436-438).  Returns the path."""
+    os.makedirs(work_dir, exist_ok=True)
+    path = f"{work_dir}/model_ckpt_steps_{int(global_step)}.ckpt"
+    checkpoint = {"epoch": int(epoch), "global_step": int(global_step), "checkpoint_callback_best": best_val,
+                  "optimizer_states": [optimizer.state_dict()] if optimizer is not None else [],
+                  "state_dict": {model_name: {k: v.detach().cpu() for k, v in model.state_dict().items()}}}
+    tmp = path + ".part"
+    torch.save(checkpoint, tmp)
+    os.replace(tmp, path)
+    for old in get_all_ckpts(work_dir)[int(num_ckpt_keep):]:
+        os.remove(old)
+    return path
+
+
+def resume(model, work_dir, optimizer=None, model_name="model", strict=True, drop_keys=()):
+    """The trainer's resume (utils/commons/trainer.py:372-429: restore_weights + restore_opt_state) for one model / one optimizer:
+    loads the newest checkpoint of `work_dir` when there is one and returns its (global_step, epoch), else (0, 0)."""
+    checkpoint, path = get_last_checkpoint(work_dir)
+    if checkpoint is None:
+        return 0, 0
+    load_ckpt(model, path, model_name, force=True, strict=strict, drop_keys=drop_keys)
+    states = checkpoint.get("optimizer_states") or []
+    if optimizer is not None and states:
+        optimizer.load_state_dict(states[0])
+        dev = next(model.parameters()).device
+        for state in optimizer.state.values():              # optimizer state follows the parameters' device (trainer.py:414-421)
+            for k, v in state.items():
+                if isinstance(v, torch.Tensor):
+                    state[k] = v.to(dev) if v.dim() > 0 or k != "step" else v
+    return int(checkpoint.get("global_step", 0)), int(checkpoint.get("epoch", 0))

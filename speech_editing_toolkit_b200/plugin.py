@@ -221,8 +221,9 @@ class SpeechDenoiserTaskB200:
         """`-hp b200_train_steps=N` (needs `b200_vocab` for the native condition encoder): N optimizer steps of the training step over one
         seeded synthetic batch — `_training_step` (model call + native mel losses), backward through the native DiffNet chain, the optimizer
         the reference builds (AdamW, lr / betas / weight_decay of the yaml; tasks/tts/speech_base.py:110-118), gradients all-reduced over
-        the process group when one is initialised.  A smoke run of the training leg, not the reference's Trainer (no dataset, no
-        checkpoints, no validation)."""
+        the process group when one is initialised; with an experiment directory (`--exp_name`) it resumes from / saves a checkpoint in the
+        trainer's layout (ckpt.resume / ckpt.save_ckpt).  A smoke run of the training leg, not the reference's Trainer (no dataset, no
+        validation)."""
         import time
         from . import train
         hp = self.hparams
@@ -240,6 +241,10 @@ class SpeechDenoiserTaskB200:
         opt = torch.optim.AdamW(params, lr=float(hp.get("lr", 2e-4)), betas=(float(hp.get("optimizer_adam_beta1", 0.9)), float(hp.get("optimizer_adam_beta2", 0.98))),
                                 weight_decay=float(hp.get("weight_decay", 0.0)))
         red = train.BucketedAllReduce(dict(self.model.denoise_fn.named_parameters()))
+        step0 = 0
+        if hp.get("work_dir"):                                       # resume as the trainer does (weights, optimizer state, step count)
+            from .ckpt import SCHEDULE_BUFFERS, resume
+            step0, _ = resume(self.model, hp["work_dir"], optimizer=opt, drop_keys=SCHEDULE_BUFFERS)
         log = []
         t0 = None
         for i in range(steps + 1):
@@ -256,6 +261,9 @@ class SpeechDenoiserTaskB200:
         dt = (time.perf_counter() - t0) / max(steps, 1)
         print(f"| B200 spec_denoiser training: {steps} steps of {B}x{T} frames, {dt * 1e3:.1f} ms / step ({B * T / dt:.0f} mel-frames/s); "
               f"losses {log[0]} -> {log[-1]}")
+        if hp.get("work_dir"):                                       # model_ckpt_steps_<N>.ckpt in the trainer's layout (trainer.py:431-470)
+            from .ckpt import save_ckpt
+            save_ckpt(self.model, hp["work_dir"], step0 + steps + 1, optimizer=opt, num_ckpt_keep=int(hp.get("num_ckpt_keep", 3)))
         return log
 
     @torch.no_grad()

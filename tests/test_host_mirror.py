@@ -236,3 +236,40 @@ def test_campnet_task_run_model_composites_like_the_reference():
     out = task.run_model({"txt_tokens": torch.ones(B, 3, dtype=torch.long), "mels": mels, "time_mel_masks": mask})
     assert seen["time_mel_masks"].shape == (B, T, 1) and seen["infer"] is True and seen["stutter_mel_masks"] is None
     assert torch.equal(out["mel_out"][:, 2:4], fine[:, 2:4]) and torch.equal(out["mel_out"][:, :2], mels[:, :2])
+
+
+def test_checkpoint_save_resume_roundtrip_in_the_reference_layout(tmp_path):
+    """save_ckpt / resume (the trainer's dump_checkpoint / restore_weights / restore_opt_state, utils/commons/trainer.py:372-470): file
+    name, keys, atomic write, pruning to num_ckpt_keep, optimizer state; with the reference present its own load_ckpt reads the file."""
+    from speech_editing_toolkit_b200 import ckpt
+    from speech_editing_toolkit_b200.modules import DiffNetB200
+    hp = dict(HP, residual_layers=2)
+    net = DiffNetB200(80, hp)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
+    for p in net.parameters():
+        p.grad = torch.ones_like(p) * 0.01
+    opt.step()
+    for step in (10, 20, 30, 40):
+        path = ckpt.save_ckpt(net, str(tmp_path), step, optimizer=opt, epoch=1, best_val=0.5, num_ckpt_keep=2)
+    assert path.endswith("model_ckpt_steps_40.ckpt") and not os.path.exists(path + ".part")
+    assert [os.path.basename(p) for p in ckpt.get_all_ckpts(str(tmp_path))] == ["model_ckpt_steps_40.ckpt", "model_ckpt_steps_30.ckpt"]
+    blob = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(blob) == {"epoch", "global_step", "checkpoint_callback_best", "optimizer_states", "state_dict"} and set(blob["state_dict"]) == {"model"}
+    fresh = DiffNetB200(80, hp)
+    opt2 = torch.optim.AdamW(fresh.parameters(), lr=1e-3)
+    assert ckpt.resume(fresh, str(tmp_path), optimizer=opt2) == (40, 1)
+    for (k, a), (_, b) in zip(net.state_dict().items(), fresh.state_dict().items()):
+        assert torch.equal(a, b), k
+    s1, s2 = opt.state_dict()["state"], opt2.state_dict()["state"]
+    assert all(torch.equal(s1[i]["exp_avg"], s2[i]["exp_avg"]) for i in s1)
+    assert ckpt.resume(DiffNetB200(80, hp), str(tmp_path / "empty")) == (0, 0)
+    if refshim.available():
+        refshim.install("egs/spec_denoiser.yaml", overrides="residual_layers=2")
+        from utils.commons.hparams import hparams as ref_hparams
+        ref_hparams["residual_layers"] = 2
+        from modules.speech_editing.spec_denoiser.diffnet import DiffNet
+        from utils.commons.ckpt_utils import load_ckpt as ref_load_ckpt
+        ref_net = DiffNet(80)
+        ref_load_ckpt(ref_net, str(tmp_path), "model", strict=True)
+        for k, v in net.state_dict().items():
+            assert torch.equal(v, ref_net.state_dict()[k]), k
