@@ -268,22 +268,34 @@ __global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict
   st_operand<4>(dst + 4 * i, v, rnd);
 }
 
-// dst[r * ldd + col0 + j * cblk + c] = op(src[r * sr + c * sc + j * sj])   (weight repacking on the device, once per optimizer step)
+// dst[r * ldd + col0 + j * cblk + c] = op(src[r * sr + c * sc + j * sj] (+ add[...]))   (weight repacking on the device, once per optimizer step)
+// All repacking jobs of one fse_train_load_weights_device call in ONE launch (125 jobs for 20 layers: as separate launches they cost
+// 0.4 ms of device time and as much host time per optimizer step).  Block b belongs to the job whose block range contains it.
+struct PackJob {
+  void* dst; const float* src; const float* add;       // add: optional second source with the same indexing (summed biases)
+  long ldd, col0, sr, sc, sj, cblk;
+  int R, Cn, J, block0;                 // block0: first block of this job
+};
 template <typename TOp>
-__global__ void __launch_bounds__(256) pack_strided_kernel(TOp* __restrict__ dst, long ldd, long col0, const float* __restrict__ src, int R, int Cn,
-                                                           int J, long sr, long sc, long sj, long cblk, bool tf32) {
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t total = static_cast<size_t>(R) * Cn * J;
+__global__ void __launch_bounds__(256) pack_jobs_kernel(const PackJob* __restrict__ jobs, int njobs, bool tf32) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {                     // last job with block0 <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block0 <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid - 1;
+  }
+  const PackJob jb = jobs[lo];
+  const size_t i = static_cast<size_t>(blockIdx.x - jb.block0) * blockDim.x + threadIdx.x;
+  const size_t total = static_cast<size_t>(jb.R) * jb.Cn * jb.J;
   if (i >= total) return;
-  const int c = static_cast<int>(i % Cn);
-  const int j = static_cast<int>((i / Cn) % J);
-  const int r = static_cast<int>(i / (static_cast<size_t>(Cn) * J));
-  float v = src[r * sr + c * sc + j * sj];
+  const int c = static_cast<int>(i % jb.Cn);
+  const int j = static_cast<int>((i / jb.Cn) % jb.J);
+  const int r = static_cast<int>(i / (static_cast<size_t>(jb.Cn) * jb.J));
+  float v = jb.src[r * jb.sr + c * jb.sc + j * jb.sj];
+  if (jb.add) v += jb.add[r * jb.sr + c * jb.sc + j * jb.sj];
   if (tf32) v = ptx::round_tf32(v);
-  const float one[2] = {v, 0.f};
-  TOp* p = dst + r * ldd + col0 + j * cblk + c;
-  if constexpr (std::is_same<TOp, float>::value) *p = one[0];
-  else *p = __float2bfloat16_rn(one[0]);
+  TOp* p = static_cast<TOp*>(jb.dst) + r * jb.ldd + jb.col0 + j * jb.cblk + c;
+  if constexpr (std::is_same<TOp, float>::value) *p = v;
+  else *p = __float2bfloat16_rn(v);
 }
 
 }  // namespace fse
@@ -293,6 +305,9 @@ using namespace fse;
 // ------------------------------------------------------------------ handle
 struct fse_trainer {
   fse_denoiser_config cfg{};
+  std::vector<PackJob> pack_host, pack_fp32_host;     // repacking jobs of the last load (re-uploaded only when a pointer changed)
+  PackJob* pack_dev = nullptr; PackJob* pack_fp32_dev = nullptr;
+  int pack_blocks = 0, pack_fp32_blocks = 0;
   bool bf16 = true, tc = true;
   int KB = 64;
   bool loaded = false;
@@ -524,9 +539,20 @@ int train_pack(fse_trainer* h, const TensorTable& tt, cudaStream_t st) {
   const bool tf32 = h->cfg.mode == FSE_MODE_TC_TF32;
   int rc = FSE_OK;
   auto G = [&](const std::string& name, int64_t numel) { return rc == FSE_OK ? tt.get(name, numel, &rc) : nullptr; };
-  auto pack = [&](void* dst, long ldd, long col0, const float* src, int R, int Cn, int J, long sr, long sc, long sj, long cblk) {
+  // the repacking jobs are collected and run as ONE launch (plus one for the fp32 bias sums) at the end of this function
+  std::vector<PackJob> jobs, jobs32;
+  int blocks = 0, blocks32 = 0;
+  auto add_job = [](std::vector<PackJob>& v, int& nb, void* dst, long ldd, long col0, const float* src, int R, int Cn, int J, long sr, long sc, long sj, long cblk,
+                    const float* add = nullptr) {
     const size_t total = static_cast<size_t>(R) * Cn * J;
-    pack_strided_kernel<TOp><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(static_cast<TOp*>(dst), ldd, col0, src, R, Cn, J, sr, sc, sj, cblk, tf32);
+    PackJob jb{};                                           // zero-initialised incl. padding: the tables are compared with memcmp
+    jb.dst = dst; jb.src = src; jb.add = add; jb.ldd = ldd; jb.col0 = col0; jb.sr = sr; jb.sc = sc; jb.sj = sj; jb.cblk = cblk;
+    jb.R = R; jb.Cn = Cn; jb.J = J; jb.block0 = nb;
+    v.push_back(jb);
+    nb += static_cast<int>((total + 255) / 256);
+  };
+  auto pack = [&](void* dst, long ldd, long col0, const float* src, int R, int Cn, int J, long sr, long sc, long sj, long cblk) {
+    add_job(jobs, blocks, dst, ldd, col0, src, R, Cn, J, sr, sc, sj, cblk);
   };
   const float* w_in = G("input_projection.weight", (int64_t)C * M);
   h->b_in = G("input_projection.bias", C);
@@ -558,17 +584,28 @@ int train_pack(fse_trainer* h, const TensorTable& tt, cudaStream_t st) {
     pack(static_cast<TOp*>(h->WoT) + static_cast<size_t>(l) * C * 2 * C, 2 * C, 0, wop, C, 2 * C, 1, 1, C, 0, 0);     // dst[c, n] = wop[n, c]
     pack(static_cast<TOp*>(h->WyT) + static_cast<size_t>(l) * C * 6 * C, 6 * C, 0, wdc, C, 2 * C, 3, 3, (long)C * 3, 1, 2 * C);   // dst[c, j*2C + n] = wdc[n, c, j]
     pack(h->WcpT, (long)L * 2 * C, (long)l * 2 * C, wcp, H, 2 * C, 1, 1, H, 0, 0);                                       // dst[h, l*2C + n] = wcp[n, h]
-    // b_y = dilated_conv.bias + conditioner_projection.bias
-    pack_strided_kernel<float><<<(2 * C + 255) / 256, 256, 0, st>>>(h->b_y + static_cast<size_t>(l) * 2 * C, 0, 0, bdc, 1, 2 * C, 1, 0, 1, 0, 0, false);
-    (void)bcp;
+    // b_y = dilated_conv.bias + conditioner_projection.bias (one job with two sources)
+    add_job(jobs32, blocks32, h->b_y + static_cast<size_t>(l) * 2 * C, 0, 0, bdc, 1, 2 * C, 1, 0, 1, 0, 0, bcp);
   }
+  auto same = [](const std::vector<PackJob>& a, const std::vector<PackJob>& b) {
+    return a.size() == b.size() && (a.empty() || std::memcmp(a.data(), b.data(), a.size() * sizeof(PackJob)) == 0);
+  };
+  auto upload = [&](const std::vector<PackJob>& v, std::vector<PackJob>& host, PackJob*& dev) -> int {
+    if (dev && same(v, host)) return FSE_OK;              // same parameter tensors as last step: the table on the device is current
+    if (dev && host.size() != v.size()) { FSE_CUDA(cudaFree(dev)); dev = nullptr; }
+    if (!dev) FSE_CUDA(cudaMalloc(reinterpret_cast<void**>(&dev), v.size() * sizeof(PackJob)));
+    FSE_CUDA(cudaStreamSynchronize(st));                    // a previous launch may still read the old table / the host copy is reused
+    host = v;
+    FSE_CUDA(cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(PackJob), cudaMemcpyHostToDevice, st));
+    return FSE_OK;
+  };
+  FSE_TRY(upload(jobs, h->pack_host, h->pack_dev));
+  FSE_TRY(upload(jobs32, h->pack_fp32_host, h->pack_fp32_dev));
+  h->pack_blocks = blocks; h->pack_fp32_blocks = blocks32;
+  pack_jobs_kernel<TOp><<<blocks, 256, 0, st>>>(h->pack_dev, static_cast<int>(jobs.size()), tf32);
+  pack_jobs_kernel<float><<<blocks32, 256, 0, st>>>(h->pack_fp32_dev, static_cast<int>(jobs32.size()), false);
   FSE_CUDA(cudaGetLastError());
   return FSE_OK;
-}
-
-__global__ void add_vec_kernel(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ b, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = a[i] + b[i];
 }
 
 }  // namespace
@@ -621,6 +658,8 @@ void fse_train_destroy(fse_trainer* h) {
   if (!h) return;
   void* ptrs[] = {h->W_in, h->WoutT, h->W_skip, h->WskipT, h->W_out, h->Wy, h->Wo, h->WoT, h->WyT, h->WcpT, h->b_y};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->pack_dev) cudaFree(h->pack_dev);
+  if (h->pack_fp32_dev) cudaFree(h->pack_fp32_dev);
   delete h;
 }
 
@@ -630,16 +669,6 @@ int fse_train_load_weights_device(fse_trainer* h, const fse_tensor* tensors, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int rc = h->bf16 ? train_pack<__nv_bfloat16>(h, tt, st) : train_pack<float>(h, tt, st);
   if (rc != FSE_OK) return rc;
-  // b_y[l] += conditioner_projection.bias (the pack above copied dilated_conv.bias)
-  const int C = h->cfg.channels;
-  for (int l = 0; l < h->cfg.layers; ++l) {
-    int r2 = FSE_OK;
-    const float* bcp = tt.get("residual_layers." + std::to_string(l) + ".conditioner_projection.bias", 2 * C, &r2);
-    if (r2) return r2;
-    float* by = h->b_y + static_cast<size_t>(l) * 2 * C;
-    add_vec_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(by, by, bcp, 2 * C);
-  }
-  FSE_CUDA(cudaGetLastError());
   h->loaded = true;
   return FSE_OK;
 }
