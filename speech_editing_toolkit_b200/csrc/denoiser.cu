@@ -194,6 +194,13 @@ struct fse_denoiser {
   // fused multi-layer kernel (denoiser_fused.cuh): per-layer weight maps in device memory, grid barrier word
   bool fused = false;
   bool fused_shared_a = true;    // one activation load per channel block + row-shifted tap descriptors (FSE_FUSED_SHARED_A=0: per-tap loads)
+  // FSE_STREAM_PDL=1: the streamed kernel is a programmatic dependent launch (its prologue — barrier init, TMEM allocation, cluster
+  // sync, tensor-map prefetch — overlaps the input projection's tail).  That needs the kernel to follow a KERNEL in the stream, so
+  // the per-launch memset of the publication counters goes away: two counter arrays alternate, launch k uses one and zeroes the
+  // other for launch k+1 (both are zeroed once at the start of every fse_sample / fse_denoise_step call).
+  bool stream_pdl = false;
+  int flag_phase = 0;
+  int l2_hint = 0;           // FSE_STREAM_L2HINT: L2 eviction priorities of the streamed kernel (denoiser_stream.cuh, kL2Hint* bits)
   bool fused_stream = true;  // (layer, unit) items dealt round-robin, neighbour flags instead of the grid barrier (FSE_FUSED_STREAM=0: lock step)
   bool fused_pair = false;   // default when fused: CTA pairs (tcgen05 cta_group::2), each CTA loads half of every weight tile
   CUtensorMap* d_mW1 = nullptr; CUtensorMap* d_mW2f = nullptr; CUtensorMap* d_mW1p = nullptr; CUtensorMap* d_mW2p = nullptr;
@@ -233,7 +240,8 @@ namespace {
 struct Workspace {
   float* h; void* hb; void* hb1; void* u; void* rb; void* xb; void* condb;
   float* xa; float* xbuf2; float* tvals; float* temb; float* d; float* dbias;
-  unsigned int* done;             // [L, tiles] layer-publication counters of the streamed residual-layer kernel
+  unsigned int* done;             // 2 x [L, tiles] layer-publication counters of the streamed residual-layer kernel
+  size_t done_n;                  // counters per array
   size_t bytes;
 };
 
@@ -260,7 +268,8 @@ Workspace carve(const fse_denoiser* h, void* base, int B, int T) {
   o = take(nT * C * 4); w.temb = reinterpret_cast<float*>(p + o);
   o = take(nT * L * C * 4); w.d = reinterpret_cast<float*>(p + o);
   o = take(nT * L * 3 * 2 * C * 4); w.dbias = reinterpret_cast<float*>(p + o);
-  o = take(h->fused ? static_cast<size_t>(L) * B * ((T + kTileM - 1) / kTileM) * 4 : 0); w.done = reinterpret_cast<unsigned int*>(p + o);
+  w.done_n = h->fused ? static_cast<size_t>(L) * B * ((T + kTileM - 1) / kTileM) : 0;
+  o = take(2 * w.done_n * 4); w.done = reinterpret_cast<unsigned int*>(p + o);
   w.bytes = off;
   return w;
 }
@@ -306,6 +315,15 @@ int run_time_tables(fse_denoiser* h, const Workspace& w, int nT, cudaStream_t st
   return FSE_OK;
 }
 
+// FSE_STREAM_PDL: both publication-counter arrays are zeroed once per C-ABI call; the launches then alternate between them.
+int reset_stream_flags(fse_denoiser* h, const Workspace& w, cudaStream_t st) {
+  if (!h->fused || !h->stream_pdl || w.done_n == 0) return FSE_OK;
+  FSE_CUDA(cudaMemsetAsync(w.done, 0, 2 * w.done_n * sizeof(unsigned int), st));
+  ++h->launches;
+  h->flag_phase = 0;
+  return FSE_OK;
+}
+
 // All L residual layers in one persistent launch (denoiser_stream.cuh; the lock-step predecessor denoiser_fused.cuh behind
 // FSE_FUSED_STREAM=0).  The CTAs of these kernels wait for each other (per-unit flags / grid barrier), so the grid is capped by
 // what the driver says can be co-resident; the function attributes and that cap are cached in the handle (one handle = one device).
@@ -319,9 +337,10 @@ int run_fused_layers(fse_denoiser* h, const Workspace& w, int Bc, int b0, int T,
   fp.u_all = static_cast<__nv_bfloat16*>(w.u);
   fp.dbias = w.dbias + static_cast<size_t>(tidx_base) * L * 3 * 2 * C;
   fp.dbias_bstride = static_cast<long long>(tidx_bstride) * L * 3 * 2 * C;
-  fp.b2 = h->b2; fp.grid_bar = h->d_grid_bar; fp.done = w.done; fp.mW1 = h->d_mW1; fp.mW2 = h->d_mW2f;
+  fp.b2 = h->b2; fp.grid_bar = h->d_grid_bar; fp.done = w.done; fp.done_clear = nullptr; fp.done_clear_n = 0; fp.mW1 = h->d_mW1; fp.mW2 = h->d_mW2f;
   fp.mW1p = h->d_mW1p; fp.mW2p = h->d_mW2p;
   fp.dbg = h->dbg_buf;
+  fp.l2_hint = h->l2_hint;
   if (!h->fused_attr_set) {
     FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
     FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
@@ -333,18 +352,28 @@ int run_fused_layers(fse_denoiser* h, const Workspace& w, int Bc, int b0, int T,
   }
   const int tiles = Bc * ((T + kTileM - 1) / kTileM);
   const bool stream = tf32 || (h->fused_stream && h->fused_shared_a);
-  if (stream) FSE_CUDA(cudaMemsetAsync(w.done, 0, static_cast<size_t>(L) * tiles * sizeof(unsigned int), st));
-  else FSE_CUDA(cudaMemsetAsync(h->d_grid_bar, 0, sizeof(unsigned int), st));
-  ++h->launches;
+  const bool pdl = stream && h->fused_pair && h->stream_pdl && !h->prof.on;
+  if (pdl) {
+    fp.done = w.done + static_cast<size_t>(h->flag_phase) * w.done_n;
+    fp.done_clear = w.done + static_cast<size_t>(h->flag_phase ^ 1) * w.done_n;
+    fp.done_clear_n = static_cast<unsigned int>(w.done_n);
+    h->flag_phase ^= 1;
+  } else {
+    if (stream) FSE_CUDA(cudaMemsetAsync(w.done, 0, static_cast<size_t>(L) * tiles * sizeof(unsigned int), st));
+    else FSE_CUDA(cudaMemsetAsync(h->d_grid_bar, 0, sizeof(unsigned int), st));
+    ++h->launches;
+  }
   h->prof.begin(1, st);
   if (h->fused_pair) {
     int grid = (tiles + 1) / 2 * 2;                      // whole clusters of 2
     const size_t smem = tf32 ? kStreamTf32SmemBytes : kFusedSmemBytes;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(h->num_sms / 2 * 2); cfg.blockDim = dim3(stream ? kStreamThreads : kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     // Every cluster of the grid must be resident at once.  A GPC with an odd number of usable SMs leaves one SM without a
     // partner, so ask the driver instead of assuming SMs / 2.
@@ -359,6 +388,7 @@ int run_fused_layers(fse_denoiser* h, const Workspace& w, int Bc, int b0, int T,
     }
     if (grid > 2 * h->max_clusters[which]) grid = 2 * h->max_clusters[which];
     cfg.gridDim = dim3(grid);
+    if (pdl) cfg.numAttrs = 2;
     if (tf32)
       FSE_CUDA(cudaLaunchKernelEx(&cfg, denoiser_stream_kernel<true, true>, h->plan.m_hb0_halo, h->plan.m_hb1_halo, h->plan.m_cond, h->plan.m_u, fp));
     else if (stream)
@@ -489,6 +519,7 @@ int denoise_step_impl(fse_denoiser* h, const float* x_t, const float* cond, cons
                       void* ws, cudaStream_t st) {
   Workspace w = carve(h, ws, B, T);
   FSE_TRY(build_plan(h, w, ws, cond, B, T));
+  FSE_TRY(reset_stream_flags(h, w, st));
   const int M = h->cfg.n_mels;
   tvals_from_i64_kernel<<<(B + 255) / 256, 256, 0, st>>>(reinterpret_cast<const long long*>(t), w.tvals, B);
   FSE_CUDA(cudaGetLastError());
@@ -508,6 +539,7 @@ int sample_impl(fse_denoiser* h, const float* cond, const float* noise, const fl
                 float* mel_out, float* x_trace, int B, int T, void* ws, cudaStream_t st) {
   Workspace w = carve(h, ws, B, T);
   FSE_TRY(build_plan(h, w, ws, cond, B, T));
+  FSE_TRY(reset_stream_flags(h, w, st));
   const int M = h->cfg.n_mels, S = h->S;
   const size_t xsz = static_cast<size_t>(B) * M * T;
   tvals_desc_kernel<<<(S + 255) / 256, 256, 0, st>>>(w.tvals, S);
@@ -609,6 +641,8 @@ int fse_denoiser_create(const fse_denoiser_config* cfg, fse_denoiser** out) {
              cfg->hidden % 64 == 0 && !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 0);
   h->fused_pair = h->fused && (cfg->mode == FSE_MODE_TC_TF32 || !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 1));   // FSE_FUSED=1: single-CTA variant (bf16 only)
   h->fused_stream = !(getenv("FSE_FUSED_STREAM") && atoi(getenv("FSE_FUSED_STREAM")) == 0);
+  if (const char* e = getenv("FSE_STREAM_L2HINT")) h->l2_hint = atoi(e);
+  if (const char* e = getenv("FSE_STREAM_PDL")) h->stream_pdl = atoi(e) != 0;
   h->fused_shared_a = !(getenv("FSE_FUSED_SHARED_A") && atoi(getenv("FSE_FUSED_SHARED_A")) == 0);   // measured: 92.3 vs 95.3 ms/step
   if (const char* e = getenv("FSE_GRAPH")) h->use_graph = atoi(e) != 0;
   if (cudaMalloc(reinterpret_cast<void**>(&h->d_seed), 8) != cudaSuccess) { delete h; return fail(FSE_ECUDA, "cudaMalloc(seed) failed"); }
