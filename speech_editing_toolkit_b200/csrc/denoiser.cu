@@ -194,13 +194,12 @@ struct fse_denoiser {
   // fused multi-layer kernel (denoiser_fused.cuh): per-layer weight maps in device memory, grid barrier word
   bool fused = false;
   bool fused_shared_a = true;    // one activation load per channel block + row-shifted tap descriptors (FSE_FUSED_SHARED_A=0: per-tap loads)
-  // FSE_STREAM_PDL=1: the streamed kernel is a programmatic dependent launch (its prologue — barrier init, TMEM allocation, cluster
+  // The streamed kernel is a programmatic dependent launch (FSE_STREAM_PDL=0 restores the plain launch) (its prologue — barrier init, TMEM allocation, cluster
   // sync, tensor-map prefetch — overlaps the input projection's tail).  That needs the kernel to follow a KERNEL in the stream, so
   // the per-launch memset of the publication counters goes away: two counter arrays alternate, launch k uses one and zeroes the
   // other for launch k+1 (both are zeroed once at the start of every fse_sample / fse_denoise_step call).
-  bool stream_pdl = false;
+  bool stream_pdl = true;
   int flag_phase = 0;
-  int l2_hint = 0;           // FSE_STREAM_L2HINT: L2 eviction priorities of the streamed kernel (denoiser_stream.cuh, kL2Hint* bits)
   bool fused_stream = true;  // (layer, unit) items dealt round-robin, neighbour flags instead of the grid barrier (FSE_FUSED_STREAM=0: lock step)
   bool fused_pair = false;   // default when fused: CTA pairs (tcgen05 cta_group::2), each CTA loads half of every weight tile
   CUtensorMap* d_mW1 = nullptr; CUtensorMap* d_mW2f = nullptr; CUtensorMap* d_mW1p = nullptr; CUtensorMap* d_mW2p = nullptr;
@@ -315,7 +314,7 @@ int run_time_tables(fse_denoiser* h, const Workspace& w, int nT, cudaStream_t st
   return FSE_OK;
 }
 
-// FSE_STREAM_PDL: both publication-counter arrays are zeroed once per C-ABI call; the launches then alternate between them.
+// Programmatic dependent launch of the streamed kernel: both publication-counter arrays are zeroed once per C-ABI call; the launches then alternate between them.
 int reset_stream_flags(fse_denoiser* h, const Workspace& w, cudaStream_t st) {
   if (!h->fused || !h->stream_pdl || w.done_n == 0) return FSE_OK;
   FSE_CUDA(cudaMemsetAsync(w.done, 0, 2 * w.done_n * sizeof(unsigned int), st));
@@ -340,7 +339,6 @@ int run_fused_layers(fse_denoiser* h, const Workspace& w, int Bc, int b0, int T,
   fp.b2 = h->b2; fp.grid_bar = h->d_grid_bar; fp.done = w.done; fp.done_clear = nullptr; fp.done_clear_n = 0; fp.mW1 = h->d_mW1; fp.mW2 = h->d_mW2f;
   fp.mW1p = h->d_mW1p; fp.mW2p = h->d_mW2p;
   fp.dbg = h->dbg_buf;
-  fp.l2_hint = h->l2_hint;
   if (!h->fused_attr_set) {
     FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
     FSE_CUDA(cudaFuncSetAttribute(denoiser_layers_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kFusedSmemBytes)));
@@ -641,7 +639,6 @@ int fse_denoiser_create(const fse_denoiser_config* cfg, fse_denoiser** out) {
              cfg->hidden % 64 == 0 && !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 0);
   h->fused_pair = h->fused && (cfg->mode == FSE_MODE_TC_TF32 || !(getenv("FSE_FUSED") && atoi(getenv("FSE_FUSED")) == 1));   // FSE_FUSED=1: single-CTA variant (bf16 only)
   h->fused_stream = !(getenv("FSE_FUSED_STREAM") && atoi(getenv("FSE_FUSED_STREAM")) == 0);
-  if (const char* e = getenv("FSE_STREAM_L2HINT")) h->l2_hint = atoi(e);
   if (const char* e = getenv("FSE_STREAM_PDL")) h->stream_pdl = atoi(e) != 0;
   h->fused_shared_a = !(getenv("FSE_FUSED_SHARED_A") && atoi(getenv("FSE_FUSED_SHARED_A")) == 0);   // measured: 92.3 vs 95.3 ms/step
   if (const char* e = getenv("FSE_GRAPH")) h->use_graph = atoi(e) != 0;

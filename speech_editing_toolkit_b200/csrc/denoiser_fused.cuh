@@ -38,14 +38,13 @@ struct FusedParams {
   const float* b2;                // [L, 256] residual half of output_projection.bias
   unsigned int* grid_bar;         // zeroed before the launch (lock-step kernel)
   unsigned int* done;             // [L, units] publication counters, zero when the launch starts (denoiser_stream.cuh)
-  unsigned int* done_clear;       // optional: the OTHER counter array, zeroed by this launch for the next one (FSE_STREAM_PDL)
+  unsigned int* done_clear;       // optional: the OTHER counter array, zeroed by this launch for the next one (programmatic dependent launch)
   unsigned int done_clear_n;
   const CUtensorMap* mW1;         // [L] in global memory: [512, 960] gate weights, box 64 x 256
   const CUtensorMap* mW2;         // [L]: [256, 256] residual weights, box 64 x 256
   const CUtensorMap* mW1p;        // [L] same tensors with box 64 x 128 (CTA-pair mode: each CTA loads half of every tile)
   const CUtensorMap* mW2p;        // [L]
   long long* dbg;                 // optional [64] clock64 stamps of CTA 0 in layer 3 (developer aid)
-  int l2_hint;                    // streamed kernel: L2 eviction-priority switches (denoiser_stream.cuh, kL2Hint*)
 };
 
 // fp32 residual stream: read once per layer, never reused from L1

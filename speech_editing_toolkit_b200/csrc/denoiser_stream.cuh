@@ -31,22 +31,6 @@ __device__ __forceinline__ float4 ld_cg_f4(const float* p) {
   return v;
 }
 
-__device__ __forceinline__ float4 ld_cg_f4_l2hint(const float* p, uint64_t policy) {
-  float4 v;
-  asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy) : "memory");
-  return v;
-}
-
-// FusedParams::l2_hint (FSE_STREAM_L2HINT, pair mode): L2 eviction priorities for the launch's three re-used streams.  The residual
-// stream written by layer l is read by layer l+1 one to two item periods later, cond is re-read by every layer, and both are pushed
-// out of the 126 MB L2 by the write-once u_all stream and the weights unless they are marked (ncu: 1.3 GB of DRAM writes + 0.5 GB of
-// reads per launch against 0.67 GB of u_all).
-constexpr int kL2HintHStore = 1;      // epilogue stores of h / hb: evict_last
-constexpr int kL2HintCondLoad = 2;    // TMA loads of cond: evict_last
-constexpr int kL2HintHLoad = 4;       // TMA loads of the hb / hf tiles: evict_last
-constexpr int kL2HintWLoad = 8;       // TMA loads of the weights: evict_last
-constexpr int kL2HintHLastRead = 16;  // the residual epilogue's read of h (its last use): evict_first
-
 __device__ __forceinline__ void stream_wait_done(const unsigned int* flag, unsigned int target) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
@@ -181,8 +165,6 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
     if (lane == 0) {
       int ga = 0, kw = 0, it = 0;
       const int nrow = kPair ? static_cast<int>(rank) * 128 : 0;       // this CTA's half of every weight tile
-      const uint64_t pol_last = ptx::l2_policy_evict_last();
-      const bool hint_w = kPair && (p.l2_hint & kL2HintWLoad), hint_c = kPair && (p.l2_hint & kL2HintCondLoad), hint_h = kPair && (p.l2_hint & kL2HintHLoad);
       for (int g = pair0; g < total_items; g += npairs, ++it) {
         const int l = g / total_units, unit = g - l * total_units;
         const CUtensorMap* mHb = (l & 1) ? &mapHb1 : &mapHb0;
@@ -205,10 +187,8 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
             const int s = kw % WS;
             ptx::mbar_wait(&w_empty[s], ((kw / WS) & 1) ^ 1u);
             if (leader) ptx::mbar_arrive_expect_tx(&w_full[s], static_cast<uint32_t>(WB) * kMul);
-            if constexpr (kPair) {
-              if (hint_w) ptx::tma_load_2d_pair_hint(sW + s * WB, mW2, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * KC, nrow, pol_last);
-              else ptx::tma_load_2d_pair(sW + s * WB, mW2, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * KC, nrow);
-            } else ptx::tma_load_2d(sW + s * WB, mW2, &w_full[s], kb * KC, 0);
+            if constexpr (kPair) ptx::tma_load_2d_pair(sW + s * WB, mW2, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * KC, nrow);
+            else ptx::tma_load_2d(sW + s * WB, mW2, &w_full[s], kb * KC, 0);
           }
         };
         for (int half = 0; half < 2; ++half) {
@@ -223,10 +203,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
             const int tt = is_hb ? t0 - 1 : t0;
             if (leader) ptx::mbar_arrive_expect_tx(&a_full[slot], rows * 128u * kMul);
             if constexpr (kPair) {
-              if (is_hb ? hint_h : hint_c)
-                ptx::tma_load_3d_pair_hint(sA + slot * AB, is_hb ? mHb : &mapCond, ptx::mapa_u32(ptx::smem_u32(&a_full[slot]), 0), c0, tt, b, pol_last);
-              else
-                ptx::tma_load_3d_pair(sA + slot * AB, is_hb ? mHb : &mapCond, ptx::mapa_u32(ptx::smem_u32(&a_full[slot]), 0), c0, tt, b);
+              ptx::tma_load_3d_pair(sA + slot * AB, is_hb ? mHb : &mapCond, ptx::mapa_u32(ptx::smem_u32(&a_full[slot]), 0), c0, tt, b);
             } else {
               ptx::tma_load_3d(sA + slot * AB, is_hb ? mHb : &mapCond, &a_full[slot], c0, tt, b);
             }
@@ -236,10 +213,8 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
               ptx::mbar_wait(&w_empty[s], ((kw / WS) & 1) ^ 1u);
               if (leader) ptx::mbar_arrive_expect_tx(&w_full[s], static_cast<uint32_t>(WB) * kMul);
               const int kb = is_hb ? j * NHB + grp : 3 * NHB + (grp - NHB);      // weight k-blocks are packed tap-major
-              if constexpr (kPair) {
-                if (hint_w) ptx::tma_load_2d_pair_hint(sW + s * WB, mW1, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * KC, half * 256 + nrow, pol_last);
-                else ptx::tma_load_2d_pair(sW + s * WB, mW1, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * KC, half * 256 + nrow);
-              } else ptx::tma_load_2d(sW + s * WB, mW1, &w_full[s], kb * KC, half * 256);
+              if constexpr (kPair) ptx::tma_load_2d_pair(sW + s * WB, mW1, ptx::mapa_u32(ptx::smem_u32(&w_full[s]), 0), kb * KC, half * 256 + nrow);
+              else ptx::tma_load_2d(sW + s * WB, mW1, &w_full[s], kb * KC, half * 256);
             }
           }
         }
@@ -410,8 +385,6 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
       if constexpr (kPair) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(bar), 0)); else ptx::mbar_arrive(bar);
     };
     int it = 0, cur_l = -1;
-    const uint64_t pol_last = ptx::l2_policy_evict_last(), pol_first = ptx::l2_policy_evict_first();
-    const bool hint_st = (p.l2_hint & kL2HintHStore) != 0, hint_ld = (p.l2_hint & kL2HintHLastRead) != 0;
     for (int g = pair0; g < total_items; g += npairs, ++it) {
       const int l = g / total_units, unit = g - l * total_units;
       if (l != cur_l) {
@@ -549,9 +522,7 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
         auto load_h = [&](int c, float4 (&hx)[8]) {                 // this lane's part of residual-stream chunk c
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            hx[i] = (tq + 4 * i < p.T) ? (hint_ld ? ld_cg_f4_l2hint(hq + static_cast<size_t>(4 * i) * kFC + c * 32, pol_first)
-                                                  : ld_cg_f4(hq + static_cast<size_t>(4 * i) * kFC + c * 32))
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+            hx[i] = (tq + 4 * i < p.T) ? ld_cg_f4(hq + static_cast<size_t>(4 * i) * kFC + c * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         auto stage = [&](int c, float* stg) {                       // accumulator chunk c: TMEM -> registers -> scratch
           uint32_t rr[32];
@@ -574,13 +545,8 @@ denoiser_stream_kernel(const __grid_constant__ CUtensorMap mapHb0, const __grid_
               v[1] = (hx[i].y + (a.y + bv.y)) * 0.70710678118654752440f;
               v[2] = (hx[i].z + (a.z + bv.z)) * 0.70710678118654752440f;
               v[3] = (hx[i].w + (a.w + bv.w)) * 0.70710678118654752440f;
-              if (hint_st) {
-                ptx::st_f4_l2hint(hoq + static_cast<size_t>(4 * i) * kFC + c * 32, v[0], v[1], v[2], v[3], pol_last);
-                if constexpr (!kTF32) ptx::st_b32x2_l2hint(hbq + static_cast<size_t>(4 * i) * kFC + c * 32, pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pol_last);
-              } else {
-                st_vec<4>(hoq + static_cast<size_t>(4 * i) * kFC + c * 32, v);
-                if constexpr (!kTF32) st_vec<4>(hbq + static_cast<size_t>(4 * i) * kFC + c * 32, v);
-              }
+              st_vec<4>(hoq + static_cast<size_t>(4 * i) * kFC + c * 32, v);
+              if constexpr (!kTF32) st_vec<4>(hbq + static_cast<size_t>(4 * i) * kFC + c * 32, v);
             }
           }
           __syncwarp();                                             // all lanes have read the scratch

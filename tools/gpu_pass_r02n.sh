@@ -1,7 +1,8 @@
 #!/bin/bash
 # Round 2, pass N: A/B of the streamed kernel's L2 eviction priorities (FSE_STREAM_L2HINT) and of its programmatic dependent launch
 # with alternating publication counters (FSE_STREAM_PDL): timing by CUDA events over graph replays, DRAM bytes by ncu, results must
-# be bit-identical; then the GPU suite with both switched on.
+# be bit-identical; then the GPU suite with both switched on.  (As run; the L2-hint switch and its sweep tool were removed afterwards —
+# no effect on time or DRAM bytes, profiles/r02n_* — and the dependent launch became the default; tools/sample_ab.py is the A/B tool now.)
 mkdir -p gpurun_out
 L=gpurun_out/r02n_l2hint_pdl.log
 : > $L
