@@ -100,6 +100,31 @@ def test_stream_kernel_is_deterministic_at_bench_shape(lib_built):
         assert torch.equal(first, again), f"run {i} differs"
 
 
+@pytest.mark.parametrize("mode", ["tc_bf16", "tc_tf32"])
+def test_stream_dependent_launch_equals_plain_launch(lib_built, mode, monkeypatch):
+    """The streamed kernel as a programmatic dependent launch with alternating publication counters (the default) against the
+    memset + plain launch it replaced (FSE_STREAM_PDL=0), eagerly and as a replayed graph, also with the batch walked in chunks
+    (FSE_BATCH_CHUNK: several streamed launches per evaluation, odd tile counts): schedules differ, bits must not."""
+    _need_gpu()
+    from speech_editing_toolkit_b200 import synth
+    S, B, T = 6, 5, 700                                   # 6 tiles per item, 30 tiles: 15 CTA pairs' worth of units, ragged last tile
+    cond, noise = cu(synth.synthetic_cond(77, B, T)), cu(synth.synthetic_noise(77, S, B, T))
+    outs = {}
+    for pdl, chunk in (("0", "0"), ("1", "0"), ("1", "2"), ("0", "2")):
+        monkeypatch.setenv("FSE_STREAM_PDL", pdl)
+        monkeypatch.setenv("FSE_BATCH_CHUNK", chunk)
+        d = _denoiser(mode, S)
+        runs = [d.sample(cond, noise).clone() for _ in range(4)]     # eager, capture, two replays
+        for i, r in enumerate(runs[1:]):
+            assert torch.equal(runs[0], r), f"pdl={pdl} chunk={chunk}: call {i + 1} differs from the eager call"
+        outs[(pdl, chunk)] = runs[0]
+        del d
+    ref = outs[("0", "0")]
+    for k, v in outs.items():
+        assert torch.equal(ref, v), f"FSE_STREAM_PDL={k[0]} FSE_BATCH_CHUNK={k[1]} changes the result"
+    print(f"[margin] {mode}: dependent launch / plain launch / chunked batch: bit-identical over {len(outs)} variants x 4 calls")
+
+
 @pytest.mark.parametrize("mode", ["simt_f32", "tc_bf16", "tc_tf32"])
 def test_hifigan_t1024_vs_reference_fixture(lib_built, mode):
     """hifigan.py:126-142 at T=1024 (stage-4 tensors of 262 144 rows: the multi-sub-tile / many-wave regime)."""
