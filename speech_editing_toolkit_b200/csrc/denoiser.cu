@@ -318,7 +318,6 @@ int run_time_tables(fse_denoiser* h, const Workspace& w, int nT, cudaStream_t st
 int reset_stream_flags(fse_denoiser* h, const Workspace& w, cudaStream_t st) {
   if (!h->fused || !h->stream_pdl || w.done_n == 0) return FSE_OK;
   FSE_CUDA(cudaMemsetAsync(w.done, 0, 2 * w.done_n * sizeof(unsigned int), st));
-  ++h->launches;
   h->flag_phase = 0;
   return FSE_OK;
 }
@@ -359,8 +358,8 @@ int run_fused_layers(fse_denoiser* h, const Workspace& w, int Bc, int b0, int T,
   } else {
     if (stream) FSE_CUDA(cudaMemsetAsync(w.done, 0, static_cast<size_t>(L) * tiles * sizeof(unsigned int), st));
     else FSE_CUDA(cudaMemsetAsync(h->d_grid_bar, 0, sizeof(unsigned int), st));
-    ++h->launches;
   }
+  ++h->launches;                                         // the kernel below (memsets are not counted)
   h->prof.begin(1, st);
   if (h->fused_pair) {
     int grid = (tiles + 1) / 2 * 2;                      // whole clusters of 2
