@@ -15,8 +15,12 @@ librosa's published algorithm:
         of the zero-padded signal, n_frames = 1 + len(wav) // hop, rfft per frame (complex64 in librosa for float32 input)
   filters.mel: Slaney mel scale (htk=False: linear below 1 kHz at 200/3 Hz per mel, log above with step ln(6.4)/27), n_mels + 2
         band edges, triangular weights on the rfft bin centres, Slaney area normalisation 2 / (f[i+2] - f[i]), float32
-Secondary pins used by tests/test_mel_frontend_oracle.py: torch.stft (an independent implementation of the same transform) and
-the filterbank's invariants (band edges, unit-area triangles, zero outside [fmin, fmax]).
+Secondary pins used by tests/test_mel_frontend_oracle.py: torch.stft (an independent implementation of the same transform), the
+filterbank's invariants (band edges, unit-area triangles, zero outside [fmin, fmax]), the fixture tests/golden/mel_frontend.npz
+made without this file (scipy.signal.stft + a Slaney filterbank checked against the constants in librosa's documentation), and
+two third-party implementations that are documented and tested upstream to reproduce librosa — torchaudio's
+melscale_fbanks / MelSpectrogram with norm="slaney", mel_scale="slaney" (filterbank equal to 7e-8, whole wav -> log10-mel pipeline to
+2e-6) and transformers.audio_utils.mel_filter_bank (equal to 1e-9).  librosa's own outputs remain unavailable here.
 """
 from __future__ import annotations
 

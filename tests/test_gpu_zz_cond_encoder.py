@@ -276,3 +276,13 @@ def test_mel_frontend_vs_oracle(lib_built):
     lin_g, lin_w = 10 ** got.astype(np.float64), 10 ** g["mel"].astype(np.float64)
     assert (np.abs(lin_g - lin_w) <= 1e-5 * lin_w.max(axis=1, keepdims=True) + 1e-7).all()
     print(f"[margin] mel front-end vs independent fixture: max |log10 diff| {np.abs(got - g['mel']).max():.3e}")
+    # ... and torchaudio's librosa-compatible MelSpectrogram (slaney / slaney, centre zero padding) evaluated on the same samples
+    try:
+        import torchaudio
+    except ImportError:
+        return
+    ms = torchaudio.transforms.MelSpectrogram(sample_rate=22050, n_fft=1024, win_length=1024, hop_length=256, f_min=55.0, f_max=7600.0,
+                                              n_mels=80, power=1.0, norm="slaney", mel_scale="slaney", center=True, pad_mode="constant")
+    lin_t = ms(torch.from_numpy(g["wav"])).T.numpy().astype(np.float64)
+    assert (np.abs(lin_g - np.maximum(lin_t, 1e-6)) <= 1e-5 * lin_t.max(axis=1, keepdims=True) + 1e-7).all()
+    print(f"[margin] mel front-end vs torchaudio MelSpectrogram: max |log10 diff| {np.abs(got - np.log10(np.maximum(lin_t, 1e-6))).max():.3e}")

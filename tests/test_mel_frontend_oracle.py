@@ -90,3 +90,30 @@ def test_oracle_against_the_independent_fixture_and_librosa_published_constants(
     assert abs(float(MO.hz_to_mel(60.0)) - 0.9) < 1e-12          # librosa docs: hz_to_mel(60) -> 0.9
     assert np.allclose(MO.hz_to_mel(np.array([110.0, 220.0, 440.0])), [1.65, 3.3, 6.6])
     assert np.allclose(MO.mel_to_hz(np.array([1.0, 2, 3, 4, 5])), [66.667, 133.333, 200.0, 266.667, 333.333], atol=1e-3)
+
+
+def test_oracle_against_third_party_librosa_compatible_implementations():
+    """Two independently written implementations that are documented (and tested upstream) to reproduce librosa: torchaudio's
+    `melscale_fbanks(norm="slaney", mel_scale="slaney")` / `MelSpectrogram(power=1, center=True, pad_mode="constant")` and
+    transformers' `audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney")` (the Whisper feature extractor's filterbank).
+    librosa itself is absent from this image, so these are the closest available stand-ins for `librosa.filters.mel` and
+    `librosa.stft` as utils/audio/__init__.py:34-81 calls them (sr 22050, n_fft 1024, hop 256, 80 mels, 55-7600 Hz, eps 1e-6)."""
+    import os
+    import pytest
+    fb = MO.mel_basis()
+    ta = pytest.importorskip("torchaudio")
+    ta_fb = ta.functional.melscale_fbanks(513, 55.0, 7600.0, 80, 22050, norm="slaney", mel_scale="slaney").T.numpy()
+    assert np.abs(fb - ta_fb).max() < 5e-7 * fb.max() * 40                     # fp32 filterbank of torchaudio: ~7e-8 absolute
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mel_frontend.npz"))
+    ms = ta.transforms.MelSpectrogram(sample_rate=22050, n_fft=1024, win_length=1024, hop_length=256, f_min=55.0, f_max=7600.0, n_mels=80,
+                                      power=1.0, norm="slaney", mel_scale="slaney", center=True, pad_mode="constant")
+    rs = np.random.RandomState(5)
+    for wav in (g["wav"], (rs.standard_normal(256 * 11 + 13) * 0.3).astype(np.float32)):
+        want = torch.log10(torch.clamp(ms(torch.from_numpy(wav)), min=1e-6)).T.numpy()
+        got = MO.wav2mel(wav)
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() < 2e-5
+    au = pytest.importorskip("transformers.audio_utils")
+    hf_fb = au.mel_filter_bank(num_frequency_bins=513, num_mel_filters=80, min_frequency=55.0, max_frequency=7600.0, sampling_rate=22050,
+                               norm="slaney", mel_scale="slaney").T
+    assert np.abs(fb - hf_fb).max() < 1e-8
