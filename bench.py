@@ -116,6 +116,38 @@ def tensor_peak(mode, pk):
     return pk["bf16_sustained"], pk["src"] + ", sustained bf16"
 
 
+def library_gemm_check(dev, seconds=1.5):
+    """Informational cross-check of the roofline denominators (not used for `frac`): cuBLAS 8192^3 GEMMs launched back to back for
+    ~`seconds` each, bf16 and fp32-with-TF32 — the library's own sustained rate on THIS box under THIS power cap, next to the
+    driver-measured bf16 figure in MEASURED_PEAKS.json and the tf32 = bf16 / 2 rule `peak` is derived with."""
+    import torch
+    out = {}
+    n = 8192
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        for name, dt, tf32 in (("bf16", torch.bfloat16, False), ("tf32", torch.float32, True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            a = torch.randn(n, n, device=dev, dtype=dt)
+            b = torch.randn(n, n, device=dev, dtype=dt)
+            c = torch.empty(n, n, device=dev, dtype=dt)
+            for _ in range(5):
+                torch.matmul(a, b, out=c)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b, out=c); e1.record(); torch.cuda.synchronize()
+            reps = max(10, int(seconds * 1e3 / max(e0.elapsed_time(e1), 1e-3)))
+            e0.record()
+            for _ in range(reps):
+                torch.matmul(a, b, out=c)
+            e1.record(); torch.cuda.synchronize()
+            out[f"cublas_{name}_sustained_tflops"] = 2.0 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
+            del a, b, c
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    out["how"] = f"torch.matmul {n}^3 back to back for ~{seconds} s per dtype on this box, after the timed regions"
+    return out
+
+
 def stream_traffic(mode, B, T):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the streamed residual-layer kernel at the bench shape, read
     from the committed ncu artefact profiles/stream_kernel_traffic.json (written by tools/ncu_traffic.py from an `ncu --set full`
@@ -587,6 +619,11 @@ def run_b200(args):
         return
     pk = peaks()
     roofline = roofline_record(args.mode, prof_d, B, T, pk) if prof_d else None
+    if roofline is not None and world == 1:
+        try:
+            roofline["library_check"] = library_gemm_check(dev)
+        except Exception as e:      # informational only
+            roofline["library_check"] = {"error": f"{type(e).__name__}: {e}"}
     breakdown = {}
     if prof_d:
         breakdown["denoiser_ms_per_step"] = {k: v[0] / args.steps for k, v in prof_d.items()}
