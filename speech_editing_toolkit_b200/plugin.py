@@ -267,6 +267,53 @@ class SpeechDenoiserTaskB200:
         return log
 
     @torch.no_grad()
+    def validation_step(self, sample: dict, batch_idx: int = 0):
+        """SpeechDenoiserTask.validation_step (tasks/speech_editing/spec_denoiser.py:64-88): the losses of the training-branch forward
+        (`run_model(infer=False)`: q_sample at a random t, one denoiser evaluation, masked mel losses) as python scalars with their sum
+        and `nsamples`; for the first `num_valid_plots` batches also a full sampling run composited with the reference mel and, when a
+        vocoder was built (validation_start), its waveform for the first item — the tensors the reference hands to its tensorboard
+        logger (`plot_wav` / `plot_mel`, which are out of scope) are returned under `mel_out` / `wav_out` instead."""
+        losses, _ = self.run_model(sample, infer=False)
+        out = {"losses": {k: float(v) for k, v in losses.items()}}
+        out["total_loss"] = float(sum(out["losses"].values()))
+        out["nsamples"] = int(sample.get("nsamples", sample["txt_tokens"].shape[0]))
+        if batch_idx < int(self.hparams.get("num_valid_plots", 0) or 0):
+            model_out = self.run_model(sample, infer=True)
+            out["mel_out"] = model_out["mel_out"]
+            if self.vocoder is not None:
+                out["wav_out"] = self.vocoder(model_out["mel_out"][:1])
+        return out
+
+    def validation_start(self):
+        """SpeechBaseTask.validation_start (tasks/tts/speech_base.py:194-195)."""
+        return self.build_vocoder()
+
+    def validation_end(self, outputs):
+        """BaseTask.validation_end (utils/commons/base_task.py:154-185): nsamples-weighted means of every loss and of the total,
+        rounded to four decimals, as {'tb_log': {'val/<name>': mean}, 'val_loss': mean total}; empty outputs are skipped."""
+        sums, counts = {"total_loss": 0.0}, {"total_loss": 0}
+        for output in outputs:
+            if not output:
+                continue
+            if isinstance(output, dict):
+                if "losses" not in output:
+                    raise AssertionError('Key "losses" should exist in validation output.')
+                n = output.get("nsamples", 1)
+                losses = {k: float(v) for k, v in output["losses"].items()}
+                total = float(output.get("total_loss", sum(losses.values())))
+            else:
+                if len(output) != 2:
+                    raise AssertionError("Validation output should only consist of two elements: (total_loss, losses)")
+                n, (total, losses) = 1, output
+                total, losses = float(total), {k: float(v) for k, v in losses.items()}
+            for k, v in list(losses.items()) + [("total_loss", total)]:
+                sums[k] = sums.get(k, 0.0) + v * n
+                counts[k] = counts.get(k, 0) + n
+        means = {k: round(sums[k] / counts[k], 4) if counts[k] else 0.0 for k in sums}
+        print(f"| Validation results: {means}")
+        return {"tb_log": {f"val/{k}": v for k, v in means.items()}, "val_loss": means["total_loss"]}
+
+    @torch.no_grad()
     def test_step(self, sample: dict, batch_idx: int = 0):
         """speech_editing_base.py:151-192 minus file output: sample -> composite -> vocoder."""
         dev = torch.device("cuda")

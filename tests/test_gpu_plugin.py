@@ -175,3 +175,51 @@ def test_task_start_runs_the_inference_and_the_training_leg_from_the_reference_y
         os.chdir(cwd)
     assert len(log) == 4 and all(np.isfinite(list(e.values())).all() for e in log) and set(log[0]) == {"l1_coarse", "ssim_coarse"}
     print("[margin] task start(): inference leg ok, training leg losses", log[0], "->", log[-1])
+
+
+def test_task_validation_step_on_a_synthetic_batch(lib_built):
+    """SpeechDenoiserTaskB200.validation_start / validation_step / validation_end (tasks/speech_editing/spec_denoiser.py:64-88,
+    tasks/tts/speech_base.py:194-211, utils/commons/base_task.py:154-185) over a seeded synthetic editing batch with the reference's own
+    yaml: finite scalar losses of the training-branch forward, the sampled + composited mel for the first num_valid_plots batches
+    (unedited frames = the input mel, bit for bit), the vocoder's waveform of its first item."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import os
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("no reference tree (oracle/_ref) on this box")
+    cfg = os.path.join(refshim.REF_ROOT, "egs", "spec_denoiser.yaml")
+    from speech_editing_toolkit_b200 import plugin, synth
+    from speech_editing_toolkit_b200.hparams import set_hparams
+    cwd = os.getcwd()
+    os.chdir(refshim.REF_ROOT)
+    try:
+        set_hparams(cfg, hparams_str="task_cls=speech_editing_toolkit_b200.plugin.SpeechDenoiserTaskB200,timesteps=4,max_sentences=2,b200_frames=128,"
+                                     "residual_layers=4,b200_vocab=80,num_valid_plots=1", print_hparams=False)
+    finally:
+        os.chdir(cwd)
+    task = plugin.SpeechDenoiserTaskB200()
+    hp = task.hparams
+    task.build_model()
+    t_ = lambda sd: {k: torch.from_numpy(v) for k, v in sd.items()}
+    task.model.denoise_fn.load_state_dict(t_(synth.denoiser_state_dict(1234, hp["audio_num_mel_bins"], hp["hidden_size"], hp["residual_channels"], hp["residual_layers"])))
+    task.model.fs.load_state_dict(t_(synth.fastspeech_state_dict(1234, 80)), strict=False)
+    task.model.mel_encoder.load_state_dict(t_(synth.mel_encoder_state_dict(1234)))
+    task.validation_start()
+    B, T = 2, 128
+    b = synth.synthetic_edit_batch(1234, B, T, hp["audio_num_mel_bins"], vocab=80)
+    sample = {k: torch.from_numpy(v).cuda() for k, v in b.items()}
+    sample["mels"] = sample.pop("ref_mels")
+    sample["nsamples"] = B
+    torch.manual_seed(0)
+    o0, o1 = task.validation_step(sample, 0), task.validation_step(sample, 1)
+    for o in (o0, o1):
+        assert set(o["losses"]) == {"l1_coarse", "ssim_coarse"} and np.isfinite(list(o["losses"].values())).all()
+        assert abs(o["total_loss"] - sum(o["losses"].values())) < 1e-6 and o["nsamples"] == B
+    assert "mel_out" not in o1 and tuple(o0["mel_out"].shape) == (B, T, 80) and tuple(o0["wav_out"].shape) == (1, T * 256)
+    assert bool(torch.isfinite(o0["mel_out"]).all()) and bool(torch.isfinite(o0["wav_out"]).all())
+    keep = sample["time_mel_masks"] == 0
+    assert torch.equal(o0["mel_out"][keep], sample["mels"][keep])
+    end = task.validation_end([o0, o1])
+    assert np.isfinite(end["val_loss"]) and set(end["tb_log"]) == {"val/total_loss", "val/l1_coarse", "val/ssim_coarse"}
+    print("[margin] task validation_step: losses", o0["losses"], o1["losses"], "val_loss", end["val_loss"])

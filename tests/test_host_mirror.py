@@ -238,6 +238,41 @@ def test_campnet_task_run_model_composites_like_the_reference():
     assert torch.equal(out["mel_out"][:, 2:4], fine[:, 2:4]) and torch.equal(out["mel_out"][:, :2], mels[:, :2])
 
 
+def test_task_validation_step_and_end_host_logic():
+    """SpeechDenoiserTaskB200.validation_step / validation_end against the reference's contract (tasks/speech_editing/spec_denoiser.py:64-88,
+    utils/commons/base_task.py:154-185) with a stand-in run_model: scalar losses + total + nsamples, the sampling run only for the first
+    num_valid_plots batches, nsamples-weighted means rounded to four decimals."""
+    from speech_editing_toolkit_b200 import plugin
+    task = plugin.SpeechDenoiserTaskB200()
+    task.hparams = {"num_valid_plots": 1}
+    calls = []
+
+    def fake_run_model(sample, infer=False, *a, **kw):
+        calls.append(infer)
+        out = {"mel_out": torch.full((2, 4, 80), float(sample["k"]))}
+        if infer:
+            return out
+        return {"l1_coarse": torch.tensor(0.25 * sample["k"]), "ssim_coarse": torch.tensor(0.125)}, out
+
+    task.run_model = fake_run_model
+    s1 = {"k": 1, "txt_tokens": torch.ones(2, 3, dtype=torch.long), "nsamples": 2}
+    s2 = {"k": 3, "txt_tokens": torch.ones(6, 3, dtype=torch.long)}                      # nsamples falls back to the batch size
+    o1, o2 = task.validation_step(s1, 0), task.validation_step(s2, 1)
+    assert calls == [False, True, False]                                                 # batch 0 also sampled, batch 1 did not
+    assert o1["losses"] == {"l1_coarse": 0.25, "ssim_coarse": 0.125} and o1["total_loss"] == 0.375 and o1["nsamples"] == 2
+    assert "mel_out" in o1 and "wav_out" not in o1 and "mel_out" not in o2 and o2["nsamples"] == 6
+    end = task.validation_end([o1, {}, o2])
+    want_l1 = round((0.25 * 2 + 0.75 * 6) / 8, 4)
+    assert end["tb_log"] == {"val/total_loss": round(want_l1 + 0.125, 4), "val/l1_coarse": want_l1, "val/ssim_coarse": 0.125}
+    assert end["val_loss"] == end["tb_log"]["val/total_loss"]
+    # the (total_loss, losses) tuple form of base_task.py:168-172 counts as one sample
+    end2 = task.validation_end([(torch.tensor(1.0), {"a": torch.tensor(1.0)}), (3.0, {"a": 3.0})])
+    assert end2["val_loss"] == 2.0 and end2["tb_log"]["val/a"] == 2.0
+    import pytest
+    with pytest.raises(AssertionError):
+        task.validation_end([{"total_loss": 1.0}])
+
+
 def test_checkpoint_save_resume_roundtrip_in_the_reference_layout(tmp_path):
     """save_ckpt / resume (the trainer's dump_checkpoint / restore_weights / restore_opt_state, utils/commons/trainer.py:372-470): file
     name, keys, atomic write, pruning to num_ckpt_keep, optimizer state; with the reference present its own load_ckpt reads the file."""
